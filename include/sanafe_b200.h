@@ -1,0 +1,335 @@
+/* sanafe_b200.h — C ABI of the B200-native SANA-FE time-step engine.
+ *
+ * Drop-in boundary for ONE path of the reference: SpikingChip::load / sim /
+ * step / sim_hw_timestep and everything they call (reference src/chip.cpp,
+ * pipeline.*, models.cpp, schedule.cpp "simple"). Plain pointers and sizes
+ * only; no C++ or torch types cross this boundary; every function returns an
+ * int status (0 = ok) or a handle/NULL and leaves a message for sfe_last_error().
+ * No exception crosses the ABI.
+ *
+ * Two levels:
+ *   description level  sfe_arch_* / sfe_net_* / sfe_chip_*   mirrors the reference's
+ *                      Architecture / SpikingNetwork / SpikingChip surface
+ *   table level        sfe_tables + sfe_engine_*             the lowered SoA/CSR form the
+ *                      device kernels consume (also what oracle/sfe_oracle.c consumes)
+ */
+#ifndef SANAFE_B200_H_
+#define SANAFE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sfe_synth.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFE_ABI_VERSION 1
+
+/* ---- enums (values follow the reference where it has them) -------------- */
+/* src/arch.hpp:41-49 BufferPosition */
+enum
+{
+    SFE_BUF_BEFORE_DENDRITE = 0,
+    SFE_BUF_INSIDE_DENDRITE = 1,
+    SFE_BUF_BEFORE_SOMA = 2,
+    SFE_BUF_INSIDE_SOMA = 3,
+    SFE_BUF_BEFORE_AXON_OUT = 4
+};
+/* src/arch.hpp:61-68 NeuronResetModes */
+enum
+{
+    SFE_RESET_NONE = 0,
+    SFE_RESET_SOFT = 1,
+    SFE_RESET_HARD = 2,
+    SFE_RESET_SATURATE = 3
+};
+/* src/mapped.hpp:22-28 NeuronStatus */
+enum
+{
+    SFE_STATUS_UNSET = 0,
+    SFE_STATUS_IDLE = 1,
+    SFE_STATUS_UPDATED = 2,
+    SFE_STATUS_FIRED = 3
+};
+/* src/chip.hpp:40-45 TimingModel */
+enum
+{
+    SFE_TIMING_SIMPLE = 0,
+    SFE_TIMING_DETAILED = 1,
+    SFE_TIMING_CYCLE = 2
+};
+/* soma models: src/models.cpp:933-967 + plugins/hodgkin_huxley.cpp */
+enum
+{
+    SFE_SOMA_LIF = 0,       /* "leaky_integrate_fire"   src/models.cpp:497-567 */
+    SFE_SOMA_TRUENORTH = 1, /* "truenorth"              src/models.cpp:799-830 */
+    SFE_SOMA_INPUT = 2,     /* "input"                  src/models.cpp:863-903 */
+    SFE_SOMA_HH = 3         /* "hodgkin_huxley" plugin  plugins/hodgkin_huxley.cpp:116-170 */
+};
+/* dendrite models */
+enum
+{
+    SFE_DEND_ACCUMULATOR = 0,      /* src/models.cpp:71-94  */
+    SFE_DEND_ACCUMULATOR_DELAY = 1 /* src/models.cpp:96-131 */
+};
+/* how one core's message phase accumulates synaptic charge */
+enum
+{
+    SFE_ACC_PACKED32 = 0, /* exact fixed point: 20-bit sum + 12-bit count in one u32 smem atomic */
+    SFE_ACC_DUAL32 = 1,   /* exact fixed point: int32 sum + u32 count, two smem atomics */
+    SFE_ACC_ORDERED = 2   /* sequential fp64 adds in message arrival order (any weights) */
+};
+/* sfe_soma_class.flags */
+#define SFE_SOMA_FORCE_UPDATE 1u
+#define SFE_SOMA_LEAK_TOWARDS_ZERO 2u
+#define SFE_SOMA_LOG_U 4u
+
+/* ---- lowered tables ------------------------------------------------------ */
+typedef struct sfe_tile_desc
+{
+    uint32_t x, y; /* x = id / noc_height, y = id % noc_height  src/arch.cpp:78-104 */
+    double energy_east, energy_west, energy_south, energy_north;
+    double latency_east, latency_west, latency_south, latency_north;
+} sfe_tile_desc;
+
+typedef struct sfe_core_desc
+{
+    uint32_t id;          /* global core id (creation order) */
+    uint32_t tile;
+    uint32_t offset;      /* offset within tile */
+    uint32_t buffer_pos;  /* SFE_BUF_* */
+    uint32_t neuron_begin, neuron_count;   /* neurons in in-core mapped order */
+    uint32_t axon_in_begin, axon_in_count; /* axons-in in creation (= arrival) order */
+    uint64_t syn_begin;   /* first synapse of this core in the synapse arrays */
+    uint64_t syn_count;
+    uint32_t acc_mode;    /* SFE_ACC_* */
+    int32_t weight_shift; /* exact modes: every weight is k * 2^-weight_shift */
+    uint32_t ring;        /* dendrite ring slots = max synaptic delay + 1 */
+    uint32_t dend_in_msg; /* 1: dendrite unit is in the message pipeline (buffer_pos >= 1) */
+    /* axon units with the reference's quirks folded in:
+     * latency: axon_in_hw[0] / axon_out_hw[0]; energy: only when the core has
+     * exactly one such unit (the reference counts the LAST unit's energy while
+     * crediting activity to unit 0). */
+    double energy_axon_in, latency_axon_in;
+    double energy_axon_out, latency_axon_out;
+} sfe_core_desc;
+
+typedef struct sfe_soma_class
+{
+    uint32_t model;         /* SFE_SOMA_* */
+    uint32_t reset_mode;    /* SFE_RESET_* */
+    uint32_t reverse_reset_mode;
+    int32_t refractory_delay;
+    uint32_t flags;         /* SFE_SOMA_* flags */
+    uint32_t random_mask;   /* truenorth only; must be 0 (std::rand() is not reproducible) */
+    uint32_t dend_model;    /* SFE_DEND_* of the neuron's dendrite unit */
+    uint32_t dend_in_neuron;/* 1: dendrite unit is in the neuron pipeline (buffer_pos <= 1) */
+    double threshold, reverse_threshold, reset, reverse_reset;
+    double leak;            /* LIF leak_decay | truenorth leak */
+    double input_decay;
+    /* default costs of the soma unit (src/pipeline.hpp:631-714) */
+    double energy_access, energy_update, energy_spike_out;
+    double latency_access, latency_update, latency_spike_out;
+    /* default costs of the dendrite unit when it runs in the neuron pipeline */
+    double dend_energy_update, dend_latency_update;
+} sfe_soma_class;
+
+/* per-event default costs of one (synapse unit, dendrite unit) pairing; an axon
+ * whose synapses mix units gets a class with per_message = 1 holding totals */
+typedef struct sfe_cost_class
+{
+    double syn_energy, syn_latency; /* src/pipeline.hpp:511-572 */
+    double den_energy, den_latency; /* src/pipeline.hpp:574-629 (0 if dendrite not in message pipeline) */
+    uint32_t per_message;
+    uint32_t pad;
+} sfe_cost_class;
+
+/* one axon-in = one (pre-neuron, destination core) pair = one message per spike */
+typedef struct sfe_axon_in
+{
+    uint32_t syn_off;    /* relative to core.syn_begin */
+    uint32_t syn_count;  /* = Message.spikes  src/message.cpp:52 */
+    uint32_t hop;        /* dx | dy<<12 | east<<24 | north<<25   src/chip.cpp:1127-1169 */
+    uint32_t cost_class;
+} sfe_axon_in;
+#define SFE_HOP_DX(h) ((h) & 0xfffu)
+#define SFE_HOP_DY(h) (((h) >> 12) & 0xfffu)
+#define SFE_HOP_EAST(h) (((h) >> 24) & 1u)
+#define SFE_HOP_NORTH(h) (((h) >> 25) & 1u)
+
+/* synapse meta word: post-neuron offset within core | delay << 16 */
+#define SFE_SYN_POST(m) ((m) & 0xffffu)
+#define SFE_SYN_DELAY(m) (((m) >> 16) & 0x7u)
+
+typedef struct sfe_input_desc /* "input" soma: state is per hardware UNIT (src/models.cpp:832-903) */
+{
+    uint32_t spikes_off, spikes_len; /* into sfe_tables.input_spikes (1 byte per step) */
+    uint32_t share_count, share_rank;/* neurons sharing the unit, this neuron's rank among them */
+    double rate;
+    double poisson;                  /* must be 0 (mt19937 stream not reproduced yet) */
+} sfe_input_desc;
+
+typedef struct sfe_hh_init /* Hodgkin-Huxley plugin initial state, one neuron per unit */
+{
+    double m, n, h, current;
+} sfe_hh_init;
+
+typedef struct sfe_tables
+{
+    uint32_t abi_version;
+    uint32_t noc_width, noc_height, noc_buffer_size, max_cores_per_tile;
+    uint32_t n_tiles, n_cores, n_neurons, n_axons_in, n_soma_classes, n_cost_classes;
+    uint32_t n_inputs, n_hh, n_probes;
+    uint32_t mapped_tiles, mapped_cores;
+    uint64_t n_synapses, n_axons_out;
+    double sync_delay; /* LookupTable::get(mapped_tiles)  src/chip.cpp:562-574, src/utils.hpp:19-45 */
+
+    const sfe_tile_desc *tiles;
+    const sfe_core_desc *cores;
+    const sfe_soma_class *soma_classes;
+    const sfe_cost_class *cost_classes;
+
+    /* neurons, indexed by device index (cores in id order, in-core mapped order) */
+    const uint32_t *neuron_class;
+    const uint32_t *neuron_aux;      /* index into inputs / hh (by model), else 0 */
+    const double *neuron_bias;
+    const double *neuron_potential0; /* initial potential (LIF attribute "potential") */
+    const uint32_t *axon_out_begin;  /* n_neurons + 1 */
+    const uint32_t *axon_out_target; /* n_axons_out: global axon-in ids, in the order messages are sent */
+    const sfe_input_desc *inputs;
+    const uint8_t *input_spikes;
+    uint64_t n_input_spikes;
+    const sfe_hh_init *hh;
+    const uint32_t *probes;          /* device indices whose potential is traced each step */
+
+    /* axons-in, grouped by destination core in arrival order */
+    const sfe_axon_in *axons_in;
+    const uint32_t *axon_src;        /* source neuron (device index) of each axon-in */
+
+    /* synapses, grouped by destination core, axon, creation order. NULL when the
+     * tables describe a synthetic network that is generated on the device. */
+    const double *syn_weight;
+    const uint32_t *syn_meta;
+    const sfe_synth_spec *synth;     /* non-NULL: generate synapses from this spec */
+} sfe_tables;
+
+/* one record per simulated timestep (src/timestep.hpp:21-42) */
+typedef struct sfe_step_record
+{
+    int64_t neurons_fired, neurons_updated, packets_sent, total_hops, spike_count;
+    double sim_time, synapse_energy, dendrite_energy, soma_energy, network_energy, total_energy;
+} sfe_step_record;
+
+/* src/chip.hpp:215-233 RunData */
+typedef struct sfe_run_data
+{
+    int64_t timestep_start, timesteps_executed;
+    int64_t spikes, packets_sent, neurons_updated, neurons_fired;
+    double total_energy, synapse_energy, dendrite_energy, soma_energy, network_energy;
+    double sim_time;
+    double wall_time;
+} sfe_run_data;
+
+/* What sim() should hand back besides the totals. Any pointer may be NULL.
+ * Buffers are caller-owned HOST memory. */
+typedef struct sfe_trace_request
+{
+    sfe_step_record *steps;   /* [timesteps] per-step records */
+    uint32_t *fired_bits;     /* [timesteps][ceil(n_neurons/32)] fired bitmask per step, device index order */
+    double *potentials;       /* [timesteps][n_probes] */
+    uint8_t *status;          /* [timesteps][n_neurons] SFE_STATUS_* (detailed-timing feed / debugging) */
+} sfe_trace_request;
+
+const char *sfe_last_error(void);
+int sfe_abi_version(void);
+/* number of CUDA devices visible; 0 when there is no GPU (never a CPU fallback) */
+int sfe_device_count(void);
+
+/* ---- table level --------------------------------------------------------- */
+typedef struct sfe_engine sfe_engine;
+
+/* Copies the tables to device `device` (synapses generated there when
+ * tables->synth is set) and zero-initialises the state. Fails when no CUDA
+ * device is present. part_rank/part_count: this engine simulates the cores
+ * whose index satisfies the contiguous core partition of rank part_rank. */
+sfe_engine *sfe_engine_create(const sfe_tables *tables, int device);
+void sfe_engine_destroy(sfe_engine *e);
+/* `stream` is a cudaStream_t (0 = the engine's own stream) */
+int sfe_engine_set_stream(sfe_engine *e, void *stream);
+/* Runs `timesteps` steps. Traces as requested. Blocks until results are on the host. */
+int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_request *req, sfe_run_data *out);
+/* Enqueue steps without any host synchronisation or read-back (benchmark / graph use). */
+int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps);
+/* Collect per-step records of the steps enqueued since the last collect. */
+int sfe_engine_collect(sfe_engine *e, sfe_run_data *out);
+/* reset(): zero model state, keep the timestep counter (src/chip.cpp:576-600) */
+int sfe_engine_reset(sfe_engine *e);
+/* Per-neuron bias patch from HOST memory (MappedNeuron.set_attributes fast path,
+ * src/pymodule.cpp:1176-1181); bias has n_neurons entries in device-index order. */
+int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n);
+int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias);
+int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n);
+int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words);
+int64_t sfe_engine_total_timesteps(const sfe_engine *e);
+/* kernel launches issued so far (for bench.py's gpu_launches) */
+int64_t sfe_engine_launch_count(const sfe_engine *e);
+/* device time (ms) of the steps enqueued between the last two timing marks */
+int sfe_engine_time_begin(sfe_engine *e);
+int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fanout);
+/* multi-GPU: raw device pointers of the fired bitmask (local slice written by the
+ * neuron phase, full mask read by the message phase) so the caller can run the
+ * NCCL all-gather between the two phases. */
+int sfe_engine_partition(sfe_engine *e, uint32_t rank, uint32_t world);
+int sfe_engine_enqueue_neuron_phase(sfe_engine *e);
+int sfe_engine_enqueue_message_phase(sfe_engine *e);
+void *sfe_engine_fired_local_ptr(sfe_engine *e, size_t *n_bytes);
+void *sfe_engine_fired_global_ptr(sfe_engine *e, size_t *n_bytes);
+size_t sfe_engine_device_bytes(const sfe_engine *e);
+
+/* ---- description level --------------------------------------------------- */
+typedef struct sfe_arch sfe_arch;
+typedef struct sfe_net sfe_net;
+typedef struct sfe_chip sfe_chip;
+
+/* load_arch / load_net  (src/arch.cpp:106-117, src/network.cpp:194-222) */
+sfe_arch *sfe_arch_load_yaml(const char *path);
+sfe_net *sfe_net_load_yaml(const char *path, sfe_arch *arch);
+/* flat JSON-lines description (oracle/yaml_to_flat.py); returns both objects */
+int sfe_load_flat(const char *path, sfe_arch **arch, sfe_net **net);
+void sfe_arch_free(sfe_arch *a);
+void sfe_net_free(sfe_net *n);
+
+/* SpikingChip(arch)  src/chip.cpp:61-104. device < 0: host-only chip (lowering
+ * and table export work; sim() fails with "no CUDA device"). */
+sfe_chip *sfe_chip_create(const sfe_arch *arch, int device);
+void sfe_chip_destroy(sfe_chip *c);
+/* SpikingChip::load  src/chip.cpp:129-138 */
+int sfe_chip_load(sfe_chip *c, const sfe_net *net);
+/* bulk extension: map the synthetic network of `spec` (sfe_synth.h) without
+ * materialising per-edge objects */
+int sfe_chip_load_synthetic(sfe_chip *c, const sfe_synth_spec *spec, int generate_on_device);
+/* SpikingChip::sim  src/chip.cpp:477-533 */
+int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, const sfe_trace_request *req,
+        sfe_run_data *out);
+int sfe_chip_reset(sfe_chip *c);       /* src/chip.cpp:576-600 */
+double sfe_chip_get_power(sfe_chip *c);/* src/chip.cpp:607-621 */
+const sfe_tables *sfe_chip_tables(const sfe_chip *c);
+sfe_engine *sfe_chip_engine(sfe_chip *c);
+/* group/offset <-> device index, trace order (lexicographic group, offset; src/chip.cpp:1616-1629) */
+int64_t sfe_chip_neuron_index(const sfe_chip *c, const char *group, uint64_t offset);
+/* MappedNeuron.set_attributes for a numeric soma attribute (bias, threshold, ...) */
+int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offset, const char *name,
+        double value);
+/* Spike rows of a fired-bit raster in the reference's trace order and format,
+ * "group.offset,timestep\n" (src/chip.cpp:1610-1630). Returns the bytes needed. */
+size_t sfe_chip_format_spikes(const sfe_chip *c, const uint32_t *fired_bits, int64_t timesteps,
+        int64_t timestep_start, char *buf, size_t cap);
+/* "group.offset\n" of every potential probe, in potentials.csv column order (src/chip.cpp:1454-1476) */
+size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SANAFE_B200_H_ */

@@ -1,0 +1,1534 @@
+// engine.cu — the per-timestep hot path of SANA-FE as hand-written sm_100a kernels.
+//
+// Replaces SpikingChip::sim_hw_timestep and everything under it (reference
+// src/chip.cpp:1053-1108): one timestep = three kernels on one stream, no host
+// synchronisation inside a run.
+//
+//   soma_kernel      neuron phase           (src/chip.cpp:624-654,710-736,802-834; models.cpp)
+//                    CTA per simulated core; SoA state; warp-ballot spike raster; fired
+//                    neurons raise the inbox bits of their axons; block reductions give
+//                    the per-core counters / energy / generation-delay sum
+//   fanout_kernel    message phase          (src/chip.cpp:656-764,1127-1169; models.cpp:29-131)
+//                    CTA per destination core; walks the inbox bitmask (= message arrival
+//                    order), streams each active axon's CSR segment (fp64 weight + u32
+//                    meta) from HBM and accumulates into shared-memory dendrite
+//                    accumulators (exact fixed point, or ordered fp64 when the weights
+//                    are not provably order-independent)
+//   finalize_kernel  energy, counters, simple timing (src/chip.cpp:1028-1051,1171-1261;
+//                    src/schedule.cpp:61-102); appends one sfe_step_record to the device log
+//
+// All arithmetic that decides a spike is IEEE fp64 without FMA contraction
+// (compiled with -fmad=false), so rasters are bit-identical to the reference.
+// There is no CPU fallback: every entry point fails when no CUDA device exists.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.hpp"
+#include "sanafe_b200.h"
+
+namespace sfe
+{
+void set_last_error(const std::string &msg);
+}
+
+namespace
+{
+// ---------------------------------------------------------------------------
+// Device-side tables
+// ---------------------------------------------------------------------------
+struct CoreDev
+{
+    uint32_t neuron_begin, neuron_count;
+    uint32_t axon_begin, axon_count;  // into axons_in[] (unpadded global ids)
+    uint32_t inbox_word_begin;        // padded: each core's inbox starts on a word
+    uint32_t fired_word_begin;        // padded: each core's raster starts on a word
+    uint32_t dend_base;               // into din*: layout [slot][k] per core
+    uint32_t ring;                    // delay-ring slots
+    uint32_t acc_mode;                // SFE_ACC_*
+    uint32_t dend_in_msg;
+    uint32_t tile;
+    uint32_t pad0;
+    unsigned long long syn_begin;
+    double scale, inv_scale;          // 2^shift, 2^-shift
+    double lat_axon_in, e_axon_in, lat_axon_out, e_axon_out;
+    double e_east, e_west, e_south, e_north; // hop energies of the core's (destination) tile
+};
+
+struct StatsN // written by soma_kernel, one per core
+{
+    uint32_t updated, fired, packets, pad;
+    double soma_e, dend_e, gen_sum;
+};
+
+struct StatsM // written by fanout_kernel, one per core
+{
+    uint32_t msgs, pad;
+    unsigned long long events, hop_e, hop_w, hop_n, hop_s;
+    double syn_e, den_e, proc;
+};
+
+struct DevTables
+{
+    const CoreDev *cores;
+    const uint32_t *soma_core_list;   // cores that have neurons
+    const uint32_t *fanout_core_list; // cores that have axons-in
+    const sfe_soma_class *classes;
+    const sfe_cost_class *costs;
+    const uint32_t *neuron_class;
+    const uint32_t *neuron_aux;
+    const uint32_t *axon_out_begin;
+    const uint32_t *axon_out_bit;     // padded inbox bit index of each axon-out
+    const sfe_input_desc *inputs;
+    const uint8_t *input_spikes;
+    const sfe_axon_in *axons_in;
+    const double *syn_w;
+    const uint32_t *syn_meta;
+    const uint32_t *probes;
+    uint32_t n_cores, n_probes, n_neurons;
+    double sync_delay;
+};
+
+struct DevState
+{
+    double *v, *u, *bias;
+    int32_t *refractory;
+    uint8_t *status;
+    uint32_t *fired_bits;  // padded per core
+    uint32_t *inbox;       // padded per core
+    uint32_t *din32;       // PACKED32: packed | DUAL32: sum
+    uint32_t *dcnt32;      // DUAL32: count | ORDERED: has flag
+    double *din64;         // ORDERED: value
+    double *hh;            // [5][n_hh]: V, m, n, h, I
+    uint32_t n_hh;
+    StatsN *stats_n;
+    StatsM *stats_m;
+    sfe_step_record *log;  // ring of step records
+    uint32_t log_cap;
+    double *probe_out;     // [n_probes] potentials of the current step
+    long long *step;       // [0] = timesteps simulated so far (T-1 during step T), [1] = log cursor
+};
+
+// ---------------------------------------------------------------------------
+// Small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t x)
+{
+    return __reduce_add_sync(0xffffffffu, x);
+}
+__device__ __forceinline__ double warp_max(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// Block-wide sum, result valid in thread 0. `scratch` holds >= 32 elements.
+template <typename T> __device__ __forceinline__ T block_sum(T x, T *scratch)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    x = warp_sum(x);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+        x = lane < nwarps ? scratch[lane] : T(0);
+        x = warp_sum(x);
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------
+// Soma models (device functors). Same operation order as the reference; no FMA.
+// ---------------------------------------------------------------------------
+// LoihiLifModel::update  src/models.cpp:497-567
+__device__ __forceinline__ int lif_update(const sfe_soma_class &c, double &v, double &u, int &refractory,
+        const double bias, const bool has_in, const double in, const long long steps_done)
+{
+    int state = SFE_STATUS_IDLE;
+    if ((fabs(v) > 0.0) || has_in || (fabs(bias) > 0.0) || (c.flags & SFE_SOMA_FORCE_UPDATE)) state = SFE_STATUS_UPDATED;
+    if (steps_done > 0)
+    {
+        u = u * c.input_decay;
+        v = v * c.leak;
+    }
+    v = static_cast<double>(__double2int_rz(v * 64.0)) / 64.0; // loihi_quantize (C int cast)
+    if (refractory <= 0)
+    {
+        v = v + bias;
+        u = u + (has_in ? in : 0.0);
+        v = v + u;
+        if (v > c.threshold)
+        {
+            if (c.reset_mode == SFE_RESET_HARD) v = c.reset;
+            else if (c.reset_mode == SFE_RESET_SOFT) v = v - c.threshold;
+            refractory = c.refractory_delay;
+            state = SFE_STATUS_FIRED;
+        }
+        if (v < c.reverse_threshold)
+        {
+            if (c.reverse_reset_mode == SFE_RESET_SOFT) v = v - c.reverse_threshold;
+            else if (c.reverse_reset_mode == SFE_RESET_HARD) v = c.reverse_reset;
+            else if (c.reverse_reset_mode == SFE_RESET_SATURATE) v = c.reverse_threshold;
+        }
+    }
+    refractory = max(0, refractory - 1);
+    return state;
+}
+
+// TrueNorthModel::update  src/models.cpp:724-830 (random_mask == 0 enforced at load)
+__device__ __forceinline__ int truenorth_update(
+        const sfe_soma_class &c, double &v, const double bias, const bool has_in, const double in)
+{
+    int state = SFE_STATUS_IDLE;
+    if ((fabs(v) > 0.0) || has_in || (fabs(bias) > 0.0) || (c.flags & SFE_SOMA_FORCE_UPDATE)) state = SFE_STATUS_UPDATED;
+    if (c.flags & SFE_SOMA_LEAK_TOWARDS_ZERO)
+    {
+        if (v > 0.0) v = v - c.leak;
+        else if (v < 0.0) v = v + c.leak;
+    }
+    else v = v + c.leak;
+    v = v + bias;
+    if (has_in) v = v + in;
+    if (v >= c.threshold)
+    {
+        if (c.reset_mode == SFE_RESET_HARD) v = c.reset;
+        else if (c.reset_mode == SFE_RESET_SOFT) v = v - c.threshold;
+        else if (c.reset_mode == SFE_RESET_SATURATE) v = c.threshold;
+        state = SFE_STATUS_FIRED;
+    }
+    else if (v <= c.reverse_threshold)
+    {
+        if (c.reverse_reset_mode == SFE_RESET_HARD) v = c.reverse_reset;
+        else if (c.reverse_reset_mode == SFE_RESET_SOFT) v = v + c.reverse_threshold;
+        else if (c.reverse_reset_mode == SFE_RESET_SATURATE) v = c.reverse_threshold;
+    }
+    return state;
+}
+
+// InputModel::update  src/models.cpp:863-903 (per-unit cursor shared by share_count neurons)
+__device__ __forceinline__ int input_update(
+        const sfe_input_desc &d, const uint8_t *spikes, const long long step_idx, const long long timestep)
+{
+    bool send = false;
+    const unsigned long long cursor = static_cast<unsigned long long>(step_idx) * d.share_count + d.share_rank;
+    if (cursor < d.spikes_len) send = spikes[d.spikes_off + cursor] != 0;
+    if ((d.rate > 0.0) && ((timestep % static_cast<long long>(1.0 / d.rate)) == 0)) send = true;
+    return send ? SFE_STATUS_FIRED : SFE_STATUS_IDLE;
+}
+
+// HodgkinHuxley::update  plugins/hodgkin_huxley.cpp:116-170 — the reference plugin
+// compiled as a device functor. State layout hh[5][n_hh] = V, m, n, h, I.
+__device__ __forceinline__ int hh_update(double *hh, const uint32_t n_hh, const uint32_t k)
+{
+    const double C_m = 10.0, g_Na = 1200.0, g_K = 360.0, g_L = 3.0, V_Na = 50.0, V_K = -77.0, V_L = 54.387, dt = 0.1;
+    double V = hh[k], m = hh[n_hh + k], n = hh[2 * n_hh + k], h = hh[3 * n_hh + k];
+    const double I = hh[4 * n_hh + k];
+    const double alpha_n = (0.01 * (V + 55)) / (1 - exp(-0.1 * (V + 55)));
+    const double alpha_m = (0.1 * (V + 40)) / (1 - exp(-0.1 * (V + 40)));
+    const double alpha_h = 0.07 * exp(-0.05 * (V + 65));
+    const double beta_n = 0.125 * exp(-0.01125 * (V + 55));
+    const double beta_m = 4 * exp(-0.05556 * (V + 65));
+    const double beta_h = 1 / (1 + exp(-0.1 * (V + 35)));
+    const double tau_n = 1 / (alpha_n + beta_n);
+    const double tau_m = 1 / (alpha_m + beta_m);
+    const double tau_h = 1 / (alpha_h + beta_h);
+    const double pm = alpha_m / (alpha_m + beta_m);
+    const double pn = alpha_n / (alpha_n + beta_n);
+    const double ph = alpha_h / (alpha_h + beta_h);
+    const double n4 = pow(n, 4.0);
+    const double m3 = pow(m, 3.0);
+    const double denominator = g_L + g_K * n4 + g_Na * (m3 * h);
+    const double tau_V = C_m / denominator;
+    const double Vinf = ((g_L) * V_L + g_K * n4 * V_K + g_Na * m3 * h * V_Na + I) / denominator;
+    const double prev_V = V;
+    V = Vinf + (V - Vinf) * exp(-1 * dt / tau_V);
+    m = pm + (m - pm) * exp(-1 * dt / tau_m);
+    n = pn + (n - pn) * exp(-1 * dt / tau_n);
+    h = ph + (h - ph) * exp(-1 * dt / tau_h);
+    hh[k] = V;
+    hh[n_hh + k] = m;
+    hh[2 * n_hh + k] = n;
+    hh[3 * n_hh + k] = h;
+    return ((prev_V < 25) && (V > 25)) ? SFE_STATUS_FIRED : SFE_STATUS_UPDATED;
+}
+
+// ---------------------------------------------------------------------------
+// K1: neuron phase. One CTA per mapped core.
+// ---------------------------------------------------------------------------
+constexpr int kSomaThreads = 256;
+
+__global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
+{
+    __shared__ double red_d[32];
+    __shared__ uint32_t red_u[32];
+    const uint32_t ci = t.soma_core_list[blockIdx.x];
+    const CoreDev core = t.cores[ci];
+    const long long steps_done = s.step[0];
+    const long long T = steps_done + 1;
+    const int lane = threadIdx.x & 31;
+
+    uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
+    double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
+    const uint32_t slot = core.ring > 1 ? static_cast<uint32_t>(T % core.ring) : 0u;
+    const uint32_t rounded = (core.neuron_count + 31u) & ~31u;
+
+    for (uint32_t k = threadIdx.x; k < rounded; k += kSomaThreads)
+    {
+        const bool valid = k < core.neuron_count;
+        int st = SFE_STATUS_IDLE;
+        if (valid)
+        {
+            const uint32_t i = core.neuron_begin + k;
+            const sfe_soma_class c = t.classes[t.neuron_class[i]];
+            // ---- dendrite output for this step ------------------------------
+            bool has_in = false;
+            double in = 0.0;
+            const uint32_t d = core.dend_base + slot * core.neuron_count + k;
+            if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR)
+            {
+                // buffer inside a plain accumulator: the charge is zeroed before it is
+                // read (src/models.cpp:78-82)
+                has_in = true;
+            }
+            else if (core.acc_mode == SFE_ACC_PACKED32)
+            {
+                const uint32_t raw = s.din32[d];
+                if (raw != 0u)
+                {
+                    const int sum = (static_cast<int>(raw << 12)) >> 12; // sign-extend 20 bits
+                    has_in = true;                                       // count = (raw - sum) >> 20 > 0
+                    in = static_cast<double>(sum) * core.inv_scale;
+                    if (core.ring > 1) s.din32[d] = 0u;
+                }
+            }
+            else if (core.acc_mode == SFE_ACC_DUAL32)
+            {
+                if (s.dcnt32[d] != 0u)
+                {
+                    has_in = true;
+                    in = static_cast<double>(static_cast<int>(s.din32[d])) * core.inv_scale;
+                    if (core.ring > 1)
+                    {
+                        s.din32[d] = 0u;
+                        s.dcnt32[d] = 0u;
+                    }
+                }
+            }
+            else
+            {
+                if (s.dcnt32[d] != 0u)
+                {
+                    has_in = true;
+                    in = s.din64[d];
+                    if (core.ring > 1)
+                    {
+                        s.din64[d] = 0.0;
+                        s.dcnt32[d] = 0u;
+                    }
+                }
+            }
+            double lat = 0.0;
+            if (c.dend_in_neuron)
+            {
+                dend_e += c.dend_energy_update;
+                lat += c.dend_latency_update;
+            }
+            // ---- soma ---------------------------------------------------------
+            const double bias = s.bias[i];
+            if (c.model == SFE_SOMA_LIF)
+            {
+                double v = s.v[i], u = s.u[i];
+                int refr = s.refractory[i];
+                st = lif_update(c, v, u, refr, bias, has_in, in, steps_done);
+                s.v[i] = v;
+                s.u[i] = u;
+                s.refractory[i] = refr;
+            }
+            else if (c.model == SFE_SOMA_TRUENORTH)
+            {
+                double v = s.v[i];
+                st = truenorth_update(c, v, bias, has_in, in);
+                s.v[i] = v;
+            }
+            else if (c.model == SFE_SOMA_INPUT)
+            {
+                st = input_update(t.inputs[t.neuron_aux[i]], t.input_spikes, steps_done, T);
+            }
+            else
+            {
+                st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
+            }
+            s.status[i] = static_cast<uint8_t>(st);
+            // ---- default soma costs  src/pipeline.hpp:631-714 -----------------
+            double e = c.energy_access, l = c.latency_access;
+            if (st >= SFE_STATUS_UPDATED)
+            {
+                e += c.energy_update;
+                l += c.latency_update;
+                ++n_updated;
+            }
+            if (st == SFE_STATUS_FIRED)
+            {
+                e += c.energy_spike_out;
+                l += c.latency_spike_out;
+                ++n_fired;
+                // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon
+                const uint32_t a0 = t.axon_out_begin[i], a1 = t.axon_out_begin[i + 1];
+                for (uint32_t a = a0; a < a1; ++a)
+                {
+                    const uint32_t bit = t.axon_out_bit[a];
+                    atomicOr(&s.inbox[bit >> 5], 1u << (bit & 31));
+                }
+                n_packets += a1 - a0;
+            }
+            soma_e += e;
+            lat_sum += lat + l;
+        }
+        // spike raster: one ballot per 32 neurons (warp-uniform loop)
+        const uint32_t ballot = __ballot_sync(0xffffffffu, st == SFE_STATUS_FIRED);
+        if (lane == 0) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
+    }
+    // ---- per-core reductions -------------------------------------------------
+    const uint32_t upd = block_sum(n_updated, red_u);
+    const uint32_t frd = block_sum(n_fired, red_u);
+    const uint32_t pkt = block_sum(n_packets, red_u);
+    const double se = block_sum(soma_e, red_d);
+    const double de = block_sum(dend_e, red_d);
+    const double ls = block_sum(lat_sum, red_d);
+    if (threadIdx.x == 0)
+    {
+        StatsN out;
+        out.updated = upd;
+        out.fired = frd;
+        out.packets = pkt;
+        out.pad = 0;
+        out.soma_e = se;
+        out.dend_e = de;
+        // sum of generation delays incl. the trailing placeholder message
+        // (src/chip.cpp:640-652, 821-823; src/schedule.cpp:81)
+        out.gen_sum = ls + static_cast<double>(pkt) * core.lat_axon_out;
+        s.stats_n[ci] = out;
+    }
+}
+
+// potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
+__global__ void probe_kernel(const DevTables t, const DevState s)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= t.n_probes) return;
+    const uint32_t i = t.probes[p];
+    const uint32_t model = t.classes[t.neuron_class[i]].model;
+    double v = s.v[i];
+    if (model == SFE_SOMA_HH) v = s.hh[t.neuron_aux[i]];
+    else if (model == SFE_SOMA_INPUT) v = 0.0; // PipelineUnit::get_potential default
+    s.probe_out[p] = v;
+}
+
+// ---------------------------------------------------------------------------
+// K3: message phase. One CTA per destination core.
+// ---------------------------------------------------------------------------
+constexpr int kFanoutThreads = 256;
+constexpr int kFanoutWarps = kFanoutThreads / 32;
+
+struct FanoutCounters
+{
+    uint32_t msgs;
+    unsigned long long events, hop_e, hop_w, hop_n, hop_s;
+    double syn_e, den_e, proc;
+};
+
+__device__ __forceinline__ void account_axon(
+        FanoutCounters &c, const sfe_axon_in &ax, const sfe_cost_class &cc, const double lat_axon_in)
+{
+    // receive_message / sim_estimate_network_costs  src/chip.cpp:694-708,1127-1169
+    const unsigned long long dx = SFE_HOP_DX(ax.hop), dy = SFE_HOP_DY(ax.hop);
+    if (SFE_HOP_EAST(ax.hop)) c.hop_e += dx; else c.hop_w += dx;
+    if (SFE_HOP_NORTH(ax.hop)) c.hop_n += dy; else c.hop_s += dy;
+    c.msgs += 1;
+    c.events += ax.syn_count;
+    if (cc.per_message)
+    {
+        c.syn_e += cc.syn_energy;
+        c.den_e += cc.den_energy;
+        c.proc += lat_axon_in + cc.syn_latency;
+    }
+    else
+    {
+        const double n = static_cast<double>(ax.syn_count);
+        c.syn_e += n * cc.syn_energy;
+        c.den_e += n * cc.den_energy;
+        c.proc += lat_axon_in + n * (cc.syn_latency + cc.den_latency);
+    }
+}
+
+__global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables t, const DevState s)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red_d[32];
+    __shared__ unsigned long long red_l[32];
+    __shared__ uint32_t red_u[32];
+
+    const uint32_t ci = t.fanout_core_list[blockIdx.x];
+    const CoreDev core = t.cores[ci];
+    const long long T = s.step[0] + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t P = core.neuron_count;
+    const uint32_t cells = P * core.ring;
+    // does accumulated charge survive? (not for a plain accumulator with the buffer
+    // inside the dendrite unit — the neuron phase zeroes it; only counters matter)
+    const bool accumulate = core.dend_in_msg != 0 && cells > 0;
+
+    uint32_t *acc32 = reinterpret_cast<uint32_t *>(smem_raw);          // PACKED32 / DUAL32 sum
+    uint32_t *cnt32 = acc32 + cells;                                   // DUAL32 count / ORDERED has
+    double *acc64 = reinterpret_cast<double *>(smem_raw);              // ORDERED (cnt32 placed after)
+    if (core.acc_mode == SFE_ACC_ORDERED) cnt32 = reinterpret_cast<uint32_t *>(acc64 + cells);
+
+    if (accumulate)
+    {
+        if (core.acc_mode == SFE_ACC_PACKED32)
+            for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads) acc32[x] = 0u;
+        else if (core.acc_mode == SFE_ACC_DUAL32)
+            for (uint32_t x = threadIdx.x; x < 2 * cells; x += kFanoutThreads) acc32[x] = 0u;
+        else
+            for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+            {
+                // a delay-line slot that already holds charge keeps adding to it in
+                // event order (value_or(0.0) + w, src/models.cpp:123-125): seed from HBM
+                acc64[x] = core.ring > 1 ? s.din64[core.dend_base + x] : 0.0;
+                cnt32[x] = core.ring > 1 ? s.dcnt32[core.dend_base + x] : 0u;
+            }
+    }
+    __syncthreads();
+
+    FanoutCounters cnt = {0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+    const uint32_t n_words = (core.axon_count + 31u) >> 5;
+    const double *__restrict__ w_base = t.syn_w + core.syn_begin;
+    const uint32_t *__restrict__ m_base = t.syn_meta + core.syn_begin;
+    const uint32_t ring = core.ring;
+
+    if (core.acc_mode != SFE_ACC_ORDERED)
+    {
+        // Exact fixed-point accumulation: any order gives the reference's sums
+        // bit for bit (load-time certificate), so warps take inbox words round-robin.
+        for (uint32_t wi = warp; wi < n_words; wi += kFanoutWarps)
+        {
+            uint32_t word = 0u;
+            if (lane == 0)
+            {
+                word = s.inbox[core.inbox_word_begin + wi];
+                if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u; // consume
+            }
+            word = __shfl_sync(0xffffffffu, word, 0);
+            while (word != 0u)
+            {
+                const uint32_t b = __ffs(word) - 1;
+                word &= word - 1u;
+                const sfe_axon_in ax = t.axons_in[core.axon_begin + (wi << 5) + b];
+                if (lane == 0) account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
+                if (!accumulate) continue;
+                for (uint32_t j = lane; j < ax.syn_count; j += 32)
+                {
+                    const double w = __ldg(w_base + ax.syn_off + j);
+                    const uint32_t m = __ldg(m_base + ax.syn_off + j);
+                    const uint32_t post = SFE_SYN_POST(m);
+                    const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
+                    const int fixed = __double2int_rn(w * core.scale);
+                    if (core.acc_mode == SFE_ACC_PACKED32)
+                        atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
+                    else
+                    {
+                        atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
+                        atomicAdd(&cnt32[sl * P + post], 1u);
+                    }
+                }
+            }
+        }
+    }
+    else if (warp == 0)
+    {
+        // Ordered mode: one warp replays the messages in arrival order and adds
+        // in synapse order, exactly like the reference's sequential loop.
+        for (uint32_t wi = 0; wi < n_words; ++wi)
+        {
+            uint32_t word = 0u;
+            if (lane == 0)
+            {
+                word = s.inbox[core.inbox_word_begin + wi];
+                if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u;
+            }
+            word = __shfl_sync(0xffffffffu, word, 0);
+            while (word != 0u)
+            {
+                const uint32_t b = __ffs(word) - 1;
+                word &= word - 1u;
+                const sfe_axon_in ax = t.axons_in[core.axon_begin + (wi << 5) + b];
+                if (lane == 0) account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
+                if (!accumulate) continue;
+                for (uint32_t j0 = 0; j0 < ax.syn_count; j0 += 32)
+                {
+                    const uint32_t j = j0 + lane;
+                    const bool valid = j < ax.syn_count;
+                    double w = 0.0;
+                    uint32_t cell = 0xffffffffu - lane; // distinct dummies for idle lanes
+                    if (valid)
+                    {
+                        w = __ldg(w_base + ax.syn_off + j);
+                        const uint32_t m = __ldg(m_base + ax.syn_off + j);
+                        const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
+                        cell = sl * P + SFE_SYN_POST(m);
+                    }
+                    // lanes that hit the same cell add one after the other, lowest lane first
+                    const uint32_t peers = __match_any_sync(0xffffffffu, cell);
+                    const int rank = __popc(peers & ((1u << lane) - 1u));
+                    const int rounds = __reduce_max_sync(0xffffffffu, __popc(peers));
+                    for (int r = 0; r < rounds; ++r)
+                    {
+                        if (valid && rank == r)
+                        {
+                            acc64[cell] = acc64[cell] + w;
+                            cnt32[cell] = 1u;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the dendrite state back (coalesced) ------------------------------
+    if (accumulate)
+    {
+        const uint32_t base = core.dend_base;
+        if (core.acc_mode == SFE_ACC_PACKED32)
+        {
+            if (ring > 1)
+            {
+                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+                    if (acc32[x] != 0u) s.din32[base + x] += acc32[x];
+            }
+            else
+                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads) s.din32[base + x] = acc32[x];
+        }
+        else if (core.acc_mode == SFE_ACC_DUAL32)
+        {
+            if (ring > 1)
+            {
+                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+                    if (cnt32[x] != 0u)
+                    {
+                        s.din32[base + x] += acc32[x];
+                        s.dcnt32[base + x] += cnt32[x];
+                    }
+            }
+            else
+                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+                {
+                    s.din32[base + x] = acc32[x];
+                    s.dcnt32[base + x] = cnt32[x];
+                }
+        }
+        else
+        {
+            for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+            {
+                s.din64[base + x] = acc64[x];
+                s.dcnt32[base + x] = cnt32[x];
+            }
+        }
+    }
+
+    // ---- per-core counters ---------------------------------------------------------
+    const uint32_t msgs = block_sum(cnt.msgs, red_u);
+    const unsigned long long events = block_sum(cnt.events, red_l);
+    const unsigned long long he = block_sum(cnt.hop_e, red_l);
+    const unsigned long long hw = block_sum(cnt.hop_w, red_l);
+    const unsigned long long hn = block_sum(cnt.hop_n, red_l);
+    const unsigned long long hs = block_sum(cnt.hop_s, red_l);
+    const double se = block_sum(cnt.syn_e, red_d);
+    const double de = block_sum(cnt.den_e, red_d);
+    const double pr = block_sum(cnt.proc, red_d);
+    if (threadIdx.x == 0)
+    {
+        StatsM out;
+        out.msgs = msgs;
+        out.pad = 0;
+        out.events = events;
+        out.hop_e = he;
+        out.hop_w = hw;
+        out.hop_n = hn;
+        out.hop_s = hs;
+        out.syn_e = se;
+        out.den_e = de;
+        out.proc = pr;
+        s.stats_m[ci] = out;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: energy, counters, simple timing model. One CTA.
+// ---------------------------------------------------------------------------
+constexpr int kFinalThreads = 1024;
+
+__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
+{
+    __shared__ double red_d[32];
+    __shared__ unsigned long long red_l[32];
+    unsigned long long fired = 0, updated = 0, packets = 0, hops = 0, events = 0;
+    double syn_e = 0.0, den_e = 0.0, soma_e = 0.0, net_e = 0.0, max_gen = 0.0, max_proc = 0.0;
+    for (uint32_t ci = threadIdx.x; ci < t.n_cores; ci += kFinalThreads)
+    {
+        const CoreDev &core = t.cores[ci];
+        const StatsN n = s.stats_n[ci];
+        const StatsM m = s.stats_m[ci];
+        fired += n.fired;
+        updated += n.updated;
+        packets += n.packets;
+        hops += m.hop_e + m.hop_w + m.hop_n + m.hop_s;
+        events += m.events;
+        syn_e += m.syn_e;
+        den_e += n.dend_e + m.den_e;
+        soma_e += n.soma_e;
+        // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
+        double hop = static_cast<double>(m.hop_e) * core.e_east;
+        hop += static_cast<double>(m.hop_w) * core.e_west;
+        hop += static_cast<double>(m.hop_s) * core.e_south;
+        hop += static_cast<double>(m.hop_n) * core.e_north;
+        net_e += hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
+        max_gen = fmax(max_gen, n.gen_sum);
+        max_proc = fmax(max_proc, m.proc);
+    }
+    const unsigned long long f = block_sum(fired, red_l);
+    const unsigned long long u = block_sum(updated, red_l);
+    const unsigned long long p = block_sum(packets, red_l);
+    const unsigned long long h = block_sum(hops, red_l);
+    const unsigned long long e = block_sum(events, red_l);
+    const double se = block_sum(syn_e, red_d);
+    const double de = block_sum(den_e, red_d);
+    const double so = block_sum(soma_e, red_d);
+    const double ne = block_sum(net_e, red_d);
+    // block-wide max through the same scratch
+    double mg = warp_max(max_gen), mp = warp_max(max_proc);
+    __shared__ double red_m[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0)
+    {
+        red_m[warp] = mg;
+        red_m[32 + warp] = mp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 0; w < kFinalThreads / 32; ++w)
+        {
+            mg = fmax(mg, red_m[w]);
+            mp = fmax(mp, red_m[32 + w]);
+        }
+        sfe_step_record r;
+        r.neurons_fired = static_cast<long long>(f);
+        r.neurons_updated = static_cast<long long>(u);
+        r.packets_sent = static_cast<long long>(p);
+        r.total_hops = static_cast<long long>(h);
+        r.spike_count = static_cast<long long>(e);
+        r.synapse_energy = se;
+        r.dendrite_energy = de;
+        r.soma_energy = so;
+        r.network_energy = ne;
+        r.total_energy = ne + se + de + so;
+        // schedule_messages_timestep_simple  src/schedule.cpp:61-102
+        r.sim_time = fmax(mp, mg) + t.sync_delay;
+        const long long cursor = s.step[1];
+        s.log[cursor % s.log_cap] = r;
+        s.step[1] = cursor + 1;
+        s.step[0] = s.step[0] + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Bulk synthetic network: synapse generation + exactness certificate on device
+// ---------------------------------------------------------------------------
+__global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restrict__ syn_w,
+        uint32_t *__restrict__ syn_meta, const unsigned long long total)
+{
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    const uint32_t C = sp.cores, P = sp.neurons_per_core, D = sp.dest_cores, S = sp.syn_per_axon;
+    const unsigned long long per_core = static_cast<unsigned long long>(P) * D * S;
+    for (unsigned long long g = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
+            g += stride)
+    {
+        const uint32_t d = static_cast<uint32_t>(g / per_core);
+        const unsigned long long rem = g % per_core;
+        const uint32_t slot = static_cast<uint32_t>(rem / S);
+        const uint32_t j = static_cast<uint32_t>(rem % S);
+        const uint32_t r = slot / P, p = slot % P;
+        // r-th source core of destination d, ascending core id (see lower_synthetic)
+        uint32_t src;
+        if (D == C) src = r;
+        else if (d + 1 >= D) src = d + 1 - D + r;
+        else
+        {
+            const uint32_t wrapped = D - 1 - d;
+            src = r <= d ? r : C - wrapped + (r - (d + 1));
+        }
+        const uint32_t k = (d + C - src) % C;
+        const unsigned long long n = static_cast<unsigned long long>(src) * P + p;
+        const unsigned long long axon = n * D + k;
+        const unsigned long long syn = axon * S + j;
+        const sfe_synth_axon ap = sfe_synth_axon_params(&sp, axon);
+        syn_w[g] = static_cast<double>(sfe_synth_weight(&sp, syn));
+        syn_meta[g] = sfe_synth_post(&sp, &ap, j) | (sfe_synth_delay(&sp, syn) << 16);
+    }
+}
+
+// per core: worst per-post fan-in and sum |w * 2^shift| -> accumulation mode
+__global__ void __launch_bounds__(256) certify_kernel(
+        CoreDev *cores, const uint32_t *core_list, const double *syn_w, const uint32_t *syn_meta, const uint64_t *syn_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t bad;
+    const uint32_t ci = core_list[blockIdx.x];
+    CoreDev &core = cores[ci];
+    const uint32_t P = core.neuron_count;
+    unsigned long long *sum_abs = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint32_t *fan = reinterpret_cast<uint32_t *>(sum_abs + P);
+    for (uint32_t x = threadIdx.x; x < P; x += blockDim.x)
+    {
+        sum_abs[x] = 0ull;
+        fan[x] = 0u;
+    }
+    if (threadIdx.x == 0) bad = 0u;
+    __syncthreads();
+    const unsigned long long n = syn_count[ci];
+    for (unsigned long long x = threadIdx.x; x < n; x += blockDim.x)
+    {
+        const double scaled = fabs(syn_w[core.syn_begin + x] * core.scale);
+        if (!(scaled < 2147483648.0) || scaled != rint(scaled)) bad = 1u;
+        const uint32_t post = SFE_SYN_POST(syn_meta[core.syn_begin + x]);
+        atomicAdd(&sum_abs[post], static_cast<unsigned long long>(scaled));
+        atomicAdd(&fan[post], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long worst_sum = 0ull;
+        uint32_t worst_fan = 0u;
+        for (uint32_t x = 0; x < P; ++x)
+        {
+            worst_sum = sum_abs[x] > worst_sum ? sum_abs[x] : worst_sum;
+            worst_fan = fan[x] > worst_fan ? fan[x] : worst_fan;
+        }
+        uint32_t mode = SFE_ACC_ORDERED;
+        if (bad == 0u)
+        {
+            if (worst_sum < 524288ull && worst_fan < 4096u) mode = SFE_ACC_PACKED32;
+            else if (worst_sum < 2147483648ull) mode = SFE_ACC_DUAL32;
+        }
+        core.acc_mode = mode;
+    }
+}
+
+} // namespace
+
+// ===========================================================================
+// Host side of the engine
+// ===========================================================================
+#define SFE_CUDA(call)                                                                              \
+    do                                                                                              \
+    {                                                                                               \
+        const cudaError_t err__ = (call);                                                           \
+        if (err__ != cudaSuccess)                                                                   \
+        {                                                                                           \
+            sfe::set_last_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " +  \
+                    __FILE__ + ":" + std::to_string(__LINE__) + " (" #call ")");                    \
+            return -1;                                                                              \
+        }                                                                                           \
+    } while (0)
+
+struct sfe_engine
+{
+    int device{0};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+    std::vector<void *> allocs;
+    size_t device_bytes{0};
+    DevTables t{};
+    DevState s{};
+    CoreDev *d_cores{nullptr};
+    uint32_t *d_neuron_class{nullptr};
+    sfe_soma_class *d_classes{nullptr};
+    uint32_t n_classes_cap{0};
+    std::vector<CoreDev> h_cores;
+    std::vector<uint32_t> soma_list, fanout_list;
+    std::vector<uint32_t> fired_word_begin; // per core
+    uint32_t fired_words{0}, inbox_words{0};
+    uint32_t dend_cells{0};
+    size_t fanout_smem{0};
+    uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0};
+    int64_t total_timesteps{0};
+    int64_t launches{0};
+    int64_t log_read{0}; // steps already collected from the device log
+    uint32_t log_cap{0};
+    std::vector<sfe_core_desc> core_desc; // host copy (neuron ranges)
+    std::vector<double> potential0;
+    std::vector<sfe_hh_init> hh_init;
+    // pinned staging
+    void *pinned{nullptr};
+    size_t pinned_bytes{0};
+    cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
+    bool ordered_any{false}, dual_any{false};
+
+    template <typename T> int alloc(T **p, size_t count)
+    {
+        const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        void *q = nullptr;
+        SFE_CUDA(cudaMalloc(&q, bytes));
+        SFE_CUDA(cudaMemsetAsync(q, 0, bytes, stream));
+        allocs.push_back(q);
+        device_bytes += bytes;
+        *p = static_cast<T *>(q);
+        return 0;
+    }
+    template <typename T> int upload(const T **dst, const T *src, size_t count)
+    {
+        T *p = nullptr;
+        if (alloc(&p, count) != 0) return -1;
+        if (count > 0 && src != nullptr) SFE_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+        *dst = p;
+        return 0;
+    }
+    int ensure_pinned(size_t bytes)
+    {
+        if (bytes <= pinned_bytes) return 0;
+        if (pinned != nullptr) cudaFreeHost(pinned);
+        pinned = nullptr;
+        pinned_bytes = 0;
+        SFE_CUDA(cudaMallocHost(&pinned, bytes));
+        pinned_bytes = bytes;
+        return 0;
+    }
+};
+
+extern "C" int sfe_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int engine_init_state(sfe_engine *e)
+{
+    // initial potentials and HH state (also what reset() does not restore: the
+    // reference's reset() zeroes, it does not re-apply initial attributes)
+    SFE_CUDA(cudaMemcpyAsync(e->s.v, e->potential0.data(), e->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (e->n_hh > 0)
+    {
+        std::vector<double> hh(5 * static_cast<size_t>(e->n_hh), 0.0);
+        for (uint32_t k = 0; k < e->n_hh; ++k)
+        {
+            hh[e->n_hh + k] = e->hh_init[k].m;
+            hh[2 * e->n_hh + k] = e->hh_init[k].n;
+            hh[3 * e->n_hh + k] = e->hh_init[k].h;
+            hh[4 * e->n_hh + k] = e->hh_init[k].current;
+        }
+        SFE_CUDA(cudaMemcpyAsync(e->s.hh, hh.data(), hh.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+static int engine_build(sfe_engine *e, const sfe_tables *tb)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    SFE_CUDA(cudaEventCreate(&e->ev_begin));
+    SFE_CUDA(cudaEventCreate(&e->ev_end));
+    e->n_neurons = tb->n_neurons;
+    e->n_probes = tb->n_probes;
+    e->n_cores = tb->n_cores;
+    e->n_hh = tb->n_hh;
+    e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
+    e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
+    if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
+
+    // ---- per-core device descriptors, padded bit layouts ---------------------
+    e->h_cores.resize(tb->n_cores);
+    std::vector<uint32_t> inbox_word_begin(tb->n_cores);
+    e->fired_word_begin.resize(tb->n_cores);
+    uint32_t inbox_words = 0, fired_words = 0, dend_cells = 0;
+    size_t smem_max = 0;
+    std::vector<uint64_t> syn_counts(tb->n_cores);
+    for (uint32_t c = 0; c < tb->n_cores; ++c)
+    {
+        const sfe_core_desc &cd = tb->cores[c];
+        CoreDev &d = e->h_cores[c];
+        std::memset(&d, 0, sizeof(d));
+        d.neuron_begin = cd.neuron_begin;
+        d.neuron_count = cd.neuron_count;
+        d.axon_begin = cd.axon_in_begin;
+        d.axon_count = cd.axon_in_count;
+        d.inbox_word_begin = inbox_words;
+        d.fired_word_begin = fired_words;
+        d.dend_base = dend_cells;
+        d.ring = cd.ring == 0 ? 1 : cd.ring;
+        d.acc_mode = cd.acc_mode;
+        d.dend_in_msg = cd.dend_in_msg;
+        d.tile = cd.tile;
+        d.syn_begin = cd.syn_begin;
+        d.scale = std::ldexp(1.0, cd.weight_shift);
+        d.inv_scale = std::ldexp(1.0, -cd.weight_shift);
+        d.lat_axon_in = cd.latency_axon_in;
+        d.e_axon_in = cd.energy_axon_in;
+        d.lat_axon_out = cd.latency_axon_out;
+        d.e_axon_out = cd.energy_axon_out;
+        const sfe_tile_desc &tile = tb->tiles[cd.tile];
+        d.e_east = tile.energy_east;
+        d.e_west = tile.energy_west;
+        d.e_south = tile.energy_south;
+        d.e_north = tile.energy_north;
+        inbox_word_begin[c] = inbox_words;
+        e->fired_word_begin[c] = fired_words;
+        inbox_words += (cd.axon_in_count + 31) / 32;
+        fired_words += (cd.neuron_count + 31) / 32;
+        dend_cells += cd.neuron_count * d.ring;
+        syn_counts[c] = cd.syn_count;
+        if (cd.neuron_count > 0) e->soma_list.push_back(c);
+        if (cd.axon_in_count > 0) e->fanout_list.push_back(c);
+        if (cd.acc_mode == SFE_ACC_ORDERED) e->ordered_any = true;
+        if (cd.acc_mode == SFE_ACC_DUAL32) e->dual_any = true;
+    }
+    e->inbox_words = inbox_words;
+    e->fired_words = fired_words;
+    e->dend_cells = dend_cells;
+
+    // ---- static tables -----------------------------------------------------------
+    if (e->upload(&e->t.classes, tb->soma_classes, tb->n_soma_classes) != 0) return -1;
+    e->d_classes = const_cast<sfe_soma_class *>(e->t.classes);
+    e->n_classes_cap = tb->n_soma_classes;
+    if (e->upload(&e->t.costs, tb->cost_classes, tb->n_cost_classes) != 0) return -1;
+    if (e->upload(&e->t.neuron_class, tb->neuron_class, tb->n_neurons) != 0) return -1;
+    e->d_neuron_class = const_cast<uint32_t *>(e->t.neuron_class);
+    if (e->upload(&e->t.neuron_aux, tb->neuron_aux, tb->n_neurons) != 0) return -1;
+    if (e->upload(&e->t.axon_out_begin, tb->axon_out_begin, static_cast<size_t>(tb->n_neurons) + 1) != 0) return -1;
+    {
+        // axon-out targets as padded inbox bit positions
+        std::vector<uint32_t> axon_core(tb->n_axons_in);
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+            for (uint32_t a = 0; a < tb->cores[c].axon_in_count; ++a) axon_core[tb->cores[c].axon_in_begin + a] = c;
+        std::vector<uint32_t> bits(tb->n_axons_out);
+        for (uint64_t a = 0; a < tb->n_axons_out; ++a)
+        {
+            const uint32_t id = tb->axon_out_target[a];
+            const uint32_t c = axon_core[id];
+            bits[a] = inbox_word_begin[c] * 32u + (id - tb->cores[c].axon_in_begin);
+        }
+        if (e->upload(&e->t.axon_out_bit, bits.data(), bits.size()) != 0) return -1;
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if (e->upload(&e->t.inputs, tb->inputs, tb->n_inputs) != 0) return -1;
+    if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
+    if (e->upload(&e->t.axons_in, tb->axons_in, tb->n_axons_in) != 0) return -1;
+    if (e->upload(&e->t.probes, tb->probes, tb->n_probes) != 0) return -1;
+    if (e->upload(&e->t.soma_core_list, e->soma_list.data(), e->soma_list.size()) != 0) return -1;
+    if (e->upload(&e->t.fanout_core_list, e->fanout_list.data(), e->fanout_list.size()) != 0) return -1;
+    {
+        const CoreDev *p = nullptr;
+        if (e->upload(&p, e->h_cores.data(), e->h_cores.size()) != 0) return -1;
+        e->t.cores = p;
+        e->d_cores = const_cast<CoreDev *>(p);
+    }
+    e->t.n_cores = tb->n_cores;
+    e->t.n_probes = tb->n_probes;
+    e->t.n_neurons = tb->n_neurons;
+    e->t.sync_delay = tb->sync_delay;
+
+    // ---- synapses: copied, or generated on the device ---------------------------
+    double *d_w = nullptr;
+    uint32_t *d_m = nullptr;
+    if (e->alloc(&d_w, tb->n_synapses) != 0) return -1;
+    if (e->alloc(&d_m, tb->n_synapses) != 0) return -1;
+    e->t.syn_w = d_w;
+    e->t.syn_meta = d_m;
+    if (tb->syn_weight != nullptr && tb->n_synapses > 0)
+    {
+        SFE_CUDA(cudaMemcpyAsync(d_w, tb->syn_weight, tb->n_synapses * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaMemcpyAsync(d_m, tb->syn_meta, tb->n_synapses * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    }
+    else if (tb->n_synapses > 0)
+    {
+        if (tb->synth == nullptr)
+        {
+            sfe::set_last_error("tables carry neither synapse arrays nor a synthetic spec");
+            return -1;
+        }
+        synth_generate_kernel<<<148 * 16, 256, 0, e->stream>>>(*tb->synth, d_w, d_m, tb->n_synapses);
+        SFE_CUDA(cudaGetLastError());
+        // certificate computed where the synapses are
+        const uint64_t *d_counts = nullptr;
+        if (e->upload(&d_counts, syn_counts.data(), syn_counts.size()) != 0) return -1;
+        uint32_t max_p = 0;
+        for (uint32_t c : e->fanout_list) max_p = std::max(max_p, tb->cores[c].neuron_count);
+        if (!e->fanout_list.empty())
+        {
+            certify_kernel<<<static_cast<unsigned>(e->fanout_list.size()), 256, max_p * 12, e->stream>>>(
+                    e->d_cores, e->t.fanout_core_list, d_w, d_m, d_counts);
+            SFE_CUDA(cudaGetLastError());
+        }
+        SFE_CUDA(cudaMemcpyAsync(e->h_cores.data(), e->d_cores, e->h_cores.size() * sizeof(CoreDev), cudaMemcpyDeviceToHost, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+        e->ordered_any = e->dual_any = false;
+        for (uint32_t c : e->fanout_list)
+        {
+            if (e->h_cores[c].acc_mode == SFE_ACC_ORDERED) e->ordered_any = true;
+            if (e->h_cores[c].acc_mode == SFE_ACC_DUAL32) e->dual_any = true;
+        }
+    }
+
+    // ---- state ---------------------------------------------------------------------
+    if (e->alloc(&e->s.v, tb->n_neurons) != 0) return -1;
+    if (e->alloc(&e->s.u, tb->n_neurons) != 0) return -1;
+    if (e->alloc(&e->s.bias, tb->n_neurons) != 0) return -1;
+    if (e->alloc(&e->s.refractory, tb->n_neurons) != 0) return -1;
+    if (e->alloc(&e->s.status, tb->n_neurons) != 0) return -1;
+    if (e->alloc(&e->s.fired_bits, fired_words) != 0) return -1;
+    if (e->alloc(&e->s.inbox, inbox_words) != 0) return -1;
+    if (e->alloc(&e->s.din32, dend_cells) != 0) return -1;
+    if (e->alloc(&e->s.dcnt32, (e->ordered_any || e->dual_any) ? dend_cells : 1) != 0) return -1;
+    if (e->alloc(&e->s.din64, e->ordered_any ? dend_cells : 1) != 0) return -1;
+    if (e->alloc(&e->s.hh, 5 * static_cast<size_t>(tb->n_hh)) != 0) return -1;
+    e->s.n_hh = tb->n_hh;
+    if (e->alloc(&e->s.stats_n, tb->n_cores) != 0) return -1;
+    if (e->alloc(&e->s.stats_m, tb->n_cores) != 0) return -1;
+    e->log_cap = 4096;
+    e->s.log_cap = e->log_cap;
+    if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
+    if (e->alloc(&e->s.probe_out, tb->n_probes) != 0) return -1;
+    if (e->alloc(&e->s.step, 2) != 0) return -1;
+    SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (engine_init_state(e) != 0) return -1;
+
+    // ---- shared memory of the message phase ------------------------------------------
+    for (uint32_t c : e->fanout_list)
+    {
+        const CoreDev &d = e->h_cores[c];
+        const size_t cells = static_cast<size_t>(d.neuron_count) * d.ring;
+        const size_t need = d.acc_mode == SFE_ACC_PACKED32 ? cells * 4 : d.acc_mode == SFE_ACC_DUAL32 ? cells * 8 : cells * 12;
+        smem_max = std::max(smem_max, need);
+    }
+    e->fanout_smem = smem_max;
+    if (smem_max > 200 * 1024)
+    {
+        sfe::set_last_error("a core needs more than 200 KB of shared-memory dendrite accumulators");
+        return -1;
+    }
+    if (smem_max > 48 * 1024)
+        SFE_CUDA(cudaFuncSetAttribute(fanout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" sfe_engine *sfe_engine_create(const sfe_tables *tables, int device)
+{
+    if (tables == nullptr || tables->abi_version != SFE_ABI_VERSION)
+    {
+        sfe::set_last_error("sfe_engine_create: bad tables / ABI version");
+        return nullptr;
+    }
+    if (sfe_device_count() <= 0)
+    {
+        sfe::set_last_error("no CUDA device: the B200 engine has no CPU fallback");
+        return nullptr;
+    }
+    sfe_engine *e = new sfe_engine();
+    e->device = device;
+    if (engine_build(e, tables) != 0)
+    {
+        sfe_engine_destroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+extern "C" void sfe_engine_destroy(sfe_engine *e)
+{
+    if (e == nullptr) return;
+    cudaSetDevice(e->device);
+    if (e->stream != nullptr) cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->pinned != nullptr) cudaFreeHost(e->pinned);
+    if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end != nullptr) cudaEventDestroy(e->ev_end);
+    if (e->own_stream && e->stream != nullptr) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int sfe_engine_set_stream(sfe_engine *e, void *stream)
+{
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    e->own_stream = false;
+    e->stream = static_cast<cudaStream_t>(stream);
+    return 0;
+}
+
+static int enqueue_step(sfe_engine *e, bool probes)
+{
+    if (!e->soma_list.empty())
+    {
+        soma_kernel<<<static_cast<unsigned>(e->soma_list.size()), kSomaThreads, 0, e->stream>>>(e->t, e->s);
+        ++e->launches;
+    }
+    if (probes && e->n_probes > 0)
+    {
+        probe_kernel<<<(e->n_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
+        ++e->launches;
+    }
+    if (!e->fanout_list.empty())
+    {
+        fanout_kernel<<<static_cast<unsigned>(e->fanout_list.size()), kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s);
+        ++e->launches;
+    }
+    finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+    ++e->launches;
+    ++e->total_timesteps;
+    return 0;
+}
+
+extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->total_timesteps - e->log_read + timesteps > e->log_cap)
+    {
+        sfe::set_last_error("sfe_engine_enqueue: more than " + std::to_string(e->log_cap) +
+                " uncollected steps; call sfe_engine_collect");
+        return -1;
+    }
+    for (int64_t i = 0; i < timesteps; ++i) enqueue_step(e, false);
+    SFE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static void add_record(sfe_run_data &rd, const sfe_step_record &r)
+{
+    // update_run_data  src/chip.cpp:462-475 (same accumulation order: step by step)
+    rd.total_energy += r.total_energy;
+    rd.synapse_energy += r.synapse_energy;
+    rd.dendrite_energy += r.dendrite_energy;
+    rd.soma_energy += r.soma_energy;
+    rd.network_energy += r.network_energy;
+    rd.sim_time += r.sim_time;
+    rd.spikes += r.spike_count;
+    rd.packets_sent += r.packets_sent;
+    rd.neurons_updated += r.neurons_updated;
+    rd.neurons_fired += r.neurons_fired;
+}
+
+static int collect_records(sfe_engine *e, std::vector<sfe_step_record> &out)
+{
+    const int64_t pending = e->total_timesteps - e->log_read;
+    out.resize(static_cast<size_t>(pending));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    int64_t done = 0;
+    while (done < pending)
+    {
+        const int64_t pos = (e->log_read + done) % e->log_cap;
+        const int64_t chunk = std::min<int64_t>(pending - done, e->log_cap - pos);
+        SFE_CUDA(cudaMemcpy(out.data() + done, e->s.log + pos, chunk * sizeof(sfe_step_record), cudaMemcpyDeviceToHost));
+        done += chunk;
+    }
+    e->log_read += pending;
+    return 0;
+}
+
+extern "C" int sfe_engine_collect(sfe_engine *e, sfe_run_data *out)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    sfe_run_data rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.timestep_start = e->log_read + 1;
+    std::vector<sfe_step_record> recs;
+    if (collect_records(e, recs) != 0) return -1;
+    rd.timesteps_executed = static_cast<int64_t>(recs.size());
+    for (const sfe_step_record &r : recs) add_record(rd, r);
+    if (out != nullptr) *out = rd;
+    return 0;
+}
+
+extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_request *req, sfe_run_data *out)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->total_timesteps != e->log_read)
+    {
+        sfe::set_last_error("sfe_engine_run: uncollected enqueued steps; call sfe_engine_collect first");
+        return -1;
+    }
+    sfe_run_data rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.timestep_start = e->total_timesteps + 1; // src/chip.cpp:481
+    rd.timesteps_executed = timesteps;
+    const bool want_fired = req != nullptr && req->fired_bits != nullptr;
+    const bool want_pot = req != nullptr && req->potentials != nullptr && e->n_probes > 0;
+    const bool want_status = req != nullptr && req->status != nullptr;
+    const size_t words = (static_cast<size_t>(e->n_neurons) + 31) / 32;
+    // per-step staging in pinned memory, drained once per batch (no per-step host sync)
+    const size_t per_step = (want_fired ? e->fired_words * sizeof(uint32_t) : 0) +
+            (want_pot ? e->n_probes * sizeof(double) : 0) + (want_status ? e->n_neurons : 0);
+    const int64_t batch_cap = per_step == 0 ? e->log_cap
+                                            : std::max<int64_t>(1, std::min<int64_t>(e->log_cap, (256ll << 20) / static_cast<int64_t>(per_step)));
+    std::vector<sfe_step_record> recs;
+    int64_t done = 0;
+    while (done < timesteps)
+    {
+        const int64_t batch = std::min<int64_t>(batch_cap, timesteps - done);
+        if (per_step > 0 && e->ensure_pinned(per_step * static_cast<size_t>(batch)) != 0) return -1;
+        for (int64_t b = 0; b < batch; ++b)
+        {
+            if (!e->soma_list.empty())
+            {
+                soma_kernel<<<static_cast<unsigned>(e->soma_list.size()), kSomaThreads, 0, e->stream>>>(e->t, e->s);
+                ++e->launches;
+            }
+            unsigned char *stage = static_cast<unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
+            if (want_fired)
+            {
+                SFE_CUDA(cudaMemcpyAsync(stage, e->s.fired_bits, e->fired_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+                stage += e->fired_words * sizeof(uint32_t);
+            }
+            if (want_pot)
+            {
+                probe_kernel<<<(e->n_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
+                ++e->launches;
+                SFE_CUDA(cudaMemcpyAsync(stage, e->s.probe_out, e->n_probes * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+                stage += e->n_probes * sizeof(double);
+            }
+            if (want_status)
+                SFE_CUDA(cudaMemcpyAsync(stage, e->s.status, e->n_neurons, cudaMemcpyDeviceToHost, e->stream));
+            if (!e->fanout_list.empty())
+            {
+                fanout_kernel<<<static_cast<unsigned>(e->fanout_list.size()), kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s);
+                ++e->launches;
+            }
+            finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+            ++e->launches;
+            ++e->total_timesteps;
+        }
+        SFE_CUDA(cudaGetLastError());
+        if (collect_records(e, recs) != 0) return -1;
+        for (int64_t b = 0; b < batch; ++b)
+        {
+            const sfe_step_record &r = recs[static_cast<size_t>(b)];
+            add_record(rd, r);
+            if (req != nullptr && req->steps != nullptr) req->steps[done + b] = r;
+            const unsigned char *stage = static_cast<const unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
+            if (want_fired)
+            {
+                // un-pad: per-core word-aligned raster -> device-index bit order
+                const uint32_t *padded = reinterpret_cast<const uint32_t *>(stage);
+                uint32_t *dst = req->fired_bits + static_cast<size_t>(done + b) * words;
+                std::memset(dst, 0, words * sizeof(uint32_t));
+                for (uint32_t c : e->soma_list)
+                {
+                    const sfe_core_desc &cd = e->core_desc[c];
+                    const uint32_t *src = padded + e->fired_word_begin[c];
+                    if ((cd.neuron_begin & 31u) == 0)
+                    {
+                        const uint32_t nw = (cd.neuron_count + 31) / 32;
+                        for (uint32_t x = 0; x < nw; ++x) dst[(cd.neuron_begin >> 5) + x] |= src[x];
+                    }
+                    else
+                    {
+                        for (uint32_t k = 0; k < cd.neuron_count; ++k)
+                            if ((src[k >> 5] >> (k & 31)) & 1u)
+                            {
+                                const uint32_t i = cd.neuron_begin + k;
+                                dst[i >> 5] |= 1u << (i & 31);
+                            }
+                    }
+                }
+                stage += e->fired_words * sizeof(uint32_t);
+            }
+            if (want_pot)
+            {
+                std::memcpy(req->potentials + static_cast<size_t>(done + b) * e->n_probes, stage, e->n_probes * sizeof(double));
+                stage += e->n_probes * sizeof(double);
+            }
+            if (want_status) std::memcpy(req->status + static_cast<size_t>(done + b) * e->n_neurons, stage, e->n_neurons);
+        }
+        done += batch;
+    }
+    if (out != nullptr) *out = rd;
+    return 0;
+}
+
+extern "C" int sfe_engine_reset(sfe_engine *e)
+{
+    // SpikingChip::reset  src/chip.cpp:576-600: pipeline buffers and model state are
+    // zeroed (LIF: u and v only; HH: V, m, n, h); timestep counters keep running
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaMemsetAsync(e->s.v, 0, e->n_neurons * sizeof(double), e->stream));
+    SFE_CUDA(cudaMemsetAsync(e->s.u, 0, e->n_neurons * sizeof(double), e->stream));
+    SFE_CUDA(cudaMemsetAsync(e->s.status, 0, e->n_neurons, e->stream));
+    SFE_CUDA(cudaMemsetAsync(e->s.din32, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(uint32_t), e->stream));
+    if (e->ordered_any || e->dual_any) SFE_CUDA(cudaMemsetAsync(e->s.dcnt32, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(uint32_t), e->stream));
+    if (e->ordered_any) SFE_CUDA(cudaMemsetAsync(e->s.din64, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(double), e->stream));
+    if (e->n_hh > 0) SFE_CUDA(cudaMemsetAsync(e->s.hh, 0, 4 * static_cast<size_t>(e->n_hh) * sizeof(double), e->stream));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n != e->n_neurons)
+    {
+        sfe::set_last_error("sfe_engine_set_bias: expected one bias per neuron");
+        return -1;
+    }
+    SFE_CUDA(cudaMemcpyAsync(e->s.bias, bias, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+extern "C" int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (neuron >= e->n_neurons)
+    {
+        sfe::set_last_error("sfe_engine_set_neuron_bias: neuron out of range");
+        return -1;
+    }
+    SFE_CUDA(cudaMemcpyAsync(e->s.bias + neuron, &bias, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int sfe_engine_update_classes(sfe_engine *e, const sfe_soma_class *classes, uint32_t n_classes,
+        const uint32_t *neuron_class)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n_classes > e->n_classes_cap)
+    {
+        sfe_soma_class *p = nullptr;
+        const uint32_t cap = std::max(n_classes, e->n_classes_cap * 2);
+        if (e->alloc(&p, cap) != 0) return -1;
+        e->d_classes = p;
+        e->t.classes = p;
+        e->n_classes_cap = cap;
+    }
+    SFE_CUDA(cudaMemcpyAsync(e->d_classes, classes, n_classes * sizeof(sfe_soma_class), cudaMemcpyHostToDevice, e->stream));
+    SFE_CUDA(cudaMemcpyAsync(e->d_neuron_class, neuron_class, e->n_neurons * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n != e->n_neurons)
+    {
+        sfe::set_last_error("sfe_engine_read_potentials: expected one slot per neuron");
+        return -1;
+    }
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    SFE_CUDA(cudaMemcpy(out, e->s.v, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    const size_t words = (static_cast<size_t>(e->n_neurons) + 31) / 32;
+    if (n_words != words)
+    {
+        sfe::set_last_error("sfe_engine_read_fired: wrong word count");
+        return -1;
+    }
+    std::vector<uint8_t> status(e->n_neurons);
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    SFE_CUDA(cudaMemcpy(status.data(), e->s.status, e->n_neurons, cudaMemcpyDeviceToHost));
+    std::memset(bits, 0, words * sizeof(uint32_t));
+    for (uint32_t i = 0; i < e->n_neurons; ++i)
+        if (status[i] == SFE_STATUS_FIRED) bits[i >> 5] |= 1u << (i & 31);
+    return 0;
+}
+
+extern "C" int64_t sfe_engine_total_timesteps(const sfe_engine *e)
+{
+    return e->total_timesteps;
+}
+extern "C" int64_t sfe_engine_launch_count(const sfe_engine *e)
+{
+    return e->launches;
+}
+extern "C" size_t sfe_engine_device_bytes(const sfe_engine *e)
+{
+    return e->device_bytes;
+}
+
+extern "C" int sfe_engine_time_begin(sfe_engine *e)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaEventRecord(e->ev_begin, e->stream));
+    return 0;
+}
+
+extern "C" int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fanout)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaEventRecord(e->ev_end, e->stream));
+    SFE_CUDA(cudaEventSynchronize(e->ev_end));
+    float ms = 0.f;
+    SFE_CUDA(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
+    if (ms_total != nullptr) *ms_total = ms;
+    if (ms_fanout != nullptr) *ms_fanout = 0.f;
+    return 0;
+}
+
+// multi-GPU hooks: see engine_multi.cu (not in this build yet)
+extern "C" int sfe_engine_partition(sfe_engine *, uint32_t, uint32_t)
+{
+    sfe::set_last_error("sfe_engine_partition: not implemented yet");
+    return -1;
+}
+extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *)
+{
+    sfe::set_last_error("not implemented yet");
+    return -1;
+}
+extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *)
+{
+    sfe::set_last_error("not implemented yet");
+    return -1;
+}
+extern "C" void *sfe_engine_fired_local_ptr(sfe_engine *, size_t *)
+{
+    return nullptr;
+}
+extern "C" void *sfe_engine_fired_global_ptr(sfe_engine *, size_t *)
+{
+    return nullptr;
+}

@@ -1,0 +1,320 @@
+// capi.cpp — the C ABI (include/sanafe_b200.h), description level.
+//
+// sfe_chip mirrors the reference's SpikingChip (src/chip.hpp:56-107): it is built
+// from an Architecture, load() lowers a SpikingNetwork to device tables, sim()
+// runs timesteps and returns RunData; state persists across sim() calls and
+// reset() zeroes model state without rewinding the timestep counter.
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+
+#include "../engine.hpp"
+#include "desc.hpp"
+#include "lower.hpp"
+#include "sanafe_b200.h"
+
+namespace sfe
+{
+namespace
+{
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string &msg)
+{
+    g_last_error = msg;
+}
+} // namespace sfe
+
+struct sfe_arch
+{
+    std::unique_ptr<sfe::Architecture> arch;
+};
+struct sfe_net
+{
+    std::unique_ptr<sfe::SpikingNetwork> net;
+    std::optional<sfe::SynthRequest> synth;
+};
+struct sfe_chip
+{
+    sfe::Architecture arch;
+    int device;
+    sfe::HostTables tables;
+    bool loaded{false};
+    sfe_engine *engine{nullptr};
+    // SpikingChip running totals (src/chip.cpp:535-547, 602-621)
+    double total_energy{0.0};
+    double total_sim_time{0.0};
+    explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
+};
+
+namespace
+{
+template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f())
+{
+    try
+    {
+        return f();
+    }
+    catch (const std::exception &e)
+    {
+        sfe::set_last_error(e.what());
+    }
+    catch (...)
+    {
+        sfe::set_last_error("unknown C++ exception");
+    }
+    return on_error;
+}
+
+int attach_engine(sfe_chip *c)
+{
+    if (c->engine != nullptr)
+    {
+        sfe_engine_destroy(c->engine);
+        c->engine = nullptr;
+    }
+    c->total_energy = 0.0;
+    c->total_sim_time = 0.0;
+    if (c->device < 0) return 0; // host-only chip: lowering + table export
+    c->engine = sfe_engine_create(&c->tables.view, c->device);
+    return c->engine != nullptr ? 0 : -1;
+}
+} // namespace
+
+extern "C" const char *sfe_last_error(void)
+{
+    return sfe::g_last_error.c_str();
+}
+
+extern "C" int sfe_abi_version(void)
+{
+    return SFE_ABI_VERSION;
+}
+
+extern "C" sfe_arch *sfe_arch_load_yaml(const char *path)
+{
+    return guarded(
+            [&]() -> sfe_arch * {
+                auto a = std::make_unique<sfe_arch>();
+                a->arch = sfe::load_arch_yaml(path);
+                return a.release();
+            },
+            nullptr);
+}
+
+extern "C" sfe_net *sfe_net_load_yaml(const char *path, sfe_arch *arch)
+{
+    return guarded(
+            [&]() -> sfe_net * {
+                if (arch == nullptr || !arch->arch) throw std::invalid_argument("sfe_net_load_yaml: null architecture");
+                auto n = std::make_unique<sfe_net>();
+                n->net = sfe::load_net_yaml(path, *arch->arch);
+                return n.release();
+            },
+            nullptr);
+}
+
+extern "C" int sfe_load_flat(const char *path, sfe_arch **arch, sfe_net **net)
+{
+    return guarded(
+            [&]() -> int {
+                auto a = std::make_unique<sfe_arch>();
+                auto n = std::make_unique<sfe_net>();
+                sfe::load_flat_file(path, a->arch, n->net, n->synth);
+                *arch = a.release();
+                *net = n.release();
+                return 0;
+            },
+            -1);
+}
+
+extern "C" void sfe_arch_free(sfe_arch *a)
+{
+    delete a;
+}
+extern "C" void sfe_net_free(sfe_net *n)
+{
+    delete n;
+}
+
+extern "C" sfe_chip *sfe_chip_create(const sfe_arch *arch, int device)
+{
+    return guarded(
+            [&]() -> sfe_chip * {
+                if (arch == nullptr || !arch->arch) throw std::invalid_argument("sfe_chip_create: null architecture");
+                if (device >= 0 && sfe_device_count() <= 0)
+                    throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback "
+                                             "(pass device < 0 for a host-only chip that can only lower/export tables)");
+                return new sfe_chip(*arch->arch, device);
+            },
+            nullptr);
+}
+
+extern "C" void sfe_chip_destroy(sfe_chip *c)
+{
+    if (c == nullptr) return;
+    if (c->engine != nullptr) sfe_engine_destroy(c->engine);
+    delete c;
+}
+
+extern "C" int sfe_chip_load(sfe_chip *c, const sfe_net *net)
+{
+    return guarded(
+            [&]() -> int {
+                if (net == nullptr) throw std::invalid_argument("sfe_chip_load: null network");
+                if (net->synth.has_value()) sfe::lower_synthetic(c->arch, *net->synth, true, c->tables);
+                else sfe::lower_network(c->arch, *net->net, c->tables);
+                c->loaded = true;
+                return attach_engine(c);
+            },
+            -1);
+}
+
+extern "C" int sfe_chip_load_synthetic(sfe_chip *c, const sfe_synth_spec *spec, int generate_on_device)
+{
+    return guarded(
+            [&]() -> int {
+                sfe::SynthRequest req;
+                req.spec = *spec;
+                // unit names follow BASELINE config 4
+                req.soma_hw_name = "loihi_lif";
+                req.synapse_hw_name = "loihi_dense_synapse";
+                req.dendrite_hw_name = "loihi_dendrites_delay";
+                sfe::lower_synthetic(c->arch, req, generate_on_device == 0, c->tables);
+                c->loaded = true;
+                return attach_engine(c);
+            },
+            -1);
+}
+
+extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, const sfe_trace_request *req,
+        sfe_run_data *out)
+{
+    return guarded(
+            [&]() -> int {
+                if (!c->loaded) throw std::runtime_error("sfe_chip_sim: no network loaded");
+                if (c->engine == nullptr)
+                    throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback");
+                if (timing_model != SFE_TIMING_SIMPLE)
+                    throw std::runtime_error("only the 'simple' timing model runs on the device; the detailed "
+                                             "scheduler (src/schedule.cpp:208-661) is not implemented yet and the "
+                                             "cycle-accurate model (Booksim2) is out of scope");
+                sfe_run_data rd;
+                if (sfe_engine_run(c->engine, timesteps, req, &rd) != 0) return -1;
+                c->total_energy += rd.total_energy;   // sim_update_total_energy_and_counts
+                c->total_sim_time += rd.sim_time;     // retire_timestep
+                if (out != nullptr) *out = rd;
+                return 0;
+            },
+            -1);
+}
+
+extern "C" int sfe_chip_reset(sfe_chip *c)
+{
+    if (c->engine == nullptr)
+    {
+        sfe::set_last_error("sfe_chip_reset: chip has no device engine");
+        return -1;
+    }
+    return sfe_engine_reset(c->engine);
+}
+
+extern "C" double sfe_chip_get_power(sfe_chip *c)
+{
+    return c->total_sim_time > 0.0 ? c->total_energy / c->total_sim_time : 0.0; // src/chip.cpp:607-621
+}
+
+extern "C" const sfe_tables *sfe_chip_tables(const sfe_chip *c)
+{
+    return c->loaded ? &c->tables.view : nullptr;
+}
+
+extern "C" sfe_engine *sfe_chip_engine(sfe_chip *c)
+{
+    return c->engine;
+}
+
+extern "C" int64_t sfe_chip_neuron_index(const sfe_chip *c, const char *group, uint64_t offset)
+{
+    return c->tables.find_neuron(group, offset);
+}
+
+extern "C" int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offset, const char *name,
+        double value)
+{
+    return guarded(
+            [&]() -> int {
+                const int64_t idx = c->tables.find_neuron(group, offset);
+                if (idx < 0) throw std::out_of_range(std::string("no mapped neuron ") + group + "." + std::to_string(offset));
+                const bool classes_changed = sfe::patch_neuron_attribute(c->tables, static_cast<uint32_t>(idx), name, value);
+                if (c->engine == nullptr) return 0;
+                if (std::string(name) == "bias") return sfe_engine_set_neuron_bias(c->engine, static_cast<uint32_t>(idx), value);
+                if (classes_changed)
+                    return sfe_engine_update_classes(c->engine, c->tables.soma_classes.data(),
+                            static_cast<uint32_t>(c->tables.soma_classes.size()), c->tables.neuron_class.data());
+                return 0;
+            },
+            -1);
+}
+
+// Spike rows in the reference's trace order and format (src/chip.cpp:1610-1630):
+// for every step, groups in lexicographic order, offsets ascending, only neurons
+// with log_spikes. Returns the number of bytes needed (excluding the NUL).
+extern "C" size_t sfe_chip_format_spikes(const sfe_chip *c, const uint32_t *fired_bits, int64_t timesteps,
+        int64_t timestep_start, char *buf, size_t cap)
+{
+    const sfe::HostTables &t = c->tables;
+    const size_t words = (t.names.size() + 31) / 32;
+    std::string out;
+    for (int64_t s = 0; s < timesteps; ++s)
+    {
+        const uint32_t *bits = fired_bits + static_cast<size_t>(s) * words;
+        for (size_t g = 0; g < t.group_names.size(); ++g)
+        {
+            for (size_t o = 0; o < t.group_to_device[g].size(); ++o)
+            {
+                const uint32_t i = t.group_to_device[g][o];
+                if (t.names[i].log_spikes && ((bits[i >> 5] >> (i & 31)) & 1u))
+                {
+                    out += t.group_names[g];
+                    out += '.';
+                    out += std::to_string(o);
+                    out += ',';
+                    out += std::to_string(timestep_start + s);
+                    out += '\n';
+                }
+            }
+        }
+    }
+    if (buf != nullptr && cap > 0)
+    {
+        const size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = '\0';
+    }
+    return out.size();
+}
+
+// header of potentials.csv (src/chip.cpp:1454-1476): "timestep,neuron g.o,..."
+extern "C" size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap)
+{
+    const sfe::HostTables &t = c->tables;
+    std::string out;
+    for (uint32_t i : t.probes)
+    {
+        out += t.group_names[t.names[i].group];
+        out += '.';
+        out += std::to_string(t.names[i].offset);
+        out += '\n';
+    }
+    if (buf != nullptr && cap > 0)
+    {
+        const size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = '\0';
+    }
+    return out.size();
+}

@@ -1,0 +1,1018 @@
+// lower.cpp — see lower.hpp.
+#include "lower.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <unordered_map>
+
+namespace sfe
+{
+namespace
+{
+constexpr size_t kLifMaxCompartments = 1024;   // src/models.hpp:29
+constexpr size_t kTrueNorthMaxNeurons = 4096;  // src/models.hpp:283
+constexpr size_t kMaxDelay = 5;                // src/models.hpp:158
+
+enum class UnitModel
+{
+    current_based,
+    accumulator,
+    accumulator_with_delay,
+    lif,
+    truenorth,
+    input,
+    hodgkin_huxley
+};
+
+struct UnitKey
+{
+    int family;
+    int instance;
+    bool operator<(const UnitKey &o) const
+    {
+        return family != o.family ? family < o.family : instance < o.instance;
+    }
+    bool operator==(const UnitKey &o) const { return family == o.family && instance == o.instance; }
+};
+
+struct UnitState // one used hardware unit instance of one core
+{
+    UnitModel model{};
+    size_t neuron_count{0};     // PipelineUnit::add_neuron     src/pipeline.cpp:79-85
+    size_t connection_count{0}; // PipelineUnit::add_connection src/pipeline.cpp:59-77
+    std::vector<uint8_t> delays; // accumulator_with_delay: by synapse address (src/models.cpp:133-152)
+    // "input" / HH keep ONE state per unit
+    std::vector<uint8_t> spikes;
+    double rate{0.0};
+    double poisson{0.0};
+    double hh_m{0.0}, hh_n{0.0}, hh_h{0.0}, hh_i{0.0};
+    std::vector<uint32_t> sharing; // device-order list of neurons mapped to this unit (filled later)
+};
+
+struct LConn
+{
+    uint32_t post_core;
+    uint32_t post_in_core;
+    UnitKey syn;
+    uint32_t syn_addr;
+    double weight;
+};
+
+struct LNeuron
+{
+    const Neuron *n;
+    uint32_t group;
+    UnitKey dend, soma;
+    size_t dend_addr, soma_addr;
+    sfe_soma_class cls;
+    double bias{0.0};
+    double potential0{0.0};
+    std::vector<LConn> out;
+    std::vector<std::pair<uint32_t, uint32_t>> axons_out; // (dest core, axon index in dest core)
+};
+
+struct LAxonIn
+{
+    uint32_t src_core;
+    uint32_t src_in_core;
+    std::vector<std::pair<uint32_t, uint32_t>> syn; // (src neuron's connection index) -> resolved later
+};
+
+struct LCore
+{
+    const CoreConfiguration *cfg;
+    std::vector<LNeuron> neurons;
+    std::map<UnitKey, UnitState> units;
+    std::vector<LAxonIn> axons_in;
+};
+
+UnitModel parse_model(const PipelineUnitConfiguration &u)
+{
+    const std::string &m = u.model_info.name;
+    if (u.model_info.plugin_library_path.has_value())
+    {
+        // Plugins are host C++ virtuals in the reference (src/plugins.cpp:45-98).
+        // The device path needs a device functor; the models shipped with the
+        // reference are compiled in. Anything else cannot run "with no CPU fallback".
+        if (m == "hodgkin_huxley") return UnitModel::hodgkin_huxley;
+        throw std::runtime_error("Plugin model '" + m + "' (" + *u.model_info.plugin_library_path +
+                ") has no device functor registered; host-only plugins are not supported by the B200 engine");
+    }
+    if (m == "current_based") return UnitModel::current_based;
+    if (m == "accumulator") return UnitModel::accumulator;
+    if (m == "accumulator_with_delay") return UnitModel::accumulator_with_delay;
+    if (m == "leaky_integrate_fire") return UnitModel::lif;
+    if (m == "truenorth") return UnitModel::truenorth;
+    if (m == "input") return UnitModel::input;
+    if (m == "taps")
+        throw std::runtime_error("Pipeline model 'taps' is not implemented by the B200 engine yet");
+    throw std::invalid_argument("Pipeline model not supported (" + m + ")\n"); // src/models.cpp:964-966
+}
+
+// Core::get_hw  src/core.cpp:61-97
+UnitKey get_hw(const CoreConfiguration &core, const std::string &hw_name, const bool is_synapse,
+        const bool is_dendrite, const bool is_soma)
+{
+    const bool first_available = hw_name.empty();
+    for (size_t f = 0; f < core.pipeline_hw.size(); ++f)
+    {
+        const PipelineUnitConfiguration &hw = core.pipeline_hw[f];
+        if ((is_synapse && !hw.implements_synapse) || (is_dendrite && !hw.implements_dendrite) ||
+                (is_soma && !hw.implements_soma))
+            continue;
+        if (first_available) return {static_cast<int>(f), hw.first_instance()};
+        const int inst = hw.match(hw_name);
+        if (inst >= 0) return {static_cast<int>(f), inst};
+    }
+    throw HardwareMappingError("Could not find h/w (with name:" + hw_name + ") that implements synapse:" +
+            std::to_string(static_cast<int>(is_synapse)) + ", dendrite:" +
+            std::to_string(static_cast<int>(is_dendrite)) + ", soma:" + std::to_string(static_cast<int>(is_soma)));
+}
+
+double unit_double(const PipelineUnitConfiguration &u, const char *key, const char *what)
+{
+    auto it = u.model_info.model_attributes.find(key);
+    if (it == u.model_info.model_attributes.end())
+        throw std::runtime_error(std::string(what) + " unit '" + u.name + "' does not simulate energy/latency or " +
+                "provide a default cost (" + key + ") in the architecture description.");
+    return it->second.as_double();
+}
+
+uint32_t parse_reset_mode(const std::string &s) // src/models.cpp:905-931
+{
+    if (s == "none") return SFE_RESET_NONE;
+    if (s == "soft") return SFE_RESET_SOFT;
+    if (s == "hard") return SFE_RESET_HARD;
+    if (s == "saturate") return SFE_RESET_SATURATE;
+    throw std::invalid_argument("Reset mode not recognized");
+}
+
+void check_unit_shape(const PipelineUnitConfiguration &u)
+{
+    const int functions = int(u.implements_synapse) + int(u.implements_dendrite) + int(u.implements_soma);
+    if (functions != 1)
+        throw std::runtime_error("Hardware unit '" + u.name +
+                "' implements several pipeline functions at once; combined units are not implemented by the B200 "
+                "engine yet");
+}
+
+void soma_defaults(const PipelineUnitConfiguration &u, const UnitModel model, sfe_soma_class &c)
+{
+    // defaults of LoihiCompartment / TrueNorthNeuron  src/models.hpp:222-241, 284-299
+    std::memset(&c, 0, sizeof(c));
+    c.reset_mode = SFE_RESET_HARD;
+    c.reverse_reset_mode = SFE_RESET_NONE;
+    switch (model)
+    {
+    case UnitModel::lif:
+        c.model = SFE_SOMA_LIF;
+        c.leak = 1.0;
+        break;
+    case UnitModel::truenorth:
+        c.model = SFE_SOMA_TRUENORTH;
+        c.flags = SFE_SOMA_LEAK_TOWARDS_ZERO;
+        break;
+    case UnitModel::input:
+        c.model = SFE_SOMA_INPUT;
+        break;
+    case UnitModel::hodgkin_huxley:
+        c.model = SFE_SOMA_HH;
+        break;
+    default:
+        throw std::runtime_error("Unit '" + u.name + "' is not a soma model");
+    }
+    // src/pipeline.cpp:206-266: all three metrics or none
+    c.energy_access = unit_double(u, "energy_access_neuron", "Soma");
+    c.energy_update = unit_double(u, "energy_update_neuron", "Soma");
+    c.energy_spike_out = unit_double(u, "energy_spike_out", "Soma");
+    c.latency_access = unit_double(u, "latency_access_neuron", "Soma");
+    c.latency_update = unit_double(u, "latency_update_neuron", "Soma");
+    c.latency_spike_out = unit_double(u, "latency_spike_out", "Soma");
+    if (model == UnitModel::lif && u.model_info.model_attributes.count("noise") != 0)
+        throw std::runtime_error("LIF file noise stream is not implemented by the B200 engine yet");
+}
+
+// LoihiLifModel / TrueNorthModel / InputModel / HodgkinHuxley ::set_attribute_neuron
+// (src/models.cpp:375-439, 664-722, 832-853; plugins/hodgkin_huxley.cpp:94-114)
+void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, const std::string &key, const Attr &a)
+{
+    sfe_soma_class &c = ln.cls;
+    auto set_flag = [&](uint32_t flag, bool on) { c.flags = on ? (c.flags | flag) : (c.flags & ~flag); };
+    if (model == UnitModel::lif)
+    {
+        if (key == "threshold") c.threshold = a.as_double();
+        else if (key == "reverse_threshold") c.reverse_threshold = a.as_double();
+        else if (key == "reset") c.reset = a.as_double();
+        else if (key == "reverse_reset") c.reverse_reset = a.as_double();
+        else if (key == "reset_mode") c.reset_mode = parse_reset_mode(a.as_string());
+        else if (key == "reverse_reset_mode") c.reverse_reset_mode = parse_reset_mode(a.as_string());
+        else if (key == "leak_decay") c.leak = a.as_double();
+        else if (key == "log_u") set_flag(SFE_SOMA_LOG_U, a.as_bool());
+        else if (key == "input_decay") c.input_decay = a.as_double();
+        else if (key == "bias") ln.bias = a.as_double();
+        else if (key == "force_update" || key == "force_update_every_timestep")
+            set_flag(SFE_SOMA_FORCE_UPDATE, a.as_bool());
+        else if (key == "refractory_delay") c.refractory_delay = a.as_int();
+        else if (key == "potential") ln.potential0 = a.as_double();
+    }
+    else if (model == UnitModel::truenorth)
+    {
+        if (key == "threshold") c.threshold = a.as_double();
+        else if (key == "reverse_threshold") c.reverse_threshold = a.as_double();
+        else if (key == "reset") c.reset = a.as_double();
+        else if (key == "reverse_reset") c.reverse_reset = a.as_double();
+        else if (key == "reset_mode") c.reset_mode = parse_reset_mode(a.as_string());
+        else if (key == "reverse_reset_mode") c.reverse_reset_mode = parse_reset_mode(a.as_string());
+        else if (key == "leak") c.leak = a.as_double();
+        else if (key == "bias") ln.bias = a.as_double();
+        else if (key == "force_update_every_timestep" || key == "force_update")
+            set_flag(SFE_SOMA_FORCE_UPDATE, a.as_bool());
+        else if (key == "leak_towards_zero") set_flag(SFE_SOMA_LEAK_TOWARDS_ZERO, a.as_bool());
+        else if (key == "random_mask")
+        {
+            const int mask = a.as_int();
+            if (mask < 0) throw std::invalid_argument("random_mask < 0; must be unsigned.");
+            if (mask != 0)
+                throw std::runtime_error("truenorth random_mask != 0 draws from the process-global std::rand() "
+                                         "(src/models.cpp:757), which no parallel engine can reproduce");
+            c.random_mask = 0;
+        }
+    }
+    else if (model == UnitModel::input)
+    {
+        if (key == "spikes")
+        {
+            unit.spikes.clear();
+            for (const Attr &e : a.as_list()) unit.spikes.push_back(e.as_bool() ? 1 : 0);
+        }
+        else if (key == "poisson")
+        {
+            unit.poisson = a.as_double();
+            if (unit.poisson > 0.0)
+                throw std::runtime_error("input model 'poisson' (libstdc++ mt19937 stream) is not implemented by "
+                                         "the B200 engine yet");
+        }
+        else if (key == "rate") unit.rate = a.as_double();
+    }
+    else if (model == UnitModel::hodgkin_huxley)
+    {
+        if (key == "m") unit.hh_m = a.as_double();
+        else if (key == "n") unit.hh_n = a.as_double();
+        else if (key == "h") unit.hh_h = a.as_double();
+        else if (key == "current") unit.hh_i = a.as_double();
+    }
+}
+
+// Smallest s in [0, 40] with w * 2^s integral for every w, or -1
+int exact_shift(const std::vector<double> &weights, size_t begin, size_t end)
+{
+    int shift = 0;
+    for (size_t i = begin; i < end; ++i)
+    {
+        const double w = weights[i];
+        if (!std::isfinite(w)) return -1;
+        while (shift <= 40)
+        {
+            const double scaled = std::ldexp(w, shift);
+            if (scaled == std::nearbyint(scaled)) break;
+            ++shift;
+        }
+        if (shift > 40) return -1;
+    }
+    return shift;
+}
+
+uint32_t pack_hop(const TileConfiguration &src, const TileConfiguration &dst)
+{
+    // sim_estimate_network_costs  src/chip.cpp:1127-1169
+    const uint32_t dx = static_cast<uint32_t>(src.x > dst.x ? src.x - dst.x : dst.x - src.x);
+    const uint32_t dy = static_cast<uint32_t>(src.y > dst.y ? src.y - dst.y : dst.y - src.y);
+    if (dx > 0xfff || dy > 0xfff) throw std::runtime_error("NoC larger than 4096 tiles per dimension");
+    const uint32_t east = src.x < dst.x ? 1u : 0u;
+    const uint32_t north = src.y < dst.y ? 1u : 0u;
+    return dx | (dy << 12) | (east << 24) | (north << 25);
+}
+
+struct CostKey
+{
+    double v[4];
+    uint32_t per_message;
+    bool operator<(const CostKey &o) const
+    {
+        const int c = std::memcmp(v, o.v, sizeof(v));
+        return c != 0 ? c < 0 : per_message < o.per_message;
+    }
+};
+
+uint32_t intern_cost(std::map<CostKey, uint32_t> &index, std::vector<sfe_cost_class> &classes, const CostKey &k,
+        const bool share)
+{
+    if (share)
+    {
+        auto it = index.find(k);
+        if (it != index.end()) return it->second;
+    }
+    sfe_cost_class c{};
+    c.syn_energy = k.v[0];
+    c.syn_latency = k.v[1];
+    c.den_energy = k.v[2];
+    c.den_latency = k.v[3];
+    c.per_message = k.per_message;
+    classes.push_back(c);
+    const uint32_t id = static_cast<uint32_t>(classes.size() - 1);
+    if (share) index[k] = id;
+    return id;
+}
+
+uint32_t intern_soma_class(std::map<std::string, uint32_t> &index, std::vector<sfe_soma_class> &classes,
+        const sfe_soma_class &c)
+{
+    const std::string key(reinterpret_cast<const char *>(&c), sizeof(c));
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    classes.push_back(c);
+    return index[key] = static_cast<uint32_t>(classes.size() - 1);
+}
+
+void fill_arch_tables(const Architecture &arch, HostTables &out)
+{
+    out.tiles.clear();
+    out.cores.clear();
+    out.core_names.clear();
+    for (const TileConfiguration &t : arch.tiles)
+    {
+        sfe_tile_desc d{};
+        d.x = static_cast<uint32_t>(t.x);
+        d.y = static_cast<uint32_t>(t.y);
+        d.energy_east = t.power_metrics.energy_east_hop;
+        d.energy_west = t.power_metrics.energy_west_hop;
+        d.energy_south = t.power_metrics.energy_south_hop;
+        d.energy_north = t.power_metrics.energy_north_hop;
+        d.latency_east = t.power_metrics.latency_east_hop;
+        d.latency_west = t.power_metrics.latency_west_hop;
+        d.latency_south = t.power_metrics.latency_south_hop;
+        d.latency_north = t.power_metrics.latency_north_hop;
+        out.tiles.push_back(d);
+        for (const CoreConfiguration &c : t.cores)
+        {
+            sfe_core_desc cd{};
+            cd.id = static_cast<uint32_t>(c.address.id);
+            cd.tile = static_cast<uint32_t>(t.id);
+            cd.offset = static_cast<uint32_t>(c.address.offset_within_tile);
+            cd.buffer_pos = c.pipeline.buffer_position;
+            cd.dend_in_msg = c.pipeline.buffer_position > buffer_before_dendrite_unit ? 1 : 0;
+            cd.ring = 1;
+            if (!c.axon_in.empty())
+            {
+                // latency from unit 0 (Message.dest_axon_hw = 0, src/message.cpp:58);
+                // energy from the LAST unit, which only ever counts messages when it is
+                // also unit 0 (src/chip.cpp:1214-1221)
+                cd.latency_axon_in = c.axon_in.front().latency_message_in;
+                cd.energy_axon_in = c.axon_in.size() == 1 ? c.axon_in.front().energy_message_in : 0.0;
+            }
+            if (!c.axon_out.empty())
+            {
+                cd.latency_axon_out = c.axon_out.front().latency_message_out; // src/core.cpp:147
+                cd.energy_axon_out = c.axon_out.size() == 1 ? c.axon_out.front().energy_message_out : 0.0;
+            }
+            out.cores.push_back(cd);
+            out.core_names.push_back(std::to_string(t.id) + "." + std::to_string(cd.offset));
+        }
+    }
+}
+
+void check_buffer_position(const CoreConfiguration &c)
+{
+    if (c.pipeline.buffer_position == buffer_inside_soma_unit ||
+            c.pipeline.buffer_position == buffer_before_axon_out_unit ||
+            c.pipeline.buffer_position == buffer_before_dendrite_unit)
+    {
+        throw std::runtime_error("Core '" + c.name +
+                "': buffer positions before the dendrite unit, inside the soma unit and before axon_out are not "
+                "implemented by the B200 engine yet (supported: dendrite+buffer_inside_unit, soma)");
+    }
+}
+} // namespace
+
+int64_t HostTables::find_neuron(const std::string &group, const uint64_t offset) const
+{
+    const auto it = std::lower_bound(group_names.begin(), group_names.end(), group);
+    if (it == group_names.end() || *it != group) return -1;
+    const auto &v = group_to_device[static_cast<size_t>(it - group_names.begin())];
+    return offset < v.size() ? static_cast<int64_t>(v[offset]) : -1;
+}
+
+void HostTables::finalize_view(const Architecture &arch)
+{
+    sfe_tables &v = view;
+    std::memset(&v, 0, sizeof(v));
+    v.abi_version = SFE_ABI_VERSION;
+    v.noc_width = static_cast<uint32_t>(arch.noc_width_in_tiles);
+    v.noc_height = static_cast<uint32_t>(arch.noc_height_in_tiles);
+    v.noc_buffer_size = static_cast<uint32_t>(arch.noc_buffer_size);
+    v.max_cores_per_tile = static_cast<uint32_t>(arch.max_cores_per_tile);
+    v.n_tiles = static_cast<uint32_t>(tiles.size());
+    v.n_cores = static_cast<uint32_t>(cores.size());
+    v.n_neurons = static_cast<uint32_t>(neuron_class.size());
+    v.n_axons_in = static_cast<uint32_t>(axons_in.size());
+    v.n_soma_classes = static_cast<uint32_t>(soma_classes.size());
+    v.n_cost_classes = static_cast<uint32_t>(cost_classes.size());
+    v.n_inputs = static_cast<uint32_t>(inputs.size());
+    v.n_hh = static_cast<uint32_t>(hh.size());
+    v.n_probes = static_cast<uint32_t>(probes.size());
+    v.n_axons_out = axon_out_target.size();
+    uint64_t nsyn = 0;
+    uint32_t mapped_cores = 0;
+    std::set<uint32_t> tiles_used;
+    for (const sfe_core_desc &c : cores)
+    {
+        nsyn += c.syn_count;
+        if (c.neuron_count > 0)
+        {
+            ++mapped_cores;
+            tiles_used.insert(c.tile);
+        }
+    }
+    v.n_synapses = nsyn;
+    v.mapped_cores = mapped_cores;
+    v.mapped_tiles = static_cast<uint32_t>(tiles_used.size());
+    v.sync_delay = arch.ts_sync_delay_table.get(v.mapped_tiles); // src/chip.cpp:562-574
+    v.tiles = tiles.data();
+    v.cores = cores.data();
+    v.soma_classes = soma_classes.data();
+    v.cost_classes = cost_classes.data();
+    v.neuron_class = neuron_class.data();
+    v.neuron_aux = neuron_aux.data();
+    v.neuron_bias = neuron_bias.data();
+    v.neuron_potential0 = neuron_potential0.data();
+    v.axon_out_begin = axon_out_begin.data();
+    v.axon_out_target = axon_out_target.data();
+    v.inputs = inputs.data();
+    v.input_spikes = input_spikes.data();
+    v.n_input_spikes = input_spikes.size();
+    v.hh = hh.data();
+    v.probes = probes.data();
+    v.axons_in = axons_in.data();
+    v.axon_src = axon_src.data();
+    v.syn_weight = syn_weight.empty() ? nullptr : syn_weight.data();
+    v.syn_meta = syn_meta.empty() ? nullptr : syn_meta.data();
+    v.synth = synth.has_value() ? &*synth : nullptr;
+}
+
+void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTables &out)
+{
+    out = HostTables{};
+    fill_arch_tables(arch, out);
+    const std::vector<const CoreConfiguration *> core_cfgs = arch.cores();
+    std::vector<LCore> lcores(core_cfgs.size());
+    for (size_t i = 0; i < core_cfgs.size(); ++i) lcores[i].cfg = core_cfgs[i];
+
+    // ---- groups, in std::map (lexicographic) order -------------------------
+    std::vector<const NeuronGroup *> groups;
+    for (const auto &[name, g] : net.groups)
+    {
+        out.group_names.push_back(name);
+        groups.push_back(g.get());
+    }
+    // ---- map_neurons: mapping_order fixes the in-core order (src/chip.cpp:186-234)
+    struct Pending
+    {
+        const Neuron *n;
+        uint32_t group;
+    };
+    std::vector<Pending> order;
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+        for (const Neuron &n : groups[gi]->neurons) order.push_back({&n, static_cast<uint32_t>(gi)});
+    std::sort(order.begin(), order.end(),
+            [](const Pending &a, const Pending &b) { return a.n->mapping_order < b.n->mapping_order; });
+    // (group, offset) -> (core, index in core)
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> where(groups.size());
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+        where[gi].assign(groups[gi]->neurons.size(), {UINT32_MAX, UINT32_MAX});
+
+    for (const Pending &p : order)
+    {
+        const Neuron &n = *p.n;
+        if (!n.core_address.has_value())
+            throw HardwareMappingError("Neuron: " + n.parent_group_name + "." + std::to_string(n.offset) + " not mapped.");
+        LCore &lc = lcores.at(n.core_address->id);
+        const CoreConfiguration &cfg = *lc.cfg;
+        // Core::map_neuron  src/core.cpp:116-168
+        if (lc.neurons.size() >= cfg.pipeline.max_neurons_supported)
+            throw HardwareMappingError("Error: Exceeded maximum neurons per core.");
+        if (cfg.pipeline_hw.empty()) throw std::runtime_error("Error: No units defined");
+        check_buffer_position(cfg);
+        LNeuron ln{};
+        ln.n = &n;
+        ln.group = p.group;
+        ln.dend = get_hw(cfg, n.dendrite_hw_name, false, true, false);
+        ln.soma = get_hw(cfg, n.soma_hw_name, false, false, true);
+        if (cfg.axon_out.empty()) throw std::runtime_error("Error: No axon out units defined");
+        const PipelineUnitConfiguration &dend_cfg = cfg.pipeline_hw[ln.dend.family];
+        const PipelineUnitConfiguration &soma_cfg = cfg.pipeline_hw[ln.soma.family];
+        check_unit_shape(dend_cfg);
+        check_unit_shape(soma_cfg);
+        UnitState &dend = lc.units[ln.dend];
+        dend.model = parse_model(dend_cfg);
+        ln.dend_addr = dend.neuron_count++;
+        UnitState &soma = lc.units[ln.soma];
+        soma.model = parse_model(soma_cfg);
+        ln.soma_addr = soma.neuron_count++;
+        if (dend.model != UnitModel::accumulator && dend.model != UnitModel::accumulator_with_delay)
+            throw std::runtime_error("Unit '" + dend_cfg.name + "' is not a dendrite model");
+        // capacity of the built-in models' state tables (src/models.hpp:29,283)
+        if (ln.dend_addr >= kLifMaxCompartments)
+            throw std::out_of_range("dendrite unit '" + dend_cfg.name + "' holds at most 1024 neurons");
+        if ((soma.model == UnitModel::lif && ln.soma_addr >= kLifMaxCompartments) ||
+                (soma.model == UnitModel::truenorth && ln.soma_addr >= kTrueNorthMaxNeurons))
+            throw std::out_of_range("soma unit '" + soma_cfg.name + "' is full");
+        soma_defaults(soma_cfg, soma.model, ln.cls);
+        ln.cls.dend_model =
+                dend.model == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR : SFE_DEND_ACCUMULATOR_DELAY;
+        ln.cls.dend_in_neuron = cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit ? 1 : 0;
+        if (ln.cls.dend_in_neuron != 0)
+        {
+            ln.cls.dend_energy_update = unit_double(dend_cfg, "energy_update", "Dendrite");
+            ln.cls.dend_latency_update = unit_double(dend_cfg, "latency_update", "Dendrite");
+        }
+        // MappedNeuron::set_attributes  src/mapped.cpp:113-166
+        for (const auto &[key, a] : n.model_attributes)
+        {
+            if (is_reserved_neuron_attribute(key))
+                throw std::invalid_argument("Reserved neuron attribute '" + key +
+                        "' cannot be used as a model attribute. Pass it as a direct argument instead (if supported).");
+            // dendrite models take no per-neuron attributes (src/models.hpp:80,133)
+            if (a.forward_to_soma) set_soma_attribute(ln, soma, soma.model, key, a);
+        }
+        where[p.group][n.offset] = {static_cast<uint32_t>(n.core_address->id), static_cast<uint32_t>(lc.neurons.size())};
+        lc.neurons.push_back(std::move(ln));
+    }
+
+    // ---- device indices: cores in id order, neurons in in-core order --------
+    uint32_t next = 0;
+    for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        out.cores[c].neuron_begin = next;
+        out.cores[c].neuron_count = static_cast<uint32_t>(lcores[c].neurons.size());
+        next += out.cores[c].neuron_count;
+    }
+    const uint32_t n_neurons = next;
+
+    // ---- map_connections  src/chip.cpp:334-380 --------------------------------
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+    {
+        for (const Neuron &src : groups[gi]->neurons)
+        {
+            const auto [src_core, src_idx] = where[gi][src.offset];
+            LNeuron &pre = lcores[src_core].neurons[src_idx];
+            pre.out.reserve(src.edges_out.size());
+            for (const Connection &con : src.edges_out)
+            {
+                if (!con.post_neuron.neuron_offset.has_value())
+                    throw std::invalid_argument("Post neuron doesn't specify group offset");
+                const auto git = std::lower_bound(out.group_names.begin(), out.group_names.end(), con.post_neuron.group_name);
+                if (git == out.group_names.end() || *git != con.post_neuron.group_name) throw std::out_of_range("map::at");
+                const size_t pg = static_cast<size_t>(git - out.group_names.begin());
+                const auto [post_core, post_idx] = where[pg].at(*con.post_neuron.neuron_offset);
+                LCore &pc = lcores[post_core];
+                LNeuron &post = pc.neurons[post_idx];
+                // get_synapse_hw_name  src/chip.cpp:308-332
+                const std::string &hw_name =
+                        !con.synapse_hw_name.empty() ? con.synapse_hw_name : post.n->default_synapse_hw_name;
+                LConn lcn{};
+                lcn.post_core = post_core;
+                lcn.post_in_core = post_idx;
+                lcn.syn = get_hw(*pc.cfg, hw_name, true, false, false);
+                const PipelineUnitConfiguration &syn_cfg = pc.cfg->pipeline_hw[lcn.syn.family];
+                check_unit_shape(syn_cfg);
+                UnitState &syn = pc.units[lcn.syn];
+                syn.model = parse_model(syn_cfg);
+                if (syn.model != UnitModel::current_based)
+                    throw std::runtime_error("Unit '" + syn_cfg.name + "' is not a synapse model");
+                lcn.syn_addr = static_cast<uint32_t>(syn.connection_count++);
+                lcn.weight = 0.0;
+                UnitState &dend = pc.units[post.dend];
+                // MappedConnection::set_attributes  src/mapped.cpp:60-89
+                for (const auto &[key, a] : con.synapse_attributes)
+                {
+                    if (a.forward_to_synapse && (key == "w" || key == "weight")) lcn.weight = a.as_double();
+                    if (a.forward_to_dendrite && dend.model == UnitModel::accumulator_with_delay)
+                    {
+                        // the dendrite's delay table is addressed by the SYNAPSE address
+                        if (dend.delays.size() <= lcn.syn_addr) dend.delays.resize(lcn.syn_addr + 1, 0);
+                        if (key == "delay" || key == "d")
+                        {
+                            const int delay = a.as_int();
+                            if (static_cast<size_t>(delay) > kMaxDelay) throw std::runtime_error("Error: delay > max delay\n");
+                            dend.delays[lcn.syn_addr] = static_cast<uint8_t>(delay);
+                        }
+                    }
+                }
+                pre.out.push_back(lcn);
+            }
+        }
+    }
+
+    // ---- map_axons  src/chip.cpp:382-408, 1263-1391 -----------------------------
+    // One axon per (pre-neuron, destination core). The reference visits a
+    // neuron's destination cores in std::set<Core*> (heap address) order; that
+    // order only shows in message ids / detailed timing. We use core id order.
+    for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
+        {
+            LNeuron &pre = lcores[c].neurons[i];
+            std::set<uint32_t> dests;
+            for (const LConn &k : pre.out) dests.insert(k.post_core);
+            std::unordered_map<uint32_t, uint32_t> axon_of;
+            for (const uint32_t d : dests)
+            {
+                LAxonIn a;
+                a.src_core = static_cast<uint32_t>(c);
+                a.src_in_core = static_cast<uint32_t>(i);
+                lcores[d].axons_in.push_back(std::move(a));
+                const uint32_t idx = static_cast<uint32_t>(lcores[d].axons_in.size() - 1);
+                axon_of[d] = idx;
+                pre.axons_out.emplace_back(d, idx);
+            }
+            for (size_t k = 0; k < pre.out.size(); ++k)
+                lcores[pre.out[k].post_core].axons_in[axon_of[pre.out[k].post_core]].syn.emplace_back(
+                        static_cast<uint32_t>(k), 0u);
+        }
+    }
+
+    // ---- emit neuron arrays ---------------------------------------------------
+    out.neuron_class.resize(n_neurons);
+    out.neuron_aux.assign(n_neurons, 0);
+    out.neuron_bias.resize(n_neurons);
+    out.neuron_potential0.resize(n_neurons);
+    out.names.resize(n_neurons);
+    out.group_to_device.resize(groups.size());
+    for (size_t gi = 0; gi < groups.size(); ++gi) out.group_to_device[gi].resize(groups[gi]->neurons.size());
+    std::map<std::string, uint32_t> class_index;
+    // neurons sharing an input / HH unit, in update (= in-core) order
+    for (size_t c = 0; c < lcores.size(); ++c)
+        for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
+            lcores[c].units[lcores[c].neurons[i].soma].sharing.push_back(out.cores[c].neuron_begin + static_cast<uint32_t>(i));
+    for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
+        {
+            LNeuron &ln = lcores[c].neurons[i];
+            const uint32_t dev = out.cores[c].neuron_begin + static_cast<uint32_t>(i);
+            out.neuron_class[dev] = intern_soma_class(class_index, out.soma_classes, ln.cls);
+            out.neuron_bias[dev] = ln.bias;
+            out.neuron_potential0[dev] = ln.potential0;
+            out.names[dev] = {ln.group, static_cast<uint32_t>(ln.n->offset), ln.n->log_spikes, ln.n->log_potential};
+            out.group_to_device[ln.group][ln.n->offset] = dev;
+            const UnitState &soma = lcores[c].units[ln.soma];
+            if (soma.model == UnitModel::input)
+            {
+                sfe_input_desc d{};
+                d.spikes_off = static_cast<uint32_t>(out.input_spikes.size());
+                d.spikes_len = static_cast<uint32_t>(soma.spikes.size());
+                out.input_spikes.insert(out.input_spikes.end(), soma.spikes.begin(), soma.spikes.end());
+                d.share_count = static_cast<uint32_t>(soma.sharing.size());
+                d.share_rank = static_cast<uint32_t>(
+                        std::find(soma.sharing.begin(), soma.sharing.end(), dev) - soma.sharing.begin());
+                d.rate = soma.rate;
+                d.poisson = soma.poisson;
+                out.neuron_aux[dev] = static_cast<uint32_t>(out.inputs.size());
+                out.inputs.push_back(d);
+            }
+            else if (soma.model == UnitModel::hodgkin_huxley)
+            {
+                if (soma.sharing.size() != 1)
+                    throw std::runtime_error("hodgkin_huxley keeps one neuron of state per hardware unit "
+                                             "(plugins/hodgkin_huxley.cpp:94-118); map one neuron per unit");
+                out.neuron_aux[dev] = static_cast<uint32_t>(out.hh.size());
+                out.hh.push_back({soma.hh_m, soma.hh_n, soma.hh_h, soma.hh_i});
+            }
+        }
+    }
+    // potential probes in trace order: lexicographic group, offset (src/chip.cpp:1632-1662)
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+        for (const Neuron &n : groups[gi]->neurons)
+            if (n.log_potential) out.probes.push_back(out.group_to_device[gi][n.offset]);
+
+    // ---- emit axons-out (per neuron, in sending order) -------------------------
+    std::vector<uint32_t> core_axon_base(lcores.size());
+    uint32_t axon_total = 0;
+    for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        core_axon_base[c] = axon_total;
+        out.cores[c].axon_in_begin = axon_total;
+        out.cores[c].axon_in_count = static_cast<uint32_t>(lcores[c].axons_in.size());
+        axon_total += out.cores[c].axon_in_count;
+    }
+    out.axon_out_begin.assign(n_neurons + 1, 0);
+    for (size_t c = 0; c < lcores.size(); ++c)
+        for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
+        {
+            const uint32_t dev = out.cores[c].neuron_begin + static_cast<uint32_t>(i);
+            out.axon_out_begin[dev] = static_cast<uint32_t>(out.axon_out_target.size());
+            for (const auto &[d, idx] : lcores[c].neurons[i].axons_out)
+                out.axon_out_target.push_back(core_axon_base[d] + idx);
+        }
+    out.axon_out_begin[n_neurons] = static_cast<uint32_t>(out.axon_out_target.size());
+
+    // ---- emit axons-in + synapses, per destination core -------------------------
+    out.axons_in.resize(axon_total);
+    out.axon_src.resize(axon_total);
+    std::map<CostKey, uint32_t> cost_index;
+    uint64_t syn_total = 0;
+    for (size_t c = 0; c < lcores.size(); ++c)
+        for (const LAxonIn &a : lcores[c].axons_in) syn_total += a.syn.size();
+    out.syn_weight.reserve(syn_total);
+    out.syn_meta.reserve(syn_total);
+    for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        LCore &lc = lcores[c];
+        sfe_core_desc &cd = out.cores[c];
+        cd.syn_begin = out.syn_weight.size();
+        uint32_t max_delay = 0;
+        for (size_t ai = 0; ai < lc.axons_in.size(); ++ai)
+        {
+            const LAxonIn &a = lc.axons_in[ai];
+            const LNeuron &pre = lcores[a.src_core].neurons[a.src_in_core];
+            sfe_axon_in &rec = out.axons_in[core_axon_base[c] + ai];
+            rec.syn_off = static_cast<uint32_t>(out.syn_weight.size() - cd.syn_begin);
+            rec.syn_count = static_cast<uint32_t>(a.syn.size());
+            rec.hop = pack_hop(arch.tiles[out.cores[a.src_core].tile], arch.tiles[cd.tile]);
+            out.axon_src[core_axon_base[c] + ai] = out.cores[a.src_core].neuron_begin + a.src_in_core;
+            bool uniform = true;
+            CostKey first{};
+            CostKey total{};
+            total.per_message = 1;
+            for (size_t s = 0; s < a.syn.size(); ++s)
+            {
+                const LConn &k = pre.out[a.syn[s].first];
+                const LNeuron &post = lc.neurons[k.post_in_core];
+                const PipelineUnitConfiguration &syn_cfg = lc.cfg->pipeline_hw[k.syn.family];
+                const PipelineUnitConfiguration &den_cfg = lc.cfg->pipeline_hw[post.dend.family];
+                CostKey key{};
+                key.v[0] = unit_double(syn_cfg, "energy_process_spike", "Synapse");
+                key.v[1] = unit_double(syn_cfg, "latency_process_spike", "Synapse");
+                if (cd.dend_in_msg != 0)
+                {
+                    key.v[2] = unit_double(den_cfg, "energy_update", "Dendrite");
+                    key.v[3] = unit_double(den_cfg, "latency_update", "Dendrite");
+                }
+                if (s == 0) first = key;
+                else if (std::memcmp(first.v, key.v, sizeof(key.v)) != 0) uniform = false;
+                // per-message totals in the reference's summation order
+                // (src/chip.cpp:766-789: per synapse (0.0 + syn) + den, then message += that)
+                total.v[0] += key.v[0];
+                total.v[2] += key.v[2];
+                total.v[1] += (0.0 + key.v[1]) + key.v[3];
+                const UnitState &dend = lc.units[post.dend];
+                uint32_t delay = 0;
+                if (dend.model == UnitModel::accumulator_with_delay && k.syn_addr < dend.delays.size())
+                    delay = dend.delays[k.syn_addr];
+                max_delay = std::max(max_delay, delay);
+                out.syn_weight.push_back(k.weight);
+                out.syn_meta.push_back(k.post_in_core | (delay << 16));
+            }
+            rec.cost_class = uniform ? intern_cost(cost_index, out.cost_classes, first, true)
+                                     : intern_cost(cost_index, out.cost_classes, total, false);
+        }
+        cd.syn_count = out.syn_weight.size() - cd.syn_begin;
+        cd.ring = max_delay + 1;
+        if (cd.syn_count > 0xffffffffull) throw std::runtime_error("more than 2^32 synapses on one core");
+        // exactness certificate: every weight is k * 2^-s and the
+        // per-post-neuron sums stay small enough for integer smem accumulators
+        const int shift = exact_shift(out.syn_weight, cd.syn_begin, cd.syn_begin + cd.syn_count);
+        cd.acc_mode = SFE_ACC_ORDERED;
+        cd.weight_shift = 0;
+        if (shift >= 0)
+        {
+            std::vector<double> sum_abs(lc.neurons.size(), 0.0);
+            std::vector<uint64_t> fan_in(lc.neurons.size(), 0);
+            for (uint64_t s = cd.syn_begin; s < cd.syn_begin + cd.syn_count; ++s)
+            {
+                const uint32_t post = SFE_SYN_POST(out.syn_meta[s]);
+                sum_abs[post] += std::fabs(std::ldexp(out.syn_weight[s], shift));
+                fan_in[post] += 1;
+            }
+            double worst_sum = 0.0;
+            uint64_t worst_fan = 0;
+            for (size_t i = 0; i < sum_abs.size(); ++i)
+            {
+                worst_sum = std::max(worst_sum, sum_abs[i]);
+                worst_fan = std::max(worst_fan, fan_in[i]);
+            }
+            cd.weight_shift = shift;
+            if (worst_sum < 524288.0 && worst_fan < 4096) cd.acc_mode = SFE_ACC_PACKED32;
+            else if (worst_sum < 2147483648.0) cd.acc_mode = SFE_ACC_DUAL32;
+        }
+    }
+    if (out.cost_classes.empty()) out.cost_classes.push_back(sfe_cost_class{});
+    if (out.soma_classes.empty()) out.soma_classes.push_back(sfe_soma_class{});
+    out.finalize_view(arch);
+}
+
+void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bool materialize, HostTables &out)
+{
+    out = HostTables{};
+    fill_arch_tables(arch, out);
+    const sfe_synth_spec &s = req.spec;
+    const std::vector<const CoreConfiguration *> core_cfgs = arch.cores();
+    const uint32_t C = s.cores, P = s.neurons_per_core, D = s.dest_cores, S = s.syn_per_axon;
+    if (C == 0 || C > core_cfgs.size()) throw HardwareMappingError("synthetic network needs more cores than the architecture has");
+    if (P == 0 || (P & (P - 1)) != 0 || P > 4096) throw std::invalid_argument("synthetic: neurons_per_core must be a power of two <= 4096");
+    if (D > C || S > P) throw std::invalid_argument("synthetic: dest_cores <= cores and syn_per_axon <= neurons_per_core");
+    if (s.max_delay > kMaxDelay) throw std::runtime_error("Error: delay > max delay\n");
+    if (static_cast<uint64_t>(P) * D * S > 0xffffffffull) throw std::runtime_error("more than 2^32 synapses on one core");
+
+    // All cores share one hardware description in practice; resolve units per core
+    // anyway so that errors surface exactly as for a described network.
+    sfe_soma_class cls{};
+    sfe_cost_class cost{};
+    for (uint32_t c = 0; c < C; ++c)
+    {
+        const CoreConfiguration &cfg = *core_cfgs[c];
+        if (P > cfg.pipeline.max_neurons_supported) throw HardwareMappingError("Error: Exceeded maximum neurons per core.");
+        check_buffer_position(cfg);
+        const UnitKey dk = get_hw(cfg, req.dendrite_hw_name, false, true, false);
+        const UnitKey sk = get_hw(cfg, req.soma_hw_name, false, false, true);
+        const UnitKey yk = get_hw(cfg, req.synapse_hw_name, true, false, false);
+        const PipelineUnitConfiguration &den_cfg = cfg.pipeline_hw[dk.family];
+        const PipelineUnitConfiguration &soma_cfg = cfg.pipeline_hw[sk.family];
+        const PipelineUnitConfiguration &syn_cfg = cfg.pipeline_hw[yk.family];
+        const UnitModel dm = parse_model(den_cfg);
+        if (parse_model(soma_cfg) != UnitModel::lif) throw std::runtime_error("synthetic: soma unit must be leaky_integrate_fire");
+        if (parse_model(syn_cfg) != UnitModel::current_based) throw std::runtime_error("synthetic: synapse unit must be current_based");
+        if (dm != UnitModel::accumulator && dm != UnitModel::accumulator_with_delay)
+            throw std::runtime_error("synthetic: dendrite unit must be an accumulator");
+        if (P > kLifMaxCompartments) throw std::out_of_range("soma unit '" + soma_cfg.name + "' is full");
+        sfe_soma_class k{};
+        soma_defaults(soma_cfg, UnitModel::lif, k);
+        k.threshold = s.threshold;
+        k.reset = s.reset;
+        k.leak = s.leak_decay;
+        k.dend_model = dm == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR : SFE_DEND_ACCUMULATOR_DELAY;
+        k.dend_in_neuron = cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit ? 1 : 0;
+        if (k.dend_in_neuron != 0)
+        {
+            k.dend_energy_update = unit_double(den_cfg, "energy_update", "Dendrite");
+            k.dend_latency_update = unit_double(den_cfg, "latency_update", "Dendrite");
+        }
+        sfe_cost_class q{};
+        q.syn_energy = unit_double(syn_cfg, "energy_process_spike", "Synapse");
+        q.syn_latency = unit_double(syn_cfg, "latency_process_spike", "Synapse");
+        if (out.cores[c].dend_in_msg != 0)
+        {
+            q.den_energy = unit_double(den_cfg, "energy_update", "Dendrite");
+            q.den_latency = unit_double(den_cfg, "latency_update", "Dendrite");
+        }
+        if (c == 0)
+        {
+            cls = k;
+            cost = q;
+        }
+        else if (std::memcmp(&cls, &k, sizeof(k)) != 0 || std::memcmp(&cost, &q, sizeof(q)) != 0)
+            throw std::runtime_error("synthetic: the mapped cores must share one hardware description");
+        // without a delay line the dendrite cannot hold delays
+        if (s.max_delay > 0 && dm != UnitModel::accumulator_with_delay)
+            throw std::runtime_error("synthetic: max_delay > 0 needs an accumulator_with_delay dendrite");
+    }
+    out.soma_classes.push_back(cls);
+    out.cost_classes.push_back(cost);
+
+    const uint32_t N = C * P;
+    out.group_names = {"pop"};
+    out.group_to_device.resize(1);
+    out.group_to_device[0].resize(N);
+    out.names.resize(N);
+    out.neuron_class.assign(N, 0);
+    out.neuron_aux.assign(N, 0);
+    out.neuron_bias.resize(N);
+    out.neuron_potential0.assign(N, 0.0);
+    for (uint32_t n = 0; n < N; ++n)
+    {
+        out.neuron_bias[n] = sfe_synth_has_bias(&s, n) ? s.bias : 0.0;
+        out.names[n] = {0, n, s.log_spikes != 0, n < s.log_potential_n};
+        out.group_to_device[0][n] = n;
+        if (n < s.log_potential_n) out.probes.push_back(n);
+    }
+    // Sources of destination core d, ascending core id: {(d - k) mod C, k < D}.
+    // rank_of(d, src) = position of src in that sorted list.
+    auto rank_of = [&](uint32_t d, uint32_t src) -> uint32_t {
+        if (D == C) return src;
+        if (d + 1 >= D) return src - (d + 1 - D);          // no wrap: sources d-D+1 .. d
+        const uint32_t wrapped = D - 1 - d;                // sources 0..d and C-wrapped..C-1
+        return src <= d ? src : (d + 1) + (src - (C - wrapped));
+    };
+    const uint32_t axons_per_core = P * D;
+    out.axons_in.resize(static_cast<size_t>(C) * axons_per_core);
+    out.axon_src.resize(out.axons_in.size());
+    out.axon_out_begin.resize(N + 1);
+    out.axon_out_target.resize(static_cast<size_t>(N) * D);
+    for (uint32_t c = 0; c < C; ++c)
+    {
+        sfe_core_desc &cd = out.cores[c];
+        cd.neuron_begin = c * P;
+        cd.neuron_count = P;
+        cd.axon_in_begin = c * axons_per_core;
+        cd.axon_in_count = axons_per_core;
+        cd.syn_begin = static_cast<uint64_t>(c) * axons_per_core * S;
+        cd.syn_count = static_cast<uint64_t>(axons_per_core) * S;
+        cd.ring = s.max_delay + 1;
+        cd.weight_shift = 0;
+        cd.acc_mode = SFE_ACC_DUAL32; // refined below / re-certified on the device
+    }
+    for (uint32_t n = 0; n < N; ++n)
+    {
+        const uint32_t home = n / P;
+        out.axon_out_begin[n] = n * D;
+        for (uint32_t k = 0; k < D; ++k)
+        {
+            const uint32_t d = sfe_synth_dest_core(&s, home, k);
+            const uint32_t slot = rank_of(d, home) * P + (n % P);
+            const uint32_t axon_id = d * axons_per_core + slot;
+            out.axon_out_target[static_cast<size_t>(n) * D + k] = axon_id;
+            sfe_axon_in &rec = out.axons_in[axon_id];
+            rec.syn_off = slot * S;
+            rec.syn_count = S;
+            rec.hop = pack_hop(arch.tiles[out.cores[home].tile], arch.tiles[out.cores[d].tile]);
+            rec.cost_class = 0;
+            out.axon_src[axon_id] = n;
+        }
+    }
+    out.axon_out_begin[N] = N * D;
+    // NOTE: the reference orders a neuron's axons-out by std::set<Core*>; we send
+    // in k order (home, home+1, ...). Only message ids / detailed timing see it.
+
+    out.synth = s;
+    if (materialize)
+    {
+        const uint64_t total = static_cast<uint64_t>(C) * axons_per_core * S;
+        out.syn_weight.resize(total);
+        out.syn_meta.resize(total);
+        for (uint32_t n = 0; n < N; ++n)
+        {
+            for (uint32_t k = 0; k < D; ++k)
+            {
+                const uint64_t axon = static_cast<uint64_t>(n) * D + k;
+                const uint32_t axon_id = out.axon_out_target[axon];
+                const uint32_t d = axon_id / axons_per_core;
+                const uint64_t base = out.cores[d].syn_begin + out.axons_in[axon_id].syn_off;
+                const sfe_synth_axon ap = sfe_synth_axon_params(&s, axon);
+                for (uint32_t j = 0; j < S; ++j)
+                {
+                    const uint64_t syn = axon * S + j;
+                    out.syn_weight[base + j] = static_cast<double>(sfe_synth_weight(&s, syn));
+                    out.syn_meta[base + j] = sfe_synth_post(&s, &ap, j) | (sfe_synth_delay(&s, syn) << 16);
+                }
+            }
+        }
+    }
+    // exactness certificate from the generator's bounds: integer weights, fan-in
+    // per (post, core) is at most P*D (every source neuron of every source core
+    // hits a post at most once per axon)
+    {
+        const double wmax = static_cast<double>(std::max(std::abs(s.w_min), std::abs(s.w_max)));
+        const double fan_bound = static_cast<double>(P) * D; // axons into the core; each hits a post <= once
+        const uint32_t mode = (fan_bound < 4096.0 && fan_bound * wmax < 524288.0) ? SFE_ACC_PACKED32
+                : (fan_bound * wmax < 2147483648.0)                                ? SFE_ACC_DUAL32
+                                                                                   : SFE_ACC_ORDERED;
+        for (uint32_t c = 0; c < C; ++c) out.cores[c].acc_mode = mode;
+    }
+    out.finalize_view(arch);
+}
+
+bool patch_neuron_attribute(HostTables &t, const uint32_t neuron, const std::string &name, const double value)
+{
+    if (neuron >= t.neuron_class.size()) throw std::out_of_range("neuron index out of range");
+    if (name == "bias")
+    {
+        t.neuron_bias[neuron] = value;
+        return false;
+    }
+    sfe_soma_class c = t.soma_classes[t.neuron_class[neuron]];
+    if (name == "threshold") c.threshold = value;
+    else if (name == "reverse_threshold") c.reverse_threshold = value;
+    else if (name == "reset") c.reset = value;
+    else if (name == "reverse_reset") c.reverse_reset = value;
+    else if (name == "leak_decay" || name == "leak") c.leak = value;
+    else if (name == "input_decay") c.input_decay = value;
+    else return false; // unknown attributes are ignored by the built-in models (SURVEY B-13)
+    // split the class: find an identical one or append
+    for (size_t i = 0; i < t.soma_classes.size(); ++i)
+    {
+        if (std::memcmp(&t.soma_classes[i], &c, sizeof(c)) == 0)
+        {
+            t.neuron_class[neuron] = static_cast<uint32_t>(i);
+            return true;
+        }
+    }
+    t.soma_classes.push_back(c);
+    t.neuron_class[neuron] = static_cast<uint32_t>(t.soma_classes.size() - 1);
+    t.view.soma_classes = t.soma_classes.data();
+    t.view.n_soma_classes = static_cast<uint32_t>(t.soma_classes.size());
+    return true;
+}
+
+} // namespace sfe
