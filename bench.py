@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the SANA-FE time-step hot path on B200.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+synthetic random LIF network on a loihi_large-shaped chip — 1,048,576 neurons on
+1024 cores x 1024, fan-out 1000 (8 destination cores x 125 synapses) = 1.05e9
+synapses, ~10 % of neurons firing per step, simple timing model. A "step" is one
+simulated timestep (neuron phase -> message phase -> energy/timing reduction).
+
+  value   synaptic events/s over the timed steps, network resident in HBM
+  e2e     same metric through the public API with HOST buffers every step: the
+          per-neuron bias vector goes host->device (the reference's per-frame
+          MappedNeuron.set_attributes pattern, scripts/tcad2025/dvs_gesture.py) and
+          the spike raster + step record come back device->host
+  roofline  message-phase kernel (fanout_kernel): algorithmic bytes 12 B/synaptic
+          event + 16 B/message over its CUDA-event duration
+  cpu_baseline  the reference's own C++ simulator (oracle/_ref/sanafe_ref, built
+          unmodified from the reference sources) on a bounded sample of the same
+          generator, all host cores
+
+`--impl reference` times only that CPU reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "sana-fe_b200"))
+
+METRIC = "synaptic_events_per_s"
+UNIT = "synaptic events/s"
+WORKLOAD = "synthetic LIF, loihi_large: 1024 cores x 1024 neurons, fan-out 8x125, ~10% activity, simple timing"
+
+FULL = dict(cores=1024, neurons_per_core=1024, dest_cores=8, syn_per_axon=125, seed=1, bias_permille=100,
+            bias=128.0, threshold=64.0, reset=0.0, leak_decay=0.9, w_min=-9, w_max=8, max_delay=0,
+            log_spikes=0, log_potential_n=0)
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sanafe_ref")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def sample_spec(cores):
+    """Bounded sample of the same generator for the CPU reference: `cores` of the
+    1024 cores, everything else (neurons/core, fan-in 1000 per neuron, weights) unchanged."""
+    s = dict(FULL)
+    s["cores"] = cores
+    s["dest_cores"] = min(FULL["dest_cores"], cores)
+    s.update(soma_hw_name="loihi_lif", synapse_hw_name="loihi_dense_synapse", dendrite_hw_name="loihi_dendrites_delay")
+    return s
+
+
+def run_reference_sample(steps, warmup, cores=8):
+    """The reference's own simulator (CPU, OpenMP over cores, -N = all host cores)."""
+    from sanafe_b200 import archgen
+    threads = os.cpu_count() or 1
+    if not os.path.exists(REF_BIN):
+        return None
+    tmp = tempfile.mkdtemp(prefix="sfe_ref_")
+    flat = os.path.join(tmp, "sample.jsonl")
+    archgen.write_flat(archgen.loihi_large(tiles=(cores + 3) // 4), flat, synth=sample_spec(cores))
+    out = os.path.join(tmp, "out")
+    reps = 2 if warmup > 0 else 1
+    res = subprocess.run([REF_BIN, flat, "--steps", str(steps), "--timing", "simple", "--threads", str(threads),
+                          "--out", out, "--reps", str(reps)], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stderr[-2000:])
+        return None
+    with open(os.path.join(out, "summary.json")) as f:
+        summ = json.load(f)
+    wall = summ["sim_wall_s"]  # last sim() call (earlier ones warm up); load/mapping excluded
+    return {"value": summ["spikes"] / wall, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"{cores} of 1024 cores (8192 neurons x fan-out {FULL['dest_cores'] * FULL['syn_per_axon']}, "
+                      f"{summ['synapses']} synapses), {steps} steps (after {reps - 1} warm-up sim() call), "
+                      f"{summ['spikes']} synaptic events, {wall:.3f} s",
+            "ms_per_step": 1e3 * wall / steps, "steps_per_s": steps / wall}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    base = run_reference_sample(max(args.steps, 1), args.warmup)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/sanafe_ref not built (needs /root/reference)"}))
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cores", type=int, default=FULL["cores"], help="scale the workload down (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import sanafe_b200 as sfe
+    from sanafe_b200 import archgen
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    L = sfe.lib()
+    if L.sfe_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+
+    spec_d = dict(FULL)
+    spec_d["cores"] = args.cores
+    spec_d["dest_cores"] = min(spec_d["dest_cores"], args.cores)
+    spec_d["seed"] = FULL["seed"] + rank  # N>1: independent replicas (weak scaling), see DESIGN.md
+    spec = sfe.SynthSpec(**spec_d)
+    tmp = tempfile.mkdtemp(prefix="sfe_bench_")
+    flat = os.path.join(tmp, "arch.jsonl")
+    archgen.write_flat(archgen.loihi_large(tiles=max(1, (args.cores + 3) // 4) if args.cores < 4096 else 1024), flat)
+    arch, _ = sfe.load_flat(flat)
+    chip = sfe.SpikingChip(arch, device=local_rank)
+    t0 = time.time()
+    chip.load_synthetic(spec, generate_on_device=True)
+    load_s = time.time() - t0
+    eng = chip.engine
+    tb = chip.tables
+    n = tb.n_neurons
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident throughput ------------------------------------------------
+    rd = sfe.RunData()
+    assert L.sfe_engine_enqueue(eng, args.warmup) == 0, L.sfe_last_error()
+    assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = L.sfe_engine_launch_count(eng)
+    ms_total, ms_fan = C.c_float(), C.c_float()
+    assert L.sfe_engine_time_begin(eng) == 0
+    assert L.sfe_engine_enqueue(eng, args.steps) == 0, L.sfe_last_error()
+    assert L.sfe_engine_time_end(eng, C.byref(ms_total), C.byref(ms_fan)) == 0, L.sfe_last_error()
+    launches = L.sfe_engine_launch_count(eng) - launches0
+    clocks = sampler.stop()
+    assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
+    events, messages = rd.spikes, rd.packets_sent
+    seconds = ms_total.value / 1e3
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([seconds], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(events), float(messages), float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        seconds = float(tmax.item())
+        events_all, messages_all, launches_all = (int(x) for x in tot.tolist())
+    else:
+        events_all, messages_all, launches_all = events, messages, launches
+    value = events_all / seconds
+
+    # ---- roofline of the dominant kernel (message phase) -----------------------------
+    peak, peak_src = peaks()
+    fan_bytes = 12.0 * events + 16.0 * messages          # per rank, over args.steps launches
+    fan_s = ms_fan.value / 1e3
+    achieved = fan_bytes / fan_s / 1e9 if fan_s > 0 else 0.0
+    step_bytes = fan_bytes + 48.0 * n * args.steps
+    roofline = {"bound": "hbm", "kernel": "fanout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms_per_launch": ms_fan.value / max(args.steps, 1),
+                "kernel_share_of_step": ms_fan.value / ms_total.value if ms_total.value > 0 else None,
+                "algorithmic_bytes_per_launch": fan_bytes / max(args.steps, 1),
+                "whole_step": {"achieved": step_bytes / (ms_total.value / 1e3) / 1e9,
+                               "frac": step_bytes / (ms_total.value / 1e3) / 1e9 / peak,
+                               "bytes_per_step": step_bytes / max(args.steps, 1)}}
+
+    # ---- end to end through the public API with host buffers ---------------------------
+    bias = np.array([tb.neuron_bias[i] for i in range(0, n)], dtype=np.float64) if n <= 4096 else \
+        np.ctypeslib.as_array(tb.neuron_bias, shape=(n,)).copy()
+    e2e_steps = max(10, min(args.steps, 100))
+    words = (n + 31) // 32
+    barrier()
+    e2e_events = 0
+    t_e2e = time.perf_counter()
+    for s in range(e2e_steps):
+        assert L.sfe_engine_set_bias(eng, bias.ctypes.data, n) == 0
+        rde, tr = chip.sim_raw(1, "simple", steps=True, fired=True)
+        e2e_events += rde.spikes
+    e2e_s = time.perf_counter() - t_e2e
+    if dist is not None:
+        import torch
+        tmax = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(e2e_events)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        e2e_s, e2e_events = float(tmax.item()), int(tot.item())
+    e2e = {"value": e2e_events / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * words + 88,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+
+    if rank != 0:
+        return 0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = run_reference_sample(20, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.cores == FULL["cores"] else f"DEBUG scale: {args.cores} cores",
+                   "neurons": n * world, "synapses": int(tb.n_synapses) * world, "timing_model": "simple",
+                   "l2_policy": "inputs larger than L2 (12.6 GB of synapse tables per GPU; ~1.2 GB streamed per step)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)",
+                   "activity": rd.neurons_fired / float(n * args.steps), "load_s": load_s},
+        "timesteps_per_s": args.steps / seconds, "events_per_step": events_all / args.steps,
+        "roofline": roofline,
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

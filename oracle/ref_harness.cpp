@@ -499,13 +499,19 @@ static Loaded load_flat(const std::string &path)
             m.latency_message_out = r.at(3).d();
             core->create_axon_out(r.at(1).s(), m);
         }
-        else if (kind == "unit")
+        else if (kind == "unit" || kind == "unit_range")
         {
             // ["unit", section, name, {model, plugin?, log_energy, log_latency,
             //   update_every_timestep, attrs:{...}}]
+            // ["unit_range", section, base, first, last, {...}] = base[first..last]
+            const bool is_range = (kind == "unit_range");
             const std::string &section = r.at(1).s();
-            const std::string &name = r.at(2).s();
-            const JVal &a = r.at(3);
+            const JVal &a = is_range ? r.at(5) : r.at(3);
+            const long long first = is_range ? r.at(3).i() : 0;
+            const long long last = is_range ? r.at(4).i() : 0;
+            for (long long ui = first; ui <= last; ++ui)
+            {
+            const std::string name = is_range ? r.at(2).s() + "[" + std::to_string(ui) + "]" : r.at(2).s();
             sanafe::ModelInfo mi;
             mi.name = a.at("model").s();
             if (const JVal *p = a.find("plugin")) mi.plugin_library_path = p->s();
@@ -529,6 +535,7 @@ static Loaded load_flat(const std::string &path)
                 }
             }
             if (!exists) set_flag(core->create_hardware_unit(name, mi), section);
+            }
         }
         else if (kind == "end_arch")
         {
@@ -811,7 +818,7 @@ int main(int argc, char **argv)
                 const double w = std::chrono::duration<double>(clk::now() - w0).count();
                 walls.push_back(w);
                 wall_sum += w;
-                best_wall = std::min(best_wall, w);
+                best_wall = w; // earlier calls are warm-up: report the LAST call (its RunData is what we print)
             }
         }
         std::ofstream sf(out_dir + "/summary.json");

@@ -166,6 +166,20 @@ def convert_core(core, name, flat, plugin_map):
         for unit in as_list(core[section]):
             uname = unit["name"]
             u0, u1 = parse_range(uname) if ".." in uname else (0, 0)
+            if ".." in uname and section not in ("axon_in", "axon_out"):
+                # keep name[a..b] as ONE record (loihi.yaml has 1024 input units per core)
+                ua = unit["attributes"]
+                info = {"model": str(ua["model"]),
+                        "log_energy": to_bool(ua["log_energy"]) if "log_energy" in ua else False,
+                        "log_latency": to_bool(ua["log_latency"]) if "log_latency" in ua else False,
+                        "update_every_timestep": to_bool(ua["update_every_timestep"])
+                        if "update_every_timestep" in ua else False,
+                        "attrs": model_attributes(ua)}
+                if "plugin" in ua:
+                    p = str(ua["plugin"])
+                    info["plugin"] = (plugin_map or {}).get(p, p)
+                flat.emit("unit_range", section, uname.split("[")[0], u0, u1, info)
+                continue
             for u in range(u0, u1 + 1):
                 full = uname.split("[")[0] + f"[{u}]" if ".." in uname else uname
                 ua = unit["attributes"]

@@ -896,6 +896,10 @@ struct sfe_engine
     void *pinned{nullptr};
     size_t pinned_bytes{0};
     cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
+    // per-launch timing of the message-phase kernel between time_begin/time_end
+    bool timing{false};
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used{0};
     bool ordered_any{false}, dual_any{false};
 
     template <typename T> int alloc(T **p, size_t count)
@@ -1183,6 +1187,7 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
     if (e->ev_end != nullptr) cudaEventDestroy(e->ev_end);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->own_stream && e->stream != nullptr) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1210,8 +1215,24 @@ static int enqueue_step(sfe_engine *e, bool probes)
     }
     if (!e->fanout_list.empty())
     {
+        const bool timed = e->timing && e->ev_used + 2 <= 8192;
+        if (timed)
+        {
+            while (e->ev_pool.size() < e->ev_used + 2)
+            {
+                cudaEvent_t ev;
+                cudaEventCreate(&ev);
+                e->ev_pool.push_back(ev);
+            }
+            cudaEventRecord(e->ev_pool[e->ev_used], e->stream);
+        }
         fanout_kernel<<<static_cast<unsigned>(e->fanout_list.size()), kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s);
         ++e->launches;
+        if (timed)
+        {
+            cudaEventRecord(e->ev_pool[e->ev_used + 1], e->stream);
+            e->ev_used += 2;
+        }
     }
     finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
     ++e->launches;
@@ -1492,6 +1513,8 @@ extern "C" size_t sfe_engine_device_bytes(const sfe_engine *e)
 extern "C" int sfe_engine_time_begin(sfe_engine *e)
 {
     SFE_CUDA(cudaSetDevice(e->device));
+    e->timing = true;
+    e->ev_used = 0;
     SFE_CUDA(cudaEventRecord(e->ev_begin, e->stream));
     return 0;
 }
@@ -1504,7 +1527,16 @@ extern "C" int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fan
     float ms = 0.f;
     SFE_CUDA(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));
     if (ms_total != nullptr) *ms_total = ms;
-    if (ms_fanout != nullptr) *ms_fanout = 0.f;
+    float fan = 0.f;
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2)
+    {
+        float x = 0.f;
+        SFE_CUDA(cudaEventElapsedTime(&x, e->ev_pool[i], e->ev_pool[i + 1]));
+        fan += x;
+    }
+    if (ms_fanout != nullptr) *ms_fanout = fan;
+    e->timing = false;
+    e->ev_used = 0;
     return 0;
 }
 

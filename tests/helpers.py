@@ -129,3 +129,97 @@ def load_ref_spikes(out_dir):
 
 def rundata_dict(rd):
     return {name: getattr(rd, name) for name, _ in rd._fields_}
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures (tests/golden/, generated by make_goldens.py from the reference)
+# ---------------------------------------------------------------------------
+import gzip
+import hashlib
+import tempfile
+
+GOLDEN_CASES = ["example", "dvs", "hh", "synth_small", "synth_delay", "synth_quirk", "synth_soma", "truenorth", "frac"]
+_flat_cache = {}
+
+
+def golden_flat(name):
+    """Path of the flat description of a golden case (gunzipped to a temp file if needed)."""
+    plain = os.path.join(GOLDEN, name + ".jsonl")
+    if os.path.exists(plain):
+        return plain
+    if name not in _flat_cache:
+        tmp = tempfile.NamedTemporaryFile(prefix=name + "_", suffix=".jsonl", delete=False)
+        with gzip.open(plain + ".gz", "rb") as f:
+            tmp.write(f.read())
+        tmp.close()
+        _flat_cache[name] = tmp.name
+    return _flat_cache[name]
+
+
+def golden(name):
+    with open(os.path.join(GOLDEN, name + ".golden.json")) as f:
+        return json.load(f)
+
+
+def golden_spikes(name):
+    plain = os.path.join(GOLDEN, name + ".spikes.txt")
+    if os.path.exists(plain):
+        with open(plain) as f:
+            return f.read()
+    with gzip.open(plain + ".gz", "rt") as f:
+        return f.read()
+
+
+def load_chip(name, device):
+    cwd = os.getcwd()
+    os.chdir(ROOT)  # plugin paths inside flat files are relative to the repo root
+    try:
+        arch, net = sfe.load_flat(golden_flat(name))
+        chip = sfe.SpikingChip(arch, device=device)
+        chip.load(net)
+    finally:
+        os.chdir(cwd)
+    return chip
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.where(a == b, 0.0, np.abs(a - b) / scale))) if a.size else 0.0
+
+
+def check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9):
+    """Spike raster + counters bit-exact, potentials to `potential_rtol` (0 = bit-exact),
+    energy / latency to `energy_rtol` (north_star: 1e-6), against the reference's outputs."""
+    g = golden(name)
+    s = g["summary"]
+    for key in ("spikes", "packets_sent", "neurons_updated", "neurons_fired"):
+        assert getattr(rd, key) == s[key], (name, key, getattr(rd, key), s[key])
+    for key in ("total_energy", "synapse_energy", "dendrite_energy", "soma_energy", "network_energy", "sim_time"):
+        assert rel_err(getattr(rd, key), s[key]) <= energy_rtol, (name, key, getattr(rd, key), s[key])
+    ps = g["per_step"]
+    st = out["steps"]
+    for key, col in (("fired", "neurons_fired"), ("updated", "neurons_updated"), ("packets", "packets_sent"),
+                     ("spikes", "spike_count")):
+        assert np.array_equal(st[col], np.asarray(ps[key], dtype=np.int64)), (name, key)
+    for key in ("sim_time", "synapse_energy", "dendrite_energy", "soma_energy", "network_energy", "total_energy"):
+        assert rel_err(st[key], ps[key]) <= energy_rtol, (name, key, rel_err(st[key], ps[key]))
+    text = chip.format_spikes(out["fired_bits"], 1)
+    assert text.count("\n") == g["spike_rows"], (name, text.count("\n"), g["spike_rows"])
+    assert hashlib.md5(text.encode()).hexdigest() == g["spikes_md5"], name
+    assert text == golden_spikes(name), name
+    if "potentials_shape" in g:
+        pots = out["potentials"]
+        assert list(pots.shape) == g["potentials_shape"], (name, pots.shape)
+        full = os.path.join(GOLDEN, name + ".potentials.npy")
+        if potential_rtol == 0.0:
+            sha = hashlib.sha256(np.ascontiguousarray(pots, dtype="<f8").tobytes()).hexdigest()
+            if sha != g["potentials_sha256"] and os.path.exists(full):
+                ref = np.load(full)
+                bad = np.argwhere(ref != pots)
+                raise AssertionError((name, "potentials differ", bad[:5].tolist(), rel_err(pots, ref)))
+            assert sha == g["potentials_sha256"], name
+        else:
+            ref = np.load(full)
+            assert rel_err(pots, ref) <= potential_rtol, (name, rel_err(pots, ref))

@@ -1,0 +1,94 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against
+(a) golden outputs of the reference itself and (b) the CPU restatement on larger
+seeded synthetic networks. Bit-exact rasters / counters / potentials; energy and
+latency to 1e-9 relative (north_star allows 1e-6); Hodgkin-Huxley potentials to
+1e-9 relative (device exp/pow vs glibc)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import sanafe_b200 as sfe
+from helpers import GOLDEN_CASES, Oracle, check_against_golden, golden, load_chip, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_engine_matches_reference(name):
+    chip = load_chip(name, device=0)
+    g = golden(name)
+    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+    check_against_golden(name, chip, rd, out, potential_rtol=1e-9 if name == "hh" else 0.0, energy_rtol=1e-9)
+    assert abs(chip.get_power() - g["summary"]["power"]) <= 1e-9 * abs(g["summary"]["power"])
+
+
+def test_sim_calls_continue_state():
+    """sim() twice == sim() once (state and the timestep counter persist, src/chip.cpp:481,553)."""
+    a = load_chip("synth_delay", device=0)
+    b = load_chip("synth_delay", device=0)
+    rd_a, out_a = a.sim_raw(40, steps=True, fired=True, potentials=True)
+    rd_b1, out_b1 = b.sim_raw(15, steps=True, fired=True, potentials=True)
+    rd_b2, out_b2 = b.sim_raw(25, steps=True, fired=True, potentials=True)
+    assert rd_b2.timestep_start == 16
+    assert np.array_equal(out_a["fired_bits"], np.concatenate([out_b1["fired_bits"], out_b2["fired_bits"]]))
+    assert np.array_equal(out_a["potentials"], np.concatenate([out_b1["potentials"], out_b2["potentials"]]))
+    assert rd_a.spikes == rd_b1.spikes + rd_b2.spikes
+
+
+def synth_spec(**kw):
+    base = dict(cores=32, neurons_per_core=256, dest_cores=6, syn_per_axon=48, seed=11, bias_permille=100,
+                bias=128.0, threshold=64.0, reset=0.0, leak_decay=0.9, w_min=-8, w_max=8, max_delay=0,
+                log_spikes=1, log_potential_n=512)
+    base.update(kw)
+    return sfe.SynthSpec(**base)
+
+
+def loihi_large_flat(tmp_path, tiles):
+    """loihi_large-shaped architecture from the generated-architecture helper."""
+    from sanafe_b200 import archgen
+    path = str(tmp_path / "arch.jsonl")
+    archgen.write_flat(archgen.loihi_large(tiles=tiles), path)
+    return path
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(max_delay=3, seed=5), dict(neurons_per_core=1024, syn_per_axon=125, dest_cores=8, cores=16)])
+def test_device_generated_synthetic_matches_restatement(tmp_path, kw):
+    """Bulk path: synapses generated on the device from the spec == the same network
+    materialised on the host and run through the CPU restatement."""
+    spec = synth_spec(**kw)
+    arch, _ = sfe.load_flat(loihi_large_flat(tmp_path, tiles=(spec.cores + 3) // 4))
+    dev = sfe.SpikingChip(arch, device=0)
+    dev.load_synthetic(spec, generate_on_device=True)
+    host = sfe.SpikingChip(arch, device=-1)
+    host.load_synthetic(spec, generate_on_device=False)
+    steps = 25
+    rd_d, out_d = dev.sim_raw(steps, steps=True, fired=True, potentials=True)
+    rd_h, out_h = Oracle(host).run(steps)
+    assert np.array_equal(out_d["fired_bits"], out_h["fired_bits"])
+    assert np.array_equal(out_d["potentials"], out_h["potentials"])
+    for key in ("neurons_fired", "neurons_updated", "packets_sent", "total_hops", "spike_count"):
+        assert np.array_equal(out_d["steps"][key], out_h["steps"][key]), key
+    for key in ("sim_time", "total_energy", "synapse_energy", "soma_energy", "network_energy"):
+        assert rel_err(out_d["steps"][key], out_h["steps"][key]) <= 1e-9, key
+    assert rd_d.spikes == rd_h.spikes and rd_d.spikes > 0
+
+
+def test_bias_patch_and_reset():
+    """MappedNeuron.set_attributes(bias) between sim() calls + reset() (scripts/tcad2025/dvs_gesture.py loop)."""
+    chip = load_chip("synth_soma", device=0)
+    ref = load_chip("synth_soma", device=-1)
+    oracle = Oracle(ref)
+    n = chip.tables.n_neurons
+    bias = np.array([chip.tables.neuron_bias[i] for i in range(n)])
+    for round_ in range(3):
+        rd_d, out_d = chip.sim_raw(10, steps=True, fired=True, potentials=True)
+        rd_h, out_h = oracle.run(10)
+        assert np.array_equal(out_d["fired_bits"], out_h["fired_bits"]), round_
+        assert np.array_equal(out_d["potentials"], out_h["potentials"]), round_
+        bias = np.roll(bias, 17)
+        assert sfe.lib().sfe_engine_set_bias(chip.engine, bias.ctypes.data, n) == 0
+        oracle.set_bias(bias)
+        if round_ == 1:
+            chip.reset()
+            oracle.reset()
