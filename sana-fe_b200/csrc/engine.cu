@@ -449,6 +449,7 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
 // ---------------------------------------------------------------------------
 constexpr int kFanoutThreads = 256;
 constexpr int kFanoutWarps = kFanoutThreads / 32;
+constexpr int kBatchWords = 8; // inbox words (x32 axons) a warp inspects per batch
 
 struct FanoutCounters
 {
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     __shared__ double red_d[32];
     __shared__ unsigned long long red_l[32];
     __shared__ uint32_t red_u[32];
+    __shared__ uint2 fan_list[kFanoutWarps][kBatchWords * 32];
 
     const uint32_t ci = t.fanout_core_list[blockIdx.x];
     const CoreDev core = t.cores[ci];
@@ -528,40 +530,102 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
 
     if (core.acc_mode != SFE_ACC_ORDERED)
     {
-        // Exact fixed-point accumulation: any order gives the reference's sums
-        // bit for bit (load-time certificate), so warps take inbox words round-robin.
-        for (uint32_t wi = warp; wi < n_words; wi += kFanoutWarps)
+        // Exact fixed-point accumulation: any order gives the reference's sums bit for
+        // bit (load-time certificate), so warps work independently. Each warp takes a
+        // batch of kBatchWords inbox words (256 axons), fetches the records of the
+        // active axons with one round of parallel loads, compacts them into a private
+        // shared-memory list and then streams the synapse segments with a two-deep
+        // software pipeline (loads of chunk k+1 in flight while chunk k is applied).
+        uint2 *list = fan_list[warp];
+        const uint32_t lane_lt = (1u << lane) - 1u;
+        const bool packed = core.acc_mode == SFE_ACC_PACKED32;
+        for (uint32_t w0 = warp * kBatchWords; w0 < n_words; w0 += kFanoutWarps * kBatchWords)
         {
-            uint32_t word = 0u;
-            if (lane == 0)
+            uint32_t myword = 0u;
+            if (lane < kBatchWords && w0 + lane < n_words)
             {
-                word = s.inbox[core.inbox_word_begin + wi];
-                if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u; // consume
+                myword = s.inbox[core.inbox_word_begin + w0 + lane];
+                if (myword != 0u) s.inbox[core.inbox_word_begin + w0 + lane] = 0u; // consume
             }
-            word = __shfl_sync(0xffffffffu, word, 0);
-            while (word != 0u)
+            uint32_t count = 0u;
+#pragma unroll
+            for (int q = 0; q < kBatchWords; ++q)
             {
-                const uint32_t b = __ffs(word) - 1;
-                word &= word - 1u;
-                const sfe_axon_in ax = t.axons_in[core.axon_begin + (wi << 5) + b];
-                if (lane == 0) account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
-                if (!accumulate) continue;
-                for (uint32_t j = lane; j < ax.syn_count; j += 32)
+                const uint32_t word = __shfl_sync(0xffffffffu, myword, q);
+                const bool on = (word >> lane) & 1u;
+                if (on)
                 {
-                    const double w = __ldg(w_base + ax.syn_off + j);
-                    const uint32_t m = __ldg(m_base + ax.syn_off + j);
-                    const uint32_t post = SFE_SYN_POST(m);
-                    const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
-                    const int fixed = __double2int_rn(w * core.scale);
-                    if (core.acc_mode == SFE_ACC_PACKED32)
-                        atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
-                    else
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(t.axons_in + core.axon_begin + ((w0 + q) << 5) + lane));
+                    sfe_axon_in ax;
+                    ax.syn_off = raw.x;
+                    ax.syn_count = raw.y;
+                    ax.hop = raw.z;
+                    ax.cost_class = raw.w;
+                    account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
+                    if (accumulate) list[count + __popc(word & lane_lt)] = make_uint2(ax.syn_off, ax.syn_count);
+                }
+                count += __popc(word);
+            }
+            __syncwarp();
+            if (!accumulate || count == 0u) continue;
+
+            // ---- stream the segments: chunk = 128 consecutive synapses of one axon ------
+            double cw[4], nw[4];
+            uint32_t cm[4], nm[4];
+            uint32_t cvalid = 0u, nvalid = 0u;
+            uint32_t e = 0u, j0 = 0u;
+            uint2 ent = list[0];
+            bool more = true;
+            while (more || cvalid != 0u)
+            {
+                nvalid = 0u;
+                if (more)
+                {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
                     {
-                        atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
-                        atomicAdd(&cnt32[sl * P + post], 1u);
+                        const uint32_t j = j0 + lane + 32u * u;
+                        if (j < ent.y)
+                        {
+                            nw[u] = __ldg(w_base + ent.x + j);
+                            nm[u] = __ldg(m_base + ent.x + j);
+                            nvalid |= 1u << u;
+                        }
+                    }
+                    j0 += 128u;
+                    if (j0 >= ent.y)
+                    {
+                        j0 = 0u;
+                        ++e;
+                        more = e < count;
+                        if (more) ent = list[e];
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    if (cvalid & (1u << u))
+                    {
+                        const uint32_t post = SFE_SYN_POST(cm[u]);
+                        const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(cm[u])) % ring) : 0u;
+                        const int fixed = __double2int_rn(cw[u] * core.scale);
+                        if (packed) atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
+                        else
+                        {
+                            atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
+                            atomicAdd(&cnt32[sl * P + post], 1u);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    cw[u] = nw[u];
+                    cm[u] = nm[u];
+                }
+                cvalid = nvalid;
             }
+            __syncwarp();
         }
     }
     else if (warp == 0)
