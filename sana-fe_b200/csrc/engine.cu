@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,7 +92,7 @@ struct DevTables
     const double *syn_w;
     const uint32_t *syn_meta;
     const uint32_t *probes;
-    uint32_t n_cores, n_probes, n_neurons;
+    uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
     double sync_delay;
 };
 
@@ -113,6 +114,7 @@ struct DevState
     uint32_t log_cap;
     double *probe_out;     // [n_probes] potentials of the current step
     long long *step;       // [0] = timesteps simulated so far (T-1 during step T), [1] = log cursor
+    uint32_t *work;        // ticket counter of the message phase (reset by finalize_kernel)
 };
 
 // ---------------------------------------------------------------------------
@@ -449,7 +451,8 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
 // ---------------------------------------------------------------------------
 constexpr int kFanoutThreads = 256;
 constexpr int kFanoutWarps = kFanoutThreads / 32;
-constexpr int kBatchWords = 8; // inbox words (x32 axons) a warp inspects per batch
+constexpr int kListCap = 2048; // active axons listed per round (16 KB of shared memory)
+constexpr int kCostCache = 32;  // cost classes cached in shared memory
 
 struct FanoutCounters
 {
@@ -482,18 +485,159 @@ __device__ __forceinline__ void account_axon(
     }
 }
 
-__global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables t, const DevState s)
+// One 128-synapse chunk of an axon segment held in registers by a warp: lane l owns
+// synapses 2l, 2l+1 (first half) and 64+2l, 64+2l+1 (second half) of the chunk.
+struct ChunkRegs
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 wa, wb;
+    uint2 ma, mb;
+    uint32_t rem; // synapses of the axon from this chunk's start on; 0 = empty buffer
+};
+struct ChunkCursor
+{
+    uint32_t e, j0, count, stride;
+    uint2 ent; // (padded segment offset, synapse count) of list entry e
+};
+
+__device__ __forceinline__ void chunk_load(ChunkRegs &b, ChunkCursor &c, const uint2 *list,
+        const double *__restrict__ w_base, const uint32_t *__restrict__ m_base, const int lane)
+{
+    if (c.e >= c.count)
+    {
+        b.rem = 0u;
+        return;
+    }
+    const uint32_t rem = c.ent.y - c.j0;
+    const uint32_t base = c.ent.x + c.j0; // multiple of 4 synapses: 32-byte / 16-byte aligned
+    b.rem = rem;
+    const uint32_t ja = 2u * lane, jb = 64u + 2u * lane;
+    if (ja < rem)
+    {
+        b.wa = __ldg(reinterpret_cast<const double2 *>(w_base + base + ja));
+        b.ma = __ldg(reinterpret_cast<const uint2 *>(m_base + base + ja));
+    }
+    if (jb < rem)
+    {
+        b.wb = __ldg(reinterpret_cast<const double2 *>(w_base + base + jb));
+        b.mb = __ldg(reinterpret_cast<const uint2 *>(m_base + base + jb));
+    }
+    c.j0 += 128u;
+    if (c.j0 >= c.ent.y)
+    {
+        c.j0 = 0u;
+        c.e += c.stride;
+        if (c.e < c.count) c.ent = list[c.e];
+    }
+}
+
+__device__ __forceinline__ void accumulate_one(uint32_t *acc32, uint32_t *cnt32, const uint32_t P, const uint32_t ring,
+        const long long T, const double scale, const bool packed, const double w, const uint32_t m)
+{
+    const uint32_t post = SFE_SYN_POST(m);
+    const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
+    const int fixed = __double2int_rn(w * scale);
+    if (packed) atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
+    else
+    {
+        atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
+        atomicAdd(&cnt32[sl * P + post], 1u);
+    }
+}
+
+__device__ __forceinline__ void chunk_apply(const ChunkRegs &b, uint32_t *acc32, uint32_t *cnt32, const uint32_t P,
+        const uint32_t ring, const long long T, const double scale, const bool packed, const int lane)
+{
+    const uint32_t ja = 2u * lane, jb = 64u + 2u * lane;
+    if (ja < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wa.x, b.ma.x);
+    if (ja + 1u < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wa.y, b.ma.y);
+    if (jb < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wb.x, b.mb.x);
+    if (jb + 1u < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wb.y, b.mb.y);
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier primitives for the staged variant ------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, const uint32_t bytes, const uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Streaming variants of the exact-mode message phase (selected at engine creation,
+// SFE_FANOUT=scalar|vector|tma):
+//   kStreamScalar  8 scalar loads per 128-synapse chunk, next chunk's loads issued
+//                  before the current chunk's atomics
+//   kStreamVector  LDG.128/LDG.64 vector loads, three chunks in a register ring
+//   kStreamTma     each warp owns a ring of kTmaStages shared-memory stages filled by
+//                  cp.async.bulk (TMA) with mbarrier completion: lane 0 issues two bulk
+//                  copies per chunk (weights, meta), the warp consumes from shared memory
+constexpr int kStreamScalar = 0, kStreamVector = 1, kStreamTma = 2;
+constexpr int kTmaStages = 4;
+constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
+
+template <int V>
+__global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red_d[32];
     __shared__ unsigned long long red_l[32];
     __shared__ uint32_t red_u[32];
-    __shared__ uint2 fan_list[kFanoutWarps][kBatchWords * 32];
+    __shared__ sfe_cost_class cost_cache[kCostCache];
+    __shared__ uint32_t next_item, list_n;
+    __shared__ uint32_t scan_w[kFanoutWarps];
 
-    const uint32_t ci = t.fanout_core_list[blockIdx.x];
-    const CoreDev core = t.cores[ci];
-    const long long T = s.step[0] + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long T = s.step[0] + 1;
+    const bool costs_cached = t.n_cost_classes <= kCostCache;
+    if (costs_cached)
+        for (uint32_t x = threadIdx.x; x < t.n_cost_classes; x += kFanoutThreads) cost_cache[x] = t.costs[x];
+    const sfe_cost_class *cost_table = costs_cached ? cost_cache : t.costs;
+    unsigned char *tma_base = smem_raw + tma_off;
+    unsigned long long *tma_bars = reinterpret_cast<unsigned long long *>(tma_base + kFanoutWarps * kTmaStages * kTmaStageBytes);
+    const uint32_t list_off = tma_off + (V == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8) : 0);
+    if constexpr (V == kStreamTma)
+    {
+        if (threadIdx.x < kFanoutWarps * kTmaStages) mbar_init(smem_addr(tma_bars + threadIdx.x), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
+    (void) tma_phase;
+
+    // Persistent CTAs: cores (heaviest first) are handed out through an atomic ticket,
+    // so the grid is one resident wave and no SM idles behind a wave boundary.
+    for (;;)
+    {
+    __syncthreads(); // previous core fully retired (smem accumulators, next_item)
+    if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u);
+    __syncthreads();
+    const uint32_t item = next_item;
+    if (item >= t.n_fanout_cores) break;
+    const uint32_t ci = t.fanout_core_list[item];
+    const CoreDev core = t.cores[ci];
     const uint32_t P = core.neuron_count;
     const uint32_t cells = P * core.ring;
     // does accumulated charge survive? (not for a plain accumulator with the buffer
@@ -531,101 +675,175 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     if (core.acc_mode != SFE_ACC_ORDERED)
     {
         // Exact fixed-point accumulation: any order gives the reference's sums bit for
-        // bit (load-time certificate), so warps work independently. Each warp takes a
-        // batch of kBatchWords inbox words (256 axons), fetches the records of the
-        // active axons with one round of parallel loads, compacts them into a private
-        // shared-memory list and then streams the synapse segments with a two-deep
-        // software pipeline (loads of chunk k+1 in flight while chunk k is applied).
-        uint2 *list = fan_list[warp];
-        const uint32_t lane_lt = (1u << lane) - 1u;
+        // bit (load-time certificate). Per round (normally one per core):
+        //   pass 1  one inbox word per thread, block scan of the popcounts -> every
+        //           active axon gets a slot in a CTA-wide shared-memory list
+        //   pass 2  the axon records of the listed axons are fetched with independent
+        //           loads (one global latency for the whole core), accounted, and the
+        //           list is rewritten as (segment offset, synapse count)
+        //   stream  warp w takes entries w, w+8, ... and streams their CSR segments
         const bool packed = core.acc_mode == SFE_ACC_PACKED32;
-        for (uint32_t w0 = warp * kBatchWords; w0 < n_words; w0 += kFanoutWarps * kBatchWords)
+        uint2 *list = reinterpret_cast<uint2 *>(smem_raw + list_off);
+        for (uint32_t wb = 0; wb < n_words;)
         {
-            uint32_t myword = 0u;
-            if (lane < kBatchWords && w0 + lane < n_words)
-            {
-                myword = s.inbox[core.inbox_word_begin + w0 + lane];
-                if (myword != 0u) s.inbox[core.inbox_word_begin + w0 + lane] = 0u; // consume
-            }
-            uint32_t count = 0u;
+            const uint32_t wi = wb + threadIdx.x;
+            const uint32_t word = wi < n_words ? s.inbox[core.inbox_word_begin + wi] : 0u;
+            const uint32_t pc = __popc(word);
+            uint32_t incl = pc;
 #pragma unroll
-            for (int q = 0; q < kBatchWords; ++q)
+            for (int o = 1; o < 32; o <<= 1)
             {
-                const uint32_t word = __shfl_sync(0xffffffffu, myword, q);
-                const bool on = (word >> lane) & 1u;
-                if (on)
-                {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(t.axons_in + core.axon_begin + ((w0 + q) << 5) + lane));
-                    sfe_axon_in ax;
-                    ax.syn_off = raw.x;
-                    ax.syn_count = raw.y;
-                    ax.hop = raw.z;
-                    ax.cost_class = raw.w;
-                    account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
-                    if (accumulate) list[count + __popc(word & lane_lt)] = make_uint2(ax.syn_off, ax.syn_count);
-                }
-                count += __popc(word);
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
             }
-            __syncwarp();
-            if (!accumulate || count == 0u) continue;
+            if (lane == 31) scan_w[warp] = incl;
+            __syncthreads();
+            uint32_t base = incl - pc, total = 0u;
+#pragma unroll
+            for (int w = 0; w < kFanoutWarps; ++w)
+            {
+                const uint32_t x = scan_w[w];
+                if (w < warp) base += x;
+                total += x;
+            }
+            const bool ok = base + pc <= kListCap;
+            const uint32_t accepted = __syncthreads_count(ok); // ok is monotone in the word index
+            if (threadIdx.x == accepted || (accepted == kFanoutThreads && threadIdx.x == 0))
+                list_n = accepted == kFanoutThreads ? total : base;
+            if (ok && word != 0u)
+            {
+                s.inbox[core.inbox_word_begin + wi] = 0u; // consume
+                uint32_t bits = word, slot = base;
+                while (bits != 0u)
+                {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    list[slot++] = make_uint2((wi << 5) + b, 0u);
+                }
+            }
+            __syncthreads();
+            const uint32_t n_list = list_n;
+            for (uint32_t e = threadIdx.x; e < n_list; e += kFanoutThreads)
+            {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(t.axons_in + core.axon_begin + list[e].x));
+                sfe_axon_in ax;
+                ax.syn_off = raw.x;
+                ax.syn_count = raw.y;
+                ax.hop = raw.z;
+                ax.cost_class = raw.w;
+                account_axon(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
+                list[e] = make_uint2(ax.syn_off, ax.syn_count);
+            }
+            __syncthreads();
+            wb += accepted;
+            if (!accumulate || static_cast<uint32_t>(warp) >= n_list) continue;
 
             // ---- stream the segments: chunk = 128 consecutive synapses of one axon ------
-            double cw[4], nw[4];
-            uint32_t cm[4], nm[4];
-            uint32_t cvalid = 0u, nvalid = 0u;
-            uint32_t e = 0u, j0 = 0u;
-            uint2 ent = list[0];
-            bool more = true;
-            while (more || cvalid != 0u)
+            // Segments are padded to 4 synapses and 16-byte aligned in HBM (engine-side layout).
+            ChunkCursor cur;
+            cur.e = warp;
+            cur.j0 = 0u;
+            cur.count = n_list;
+            cur.stride = kFanoutWarps;
+            cur.ent = list[warp];
+            if constexpr (V == kStreamTma)
             {
-                nvalid = 0u;
-                if (more)
+                unsigned char *stage0 = tma_base + warp * kTmaStages * kTmaStageBytes;
+                const uint32_t bar0 = smem_addr(tma_bars + warp * kTmaStages);
+                auto issue = [&](const int st) -> uint32_t {
+                    if (cur.e >= cur.count) return 0u;
+                    const uint32_t rem = cur.ent.y - cur.j0;
+                    const uint32_t base_syn = cur.ent.x + cur.j0;
+                    const uint32_t n4 = (min(rem, 128u) + 3u) & ~3u;
+                    if (lane == 0)
+                    {
+                        const uint32_t bar = bar0 + 8u * st;
+                        const uint32_t dst = smem_addr(stage0 + st * kTmaStageBytes);
+                        mbar_expect_tx(bar, n4 * 12u);
+                        bulk_g2s(dst, w_base + base_syn, n4 * 8u, bar);
+                        bulk_g2s(dst + 1024u, m_base + base_syn, n4 * 4u, bar);
+                    }
+                    cur.j0 += 128u;
+                    if (cur.j0 >= cur.ent.y)
+                    {
+                        cur.j0 = 0u;
+                        cur.e += cur.stride;
+                        if (cur.e < cur.count) cur.ent = list[cur.e];
+                    }
+                    return rem;
+                };
+                uint32_t rem_s[kTmaStages];
+#pragma unroll
+                for (int st = 0; st < kTmaStages; ++st) rem_s[st] = issue(st);
+                bool done = false;
+                while (!done)
                 {
+#pragma unroll
+                    for (int st = 0; st < kTmaStages; ++st)
+                    {
+                        if (rem_s[st] == 0u)
+                        {
+                            done = true;
+                            break;
+                        }
+                        mbar_wait(bar0 + 8u * st, (tma_phase >> st) & 1u);
+                        tma_phase ^= 1u << st;
+                        const double *ws = reinterpret_cast<const double *>(stage0 + st * kTmaStageBytes);
+                        const uint32_t *ms = reinterpret_cast<const uint32_t *>(stage0 + st * kTmaStageBytes + 1024);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const uint32_t j = lane + 32u * u;
+                            if (j < rem_s[st]) accumulate_one(acc32, cnt32, P, ring, T, core.scale, packed, ws[j], ms[j]);
+                        }
+                        __syncwarp(); // every lane is done with the stage before it is refilled
+                        rem_s[st] = issue(st);
+                    }
+                }
+            }
+            else
+            {
+                double cw[4], nw[4];
+                uint32_t cm[4], nm[4];
+                uint32_t cvalid = 0u, nvalid = 0u;
+                bool more = true;
+                while (more || cvalid != 0u)
+                {
+                    nvalid = 0u;
+                    if (more)
+                    {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const uint32_t j = cur.j0 + lane + 32u * u;
+                            if (j < cur.ent.y)
+                            {
+                                nw[u] = __ldg(w_base + cur.ent.x + j);
+                                nm[u] = __ldg(m_base + cur.ent.x + j);
+                                nvalid |= 1u << u;
+                            }
+                        }
+                        cur.j0 += 128u;
+                        if (cur.j0 >= cur.ent.y)
+                        {
+                            cur.j0 = 0u;
+                            cur.e += cur.stride;
+                            more = cur.e < cur.count;
+                            if (more) cur.ent = list[cur.e];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (cvalid & (1u << u)) accumulate_one(acc32, cnt32, P, ring, T, core.scale, packed, cw[u], cm[u]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                     {
-                        const uint32_t j = j0 + lane + 32u * u;
-                        if (j < ent.y)
-                        {
-                            nw[u] = __ldg(w_base + ent.x + j);
-                            nm[u] = __ldg(m_base + ent.x + j);
-                            nvalid |= 1u << u;
-                        }
+                        cw[u] = nw[u];
+                        cm[u] = nm[u];
                     }
-                    j0 += 128u;
-                    if (j0 >= ent.y)
-                    {
-                        j0 = 0u;
-                        ++e;
-                        more = e < count;
-                        if (more) ent = list[e];
-                    }
+                    cvalid = nvalid;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                {
-                    if (cvalid & (1u << u))
-                    {
-                        const uint32_t post = SFE_SYN_POST(cm[u]);
-                        const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(cm[u])) % ring) : 0u;
-                        const int fixed = __double2int_rn(cw[u] * core.scale);
-                        if (packed) atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
-                        else
-                        {
-                            atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
-                            atomicAdd(&cnt32[sl * P + post], 1u);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                {
-                    cw[u] = nw[u];
-                    cm[u] = nm[u];
-                }
-                cvalid = nvalid;
             }
-            __syncwarp();
         }
     }
     else if (warp == 0)
@@ -646,7 +864,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
                 const uint32_t b = __ffs(word) - 1;
                 word &= word - 1u;
                 const sfe_axon_in ax = t.axons_in[core.axon_begin + (wi << 5) + b];
-                if (lane == 0) account_axon(cnt, ax, t.costs[ax.cost_class], core.lat_axon_in);
+                if (lane == 0) account_axon(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
                 if (!accumulate) continue;
                 for (uint32_t j0 = 0; j0 < ax.syn_count; j0 += 32)
                 {
@@ -747,6 +965,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         out.proc = pr;
         s.stats_m[ci] = out;
     }
+    } // persistent loop
 }
 
 // ---------------------------------------------------------------------------
@@ -826,6 +1045,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
         s.log[cursor % s.log_cap] = r;
         s.step[1] = cursor + 1;
         s.step[0] = s.step[0] + 1;
+        *s.work = 0u;
     }
 }
 
@@ -837,14 +1057,21 @@ __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restric
 {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const uint32_t C = sp.cores, P = sp.neurons_per_core, D = sp.dest_cores, S = sp.syn_per_axon;
-    const unsigned long long per_core = static_cast<unsigned long long>(P) * D * S;
+    const uint32_t Sp = (S + 3u) & ~3u; // device layout: every axon segment padded to 4 synapses
+    const unsigned long long per_core = static_cast<unsigned long long>(P) * D * Sp;
     for (unsigned long long g = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
             g += stride)
     {
         const uint32_t d = static_cast<uint32_t>(g / per_core);
         const unsigned long long rem = g % per_core;
-        const uint32_t slot = static_cast<uint32_t>(rem / S);
-        const uint32_t j = static_cast<uint32_t>(rem % S);
+        const uint32_t slot = static_cast<uint32_t>(rem / Sp);
+        const uint32_t j = static_cast<uint32_t>(rem % Sp);
+        if (j >= S)
+        {
+            syn_w[g] = 0.0;
+            syn_meta[g] = 0u;
+            continue;
+        }
         const uint32_t r = slot / P, p = slot % P;
         // r-th source core of destination d, ascending core id (see lower_synthetic)
         uint32_t src;
@@ -867,7 +1094,7 @@ __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restric
 
 // per core: worst per-post fan-in and sum |w * 2^shift| -> accumulation mode
 __global__ void __launch_bounds__(256) certify_kernel(
-        CoreDev *cores, const uint32_t *core_list, const double *syn_w, const uint32_t *syn_meta, const uint64_t *syn_count)
+        CoreDev *cores, const uint32_t *core_list, const sfe_axon_in *axons, const double *syn_w, const uint32_t *syn_meta)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t bad;
@@ -883,14 +1110,18 @@ __global__ void __launch_bounds__(256) certify_kernel(
     }
     if (threadIdx.x == 0) bad = 0u;
     __syncthreads();
-    const unsigned long long n = syn_count[ci];
-    for (unsigned long long x = threadIdx.x; x < n; x += blockDim.x)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t a = warp; a < core.axon_count; a += nwarps)
     {
-        const double scaled = fabs(syn_w[core.syn_begin + x] * core.scale);
-        if (!(scaled < 2147483648.0) || scaled != rint(scaled)) bad = 1u;
-        const uint32_t post = SFE_SYN_POST(syn_meta[core.syn_begin + x]);
-        atomicAdd(&sum_abs[post], static_cast<unsigned long long>(scaled));
-        atomicAdd(&fan[post], 1u);
+        const sfe_axon_in ax = axons[core.axon_begin + a];
+        for (uint32_t j = lane; j < ax.syn_count; j += 32)
+        {
+            const double scaled = fabs(syn_w[core.syn_begin + ax.syn_off + j] * core.scale);
+            if (!(scaled < 2147483648.0) || scaled != rint(scaled)) bad = 1u;
+            const uint32_t post = SFE_SYN_POST(syn_meta[core.syn_begin + ax.syn_off + j]);
+            atomicAdd(&sum_abs[post], static_cast<unsigned long long>(scaled));
+            atomicAdd(&fan[post], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -948,6 +1179,9 @@ struct sfe_engine
     uint32_t fired_words{0}, inbox_words{0};
     uint32_t dend_cells{0};
     size_t fanout_smem{0};
+    uint32_t tma_off{0};
+    int fanout_variant{kStreamTma};
+    unsigned fanout_grid{1};
     uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0};
     int64_t total_timesteps{0};
     int64_t launches{0};
@@ -1120,8 +1354,35 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     }
     if (e->upload(&e->t.inputs, tb->inputs, tb->n_inputs) != 0) return -1;
     if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
-    if (e->upload(&e->t.axons_in, tb->axons_in, tb->n_axons_in) != 0) return -1;
+    // Device synapse layout: every axon segment starts on a multiple of 4 synapses
+    // (32-byte aligned weights, 16-byte aligned meta words) so the message phase can
+    // use 128-bit loads; the axon records carry the padded offsets.
+    std::vector<sfe_axon_in> dev_axons(tb->axons_in, tb->axons_in + tb->n_axons_in);
+    uint64_t padded_total = 0;
+    for (uint32_t c = 0; c < tb->n_cores; ++c)
+    {
+        const sfe_core_desc &cd = tb->cores[c];
+        e->h_cores[c].syn_begin = padded_total;
+        uint64_t off = 0;
+        for (uint32_t a = 0; a < cd.axon_in_count; ++a)
+        {
+            sfe_axon_in &ax = dev_axons[cd.axon_in_begin + a];
+            if (off > 0xffffffffull)
+            {
+                sfe::set_last_error("more than 2^32 padded synapses on one core");
+                return -1;
+            }
+            ax.syn_off = static_cast<uint32_t>(off);
+            off += (static_cast<uint64_t>(ax.syn_count) + 3u) & ~3ull;
+        }
+        padded_total += off;
+    }
+    if (e->upload(&e->t.axons_in, dev_axons.data(), dev_axons.size()) != 0) return -1;
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
     if (e->upload(&e->t.probes, tb->probes, tb->n_probes) != 0) return -1;
+    // heaviest destination cores first (longest-processing-time order for the ticket queue)
+    std::stable_sort(e->fanout_list.begin(), e->fanout_list.end(),
+            [&](uint32_t a, uint32_t b) { return tb->cores[a].syn_count > tb->cores[b].syn_count; });
     if (e->upload(&e->t.soma_core_list, e->soma_list.data(), e->soma_list.size()) != 0) return -1;
     if (e->upload(&e->t.fanout_core_list, e->fanout_list.data(), e->fanout_list.size()) != 0) return -1;
     {
@@ -1133,19 +1394,41 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->t.n_cores = tb->n_cores;
     e->t.n_probes = tb->n_probes;
     e->t.n_neurons = tb->n_neurons;
+    e->t.n_cost_classes = tb->n_cost_classes;
+    e->t.n_fanout_cores = static_cast<uint32_t>(e->fanout_list.size());
     e->t.sync_delay = tb->sync_delay;
 
     // ---- synapses: copied, or generated on the device ---------------------------
     double *d_w = nullptr;
     uint32_t *d_m = nullptr;
-    if (e->alloc(&d_w, tb->n_synapses) != 0) return -1;
-    if (e->alloc(&d_m, tb->n_synapses) != 0) return -1;
+    if (e->alloc(&d_w, padded_total) != 0) return -1;
+    if (e->alloc(&d_m, padded_total) != 0) return -1;
     e->t.syn_w = d_w;
     e->t.syn_meta = d_m;
     if (tb->syn_weight != nullptr && tb->n_synapses > 0)
     {
-        SFE_CUDA(cudaMemcpyAsync(d_w, tb->syn_weight, tb->n_synapses * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        SFE_CUDA(cudaMemcpyAsync(d_m, tb->syn_meta, tb->n_synapses * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        // repack into the padded layout, one core at a time (bounded staging)
+        std::vector<double> pw;
+        std::vector<uint32_t> pm;
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+        {
+            const sfe_core_desc &cd = tb->cores[c];
+            if (cd.axon_in_count == 0) continue;
+            const sfe_axon_in &last = dev_axons[cd.axon_in_begin + cd.axon_in_count - 1];
+            const uint64_t core_padded = last.syn_off + ((static_cast<uint64_t>(last.syn_count) + 3u) & ~3ull);
+            pw.assign(core_padded, 0.0);
+            pm.assign(core_padded, 0u);
+            for (uint32_t a = 0; a < cd.axon_in_count; ++a)
+            {
+                const sfe_axon_in &src = tb->axons_in[cd.axon_in_begin + a];
+                const sfe_axon_in &dst = dev_axons[cd.axon_in_begin + a];
+                std::memcpy(pw.data() + dst.syn_off, tb->syn_weight + cd.syn_begin + src.syn_off, src.syn_count * sizeof(double));
+                std::memcpy(pm.data() + dst.syn_off, tb->syn_meta + cd.syn_begin + src.syn_off, src.syn_count * sizeof(uint32_t));
+            }
+            SFE_CUDA(cudaMemcpyAsync(d_w + e->h_cores[c].syn_begin, pw.data(), core_padded * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            SFE_CUDA(cudaMemcpyAsync(d_m + e->h_cores[c].syn_begin, pm.data(), core_padded * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+            SFE_CUDA(cudaStreamSynchronize(e->stream));
+        }
     }
     else if (tb->n_synapses > 0)
     {
@@ -1154,17 +1437,15 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             sfe::set_last_error("tables carry neither synapse arrays nor a synthetic spec");
             return -1;
         }
-        synth_generate_kernel<<<148 * 16, 256, 0, e->stream>>>(*tb->synth, d_w, d_m, tb->n_synapses);
+        synth_generate_kernel<<<148 * 16, 256, 0, e->stream>>>(*tb->synth, d_w, d_m, padded_total);
         SFE_CUDA(cudaGetLastError());
         // certificate computed where the synapses are
-        const uint64_t *d_counts = nullptr;
-        if (e->upload(&d_counts, syn_counts.data(), syn_counts.size()) != 0) return -1;
         uint32_t max_p = 0;
         for (uint32_t c : e->fanout_list) max_p = std::max(max_p, tb->cores[c].neuron_count);
         if (!e->fanout_list.empty())
         {
             certify_kernel<<<static_cast<unsigned>(e->fanout_list.size()), 256, max_p * 12, e->stream>>>(
-                    e->d_cores, e->t.fanout_core_list, d_w, d_m, d_counts);
+                    e->d_cores, e->t.fanout_core_list, e->t.axons_in, d_w, d_m);
             SFE_CUDA(cudaGetLastError());
         }
         SFE_CUDA(cudaMemcpyAsync(e->h_cores.data(), e->d_cores, e->h_cores.size() * sizeof(CoreDev), cudaMemcpyDeviceToHost, e->stream));
@@ -1197,6 +1478,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
     if (e->alloc(&e->s.probe_out, tb->n_probes) != 0) return -1;
     if (e->alloc(&e->s.step, 2) != 0) return -1;
+    if (e->alloc(&e->s.work, 1) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (engine_init_state(e) != 0) return -1;
 
@@ -1208,14 +1490,38 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         const size_t need = d.acc_mode == SFE_ACC_PACKED32 ? cells * 4 : d.acc_mode == SFE_ACC_DUAL32 ? cells * 8 : cells * 12;
         smem_max = std::max(smem_max, need);
     }
+    if (const char *v = std::getenv("SFE_FANOUT"))
+    {
+        const std::string name(v);
+        if (name == "scalar") e->fanout_variant = kStreamScalar;
+        else if (name == "tma") e->fanout_variant = kStreamTma;
+        else
+        {
+            sfe::set_last_error("SFE_FANOUT must be scalar or tma");
+            return -1;
+        }
+    }
+    e->tma_off = static_cast<uint32_t>((smem_max + 127) & ~static_cast<size_t>(127));
+    smem_max = e->tma_off + (e->fanout_variant == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8) : 0) +
+            kListCap * sizeof(uint2);
     e->fanout_smem = smem_max;
     if (smem_max > 200 * 1024)
     {
         sfe::set_last_error("a core needs more than 200 KB of shared-memory dendrite accumulators");
         return -1;
     }
-    if (smem_max > 48 * 1024)
-        SFE_CUDA(cudaFuncSetAttribute(fanout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    {
+        int per_sm = 1, sms = 1;
+        if (e->fanout_variant == kStreamTma)
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamTma>, kFanoutThreads, smem_max));
+        else
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar>, kFanoutThreads, smem_max));
+        SFE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+        if (const char *v = std::getenv("SFE_FANOUT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
+        e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(e->fanout_list.size(), static_cast<size_t>(per_sm) * sms)));
+    }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -1265,6 +1571,15 @@ extern "C" int sfe_engine_set_stream(sfe_engine *e, void *stream)
     return 0;
 }
 
+static void launch_fanout(sfe_engine *e)
+{
+    const unsigned grid = e->fanout_grid;
+    if (e->fanout_variant == kStreamTma)
+        fanout_kernel<kStreamTma><<<grid, kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s, e->tma_off);
+    else
+        fanout_kernel<kStreamScalar><<<grid, kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s, e->tma_off);
+}
+
 static int enqueue_step(sfe_engine *e, bool probes)
 {
     if (!e->soma_list.empty())
@@ -1290,7 +1605,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
             }
             cudaEventRecord(e->ev_pool[e->ev_used], e->stream);
         }
-        fanout_kernel<<<static_cast<unsigned>(e->fanout_list.size()), kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s);
+        launch_fanout(e);
         ++e->launches;
         if (timed)
         {
@@ -1415,7 +1730,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 SFE_CUDA(cudaMemcpyAsync(stage, e->s.status, e->n_neurons, cudaMemcpyDeviceToHost, e->stream));
             if (!e->fanout_list.empty())
             {
-                fanout_kernel<<<static_cast<unsigned>(e->fanout_list.size()), kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s);
+                launch_fanout(e);
                 ++e->launches;
             }
             finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
