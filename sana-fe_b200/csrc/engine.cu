@@ -55,6 +55,7 @@ struct CoreDev
     uint32_t acc_mode;                // SFE_ACC_*
     uint32_t dend_in_msg;
     uint32_t tile;
+    uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t pad0;
     unsigned long long syn_begin;
     double scale, inv_scale;          // 2^shift, 2^-shift
@@ -75,11 +76,15 @@ struct StatsM // written by fanout_kernel, one per core
     double syn_e, den_e, proc;
 };
 
+struct SomaSegment;
 struct DevTables
 {
     const CoreDev *cores;
-    const uint32_t *soma_core_list;   // cores that have neurons
+    const struct SomaSegment *soma_segments; // one record per neuron-phase segment
+    uint32_t n_soma_classes;
     const uint32_t *fanout_core_list; // cores that have axons-in
+    const uint32_t *active_core_list; // cores with neurons or axons-in (ascending id)
+    uint32_t n_active_cores;
     const sfe_soma_class *classes;
     const sfe_cost_class *costs;
     const uint32_t *neuron_class;
@@ -96,6 +101,7 @@ struct DevTables
     double sync_delay;
 };
 
+struct StepPartial;
 struct DevState
 {
     double *v, *u, *bias;
@@ -115,6 +121,8 @@ struct DevState
     double *probe_out;     // [n_probes] potentials of the current step
     long long *step;       // [0] = timesteps simulated so far (T-1 during step T), [1] = log cursor
     uint32_t *work;        // ticket counter of the message phase (reset by finalize_kernel)
+    uint32_t *final_ticket;
+    struct StepPartial *partials;
 };
 
 // ---------------------------------------------------------------------------
@@ -275,33 +283,65 @@ __device__ __forceinline__ int hh_update(double *hh, const uint32_t n_hh, const 
 }
 
 // ---------------------------------------------------------------------------
-// K1: neuron phase. One CTA per mapped core.
+// K1: neuron phase. One CTA per segment of kSomaThreads consecutive neurons of a core
+// (one neuron per thread: every load of the step is issued at once).
+// kExotic = the chip maps input / Hodgkin-Huxley somas (kept out of the LIF /
+// TrueNorth instantiation so the common case stays at low register pressure).
 // ---------------------------------------------------------------------------
 constexpr int kSomaThreads = 256;
 
+constexpr int kClassCache = 24; // soma parameter classes cached in shared memory (160 B each)
+
+// everything the neuron phase needs about its core, in one record (one dependent load
+// less than going through the core table)
+struct SomaSegment
+{
+    uint32_t k0;               // first neuron of the segment within the core
+    uint32_t neuron_begin, neuron_count;
+    uint32_t fired_word_begin;
+    uint32_t dend_base, ring, acc_mode, pad;
+    double inv_scale;
+};
+
+template <bool kExotic>
 __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
 {
-    __shared__ double red_d[32];
-    __shared__ uint32_t red_u[32];
-    const uint32_t ci = t.soma_core_list[blockIdx.x];
-    const CoreDev core = t.cores[ci];
+    __shared__ sfe_soma_class class_cache[kClassCache];
+    const SomaSegment core = t.soma_segments[blockIdx.x];
     const long long steps_done = s.step[0];
     const long long T = steps_done + 1;
     const int lane = threadIdx.x & 31;
+    const bool classes_cached = t.n_soma_classes <= kClassCache;
+    if (classes_cached)
+    {
+        // 8-byte words of the class table, cooperatively
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(t.classes);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_cache);
+        for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
+    }
 
     uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
     double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
     const uint32_t slot = core.ring > 1 ? static_cast<uint32_t>(T % core.ring) : 0u;
-    const uint32_t rounded = (core.neuron_count + 31u) & ~31u;
 
-    for (uint32_t k = threadIdx.x; k < rounded; k += kSomaThreads)
     {
+        const uint32_t k = core.k0 + threadIdx.x;
         const bool valid = k < core.neuron_count;
         int st = SFE_STATUS_IDLE;
+        // every global load of the step is issued before the first use
+        uint32_t cid = 0u, a0 = 0u, a1 = 0u;
         if (valid)
         {
             const uint32_t i = core.neuron_begin + k;
-            const sfe_soma_class c = t.classes[t.neuron_class[i]];
+            cid = __ldg(t.neuron_class + i);
+            a0 = __ldg(t.axon_out_begin + i);
+            a1 = __ldg(t.axon_out_begin + i + 1);
+        }
+        __syncthreads(); // class cache filled
+        if (valid)
+        {
+            const uint32_t i = core.neuron_begin + k;
+            const sfe_soma_class c = classes_cached ? class_cache[cid] : t.classes[cid];
             // ---- dendrite output for this step ------------------------------
             bool has_in = false;
             double in = 0.0;
@@ -372,13 +412,10 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 st = truenorth_update(c, v, bias, has_in, in);
                 s.v[i] = v;
             }
-            else if (c.model == SFE_SOMA_INPUT)
+            else if constexpr (kExotic)
             {
-                st = input_update(t.inputs[t.neuron_aux[i]], t.input_spikes, steps_done, T);
-            }
-            else
-            {
-                st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
+                if (c.model == SFE_SOMA_INPUT) st = input_update(t.inputs[t.neuron_aux[i]], t.input_spikes, steps_done, T);
+                else st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
             }
             s.status[i] = static_cast<uint8_t>(st);
             // ---- default soma costs  src/pipeline.hpp:631-714 -----------------
@@ -394,42 +431,65 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 e += c.energy_spike_out;
                 l += c.latency_spike_out;
                 ++n_fired;
-                // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon
-                const uint32_t a0 = t.axon_out_begin[i], a1 = t.axon_out_begin[i + 1];
-                for (uint32_t a = a0; a < a1; ++a)
-                {
-                    const uint32_t bit = t.axon_out_bit[a];
-                    atomicOr(&s.inbox[bit >> 5], 1u << (bit & 31));
-                }
-                n_packets += a1 - a0;
             }
             soma_e += e;
             lat_sum += lat + l;
         }
-        // spike raster: one ballot per 32 neurons (warp-uniform loop)
+        // spike raster: one ballot per 32 neurons
         const uint32_t ballot = __ballot_sync(0xffffffffu, st == SFE_STATUS_FIRED);
-        if (lane == 0) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
+        if (lane == 0 && k < ((core.neuron_count + 31u) & ~31u)) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
+        // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon of a fired
+        // neuron: raise the inbox bit of every target (loads batched eight at a time).
+        if (st == SFE_STATUS_FIRED)
+        {
+            n_packets += a1 - a0;
+            for (uint32_t base = a0; base < a1; base += 8u)
+            {
+                uint32_t bit[8];
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                    if (base + x < a1) bit[x] = __ldg(t.axon_out_bit + base + x);
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                    if (base + x < a1) atomicOr(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
+            }
+        }
     }
-    // ---- per-core reductions -------------------------------------------------
-    const uint32_t upd = block_sum(n_updated, red_u);
-    const uint32_t frd = block_sum(n_fired, red_u);
-    const uint32_t pkt = block_sum(n_packets, red_u);
-    const double se = block_sum(soma_e, red_d);
-    const double de = block_sum(dend_e, red_d);
-    const double ls = block_sum(lat_sum, red_d);
+    // ---- per-segment reductions: warp shuffles, one barrier -------------------------
+    __shared__ double part_d[kSomaThreads / 32][3];
+    __shared__ uint32_t part_u[kSomaThreads / 32][3];
+    n_updated = warp_sum(n_updated);
+    n_fired = warp_sum(n_fired);
+    n_packets = warp_sum(n_packets);
+    soma_e = warp_sum(soma_e);
+    dend_e = warp_sum(dend_e);
+    lat_sum = warp_sum(lat_sum);
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0)
+    {
+        part_u[warp][0] = n_updated;
+        part_u[warp][1] = n_fired;
+        part_u[warp][2] = n_packets;
+        part_d[warp][0] = soma_e;
+        part_d[warp][1] = dend_e;
+        part_d[warp][2] = lat_sum;
+    }
+    __syncthreads();
     if (threadIdx.x == 0)
     {
-        StatsN out;
-        out.updated = upd;
-        out.fired = frd;
-        out.packets = pkt;
-        out.pad = 0;
-        out.soma_e = se;
-        out.dend_e = de;
-        // sum of generation delays incl. the trailing placeholder message
+        StatsN out = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+        for (int w = 0; w < kSomaThreads / 32; ++w) // fixed order: deterministic sums
+        {
+            out.updated += part_u[w][0];
+            out.fired += part_u[w][1];
+            out.packets += part_u[w][2];
+            out.soma_e += part_d[w][0];
+            out.dend_e += part_d[w][1];
+            out.gen_sum += part_d[w][2]; // finalize adds packets * latency_axon_out per core
+        }
+        // gen_sum: sum of generation delays incl. the trailing placeholder message
         // (src/chip.cpp:640-652, 821-823; src/schedule.cpp:81)
-        out.gen_sum = ls + static_cast<double>(pkt) * core.lat_axon_out;
-        s.stats_n[ci] = out;
+        s.stats_n[blockIdx.x] = out;
     }
 }
 
@@ -485,50 +545,11 @@ __device__ __forceinline__ void account_axon(
     }
 }
 
-// One 128-synapse chunk of an axon segment held in registers by a warp: lane l owns
-// synapses 2l, 2l+1 (first half) and 64+2l, 64+2l+1 (second half) of the chunk.
-struct ChunkRegs
-{
-    double2 wa, wb;
-    uint2 ma, mb;
-    uint32_t rem; // synapses of the axon from this chunk's start on; 0 = empty buffer
-};
 struct ChunkCursor
 {
     uint32_t e, j0, count, stride;
     uint2 ent; // (padded segment offset, synapse count) of list entry e
 };
-
-__device__ __forceinline__ void chunk_load(ChunkRegs &b, ChunkCursor &c, const uint2 *list,
-        const double *__restrict__ w_base, const uint32_t *__restrict__ m_base, const int lane)
-{
-    if (c.e >= c.count)
-    {
-        b.rem = 0u;
-        return;
-    }
-    const uint32_t rem = c.ent.y - c.j0;
-    const uint32_t base = c.ent.x + c.j0; // multiple of 4 synapses: 32-byte / 16-byte aligned
-    b.rem = rem;
-    const uint32_t ja = 2u * lane, jb = 64u + 2u * lane;
-    if (ja < rem)
-    {
-        b.wa = __ldg(reinterpret_cast<const double2 *>(w_base + base + ja));
-        b.ma = __ldg(reinterpret_cast<const uint2 *>(m_base + base + ja));
-    }
-    if (jb < rem)
-    {
-        b.wb = __ldg(reinterpret_cast<const double2 *>(w_base + base + jb));
-        b.mb = __ldg(reinterpret_cast<const uint2 *>(m_base + base + jb));
-    }
-    c.j0 += 128u;
-    if (c.j0 >= c.ent.y)
-    {
-        c.j0 = 0u;
-        c.e += c.stride;
-        if (c.e < c.count) c.ent = list[c.e];
-    }
-}
 
 __device__ __forceinline__ void accumulate_one(uint32_t *acc32, uint32_t *cnt32, const uint32_t P, const uint32_t ring,
         const long long T, const double scale, const bool packed, const double w, const uint32_t m)
@@ -542,16 +563,6 @@ __device__ __forceinline__ void accumulate_one(uint32_t *acc32, uint32_t *cnt32,
         atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
         atomicAdd(&cnt32[sl * P + post], 1u);
     }
-}
-
-__device__ __forceinline__ void chunk_apply(const ChunkRegs &b, uint32_t *acc32, uint32_t *cnt32, const uint32_t P,
-        const uint32_t ring, const long long T, const double scale, const bool packed, const int lane)
-{
-    const uint32_t ja = 2u * lane, jb = 64u + 2u * lane;
-    if (ja < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wa.x, b.ma.x);
-    if (ja + 1u < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wa.y, b.ma.y);
-    if (jb < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wb.x, b.mb.x);
-    if (jb + 1u < b.rem) accumulate_one(acc32, cnt32, P, ring, T, scale, packed, b.wb.y, b.mb.y);
 }
 
 // ---- TMA (cp.async.bulk) + mbarrier primitives for the staged variant ------------
@@ -591,11 +602,10 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 // SFE_FANOUT=scalar|vector|tma):
 //   kStreamScalar  8 scalar loads per 128-synapse chunk, next chunk's loads issued
 //                  before the current chunk's atomics
-//   kStreamVector  LDG.128/LDG.64 vector loads, three chunks in a register ring
 //   kStreamTma     each warp owns a ring of kTmaStages shared-memory stages filled by
 //                  cp.async.bulk (TMA) with mbarrier completion: lane 0 issues two bulk
 //                  copies per chunk (weights, meta), the warp consumes from shared memory
-constexpr int kStreamScalar = 0, kStreamVector = 1, kStreamTma = 2;
+constexpr int kStreamScalar = 0, kStreamTma = 2;
 constexpr int kTmaStages = 4;
 constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
 
@@ -969,84 +979,150 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
 }
 
 // ---------------------------------------------------------------------------
-// K5: energy, counters, simple timing model. One CTA.
+// K5: energy, counters, simple timing model. One thread per active core; the last
+// CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
+// step record, so every floating-point sum is formed in the same order on every run.
 // ---------------------------------------------------------------------------
-constexpr int kFinalThreads = 1024;
+constexpr int kFinalThreads = 256;
+
+struct StepPartial
+{
+    unsigned long long fired, updated, packets, hops, events;
+    double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
+};
+
+__device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
+{
+    StepPartial r;
+    r.fired = __ldcg(&p->fired);
+    r.updated = __ldcg(&p->updated);
+    r.packets = __ldcg(&p->packets);
+    r.hops = __ldcg(&p->hops);
+    r.events = __ldcg(&p->events);
+    r.syn_e = __ldcg(&p->syn_e);
+    r.den_e = __ldcg(&p->den_e);
+    r.soma_e = __ldcg(&p->soma_e);
+    r.net_e = __ldcg(&p->net_e);
+    r.max_gen = __ldcg(&p->max_gen);
+    r.max_proc = __ldcg(&p->max_proc);
+    return r;
+}
 
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
 {
-    __shared__ double red_d[32];
-    __shared__ unsigned long long red_l[32];
-    unsigned long long fired = 0, updated = 0, packets = 0, hops = 0, events = 0;
-    double syn_e = 0.0, den_e = 0.0, soma_e = 0.0, net_e = 0.0, max_gen = 0.0, max_proc = 0.0;
-    for (uint32_t ci = threadIdx.x; ci < t.n_cores; ci += kFinalThreads)
+    __shared__ StepPartial warp_part[kFinalThreads / 32];
+    __shared__ uint32_t ticket_s;
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const uint32_t a = blockIdx.x * kFinalThreads + threadIdx.x;
+    if (a < t.n_active_cores)
     {
+        const uint32_t ci = t.active_core_list[a];
         const CoreDev &core = t.cores[ci];
-        const StatsN n = s.stats_n[ci];
+        StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+        for (uint32_t g = 0; g < core.seg_count; ++g) // fixed order: deterministic sums
+        {
+            const StatsN x = s.stats_n[core.seg_begin + g];
+            n.updated += x.updated;
+            n.fired += x.fired;
+            n.packets += x.packets;
+            n.soma_e += x.soma_e;
+            n.dend_e += x.dend_e;
+            n.gen_sum += x.gen_sum;
+        }
+        n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
         const StatsM m = s.stats_m[ci];
-        fired += n.fired;
-        updated += n.updated;
-        packets += n.packets;
-        hops += m.hop_e + m.hop_w + m.hop_n + m.hop_s;
-        events += m.events;
-        syn_e += m.syn_e;
-        den_e += n.dend_e + m.den_e;
-        soma_e += n.soma_e;
+        p.fired = n.fired;
+        p.updated = n.updated;
+        p.packets = n.packets;
+        p.hops = m.hop_e + m.hop_w + m.hop_n + m.hop_s;
+        p.events = m.events;
+        p.syn_e = m.syn_e;
+        p.den_e = n.dend_e + m.den_e;
+        p.soma_e = n.soma_e;
         // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
         double hop = static_cast<double>(m.hop_e) * core.e_east;
         hop += static_cast<double>(m.hop_w) * core.e_west;
         hop += static_cast<double>(m.hop_s) * core.e_south;
         hop += static_cast<double>(m.hop_n) * core.e_north;
-        net_e += hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
-        max_gen = fmax(max_gen, n.gen_sum);
-        max_proc = fmax(max_proc, m.proc);
+        p.net_e = hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
+        p.max_gen = n.gen_sum;
+        p.max_proc = m.proc;
     }
-    const unsigned long long f = block_sum(fired, red_l);
-    const unsigned long long u = block_sum(updated, red_l);
-    const unsigned long long p = block_sum(packets, red_l);
-    const unsigned long long h = block_sum(hops, red_l);
-    const unsigned long long e = block_sum(events, red_l);
-    const double se = block_sum(syn_e, red_d);
-    const double de = block_sum(den_e, red_d);
-    const double so = block_sum(soma_e, red_d);
-    const double ne = block_sum(net_e, red_d);
-    // block-wide max through the same scratch
-    double mg = warp_max(max_gen), mp = warp_max(max_proc);
-    __shared__ double red_m[64];
+    p.fired = warp_sum(p.fired);
+    p.updated = warp_sum(p.updated);
+    p.packets = warp_sum(p.packets);
+    p.hops = warp_sum(p.hops);
+    p.events = warp_sum(p.events);
+    p.syn_e = warp_sum(p.syn_e);
+    p.den_e = warp_sum(p.den_e);
+    p.soma_e = warp_sum(p.soma_e);
+    p.net_e = warp_sum(p.net_e);
+    p.max_gen = warp_max(p.max_gen);
+    p.max_proc = warp_max(p.max_proc);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0)
-    {
-        red_m[warp] = mg;
-        red_m[32 + warp] = mp;
-    }
+    if (lane == 0) warp_part[warp] = p;
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        for (int w = 0; w < kFinalThreads / 32; ++w)
+        StepPartial b = warp_part[0];
+        for (int w = 1; w < kFinalThreads / 32; ++w)
         {
-            mg = fmax(mg, red_m[w]);
-            mp = fmax(mp, red_m[32 + w]);
+            const StepPartial &x = warp_part[w];
+            b.fired += x.fired;
+            b.updated += x.updated;
+            b.packets += x.packets;
+            b.hops += x.hops;
+            b.events += x.events;
+            b.syn_e += x.syn_e;
+            b.den_e += x.den_e;
+            b.soma_e += x.soma_e;
+            b.net_e += x.net_e;
+            b.max_gen = fmax(b.max_gen, x.max_gen);
+            b.max_proc = fmax(b.max_proc, x.max_proc);
         }
-        sfe_step_record r;
-        r.neurons_fired = static_cast<long long>(f);
-        r.neurons_updated = static_cast<long long>(u);
-        r.packets_sent = static_cast<long long>(p);
-        r.total_hops = static_cast<long long>(h);
-        r.spike_count = static_cast<long long>(e);
-        r.synapse_energy = se;
-        r.dendrite_energy = de;
-        r.soma_energy = so;
-        r.network_energy = ne;
-        r.total_energy = ne + se + de + so;
-        // schedule_messages_timestep_simple  src/schedule.cpp:61-102
-        r.sim_time = fmax(mp, mg) + t.sync_delay;
-        const long long cursor = s.step[1];
-        s.log[cursor % s.log_cap] = r;
-        s.step[1] = cursor + 1;
-        s.step[0] = s.step[0] + 1;
-        *s.work = 0u;
+        s.partials[blockIdx.x] = b;
+        __threadfence();
+        ticket_s = atomicAdd(s.final_ticket, 1u);
     }
+    __syncthreads();
+    if (ticket_s != gridDim.x - 1 || threadIdx.x != 0) return;
+    // ---- last CTA: fold the partials (block order) and append the step record ----------
+    __threadfence();
+    StepPartial b = load_partial(&s.partials[0]);
+    for (uint32_t k = 1; k < gridDim.x; ++k)
+    {
+        const StepPartial x = load_partial(&s.partials[k]);
+        b.fired += x.fired;
+        b.updated += x.updated;
+        b.packets += x.packets;
+        b.hops += x.hops;
+        b.events += x.events;
+        b.syn_e += x.syn_e;
+        b.den_e += x.den_e;
+        b.soma_e += x.soma_e;
+        b.net_e += x.net_e;
+        b.max_gen = fmax(b.max_gen, x.max_gen);
+        b.max_proc = fmax(b.max_proc, x.max_proc);
+    }
+    sfe_step_record r;
+    r.neurons_fired = static_cast<long long>(b.fired);
+    r.neurons_updated = static_cast<long long>(b.updated);
+    r.packets_sent = static_cast<long long>(b.packets);
+    r.total_hops = static_cast<long long>(b.hops);
+    r.spike_count = static_cast<long long>(b.events);
+    r.synapse_energy = b.syn_e;
+    r.dendrite_energy = b.den_e;
+    r.soma_energy = b.soma_e;
+    r.network_energy = b.net_e;
+    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
+    // schedule_messages_timestep_simple  src/schedule.cpp:61-102
+    r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
+    const long long cursor = s.step[1];
+    s.log[cursor % s.log_cap] = r;
+    s.step[1] = cursor + 1;
+    s.step[0] = s.step[0] + 1;
+    *s.work = 0u;
+    *s.final_ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -1182,6 +1258,9 @@ struct sfe_engine
     uint32_t tma_off{0};
     int fanout_variant{kStreamTma};
     unsigned fanout_grid{1};
+    unsigned final_grid{1};
+    uint32_t n_segments{0};
+    bool exotic{false};
     uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0};
     int64_t total_timesteps{0};
     int64_t launches{0};
@@ -1275,6 +1354,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->n_cores = tb->n_cores;
     e->n_hh = tb->n_hh;
     e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
+    for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
+        if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH) e->exotic = true;
     e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
     if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
 
@@ -1383,8 +1464,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     // heaviest destination cores first (longest-processing-time order for the ticket queue)
     std::stable_sort(e->fanout_list.begin(), e->fanout_list.end(),
             [&](uint32_t a, uint32_t b) { return tb->cores[a].syn_count > tb->cores[b].syn_count; });
-    if (e->upload(&e->t.soma_core_list, e->soma_list.data(), e->soma_list.size()) != 0) return -1;
+
     if (e->upload(&e->t.fanout_core_list, e->fanout_list.data(), e->fanout_list.size()) != 0) return -1;
+    {
+        std::vector<uint32_t> active;
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+            if (tb->cores[c].neuron_count > 0 || tb->cores[c].axon_in_count > 0) active.push_back(c);
+        e->t.n_active_cores = static_cast<uint32_t>(active.size());
+        if (e->upload(&e->t.active_core_list, active.data(), active.size()) != 0) return -1;
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+    }
     {
         const CoreDev *p = nullptr;
         if (e->upload(&p, e->h_cores.data(), e->h_cores.size()) != 0) return -1;
@@ -1395,6 +1484,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->t.n_probes = tb->n_probes;
     e->t.n_neurons = tb->n_neurons;
     e->t.n_cost_classes = tb->n_cost_classes;
+    e->t.n_soma_classes = tb->n_soma_classes;
     e->t.n_fanout_cores = static_cast<uint32_t>(e->fanout_list.size());
     e->t.sync_delay = tb->sync_delay;
 
@@ -1458,6 +1548,34 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         }
     }
 
+    // ---- neuron-phase segments (after certification: they carry the accumulation mode)
+    {
+        std::vector<SomaSegment> segs;
+        for (uint32_t c : e->soma_list)
+        {
+            e->h_cores[c].seg_begin = static_cast<uint32_t>(segs.size());
+            const CoreDev &d = e->h_cores[c];
+            for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += kSomaThreads)
+            {
+                SomaSegment g;
+                g.k0 = k0;
+                g.neuron_begin = d.neuron_begin;
+                g.neuron_count = d.neuron_count;
+                g.fired_word_begin = d.fired_word_begin;
+                g.dend_base = d.dend_base;
+                g.ring = d.ring;
+                g.acc_mode = d.acc_mode;
+                g.pad = 0;
+                g.inv_scale = d.inv_scale;
+                segs.push_back(g);
+            }
+            e->h_cores[c].seg_count = static_cast<uint32_t>(segs.size()) - e->h_cores[c].seg_begin;
+        }
+        e->n_segments = static_cast<uint32_t>(segs.size());
+        if (e->upload(&e->t.soma_segments, segs.data(), segs.size()) != 0) return -1;
+        SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+    }
     // ---- state ---------------------------------------------------------------------
     if (e->alloc(&e->s.v, tb->n_neurons) != 0) return -1;
     if (e->alloc(&e->s.u, tb->n_neurons) != 0) return -1;
@@ -1471,7 +1589,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.din64, e->ordered_any ? dend_cells : 1) != 0) return -1;
     if (e->alloc(&e->s.hh, 5 * static_cast<size_t>(tb->n_hh)) != 0) return -1;
     e->s.n_hh = tb->n_hh;
-    if (e->alloc(&e->s.stats_n, tb->n_cores) != 0) return -1;
+    if (e->alloc(&e->s.stats_n, e->n_segments) != 0) return -1;
     if (e->alloc(&e->s.stats_m, tb->n_cores) != 0) return -1;
     e->log_cap = 4096;
     e->s.log_cap = e->log_cap;
@@ -1479,6 +1597,9 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.probe_out, tb->n_probes) != 0) return -1;
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->s.work, 1) != 0) return -1;
+    if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
+    e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads - 1) / kFinalThreads);
+    if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (engine_init_state(e) != 0) return -1;
 
@@ -1571,6 +1692,12 @@ extern "C" int sfe_engine_set_stream(sfe_engine *e, void *stream)
     return 0;
 }
 
+static void launch_soma(sfe_engine *e)
+{
+    if (e->exotic) soma_kernel<true><<<e->n_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
+    else soma_kernel<false><<<e->n_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
+}
+
 static void launch_fanout(sfe_engine *e)
 {
     const unsigned grid = e->fanout_grid;
@@ -1584,7 +1711,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
 {
     if (!e->soma_list.empty())
     {
-        soma_kernel<<<static_cast<unsigned>(e->soma_list.size()), kSomaThreads, 0, e->stream>>>(e->t, e->s);
+        launch_soma(e);
         ++e->launches;
     }
     if (probes && e->n_probes > 0)
@@ -1613,7 +1740,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
             e->ev_used += 2;
         }
     }
-    finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+    finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
     ++e->launches;
     ++e->total_timesteps;
     return 0;
@@ -1710,7 +1837,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
         {
             if (!e->soma_list.empty())
             {
-                soma_kernel<<<static_cast<unsigned>(e->soma_list.size()), kSomaThreads, 0, e->stream>>>(e->t, e->s);
+                launch_soma(e);
                 ++e->launches;
             }
             unsigned char *stage = static_cast<unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
@@ -1733,7 +1860,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 launch_fanout(e);
                 ++e->launches;
             }
-            finalize_kernel<<<1, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+            finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
             ++e->launches;
             ++e->total_timesteps;
         }
@@ -1839,6 +1966,7 @@ int sfe_engine_update_classes(sfe_engine *e, const sfe_soma_class *classes, uint
         e->t.classes = p;
         e->n_classes_cap = cap;
     }
+    e->t.n_soma_classes = n_classes;
     SFE_CUDA(cudaMemcpyAsync(e->d_classes, classes, n_classes * sizeof(sfe_soma_class), cudaMemcpyHostToDevice, e->stream));
     SFE_CUDA(cudaMemcpyAsync(e->d_neuron_class, neuron_class, e->n_neurons * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     SFE_CUDA(cudaStreamSynchronize(e->stream));
