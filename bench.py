@@ -43,6 +43,20 @@ FULL = dict(cores=1024, neurons_per_core=1024, dest_cores=8, syn_per_axon=125, s
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sanafe_ref")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per fanout_kernel launch from the committed
+    `ncu --set full` capture of this same workload (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_full_summary.json")
+    if not os.path.exists(path):
+        return None
+    def gb(text):
+        val, unit = text.split()[:2]
+        return float(val) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
+    vals = [gb(r["dram__bytes_read.sum"]) + gb(r["dram__bytes_write.sum"])
+            for r in json.load(open(path)) if "fanout_kernel" in r["Kernel Name"]]
+    return sum(vals) / len(vals) if vals else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -239,7 +253,9 @@ def main():
     achieved = fan_bytes / fan_s / 1e9 if fan_s > 0 else 0.0
     step_bytes = fan_bytes + 48.0 * n * args.steps
     roofline = {"bound": "hbm", "kernel": "fanout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic() if args.cores == FULL["cores"] else None,
+                "traffic_source": "profiles/r1_ncu_full_summary.json (ncu --set full, bytes per launch)",
+                "peak_source": peak_src,
                 "kernel_ms_per_launch": ms_fan.value / max(args.steps, 1),
                 "kernel_share_of_step": ms_fan.value / ms_total.value if ms_total.value > 0 else None,
                 "algorithmic_bytes_per_launch": fan_bytes / max(args.steps, 1),
