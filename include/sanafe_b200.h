@@ -278,14 +278,29 @@ int64_t sfe_engine_launch_count(const sfe_engine *e);
 /* device time (ms) of the steps enqueued between the last two timing marks */
 int sfe_engine_time_begin(sfe_engine *e);
 int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fanout);
-/* multi-GPU: raw device pointers of the fired bitmask (local slice written by the
- * neuron phase, full mask read by the message phase) so the caller can run the
- * NCCL all-gather between the two phases. */
-int sfe_engine_partition(sfe_engine *e, uint32_t rank, uint32_t world);
+/* ---- multi-GPU: the chip's cores are partitioned into `world` contiguous ranges (balanced by
+ * synapse count); rank r simulates range r. One timestep is
+ *     sfe_engine_enqueue_neuron_phase   local neuron phase, writes this rank's raster slice
+ *     all-gather of the slices          (NCCL by the caller: local ptr -> global ptr, equal sizes)
+ *     sfe_engine_enqueue_message_phase  raises the local inbox bits of every fired neuron of the
+ *                                       chip, then message phase + energy/timing of the local cores
+ * Per-step records are partial (local cores): sum counts/energies over ranks, max of sim_time. */
+sfe_engine *sfe_engine_create_partitioned(const sfe_tables *tables, int device, uint32_t rank, uint32_t world);
 int sfe_engine_enqueue_neuron_phase(sfe_engine *e);
 int sfe_engine_enqueue_message_phase(sfe_engine *e);
 void *sfe_engine_fired_local_ptr(sfe_engine *e, size_t *n_bytes);
 void *sfe_engine_fired_global_ptr(sfe_engine *e, size_t *n_bytes);
+/* caller-owned exchange buffers (device memory): local = slice, global = world * slice */
+int sfe_engine_set_exchange_buffers(sfe_engine *e, void *local, void *global);
+int64_t sfe_engine_collect_records(sfe_engine *e, sfe_step_record *out, int64_t cap);
+int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, uint32_t *world, uint32_t *slice_words,
+        uint32_t *local_cores, uint64_t *local_neurons);
+int sfe_engine_raster_layout(const sfe_engine *e, uint32_t *word_begin, size_t n_cores);
+int sfe_engine_synchronize(sfe_engine *e);
+int sfe_device_memcpy(void *dst, const void *src, size_t bytes);
+/* pinned host memory for buffers that cross the ABI every step */
+void *sfe_host_alloc(size_t bytes);
+void sfe_host_free(void *p);
 size_t sfe_engine_device_bytes(const sfe_engine *e);
 
 /* ---- description level --------------------------------------------------- */
@@ -304,6 +319,8 @@ void sfe_net_free(sfe_net *n);
 /* SpikingChip(arch)  src/chip.cpp:61-104. device < 0: host-only chip (lowering
  * and table export work; sim() fails with "no CUDA device"). */
 sfe_chip *sfe_chip_create(const sfe_arch *arch, int device);
+/* before load(): this chip object simulates partition `rank` of `world` (multi-GPU) */
+int sfe_chip_set_partition(sfe_chip *c, uint32_t rank, uint32_t world);
 void sfe_chip_destroy(sfe_chip *c);
 /* SpikingChip::load  src/chip.cpp:129-138 */
 int sfe_chip_load(sfe_chip *c, const sfe_net *net);

@@ -80,7 +80,11 @@ struct SomaSegment;
 struct DevTables
 {
     const CoreDev *cores;
-    const struct SomaSegment *soma_segments; // one record per neuron-phase segment
+    const struct SomaSegment *soma_segments; // one record per neuron-phase segment (local cores)
+    const struct SomaSegment *all_segments;  // segments of every core of the chip (multi-GPU expand)
+    uint32_t n_all_segments;
+    uint32_t partitioned;             // 1: this engine simulates a core range; spikes arrive via the exchanged raster
+    uint32_t inbox_lo, inbox_hi;      // local inbox word range [lo, hi)
     uint32_t n_soma_classes;
     const uint32_t *fanout_core_list; // cores that have axons-in
     const uint32_t *active_core_list; // cores with neurons or axons-in (ascending id)
@@ -107,7 +111,8 @@ struct DevState
     double *v, *u, *bias;
     int32_t *refractory;
     uint8_t *status;
-    uint32_t *fired_bits;  // padded per core
+    uint32_t *fired_bits;  // padded per core (write base of the neuron phase)
+    const uint32_t *fired_global; // raster of the whole chip (after the exchange when partitioned)
     uint32_t *inbox;       // padded per core
     uint32_t *din32;       // PACKED32: packed | DUAL32: sum
     uint32_t *dcnt32;      // DUAL32: count | ORDERED: has flag
@@ -440,9 +445,9 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         if (lane == 0 && k < ((core.neuron_count + 31u) & ~31u)) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
         // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon of a fired
         // neuron: raise the inbox bit of every target (loads batched eight at a time).
-        if (st == SFE_STATUS_FIRED)
+        if (st == SFE_STATUS_FIRED) n_packets += a1 - a0;
+        if (st == SFE_STATUS_FIRED && t.partitioned == 0u)
         {
-            n_packets += a1 - a0;
             for (uint32_t base = a0; base < a1; base += 8u)
             {
                 uint32_t bit[8];
@@ -504,6 +509,26 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
     if (model == SFE_SOMA_HH) v = s.hh[t.neuron_aux[i]];
     else if (model == SFE_SOMA_INPUT) v = 0.0; // PipelineUnit::get_potential default
     s.probe_out[p] = v;
+}
+
+// Multi-GPU: after the fired rasters of all partitions have been exchanged, every rank
+// raises the inbox bits of ITS axons for every neuron of the chip that fired
+// (partition by destination core, exchange the fired-source set).
+__global__ void __launch_bounds__(kSomaThreads) expand_kernel(const DevTables t, const DevState s)
+{
+    const SomaSegment seg = t.all_segments[blockIdx.x];
+    const uint32_t k = seg.k0 + threadIdx.x;
+    if (k >= seg.neuron_count) return;
+    const uint32_t word = __ldg(s.fired_global + seg.fired_word_begin + (k >> 5));
+    if (((word >> (k & 31)) & 1u) == 0u) return;
+    const uint32_t i = seg.neuron_begin + k;
+    const uint32_t a0 = __ldg(t.axon_out_begin + i), a1 = __ldg(t.axon_out_begin + i + 1);
+    for (uint32_t a = a0; a < a1; ++a)
+    {
+        const uint32_t bit = __ldg(t.axon_out_bit + a);
+        const uint32_t w = bit >> 5;
+        if (w >= t.inbox_lo && w < t.inbox_hi) atomicOr(&s.inbox[w], 1u << (bit & 31));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1129,7 +1154,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
 // Bulk synthetic network: synapse generation + exactness certificate on device
 // ---------------------------------------------------------------------------
 __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restrict__ syn_w,
-        uint32_t *__restrict__ syn_meta, const unsigned long long total)
+        uint32_t *__restrict__ syn_meta, const unsigned long long total, const uint32_t first_core)
 {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const uint32_t C = sp.cores, P = sp.neurons_per_core, D = sp.dest_cores, S = sp.syn_per_axon;
@@ -1138,7 +1163,7 @@ __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restric
     for (unsigned long long g = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
             g += stride)
     {
-        const uint32_t d = static_cast<uint32_t>(g / per_core);
+        const uint32_t d = first_core + static_cast<uint32_t>(g / per_core);
         const unsigned long long rem = g % per_core;
         const uint32_t slot = static_cast<uint32_t>(rem / Sp);
         const uint32_t j = static_cast<uint32_t>(rem % Sp);
@@ -1250,7 +1275,7 @@ struct sfe_engine
     sfe_soma_class *d_classes{nullptr};
     uint32_t n_classes_cap{0};
     std::vector<CoreDev> h_cores;
-    std::vector<uint32_t> soma_list, fanout_list;
+    std::vector<uint32_t> soma_list, fanout_list, all_soma_list;
     std::vector<uint32_t> fired_word_begin; // per core
     uint32_t fired_words{0}, inbox_words{0};
     uint32_t dend_cells{0};
@@ -1260,7 +1285,15 @@ struct sfe_engine
     unsigned fanout_grid{1};
     unsigned final_grid{1};
     uint32_t n_segments{0};
+    uint32_t n_all_segments{0};
     bool exotic{false};
+    // multi-GPU partition (contiguous core ranges)
+    uint32_t rank{0}, world{1};
+    std::vector<uint32_t> owner;      // rank that simulates each core
+    uint32_t slice_words{0};          // raster words per rank slice (equal for all ranks)
+    uint32_t *d_fired_local{nullptr}; // this rank's raster slice (slice_words)
+    uint32_t *d_fired_global{nullptr};// world * slice_words
+    bool external_exchange{false};
     uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0};
     int64_t total_timesteps{0};
     int64_t launches{0};
@@ -1359,13 +1392,40 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
     if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
 
+    // ---- partition: contiguous core ranges balanced by synapse + neuron work -------
+    e->owner.assign(tb->n_cores, 0);
+    if (e->world > 1)
+    {
+        double total = 0.0;
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+            total += static_cast<double>(tb->cores[c].syn_count) + 64.0 * tb->cores[c].neuron_count;
+        double before = 0.0;
+        uint32_t last = 0;
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+        {
+            const double w = static_cast<double>(tb->cores[c].syn_count) + 64.0 * tb->cores[c].neuron_count;
+            if (w > 0.0 && total > 0.0)
+                last = std::max(last, std::min(e->world - 1, static_cast<uint32_t>((before + 0.5 * w) * e->world / total)));
+            e->owner[c] = last;
+            before += w;
+        }
+    }
+    auto is_local = [&](uint32_t c) { return e->owner[c] == e->rank; };
+    // raster layout: one equal-sized slice per rank (all-gather friendly), cores word-aligned
+    {
+        std::vector<uint32_t> words(e->world, 0);
+        for (uint32_t c = 0; c < tb->n_cores; ++c) words[e->owner[c]] += (tb->cores[c].neuron_count + 31) / 32;
+        e->slice_words = std::max<uint32_t>(1, *std::max_element(words.begin(), words.end()));
+    }
+
     // ---- per-core device descriptors, padded bit layouts ---------------------
     e->h_cores.resize(tb->n_cores);
     std::vector<uint32_t> inbox_word_begin(tb->n_cores);
     e->fired_word_begin.resize(tb->n_cores);
-    uint32_t inbox_words = 0, fired_words = 0, dend_cells = 0;
+    uint32_t inbox_words = 0, dend_cells = 0;
+    std::vector<uint32_t> slice_fill(e->world, 0);
+    uint32_t inbox_lo = UINT32_MAX, inbox_hi = 0;
     size_t smem_max = 0;
-    std::vector<uint64_t> syn_counts(tb->n_cores);
     for (uint32_t c = 0; c < tb->n_cores; ++c)
     {
         const sfe_core_desc &cd = tb->cores[c];
@@ -1376,7 +1436,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.axon_begin = cd.axon_in_begin;
         d.axon_count = cd.axon_in_count;
         d.inbox_word_begin = inbox_words;
-        d.fired_word_begin = fired_words;
+        d.fired_word_begin = e->owner[c] * e->slice_words + slice_fill[e->owner[c]];
         d.dend_base = dend_cells;
         d.ring = cd.ring == 0 ? 1 : cd.ring;
         d.acc_mode = cd.acc_mode;
@@ -1395,19 +1455,28 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.e_south = tile.energy_south;
         d.e_north = tile.energy_north;
         inbox_word_begin[c] = inbox_words;
-        e->fired_word_begin[c] = fired_words;
+        e->fired_word_begin[c] = d.fired_word_begin;
+        if (is_local(c) && cd.axon_in_count > 0)
+        {
+            inbox_lo = std::min(inbox_lo, inbox_words);
+            inbox_hi = std::max(inbox_hi, inbox_words + (cd.axon_in_count + 31) / 32);
+        }
         inbox_words += (cd.axon_in_count + 31) / 32;
-        fired_words += (cd.neuron_count + 31) / 32;
+        slice_fill[e->owner[c]] += (cd.neuron_count + 31) / 32;
         dend_cells += cd.neuron_count * d.ring;
-        syn_counts[c] = cd.syn_count;
+        if (cd.neuron_count > 0) e->all_soma_list.push_back(c);
+        if (!is_local(c)) continue;
         if (cd.neuron_count > 0) e->soma_list.push_back(c);
         if (cd.axon_in_count > 0) e->fanout_list.push_back(c);
         if (cd.acc_mode == SFE_ACC_ORDERED) e->ordered_any = true;
         if (cd.acc_mode == SFE_ACC_DUAL32) e->dual_any = true;
     }
     e->inbox_words = inbox_words;
-    e->fired_words = fired_words;
+    e->fired_words = e->world * e->slice_words;
     e->dend_cells = dend_cells;
+    e->t.partitioned = e->world > 1 ? 1u : 0u;
+    e->t.inbox_lo = inbox_lo == UINT32_MAX ? 0u : inbox_lo;
+    e->t.inbox_hi = inbox_hi;
 
     // ---- static tables -----------------------------------------------------------
     if (e->upload(&e->t.classes, tb->soma_classes, tb->n_soma_classes) != 0) return -1;
@@ -1444,6 +1513,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     {
         const sfe_core_desc &cd = tb->cores[c];
         e->h_cores[c].syn_begin = padded_total;
+        if (!is_local(c)) continue; // another rank holds this core's synapses
         uint64_t off = 0;
         for (uint32_t a = 0; a < cd.axon_in_count; ++a)
         {
@@ -1503,7 +1573,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         for (uint32_t c = 0; c < tb->n_cores; ++c)
         {
             const sfe_core_desc &cd = tb->cores[c];
-            if (cd.axon_in_count == 0) continue;
+            if (cd.axon_in_count == 0 || !is_local(c)) continue;
             const sfe_axon_in &last = dev_axons[cd.axon_in_begin + cd.axon_in_count - 1];
             const uint64_t core_padded = last.syn_off + ((static_cast<uint64_t>(last.syn_count) + 3u) & ~3ull);
             pw.assign(core_padded, 0.0);
@@ -1520,14 +1590,15 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             SFE_CUDA(cudaStreamSynchronize(e->stream));
         }
     }
-    else if (tb->n_synapses > 0)
+    else if (tb->n_synapses > 0 && padded_total > 0)
     {
         if (tb->synth == nullptr)
         {
             sfe::set_last_error("tables carry neither synapse arrays nor a synthetic spec");
             return -1;
         }
-        synth_generate_kernel<<<148 * 16, 256, 0, e->stream>>>(*tb->synth, d_w, d_m, padded_total);
+        const uint32_t first_local = e->fanout_list.empty() ? 0u : *std::min_element(e->fanout_list.begin(), e->fanout_list.end());
+        synth_generate_kernel<<<148 * 16, 256, 0, e->stream>>>(*tb->synth, d_w, d_m, padded_total, first_local);
         SFE_CUDA(cudaGetLastError());
         // certificate computed where the synapses are
         uint32_t max_p = 0;
@@ -1573,6 +1644,26 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         }
         e->n_segments = static_cast<uint32_t>(segs.size());
         if (e->upload(&e->t.soma_segments, segs.data(), segs.size()) != 0) return -1;
+        if (e->world > 1)
+        {
+            std::vector<SomaSegment> all;
+            for (uint32_t c : e->all_soma_list)
+            {
+                const CoreDev &d = e->h_cores[c];
+                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += kSomaThreads)
+                {
+                    SomaSegment g{};
+                    g.k0 = k0;
+                    g.neuron_begin = d.neuron_begin;
+                    g.neuron_count = d.neuron_count;
+                    g.fired_word_begin = d.fired_word_begin;
+                    all.push_back(g);
+                }
+            }
+            e->n_all_segments = static_cast<uint32_t>(all.size());
+            e->t.n_all_segments = e->n_all_segments;
+            if (e->upload(&e->t.all_segments, all.data(), all.size()) != 0) return -1;
+        }
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -1582,7 +1673,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.bias, tb->n_neurons) != 0) return -1;
     if (e->alloc(&e->s.refractory, tb->n_neurons) != 0) return -1;
     if (e->alloc(&e->s.status, tb->n_neurons) != 0) return -1;
-    if (e->alloc(&e->s.fired_bits, fired_words) != 0) return -1;
+    if (e->alloc(&e->d_fired_global, e->fired_words) != 0) return -1;
+    if (e->world > 1)
+    {
+        if (e->alloc(&e->d_fired_local, e->slice_words) != 0) return -1;
+    }
+    else e->d_fired_local = e->d_fired_global;
+    // the neuron phase indexes the raster with chip-wide word offsets: bias the write
+    // base so that this rank's slice lands at the start of its local buffer
+    e->s.fired_bits = e->d_fired_local - static_cast<size_t>(e->rank) * e->slice_words * (e->world > 1 ? 1 : 0);
+    e->s.fired_global = e->d_fired_global;
     if (e->alloc(&e->s.inbox, inbox_words) != 0) return -1;
     if (e->alloc(&e->s.din32, dend_cells) != 0) return -1;
     if (e->alloc(&e->s.dcnt32, (e->ordered_any || e->dual_any) ? dend_cells : 1) != 0) return -1;
@@ -1647,11 +1747,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     return 0;
 }
 
-extern "C" sfe_engine *sfe_engine_create(const sfe_tables *tables, int device)
+extern "C" sfe_engine *sfe_engine_create_partitioned(const sfe_tables *tables, int device, uint32_t rank, uint32_t world)
 {
     if (tables == nullptr || tables->abi_version != SFE_ABI_VERSION)
     {
         sfe::set_last_error("sfe_engine_create: bad tables / ABI version");
+        return nullptr;
+    }
+    if (world == 0 || rank >= world)
+    {
+        sfe::set_last_error("sfe_engine_create_partitioned: need rank < world");
         return nullptr;
     }
     if (sfe_device_count() <= 0)
@@ -1661,12 +1766,19 @@ extern "C" sfe_engine *sfe_engine_create(const sfe_tables *tables, int device)
     }
     sfe_engine *e = new sfe_engine();
     e->device = device;
+    e->rank = rank;
+    e->world = world;
     if (engine_build(e, tables) != 0)
     {
         sfe_engine_destroy(e);
         return nullptr;
     }
     return e;
+}
+
+extern "C" sfe_engine *sfe_engine_create(const sfe_tables *tables, int device)
+{
+    return sfe_engine_create_partitioned(tables, device, 0, 1);
 }
 
 extern "C" void sfe_engine_destroy(sfe_engine *e)
@@ -1749,6 +1861,11 @@ static int enqueue_step(sfe_engine *e, bool probes)
 extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
 {
     SFE_CUDA(cudaSetDevice(e->device));
+    if (e->world > 1)
+    {
+        sfe::set_last_error("sfe_engine_enqueue: a partitioned engine needs the raster exchange between the phases");
+        return -1;
+    }
     if (e->total_timesteps - e->log_read + timesteps > e->log_cap)
     {
         sfe::set_last_error("sfe_engine_enqueue: more than " + std::to_string(e->log_cap) +
@@ -1814,6 +1931,12 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
         sfe::set_last_error("sfe_engine_run: uncollected enqueued steps; call sfe_engine_collect first");
         return -1;
     }
+    if (e->world > 1)
+    {
+        sfe::set_last_error("sfe_engine_run: a partitioned engine is stepped with sfe_engine_enqueue_neuron_phase / "
+                            "exchange / sfe_engine_enqueue_message_phase");
+        return -1;
+    }
     sfe_run_data rd;
     std::memset(&rd, 0, sizeof(rd));
     rd.timestep_start = e->total_timesteps + 1; // src/chip.cpp:481
@@ -1843,7 +1966,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
             unsigned char *stage = static_cast<unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
             if (want_fired)
             {
-                SFE_CUDA(cudaMemcpyAsync(stage, e->s.fired_bits, e->fired_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+                SFE_CUDA(cudaMemcpyAsync(stage, e->d_fired_global, e->fired_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
                 stage += e->fired_words * sizeof(uint32_t);
             }
             if (want_pot)
@@ -2047,27 +2170,145 @@ extern "C" int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fan
     return 0;
 }
 
-// multi-GPU hooks: see engine_multi.cu (not in this build yet)
-extern "C" int sfe_engine_partition(sfe_engine *, uint32_t, uint32_t)
+// ---- multi-GPU: one engine per rank, spikes exchanged as a fired-bit raster ---------------
+// step = enqueue_neuron_phase -> all-gather(local slice -> global raster) -> enqueue_message_phase
+extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
 {
-    sfe::set_last_error("sfe_engine_partition: not implemented yet");
-    return -1;
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->total_timesteps - e->log_read + 1 > e->log_cap)
+    {
+        sfe::set_last_error("more than " + std::to_string(e->log_cap) + " uncollected steps; call sfe_engine_collect_records");
+        return -1;
+    }
+    if (!e->soma_list.empty())
+    {
+        launch_soma(e);
+        ++e->launches;
+    }
+    SFE_CUDA(cudaGetLastError());
+    return 0;
 }
-extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *)
+
+extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
 {
-    sfe::set_last_error("not implemented yet");
-    return -1;
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->world > 1 && e->n_all_segments > 0)
+    {
+        expand_kernel<<<e->n_all_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
+        ++e->launches;
+    }
+    if (!e->fanout_list.empty())
+    {
+        launch_fanout(e);
+        ++e->launches;
+    }
+    finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+    ++e->launches;
+    ++e->total_timesteps;
+    SFE_CUDA(cudaGetLastError());
+    return 0;
 }
-extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *)
+
+extern "C" void *sfe_engine_fired_local_ptr(sfe_engine *e, size_t *n_bytes)
 {
-    sfe::set_last_error("not implemented yet");
-    return -1;
+    if (n_bytes != nullptr) *n_bytes = static_cast<size_t>(e->slice_words) * sizeof(uint32_t);
+    return e->d_fired_local;
 }
-extern "C" void *sfe_engine_fired_local_ptr(sfe_engine *, size_t *)
+
+extern "C" void *sfe_engine_fired_global_ptr(sfe_engine *e, size_t *n_bytes)
 {
-    return nullptr;
+    if (n_bytes != nullptr) *n_bytes = static_cast<size_t>(e->fired_words) * sizeof(uint32_t);
+    return e->d_fired_global;
 }
-extern "C" void *sfe_engine_fired_global_ptr(sfe_engine *, size_t *)
+
+// Let the caller own the exchange buffers (e.g. torch tensors handed to NCCL):
+// local = slice_words u32, global = world * slice_words u32, both device memory.
+extern "C" int sfe_engine_set_exchange_buffers(sfe_engine *e, void *local, void *global)
 {
-    return nullptr;
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    e->d_fired_local = static_cast<uint32_t *>(local);
+    e->d_fired_global = static_cast<uint32_t *>(global);
+    e->s.fired_bits = e->d_fired_local - static_cast<size_t>(e->rank) * e->slice_words * (e->world > 1 ? 1 : 0);
+    e->s.fired_global = e->d_fired_global;
+    e->external_exchange = true;
+    return 0;
+}
+
+// per-step records of this rank's partition since the last collect (counts / energies are
+// partial sums over the local cores, sim_time the local maximum): the caller sums the former
+// over ranks and takes the maximum of the latter, step by step
+extern "C" int64_t sfe_engine_collect_records(sfe_engine *e, sfe_step_record *out, int64_t cap)
+{
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    const int64_t pending = e->total_timesteps - e->log_read;
+    if (pending > cap)
+    {
+        sfe::set_last_error("sfe_engine_collect_records: buffer too small");
+        return -1;
+    }
+    std::vector<sfe_step_record> recs;
+    if (collect_records(e, recs) != 0) return -1;
+    std::memcpy(out, recs.data(), recs.size() * sizeof(sfe_step_record));
+    return pending;
+}
+
+extern "C" int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, uint32_t *world, uint32_t *slice_words,
+        uint32_t *local_cores, uint64_t *local_neurons)
+{
+    if (rank != nullptr) *rank = e->rank;
+    if (world != nullptr) *world = e->world;
+    if (slice_words != nullptr) *slice_words = e->slice_words;
+    if (local_cores != nullptr) *local_cores = static_cast<uint32_t>(e->soma_list.size());
+    if (local_neurons != nullptr)
+    {
+        uint64_t n = 0;
+        for (uint32_t c : e->soma_list) n += e->core_desc[c].neuron_count;
+        *local_neurons = n;
+    }
+    return 0;
+}
+
+extern "C" int sfe_engine_synchronize(sfe_engine *e)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// plain cudaMemcpy (any direction, unified addressing); for tests and small exchanges
+extern "C" int sfe_device_memcpy(void *dst, const void *src, size_t bytes)
+{
+    SFE_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return 0;
+}
+
+// first raster word of every core in the (global) fired raster
+extern "C" int sfe_engine_raster_layout(const sfe_engine *e, uint32_t *word_begin, size_t n_cores)
+{
+    if (n_cores != e->fired_word_begin.size())
+    {
+        sfe::set_last_error("sfe_engine_raster_layout: expected one slot per core");
+        return -1;
+    }
+    std::memcpy(word_begin, e->fired_word_begin.data(), n_cores * sizeof(uint32_t));
+    return 0;
+}
+
+// pinned host memory for buffers that cross the ABI every step (bias vectors, rasters)
+extern "C" void *sfe_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        sfe::set_last_error("sfe_host_alloc: cudaMallocHost failed");
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void sfe_host_free(void *p)
+{
+    if (p != nullptr) cudaFreeHost(p);
 }

@@ -47,6 +47,7 @@ struct sfe_chip
     // SpikingChip running totals (src/chip.cpp:535-547, 602-621)
     double total_energy{0.0};
     double total_sim_time{0.0};
+    uint32_t rank{0}, world{1};
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -79,7 +80,7 @@ int attach_engine(sfe_chip *c)
     c->total_energy = 0.0;
     c->total_sim_time = 0.0;
     if (c->device < 0) return 0; // host-only chip: lowering + table export
-    c->engine = sfe_engine_create(&c->tables.view, c->device);
+    c->engine = sfe_engine_create_partitioned(&c->tables.view, c->device, c->rank, c->world);
     return c->engine != nullptr ? 0 : -1;
 }
 } // namespace
@@ -151,6 +152,18 @@ extern "C" sfe_chip *sfe_chip_create(const sfe_arch *arch, int device)
                 return new sfe_chip(*arch->arch, device);
             },
             nullptr);
+}
+
+extern "C" int sfe_chip_set_partition(sfe_chip *c, uint32_t rank, uint32_t world)
+{
+    if (world == 0 || rank >= world)
+    {
+        sfe::set_last_error("sfe_chip_set_partition: need rank < world");
+        return -1;
+    }
+    c->rank = rank;
+    c->world = world;
+    return 0;
 }
 
 extern "C" void sfe_chip_destroy(sfe_chip *c)

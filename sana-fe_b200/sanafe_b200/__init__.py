@@ -147,7 +147,15 @@ def lib():
         "sfe_engine_total_timesteps": (i64, [vp]), "sfe_engine_launch_count": (i64, [vp]),
         "sfe_engine_time_begin": (C.c_int, [vp]),
         "sfe_engine_time_end": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-        "sfe_engine_partition": (C.c_int, [vp, u32, u32]),
+        "sfe_engine_create_partitioned": (vp, [C.POINTER(Tables), C.c_int, u32, u32]),
+        "sfe_engine_set_exchange_buffers": (C.c_int, [vp, vp, vp]),
+        "sfe_engine_collect_records": (i64, [vp, vp, i64]),
+        "sfe_engine_partition_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
+        "sfe_chip_set_partition": (C.c_int, [vp, u32, u32]),
+        "sfe_engine_raster_layout": (C.c_int, [vp, vp, sz]),
+        "sfe_engine_synchronize": (C.c_int, [vp]),
+        "sfe_device_memcpy": (C.c_int, [vp, vp, sz]),
+        "sfe_host_alloc": (vp, [sz]), "sfe_host_free": (None, [vp]),
         "sfe_engine_enqueue_neuron_phase": (C.c_int, [vp]), "sfe_engine_enqueue_message_phase": (C.c_int, [vp]),
         "sfe_engine_fired_local_ptr": (vp, [vp, C.POINTER(sz)]), "sfe_engine_fired_global_ptr": (vp, [vp, C.POINTER(sz)]),
         "sfe_engine_device_bytes": (sz, [vp]),
@@ -245,6 +253,10 @@ class SpikingChip:
         if getattr(self, "_h", None):
             lib().sfe_chip_destroy(self._h)
             self._h = None
+
+    def set_partition(self, rank, world):
+        """Multi-GPU: this chip simulates core range `rank` of `world` (call before load)."""
+        _check(lib().sfe_chip_set_partition(self._h, rank, world))
 
     def load(self, net, overwrite=False):
         _check(lib().sfe_chip_load(self._h, net._h))
@@ -368,3 +380,108 @@ class SpikingChip:
                 f.write(text)
         else:
             sink.write(text)
+
+
+def merge_partition_records(per_rank):
+    """Combine the per-step records of all partitions of one chip: counts and energies
+    are partial sums over each rank's cores (summed in rank order), sim_time is the
+    local maximum (simple timing model: max over cores, src/schedule.cpp:89-98)."""
+    out = per_rank[0].copy()
+    for rec in per_rank[1:]:
+        for name in out.dtype.names:
+            if name == "sim_time":
+                out[name] = np.maximum(out[name], rec[name])
+            else:
+                out[name] = out[name] + rec[name]
+    return out
+
+
+def run_data_from_records(records, timestep_start=1):
+    """RunData totals from per-step records, accumulated step by step (src/chip.cpp:462-475)."""
+    rd = RunData()
+    rd.timestep_start = timestep_start
+    rd.timesteps_executed = len(records)
+    for r in records:
+        rd.total_energy += float(r["total_energy"])
+        rd.synapse_energy += float(r["synapse_energy"])
+        rd.dendrite_energy += float(r["dendrite_energy"])
+        rd.soma_energy += float(r["soma_energy"])
+        rd.network_energy += float(r["network_energy"])
+        rd.sim_time += float(r["sim_time"])
+        rd.spikes += int(r["spike_count"])
+        rd.packets_sent += int(r["packets_sent"])
+        rd.neurons_updated += int(r["neurons_updated"])
+        rd.neurons_fired += int(r["neurons_fired"])
+    return rd
+
+
+class PartitionedChip:
+    """One simulated chip split over `world` engines (one per GPU; all on one device
+    when `devices` repeats an index, which is how the single-GPU tests emulate the
+    multi-GPU path). `exchange` moves every rank's raster slice into every rank's
+    global raster between the two phases of a step: device copies here, an NCCL
+    all-gather in bench.py."""
+
+    def __init__(self, make_chip, world, devices=None):
+        self.world = world
+        self.chips = []
+        for r in range(world):
+            chip = make_chip(devices[r] if devices else 0, r, world)
+            self.chips.append(chip)
+        L = lib()
+        self.local, self.glob = [], []
+        for c in self.chips:
+            nb = C.c_size_t()
+            self.local.append(L.sfe_engine_fired_local_ptr(c.engine, C.byref(nb)))
+            self.slice_bytes = nb.value
+            self.glob.append(L.sfe_engine_fired_global_ptr(c.engine, C.byref(nb)))
+            self.global_bytes = nb.value
+
+    def exchange(self):
+        L = lib()
+        for c in self.chips:
+            _check(L.sfe_engine_synchronize(c.engine))
+        for dst in range(self.world):
+            for src in range(self.world):
+                _check(L.sfe_device_memcpy(self.glob[dst] + src * self.slice_bytes, self.local[src], self.slice_bytes))
+
+    def step(self):
+        L = lib()
+        for c in self.chips:
+            _check(L.sfe_engine_enqueue_neuron_phase(c.engine))
+        self.exchange()
+        for c in self.chips:
+            _check(L.sfe_engine_enqueue_message_phase(c.engine))
+
+    def raster(self):
+        """Global fired raster of the last step in device-index bit order."""
+        L = lib()
+        c0 = self.chips[0]
+        t = c0.tables
+        _check(L.sfe_engine_synchronize(c0.engine))
+        padded = np.zeros(self.global_bytes // 4, dtype=np.uint32)
+        _check(L.sfe_device_memcpy(padded.ctypes.data, self.glob[0], self.global_bytes))
+        begin = np.zeros(t.n_cores, dtype=np.uint32)
+        _check(L.sfe_engine_raster_layout(c0.engine, begin.ctypes.data, t.n_cores))
+        bits = np.zeros(t.n_neurons, dtype=bool)
+        for c in range(t.n_cores):
+            cd = t.cores[c]
+            if cd.neuron_count == 0:
+                continue
+            words = padded[begin[c]:begin[c] + (cd.neuron_count + 31) // 32]
+            unpacked = np.unpackbits(words.view(np.uint8), bitorder="little")[:cd.neuron_count]
+            bits[cd.neuron_begin:cd.neuron_begin + cd.neuron_count] = unpacked.astype(bool)
+        return np.packbits(bits, bitorder="little").view(np.uint8)
+
+    def collect(self):
+        """Merged per-step records of the steps run since the last collect."""
+        L = lib()
+        per_rank = []
+        for c in self.chips:
+            n = L.sfe_engine_total_timesteps(c.engine)
+            buf = np.zeros(max(n, 1), dtype=STEP_DTYPE)
+            got = L.sfe_engine_collect_records(c.engine, buf.ctypes.data, len(buf))
+            if got < 0:
+                raise SanafeError(L.sfe_last_error().decode())
+            per_rank.append(buf[:got])
+        return merge_partition_records(per_rank)
