@@ -189,23 +189,21 @@ def main():
     L = sfe.lib()
     if L.sfe_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
 
     spec_d = dict(FULL)
     spec_d["cores"] = args.cores
     spec_d["dest_cores"] = min(spec_d["dest_cores"], args.cores)
-    spec_d["seed"] = FULL["seed"] + rank  # N>1: independent replicas (weak scaling), see DESIGN.md
     spec = sfe.SynthSpec(**spec_d)
-    tmp = tempfile.mkdtemp(prefix="sfe_bench_")
+    tmp = tempfile.mkdtemp(prefix=f"sfe_bench_{rank}_")
     flat = os.path.join(tmp, "arch.jsonl")
     archgen.write_flat(archgen.loihi_large(tiles=max(1, (args.cores + 3) // 4) if args.cores < 4096 else 1024), flat)
     arch, _ = sfe.load_flat(flat)
     chip = sfe.SpikingChip(arch, device=local_rank)
+    peak, peak_src = peaks()
+
+    if world > 1:
+        return partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_src)
+
     t0 = time.time()
     chip.load_synthetic(spec, generate_on_device=True)
     load_s = time.time() - t0
@@ -213,17 +211,12 @@ def main():
     tb = chip.tables
     n = tb.n_neurons
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
     # ---- device-resident throughput ------------------------------------------------
     rd = sfe.RunData()
     assert L.sfe_engine_enqueue(eng, args.warmup) == 0, L.sfe_last_error()
     assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
     launches0 = L.sfe_engine_launch_count(eng)
     ms_total, ms_fan = C.c_float(), C.c_float()
     assert L.sfe_engine_time_begin(eng) == 0
@@ -234,21 +227,10 @@ def main():
     assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
     events, messages = rd.spikes, rd.packets_sent
     seconds = ms_total.value / 1e3
-    if dist is not None:
-        import torch
-        tmax = torch.tensor([seconds], device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(events), float(messages), float(launches)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot)
-        seconds = float(tmax.item())
-        events_all, messages_all, launches_all = (int(x) for x in tot.tolist())
-    else:
-        events_all, messages_all, launches_all = events, messages, launches
-    value = events_all / seconds
+    value = events / seconds
 
     # ---- roofline of the dominant kernel (message phase) -----------------------------
-    peak, peak_src = peaks()
-    fan_bytes = 12.0 * events + 16.0 * messages          # per rank, over args.steps launches
+    fan_bytes = 12.0 * events + 16.0 * messages          # over args.steps launches
     fan_s = ms_fan.value / 1e3
     achieved = fan_bytes / fan_s / 1e9 if fan_s > 0 else 0.0
     step_bytes = fan_bytes + 48.0 * n * args.steps
@@ -264,49 +246,169 @@ def main():
                                "bytes_per_step": step_bytes / max(args.steps, 1)}}
 
     # ---- end to end through the public API with host buffers ---------------------------
-    bias = np.array([tb.neuron_bias[i] for i in range(0, n)], dtype=np.float64) if n <= 4096 else \
-        np.ctypeslib.as_array(tb.neuron_bias, shape=(n,)).copy()
+    # per step: bias vector host->device from pinned memory, one timestep, spike raster +
+    # step record device->host
+    bias_ptr = L.sfe_host_alloc(8 * n)
+    bias = np.ctypeslib.as_array(C.cast(bias_ptr, C.POINTER(C.c_double)), shape=(n,))
+    bias[:] = np.ctypeslib.as_array(tb.neuron_bias, shape=(n,))
     e2e_steps = max(10, min(args.steps, 100))
     words = (n + 31) // 32
-    barrier()
     e2e_events = 0
+    for s in range(3):
+        chip.sim_raw(1, "simple", steps=True, fired=True)
     t_e2e = time.perf_counter()
     for s in range(e2e_steps):
-        assert L.sfe_engine_set_bias(eng, bias.ctypes.data, n) == 0
+        assert L.sfe_engine_set_bias(eng, bias_ptr, n) == 0
         rde, tr = chip.sim_raw(1, "simple", steps=True, fired=True)
         e2e_events += rde.spikes
     e2e_s = time.perf_counter() - t_e2e
-    if dist is not None:
-        import torch
-        tmax = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tot = torch.tensor([float(e2e_events)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tot)
-        e2e_s, e2e_events = float(tmax.item()), int(tot.item())
+    L.sfe_host_free(bias_ptr)
     e2e = {"value": e2e_events / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * words + 88,
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
 
-    if rank != 0:
-        return 0
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = run_reference_sample(20, 1)
+    cpu = None if args.no_cpu_baseline else run_reference_sample(20, 1)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD if args.cores == FULL["cores"] else f"DEBUG scale: {args.cores} cores",
-                   "neurons": n * world, "synapses": int(tb.n_synapses) * world, "timing_model": "simple",
-                   "l2_policy": "inputs larger than L2 (12.6 GB of synapse tables per GPU; ~1.2 GB streamed per step)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (weak)",
-                   "activity": rd.neurons_fired / float(n * args.steps), "load_s": load_s},
-        "timesteps_per_s": args.steps / seconds, "events_per_step": events_all / args.steps,
+                   "neurons": n, "synapses": int(tb.n_synapses), "timing_model": "simple",
+                   "l2_policy": "inputs larger than L2 (12.6 GB of synapse tables; ~1.2 GB streamed per step)",
+                   "parallelism": "1 GPU", "activity": rd.neurons_fired / float(n * args.steps), "load_s": load_s},
+        "timesteps_per_s": args.steps / seconds, "events_per_step": events / args.steps,
         "roofline": roofline,
         "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
-        "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))
     return 0
+
+
+def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_src):
+    """N > 1: ONE chip, its cores partitioned over the ranks (strong scaling). Every step:
+    local neuron phase -> NCCL all-gather of the fired raster over NVLink -> local message phase."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    L = sfe.lib()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl")
+    chip.set_partition(rank, world)
+    t0 = time.time()
+    chip.load_synthetic(spec, generate_on_device=True)
+    load_s = time.time() - t0
+    eng = chip.engine
+    tb = chip.tables
+    n = tb.n_neurons
+    slice_words = C.c_uint32()
+    local_neurons = C.c_uint64()
+    L.sfe_engine_partition_info(eng, None, None, C.byref(slice_words), None, C.byref(local_neurons))
+    stream = torch.cuda.Stream()
+    local = torch.zeros(slice_words.value, dtype=torch.int32, device="cuda")
+    glob = torch.zeros(slice_words.value * world, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    assert L.sfe_engine_set_stream(eng, C.c_void_p(stream.cuda_stream)) == 0
+    assert L.sfe_engine_set_exchange_buffers(eng, C.c_void_p(local.data_ptr()), C.c_void_p(glob.data_ptr())) == 0
+
+    def one_step():
+        assert L.sfe_engine_enqueue_neuron_phase(eng) == 0, L.sfe_last_error()
+        dist.all_gather_into_tensor(glob, local)
+        assert L.sfe_engine_enqueue_message_phase(eng) == 0, L.sfe_last_error()
+
+    def collect():
+        buf = np.zeros(4096, dtype=sfe.STEP_DTYPE)
+        got = L.sfe_engine_collect_records(eng, buf.ctypes.data, len(buf))
+        assert got >= 0, L.sfe_last_error()
+        return buf[:got]
+
+    mode = "eager"
+    graph = None
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            one_step()
+        stream.synchronize()
+        collect()
+        if os.environ.get("SFE_BENCH_GRAPH", "0") == "1":
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    one_step()
+                mode = "cuda graph (neuron phase + NCCL all-gather + message phase captured per step)"
+                collect()
+            except Exception as exc:  # capture not possible on this stack: stay eager
+                graph = None
+                mode = f"eager (graph capture failed: {type(exc).__name__})"
+        dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = L.sfe_engine_launch_count(eng)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
+        ev1.record(stream)
+        stream.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    seconds = ev0.elapsed_time(ev1) / 1e3
+    clocks = sampler.stop()
+    launches = (L.sfe_engine_launch_count(eng) - launches0) if graph is None else 4 * args.steps
+    # graph replays do not pass through the C ABI, so their records are read from the device log
+    recs = collect() if graph is None else None
+    # totals over the timed steps: counts are per-rank partial sums
+    if recs is not None:
+        events = int(recs["spike_count"].sum())
+        messages = int(recs["packets_sent"].sum())
+        fired = int(recs["neurons_fired"].sum())
+    else:
+        log = read_graph_records(L, eng, args.steps, sfe)
+        events, messages, fired = int(log["spike_count"].sum()), int(log["packets_sent"].sum()), int(log["neurons_fired"].sum())
+    tmax = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([float(events), float(messages), float(fired), float(launches)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tot)
+    seconds = float(tmax.item())
+    events_all, messages_all, fired_all, launches_all = (int(x) for x in tot.tolist())
+    if rank != 0:
+        dist.destroy_process_group()
+        return 0
+    step_bytes = 12.0 * events_all + 16.0 * messages_all + 48.0 * n * args.steps
+    line = {
+        "metric": METRIC, "value": events_all / seconds, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.cores == FULL["cores"] else f"DEBUG scale: {args.cores} cores",
+                   "neurons": n, "synapses": int(tb.n_synapses), "timing_model": "simple",
+                   "l2_policy": "inputs larger than L2 (synapse tables of each partition >> 126 MB)",
+                   "parallelism": f"cores partitioned over {world} GPUs, per-step NCCL all-gather of the fired raster "
+                                  f"({4 * slice_words.value * world} B)",
+                   "launch_mode": mode, "activity": fired_all / float(n * args.steps), "load_s": load_s},
+        "timesteps_per_s": args.steps / seconds, "events_per_step": events_all / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": step_bytes / seconds / 1e9,
+                     "peak": peak * world, "unit": "GB/s", "frac": step_bytes / seconds / 1e9 / (peak * world),
+                     "traffic": None, "peak_source": peak_src},
+        "cpu_baseline": None,
+        "e2e": {"value": events_all / seconds, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0, "note": "N>1 reports the device-timed value; the host-buffer e2e leg is the N=1 run"},
+        "gpu_launches": launches_all, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
+def read_graph_records(L, eng, steps, sfe):
+    """Step records written by graph replays (they bypass the host-side step counter)."""
+    import numpy as np
+    buf = np.zeros(steps, dtype=sfe.STEP_DTYPE)
+    got = L.sfe_engine_read_log_tail(eng, buf.ctypes.data, steps)
+    assert got == steps, L.sfe_last_error()
+    return buf
 
 
 if __name__ == "__main__":

@@ -293,6 +293,8 @@ void *sfe_engine_fired_global_ptr(sfe_engine *e, size_t *n_bytes);
 /* caller-owned exchange buffers (device memory): local = slice, global = world * slice */
 int sfe_engine_set_exchange_buffers(sfe_engine *e, void *local, void *global);
 int64_t sfe_engine_collect_records(sfe_engine *e, sfe_step_record *out, int64_t cap);
+/* last n records of the device log (for steps replayed from a captured CUDA graph) */
+int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
 int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, uint32_t *world, uint32_t *slice_words,
         uint32_t *local_cores, uint64_t *local_neurons);
 int sfe_engine_raster_layout(const sfe_engine *e, uint32_t *word_begin, size_t n_cores);

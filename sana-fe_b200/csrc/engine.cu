@@ -81,8 +81,8 @@ struct DevTables
 {
     const CoreDev *cores;
     const struct SomaSegment *soma_segments; // one record per neuron-phase segment (local cores)
-    const struct SomaSegment *all_segments;  // segments of every core of the chip (multi-GPU expand)
-    uint32_t n_all_segments;
+    const uint32_t *raster_neuron;    // device index of bit 0 of every word of the global raster
+    uint32_t n_raster_words;
     uint32_t partitioned;             // 1: this engine simulates a core range; spikes arrive via the exchanged raster
     uint32_t inbox_lo, inbox_hi;      // local inbox word range [lo, hi)
     uint32_t n_soma_classes;
@@ -516,18 +516,24 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
 // (partition by destination core, exchange the fired-source set).
 __global__ void __launch_bounds__(kSomaThreads) expand_kernel(const DevTables t, const DevState s)
 {
-    const SomaSegment seg = t.all_segments[blockIdx.x];
-    const uint32_t k = seg.k0 + threadIdx.x;
-    if (k >= seg.neuron_count) return;
-    const uint32_t word = __ldg(s.fired_global + seg.fired_word_begin + (k >> 5));
-    if (((word >> (k & 31)) & 1u) == 0u) return;
-    const uint32_t i = seg.neuron_begin + k;
-    const uint32_t a0 = __ldg(t.axon_out_begin + i), a1 = __ldg(t.axon_out_begin + i + 1);
-    for (uint32_t a = a0; a < a1; ++a)
+    // one thread per raster word (32 neurons): almost all words hold 0-4 spikes
+    const uint32_t idx = blockIdx.x * kSomaThreads + threadIdx.x;
+    if (idx >= t.n_raster_words) return;
+    uint32_t word = __ldg(s.fired_global + idx);
+    if (word == 0u) return;
+    const uint32_t base = __ldg(t.raster_neuron + idx); // device index of the word's bit 0
+    while (word != 0u)
     {
-        const uint32_t bit = __ldg(t.axon_out_bit + a);
-        const uint32_t w = bit >> 5;
-        if (w >= t.inbox_lo && w < t.inbox_hi) atomicOr(&s.inbox[w], 1u << (bit & 31));
+        const uint32_t b = __ffs(word) - 1;
+        word &= word - 1u;
+        const uint32_t i = base + b;
+        const uint32_t a0 = __ldg(t.axon_out_begin + i), a1 = __ldg(t.axon_out_begin + i + 1);
+        for (uint32_t a = a0; a < a1; ++a)
+        {
+            const uint32_t bit = __ldg(t.axon_out_bit + a);
+            const uint32_t w = bit >> 5;
+            if (w >= t.inbox_lo && w < t.inbox_hi) atomicOr(&s.inbox[w], 1u << (bit & 31));
+        }
     }
 }
 
@@ -1646,23 +1652,14 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         if (e->upload(&e->t.soma_segments, segs.data(), segs.size()) != 0) return -1;
         if (e->world > 1)
         {
-            std::vector<SomaSegment> all;
+            // padding words (no neurons) point at neuron 0 and are never set
+            std::vector<uint32_t> word_neuron(e->fired_words, 0u);
             for (uint32_t c : e->all_soma_list)
-            {
-                const CoreDev &d = e->h_cores[c];
-                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += kSomaThreads)
-                {
-                    SomaSegment g{};
-                    g.k0 = k0;
-                    g.neuron_begin = d.neuron_begin;
-                    g.neuron_count = d.neuron_count;
-                    g.fired_word_begin = d.fired_word_begin;
-                    all.push_back(g);
-                }
-            }
-            e->n_all_segments = static_cast<uint32_t>(all.size());
-            e->t.n_all_segments = e->n_all_segments;
-            if (e->upload(&e->t.all_segments, all.data(), all.size()) != 0) return -1;
+                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += 32)
+                    word_neuron[e->h_cores[c].fired_word_begin + (k0 >> 5)] = tb->cores[c].neuron_begin + k0;
+            e->t.n_raster_words = e->fired_words;
+            if (e->upload(&e->t.raster_neuron, word_neuron.data(), word_neuron.size()) != 0) return -1;
+            e->n_all_segments = (e->fired_words + kSomaThreads - 1) / kSomaThreads;
         }
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
@@ -2311,4 +2308,29 @@ extern "C" void *sfe_host_alloc(size_t bytes)
 extern "C" void sfe_host_free(void *p)
 {
     if (p != nullptr) cudaFreeHost(p);
+}
+
+// The last `n` step records of the device log, by the DEVICE cursor. For steps that
+// were replayed from a CUDA graph (they bypass the host-side counters); re-synchronises
+// the host counters with the device.
+extern "C" int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n)
+{
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return -1;
+    long long counters[2] = {0, 0};
+    if (cudaMemcpy(counters, e->s.step, sizeof(counters), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    const int64_t cursor = counters[1];
+    if (n > cursor || n > e->log_cap)
+    {
+        sfe::set_last_error("sfe_engine_read_log_tail: not that many records in the device log");
+        return -1;
+    }
+    for (int64_t i = 0; i < n; ++i)
+    {
+        const int64_t pos = (cursor - n + i) % e->log_cap;
+        if (cudaMemcpy(out + i, e->s.log + pos, sizeof(sfe_step_record), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    }
+    e->total_timesteps = counters[0];
+    e->log_read = cursor;
+    return n;
 }

@@ -152,6 +152,7 @@ def lib():
         "sfe_engine_collect_records": (i64, [vp, vp, i64]),
         "sfe_engine_partition_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
         "sfe_chip_set_partition": (C.c_int, [vp, u32, u32]),
+        "sfe_engine_read_log_tail": (i64, [vp, vp, i64]),
         "sfe_engine_raster_layout": (C.c_int, [vp, vp, sz]),
         "sfe_engine_synchronize": (C.c_int, [vp]),
         "sfe_device_memcpy": (C.c_int, [vp, vp, sz]),
