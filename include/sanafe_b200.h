@@ -229,7 +229,8 @@ typedef struct sfe_run_data
     int64_t spikes, packets_sent, neurons_updated, neurons_fired;
     double total_energy, synapse_energy, dendrite_energy, soma_energy, network_energy;
     double sim_time;
-    double wall_time;
+    double wall_time;          /* host wall-clock seconds of the sim() call */
+    double scheduler_wall_time;/* of which: host-side detailed scheduler (0 for the simple model) */
 } sfe_run_data;
 
 /* What sim() should hand back besides the totals. Any pointer may be NULL.
@@ -332,6 +333,9 @@ int sfe_chip_load_synthetic(sfe_chip *c, const sfe_synth_spec *spec, int generat
 /* SpikingChip::sim  src/chip.cpp:477-533 */
 int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, const sfe_trace_request *req,
         sfe_run_data *out);
+/* host-side detailed timing model (src/schedule.cpp:208-620) over a status trace
+ * ([timesteps][n_neurons] SFE_STATUS_* bytes): per-step sim_time */
+int sfe_chip_schedule_detailed(sfe_chip *c, const uint8_t *status, int64_t timesteps, double *sim_time);
 int sfe_chip_reset(sfe_chip *c);       /* src/chip.cpp:576-600 */
 double sfe_chip_get_power(sfe_chip *c);/* src/chip.cpp:607-621 */
 const sfe_tables *sfe_chip_tables(const sfe_chip *c);

@@ -1203,7 +1203,7 @@ __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restric
 __global__ void __launch_bounds__(256) certify_kernel(
         CoreDev *cores, const uint32_t *core_list, const sfe_axon_in *axons, const double *syn_w, const uint32_t *syn_meta)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t bad;
     const uint32_t ci = core_list[blockIdx.x];
     CoreDev &core = cores[ci];

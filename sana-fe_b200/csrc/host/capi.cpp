@@ -4,6 +4,7 @@
 // from an Architecture, load() lowers a SpikingNetwork to device tables, sim()
 // runs timesteps and returns RunData; state persists across sim() calls and
 // reset() zeroes model state without rewinding the timestep counter.
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -14,6 +15,7 @@
 #include "../engine.hpp"
 #include "desc.hpp"
 #include "lower.hpp"
+#include "schedule.hpp"
 #include "sanafe_b200.h"
 
 namespace sfe
@@ -48,6 +50,7 @@ struct sfe_chip
     double total_energy{0.0};
     double total_sim_time{0.0};
     uint32_t rank{0}, world{1};
+    std::unique_ptr<sfe::DetailedScheduler> scheduler; // built on first use
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -211,12 +214,72 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                 if (!c->loaded) throw std::runtime_error("sfe_chip_sim: no network loaded");
                 if (c->engine == nullptr)
                     throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback");
-                if (timing_model != SFE_TIMING_SIMPLE)
-                    throw std::runtime_error("only the 'simple' timing model runs on the device; the detailed "
-                                             "scheduler (src/schedule.cpp:208-661) is not implemented yet and the "
-                                             "cycle-accurate model (Booksim2) is out of scope");
+                const auto wall0 = std::chrono::steady_clock::now();
+                if (timing_model == SFE_TIMING_CYCLE)
+                    throw std::runtime_error("the cycle-accurate timing model needs Booksim2 (third-party, not "
+                                             "available): out of scope");
                 sfe_run_data rd;
-                if (sfe_engine_run(c->engine, timesteps, req, &rd) != 0) return -1;
+                if (timing_model == SFE_TIMING_SIMPLE)
+                {
+                    if (sfe_engine_run(c->engine, timesteps, req, &rd) != 0) return -1;
+                }
+                else
+                {
+                    // Detailed model: the device runs the timesteps and hands back one status
+                    // byte per neuron and step; the host scheduler (src/schedule.cpp:208-620
+                    // restated in schedule.cpp) turns them into per-step sim_time.
+                    if (c->world > 1) throw std::runtime_error("detailed timing is not available on a partitioned chip");
+                    if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
+                    const size_t n = c->tables.view.n_neurons;
+                    const size_t words = (n + 31) / 32;
+                    const int64_t batch_cap = std::max<int64_t>(1, std::min<int64_t>(4096, (64ll << 20) / static_cast<int64_t>(std::max<size_t>(n, 1))));
+                    std::vector<uint8_t> status;
+                    std::vector<sfe_step_record> recs;
+                    std::memset(&rd, 0, sizeof(rd));
+                    double sched_s = 0.0;
+                    for (int64_t done = 0; done < timesteps;)
+                    {
+                        const int64_t batch = std::min<int64_t>(batch_cap, timesteps - done);
+                        status.resize(static_cast<size_t>(batch) * n);
+                        recs.resize(static_cast<size_t>(batch));
+                        sfe_trace_request sub{};
+                        sub.steps = recs.data();
+                        sub.status = status.data();
+                        if (req != nullptr)
+                        {
+                            if (req->fired_bits != nullptr) sub.fired_bits = req->fired_bits + static_cast<size_t>(done) * words;
+                            if (req->potentials != nullptr) sub.potentials = req->potentials + static_cast<size_t>(done) * c->tables.view.n_probes;
+                        }
+                        sfe_run_data part;
+                        if (sfe_engine_run(c->engine, batch, &sub, &part) != 0) return -1;
+                        if (done == 0) rd.timestep_start = part.timestep_start;
+                        const auto s0 = std::chrono::steady_clock::now();
+                        for (int64_t b = 0; b < batch; ++b)
+                        {
+                            sfe_step_record &r = recs[static_cast<size_t>(b)];
+                            r.sim_time = c->scheduler->schedule_step(status.data() + static_cast<size_t>(b) * n);
+                            // update_run_data  src/chip.cpp:462-475
+                            rd.total_energy += r.total_energy;
+                            rd.synapse_energy += r.synapse_energy;
+                            rd.dendrite_energy += r.dendrite_energy;
+                            rd.soma_energy += r.soma_energy;
+                            rd.network_energy += r.network_energy;
+                            rd.sim_time += r.sim_time;
+                            rd.spikes += r.spike_count;
+                            rd.packets_sent += r.packets_sent;
+                            rd.neurons_updated += r.neurons_updated;
+                            rd.neurons_fired += r.neurons_fired;
+                            if (req != nullptr && req->steps != nullptr) req->steps[done + b] = r;
+                            if (req != nullptr && req->status != nullptr)
+                                std::memcpy(req->status + static_cast<size_t>(done + b) * n, status.data() + static_cast<size_t>(b) * n, n);
+                        }
+                        sched_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+                        done += batch;
+                    }
+                    rd.timesteps_executed = timesteps;
+                    rd.scheduler_wall_time = sched_s;
+                }
+                rd.wall_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
                 c->total_energy += rd.total_energy;   // sim_update_total_energy_and_counts
                 c->total_sim_time += rd.sim_time;     // retire_timestep
                 if (out != nullptr) *out = rd;
@@ -330,4 +393,22 @@ extern "C" size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap)
         buf[n] = '\0';
     }
     return out.size();
+}
+
+// Detailed timing model over a caller-supplied status trace ([timesteps][n_neurons]
+// SFE_STATUS_* bytes, e.g. sfe_trace_request.status of an earlier run): per-step
+// sim_time of schedule_messages_timestep_detailed (src/schedule.cpp:208-292). Pure
+// host code (the scheduler is host-side in the reference too).
+extern "C" int sfe_chip_schedule_detailed(sfe_chip *c, const uint8_t *status, int64_t timesteps, double *sim_time)
+{
+    return guarded(
+            [&]() -> int {
+                if (!c->loaded) throw std::runtime_error("sfe_chip_schedule_detailed: no network loaded");
+                if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
+                const size_t n = c->tables.view.n_neurons;
+                for (int64_t s = 0; s < timesteps; ++s)
+                    sim_time[s] = c->scheduler->schedule_step(status + static_cast<size_t>(s) * n);
+                return 0;
+            },
+            -1);
 }

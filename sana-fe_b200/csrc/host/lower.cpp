@@ -923,16 +923,22 @@ void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bo
         cd.weight_shift = 0;
         cd.acc_mode = SFE_ACC_DUAL32; // refined below / re-certified on the device
     }
+    std::vector<std::pair<uint32_t, uint32_t>> order(D); // (destination core, k)
     for (uint32_t n = 0; n < N; ++n)
     {
         const uint32_t home = n / P;
         out.axon_out_begin[n] = n * D;
-        for (uint32_t k = 0; k < D; ++k)
+        // The reference visits a neuron's destination cores in std::set<Core*> order,
+        // which in practice is ascending (tile, core) order (checked against the
+        // reference's own mapping dump); messages are sent in that order.
+        for (uint32_t k = 0; k < D; ++k) order[k] = {sfe_synth_dest_core(&s, home, k), k};
+        std::sort(order.begin(), order.end());
+        for (uint32_t q = 0; q < D; ++q)
         {
-            const uint32_t d = sfe_synth_dest_core(&s, home, k);
+            const uint32_t d = order[q].first;
             const uint32_t slot = rank_of(d, home) * P + (n % P);
             const uint32_t axon_id = d * axons_per_core + slot;
-            out.axon_out_target[static_cast<size_t>(n) * D + k] = axon_id;
+            out.axon_out_target[static_cast<size_t>(n) * D + q] = axon_id;
             sfe_axon_in &rec = out.axons_in[axon_id];
             rec.syn_off = slot * S;
             rec.syn_count = S;
@@ -942,8 +948,6 @@ void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bo
         }
     }
     out.axon_out_begin[N] = N * D;
-    // NOTE: the reference orders a neuron's axons-out by std::set<Core*>; we send
-    // in k order (home, home+1, ...). Only message ids / detailed timing see it.
 
     out.synth = s;
     if (materialize)
@@ -953,11 +957,12 @@ void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bo
         out.syn_meta.resize(total);
         for (uint32_t n = 0; n < N; ++n)
         {
+            const uint32_t home = n / P;
             for (uint32_t k = 0; k < D; ++k)
             {
                 const uint64_t axon = static_cast<uint64_t>(n) * D + k;
-                const uint32_t axon_id = out.axon_out_target[axon];
-                const uint32_t d = axon_id / axons_per_core;
+                const uint32_t d = sfe_synth_dest_core(&s, home, k);
+                const uint32_t axon_id = d * axons_per_core + rank_of(d, home) * P + (n % P);
                 const uint64_t base = out.cores[d].syn_begin + out.axons_in[axon_id].syn_off;
                 const sfe_synth_axon ap = sfe_synth_axon_params(&s, axon);
                 for (uint32_t j = 0; j < S; ++j)

@@ -1,0 +1,278 @@
+// schedule.cpp — the "detailed" timing model on the host, fed by device records.
+//
+// The reference's semi-analytical NoC scheduler (src/schedule.cpp:208-620) is a
+// strictly sequential priority-queue simulation over the messages of one
+// timestep; it stays on the host. What the device hands over per
+// step is one status byte per neuron (idle / updated / fired); every other
+// message field is a load-time constant of the lowered tables, so the per-core
+// message lists are rebuilt here exactly as process_neurons /
+// pipeline_process_axon_out build them (src/chip.cpp:624-654, 710-736, 802-834):
+// same order, same floating-point accumulation of generation delays.
+#include "schedule.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <list>
+#include <queue>
+#include <stdexcept>
+
+namespace sfe
+{
+namespace
+{
+enum Direction : uint32_t // src/schedule.hpp:31-39
+{
+    north = 0U,
+    east = 1U,
+    south = 2U,
+    west = 3U,
+    ndirections = 4U,
+};
+
+struct Msg
+{
+    double generation_delay{0.0};
+    double processing_delay{0.0};
+    double min_hop_delay{0.0};
+    double sent{0.0}, received{0.0}, processed{0.0};
+    uint32_t hops{0};
+    uint32_t src_x{0}, src_y{0}, dest_x{0}, dest_y{0};
+    uint32_t src_core_offset{0}, src_core{0}, dest_core{0};
+    bool placeholder{true};
+    bool in_noc{false};
+};
+
+struct BySentTime // CompareMessagesBySentTime  src/message.cpp:61-65
+{
+    bool operator()(const Msg &a, const Msg &b) const noexcept { return a.sent > b.sent; }
+};
+
+struct Noc // NocInfo  src/schedule.hpp:170-202
+{
+    size_t width, height, links_per_router;
+    std::vector<std::list<Msg>> received;
+    std::vector<double> density;
+    std::vector<double> core_free;
+    double mean_rx{0.0};
+    long in_noc{0};
+
+    size_t idx(size_t x, size_t y, size_t link) const { return (x * height * links_per_router) + (y * links_per_router) + link; }
+
+    template <typename F> void walk_route(const Msg &m, F &&visit) const
+    {
+        // dimension-order route: x first, then y; first link = the sending core's
+        // injection link (src/schedule.cpp:449-611)
+        const int xi = (m.src_x < m.dest_x) ? 1 : -1;
+        const int yi = (m.src_y < m.dest_y) ? 1 : -1;
+        size_t prev = ndirections + m.src_core_offset;
+        for (size_t x = m.src_x; x != m.dest_x; x += xi)
+        {
+            const size_t dir = (xi > 0) ? east : west;
+            if (x == m.src_x) visit(idx(x, m.src_y, ndirections + m.src_core_offset));
+            else visit(idx(x, m.src_y, dir));
+            prev = dir;
+        }
+        for (size_t y = m.src_y; y != m.dest_y; y += yi)
+        {
+            const size_t dir = (yi > 0) ? north : south;
+            if (m.src_x == m.dest_x && y == m.src_y) visit(idx(m.dest_x, y, ndirections + m.src_core_offset));
+            else visit(idx(m.dest_x, y, prev));
+            prev = dir;
+        }
+        if (m.src_x == m.dest_x && m.src_y == m.dest_y) visit(idx(m.dest_x, m.dest_y, ndirections + m.src_core_offset));
+        else visit(idx(m.dest_x, m.dest_y, prev));
+    }
+
+    double congestion(const Msg &m) const
+    {
+        double flow = 0.0;
+        walk_route(m, [&](size_t link) { flow += density[link]; });
+        return flow;
+    }
+
+    void track(const Msg &m, const bool entering)
+    {
+        if (m.src_x > width || m.dest_x > width) throw std::runtime_error("Message x > NoC width");
+        if (m.src_y > height || m.dest_y > height) throw std::runtime_error("Message y > NoC height");
+        double adjust = 1.0 / (2.0 + static_cast<double>(m.hops));
+        if (!entering) adjust *= -1.0;
+        walk_route(m, [&](size_t link) { density[link] += adjust; });
+        // update_rolling_averages  src/schedule.cpp:449-475
+        if (entering)
+        {
+            mean_rx += (m.processing_delay - mean_rx) / (static_cast<double>(in_noc) + 1.0);
+            in_noc++;
+        }
+        else
+        {
+            if (in_noc > 1) mean_rx += (mean_rx - m.processing_delay) / (static_cast<double>(in_noc) - 1.0);
+            else mean_rx = 0.0;
+            in_noc--;
+        }
+    }
+};
+} // namespace
+
+DetailedScheduler::DetailedScheduler(const sfe_tables &t) : t_(t)
+{
+    axon_core_.resize(t.n_axons_in);
+    axon_proc_.resize(t.n_axons_in);
+    for (uint32_t c = 0; c < t.n_cores; ++c)
+    {
+        const sfe_core_desc &cd = t.cores[c];
+        for (uint32_t a = 0; a < cd.axon_in_count; ++a)
+        {
+            const uint32_t id = cd.axon_in_begin + a;
+            axon_core_[id] = c;
+            // process_message  src/chip.cpp:738-764: axon-in latency, then per synapse
+            // the pipeline's (0.0 + synapse) + dendrite latency, added one by one
+            const sfe_axon_in &ax = t.axons_in[id];
+            const sfe_cost_class &cc = t.cost_classes[ax.cost_class];
+            double lat = cd.latency_axon_in;
+            if (cc.per_message) lat += cc.syn_latency;
+            else
+                for (uint32_t s = 0; s < ax.syn_count; ++s) lat += (0.0 + cc.syn_latency) + cc.den_latency;
+            axon_proc_[id] = lat;
+        }
+    }
+}
+
+double DetailedScheduler::schedule_step(const uint8_t *status)
+{
+    const sfe_tables &t = t_;
+    // ---- rebuild the per-sending-core message lists ------------------------------
+    std::vector<std::list<Msg>> queues(t.n_cores);
+    for (uint32_t c = 0; c < t.n_cores; ++c)
+    {
+        const sfe_core_desc &cd = t.cores[c];
+        if (cd.neuron_count == 0) continue;
+        const sfe_tile_desc &src_tile = t.tiles[cd.tile];
+        double next_delay = 0.0;
+        for (uint32_t k = 0; k < cd.neuron_count; ++k)
+        {
+            const uint32_t i = cd.neuron_begin + k;
+            const sfe_soma_class &cls = t.soma_classes[t.neuron_class[i]];
+            const uint8_t st = status[i];
+            double lat = 0.0;
+            if (cls.dend_in_neuron) lat += cls.dend_latency_update;
+            double soma = cls.latency_access;
+            if (st == SFE_STATUS_UPDATED || st == SFE_STATUS_FIRED) soma += cls.latency_update;
+            if (st == SFE_STATUS_FIRED) soma += cls.latency_spike_out;
+            lat += soma;
+            next_delay += lat;
+            if (st != SFE_STATUS_FIRED) continue;
+            for (uint32_t a = t.axon_out_begin[i]; a < t.axon_out_begin[i + 1]; ++a)
+            {
+                const uint32_t id = t.axon_out_target[a];
+                const uint32_t dc = axon_core_[id];
+                const sfe_core_desc &dd = t.cores[dc];
+                const sfe_tile_desc &dst_tile = t.tiles[dd.tile];
+                const sfe_axon_in &ax = t.axons_in[id];
+                Msg m;
+                m.placeholder = false;
+                m.generation_delay = next_delay + cd.latency_axon_out;
+                next_delay = 0.0;
+                m.processing_delay = axon_proc_[id];
+                const uint32_t dx = SFE_HOP_DX(ax.hop), dy = SFE_HOP_DY(ax.hop);
+                m.hops = dx + dy;
+                // sim_estimate_network_costs  src/chip.cpp:1127-1169 (source tile's latencies)
+                m.min_hop_delay = 0.0;
+                m.min_hop_delay += static_cast<double>(dx) * (SFE_HOP_EAST(ax.hop) ? src_tile.latency_east : src_tile.latency_west);
+                m.min_hop_delay += static_cast<double>(dy) * (SFE_HOP_NORTH(ax.hop) ? src_tile.latency_north : src_tile.latency_south);
+                m.src_x = src_tile.x;
+                m.src_y = src_tile.y;
+                m.dest_x = dst_tile.x;
+                m.dest_y = dst_tile.y;
+                m.src_core_offset = cd.offset;
+                m.src_core = c;
+                m.dest_core = dc;
+                queues[c].push_back(m);
+            }
+        }
+        if (next_delay != 0.0)
+        {
+            Msg m; // placeholder: processing that sends nothing (src/chip.cpp:640-652)
+            m.generation_delay = next_delay;
+            m.src_x = src_tile.x;
+            m.src_y = src_tile.y;
+            m.src_core_offset = cd.offset;
+            m.src_core = c;
+            queues[c].push_back(m);
+        }
+    }
+
+    // ---- schedule_messages_timestep_detailed  src/schedule.cpp:208-292 -----------------
+    Noc noc;
+    noc.width = t.noc_width;
+    noc.height = t.noc_height;
+    noc.links_per_router = t.max_cores_per_tile + ndirections;
+    noc.received.resize(t.n_cores);
+    noc.core_free.assign(t.n_cores, 0.0);
+    noc.density.assign(static_cast<size_t>(t.noc_width) * t.noc_height * noc.links_per_router, 0.0);
+    std::priority_queue<Msg, std::vector<Msg>, BySentTime> pq;
+    for (auto &q : queues)
+    {
+        if (q.empty()) continue;
+        Msg m = q.front();
+        q.pop_front();
+        m.sent = m.generation_delay;
+        pq.push(m);
+    }
+    std::vector<uint32_t> busy; // destination cores that currently hold tracked messages, ascending
+    double last = 0.0;
+    while (!pq.empty())
+    {
+        Msg m = pq.top();
+        pq.pop();
+        last = std::max(last, m.sent);
+        // noc_update_all_tracked_messages: destination cores in id order, FIFO order within
+        for (size_t b = 0; b < busy.size();)
+        {
+            auto &q = noc.received[busy[b]];
+            q.remove_if([&](Msg &x) {
+                if (x.in_noc && (m.sent >= x.received))
+                {
+                    x.in_noc = false;
+                    noc.track(x, false);
+                    return true;
+                }
+                return false;
+            });
+            if (q.empty()) busy.erase(busy.begin() + static_cast<long>(b));
+            else ++b;
+        }
+        if (!m.placeholder)
+        {
+            // schedule_handle_message  src/schedule.cpp:306-358
+            const double along_route = noc.congestion(m);
+            const double capacity = static_cast<double>((m.hops + 1UL) * t.noc_buffer_size);
+            if (along_route > capacity) m.sent += (along_route - capacity) * noc.mean_rx;
+            const double congestion_delay = along_route * noc.mean_rx / (static_cast<double>(m.hops) + 1.0);
+            const double network_delay = std::max(m.min_hop_delay, congestion_delay);
+            const double earliest = m.sent + network_delay;
+            m.received = std::max(noc.core_free[m.dest_core], earliest);
+            noc.core_free[m.dest_core] =
+                    std::max(noc.core_free[m.dest_core] + m.processing_delay, earliest + m.processing_delay);
+            m.processed = noc.core_free[m.dest_core];
+            m.in_noc = true;
+            if (noc.received[m.dest_core].empty())
+                busy.insert(std::lower_bound(busy.begin(), busy.end(), m.dest_core), m.dest_core);
+            noc.received[m.dest_core].push_back(m);
+            noc.track(m, true);
+            last = std::max(last, m.processed);
+        }
+        auto &q = queues[m.src_core];
+        if (!q.empty())
+        {
+            // schedule_push_next_message  src/schedule.cpp:360-378
+            Msg next = q.front();
+            q.pop_front();
+            next.sent = m.sent + next.generation_delay;
+            pq.push(next);
+            last = std::max(last, next.sent);
+        }
+    }
+    return last + t.sync_delay;
+}
+
+} // namespace sfe

@@ -114,7 +114,7 @@ class RunData(C.Structure):
                 ("packets_sent", C.c_int64), ("neurons_updated", C.c_int64), ("neurons_fired", C.c_int64),
                 ("total_energy", C.c_double), ("synapse_energy", C.c_double), ("dendrite_energy", C.c_double),
                 ("soma_energy", C.c_double), ("network_energy", C.c_double), ("sim_time", C.c_double),
-                ("wall_time", C.c_double)]
+                ("wall_time", C.c_double), ("scheduler_wall_time", C.c_double)]
 
 
 class TraceRequest(C.Structure):
@@ -167,6 +167,7 @@ def lib():
         "sfe_chip_load": (C.c_int, [vp, vp]),
         "sfe_chip_load_synthetic": (C.c_int, [vp, C.POINTER(SynthSpec), C.c_int]),
         "sfe_chip_sim": (C.c_int, [vp, i64, C.c_int, C.POINTER(TraceRequest), C.POINTER(RunData)]),
+        "sfe_chip_schedule_detailed": (C.c_int, [vp, vp, i64, vp]),
         "sfe_chip_reset": (C.c_int, [vp]), "sfe_chip_get_power": (dbl, [vp]),
         "sfe_chip_tables": (C.POINTER(Tables), [vp]), "sfe_chip_engine": (vp, [vp]),
         "sfe_chip_neuron_index": (i64, [vp, cstr, u64]),
