@@ -56,6 +56,7 @@ struct CoreDev
     uint32_t dend_in_msg;
     uint32_t tile;
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
+    uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
     uint32_t pad0;
     unsigned long long syn_begin;
     double scale, inv_scale;          // 2^shift, 2^-shift
@@ -69,7 +70,12 @@ struct StatsN // written by soma_kernel, one per core
     double soma_e, dend_e, gen_sum;
 };
 
-struct StatsM // written by fanout_kernel, one per core
+struct FanItem // one unit of message-phase work: a slice of one core's inbox
+{
+    uint32_t core, word_lo, word_hi, pad;
+};
+
+struct StatsM // written by fanout_kernel, one per work item
 {
     uint32_t msgs, pad;
     unsigned long long events, hop_e, hop_w, hop_n, hop_s;
@@ -87,6 +93,9 @@ struct DevTables
     uint32_t inbox_lo, inbox_hi;      // local inbox word range [lo, hi)
     uint32_t n_soma_classes;
     const uint32_t *fanout_core_list; // cores that have axons-in
+    const FanItem *fan_items;         // message-phase work items, grouped by core
+    const uint32_t *fan_order;        // ticket -> item id, heaviest first
+    uint32_t n_fan_items;
     const uint32_t *active_core_list; // cores with neurons or axons-in (ascending id)
     uint32_t n_active_cores;
     const sfe_soma_class *classes;
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                     const int sum = (static_cast<int>(raw << 12)) >> 12; // sign-extend 20 bits
                     has_in = true;                                       // count = (raw - sum) >> 20 > 0
                     in = static_cast<double>(sum) * core.inv_scale;
-                    if (core.ring > 1) s.din32[d] = 0u;
+                    s.din32[d] = 0u; // consumed (the message phase accumulates into zeroed slots)
                 }
             }
             else if (core.acc_mode == SFE_ACC_DUAL32)
@@ -374,11 +383,8 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 {
                     has_in = true;
                     in = static_cast<double>(static_cast<int>(s.din32[d])) * core.inv_scale;
-                    if (core.ring > 1)
-                    {
-                        s.din32[d] = 0u;
-                        s.dcnt32[d] = 0u;
-                    }
+                    s.din32[d] = 0u;
+                    s.dcnt32[d] = 0u;
                 }
             }
             else
@@ -644,9 +650,8 @@ template <int V>
 __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double red_d[32];
-    __shared__ unsigned long long red_l[32];
-    __shared__ uint32_t red_u[32];
+    __shared__ double part_d[kFanoutWarps][3];
+    __shared__ unsigned long long part_l[kFanoutWarps][6];
     __shared__ sfe_cost_class cost_cache[kCostCache];
     __shared__ uint32_t next_item, list_n;
     __shared__ uint32_t scan_w[kFanoutWarps];
@@ -675,9 +680,11 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     __syncthreads(); // previous core fully retired (smem accumulators, next_item)
     if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u);
     __syncthreads();
-    const uint32_t item = next_item;
-    if (item >= t.n_fanout_cores) break;
-    const uint32_t ci = t.fanout_core_list[item];
+    const uint32_t ticket = next_item;
+    if (ticket >= t.n_fan_items) break;
+    const uint32_t item_id = t.fan_order[ticket];
+    const FanItem item = t.fan_items[item_id];
+    const uint32_t ci = item.core;
     const CoreDev core = t.cores[ci];
     const uint32_t P = core.neuron_count;
     const uint32_t cells = P * core.ring;
@@ -708,7 +715,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     __syncthreads();
 
     FanoutCounters cnt = {0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
-    const uint32_t n_words = (core.axon_count + 31u) >> 5;
+    const uint32_t n_words = item.word_hi; // this item's slice of the core's inbox: [word_lo, word_hi)
     const double *__restrict__ w_base = t.syn_w + core.syn_begin;
     const uint32_t *__restrict__ m_base = t.syn_meta + core.syn_begin;
     const uint32_t ring = core.ring;
@@ -725,7 +732,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         //   stream  warp w takes entries w, w+8, ... and streams their CSR segments
         const bool packed = core.acc_mode == SFE_ACC_PACKED32;
         uint2 *list = reinterpret_cast<uint2 *>(smem_raw + list_off);
-        for (uint32_t wb = 0; wb < n_words;)
+        for (uint32_t wb = item.word_lo; wb < n_words;)
         {
             const uint32_t wi = wb + threadIdx.x;
             const uint32_t word = wi < n_words ? s.inbox[core.inbox_word_begin + wi] : 0u;
@@ -943,32 +950,21 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     if (accumulate)
     {
         const uint32_t base = core.dend_base;
+        // Exact modes: several items (inbox slices) of one core may run on different CTAs,
+        // and integer sums commute, so partial sums are merged with fire-and-forget global
+        // atomics; the neuron phase zeroes a slot when it consumes it.
         if (core.acc_mode == SFE_ACC_PACKED32)
         {
-            if (ring > 1)
-            {
-                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
-                    if (acc32[x] != 0u) s.din32[base + x] += acc32[x];
-            }
-            else
-                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads) s.din32[base + x] = acc32[x];
+            for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+                if (acc32[x] != 0u) atomicAdd(&s.din32[base + x], acc32[x]);
         }
         else if (core.acc_mode == SFE_ACC_DUAL32)
         {
-            if (ring > 1)
-            {
-                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
-                    if (cnt32[x] != 0u)
-                    {
-                        s.din32[base + x] += acc32[x];
-                        s.dcnt32[base + x] += cnt32[x];
-                    }
-            }
-            else
-                for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+            for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
+                if (cnt32[x] != 0u)
                 {
-                    s.din32[base + x] = acc32[x];
-                    s.dcnt32[base + x] = cnt32[x];
+                    atomicAdd(&s.din32[base + x], acc32[x]);
+                    atomicAdd(&s.dcnt32[base + x], cnt32[x]);
                 }
         }
         else
@@ -981,30 +977,47 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         }
     }
 
-    // ---- per-core counters ---------------------------------------------------------
-    const uint32_t msgs = block_sum(cnt.msgs, red_u);
-    const unsigned long long events = block_sum(cnt.events, red_l);
-    const unsigned long long he = block_sum(cnt.hop_e, red_l);
-    const unsigned long long hw = block_sum(cnt.hop_w, red_l);
-    const unsigned long long hn = block_sum(cnt.hop_n, red_l);
-    const unsigned long long hs = block_sum(cnt.hop_s, red_l);
-    const double se = block_sum(cnt.syn_e, red_d);
-    const double de = block_sum(cnt.den_e, red_d);
-    const double pr = block_sum(cnt.proc, red_d);
-    if (threadIdx.x == 0)
+    // ---- per-item counters: warp shuffles, one barrier, fixed order ---------------------
     {
-        StatsM out;
-        out.msgs = msgs;
-        out.pad = 0;
-        out.events = events;
-        out.hop_e = he;
-        out.hop_w = hw;
-        out.hop_n = hn;
-        out.hop_s = hs;
-        out.syn_e = se;
-        out.den_e = de;
-        out.proc = pr;
-        s.stats_m[ci] = out;
+        const unsigned long long v_msgs = warp_sum(static_cast<unsigned long long>(cnt.msgs));
+        const unsigned long long v_events = warp_sum(cnt.events);
+        const unsigned long long v_he = warp_sum(cnt.hop_e);
+        const unsigned long long v_hw = warp_sum(cnt.hop_w);
+        const unsigned long long v_hn = warp_sum(cnt.hop_n);
+        const unsigned long long v_hs = warp_sum(cnt.hop_s);
+        const double v_se = warp_sum(cnt.syn_e);
+        const double v_de = warp_sum(cnt.den_e);
+        const double v_pr = warp_sum(cnt.proc);
+        if (lane == 0)
+        {
+            part_l[warp][0] = v_msgs;
+            part_l[warp][1] = v_events;
+            part_l[warp][2] = v_he;
+            part_l[warp][3] = v_hw;
+            part_l[warp][4] = v_hn;
+            part_l[warp][5] = v_hs;
+            part_d[warp][0] = v_se;
+            part_d[warp][1] = v_de;
+            part_d[warp][2] = v_pr;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            StatsM out = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+            for (int w = 0; w < kFanoutWarps; ++w)
+            {
+                out.msgs += static_cast<uint32_t>(part_l[w][0]);
+                out.events += part_l[w][1];
+                out.hop_e += part_l[w][2];
+                out.hop_w += part_l[w][3];
+                out.hop_n += part_l[w][4];
+                out.hop_s += part_l[w][5];
+                out.syn_e += part_d[w][0];
+                out.den_e += part_d[w][1];
+                out.proc += part_d[w][2];
+            }
+            s.stats_m[item_id] = out;
+        }
     }
     } // persistent loop
 }
@@ -1061,7 +1074,20 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
             n.gen_sum += x.gen_sum;
         }
         n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
-        const StatsM m = s.stats_m[ci];
+        StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+        for (uint32_t g = 0; g < core.item_count; ++g) // fixed order: deterministic sums
+        {
+            const StatsM x = s.stats_m[core.item_begin + g];
+            m.msgs += x.msgs;
+            m.events += x.events;
+            m.hop_e += x.hop_e;
+            m.hop_w += x.hop_w;
+            m.hop_n += x.hop_n;
+            m.hop_s += x.hop_s;
+            m.syn_e += x.syn_e;
+            m.den_e += x.den_e;
+            m.proc += x.proc;
+        }
         p.fired = n.fired;
         p.updated = n.updated;
         p.packets = n.packets;
@@ -1687,7 +1713,6 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.hh, 5 * static_cast<size_t>(tb->n_hh)) != 0) return -1;
     e->s.n_hh = tb->n_hh;
     if (e->alloc(&e->s.stats_n, e->n_segments) != 0) return -1;
-    if (e->alloc(&e->s.stats_m, tb->n_cores) != 0) return -1;
     e->log_cap = 4096;
     e->s.log_cap = e->log_cap;
     if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
@@ -1738,7 +1763,44 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar>, kFanoutThreads, smem_max));
         SFE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
         if (const char *v = std::getenv("SFE_FANOUT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
-        e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(e->fanout_list.size(), static_cast<size_t>(per_sm) * sms)));
+        // ---- message-phase work items: split every core's inbox into slices so that there
+        // are several items per resident CTA (no tail behind the slowest core, and a rank
+        // that owns few cores still fills the GPU)
+        const size_t slots = static_cast<size_t>(per_sm) * sms;
+        size_t split = e->fanout_list.empty() ? 1 : std::max<size_t>(1, std::min<size_t>(16, (6 * slots) / e->fanout_list.size()));
+        if (const char *v = std::getenv("SFE_FANOUT_SPLIT")) split = std::max(1, std::atoi(v));
+        std::vector<FanItem> items;
+        std::vector<double> weight;
+        for (uint32_t c : e->fanout_list)
+        {
+            const CoreDev &d = e->h_cores[c];
+            const uint32_t words = (d.axon_count + 31u) / 32u;
+            const uint32_t parts = d.acc_mode == SFE_ACC_ORDERED
+                    ? 1u
+                    : static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(split, words / 8)));
+            e->h_cores[c].item_begin = static_cast<uint32_t>(items.size());
+            e->h_cores[c].item_count = parts;
+            for (uint32_t k = 0; k < parts; ++k)
+            {
+                FanItem it;
+                it.core = c;
+                it.word_lo = static_cast<uint32_t>(static_cast<uint64_t>(words) * k / parts);
+                it.word_hi = static_cast<uint32_t>(static_cast<uint64_t>(words) * (k + 1) / parts);
+                it.pad = 0;
+                items.push_back(it);
+                weight.push_back(static_cast<double>(tb->cores[c].syn_count) / parts);
+            }
+        }
+        std::vector<uint32_t> order(items.size());
+        for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+        e->t.n_fan_items = static_cast<uint32_t>(items.size());
+        if (e->upload(&e->t.fan_items, items.data(), items.size()) != 0) return -1;
+        if (e->upload(&e->t.fan_order, order.data(), order.size()) != 0) return -1;
+        if (e->alloc(&e->s.stats_m, items.size()) != 0) return -1;
+        SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+        e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(items.size(), slots)));
     }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
