@@ -284,16 +284,30 @@ def main():
     return 0
 
 
+def nccl_library_path():
+    """The NCCL the image ships with torch (dlopen'ed by the engine)."""
+    try:
+        import nvidia.nccl
+        cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
 def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_src):
     """N > 1: ONE chip, its cores partitioned over the ranks (strong scaling). Every step:
-    local neuron phase -> NCCL all-gather of the fired raster over NVLink -> local message phase."""
+    local neuron phase -> ncclAllGather of the fired raster over NVLink -> local message
+    phase; the whole run is enqueued from C++ (sfe_engine_enqueue_partitioned), torch.distributed
+    only carries the NCCL id and the final reductions."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     L = sfe.lib()
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl")
+    dist.init_process_group("gloo")
     chip.set_partition(rank, world)
     t0 = time.time()
     chip.load_synthetic(spec, generate_on_device=True)
@@ -302,19 +316,14 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     tb = chip.tables
     n = tb.n_neurons
     slice_words = C.c_uint32()
-    local_neurons = C.c_uint64()
-    L.sfe_engine_partition_info(eng, None, None, C.byref(slice_words), None, C.byref(local_neurons))
-    stream = torch.cuda.Stream()
-    local = torch.zeros(slice_words.value, dtype=torch.int32, device="cuda")
-    glob = torch.zeros(slice_words.value * world, dtype=torch.int32, device="cuda")
-    torch.cuda.synchronize()
-    assert L.sfe_engine_set_stream(eng, C.c_void_p(stream.cuda_stream)) == 0
-    assert L.sfe_engine_set_exchange_buffers(eng, C.c_void_p(local.data_ptr()), C.c_void_p(glob.data_ptr())) == 0
-
-    def one_step():
-        assert L.sfe_engine_enqueue_neuron_phase(eng) == 0, L.sfe_last_error()
-        dist.all_gather_into_tensor(glob, local)
-        assert L.sfe_engine_enqueue_message_phase(eng) == 0, L.sfe_last_error()
+    L.sfe_engine_partition_info(eng, None, None, C.byref(slice_words), None, None)
+    lib_path = nccl_library_path().encode()
+    uid = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        assert L.sfe_nccl_get_unique_id(uid.ctypes.data, lib_path) == 0, L.sfe_last_error()
+    uid_t = torch.from_numpy(uid)
+    dist.broadcast(uid_t, src=0)
+    assert L.sfe_engine_comm_init(eng, uid_t.numpy().ctypes.data, lib_path) == 0, L.sfe_last_error()
 
     def collect():
         buf = np.zeros(4096, dtype=sfe.STEP_DTYPE)
@@ -322,62 +331,38 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
         assert got >= 0, L.sfe_last_error()
         return buf[:got]
 
-    mode = "eager"
-    graph = None
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            one_step()
-        stream.synchronize()
-        collect()
-        if os.environ.get("SFE_BENCH_GRAPH", "0") == "1":
-            try:
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=stream):
-                    one_step()
-                mode = "cuda graph (neuron phase + NCCL all-gather + message phase captured per step)"
-                collect()
-            except Exception as exc:  # capture not possible on this stack: stay eager
-                graph = None
-                mode = f"eager (graph capture failed: {type(exc).__name__})"
-        dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        launches0 = L.sfe_engine_launch_count(eng)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            if graph is not None:
-                graph.replay()
-            else:
-                one_step()
-        ev1.record(stream)
-        stream.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-    seconds = ev0.elapsed_time(ev1) / 1e3
+    assert L.sfe_engine_enqueue_partitioned(eng, args.warmup) == 0, L.sfe_last_error()
+    assert L.sfe_engine_synchronize(eng) == 0
+    collect()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.sfe_engine_launch_count(eng)
+    ms_total, ms_fan = C.c_float(), C.c_float()
+    assert L.sfe_engine_time_begin(eng) == 0
+    assert L.sfe_engine_enqueue_partitioned(eng, args.steps) == 0, L.sfe_last_error()
+    assert L.sfe_engine_time_end(eng, C.byref(ms_total), C.byref(ms_fan)) == 0, L.sfe_last_error()
+    dist.barrier()
+    seconds = ms_total.value / 1e3
     clocks = sampler.stop()
-    launches = (L.sfe_engine_launch_count(eng) - launches0) if graph is None else 4 * args.steps
-    # graph replays do not pass through the C ABI, so their records are read from the device log
-    recs = collect() if graph is None else None
-    # totals over the timed steps: counts are per-rank partial sums
-    if recs is not None:
-        events = int(recs["spike_count"].sum())
-        messages = int(recs["packets_sent"].sum())
-        fired = int(recs["neurons_fired"].sum())
-    else:
-        log = read_graph_records(L, eng, args.steps, sfe)
-        events, messages, fired = int(log["spike_count"].sum()), int(log["packets_sent"].sum()), int(log["neurons_fired"].sum())
-    tmax = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+    launches = L.sfe_engine_launch_count(eng) - launches0
+    recs = collect()
+    events = int(recs["spike_count"].sum())
+    messages = int(recs["packets_sent"].sum())
+    fired = int(recs["neurons_fired"].sum())
+    tmax = torch.tensor([seconds], dtype=torch.float64)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([float(events), float(messages), float(fired), float(launches)], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(events), float(messages), float(fired), float(launches), ms_fan.value / 1e3], dtype=torch.float64)
     dist.all_reduce(tot)
     seconds = float(tmax.item())
-    events_all, messages_all, fired_all, launches_all = (int(x) for x in tot.tolist())
+    events_all, messages_all, fired_all, launches_all = (int(x) for x in tot.tolist()[:4])
+    fan_s_mean = tot.tolist()[4] / world
+    L.sfe_engine_comm_destroy(eng)
     if rank != 0:
         dist.destroy_process_group()
         return 0
     step_bytes = 12.0 * events_all + 16.0 * messages_all + 48.0 * n * args.steps
+    fan_bytes = 12.0 * events_all + 16.0 * messages_all
     line = {
         "metric": METRIC, "value": events_all / seconds, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
@@ -385,13 +370,17 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
         "config": {"workload": WORKLOAD if args.cores == FULL["cores"] else f"DEBUG scale: {args.cores} cores",
                    "neurons": n, "synapses": int(tb.n_synapses), "timing_model": "simple",
                    "l2_policy": "inputs larger than L2 (synapse tables of each partition >> 126 MB)",
-                   "parallelism": f"cores partitioned over {world} GPUs, per-step NCCL all-gather of the fired raster "
-                                  f"({4 * slice_words.value * world} B)",
-                   "launch_mode": mode, "activity": fired_all / float(n * args.steps), "load_s": load_s},
+                   "parallelism": f"cores partitioned over {world} GPUs, per-step ncclAllGather of the fired raster "
+                                  f"({4 * slice_words.value * world} B) enqueued from C++",
+                   "activity": fired_all / float(n * args.steps), "load_s": load_s},
         "timesteps_per_s": args.steps / seconds, "events_per_step": events_all / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "whole step, all ranks", "achieved": step_bytes / seconds / 1e9,
-                     "peak": peak * world, "unit": "GB/s", "frac": step_bytes / seconds / 1e9 / (peak * world),
-                     "traffic": None, "peak_source": peak_src},
+        "roofline": {"bound": "hbm", "kernel": "fanout_kernel (all ranks)",
+                     "achieved": fan_bytes / fan_s_mean / 1e9 if fan_s_mean > 0 else None,
+                     "peak": peak * world, "unit": "GB/s",
+                     "frac": (fan_bytes / fan_s_mean / 1e9 / (peak * world)) if fan_s_mean > 0 else None,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel_ms_per_launch": 1e3 * fan_s_mean / args.steps,
+                     "whole_step": {"achieved": step_bytes / seconds / 1e9, "frac": step_bytes / seconds / 1e9 / (peak * world)}},
         "cpu_baseline": None,
         "e2e": {"value": events_all / seconds, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0, "note": "N>1 reports the device-timed value; the host-buffer e2e leg is the N=1 run"},

@@ -294,6 +294,14 @@ void *sfe_engine_fired_global_ptr(sfe_engine *e, size_t *n_bytes);
 /* caller-owned exchange buffers (device memory): local = slice, global = world * slice */
 int sfe_engine_set_exchange_buffers(sfe_engine *e, void *local, void *global);
 int64_t sfe_engine_collect_records(sfe_engine *e, sfe_step_record *out, int64_t cap);
+/* NCCL exchange driven from C++ (libnccl.so.2 is dlopen'ed; pass its path or NULL): rank 0
+ * obtains a 128-byte unique id and ships it to the other ranks, every rank then calls
+ * sfe_engine_comm_init; sfe_engine_enqueue_partitioned enqueues whole steps (neuron phase,
+ * ncclAllGather of the raster slices over NVLink, message phase) without host round trips. */
+int sfe_nccl_get_unique_id(void *out128, const char *libnccl_path);
+int sfe_engine_comm_init(sfe_engine *e, const void *unique_id128, const char *libnccl_path);
+int sfe_engine_comm_destroy(sfe_engine *e);
+int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps);
 /* last n records of the device log (for steps replayed from a captured CUDA graph) */
 int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
 int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, uint32_t *world, uint32_t *slice_words,

@@ -2248,6 +2248,18 @@ extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
     return 0;
 }
 
+// SFE_PHASE_PROFILE diagnostic: events dropped between the kernels of a partitioned step
+static std::vector<cudaEvent_t> g_prof_events;
+static bool g_prof_on = false;
+static void prof_mark(sfe_engine *e)
+{
+    if (!g_prof_on) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, e->stream);
+    g_prof_events.push_back(ev);
+}
+
 extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
 {
     SFE_CUDA(cudaSetDevice(e->device));
@@ -2256,11 +2268,13 @@ extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
         expand_kernel<<<e->n_all_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
         ++e->launches;
     }
+    prof_mark(e);
     if (!e->fanout_list.empty())
     {
         launch_fanout(e);
         ++e->launches;
     }
+    prof_mark(e);
     finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
     ++e->launches;
     ++e->total_timesteps;
@@ -2395,4 +2409,179 @@ extern "C" int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out,
     e->total_timesteps = counters[0];
     e->log_read = cursor;
     return n;
+}
+
+// ===========================================================================
+// NCCL exchange driven from C++ (no Python in the per-step loop)
+// ===========================================================================
+// libnccl is loaded at run time (dlopen) so the single-GPU library has no NCCL
+// dependency. Only four entry points are used; their signatures and the enum
+// values below are those of NCCL 2.x's public nccl.h.
+#include <dlfcn.h>
+
+namespace
+{
+constexpr int kNcclUniqueIdBytes = 128;
+struct NcclUniqueId
+{
+    char internal[kNcclUniqueIdBytes];
+};
+constexpr int kNcclUint32 = 3; // ncclDataType_t::ncclUint32
+using NcclComm = void *;
+struct NcclApi
+{
+    void *lib{nullptr};
+    int (*GetUniqueId)(NcclUniqueId *){nullptr};
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int){nullptr};
+    int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t){nullptr};
+    int (*CommDestroy)(NcclComm){nullptr};
+    const char *(*GetErrorString)(int){nullptr};
+};
+NcclApi g_nccl;
+
+int nccl_load(const char *path)
+{
+    if (g_nccl.lib != nullptr) return 0;
+    const char *candidates[] = {path, std::getenv("SFE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *c : candidates)
+    {
+        if (c == nullptr || *c == '\0') continue;
+        g_nccl.lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib != nullptr) break;
+    }
+    if (g_nccl.lib == nullptr)
+    {
+        sfe::set_last_error("could not load libnccl.so.2 (pass its path or set SFE_NCCL_LIB)");
+        return -1;
+    }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(g_nccl.lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(g_nccl.lib, "ncclCommInitRank"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(g_nccl.lib, "ncclAllGather"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(g_nccl.lib, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(g_nccl.lib, "ncclGetErrorString"));
+    if (g_nccl.GetUniqueId == nullptr || g_nccl.CommInitRank == nullptr || g_nccl.AllGather == nullptr ||
+            g_nccl.CommDestroy == nullptr || g_nccl.GetErrorString == nullptr)
+    {
+        sfe::set_last_error("libnccl lacks an expected symbol");
+        return -1;
+    }
+    return 0;
+}
+std::vector<std::pair<sfe_engine *, NcclComm>> g_comms; // engine -> communicator
+
+NcclComm comm_of(sfe_engine *e)
+{
+    for (auto &kv : g_comms)
+        if (kv.first == e) return kv.second;
+    return nullptr;
+}
+} // namespace
+
+// rank 0 creates the id (128 bytes) and ships it to the other ranks (torch.distributed / any channel)
+extern "C" int sfe_nccl_get_unique_id(void *out128, const char *libnccl_path)
+{
+    if (nccl_load(libnccl_path) != 0) return -1;
+    NcclUniqueId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0)
+    {
+        sfe::set_last_error(std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+        return -1;
+    }
+    std::memcpy(out128, id.internal, kNcclUniqueIdBytes);
+    return 0;
+}
+
+extern "C" int sfe_engine_comm_init(sfe_engine *e, const void *unique_id128, const char *libnccl_path)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (nccl_load(libnccl_path) != 0) return -1;
+    NcclUniqueId id;
+    std::memcpy(id.internal, unique_id128, kNcclUniqueIdBytes);
+    NcclComm comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, static_cast<int>(e->world), id, static_cast<int>(e->rank));
+    if (rc != 0)
+    {
+        sfe::set_last_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+        return -1;
+    }
+    g_comms.emplace_back(e, comm);
+    return 0;
+}
+
+extern "C" int sfe_engine_comm_destroy(sfe_engine *e)
+{
+    for (size_t i = 0; i < g_comms.size(); ++i)
+        if (g_comms[i].first == e)
+        {
+            g_nccl.CommDestroy(g_comms[i].second);
+            g_comms.erase(g_comms.begin() + static_cast<long>(i));
+            break;
+        }
+    return 0;
+}
+
+// `timesteps` full steps of a partitioned chip, enqueued back to back on the engine's
+// stream: neuron phase -> ncclAllGather(raster slices) over NVLink -> expand + message phase
+extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    NcclComm comm = comm_of(e);
+    if (e->world > 1 && comm == nullptr)
+    {
+        sfe::set_last_error("sfe_engine_enqueue_partitioned: call sfe_engine_comm_init first");
+        return -1;
+    }
+    if (e->total_timesteps - e->log_read + timesteps > e->log_cap)
+    {
+        sfe::set_last_error("more than " + std::to_string(e->log_cap) + " uncollected steps; collect first");
+        return -1;
+    }
+    // SFE_PHASE_PROFILE=1: bracket every kernel with events and print the mean device time of
+    // each (diagnostic only)
+    static const bool profile = std::getenv("SFE_PHASE_PROFILE") != nullptr;
+    const int64_t prof_steps = profile ? std::min<int64_t>(timesteps, 128) : 0;
+    for (int64_t s = 0; s < timesteps; ++s)
+    {
+        g_prof_on = s < prof_steps;
+        prof_mark(e);
+        if (sfe_engine_enqueue_neuron_phase(e) != 0) return -1;
+        prof_mark(e);
+        if (e->world > 1)
+        {
+            const int rc = g_nccl.AllGather(e->d_fired_local, e->d_fired_global, e->slice_words, kNcclUint32, comm, e->stream);
+            if (rc != 0)
+            {
+                sfe::set_last_error(std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc));
+                return -1;
+            }
+            ++e->launches;
+        }
+        prof_mark(e);
+        if (sfe_engine_enqueue_message_phase(e) != 0) return -1; // marks after expand and after fanout
+        prof_mark(e);
+    }
+    g_prof_on = false;
+    if (prof_steps > 0)
+    {
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+        constexpr int kMarks = 6;
+        double acc[kMarks] = {0, 0, 0, 0, 0, 0};
+        for (int64_t s = 0; s < prof_steps; ++s)
+            for (int k = 0; k < kMarks; ++k)
+            {
+                const size_t a = static_cast<size_t>(s) * kMarks + k;
+                if (a + 1 >= g_prof_events.size()) break;
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, g_prof_events[a], g_prof_events[a + 1]);
+                acc[k] += ms;
+            }
+        const double d = 1e3 / static_cast<double>(prof_steps);
+        std::fprintf(stderr, "[sfe phase profile] rank %d: soma %.1f us, exchange %.1f us, expand %.1f us, fanout %.1f us, "
+                "finalize %.1f us, gap %.1f us (mean of %lld steps)\n",
+                e->rank, acc[0] * d, acc[1] * d, acc[2] * d, acc[3] * d, acc[4] * d, acc[5] * d, static_cast<long long>(prof_steps));
+        for (cudaEvent_t ev : g_prof_events) cudaEventDestroy(ev);
+        g_prof_events.clear();
+    }
+    return 0;
 }

@@ -153,6 +153,10 @@ def lib():
         "sfe_engine_partition_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
         "sfe_chip_set_partition": (C.c_int, [vp, u32, u32]),
         "sfe_engine_read_log_tail": (i64, [vp, vp, i64]),
+        "sfe_nccl_get_unique_id": (C.c_int, [vp, cstr]),
+        "sfe_engine_comm_init": (C.c_int, [vp, vp, cstr]),
+        "sfe_engine_comm_destroy": (C.c_int, [vp]),
+        "sfe_engine_enqueue_partitioned": (C.c_int, [vp, i64]),
         "sfe_engine_raster_layout": (C.c_int, [vp, vp, sz]),
         "sfe_engine_synchronize": (C.c_int, [vp]),
         "sfe_device_memcpy": (C.c_int, [vp, vp, sz]),
