@@ -304,6 +304,12 @@ int sfe_engine_comm_destroy(sfe_engine *e);
 int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps);
 /* last n records of the device log (for steps replayed from a captured CUDA graph) */
 int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
+/* Host-only plan of a chip split over `world` GPUs (no CUDA call): owner[c] = rank of core c
+ * (contiguous ranges balanced by synapse + neuron work; the reference keeps all cores in one
+ * process, src/chip.cpp:586-618), fired_word_begin[c] = first word of core c in the exchanged
+ * fired-bit raster (world equal slices of *slice_words words). Outputs may be NULL. */
+int sfe_plan_partition(const sfe_tables *tables, uint32_t world, uint32_t *owner, uint32_t *fired_word_begin,
+        uint32_t *slice_words);
 int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, uint32_t *world, uint32_t *slice_words,
         uint32_t *local_cores, uint64_t *local_neurons);
 int sfe_engine_raster_layout(const sfe_engine *e, uint32_t *word_begin, size_t n_cores);

@@ -1424,38 +1424,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
     if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
 
-    // ---- partition: contiguous core ranges balanced by synapse + neuron work -------
+    // ---- partition + raster layout (host/partition.cpp) --------------------------
     e->owner.assign(tb->n_cores, 0);
-    if (e->world > 1)
-    {
-        double total = 0.0;
-        for (uint32_t c = 0; c < tb->n_cores; ++c)
-            total += static_cast<double>(tb->cores[c].syn_count) + 64.0 * tb->cores[c].neuron_count;
-        double before = 0.0;
-        uint32_t last = 0;
-        for (uint32_t c = 0; c < tb->n_cores; ++c)
-        {
-            const double w = static_cast<double>(tb->cores[c].syn_count) + 64.0 * tb->cores[c].neuron_count;
-            if (w > 0.0 && total > 0.0)
-                last = std::max(last, std::min(e->world - 1, static_cast<uint32_t>((before + 0.5 * w) * e->world / total)));
-            e->owner[c] = last;
-            before += w;
-        }
-    }
+    e->fired_word_begin.assign(tb->n_cores, 0);
+    if (sfe_plan_partition(tb, e->world, e->owner.data(), e->fired_word_begin.data(), &e->slice_words) != 0) return -1;
     auto is_local = [&](uint32_t c) { return e->owner[c] == e->rank; };
-    // raster layout: one equal-sized slice per rank (all-gather friendly), cores word-aligned
-    {
-        std::vector<uint32_t> words(e->world, 0);
-        for (uint32_t c = 0; c < tb->n_cores; ++c) words[e->owner[c]] += (tb->cores[c].neuron_count + 31) / 32;
-        e->slice_words = std::max<uint32_t>(1, *std::max_element(words.begin(), words.end()));
-    }
 
     // ---- per-core device descriptors, padded bit layouts ---------------------
     e->h_cores.resize(tb->n_cores);
     std::vector<uint32_t> inbox_word_begin(tb->n_cores);
-    e->fired_word_begin.resize(tb->n_cores);
     uint32_t inbox_words = 0, dend_cells = 0;
-    std::vector<uint32_t> slice_fill(e->world, 0);
     uint32_t inbox_lo = UINT32_MAX, inbox_hi = 0;
     size_t smem_max = 0;
     for (uint32_t c = 0; c < tb->n_cores; ++c)
@@ -1468,7 +1446,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.axon_begin = cd.axon_in_begin;
         d.axon_count = cd.axon_in_count;
         d.inbox_word_begin = inbox_words;
-        d.fired_word_begin = e->owner[c] * e->slice_words + slice_fill[e->owner[c]];
+        d.fired_word_begin = e->fired_word_begin[c];
         d.dend_base = dend_cells;
         d.ring = cd.ring == 0 ? 1 : cd.ring;
         d.acc_mode = cd.acc_mode;
@@ -1487,14 +1465,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.e_south = tile.energy_south;
         d.e_north = tile.energy_north;
         inbox_word_begin[c] = inbox_words;
-        e->fired_word_begin[c] = d.fired_word_begin;
         if (is_local(c) && cd.axon_in_count > 0)
         {
             inbox_lo = std::min(inbox_lo, inbox_words);
             inbox_hi = std::max(inbox_hi, inbox_words + (cd.axon_in_count + 31) / 32);
         }
         inbox_words += (cd.axon_in_count + 31) / 32;
-        slice_fill[e->owner[c]] += (cd.neuron_count + 31) / 32;
         dend_cells += cd.neuron_count * d.ring;
         if (cd.neuron_count > 0) e->all_soma_list.push_back(c);
         if (!is_local(c)) continue;
