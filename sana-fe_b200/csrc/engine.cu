@@ -104,6 +104,11 @@ struct DevTables
     const uint32_t *neuron_aux;
     const uint32_t *axon_out_begin;
     const uint32_t *axon_out_bit;     // padded inbox bit index of each axon-out
+    // partitioned chip: the neurons of the whole chip that reach THIS rank's cores
+    const uint32_t *expand_word;      // raster word index of every relevant word
+    const uint32_t *expand_begin;     // CSR over (relevant word, bit): n_expand_words * 32 + 1
+    const uint32_t *expand_bit;       // local inbox bit positions
+    uint32_t n_expand_words;
     const sfe_input_desc *inputs;
     const uint8_t *input_spikes;
     const sfe_axon_in *axons_in;
@@ -522,24 +527,22 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
 // (partition by destination core, exchange the fired-source set).
 __global__ void __launch_bounds__(kSomaThreads) expand_kernel(const DevTables t, const DevState s)
 {
-    // one thread per raster word (32 neurons): almost all words hold 0-4 spikes
+    // one thread per neuron of the raster words that can reach this rank (load-time list);
+    // a fired neuron raises its local inbox bits, loads batched eight at a time
     const uint32_t idx = blockIdx.x * kSomaThreads + threadIdx.x;
-    if (idx >= t.n_raster_words) return;
-    uint32_t word = __ldg(s.fired_global + idx);
-    if (word == 0u) return;
-    const uint32_t base = __ldg(t.raster_neuron + idx); // device index of the word's bit 0
-    while (word != 0u)
+    if (idx >= t.n_expand_words * 32u) return;
+    const uint32_t word = __ldg(s.fired_global + __ldg(t.expand_word + (idx >> 5)));
+    if (((word >> (idx & 31u)) & 1u) == 0u) return;
+    const uint32_t a0 = __ldg(t.expand_begin + idx), a1 = __ldg(t.expand_begin + idx + 1);
+    for (uint32_t base = a0; base < a1; base += 8u)
     {
-        const uint32_t b = __ffs(word) - 1;
-        word &= word - 1u;
-        const uint32_t i = base + b;
-        const uint32_t a0 = __ldg(t.axon_out_begin + i), a1 = __ldg(t.axon_out_begin + i + 1);
-        for (uint32_t a = a0; a < a1; ++a)
-        {
-            const uint32_t bit = __ldg(t.axon_out_bit + a);
-            const uint32_t w = bit >> 5;
-            if (w >= t.inbox_lo && w < t.inbox_hi) atomicOr(&s.inbox[w], 1u << (bit & 31));
-        }
+        uint32_t bit[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+            if (base + x < a1) bit[x] = __ldg(t.expand_bit + base + x);
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+            if (base + x < a1) atomicOr(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
     }
 }
 
@@ -1052,18 +1055,53 @@ __device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 
     return r;
 }
 
+__device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &x)
+{
+    b.fired += x.fired;
+    b.updated += x.updated;
+    b.packets += x.packets;
+    b.hops += x.hops;
+    b.events += x.events;
+    b.syn_e += x.syn_e;
+    b.den_e += x.den_e;
+    b.soma_e += x.soma_e;
+    b.net_e += x.net_e;
+    b.max_gen = fmax(b.max_gen, x.max_gen);
+    b.max_proc = fmax(b.max_proc, x.max_proc);
+}
+
+__device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly: a fixed order
+{
+    p.fired = warp_sum(p.fired);
+    p.updated = warp_sum(p.updated);
+    p.packets = warp_sum(p.packets);
+    p.hops = warp_sum(p.hops);
+    p.events = warp_sum(p.events);
+    p.syn_e = warp_sum(p.syn_e);
+    p.den_e = warp_sum(p.den_e);
+    p.soma_e = warp_sum(p.soma_e);
+    p.net_e = warp_sum(p.net_e);
+    p.max_gen = warp_max(p.max_gen);
+    p.max_proc = warp_max(p.max_proc);
+    return p;
+}
+
+// One WARP per active core: the lanes fetch the core's segment / work-item statistics in
+// parallel (one round trip instead of seg_count + item_count dependent ones) and fold them
+// with a butterfly; every sum is formed in the same order on every run.
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
 {
     __shared__ StepPartial warp_part[kFinalThreads / 32];
     __shared__ uint32_t ticket_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const uint32_t a = blockIdx.x * kFinalThreads + threadIdx.x;
+    const uint32_t a = blockIdx.x * (kFinalThreads / 32) + warp;
     if (a < t.n_active_cores)
     {
         const uint32_t ci = t.active_core_list[a];
         const CoreDev &core = t.cores[ci];
         StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
-        for (uint32_t g = 0; g < core.seg_count; ++g) // fixed order: deterministic sums
+        for (uint32_t g = lane; g < core.seg_count; g += 32)
         {
             const StatsN x = s.stats_n[core.seg_begin + g];
             n.updated += x.updated;
@@ -1073,9 +1111,8 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
             n.dend_e += x.dend_e;
             n.gen_sum += x.gen_sum;
         }
-        n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
         StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
-        for (uint32_t g = 0; g < core.item_count; ++g) // fixed order: deterministic sums
+        for (uint32_t g = lane; g < core.item_count; g += 32)
         {
             const StatsM x = s.stats_m[core.item_begin + g];
             m.msgs += x.msgs;
@@ -1088,6 +1125,22 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
             m.den_e += x.den_e;
             m.proc += x.proc;
         }
+        n.updated = warp_sum(n.updated);
+        n.fired = warp_sum(n.fired);
+        n.packets = warp_sum(n.packets);
+        n.soma_e = warp_sum(n.soma_e);
+        n.dend_e = warp_sum(n.dend_e);
+        n.gen_sum = warp_sum(n.gen_sum);
+        m.msgs = warp_sum(m.msgs);
+        m.events = warp_sum(m.events);
+        m.hop_e = warp_sum(m.hop_e);
+        m.hop_w = warp_sum(m.hop_w);
+        m.hop_n = warp_sum(m.hop_n);
+        m.hop_s = warp_sum(m.hop_s);
+        m.syn_e = warp_sum(m.syn_e);
+        m.den_e = warp_sum(m.den_e);
+        m.proc = warp_sum(m.proc);
+        n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
         p.fired = n.fired;
         p.updated = n.updated;
         p.packets = n.packets;
@@ -1105,62 +1158,29 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
         p.max_gen = n.gen_sum;
         p.max_proc = m.proc;
     }
-    p.fired = warp_sum(p.fired);
-    p.updated = warp_sum(p.updated);
-    p.packets = warp_sum(p.packets);
-    p.hops = warp_sum(p.hops);
-    p.events = warp_sum(p.events);
-    p.syn_e = warp_sum(p.syn_e);
-    p.den_e = warp_sum(p.den_e);
-    p.soma_e = warp_sum(p.soma_e);
-    p.net_e = warp_sum(p.net_e);
-    p.max_gen = warp_max(p.max_gen);
-    p.max_proc = warp_max(p.max_proc);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) warp_part[warp] = p;
     __syncthreads();
     if (threadIdx.x == 0)
     {
         StepPartial b = warp_part[0];
-        for (int w = 1; w < kFinalThreads / 32; ++w)
-        {
-            const StepPartial &x = warp_part[w];
-            b.fired += x.fired;
-            b.updated += x.updated;
-            b.packets += x.packets;
-            b.hops += x.hops;
-            b.events += x.events;
-            b.syn_e += x.syn_e;
-            b.den_e += x.den_e;
-            b.soma_e += x.soma_e;
-            b.net_e += x.net_e;
-            b.max_gen = fmax(b.max_gen, x.max_gen);
-            b.max_proc = fmax(b.max_proc, x.max_proc);
-        }
+        for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
         s.partials[blockIdx.x] = b;
         __threadfence();
         ticket_s = atomicAdd(s.final_ticket, 1u);
     }
     __syncthreads();
-    if (ticket_s != gridDim.x - 1 || threadIdx.x != 0) return;
-    // ---- last CTA: fold the partials (block order) and append the step record ----------
+    if (ticket_s != gridDim.x - 1) return;
+    // ---- last CTA: fold the per-CTA partials and append the step record ------------------
     __threadfence();
-    StepPartial b = load_partial(&s.partials[0]);
-    for (uint32_t k = 1; k < gridDim.x; ++k)
-    {
-        const StepPartial x = load_partial(&s.partials[k]);
-        b.fired += x.fired;
-        b.updated += x.updated;
-        b.packets += x.packets;
-        b.hops += x.hops;
-        b.events += x.events;
-        b.syn_e += x.syn_e;
-        b.den_e += x.den_e;
-        b.soma_e += x.soma_e;
-        b.net_e += x.net_e;
-        b.max_gen = fmax(b.max_gen, x.max_gen);
-        b.max_proc = fmax(b.max_proc, x.max_proc);
-    }
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (uint32_t k = threadIdx.x; k < gridDim.x; k += kFinalThreads) fold_partial(b, load_partial(&s.partials[k]));
+    b = warp_fold(b);
+    __syncthreads(); // warp_part is reused
+    if (lane == 0) warp_part[warp] = b;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    b = warp_part[0];
+    for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
     sfe_step_record r;
     r.neurons_fired = static_cast<long long>(b.fired);
     r.neurons_updated = static_cast<long long>(b.updated);
@@ -1508,6 +1528,37 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             bits[a] = inbox_word_begin[c] * 32u + (id - tb->cores[c].axon_in_begin);
         }
         if (e->upload(&e->t.axon_out_bit, bits.data(), bits.size()) != 0) return -1;
+        if (e->world > 1)
+        {
+            // the part of every neuron's axon-out list that lands in this rank's inbox range,
+            // kept only for raster words with at least one such neuron
+            const uint64_t lo = static_cast<uint64_t>(e->t.inbox_lo) * 32u, hi = static_cast<uint64_t>(e->t.inbox_hi) * 32u;
+            std::vector<uint32_t> x_word, x_begin, x_bit;
+            x_begin.push_back(0u);
+            for (uint32_t c = 0; c < tb->n_cores; ++c)
+                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += 32)
+                {
+                    const size_t mark_begin = x_begin.size(), mark_bit = x_bit.size();
+                    for (uint32_t k = k0; k < k0 + 32; ++k)
+                    {
+                        if (k < tb->cores[c].neuron_count)
+                        {
+                            const uint32_t i = tb->cores[c].neuron_begin + k;
+                            for (uint32_t a = tb->axon_out_begin[i]; a < tb->axon_out_begin[i + 1]; ++a)
+                                if (bits[a] >= lo && bits[a] < hi) x_bit.push_back(bits[a]);
+                        }
+                        x_begin.push_back(static_cast<uint32_t>(x_bit.size()));
+                    }
+                    if (x_bit.size() == mark_bit) x_begin.resize(mark_begin); // nothing reaches this rank
+                    else x_word.push_back(e->fired_word_begin[c] + (k0 >> 5));
+                }
+            e->t.n_expand_words = static_cast<uint32_t>(x_word.size());
+            if (x_bit.empty()) x_bit.push_back(0u);
+            if (x_word.empty()) x_word.push_back(0u);
+            if (e->upload(&e->t.expand_word, x_word.data(), x_word.size()) != 0) return -1;
+            if (e->upload(&e->t.expand_begin, x_begin.data(), x_begin.size()) != 0) return -1;
+            if (e->upload(&e->t.expand_bit, x_bit.data(), x_bit.size()) != 0) return -1;
+        }
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
     if (e->upload(&e->t.inputs, tb->inputs, tb->n_inputs) != 0) return -1;
@@ -1661,7 +1712,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                     word_neuron[e->h_cores[c].fired_word_begin + (k0 >> 5)] = tb->cores[c].neuron_begin + k0;
             e->t.n_raster_words = e->fired_words;
             if (e->upload(&e->t.raster_neuron, word_neuron.data(), word_neuron.size()) != 0) return -1;
-            e->n_all_segments = (e->fired_words + kSomaThreads - 1) / kSomaThreads;
+            e->n_all_segments = (e->t.n_expand_words * 32u + kSomaThreads - 1) / kSomaThreads;
         }
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
@@ -1696,7 +1747,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->s.work, 1) != 0) return -1;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
-    e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads - 1) / kFinalThreads);
+    e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
     if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (engine_init_state(e) != 0) return -1;
@@ -1743,7 +1794,34 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         // are several items per resident CTA (no tail behind the slowest core, and a rank
         // that owns few cores still fills the GPU)
         const size_t slots = static_cast<size_t>(per_sm) * sms;
-        size_t split = e->fanout_list.empty() ? 1 : std::max<size_t>(1, std::min<size_t>(16, (6 * slots) / e->fanout_list.size()));
+        // The split is chosen with a small cost model: a CTA that processes k items pays k times a
+        // fixed latency (ticket, descriptors, inbox scan, axon records, epilogue: ~5 us of dependent
+        // round trips) plus its share of the streaming time, and the step ends with the CTA that
+        // drew the most items. Few cores -> exactly one item per CTA; many cores -> enough items
+        // per CTA that the last wave is short.
+        size_t split = 1;
+        if (!e->fanout_list.empty())
+        {
+            double syn = 0.0;
+            for (uint32_t c : e->fanout_list) syn += static_cast<double>(tb->cores[c].syn_count);
+            const double n_cores_f = static_cast<double>(e->fanout_list.size());
+            const double core_bytes = 12.0 * 0.1 * syn / n_cores_f; // nominal 10 % activity
+            const double fixed_us = 5.0, hbm_bytes_per_us = 6.5e6, cta_bytes_per_us = 3.0e4;
+            double best = 0.0;
+            for (size_t cand = 1; cand <= 16; ++cand)
+            {
+                const double items = n_cores_f * static_cast<double>(cand);
+                const double per_cta = std::ceil(items / static_cast<double>(slots));
+                const double rate = std::min(cta_bytes_per_us, hbm_bytes_per_us / std::min<double>(items, static_cast<double>(slots)));
+                const double cost = per_cta * (fixed_us + core_bytes / static_cast<double>(cand) / rate);
+                // fewer items unless clearly better; a single wave should fill the resident CTAs
+                if (cand == 1 || cost < best * 0.98 || (per_cta == 1.0 && cost <= best * 1.001))
+                {
+                    best = cost;
+                    split = cand;
+                }
+            }
+        }
         if (const char *v = std::getenv("SFE_FANOUT_SPLIT")) split = std::max(1, std::atoi(v));
         std::vector<FanItem> items;
         std::vector<double> weight;
