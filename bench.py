@@ -317,13 +317,24 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     n = tb.n_neurons
     slice_words = C.c_uint32()
     L.sfe_engine_partition_info(eng, None, None, C.byref(slice_words), None, None)
-    lib_path = nccl_library_path().encode()
-    uid = np.zeros(128, dtype=np.uint8)
-    if rank == 0:
-        assert L.sfe_nccl_get_unique_id(uid.ctypes.data, lib_path) == 0, L.sfe_last_error()
-    uid_t = torch.from_numpy(uid)
-    dist.broadcast(uid_t, src=0)
-    assert L.sfe_engine_comm_init(eng, uid_t.numpy().ctypes.data, lib_path) == 0, L.sfe_last_error()
+    exchange = os.environ.get("SFE_EXCHANGE", "p2p")
+    if exchange == "p2p":
+        # fused exchange: the neuron-phase kernel stores the raster into every peer over NVLink
+        mine = np.zeros(64, dtype=np.uint8)
+        assert L.sfe_engine_p2p_export(eng, mine.ctypes.data) == 0, L.sfe_last_error()
+        everyone = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(everyone, torch.from_numpy(mine))
+        handles = np.concatenate([h.numpy() for h in everyone])
+        assert L.sfe_engine_p2p_attach(eng, handles.ctypes.data) == 0, L.sfe_last_error()
+        dist.barrier()
+    else:
+        lib_path = nccl_library_path().encode()
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            assert L.sfe_nccl_get_unique_id(uid.ctypes.data, lib_path) == 0, L.sfe_last_error()
+        uid_t = torch.from_numpy(uid)
+        dist.broadcast(uid_t, src=0)
+        assert L.sfe_engine_comm_init(eng, uid_t.numpy().ctypes.data, lib_path) == 0, L.sfe_last_error()
 
     def collect():
         buf = np.zeros(4096, dtype=sfe.STEP_DTYPE)
@@ -357,7 +368,14 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     seconds = float(tmax.item())
     events_all, messages_all, fired_all, launches_all = (int(x) for x in tot.tolist()[:4])
     fan_s_mean = tot.tolist()[4] / world
-    L.sfe_engine_comm_destroy(eng)
+    xerr = L.sfe_engine_exchange_error(eng)
+    dist.barrier()
+    if exchange == "p2p":
+        L.sfe_engine_p2p_detach(eng)
+    else:
+        L.sfe_engine_comm_destroy(eng)
+    if xerr != 0:
+        raise SystemExit("bench.py: a peer did not arrive at the raster exchange in time; results invalid")
     if rank != 0:
         dist.destroy_process_group()
         return 0
@@ -370,8 +388,9 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
         "config": {"workload": WORKLOAD if args.cores == FULL["cores"] else f"DEBUG scale: {args.cores} cores",
                    "neurons": n, "synapses": int(tb.n_synapses), "timing_model": "simple",
                    "l2_policy": "inputs larger than L2 (synapse tables of each partition >> 126 MB)",
-                   "parallelism": f"cores partitioned over {world} GPUs, per-step ncclAllGather of the fired raster "
-                                  f"({4 * slice_words.value * world} B) enqueued from C++",
+                   "parallelism": f"cores partitioned over {world} GPUs; fired raster ({4 * slice_words.value * world} B/step) "
+                                  + ("stored into every peer by the neuron-phase kernel over NVLink (CUDA IPC), flag barrier"
+                                     if exchange == "p2p" else "exchanged with ncclAllGather enqueued from C++"),
                    "activity": fired_all / float(n * args.steps), "load_s": load_s},
         "timesteps_per_s": args.steps / seconds, "events_per_step": events_all / args.steps,
         "roofline": {"bound": "hbm", "kernel": "fanout_kernel (all ranks)",

@@ -302,6 +302,18 @@ int sfe_nccl_get_unique_id(void *out128, const char *libnccl_path);
 int sfe_engine_comm_init(sfe_engine *e, const void *unique_id128, const char *libnccl_path);
 int sfe_engine_comm_destroy(sfe_engine *e);
 int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps);
+/* Peer-memory exchange (CUDA IPC over NVLink / NVSwitch), one process per GPU, up to 8 ranks:
+ * the neuron-phase kernel of every rank stores its raster words directly into every rank's
+ * double-buffered raster and raises an arrival flag there; the message phase begins by waiting
+ * (bounded) for all flags — no collective launch between the phases. Every rank exports a
+ * 64-byte handle, the caller gathers the handles of all ranks in rank order (its own control
+ * plane) and hands them to attach. After attach, sfe_engine_enqueue_partitioned needs no NCCL
+ * communicator. All ranks must enqueue the same number of steps and synchronise on the host
+ * before detach/destroy. sfe_engine_exchange_error: 1 if a peer failed to arrive in time. */
+int sfe_engine_p2p_export(sfe_engine *e, void *handle64);
+int sfe_engine_p2p_attach(sfe_engine *e, const void *handles_world_x_64);
+int sfe_engine_p2p_detach(sfe_engine *e);
+int sfe_engine_exchange_error(sfe_engine *e);
 /* last n records of the device log (for steps replayed from a captured CUDA graph) */
 int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
 /* Host-only plan of a chip split over `world` GPUs (no CUDA call): owner[c] = rank of core c

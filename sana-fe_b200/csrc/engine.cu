@@ -87,8 +87,6 @@ struct DevTables
 {
     const CoreDev *cores;
     const struct SomaSegment *soma_segments; // one record per neuron-phase segment (local cores)
-    const uint32_t *raster_neuron;    // device index of bit 0 of every word of the global raster
-    uint32_t n_raster_words;
     uint32_t partitioned;             // 1: this engine simulates a core range; spikes arrive via the exchanged raster
     uint32_t inbox_lo, inbox_hi;      // local inbox word range [lo, hi)
     uint32_t n_soma_classes;
@@ -104,11 +102,9 @@ struct DevTables
     const uint32_t *neuron_aux;
     const uint32_t *axon_out_begin;
     const uint32_t *axon_out_bit;     // padded inbox bit index of each axon-out
-    // partitioned chip: the neurons of the whole chip that reach THIS rank's cores
-    const uint32_t *expand_word;      // raster word index of every relevant word
-    const uint32_t *expand_begin;     // CSR over (relevant word, bit): n_expand_words * 32 + 1
-    const uint32_t *expand_bit;       // local inbox bit positions
-    uint32_t n_expand_words;
+    // partitioned chip: raster bit of the source neuron of every local axon-in, indexed by
+    // (inbox bit position - 32 * inbox_lo); 0xFFFFFFFF for padding bits
+    const uint32_t *axon_src;
     const sfe_input_desc *inputs;
     const uint8_t *input_spikes;
     const sfe_axon_in *axons_in;
@@ -119,9 +115,29 @@ struct DevTables
     double sync_delay;
 };
 
+// Multi-GPU exchange over peer memory (NVLink): every rank's neuron phase stores its raster
+// words straight into every rank's double-buffered raster and then raises an arrival flag
+// there; the message phase of a rank starts by waiting for the flags of all ranks.
+constexpr int kMaxPeers = 8;
+struct Exchange
+{
+    uint32_t *raster[kMaxPeers];  // [2][fired_words] of every rank (own entry: local memory)
+    uint32_t *flags[kMaxPeers];   // [world] arrival flags of every rank
+    uint32_t n_peers;             // 0: exchange done by the host side (NCCL / device copies)
+    uint32_t rank;
+    uint32_t fired_words;
+    uint32_t slice_words;         // words per rank slice (multiple of 4)
+    uint32_t acquire_mode, pad;
+    const uint32_t *local_slice;  // this rank's slice as the neuron phase wrote it
+    unsigned long long *epoch;    // steps finished by this engine since creation (never reset)
+    uint32_t *error;              // sticky: a peer did not arrive in time
+    unsigned long long *stamps;   // diagnostic (SFE_PHASE_PROFILE): [4096][4] %globaltimer of CTA 0
+};
+
 struct StepPartial;
 struct DevState
 {
+    Exchange x;
     double *v, *u, *bias;
     int32_t *refractory;
     uint8_t *status;
@@ -147,6 +163,90 @@ struct DevState
 // ---------------------------------------------------------------------------
 // Small device helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, const uint32_t v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+
+// Peer-memory exchange, first half (CTA 0 of the kernel that opens the message phase): copy
+// this rank's raster slice into every rank's raster with 16-byte stores over NVLink, fence once
+// at system scope, publish the arrival flags. The neuron phase that wrote the slice is the
+// previous kernel on the stream, so no intra-kernel ordering is needed on the producer side.
+__device__ __forceinline__ void exchange_publish(const Exchange &x)
+{
+    const unsigned long long epoch = *x.epoch;
+    const size_t at = (epoch & 1ull) * x.fired_words + static_cast<size_t>(x.rank) * x.slice_words; // 16-byte aligned
+    const uint4 *src = reinterpret_cast<const uint4 *>(x.local_slice);
+    const uint32_t n_vec = x.slice_words / 4u;
+    for (uint32_t i0 = threadIdx.x; i0 < n_vec; i0 += 8u * blockDim.x)
+    {
+        uint4 v[8]; // eight independent loads in flight, then the stores (posted)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j * blockDim.x < n_vec) v[j] = __ldcg(src + i0 + j * blockDim.x);
+        for (uint32_t q = 0; q < x.n_peers; ++q)
+        {
+            uint4 *dst = reinterpret_cast<uint4 *>(x.raster[q] + at);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (i0 + j * blockDim.x < n_vec) dst[i0 + j * blockDim.x] = v[j];
+        }
+    }
+    // ONE system-scope fence per step: the barrier orders every thread's stores before thread 0,
+    // its fence is cumulative over them, the flags follow as relaxed stores (a release store per
+    // peer would repeat the fence, which is by far the most expensive instruction here)
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    const uint32_t arrive = static_cast<uint32_t>(epoch) + 1u;
+    for (uint32_t q = 0; q < x.n_peers; ++q) st_relaxed_sys(x.flags[q] + x.rank, arrive);
+}
+
+// Message-phase prologue: wait until every rank has published the current step (bounded: a
+// missing peer sets the sticky error flag instead of hanging the GPU). Returns the raster.
+__device__ __forceinline__ const uint32_t *exchange_wait(const Exchange &x)
+{
+    const unsigned long long epoch = *x.epoch;
+    if (threadIdx.x < x.n_peers && ld_relaxed_sys(x.error) == 0u)
+    {
+        const uint32_t want = static_cast<uint32_t>(epoch) + 1u;
+        const uint32_t *flag = x.flags[x.rank] + threadIdx.x;
+        // time limit on the SM's own cycle counter (%globaltimer is a chip-wide register: polling it
+        // from every waiting CTA is slow and contended); ~2 s at 2 GHz
+        const long long t0 = clock64();
+        while (static_cast<int32_t>(ld_relaxed_sys(flag) - want) < 0)
+        {
+            __nanosleep(40);
+            if (clock64() - t0 > 4000000000ll)
+            {
+                atomicExch(x.error, 1u);
+                break;
+            }
+        }
+        if (x.acquire_mode == 1u) (void) ld_acquire_sys(flag); // pairs with the publisher's fence + relaxed store
+        else if (x.acquire_mode == 2u) __threadfence();
+    }
+    __syncthreads();
+    return x.raster[x.rank] + (epoch & 1ull) * x.fired_words;
+}
 __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll
@@ -522,28 +622,44 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
     s.probe_out[p] = v;
 }
 
-// Multi-GPU: after the fired rasters of all partitions have been exchanged, every rank
-// raises the inbox bits of ITS axons for every neuron of the chip that fired
-// (partition by destination core, exchange the fired-source set).
-__global__ void __launch_bounds__(kSomaThreads) expand_kernel(const DevTables t, const DevState s)
+// Multi-GPU: a rank sees the spikes of the whole chip as a fired-bit raster (SURVEY 8e:
+// partition by destination core, exchange the fired-source set). The message phase derives the
+// inbox word of 32 local axons by looking up the raster bit of each axon's source neuron.
+// Raster lookups are plain (L1-cached, coherent-path) loads. The raster changes only between
+// kernels (NCCL / copies) or, with the peer-memory exchange, before this CTA's acquire of the
+// arrival flags; every lookup comes after that point, so cached lines are never stale. Not
+// __ldg: the non-coherent path is outside the memory model's guarantees for data written
+// while the kernel runs.
+__device__ __forceinline__ uint32_t ld_raster(const uint32_t *p)
 {
-    // one thread per neuron of the raster words that can reach this rank (load-time list);
-    // a fired neuron raises its local inbox bits, loads batched eight at a time
-    const uint32_t idx = blockIdx.x * kSomaThreads + threadIdx.x;
-    if (idx >= t.n_expand_words * 32u) return;
-    const uint32_t word = __ldg(s.fired_global + __ldg(t.expand_word + (idx >> 5)));
-    if (((word >> (idx & 31u)) & 1u) == 0u) return;
-    const uint32_t a0 = __ldg(t.expand_begin + idx), a1 = __ldg(t.expand_begin + idx + 1);
-    for (uint32_t base = a0; base < a1; base += 8u)
+    return *p;
+}
+
+__device__ __forceinline__ uint32_t gather_inbox_word(const uint32_t *__restrict__ src32, const uint32_t *raster)
+{
+    uint32_t word = 0u;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) // two halves: 16 source ids + 16 raster words in flight per thread
     {
-        uint32_t bit[8];
+        uint4 v[4];
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-            if (base + x < a1) bit[x] = __ldg(t.expand_bit + base + x);
+        for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const uint4 *>(src32) + 4 * h + q);
+        uint32_t half = 0u;
 #pragma unroll
-        for (int x = 0; x < 8; ++x)
-            if (base + x < a1) atomicOr(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
+        for (int q = 0; q < 4; ++q)
+        {
+            const uint32_t src[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                // padding axons point at 0xFFFFFFFF
+                const uint32_t r = src[k] != 0xFFFFFFFFu ? ld_raster(raster + (src[k] >> 5)) : 0u;
+                half |= ((r >> (src[k] & 31u)) & 1u) << (4 * q + k);
+            }
+        }
+        word |= half << (16 * h);
     }
+    return word;
 }
 
 // ---------------------------------------------------------------------------
@@ -676,6 +792,23 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
     (void) tma_phase;
 
+    // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory
+    // exchange the collective is fused into this kernel: CTA 0 pushes this rank's raster slice
+    // to every rank over NVLink and raises the arrival flags, every CTA (the grid is one
+    // resident wave) waits for the slices of all ranks before it touches the raster.
+    const uint32_t *raster = s.fired_global;
+    if (s.x.n_peers > 0u)
+    {
+        const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+        unsigned long long *st = stamp ? s.x.stamps + (*s.x.epoch & 4095ull) * 4ull : nullptr;
+        if (stamp) st[0] = global_timer_ns();
+        if (blockIdx.x == 0) exchange_publish(s.x);
+        if (stamp) st[1] = global_timer_ns();
+        raster = exchange_wait(s.x);
+        if (stamp) st[2] = global_timer_ns();
+    }
+    const bool gather = t.partitioned != 0u;
+
     // Persistent CTAs: cores (heaviest first) are handed out through an atomic ticket,
     // so the grid is one resident wave and no SM idles behind a wave boundary.
     for (;;)
@@ -738,7 +871,10 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         for (uint32_t wb = item.word_lo; wb < n_words;)
         {
             const uint32_t wi = wb + threadIdx.x;
-            const uint32_t word = wi < n_words ? s.inbox[core.inbox_word_begin + wi] : 0u;
+            uint32_t word = 0u;
+            if (wi < n_words)
+                word = gather ? gather_inbox_word(t.axon_src + (static_cast<size_t>(core.inbox_word_begin + wi - t.inbox_lo) << 5), raster)
+                              : s.inbox[core.inbox_word_begin + wi];
             const uint32_t pc = __popc(word);
             uint32_t incl = pc;
 #pragma unroll
@@ -763,7 +899,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
                 list_n = accepted == kFanoutThreads ? total : base;
             if (ok && word != 0u)
             {
-                s.inbox[core.inbox_word_begin + wi] = 0u; // consume
+                if (!gather) s.inbox[core.inbox_word_begin + wi] = 0u; // consume
                 uint32_t bits = word, slot = base;
                 while (bits != 0u)
                 {
@@ -904,12 +1040,21 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         for (uint32_t wi = 0; wi < n_words; ++wi)
         {
             uint32_t word = 0u;
-            if (lane == 0)
+            if (gather)
             {
-                word = s.inbox[core.inbox_word_begin + wi];
-                if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u;
+                const uint32_t src = __ldg(t.axon_src + (static_cast<size_t>(core.inbox_word_begin + wi - t.inbox_lo) << 5) + lane);
+                const uint32_t r = src != 0xFFFFFFFFu ? ld_raster(raster + (src >> 5)) : 0u;
+                word = __ballot_sync(0xffffffffu, ((r >> (src & 31u)) & 1u) != 0u);
             }
-            word = __shfl_sync(0xffffffffu, word, 0);
+            else
+            {
+                if (lane == 0)
+                {
+                    word = s.inbox[core.inbox_word_begin + wi];
+                    if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u;
+                }
+                word = __shfl_sync(0xffffffffu, word, 0);
+            }
             while (word != 0u)
             {
                 const uint32_t b = __ffs(word) - 1;
@@ -1200,6 +1345,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
     s.step[0] = s.step[0] + 1;
     *s.work = 0u;
     *s.final_ticket = 0u;
+    *s.x.epoch += 1ull;
 }
 
 // ---------------------------------------------------------------------------
@@ -1315,6 +1461,9 @@ __global__ void __launch_bounds__(256) certify_kernel(
 
 struct sfe_engine
 {
+    uint32_t *p2p_block{nullptr};        // [2][fired_words] raster + [kMaxPeers] flags, exported over CUDA IPC
+    void *p2p_peer_base[kMaxPeers] = {}; // opened peer blocks (own entry stays null)
+    bool p2p_on{false};
     int device{0};
     cudaStream_t stream{nullptr};
     bool own_stream{false};
@@ -1337,7 +1486,6 @@ struct sfe_engine
     unsigned fanout_grid{1};
     unsigned final_grid{1};
     uint32_t n_segments{0};
-    uint32_t n_all_segments{0};
     bool exotic{false};
     // multi-GPU partition (contiguous core ranges)
     uint32_t rank{0}, world{1};
@@ -1530,34 +1678,17 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         if (e->upload(&e->t.axon_out_bit, bits.data(), bits.size()) != 0) return -1;
         if (e->world > 1)
         {
-            // the part of every neuron's axon-out list that lands in this rank's inbox range,
-            // kept only for raster words with at least one such neuron
+            // source neuron (as a raster bit) of every axon-in of this rank's inbox range
             const uint64_t lo = static_cast<uint64_t>(e->t.inbox_lo) * 32u, hi = static_cast<uint64_t>(e->t.inbox_hi) * 32u;
-            std::vector<uint32_t> x_word, x_begin, x_bit;
-            x_begin.push_back(0u);
+            std::vector<uint32_t> src(std::max<uint64_t>(hi > lo ? hi - lo : 0, 32), 0xFFFFFFFFu);
             for (uint32_t c = 0; c < tb->n_cores; ++c)
-                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += 32)
+                for (uint32_t k = 0; k < tb->cores[c].neuron_count; ++k)
                 {
-                    const size_t mark_begin = x_begin.size(), mark_bit = x_bit.size();
-                    for (uint32_t k = k0; k < k0 + 32; ++k)
-                    {
-                        if (k < tb->cores[c].neuron_count)
-                        {
-                            const uint32_t i = tb->cores[c].neuron_begin + k;
-                            for (uint32_t a = tb->axon_out_begin[i]; a < tb->axon_out_begin[i + 1]; ++a)
-                                if (bits[a] >= lo && bits[a] < hi) x_bit.push_back(bits[a]);
-                        }
-                        x_begin.push_back(static_cast<uint32_t>(x_bit.size()));
-                    }
-                    if (x_bit.size() == mark_bit) x_begin.resize(mark_begin); // nothing reaches this rank
-                    else x_word.push_back(e->fired_word_begin[c] + (k0 >> 5));
+                    const uint32_t i = tb->cores[c].neuron_begin + k;
+                    for (uint32_t a = tb->axon_out_begin[i]; a < tb->axon_out_begin[i + 1]; ++a)
+                        if (bits[a] >= lo && bits[a] < hi) src[bits[a] - lo] = e->fired_word_begin[c] * 32u + k;
                 }
-            e->t.n_expand_words = static_cast<uint32_t>(x_word.size());
-            if (x_bit.empty()) x_bit.push_back(0u);
-            if (x_word.empty()) x_word.push_back(0u);
-            if (e->upload(&e->t.expand_word, x_word.data(), x_word.size()) != 0) return -1;
-            if (e->upload(&e->t.expand_begin, x_begin.data(), x_begin.size()) != 0) return -1;
-            if (e->upload(&e->t.expand_bit, x_bit.data(), x_bit.size()) != 0) return -1;
+            if (e->upload(&e->t.axon_src, src.data(), src.size()) != 0) return -1;
         }
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -1703,17 +1834,6 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         }
         e->n_segments = static_cast<uint32_t>(segs.size());
         if (e->upload(&e->t.soma_segments, segs.data(), segs.size()) != 0) return -1;
-        if (e->world > 1)
-        {
-            // padding words (no neurons) point at neuron 0 and are never set
-            std::vector<uint32_t> word_neuron(e->fired_words, 0u);
-            for (uint32_t c : e->all_soma_list)
-                for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += 32)
-                    word_neuron[e->h_cores[c].fired_word_begin + (k0 >> 5)] = tb->cores[c].neuron_begin + k0;
-            e->t.n_raster_words = e->fired_words;
-            if (e->upload(&e->t.raster_neuron, word_neuron.data(), word_neuron.size()) != 0) return -1;
-            e->n_all_segments = (e->t.n_expand_words * 32u + kSomaThreads - 1) / kSomaThreads;
-        }
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -1747,6 +1867,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->s.work, 1) != 0) return -1;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
+    if (e->alloc(&e->s.x.epoch, 1) != 0) return -1;
+    if (e->alloc(&e->s.x.error, 1) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
     if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -1899,6 +2021,8 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     if (e == nullptr) return;
     cudaSetDevice(e->device);
     if (e->stream != nullptr) cudaStreamSynchronize(e->stream);
+    for (void *&p : e->p2p_peer_base)
+        if (p != nullptr) cudaIpcCloseMemHandle(p);
     for (void *p : e->allocs) cudaFree(p);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
@@ -2283,6 +2407,90 @@ extern "C" int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fan
     return 0;
 }
 
+// ---- peer-memory exchange (CUDA IPC over NVLink) ------------------------------------------
+// One process per GPU: every rank exports its exchange block, the 64-byte handles travel
+// through the caller's control plane (torch.distributed / MPI), every rank opens the others.
+extern "C" int sfe_engine_p2p_export(sfe_engine *e, void *handle64)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    if (e->world > kMaxPeers)
+    {
+        sfe::set_last_error("the peer-memory exchange supports up to 8 ranks (one NVSwitch box)");
+        return -1;
+    }
+    if (e->p2p_block == nullptr)
+        if (e->alloc(&e->p2p_block, 2 * static_cast<size_t>(e->fired_words) + kMaxPeers) != 0) return -1;
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    cudaIpcMemHandle_t h;
+    SFE_CUDA(cudaIpcGetMemHandle(&h, e->p2p_block));
+    std::memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int sfe_engine_p2p_attach(sfe_engine *e, const void *handles)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->p2p_block == nullptr)
+    {
+        sfe::set_last_error("sfe_engine_p2p_attach: call sfe_engine_p2p_export first");
+        return -1;
+    }
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    for (uint32_t q = 0; q < e->world; ++q)
+    {
+        uint32_t *base = e->p2p_block;
+        if (q != e->rank)
+        {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const unsigned char *>(handles) + 64 * static_cast<size_t>(q), sizeof(h));
+            void *opened = nullptr;
+            SFE_CUDA(cudaIpcOpenMemHandle(&opened, h, cudaIpcMemLazyEnablePeerAccess));
+            e->p2p_peer_base[q] = opened;
+            base = static_cast<uint32_t *>(opened);
+        }
+        e->s.x.raster[q] = base;
+        e->s.x.flags[q] = base + 2 * static_cast<size_t>(e->fired_words);
+    }
+    e->s.x.n_peers = e->world;
+    e->s.x.rank = e->rank;
+    e->s.x.fired_words = e->fired_words;
+    e->s.x.slice_words = e->slice_words;
+    e->s.x.local_slice = e->d_fired_local;
+    e->s.x.acquire_mode = 1u;
+    if (const char *v = std::getenv("SFE_XCHG_ACQUIRE")) e->s.x.acquire_mode = static_cast<uint32_t>(std::atoi(v));
+    if (std::getenv("SFE_PHASE_PROFILE") != nullptr && e->s.x.stamps == nullptr)
+        if (e->alloc(&e->s.x.stamps, 4096 * 4) != 0) return -1;
+    e->p2p_on = true;
+    return 0;
+}
+
+// Callers synchronise all ranks (host barrier) before detaching: a peer may still be storing.
+extern "C" int sfe_engine_p2p_detach(sfe_engine *e)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    for (uint32_t q = 0; q < kMaxPeers; ++q)
+        if (e->p2p_peer_base[q] != nullptr)
+        {
+            cudaIpcCloseMemHandle(e->p2p_peer_base[q]);
+            e->p2p_peer_base[q] = nullptr;
+        }
+    e->s.x.n_peers = 0;
+    e->p2p_on = false;
+    return 0;
+}
+
+// 0 = fine, 1 = a peer failed to arrive within the in-kernel time limit (results invalid)
+extern "C" int sfe_engine_exchange_error(sfe_engine *e)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    uint32_t v = 0;
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    SFE_CUDA(cudaMemcpy(&v, e->s.x.error, sizeof(v), cudaMemcpyDeviceToHost));
+    return static_cast<int>(v);
+}
+
 // ---- multi-GPU: one engine per rank, spikes exchanged as a fired-bit raster ---------------
 // step = enqueue_neuron_phase -> all-gather(local slice -> global raster) -> enqueue_message_phase
 extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
@@ -2317,13 +2525,10 @@ static void prof_mark(sfe_engine *e)
 extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
 {
     SFE_CUDA(cudaSetDevice(e->device));
-    if (e->world > 1 && e->n_all_segments > 0)
-    {
-        expand_kernel<<<e->n_all_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
-        ++e->launches;
-    }
-    prof_mark(e);
-    if (!e->fanout_list.empty())
+    // with the peer-memory exchange every rank launches the message phase, work or not: its
+    // first CTA publishes this rank's raster slice and all ranks stay within one step of each
+    // other (which is what the double-buffered raster assumes)
+    if (!e->fanout_list.empty() || e->p2p_on)
     {
         launch_fanout(e);
         ++e->launches;
@@ -2581,9 +2786,9 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
 {
     SFE_CUDA(cudaSetDevice(e->device));
     NcclComm comm = comm_of(e);
-    if (e->world > 1 && comm == nullptr)
+    if (e->world > 1 && comm == nullptr && !e->p2p_on)
     {
-        sfe::set_last_error("sfe_engine_enqueue_partitioned: call sfe_engine_comm_init first");
+        sfe::set_last_error("sfe_engine_enqueue_partitioned: call sfe_engine_p2p_attach or sfe_engine_comm_init first");
         return -1;
     }
     if (e->total_timesteps - e->log_read + timesteps > e->log_cap)
@@ -2601,7 +2806,7 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
         prof_mark(e);
         if (sfe_engine_enqueue_neuron_phase(e) != 0) return -1;
         prof_mark(e);
-        if (e->world > 1)
+        if (e->world > 1 && !e->p2p_on)
         {
             const int rc = g_nccl.AllGather(e->d_fired_local, e->d_fired_global, e->slice_words, kNcclUint32, comm, e->stream);
             if (rc != 0)
@@ -2619,8 +2824,8 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
     if (prof_steps > 0)
     {
         SFE_CUDA(cudaStreamSynchronize(e->stream));
-        constexpr int kMarks = 6;
-        double acc[kMarks] = {0, 0, 0, 0, 0, 0};
+        constexpr int kMarks = 5;
+        double acc[kMarks] = {0, 0, 0, 0, 0};
         for (int64_t s = 0; s < prof_steps; ++s)
             for (int k = 0; k < kMarks; ++k)
             {
@@ -2631,9 +2836,26 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
                 acc[k] += ms;
             }
         const double d = 1e3 / static_cast<double>(prof_steps);
-        std::fprintf(stderr, "[sfe phase profile] rank %d: soma %.1f us, exchange %.1f us, expand %.1f us, fanout %.1f us, "
+        std::fprintf(stderr, "[sfe phase profile] rank %d: soma %.1f us, exchange %.1f us, fanout %.1f us, "
                 "finalize %.1f us, gap %.1f us (mean of %lld steps)\n",
-                e->rank, acc[0] * d, acc[1] * d, acc[2] * d, acc[3] * d, acc[4] * d, acc[5] * d, static_cast<long long>(prof_steps));
+                e->rank, acc[0] * d, acc[1] * d, acc[2] * d, acc[3] * d, acc[4] * d, static_cast<long long>(prof_steps));
+        if (e->p2p_on && e->s.x.stamps != nullptr)
+        {
+            std::vector<unsigned long long> st(4096 * 4);
+            cudaMemcpy(st.data(), e->s.x.stamps, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            double pub = 0.0, wait = 0.0;
+            int n = 0;
+            for (int k = 0; k < 4096; ++k)
+                if (st[4 * k + 2] > st[4 * k] && st[4 * k] != 0)
+                {
+                    pub += static_cast<double>(st[4 * k + 1] - st[4 * k]);
+                    wait += static_cast<double>(st[4 * k + 2] - st[4 * k + 1]);
+                    ++n;
+                }
+            if (n > 0)
+                std::fprintf(stderr, "[sfe phase profile] rank %d: inside fanout CTA 0: publish %.1f us, wait for peers %.1f us (%d steps)\n",
+                        e->rank, 1e-3 * pub / n, 1e-3 * wait / n, n);
+        }
         for (cudaEvent_t ev : g_prof_events) cudaEventDestroy(ev);
         g_prof_events.clear();
     }

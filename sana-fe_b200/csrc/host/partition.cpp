@@ -43,7 +43,8 @@ extern "C" int sfe_plan_partition(const sfe_tables *tb, uint32_t world, uint32_t
     // raster: one equal-sized slice per rank, every core starts on a word boundary
     std::vector<uint32_t> words(world, 0);
     for (uint32_t c = 0; c < tb->n_cores; ++c) words[own[c]] += (tb->cores[c].neuron_count + 31) / 32;
-    const uint32_t slice = std::max<uint32_t>(1, *std::max_element(words.begin(), words.end()));
+    // slices are multiples of 4 words: ranks push them to their peers with 16-byte stores
+    const uint32_t slice = (std::max<uint32_t>(1, *std::max_element(words.begin(), words.end())) + 3u) & ~3u;
     std::vector<uint32_t> fill(world, 0);
     for (uint32_t c = 0; c < tb->n_cores; ++c)
     {

@@ -158,6 +158,10 @@ def lib():
         "sfe_engine_comm_destroy": (C.c_int, [vp]),
         "sfe_engine_enqueue_partitioned": (C.c_int, [vp, i64]),
         "sfe_engine_raster_layout": (C.c_int, [vp, vp, sz]),
+        "sfe_engine_p2p_export": (C.c_int, [vp, vp]),
+        "sfe_engine_p2p_attach": (C.c_int, [vp, vp]),
+        "sfe_engine_p2p_detach": (C.c_int, [vp]),
+        "sfe_engine_exchange_error": (C.c_int, [vp]),
         "sfe_plan_partition": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
         "sfe_engine_synchronize": (C.c_int, [vp]),
         "sfe_device_memcpy": (C.c_int, [vp, vp, sz]),
