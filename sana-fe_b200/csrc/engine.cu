@@ -57,7 +57,7 @@ struct CoreDev
     uint32_t tile;
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
-    uint32_t pad0;
+    uint32_t q4;                      // synapses of this core also exist as 4-byte records (syn_q4)
     unsigned long long syn_begin;
     double scale, inv_scale;          // 2^shift, 2^-shift
     double lat_axon_in, e_axon_in, lat_axon_out, e_axon_out;
@@ -110,6 +110,11 @@ struct DevTables
     const sfe_axon_in *axons_in;
     const double *syn_w;
     const uint32_t *syn_meta;
+    // Lossless 4-byte synapse records of cores whose certificate allows it (PACKED32, no delay
+    // ring, <= 4096 neurons): bits 0..19 = weight * 2^shift as a 20-bit two's-complement integer
+    // (exact by the certificate), bits 20..31 = post-synaptic neuron. Same padded indexing as
+    // syn_w / syn_meta; a third of their bytes per synaptic event.
+    const uint32_t *syn_q4;
     const uint32_t *probes;
     uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
     double sync_delay;
@@ -178,6 +183,17 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p)
 __device__ __forceinline__ void st_relaxed_sys(uint32_t *p, const uint32_t v)
 {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Programmatic dependent launch: every kernel of the step lets its successor be scheduled right
+// away (its CTAs fill SM slots as they free up and run their table-only prologue) and waits for
+// its predecessor's completion + memory flush before touching anything a kernel writes.
+__device__ __forceinline__ void griddep_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -426,9 +442,8 @@ template <bool kExotic>
 __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
 {
     __shared__ sfe_soma_class class_cache[kClassCache];
+    griddep_launch_dependents();
     const SomaSegment core = t.soma_segments[blockIdx.x];
-    const long long steps_done = s.step[0];
-    const long long T = steps_done + 1;
     const int lane = threadIdx.x & 31;
     const bool classes_cached = t.n_soma_classes <= kClassCache;
     if (classes_cached)
@@ -438,6 +453,9 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_cache);
         for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
     }
+    griddep_wait(); // everything above reads load-time tables only
+    const long long steps_done = s.step[0];
+    const long long T = steps_done + 1;
 
     uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
     double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
@@ -447,14 +465,26 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         const uint32_t k = core.k0 + threadIdx.x;
         const bool valid = k < core.neuron_count;
         int st = SFE_STATUS_IDLE;
-        // every global load of the step is issued before the first use
-        uint32_t cid = 0u, a0 = 0u, a1 = 0u;
+        // Every global load of the step is issued before the first use, speculatively: which of
+        // them a neuron needs depends on its class, but waiting for the class first would put
+        // three dependent memory round trips where one suffices (the unused ones cost little:
+        // the neuron phase is latency-bound, not bandwidth-bound).
+        uint32_t cid = 0u, a0 = 0u, a1 = 0u, raw_sum = 0u, raw_cnt = 0u;
+        double v0 = 0.0, u0 = 0.0, bias0 = 0.0;
+        int refr0 = 0;
+        const uint32_t d = core.dend_base + slot * core.neuron_count + k;
         if (valid)
         {
             const uint32_t i = core.neuron_begin + k;
             cid = __ldg(t.neuron_class + i);
             a0 = __ldg(t.axon_out_begin + i);
             a1 = __ldg(t.axon_out_begin + i + 1);
+            v0 = s.v[i];
+            u0 = s.u[i];
+            bias0 = s.bias[i];
+            refr0 = s.refractory[i];
+            raw_sum = s.din32[d];
+            if (core.acc_mode != SFE_ACC_PACKED32) raw_cnt = s.dcnt32[d];
         }
         __syncthreads(); // class cache filled
         if (valid)
@@ -464,7 +494,6 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             // ---- dendrite output for this step ------------------------------
             bool has_in = false;
             double in = 0.0;
-            const uint32_t d = core.dend_base + slot * core.neuron_count + k;
             if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR)
             {
                 // buffer inside a plain accumulator: the charge is zeroed before it is
@@ -473,28 +502,27 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             }
             else if (core.acc_mode == SFE_ACC_PACKED32)
             {
-                const uint32_t raw = s.din32[d];
-                if (raw != 0u)
+                if (raw_sum != 0u)
                 {
-                    const int sum = (static_cast<int>(raw << 12)) >> 12; // sign-extend 20 bits
-                    has_in = true;                                       // count = (raw - sum) >> 20 > 0
+                    const int sum = (static_cast<int>(raw_sum << 12)) >> 12; // sign-extend 20 bits
+                    has_in = true;                                           // count = (raw - sum) >> 20 > 0
                     in = static_cast<double>(sum) * core.inv_scale;
                     s.din32[d] = 0u; // consumed (the message phase accumulates into zeroed slots)
                 }
             }
             else if (core.acc_mode == SFE_ACC_DUAL32)
             {
-                if (s.dcnt32[d] != 0u)
+                if (raw_cnt != 0u)
                 {
                     has_in = true;
-                    in = static_cast<double>(static_cast<int>(s.din32[d])) * core.inv_scale;
+                    in = static_cast<double>(static_cast<int>(raw_sum)) * core.inv_scale;
                     s.din32[d] = 0u;
                     s.dcnt32[d] = 0u;
                 }
             }
             else
             {
-                if (s.dcnt32[d] != 0u)
+                if (raw_cnt != 0u)
                 {
                     has_in = true;
                     in = s.din64[d];
@@ -512,11 +540,11 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 lat += c.dend_latency_update;
             }
             // ---- soma ---------------------------------------------------------
-            const double bias = s.bias[i];
+            const double bias = bias0;
             if (c.model == SFE_SOMA_LIF)
             {
-                double v = s.v[i], u = s.u[i];
-                int refr = s.refractory[i];
+                double v = v0, u = u0;
+                int refr = refr0;
                 st = lif_update(c, v, u, refr, bias, has_in, in, steps_done);
                 s.v[i] = v;
                 s.u[i] = u;
@@ -524,7 +552,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             }
             else if (c.model == SFE_SOMA_TRUENORTH)
             {
-                double v = s.v[i];
+                double v = v0;
                 st = truenorth_update(c, v, bias, has_in, in);
                 s.v[i] = v;
             }
@@ -776,7 +804,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     __shared__ uint32_t scan_w[kFanoutWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long T = s.step[0] + 1;
+    griddep_launch_dependents();
     const bool costs_cached = t.n_cost_classes <= kCostCache;
     if (costs_cached)
         for (uint32_t x = threadIdx.x; x < t.n_cost_classes; x += kFanoutThreads) cost_cache[x] = t.costs[x];
@@ -791,6 +819,8 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     }
     uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
     (void) tma_phase;
+    griddep_wait(); // everything above reads load-time tables / initialises shared memory only
+    const long long T = s.step[0] + 1;
 
     // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory
     // exchange the collective is fused into this kernel: CTA 0 pushes this rank's raster slice
@@ -933,7 +963,66 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
             cur.count = n_list;
             cur.stride = kFanoutWarps;
             cur.ent = list[warp];
-            if constexpr (V == kStreamTma)
+            if (core.q4 != 0u)
+            {
+                // 4-byte records: no staging. Lane l takes synapses l, l+32, l+64, l+96 of a
+                // 128-synapse chunk (coalesced 128-byte loads, bank-friendly posts); the loads of
+                // the next group of entries are in flight while this group is accumulated.
+                constexpr int kGroup = 4; // list entries per warp and round
+                const uint32_t *__restrict__ q_base = t.syn_q4 + core.syn_begin;
+                uint2 ent[kGroup], ent_n[kGroup];
+                uint32_t q[kGroup][4], q_n[kGroup][4];
+                auto fetch = [&](const uint32_t e0, uint2 (&en)[kGroup], uint32_t (&qq)[kGroup][4]) {
+#pragma unroll
+                    for (int g = 0; g < kGroup; ++g)
+                    {
+                        const uint32_t e = e0 + g * kFanoutWarps;
+                        en[g] = e < n_list ? list[e] : make_uint2(0u, 0u);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const uint32_t j = lane + 32u * u;
+                            qq[g][u] = j < en[g].y ? __ldg(q_base + en[g].x + j) : 0u;
+                        }
+                    }
+                };
+                fetch(warp, ent, q);
+                for (uint32_t e0 = warp; e0 < n_list; e0 += kGroup * kFanoutWarps)
+                {
+                    fetch(e0 + kGroup * kFanoutWarps, ent_n, q_n); // beyond the list: no loads
+#pragma unroll
+                    for (int g = 0; g < kGroup; ++g)
+                    {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (lane + 32u * u < ent[g].y)
+                                atomicAdd(&acc32[q[g][u] >> 20], 0x100000u + static_cast<uint32_t>(static_cast<int>(q[g][u] << 12) >> 12));
+                        // segments longer than one chunk (rare): the rest, unpipelined
+                        for (uint32_t j0 = 128u; j0 < ent[g].y; j0 += 128u)
+                        {
+                            uint32_t r[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const uint32_t j = j0 + lane + 32u * u;
+                                r[u] = j < ent[g].y ? __ldg(q_base + ent[g].x + j) : 0u;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (j0 + lane + 32u * u < ent[g].y)
+                                    atomicAdd(&acc32[r[u] >> 20], 0x100000u + static_cast<uint32_t>(static_cast<int>(r[u] << 12) >> 12));
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < kGroup; ++g)
+                    {
+                        ent[g] = ent_n[g];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) q[g][u] = q_n[g][u];
+                    }
+                }
+            }
+            else if constexpr (V == kStreamTma)
             {
                 unsigned char *stage0 = tma_base + warp * kTmaStages * kTmaStageBytes;
                 const uint32_t bar0 = smem_addr(tma_bars + warp * kTmaStages);
@@ -1238,6 +1327,8 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
 {
     __shared__ StepPartial warp_part[kFinalThreads / 32];
     __shared__ uint32_t ticket_s;
+    griddep_launch_dependents();
+    griddep_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const uint32_t a = blockIdx.x * (kFinalThreads / 32) + warp;
@@ -1442,6 +1533,26 @@ __global__ void __launch_bounds__(256) certify_kernel(
     }
 }
 
+// 4-byte records of the certified cores (one CTA column per core, warps stride over its axons)
+__global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, const uint32_t *core_list, const sfe_axon_in *axons,
+        const double *syn_w, const uint32_t *syn_meta, uint32_t *syn_q4)
+{
+    const CoreDev &core = cores[core_list[blockIdx.y]];
+    if (core.q4 == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t a = warp; a < core.axon_count; a += nwarps)
+    {
+        const sfe_axon_in ax = axons[core.axon_begin + a];
+        for (uint32_t j = lane; j < ax.syn_count; j += 32)
+        {
+            const size_t at = core.syn_begin + ax.syn_off + j;
+            const int fixed = __double2int_rn(syn_w[at] * core.scale);
+            syn_q4[at] = (static_cast<uint32_t>(fixed) & 0xFFFFFu) | (SFE_SYN_POST(syn_meta[at]) << 20);
+        }
+    }
+}
+
 } // namespace
 
 // ===========================================================================
@@ -1464,6 +1575,7 @@ struct sfe_engine
     uint32_t *p2p_block{nullptr};        // [2][fired_words] raster + [kMaxPeers] flags, exported over CUDA IPC
     void *p2p_peer_base[kMaxPeers] = {}; // opened peer blocks (own entry stays null)
     bool p2p_on{false};
+    bool q4_any{false};
     int device{0};
     cudaStream_t stream{nullptr};
     bool own_stream{false};
@@ -1809,6 +1921,31 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         }
     }
 
+    // ---- compact 4-byte synapse records for the cores whose certificate allows them -------
+    {
+        const char *env = std::getenv("SFE_SYN_Q4");
+        const bool want = env == nullptr || std::atoi(env) != 0;
+        bool any = false;
+        for (uint32_t c : e->fanout_list)
+        {
+            CoreDev &d = e->h_cores[c];
+            d.q4 = (want && d.acc_mode == SFE_ACC_PACKED32 && d.ring == 1 && d.neuron_count <= 4096 && d.dend_in_msg != 0) ? 1u : 0u;
+            any = any || d.q4 != 0u;
+        }
+        e->q4_any = any;
+        if (any)
+        {
+            uint32_t *d_q = nullptr;
+            if (e->alloc(&d_q, padded_total) != 0) return -1;
+            e->t.syn_q4 = d_q;
+            SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
+            pack_q4_kernel<<<dim3(16, static_cast<unsigned>(e->fanout_list.size())), 256, 0, e->stream>>>(
+                    e->d_cores, e->t.fanout_core_list, e->t.axons_in, d_w, d_m, d_q);
+            SFE_CUDA(cudaGetLastError());
+            SFE_CUDA(cudaStreamSynchronize(e->stream));
+        }
+    }
+
     // ---- neuron-phase segments (after certification: they carry the accumulation mode)
     {
         std::vector<SomaSegment> segs;
@@ -2041,19 +2178,47 @@ extern "C" int sfe_engine_set_stream(sfe_engine *e, void *stream)
     return 0;
 }
 
+// Kernels of the step are launched with programmatic stream serialisation (SFE_PDL=0 turns it
+// off): the launch latency and the table-only prologue of a kernel overlap the tail of the
+// kernel before it; griddepcontrol.wait inside the kernel keeps the data dependencies.
+template <typename... KArgs, typename... Args>
+static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, Args... args)
+{
+    static const bool pdl = [] {
+        const char *v = std::getenv("SFE_PDL");
+        return v == nullptr || std::atoi(v) != 0;
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static void launch_soma(sfe_engine *e)
 {
-    if (e->exotic) soma_kernel<true><<<e->n_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
-    else soma_kernel<false><<<e->n_segments, kSomaThreads, 0, e->stream>>>(e->t, e->s);
+    if (e->exotic) launch_step_kernel(e, soma_kernel<true>, e->n_segments, kSomaThreads, 0, e->t, e->s);
+    else launch_step_kernel(e, soma_kernel<false>, e->n_segments, kSomaThreads, 0, e->t, e->s);
 }
 
 static void launch_fanout(sfe_engine *e)
 {
     const unsigned grid = e->fanout_grid;
     if (e->fanout_variant == kStreamTma)
-        fanout_kernel<kStreamTma><<<grid, kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s, e->tma_off);
+        launch_step_kernel(e, fanout_kernel<kStreamTma>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
     else
-        fanout_kernel<kStreamScalar><<<grid, kFanoutThreads, e->fanout_smem, e->stream>>>(e->t, e->s, e->tma_off);
+        launch_step_kernel(e, fanout_kernel<kStreamScalar>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+}
+
+static void launch_finalize(sfe_engine *e)
+{
+    launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
 }
 
 static int enqueue_step(sfe_engine *e, bool probes)
@@ -2089,7 +2254,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
             e->ev_used += 2;
         }
     }
-    finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+    launch_finalize(e);
     ++e->launches;
     ++e->total_timesteps;
     return 0;
@@ -2220,7 +2385,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 launch_fanout(e);
                 ++e->launches;
             }
-            finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+            launch_finalize(e);
             ++e->launches;
             ++e->total_timesteps;
         }
@@ -2534,7 +2699,7 @@ extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
         ++e->launches;
     }
     prof_mark(e);
-    finalize_kernel<<<e->final_grid, kFinalThreads, 0, e->stream>>>(e->t, e->s);
+    launch_finalize(e);
     ++e->launches;
     ++e->total_timesteps;
     SFE_CUDA(cudaGetLastError());
