@@ -111,8 +111,8 @@ struct DevTables
     const double *syn_w;
     const uint32_t *syn_meta;
     // Lossless 4-byte synapse records of cores whose certificate allows it (PACKED32, no delay
-    // ring, <= 4096 neurons): bits 0..19 = weight * 2^shift as a 20-bit two's-complement integer
-    // (exact by the certificate), bits 20..31 = post-synaptic neuron. Same padded indexing as
+    // ring, <= 4096 neurons): bits 12..31 = weight * 2^shift as a 20-bit two's-complement integer
+    // (exact by the certificate), bits 0..11 = post-synaptic neuron. Same padded indexing as
     // syn_w / syn_meta; a third of their bytes per synaptic event.
     const uint32_t *syn_q4;
     const uint32_t *probes;
@@ -789,12 +789,17 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 //   kStreamTma     each warp owns a ring of kTmaStages shared-memory stages filled by
 //                  cp.async.bulk (TMA) with mbarrier completion: lane 0 issues two bulk
 //                  copies per chunk (weights, meta), the warp consumes from shared memory
-constexpr int kStreamScalar = 0, kStreamTma = 2;
+//   kStreamQ4      engines whose cores ALL carry 4-byte records: the register-pipelined q4
+//                  stream only (it is also a branch of the other two for mixed engines)
+constexpr int kStreamScalar = 0, kStreamTma = 2, kStreamQ4 = 3;
+constexpr int kQ4CtasPerSm = 4;
+constexpr int kQ4Stages = 8;        // per-warp ring of 512-byte chunks filled by cp.async (4-byte records)
+constexpr int kQ4StageBytes = 512;  // 128 records
 constexpr int kTmaStages = 4;
 constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
 
 template <int V>
-__global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
+__global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double part_d[kFanoutWarps][3];
@@ -811,7 +816,10 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     const sfe_cost_class *cost_table = costs_cached ? cost_cache : t.costs;
     unsigned char *tma_base = smem_raw + tma_off;
     unsigned long long *tma_bars = reinterpret_cast<unsigned long long *>(tma_base + kFanoutWarps * kTmaStages * kTmaStageBytes);
-    const uint32_t list_off = tma_off + (V == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8) : 0);
+    // staging area at tma_off: the TMA stages + mbarriers (kStreamTma; a warp's 4-byte-record ring
+    // reuses its stages), or the cp.async rings alone when the engine has 4-byte records
+    const uint32_t list_off = tma_off + (V == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8)
+                                                          : (t.syn_q4 != nullptr ? kFanoutWarps * kQ4Stages * kQ4StageBytes : 0));
     if constexpr (V == kStreamTma)
     {
         if (threadIdx.x < kFanoutWarps * kTmaStages) mbar_init(smem_addr(tma_bars + threadIdx.x), 1u);
@@ -852,6 +860,10 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     const FanItem item = t.fan_items[item_id];
     const uint32_t ci = item.core;
     const CoreDev core = t.cores[ci];
+    // kStreamQ4 instantiation: every core of the engine is certified for 4-byte records, the
+    // other accumulation modes and streaming variants are compiled out (fewer registers)
+    const uint32_t acc_mode = V == kStreamQ4 ? static_cast<uint32_t>(SFE_ACC_PACKED32) : core.acc_mode;
+    const bool is_q4 = V == kStreamQ4 || core.q4 != 0u;
     const uint32_t P = core.neuron_count;
     const uint32_t cells = P * core.ring;
     // does accumulated charge survive? (not for a plain accumulator with the buffer
@@ -861,13 +873,13 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     uint32_t *acc32 = reinterpret_cast<uint32_t *>(smem_raw);          // PACKED32 / DUAL32 sum
     uint32_t *cnt32 = acc32 + cells;                                   // DUAL32 count / ORDERED has
     double *acc64 = reinterpret_cast<double *>(smem_raw);              // ORDERED (cnt32 placed after)
-    if (core.acc_mode == SFE_ACC_ORDERED) cnt32 = reinterpret_cast<uint32_t *>(acc64 + cells);
+    if (acc_mode == SFE_ACC_ORDERED) cnt32 = reinterpret_cast<uint32_t *>(acc64 + cells);
 
     if (accumulate)
     {
-        if (core.acc_mode == SFE_ACC_PACKED32)
+        if (acc_mode == SFE_ACC_PACKED32)
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads) acc32[x] = 0u;
-        else if (core.acc_mode == SFE_ACC_DUAL32)
+        else if (acc_mode == SFE_ACC_DUAL32)
             for (uint32_t x = threadIdx.x; x < 2 * cells; x += kFanoutThreads) acc32[x] = 0u;
         else
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
@@ -884,9 +896,9 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
     const uint32_t n_words = item.word_hi; // this item's slice of the core's inbox: [word_lo, word_hi)
     const double *__restrict__ w_base = t.syn_w + core.syn_begin;
     const uint32_t *__restrict__ m_base = t.syn_meta + core.syn_begin;
-    const uint32_t ring = core.ring;
+    const uint32_t ring = V == kStreamQ4 ? 1u : core.ring;
 
-    if (core.acc_mode != SFE_ACC_ORDERED)
+    if (acc_mode != SFE_ACC_ORDERED)
     {
         // Exact fixed-point accumulation: any order gives the reference's sums bit for
         // bit (load-time certificate). Per round (normally one per core):
@@ -896,7 +908,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         //           loads (one global latency for the whole core), accounted, and the
         //           list is rewritten as (segment offset, synapse count)
         //   stream  warp w takes entries w, w+8, ... and streams their CSR segments
-        const bool packed = core.acc_mode == SFE_ACC_PACKED32;
+        const bool packed = acc_mode == SFE_ACC_PACKED32;
         uint2 *list = reinterpret_cast<uint2 *>(smem_raw + list_off);
         for (uint32_t wb = item.word_lo; wb < n_words;)
         {
@@ -963,64 +975,95 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
             cur.count = n_list;
             cur.stride = kFanoutWarps;
             cur.ent = list[warp];
-            if (core.q4 != 0u)
+            if (is_q4)
             {
-                // 4-byte records: no staging. Lane l takes synapses l, l+32, l+64, l+96 of a
-                // 128-synapse chunk (coalesced 128-byte loads, bank-friendly posts); the loads of
-                // the next group of entries are in flight while this group is accumulated.
-                constexpr int kGroup = 4; // list entries per warp and round
+                // 4-byte records. Each warp owns a ring of kQ4Stages 512-byte chunks in shared memory
+                // filled by cp.async: lane l moves the l-th 16 bytes of a chunk and, thanks to the
+                // lane-major layout of the table (q4_position), those are the four records it
+                // accumulates - it waits for its own copies only (no warp barrier), reads them back
+                // with one 16-byte load and adds each with one red.shared on a 32-bit shared
+                // address. Nothing is held in registers while in flight: seven chunks per warp are
+                // always on their way.
                 const uint32_t *__restrict__ q_base = t.syn_q4 + core.syn_begin;
-                uint2 ent[kGroup], ent_n[kGroup];
-                uint32_t q[kGroup][4], q_n[kGroup][4];
-                auto fetch = [&](const uint32_t e0, uint2 (&en)[kGroup], uint32_t (&qq)[kGroup][4]) {
-#pragma unroll
-                    for (int g = 0; g < kGroup; ++g)
-                    {
-                        const uint32_t e = e0 + g * kFanoutWarps;
-                        en[g] = e < n_list ? list[e] : make_uint2(0u, 0u);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                        {
-                            const uint32_t j = lane + 32u * u;
-                            qq[g][u] = j < en[g].y ? __ldg(q_base + en[g].x + j) : 0u;
-                        }
-                    }
+                uint32_t acc_s = smem_addr(acc32), ring_s = smem_addr(
+                        tma_base + warp * (V == kStreamTma ? kTmaStages * kTmaStageBytes : kQ4Stages * kQ4StageBytes) + 16 * lane);
+                // opaque copies: keeps the two shared-window addresses in registers (the compiler
+                // otherwise re-derives them from the generic pointer before every access)
+                asm volatile("mov.u32 %0, %0;" : "+r"(acc_s));
+                asm volatile("mov.u32 %0, %0;" : "+r"(ring_s));
+                auto add_q4 = [&](const uint32_t qv) {
+                    uint32_t addr;
+                    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(qv & 0xFFFu), "r"(acc_s));
+                    const uint32_t val = 0x100000u + static_cast<uint32_t>(static_cast<int>(qv) >> 12);
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
                 };
-                fetch(warp, ent, q);
-                for (uint32_t e0 = warp; e0 < n_list; e0 += kGroup * kFanoutWarps)
-                {
-                    fetch(e0 + kGroup * kFanoutWarps, ent_n, q_n); // beyond the list: no loads
-#pragma unroll
-                    for (int g = 0; g < kGroup; ++g)
+                auto issue = [&](const int st) -> uint32_t {
+                    uint32_t rem = 0u;
+                    if (cur.e < cur.count)
                     {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (lane + 32u * u < ent[g].y)
-                                atomicAdd(&acc32[q[g][u] >> 20], 0x100000u + static_cast<uint32_t>(static_cast<int>(q[g][u] << 12) >> 12));
-                        // segments longer than one chunk (rare): the rest, unpipelined
-                        for (uint32_t j0 = 128u; j0 < ent[g].y; j0 += 128u)
+                        rem = cur.ent.y - cur.j0;
+                        const uint32_t n4 = (min(rem, 128u) + 3u) & ~3u; // segments are padded to 4 records
+                        if (4u * lane < n4)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + st * kQ4StageBytes),
+                                         "l"(q_base + cur.ent.x + cur.j0 + 4u * lane)
+                                         : "memory");
+                        cur.j0 += 128u;
+                        if (cur.j0 >= cur.ent.y)
                         {
-                            uint32_t r[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                            {
-                                const uint32_t j = j0 + lane + 32u * u;
-                                r[u] = j < ent[g].y ? __ldg(q_base + ent[g].x + j) : 0u;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (j0 + lane + 32u * u < ent[g].y)
-                                    atomicAdd(&acc32[r[u] >> 20], 0x100000u + static_cast<uint32_t>(static_cast<int>(r[u] << 12) >> 12));
+                            cur.j0 = 0u;
+                            cur.e += cur.stride;
+                            if (cur.e < cur.count) cur.ent = list[cur.e];
                         }
                     }
+                    asm volatile("cp.async.commit_group;" ::: "memory"); // empty groups keep the count uniform
+                    return rem;
+                };
+                uint32_t rem_q[kQ4Stages];
 #pragma unroll
-                    for (int g = 0; g < kGroup; ++g)
+                for (int st = 0; st < kQ4Stages; ++st) rem_q[st] = issue(st);
+                bool done = false;
+                while (!done)
+                {
+#pragma unroll
+                    for (int st = 0; st < kQ4Stages; ++st)
                     {
-                        ent[g] = ent_n[g];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) q[g][u] = q_n[g][u];
+                        if (rem_q[st] == 0u)
+                        {
+                            done = true;
+                            break;
+                        }
+                        asm volatile("cp.async.wait_group %0;" ::"n"(kQ4Stages - 1) : "memory");
+                        const uint32_t n = min(rem_q[st], 128u), w = ((n + 3u) & ~3u) >> 2;
+                        if (lane < w)
+                        {
+                            uint4 rec;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w)
+                                         : "r"(ring_s + st * kQ4StageBytes)
+                                         : "memory");
+                            // up to 3 pad records close the chunk: with W >= 3 they all sit in the last quarter
+                            if (w >= 3u)
+                            {
+                                add_q4(rec.x);
+                                add_q4(rec.y);
+                                add_q4(rec.z);
+                                if (3u * w + lane < n) add_q4(rec.w);
+                            }
+                            else
+                            {
+                                if (lane < n) add_q4(rec.x);
+                                if (w + lane < n) add_q4(rec.y);
+                                if (2u * w + lane < n) add_q4(rec.z);
+                                if (3u * w + lane < n) add_q4(rec.w);
+                            }
+                        }
+                        rem_q[st] = issue(st); // the lane refills its own 16 bytes: no barrier needed
                     }
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            else if constexpr (V == kStreamQ4)
+            {
             }
             else if constexpr (V == kStreamTma)
             {
@@ -1122,7 +1165,7 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
             }
         }
     }
-    else if (warp == 0)
+    else if (V != kStreamQ4 && warp == 0)
     {
         // Ordered mode: one warp replays the messages in arrival order and adds
         // in synapse order, exactly like the reference's sequential loop.
@@ -1190,12 +1233,12 @@ __global__ void __launch_bounds__(kFanoutThreads) fanout_kernel(const DevTables 
         // Exact modes: several items (inbox slices) of one core may run on different CTAs,
         // and integer sums commute, so partial sums are merged with fire-and-forget global
         // atomics; the neuron phase zeroes a slot when it consumes it.
-        if (core.acc_mode == SFE_ACC_PACKED32)
+        if (acc_mode == SFE_ACC_PACKED32)
         {
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
                 if (acc32[x] != 0u) atomicAdd(&s.din32[base + x], acc32[x]);
         }
-        else if (core.acc_mode == SFE_ACC_DUAL32)
+        else if (acc_mode == SFE_ACC_DUAL32)
         {
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
                 if (cnt32[x] != 0u)
@@ -1533,6 +1576,18 @@ __global__ void __launch_bounds__(256) certify_kernel(
     }
 }
 
+// Where record j of a segment of `count` records sits in the 4-byte table. A segment is cut into
+// chunks of 128 records; a chunk of n records (n4 = n rounded up to 4) is stored lane-major:
+// with W = n4 / 4, record u*W + l of the chunk is at position 4*l + u. The lane that moves the
+// l-th 16-byte piece of the chunk into shared memory then owns four records whose indices are W
+// apart: it reads them back with one 16-byte load, needs no warp barrier, and for a fixed u the
+// lanes touch consecutive records (bank-friendly for strided post-synaptic indices).
+__host__ __device__ __forceinline__ uint32_t q4_position(const uint32_t j, const uint32_t count)
+{
+    const uint32_t chunk = j & ~127u, n = min(count - chunk, 128u), w = ((n + 3u) & ~3u) >> 2, r = j - chunk;
+    return chunk + 4u * (r % w) + r / w;
+}
+
 // 4-byte records of the certified cores (one CTA column per core, warps stride over its axons)
 __global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, const uint32_t *core_list, const sfe_axon_in *axons,
         const double *syn_w, const uint32_t *syn_meta, uint32_t *syn_q4)
@@ -1548,7 +1603,10 @@ __global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, cons
         {
             const size_t at = core.syn_begin + ax.syn_off + j;
             const int fixed = __double2int_rn(syn_w[at] * core.scale);
-            syn_q4[at] = (static_cast<uint32_t>(fixed) & 0xFFFFFu) | (SFE_SYN_POST(syn_meta[at]) << 20);
+            // lane-major inside every 128-record chunk: the lane that copies 16 bytes of a chunk
+            // owns records l, l+W, l+2W, l+3W of it (W = quarter width), see q4_position
+            syn_q4[core.syn_begin + ax.syn_off + q4_position(j, ax.syn_count)] =
+                    (static_cast<uint32_t>(fixed) << 12) | (SFE_SYN_POST(syn_meta[at]) & 0xFFFu);
         }
     }
 }
@@ -2030,8 +2088,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             return -1;
         }
     }
+    {
+        // every core certified for 4-byte records: the q4-only instantiation (unless a variant was forced)
+        bool all_q4 = !e->fanout_list.empty();
+        for (uint32_t c : e->fanout_list) all_q4 = all_q4 && e->h_cores[c].q4 != 0u;
+        if (all_q4 && std::getenv("SFE_FANOUT") == nullptr) e->fanout_variant = kStreamQ4;
+    }
     e->tma_off = static_cast<uint32_t>((smem_max + 127) & ~static_cast<size_t>(127));
-    smem_max = e->tma_off + (e->fanout_variant == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8) : 0) +
+    smem_max = e->tma_off +
+            (e->fanout_variant == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8)
+                                             : (e->q4_any ? kFanoutWarps * kQ4Stages * kQ4StageBytes : 0)) +
             kListCap * sizeof(uint2);
     e->fanout_smem = smem_max;
     if (smem_max > 200 * 1024)
@@ -2041,9 +2107,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     }
     SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
     SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
     {
         int per_sm = 1, sms = 1;
-        if (e->fanout_variant == kStreamTma)
+        if (e->fanout_variant == kStreamQ4)
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamQ4>, kFanoutThreads, smem_max));
+        else if (e->fanout_variant == kStreamTma)
             SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamTma>, kFanoutThreads, smem_max));
         else
             SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar>, kFanoutThreads, smem_max));
@@ -2062,9 +2131,10 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         if (!e->fanout_list.empty())
         {
             double syn = 0.0;
-            for (uint32_t c : e->fanout_list) syn += static_cast<double>(tb->cores[c].syn_count);
+            for (uint32_t c : e->fanout_list)
+                syn += static_cast<double>(tb->cores[c].syn_count) * (e->h_cores[c].q4 != 0u ? 4.0 : 12.0); // bytes per record
             const double n_cores_f = static_cast<double>(e->fanout_list.size());
-            const double core_bytes = 12.0 * 0.1 * syn / n_cores_f; // nominal 10 % activity
+            const double core_bytes = 0.1 * syn / n_cores_f; // nominal 10 % activity
             const double fixed_us = 5.0, hbm_bytes_per_us = 6.5e6, cta_bytes_per_us = 3.0e4;
             double best = 0.0;
             for (size_t cand = 1; cand <= 16; ++cand)
@@ -2210,7 +2280,9 @@ static void launch_soma(sfe_engine *e)
 static void launch_fanout(sfe_engine *e)
 {
     const unsigned grid = e->fanout_grid;
-    if (e->fanout_variant == kStreamTma)
+    if (e->fanout_variant == kStreamQ4)
+        launch_step_kernel(e, fanout_kernel<kStreamQ4>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    else if (e->fanout_variant == kStreamTma)
         launch_step_kernel(e, fanout_kernel<kStreamTma>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
     else
         launch_step_kernel(e, fanout_kernel<kStreamScalar>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
