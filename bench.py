@@ -219,9 +219,11 @@ def main():
     sampler.start()
     launches0 = L.sfe_engine_launch_count(eng)
     ms_total, ms_fan = C.c_float(), C.c_float()
+    # timed region: K steps back to back, CUDA events on the engine's stream at both ends only
+    assert L.sfe_engine_time_launches(eng, 0) == 0
     assert L.sfe_engine_time_begin(eng) == 0
     assert L.sfe_engine_enqueue(eng, args.steps) == 0, L.sfe_last_error()
-    assert L.sfe_engine_time_end(eng, C.byref(ms_total), C.byref(ms_fan)) == 0, L.sfe_last_error()
+    assert L.sfe_engine_time_end(eng, C.byref(ms_total), None) == 0, L.sfe_last_error()
     launches = L.sfe_engine_launch_count(eng) - launches0
     clocks = sampler.stop()
     assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
@@ -229,42 +231,79 @@ def main():
     seconds = ms_total.value / 1e3
     value = events / seconds
 
-    # ---- roofline of the dominant kernel (message phase) -----------------------------
-    fan_bytes = 12.0 * events + 16.0 * messages          # over args.steps launches
+    # ---- roofline of the dominant kernel (message phase): a second pass of K steps with CUDA
+    # events around every fanout_kernel launch (live, same process, same stream)
+    rd2 = sfe.RunData()
+    ms_total2 = C.c_float()
+    assert L.sfe_engine_time_launches(eng, 1) == 0
+    assert L.sfe_engine_time_begin(eng) == 0
+    assert L.sfe_engine_enqueue(eng, args.steps) == 0, L.sfe_last_error()
+    assert L.sfe_engine_time_end(eng, C.byref(ms_total2), C.byref(ms_fan)) == 0, L.sfe_last_error()
+    assert L.sfe_engine_collect(eng, C.byref(rd2)) == 0, L.sfe_last_error()
+    # canonical algorithmic bytes = 12 B per synaptic event (fp64 weight + post index)
+    # + 16 B per message. The engine stores certified cores' synapses as lossless 4-byte records,
+    # so the canonical figure can exceed the peak; `moved` is what the kernel really pulls from HBM.
+    fan_bytes = 12.0 * rd2.spikes + 16.0 * rd2.packets_sent          # over args.steps launches
+    record_bytes = 4.0 if os.environ.get("SFE_SYN_Q4", "1") != "0" else 12.0
+    layout_bytes = record_bytes * rd2.spikes + 16.0 * rd2.packets_sent
     fan_s = ms_fan.value / 1e3
     achieved = fan_bytes / fan_s / 1e9 if fan_s > 0 else 0.0
-    step_bytes = fan_bytes + 48.0 * n * args.steps
+    step_bytes = 12.0 * events + 16.0 * messages + 48.0 * n * args.steps
+    traffic = ncu_traffic() if args.cores == FULL["cores"] else None
     roofline = {"bound": "hbm", "kernel": "fanout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic() if args.cores == FULL["cores"] else None,
+                "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "profiles/r1_ncu_full_summary.json (ncu --set full, bytes per launch)",
                 "peak_source": peak_src,
                 "kernel_ms_per_launch": ms_fan.value / max(args.steps, 1),
-                "kernel_share_of_step": ms_fan.value / ms_total.value if ms_total.value > 0 else None,
+                "kernel_share_of_step": ms_fan.value / ms_total2.value if ms_total2.value > 0 else None,
                 "algorithmic_bytes_per_launch": fan_bytes / max(args.steps, 1),
+                "note": "canonical bytes (12 B/event, SURVEY 8d) over the kernel time; the engine reads lossless "
+                        f"{int(record_bytes)}-byte synapse records, see `moved`",
+                "moved": {"bytes_per_launch_layout": layout_bytes / max(args.steps, 1),
+                          "achieved": layout_bytes / fan_s / 1e9 if fan_s > 0 else None,
+                          "frac": layout_bytes / fan_s / 1e9 / peak if fan_s > 0 else None,
+                          "ncu_dram_frac": (traffic / (fan_s / max(args.steps, 1)) / 1e9 / peak) if (traffic and fan_s > 0) else None},
                 "whole_step": {"achieved": step_bytes / (ms_total.value / 1e3) / 1e9,
                                "frac": step_bytes / (ms_total.value / 1e3) / 1e9 / peak,
                                "bytes_per_step": step_bytes / max(args.steps, 1)}}
 
-    # ---- end to end through the public API with host buffers ---------------------------
-    # per step: bias vector host->device from pinned memory, one timestep, spike raster +
-    # step record device->host
-    bias_ptr = L.sfe_host_alloc(8 * n)
-    bias = np.ctypeslib.as_array(C.cast(bias_ptr, C.POINTER(C.c_double)), shape=(n,))
-    bias[:] = np.ctypeslib.as_array(tb.neuron_bias, shape=(n,))
+    # ---- end to end through the public C-ABI with HOST buffers ---------------------------
+    # per step: the step's bias vector host->device from pinned memory (8 B per neuron), one
+    # timestep, the spike raster + the step record device->host. The upload of step t+1's inputs
+    # is issued before step t's results are awaited (set_bias is double-buffered), the way a
+    # streaming caller would use the API.
+    bias_ptr = [L.sfe_host_alloc(8 * n) for _ in range(2)]
+    for ptr in bias_ptr:
+        np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))[:] = np.ctypeslib.as_array(tb.neuron_bias, shape=(n,))
     e2e_steps = max(10, min(args.steps, 100))
-    words = (n + 31) // 32
-    e2e_events = 0
-    for s in range(3):
-        chip.sim_raw(1, "simple", steps=True, fired=True)
+    nb = C.c_size_t()
+    L.sfe_engine_fired_global_ptr(eng, C.byref(nb))
+    words = nb.value // 4
+    raster_ptr = L.sfe_host_alloc(4 * words)
+    rde = sfe.RunData()
+
+    def e2e_loop(count):
+        total = 0
+        assert L.sfe_engine_set_bias(eng, bias_ptr[0], n) == 0
+        for s in range(count):
+            assert L.sfe_engine_enqueue(eng, 1) == 0, L.sfe_last_error()
+            assert L.sfe_engine_set_bias(eng, bias_ptr[(s + 1) & 1], n) == 0      # inputs of the next step
+            assert L.sfe_engine_read_raster(eng, raster_ptr, words) == 0, L.sfe_last_error()  # results of this step
+            assert L.sfe_engine_collect(eng, C.byref(rde)) == 0
+            total += rde.spikes
+        return total
+
+    e2e_loop(3)
     t_e2e = time.perf_counter()
-    for s in range(e2e_steps):
-        assert L.sfe_engine_set_bias(eng, bias_ptr, n) == 0
-        rde, tr = chip.sim_raw(1, "simple", steps=True, fired=True)
-        e2e_events += rde.spikes
+    e2e_events = e2e_loop(e2e_steps)
+    L.sfe_engine_synchronize(eng)
     e2e_s = time.perf_counter() - t_e2e
-    L.sfe_host_free(bias_ptr)
+    for ptr in bias_ptr:
+        L.sfe_host_free(ptr)
+    L.sfe_host_free(raster_ptr)
     e2e = {"value": e2e_events / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * words + 88,
-           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps}
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "note": "C-ABI calls with pinned host buffers; step t+1's bias upload overlaps step t (double-buffered set_bias)"}
 
     cpu = None if args.no_cpu_baseline else run_reference_sample(20, 1)
     line = {

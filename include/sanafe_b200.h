@@ -268,15 +268,24 @@ int sfe_engine_collect(sfe_engine *e, sfe_run_data *out);
 /* reset(): zero model state, keep the timestep counter (src/chip.cpp:576-600) */
 int sfe_engine_reset(sfe_engine *e);
 /* Per-neuron bias patch from HOST memory (MappedNeuron.set_attributes fast path,
- * src/pymodule.cpp:1176-1181); bias has n_neurons entries in device-index order. */
+ * src/pymodule.cpp:1176-1181); bias has n_neurons entries in device-index order.
+ * sfe_engine_set_bias is asynchronous and double-buffered: the vector is copied on a separate
+ * stream into the inactive device buffer (overlapping the steps already enqueued) and takes
+ * effect with the next step that is enqueued; keep the host buffer unchanged until then. */
 int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n);
 int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias);
 int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n);
 int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words);
+/* the last step's raster in the device's padded layout (world * slice words; every core starts on
+ * a word boundary, see sfe_engine_raster_layout): one device->host copy, nothing repacked */
+int sfe_engine_read_raster(sfe_engine *e, uint32_t *words, size_t n_words);
 int64_t sfe_engine_total_timesteps(const sfe_engine *e);
 /* kernel launches issued so far (for bench.py's gpu_launches) */
 int64_t sfe_engine_launch_count(const sfe_engine *e);
 /* device time (ms) of the steps enqueued between the last two timing marks */
+/* whether time_begin/time_end also bracket every message-phase launch with events (default 1);
+ * 0 for throughput runs: an event between two kernels defeats programmatic dependent launch */
+int sfe_engine_time_launches(sfe_engine *e, int on);
 int sfe_engine_time_begin(sfe_engine *e);
 int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fanout);
 /* ---- multi-GPU: the chip's cores are partitioned into `world` contiguous ranges (balanced by

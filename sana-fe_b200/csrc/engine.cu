@@ -1678,6 +1678,13 @@ struct sfe_engine
     cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
     // per-launch timing of the message-phase kernel between time_begin/time_end
     bool timing{false};
+    bool time_launches{true};
+    // whole-vector bias uploads are double-buffered and travel on their own stream, so that the
+    // upload for the next step overlaps the kernels of the current one
+    double *bias_buf[2] = {nullptr, nullptr};
+    int bias_cur{0}, bias_pending{-1};
+    cudaStream_t copy_stream{nullptr};
+    cudaEvent_t bias_ready[2] = {nullptr, nullptr}, bias_free[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used{0};
     bool ordered_any{false}, dual_any{false};
@@ -2230,6 +2237,16 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     if (e->stream != nullptr) cudaStreamSynchronize(e->stream);
     for (void *&p : e->p2p_peer_base)
         if (p != nullptr) cudaIpcCloseMemHandle(p);
+    if (e->copy_stream != nullptr)
+    {
+        cudaStreamSynchronize(e->copy_stream);
+        cudaStreamDestroy(e->copy_stream);
+        for (int k = 0; k < 2; ++k)
+        {
+            cudaEventDestroy(e->bias_ready[k]);
+            cudaEventDestroy(e->bias_free[k]);
+        }
+    }
     for (void *p : e->allocs) cudaFree(p);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
@@ -2293,8 +2310,11 @@ static void launch_finalize(sfe_engine *e)
     launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
 }
 
+static int apply_pending_bias(sfe_engine *e);
+
 static int enqueue_step(sfe_engine *e, bool probes)
 {
+    if (apply_pending_bias(e) != 0) return -1;
     if (!e->soma_list.empty())
     {
         launch_soma(e);
@@ -2307,7 +2327,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
     }
     if (!e->fanout_list.empty())
     {
-        const bool timed = e->timing && e->ev_used + 2 <= 8192;
+        const bool timed = e->timing && e->time_launches && e->ev_used + 2 <= 8192;
         if (timed)
         {
             while (e->ev_pool.size() < e->ev_used + 2)
@@ -2432,6 +2452,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
         if (per_step > 0 && e->ensure_pinned(per_step * static_cast<size_t>(batch)) != 0) return -1;
         for (int64_t b = 0; b < batch; ++b)
         {
+            if (apply_pending_bias(e) != 0) return -1;
             if (!e->soma_list.empty())
             {
                 launch_soma(e);
@@ -2525,6 +2546,22 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
     return 0;
 }
 
+// The neuron phase of the next enqueued step switches to the most recently uploaded bias vector.
+static int apply_pending_bias(sfe_engine *e)
+{
+    if (e->bias_pending < 0) return 0;
+    const int nxt = e->bias_pending;
+    SFE_CUDA(cudaEventRecord(e->bias_free[e->bias_cur], e->stream)); // every step enqueued so far read the old buffer
+    SFE_CUDA(cudaStreamWaitEvent(e->stream, e->bias_ready[nxt], 0));
+    e->s.bias = e->bias_buf[nxt];
+    e->bias_cur = nxt;
+    e->bias_pending = -1;
+    return 0;
+}
+
+// Asynchronous: the vector is copied (from pinned memory: by DMA, overlapping the kernels of the
+// steps already enqueued) into the inactive one of two device buffers; it takes effect with the
+// next step that is enqueued. The host buffer must stay untouched until that step has run.
 extern "C" int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n)
 {
     SFE_CUDA(cudaSetDevice(e->device));
@@ -2533,7 +2570,24 @@ extern "C" int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n)
         sfe::set_last_error("sfe_engine_set_bias: expected one bias per neuron");
         return -1;
     }
-    SFE_CUDA(cudaMemcpyAsync(e->s.bias, bias, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    if (e->copy_stream == nullptr)
+    {
+        SFE_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        e->bias_buf[0] = e->s.bias;
+        if (e->alloc(&e->bias_buf[1], e->n_neurons) != 0) return -1;
+        SFE_CUDA(cudaStreamSynchronize(e->stream)); // alloc() clears on the engine's stream
+        for (int k = 0; k < 2; ++k)
+        {
+            SFE_CUDA(cudaEventCreateWithFlags(&e->bias_ready[k], cudaEventDisableTiming));
+            SFE_CUDA(cudaEventCreateWithFlags(&e->bias_free[k], cudaEventDisableTiming));
+        }
+        e->bias_cur = 0;
+    }
+    const int nxt = e->bias_pending >= 0 ? e->bias_pending : 1 - e->bias_cur; // a not yet adopted upload is overwritten
+    SFE_CUDA(cudaStreamWaitEvent(e->copy_stream, e->bias_free[nxt], 0)); // no-op until the event has been recorded
+    SFE_CUDA(cudaMemcpyAsync(e->bias_buf[nxt], bias, n * sizeof(double), cudaMemcpyHostToDevice, e->copy_stream));
+    SFE_CUDA(cudaEventRecord(e->bias_ready[nxt], e->copy_stream));
+    e->bias_pending = nxt;
     return 0;
 }
 
@@ -2545,6 +2599,7 @@ extern "C" int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double
         sfe::set_last_error("sfe_engine_set_neuron_bias: neuron out of range");
         return -1;
     }
+    if (apply_pending_bias(e) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias + neuron, &bias, sizeof(double), cudaMemcpyHostToDevice, e->stream));
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
@@ -2583,6 +2638,22 @@ extern "C" int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n)
     return 0;
 }
 
+// The last step's fired-bit raster as the device keeps it (every core starts on a word boundary,
+// sfe_engine_raster_layout gives each core's first word): one D2H copy, no host-side repacking.
+extern "C" int sfe_engine_read_raster(sfe_engine *e, uint32_t *words, size_t n_words)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n_words != e->fired_words)
+    {
+        sfe::set_last_error("sfe_engine_read_raster: expected " + std::to_string(e->fired_words) + " words");
+        return -1;
+    }
+    const uint32_t *src = e->world > 1 ? e->d_fired_global : e->d_fired_local;
+    SFE_CUDA(cudaMemcpyAsync(words, src, n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
 extern "C" int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words)
 {
     SFE_CUDA(cudaSetDevice(e->device));
@@ -2612,6 +2683,15 @@ extern "C" int64_t sfe_engine_launch_count(const sfe_engine *e)
 extern "C" size_t sfe_engine_device_bytes(const sfe_engine *e)
 {
     return e->device_bytes;
+}
+
+// per-launch events of the message-phase kernel inside a timed region: on by default; off
+// for a throughput measurement (an event between two kernels keeps the second from being
+// launched early)
+extern "C" int sfe_engine_time_launches(sfe_engine *e, int on)
+{
+    e->time_launches = on != 0;
+    return 0;
 }
 
 extern "C" int sfe_engine_time_begin(sfe_engine *e)
@@ -2738,6 +2818,7 @@ extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
         sfe::set_last_error("more than " + std::to_string(e->log_cap) + " uncollected steps; call sfe_engine_collect_records");
         return -1;
     }
+    if (apply_pending_bias(e) != 0) return -1;
     if (!e->soma_list.empty())
     {
         launch_soma(e);

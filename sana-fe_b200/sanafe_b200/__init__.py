@@ -144,7 +144,9 @@ def lib():
         "sfe_engine_reset": (C.c_int, [vp]), "sfe_engine_set_bias": (C.c_int, [vp, vp, sz]),
         "sfe_engine_set_neuron_bias": (C.c_int, [vp, u32, dbl]),
         "sfe_engine_read_potentials": (C.c_int, [vp, vp, sz]), "sfe_engine_read_fired": (C.c_int, [vp, vp, sz]),
+        "sfe_engine_read_raster": (C.c_int, [vp, vp, sz]),
         "sfe_engine_total_timesteps": (i64, [vp]), "sfe_engine_launch_count": (i64, [vp]),
+        "sfe_engine_time_launches": (C.c_int, [vp, C.c_int]),
         "sfe_engine_time_begin": (C.c_int, [vp]),
         "sfe_engine_time_end": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         "sfe_engine_create_partitioned": (vp, [C.POINTER(Tables), C.c_int, u32, u32]),
