@@ -58,6 +58,7 @@ struct CoreDev
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
     uint32_t q4;                      // synapses of this core also exist as 4-byte records (syn_q4)
+    uint32_t active_idx, pad1;        // position in the active-core list (per-core step partials)
     unsigned long long syn_begin;
     double scale, inv_scale;          // 2^shift, 2^-shift
     double lat_axon_in, e_axon_in, lat_axon_out, e_axon_out;
@@ -117,6 +118,9 @@ struct DevTables
     const uint32_t *syn_q4;
     const uint32_t *probes;
     uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
+    // fused finalize: cores with work items fold themselves; the others are folded at the end
+    const uint32_t *soma_only_list;
+    uint32_t n_soma_only, n_fold_cores, fused_finalize;
     double sync_delay;
 };
 
@@ -134,7 +138,6 @@ struct Exchange
     uint32_t slice_words;         // words per rank slice (multiple of 4)
     uint32_t acquire_mode, pad;
     const uint32_t *local_slice;  // this rank's slice as the neuron phase wrote it
-    unsigned long long *epoch;    // steps finished by this engine since creation (never reset)
     uint32_t *error;              // sticky: a peer did not arrive in time
     unsigned long long *stamps;   // diagnostic (SFE_PHASE_PROFILE): [4096][4] %globaltimer of CTA 0
 };
@@ -160,8 +163,14 @@ struct DevState
     uint32_t log_cap;
     double *probe_out;     // [n_probes] potentials of the current step
     long long *step;       // [0] = timesteps simulated so far (T-1 during step T), [1] = log cursor
-    uint32_t *work;        // ticket counter of the message phase (reset by finalize_kernel)
+    // Steps enqueued on this engine so far (host-side counter, passed by value with every launch):
+    // parity / flag value of the raster exchange and base of the monotonic work-ticket counter.
+    unsigned long long step_seq;
+    uint32_t *work;        // ticket counter of the message phase: never reset, see fanout_kernel
     uint32_t *final_ticket;
+    uint32_t *core_done;    // [n_cores] work items of the core finished in this step (fused finalize)
+    uint32_t *cores_folded; // cores whose step statistics have been folded in this step
+    struct StepPartial *core_partials; // [n_active_cores]
     struct StepPartial *partials;
 };
 
@@ -206,9 +215,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 // this rank's raster slice into every rank's raster with 16-byte stores over NVLink, fence once
 // at system scope, publish the arrival flags. The neuron phase that wrote the slice is the
 // previous kernel on the stream, so no intra-kernel ordering is needed on the producer side.
-__device__ __forceinline__ void exchange_publish(const Exchange &x)
+__device__ __forceinline__ void exchange_publish(const Exchange &x, const unsigned long long epoch)
 {
-    const unsigned long long epoch = *x.epoch;
     const size_t at = (epoch & 1ull) * x.fired_words + static_cast<size_t>(x.rank) * x.slice_words; // 16-byte aligned
     const uint4 *src = reinterpret_cast<const uint4 *>(x.local_slice);
     const uint32_t n_vec = x.slice_words / 4u;
@@ -238,9 +246,8 @@ __device__ __forceinline__ void exchange_publish(const Exchange &x)
 
 // Message-phase prologue: wait until every rank has published the current step (bounded: a
 // missing peer sets the sticky error flag instead of hanging the GPU). Returns the raster.
-__device__ __forceinline__ const uint32_t *exchange_wait(const Exchange &x)
+__device__ __forceinline__ const uint32_t *exchange_wait(const Exchange &x, const unsigned long long epoch)
 {
-    const unsigned long long epoch = *x.epoch;
     if (threadIdx.x < x.n_peers && ld_relaxed_sys(x.error) == 0u)
     {
         const uint32_t want = static_cast<uint32_t>(epoch) + 1u;
@@ -782,6 +789,204 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
                  : "memory");
 }
 
+// ---------------------------------------------------------------------------
+// K5: energy, counters, simple timing model. One thread per active core; the last
+// CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
+// step record, so every floating-point sum is formed in the same order on every run.
+// ---------------------------------------------------------------------------
+constexpr int kFinalThreads = 256;
+
+struct StepPartial
+{
+    unsigned long long fired, updated, packets, hops, events;
+    double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
+};
+
+__device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
+{
+    StepPartial r;
+    r.fired = __ldcg(&p->fired);
+    r.updated = __ldcg(&p->updated);
+    r.packets = __ldcg(&p->packets);
+    r.hops = __ldcg(&p->hops);
+    r.events = __ldcg(&p->events);
+    r.syn_e = __ldcg(&p->syn_e);
+    r.den_e = __ldcg(&p->den_e);
+    r.soma_e = __ldcg(&p->soma_e);
+    r.net_e = __ldcg(&p->net_e);
+    r.max_gen = __ldcg(&p->max_gen);
+    r.max_proc = __ldcg(&p->max_proc);
+    return r;
+}
+
+__device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &x)
+{
+    b.fired += x.fired;
+    b.updated += x.updated;
+    b.packets += x.packets;
+    b.hops += x.hops;
+    b.events += x.events;
+    b.syn_e += x.syn_e;
+    b.den_e += x.den_e;
+    b.soma_e += x.soma_e;
+    b.net_e += x.net_e;
+    b.max_gen = fmax(b.max_gen, x.max_gen);
+    b.max_proc = fmax(b.max_proc, x.max_proc);
+}
+
+__device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly: a fixed order
+{
+    p.fired = warp_sum(p.fired);
+    p.updated = warp_sum(p.updated);
+    p.packets = warp_sum(p.packets);
+    p.hops = warp_sum(p.hops);
+    p.events = warp_sum(p.events);
+    p.syn_e = warp_sum(p.syn_e);
+    p.den_e = warp_sum(p.den_e);
+    p.soma_e = warp_sum(p.soma_e);
+    p.net_e = warp_sum(p.net_e);
+    p.max_gen = warp_max(p.max_gen);
+    p.max_proc = warp_max(p.max_proc);
+    return p;
+}
+
+// Step statistics of one core, computed by a full warp: the lanes fetch the core's segment /
+// work-item statistics in parallel (one round trip instead of seg_count + item_count dependent
+// ones) and fold them with a butterfly; every sum is formed in the same order on every run.
+// The result is valid in every lane. L2 loads: the statistics may come from other CTAs of the
+// running kernel (fused finalize).
+__device__ __forceinline__ StepPartial fold_core(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
+{
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const CoreDev &core = t.cores[ci];
+    StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+    for (uint32_t g = lane; g < core.seg_count; g += 32)
+    {
+        const StatsN *x = s.stats_n + core.seg_begin + g;
+        n.updated += __ldcg(&x->updated);
+        n.fired += __ldcg(&x->fired);
+        n.packets += __ldcg(&x->packets);
+        n.soma_e += __ldcg(&x->soma_e);
+        n.dend_e += __ldcg(&x->dend_e);
+        n.gen_sum += __ldcg(&x->gen_sum);
+    }
+    StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+    for (uint32_t g = lane; g < core.item_count; g += 32)
+    {
+        const StatsM *x = s.stats_m + core.item_begin + g;
+        m.msgs += __ldcg(&x->msgs);
+        m.events += __ldcg(&x->events);
+        m.hop_e += __ldcg(&x->hop_e);
+        m.hop_w += __ldcg(&x->hop_w);
+        m.hop_n += __ldcg(&x->hop_n);
+        m.hop_s += __ldcg(&x->hop_s);
+        m.syn_e += __ldcg(&x->syn_e);
+        m.den_e += __ldcg(&x->den_e);
+        m.proc += __ldcg(&x->proc);
+    }
+    n.updated = warp_sum(n.updated);
+    n.fired = warp_sum(n.fired);
+    n.packets = warp_sum(n.packets);
+    n.soma_e = warp_sum(n.soma_e);
+    n.dend_e = warp_sum(n.dend_e);
+    n.gen_sum = warp_sum(n.gen_sum);
+    m.msgs = warp_sum(m.msgs);
+    m.events = warp_sum(m.events);
+    m.hop_e = warp_sum(m.hop_e);
+    m.hop_w = warp_sum(m.hop_w);
+    m.hop_n = warp_sum(m.hop_n);
+    m.hop_s = warp_sum(m.hop_s);
+    m.syn_e = warp_sum(m.syn_e);
+    m.den_e = warp_sum(m.den_e);
+    m.proc = warp_sum(m.proc);
+    n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
+    p.fired = n.fired;
+    p.updated = n.updated;
+    p.packets = n.packets;
+    p.hops = m.hop_e + m.hop_w + m.hop_n + m.hop_s;
+    p.events = m.events;
+    p.syn_e = m.syn_e;
+    p.den_e = n.dend_e + m.den_e;
+    p.soma_e = n.soma_e;
+    // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
+    double hop = static_cast<double>(m.hop_e) * core.e_east;
+    hop += static_cast<double>(m.hop_w) * core.e_west;
+    hop += static_cast<double>(m.hop_s) * core.e_south;
+    hop += static_cast<double>(m.hop_n) * core.e_north;
+    p.net_e = hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
+    p.max_gen = n.gen_sum;
+    p.max_proc = m.proc;
+    return p;
+}
+
+// Appends the step record (one thread). schedule_messages_timestep_simple  src/schedule.cpp:61-102
+__device__ __forceinline__ void append_step_record(const DevTables &t, const DevState &s, const StepPartial &b)
+{
+    sfe_step_record r;
+    r.neurons_fired = static_cast<long long>(b.fired);
+    r.neurons_updated = static_cast<long long>(b.updated);
+    r.packets_sent = static_cast<long long>(b.packets);
+    r.total_hops = static_cast<long long>(b.hops);
+    r.spike_count = static_cast<long long>(b.events);
+    r.synapse_energy = b.syn_e;
+    r.dendrite_energy = b.den_e;
+    r.soma_energy = b.soma_e;
+    r.network_energy = b.net_e;
+    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
+    r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
+    const long long cursor = s.step[1];
+    s.log[cursor % s.log_cap] = r;
+    s.step[1] = cursor + 1;
+    s.step[0] = s.step[0] + 1;
+}
+
+// Chip-wide fold by one warp: cores without work items first, then all per-core partials.
+__device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const int lane)
+{
+    for (uint32_t k = 0; k < t.n_soma_only; ++k)
+    {
+        const uint32_t c2 = t.soma_only_list[k];
+        const StepPartial q = fold_core(t, s, c2, lane);
+        if (lane == 0) s.core_partials[t.cores[c2].active_idx] = q;
+    }
+    __syncwarp();
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&s.core_partials[k]));
+    b = warp_fold(b);
+    if (lane == 0) append_step_record(t, s, b);
+}
+
+// Fused finalize (engines whose message phase has work items): called by warp 0 of a CTA after it
+// has published the statistics of a work item of core `ci`. The CTA that completes a core's last
+// item folds the core; the CTA that folds the last core folds the chip and appends the step
+// record - no separate kernel, and the per-core folds overlap the other CTAs' streaming.
+__device__ __forceinline__ void fused_finalize(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
+{
+    uint32_t done = 0u;
+    if (lane == 0)
+    {
+        __threadfence(); // this item's statistics before the count
+        done = atomicAdd(&s.core_done[ci], 1u) + 1u;
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != t.cores[ci].item_count) return;
+    __threadfence();
+    const StepPartial p = fold_core(t, s, ci, lane);
+    uint32_t folded = 0u;
+    if (lane == 0)
+    {
+        s.core_partials[t.cores[ci].active_idx] = p;
+        s.core_done[ci] = 0u; // ready for the next step
+        __threadfence();
+        folded = atomicAdd(s.cores_folded, 1u) + 1u;
+    }
+    folded = __shfl_sync(0xffffffffu, folded, 0);
+    if (folded != t.n_fold_cores) return;
+    __threadfence();
+    if (lane == 0) *s.cores_folded = 0u;
+    fold_chip(t, s, lane);
+}
+
 // Streaming variants of the exact-mode message phase (selected at engine creation,
 // SFE_FANOUT=scalar|vector|tma):
 //   kStreamScalar  8 scalar loads per 128-synapse chunk, next chunk's loads issued
@@ -798,7 +1003,9 @@ constexpr int kQ4StageBytes = 512;  // 128 records
 constexpr int kTmaStages = 4;
 constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
 
-template <int V>
+// kFused: the message phase also folds the step (fused_finalize); chosen when no CTA gets more than
+// one work item, so that a fold never delays a next item
+template <int V, bool kFused>
 __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -838,21 +1045,27 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     if (s.x.n_peers > 0u)
     {
         const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-        unsigned long long *st = stamp ? s.x.stamps + (*s.x.epoch & 4095ull) * 4ull : nullptr;
+        unsigned long long *st = stamp ? s.x.stamps + (s.step_seq & 4095ull) * 4ull : nullptr;
         if (stamp) st[0] = global_timer_ns();
-        if (blockIdx.x == 0) exchange_publish(s.x);
+        if (blockIdx.x == 0) exchange_publish(s.x, s.step_seq);
         if (stamp) st[1] = global_timer_ns();
-        raster = exchange_wait(s.x);
+        raster = exchange_wait(s.x, s.step_seq);
         if (stamp) st[2] = global_timer_ns();
     }
     const bool gather = t.partitioned != 0u;
+    const uint32_t ticket_base = static_cast<uint32_t>(s.step_seq) * (t.n_fan_items + gridDim.x);
+    // a rank without work items (it still takes part in the exchange) has nothing that would
+    // trigger the fused finalize: its first warp folds the chip right away
+    if (kFused && t.n_fold_cores == 0u && blockIdx.x == 0 && warp == 0) fold_chip(t, s, lane);
 
     // Persistent CTAs: cores (heaviest first) are handed out through an atomic ticket,
     // so the grid is one resident wave and no SM idles behind a wave boundary.
     for (;;)
     {
     __syncthreads(); // previous core fully retired (smem accumulators, next_item)
-    if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u);
+    // the ticket counter is never reset: a step draws n_fan_items + gridDim.x tickets (every CTA
+    // ends on one failed draw), so step k's tickets start at k times that (mod 2^32)
+    if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) - ticket_base;
     __syncthreads();
     const uint32_t ticket = next_item;
     if (ticket >= t.n_fan_items) break;
@@ -1298,74 +1511,12 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             }
             s.stats_m[item_id] = out;
         }
+        if (kFused && warp == 0) fused_finalize(t, s, ci, lane); // thread 0 wrote the statistics
     }
     } // persistent loop
 }
 
-// ---------------------------------------------------------------------------
-// K5: energy, counters, simple timing model. One thread per active core; the last
-// CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
-// step record, so every floating-point sum is formed in the same order on every run.
-// ---------------------------------------------------------------------------
-constexpr int kFinalThreads = 256;
-
-struct StepPartial
-{
-    unsigned long long fired, updated, packets, hops, events;
-    double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
-};
-
-__device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
-{
-    StepPartial r;
-    r.fired = __ldcg(&p->fired);
-    r.updated = __ldcg(&p->updated);
-    r.packets = __ldcg(&p->packets);
-    r.hops = __ldcg(&p->hops);
-    r.events = __ldcg(&p->events);
-    r.syn_e = __ldcg(&p->syn_e);
-    r.den_e = __ldcg(&p->den_e);
-    r.soma_e = __ldcg(&p->soma_e);
-    r.net_e = __ldcg(&p->net_e);
-    r.max_gen = __ldcg(&p->max_gen);
-    r.max_proc = __ldcg(&p->max_proc);
-    return r;
-}
-
-__device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &x)
-{
-    b.fired += x.fired;
-    b.updated += x.updated;
-    b.packets += x.packets;
-    b.hops += x.hops;
-    b.events += x.events;
-    b.syn_e += x.syn_e;
-    b.den_e += x.den_e;
-    b.soma_e += x.soma_e;
-    b.net_e += x.net_e;
-    b.max_gen = fmax(b.max_gen, x.max_gen);
-    b.max_proc = fmax(b.max_proc, x.max_proc);
-}
-
-__device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly: a fixed order
-{
-    p.fired = warp_sum(p.fired);
-    p.updated = warp_sum(p.updated);
-    p.packets = warp_sum(p.packets);
-    p.hops = warp_sum(p.hops);
-    p.events = warp_sum(p.events);
-    p.syn_e = warp_sum(p.syn_e);
-    p.den_e = warp_sum(p.den_e);
-    p.soma_e = warp_sum(p.soma_e);
-    p.net_e = warp_sum(p.net_e);
-    p.max_gen = warp_max(p.max_gen);
-    p.max_proc = warp_max(p.max_proc);
-    return p;
-}
-
-// One WARP per active core: the lanes fetch the core's segment / work-item statistics in
-// parallel (one round trip instead of seg_count + item_count dependent ones) and fold them
-// with a butterfly; every sum is formed in the same order on every run.
+// Stand-alone finalize (engines without message-phase work items): one WARP per active core.
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
 {
     __shared__ StepPartial warp_part[kFinalThreads / 32];
@@ -1375,68 +1526,7 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const uint32_t a = blockIdx.x * (kFinalThreads / 32) + warp;
-    if (a < t.n_active_cores)
-    {
-        const uint32_t ci = t.active_core_list[a];
-        const CoreDev &core = t.cores[ci];
-        StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
-        for (uint32_t g = lane; g < core.seg_count; g += 32)
-        {
-            const StatsN x = s.stats_n[core.seg_begin + g];
-            n.updated += x.updated;
-            n.fired += x.fired;
-            n.packets += x.packets;
-            n.soma_e += x.soma_e;
-            n.dend_e += x.dend_e;
-            n.gen_sum += x.gen_sum;
-        }
-        StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
-        for (uint32_t g = lane; g < core.item_count; g += 32)
-        {
-            const StatsM x = s.stats_m[core.item_begin + g];
-            m.msgs += x.msgs;
-            m.events += x.events;
-            m.hop_e += x.hop_e;
-            m.hop_w += x.hop_w;
-            m.hop_n += x.hop_n;
-            m.hop_s += x.hop_s;
-            m.syn_e += x.syn_e;
-            m.den_e += x.den_e;
-            m.proc += x.proc;
-        }
-        n.updated = warp_sum(n.updated);
-        n.fired = warp_sum(n.fired);
-        n.packets = warp_sum(n.packets);
-        n.soma_e = warp_sum(n.soma_e);
-        n.dend_e = warp_sum(n.dend_e);
-        n.gen_sum = warp_sum(n.gen_sum);
-        m.msgs = warp_sum(m.msgs);
-        m.events = warp_sum(m.events);
-        m.hop_e = warp_sum(m.hop_e);
-        m.hop_w = warp_sum(m.hop_w);
-        m.hop_n = warp_sum(m.hop_n);
-        m.hop_s = warp_sum(m.hop_s);
-        m.syn_e = warp_sum(m.syn_e);
-        m.den_e = warp_sum(m.den_e);
-        m.proc = warp_sum(m.proc);
-        n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
-        p.fired = n.fired;
-        p.updated = n.updated;
-        p.packets = n.packets;
-        p.hops = m.hop_e + m.hop_w + m.hop_n + m.hop_s;
-        p.events = m.events;
-        p.syn_e = m.syn_e;
-        p.den_e = n.dend_e + m.den_e;
-        p.soma_e = n.soma_e;
-        // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
-        double hop = static_cast<double>(m.hop_e) * core.e_east;
-        hop += static_cast<double>(m.hop_w) * core.e_west;
-        hop += static_cast<double>(m.hop_s) * core.e_south;
-        hop += static_cast<double>(m.hop_n) * core.e_north;
-        p.net_e = hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
-        p.max_gen = n.gen_sum;
-        p.max_proc = m.proc;
-    }
+    if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane);
     if (lane == 0) warp_part[warp] = p;
     __syncthreads();
     if (threadIdx.x == 0)
@@ -1460,26 +1550,8 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
     if (threadIdx.x != 0) return;
     b = warp_part[0];
     for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
-    sfe_step_record r;
-    r.neurons_fired = static_cast<long long>(b.fired);
-    r.neurons_updated = static_cast<long long>(b.updated);
-    r.packets_sent = static_cast<long long>(b.packets);
-    r.total_hops = static_cast<long long>(b.hops);
-    r.spike_count = static_cast<long long>(b.events);
-    r.synapse_energy = b.syn_e;
-    r.dendrite_energy = b.den_e;
-    r.soma_energy = b.soma_e;
-    r.network_energy = b.net_e;
-    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
-    // schedule_messages_timestep_simple  src/schedule.cpp:61-102
-    r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
-    const long long cursor = s.step[1];
-    s.log[cursor % s.log_cap] = r;
-    s.step[1] = cursor + 1;
-    s.step[0] = s.step[0] + 1;
-    *s.work = 0u;
+    append_step_record(t, s, b);
     *s.final_ticket = 0u;
-    *s.x.epoch += 1ull;
 }
 
 // ---------------------------------------------------------------------------
@@ -1904,11 +1976,21 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
 
     if (e->upload(&e->t.fanout_core_list, e->fanout_list.data(), e->fanout_list.size()) != 0) return -1;
     {
-        std::vector<uint32_t> active;
+        // this rank's cores that do anything in a step; those with axons-in fold their own step
+        // statistics at the end of their last work item (fused finalize), the rest are folded last
+        std::vector<uint32_t> active, soma_only;
         for (uint32_t c = 0; c < tb->n_cores; ++c)
-            if (tb->cores[c].neuron_count > 0 || tb->cores[c].axon_in_count > 0) active.push_back(c);
+        {
+            if (!is_local(c) || (tb->cores[c].neuron_count == 0 && tb->cores[c].axon_in_count == 0)) continue;
+            e->h_cores[c].active_idx = static_cast<uint32_t>(active.size());
+            active.push_back(c);
+            if (tb->cores[c].axon_in_count == 0) soma_only.push_back(c);
+        }
         e->t.n_active_cores = static_cast<uint32_t>(active.size());
+        e->t.n_soma_only = static_cast<uint32_t>(soma_only.size());
+        e->t.n_fold_cores = static_cast<uint32_t>(e->fanout_list.size());
         if (e->upload(&e->t.active_core_list, active.data(), active.size()) != 0) return -1;
+        if (e->upload(&e->t.soma_only_list, soma_only.data(), soma_only.size()) != 0) return -1;
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
     {
@@ -2069,7 +2151,9 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->s.work, 1) != 0) return -1;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
-    if (e->alloc(&e->s.x.epoch, 1) != 0) return -1;
+    if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
+    if (e->alloc(&e->s.cores_folded, 1) != 0) return -1;
+    if (e->alloc(&e->s.core_partials, e->t.n_active_cores) != 0) return -1;
     if (e->alloc(&e->s.x.error, 1) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
     if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
@@ -2112,17 +2196,20 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         sfe::set_last_error("a core needs more than 200 KB of shared-memory dendrite accumulators");
         return -1;
     }
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
     {
         int per_sm = 1, sms = 1;
         if (e->fanout_variant == kStreamQ4)
-            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamQ4>, kFanoutThreads, smem_max));
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamQ4, false>, kFanoutThreads, smem_max));
         else if (e->fanout_variant == kStreamTma)
-            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamTma>, kFanoutThreads, smem_max));
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamTma, false>, kFanoutThreads, smem_max));
         else
-            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar>, kFanoutThreads, smem_max));
+            SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar, false>, kFanoutThreads, smem_max));
         SFE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
         if (const char *v = std::getenv("SFE_FANOUT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
         // ---- message-phase work items: split every core's inbox into slices so that there
@@ -2191,6 +2278,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
         e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(items.size(), slots)));
+        // fold the step inside the message phase when no CTA gets a second item (a fold then never
+        // delays a next item): ranks of a partitioned chip, small chips. SFE_FUSED_FINALIZE=0/1 forces.
+        {
+            const char *fused = std::getenv("SFE_FUSED_FINALIZE");
+            e->t.fused_finalize = fused != nullptr ? (std::atoi(fused) != 0 ? 1u : 0u) : (items.size() <= slots ? 1u : 0u);
+        }
     }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
@@ -2297,17 +2390,33 @@ static void launch_soma(sfe_engine *e)
 static void launch_fanout(sfe_engine *e)
 {
     const unsigned grid = e->fanout_grid;
+    const bool fused = e->t.fused_finalize != 0u;
     if (e->fanout_variant == kStreamQ4)
-        launch_step_kernel(e, fanout_kernel<kStreamQ4>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    {
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamQ4, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamQ4, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    }
     else if (e->fanout_variant == kStreamTma)
-        launch_step_kernel(e, fanout_kernel<kStreamTma>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    {
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamTma, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamTma, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    }
     else
-        launch_step_kernel(e, fanout_kernel<kStreamScalar>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    {
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamScalar, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamScalar, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+    }
 }
 
 static void launch_finalize(sfe_engine *e)
 {
-    launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
+    const bool fanout_ran = !e->fanout_list.empty() || e->p2p_on;
+    if (!(e->t.fused_finalize != 0u && fanout_ran))
+    {
+        launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
+        ++e->launches;
+    }
+    ++e->s.step_seq;
 }
 
 static int apply_pending_bias(sfe_engine *e);
@@ -2347,7 +2456,6 @@ static int enqueue_step(sfe_engine *e, bool probes)
         }
     }
     launch_finalize(e);
-    ++e->launches;
     ++e->total_timesteps;
     return 0;
 }
@@ -2479,7 +2587,6 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 ++e->launches;
             }
             launch_finalize(e);
-            ++e->launches;
             ++e->total_timesteps;
         }
         SFE_CUDA(cudaGetLastError());
@@ -2853,7 +2960,6 @@ extern "C" int sfe_engine_enqueue_message_phase(sfe_engine *e)
     }
     prof_mark(e);
     launch_finalize(e);
-    ++e->launches;
     ++e->total_timesteps;
     SFE_CUDA(cudaGetLastError());
     return 0;
