@@ -1003,8 +1003,7 @@ constexpr int kQ4StageBytes = 512;  // 128 records
 constexpr int kTmaStages = 4;
 constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
 
-// kFused: the message phase also folds the step (fused_finalize); chosen when no CTA gets more than
-// one work item, so that a fold never delays a next item
+// kFused: the message phase also folds the step (fused_finalize, SFE_FUSED_FINALIZE=1)
 template <int V, bool kFused>
 __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
@@ -2278,11 +2277,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
         e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(items.size(), slots)));
-        // fold the step inside the message phase when no CTA gets a second item (a fold then never
-        // delays a next item): ranks of a partitioned chip, small chips. SFE_FUSED_FINALIZE=0/1 forces.
+        // SFE_FUSED_FINALIZE=1: fold the step inside the message phase instead of a third kernel.
+        // Measured (C4 on 1/2/4/8 GPUs): no faster than the PDL-overlapped finalize kernel - the fold
+        // of the last core and of the chip is a serial tail either way - so it is off by default.
         {
             const char *fused = std::getenv("SFE_FUSED_FINALIZE");
-            e->t.fused_finalize = fused != nullptr ? (std::atoi(fused) != 0 ? 1u : 0u) : (items.size() <= slots ? 1u : 0u);
+            e->t.fused_finalize = (fused != nullptr && std::atoi(fused) != 0) ? 1u : 0u;
         }
     }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
