@@ -384,6 +384,15 @@ int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offse
  * "group.offset,timestep\n" (src/chip.cpp:1610-1630). Returns the bytes needed. */
 size_t sfe_chip_format_spikes(const sfe_chip *c, const uint32_t *fired_bits, int64_t timesteps,
         int64_t timestep_start, char *buf, size_t cap);
+/* Rows of messages.csv (sim_trace_record_message, src/chip.cpp:1731-1764; order of
+ * sim_sort_and_record_messages, :439-456) for `timesteps` steps, rebuilt from the per-neuron status
+ * bytes of those steps (sfe_trace_request.status). SFE_TIMING_DETAILED runs the NoC scheduler so
+ * that the timestamps and network / blocking delays are filled, SFE_TIMING_SIMPLE leaves them at
+ * -inf / 0 like the reference. Message ids continue over the chip's lifetime in single-thread
+ * creation order. Returns the text length; a call with buf = NULL only sizes the buffer (it does
+ * not consume message ids). */
+size_t sfe_chip_format_messages(sfe_chip *chip, const uint8_t *status, int64_t timesteps, int64_t timestep_start,
+        int timing_model, char *buf, size_t cap);
 /* "group.offset\n" of every potential probe, in potentials.csv column order (src/chip.cpp:1454-1476) */
 size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap);
 

@@ -51,6 +51,7 @@ struct sfe_chip
     double total_sim_time{0.0};
     uint32_t rank{0}, world{1};
     std::unique_ptr<sfe::DetailedScheduler> scheduler; // built on first use
+    long next_mid{0};                                  // total_messages_sent (src/chip.hpp:126): ids of traced messages
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -372,6 +373,54 @@ extern "C" size_t sfe_chip_format_spikes(const sfe_chip *c, const uint32_t *fire
         buf[n] = '\0';
     }
     return out.size();
+}
+
+// Rows of messages.csv (sim_trace_record_message, src/chip.cpp:1731-1764) for `timesteps` steps,
+// rebuilt from the per-neuron status bytes of those steps; every other message field is a
+// load-time constant of the lowered tables. SFE_TIMING_DETAILED runs the NoC scheduler so that
+// the timestamps / network / blocking delays are filled; SFE_TIMING_SIMPLE leaves them at their
+// defaults (-inf / 0), like the reference. Message ids continue the chip's lifetime counter
+// (total_messages_sent, src/chip.cpp:815) in the single-thread creation order.
+extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, int64_t timesteps, int64_t timestep_start,
+        int timing_model, char *buf, size_t cap)
+{
+    return guarded(
+            [&]() -> size_t {
+                if (!c->loaded) throw std::runtime_error("sfe_chip_format_messages: no network loaded");
+                if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
+                const sfe::HostTables &t = c->tables;
+                const size_t n = t.view.n_neurons;
+                std::ostringstream out;
+                std::vector<sfe::MessageRecord> recs;
+                const long first_mid = c->next_mid;
+                for (int64_t s = 0; s < timesteps; ++s)
+                {
+                    recs.clear();
+                    c->scheduler->trace_step(status + static_cast<size_t>(s) * n, timing_model == SFE_TIMING_DETAILED, recs,
+                            c->next_mid);
+                    for (const sfe::MessageRecord &m : recs)
+                    {
+                        const sfe::HostTables::NeuronName &nm = t.names[m.src_neuron];
+                        out << (timestep_start + s) << "," << m.mid << "," << t.group_names[nm.group] << "." << nm.offset << ","
+                            << t.core_names[m.src_core] << ",";
+                        if (m.placeholder) out << "x.x,";
+                        else out << t.core_names[m.dest_core] << ",";
+                        out << m.hops << "," << m.spikes << "," << m.sent << "," << m.received << "," << m.processed << ","
+                            << m.generation_delay << "," << m.processing_delay << "," << m.network_delay << ","
+                            << m.blocking_delay << "," << m.min_hop_delay << "," << m.messages_along_route << "\n";
+                    }
+                }
+                const std::string text = out.str();
+                if (buf != nullptr && cap > 0)
+                {
+                    const size_t k = std::min(cap - 1, text.size());
+                    std::memcpy(buf, text.data(), k);
+                    buf[k] = '\0';
+                }
+                else c->next_mid = first_mid; // sizing call: the ids are not consumed
+                return text.size();
+            },
+            static_cast<size_t>(0));
 }
 
 // header of potentials.csv (src/chip.cpp:1454-1476): "timestep,neuron g.o,..."

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <limits>
 #include <list>
 #include <queue>
 #include <stdexcept>
@@ -40,6 +41,7 @@ struct Msg
     uint32_t src_core_offset{0}, src_core{0}, dest_core{0};
     bool placeholder{true};
     bool in_noc{false};
+    uint32_t slot{0}; // index of this message's trace record
 };
 
 struct BySentTime // CompareMessagesBySentTime  src/message.cpp:61-65
@@ -137,9 +139,28 @@ DetailedScheduler::DetailedScheduler(const sfe_tables &t) : t_(t)
     }
 }
 
-double DetailedScheduler::schedule_step(const uint8_t *status)
+double DetailedScheduler::run_step(
+        const uint8_t *status, const bool schedule, std::vector<MessageRecord> *trace, long *next_mid)
 {
     const sfe_tables &t = t_;
+    const double ninf = -std::numeric_limits<double>::infinity();
+    std::vector<MessageRecord> recs; // creation order = cores ascending, in-core send order
+    auto new_record = [&](const Msg &m, const uint32_t src_neuron, const uint32_t spikes) -> uint32_t {
+        MessageRecord r;
+        r.placeholder = m.placeholder;
+        r.mid = m.placeholder ? -1L : (*next_mid)++;
+        r.src_neuron = src_neuron;
+        r.src_core = m.src_core;
+        r.dest_core = m.dest_core;
+        r.hops = m.hops;
+        r.spikes = spikes;
+        r.sent = r.received = r.processed = ninf;
+        r.generation_delay = m.generation_delay;
+        r.processing_delay = m.processing_delay;
+        r.min_hop_delay = m.min_hop_delay;
+        recs.push_back(r);
+        return static_cast<uint32_t>(recs.size() - 1);
+    };
     // ---- rebuild the per-sending-core message lists ------------------------------
     std::vector<std::list<Msg>> queues(t.n_cores);
     for (uint32_t c = 0; c < t.n_cores; ++c)
@@ -186,6 +207,7 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
                 m.src_core_offset = cd.offset;
                 m.src_core = c;
                 m.dest_core = dc;
+                if (trace != nullptr) m.slot = new_record(m, i, ax.syn_count);
                 queues[c].push_back(m);
             }
         }
@@ -197,8 +219,31 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
             m.src_y = src_tile.y;
             m.src_core_offset = cd.offset;
             m.src_core = c;
+            if (trace != nullptr) m.slot = new_record(m, cd.neuron_begin + cd.neuron_count - 1, 0u);
             queues[c].push_back(m);
         }
+    }
+    auto finish_trace = [&]() {
+        if (trace == nullptr) return;
+        // sim_sort_and_record_messages: the same std::sort on the same sequence with the same
+        // comparator (placeholders compare equal, so their order is whatever the sort leaves)
+        std::vector<const MessageRecord *> order;
+        order.reserve(recs.size());
+        for (const MessageRecord &r : recs) order.push_back(&r);
+        std::sort(order.begin(), order.end(), [](const MessageRecord *a, const MessageRecord *b) {
+            if (a->placeholder && b->placeholder) return a->mid < b->mid; // CompareMessagesByID  src/message.cpp:70-91
+            if (a->placeholder) return false;
+            if (b->placeholder) return true;
+            return a->mid < b->mid;
+        });
+        for (const MessageRecord *r : order) trace->push_back(*r);
+    };
+    if (!schedule)
+    {
+        // schedule_messages_timestep_simple  src/schedule.cpp:84-86: no blocking, network = minimum hops
+        for (MessageRecord &r : recs) r.network_delay = r.min_hop_delay;
+        finish_trace();
+        return 0.0;
     }
 
     // ---- schedule_messages_timestep_detailed  src/schedule.cpp:208-292 -----------------
@@ -216,6 +261,7 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
         Msg m = q.front();
         q.pop_front();
         m.sent = m.generation_delay;
+        if (trace != nullptr) recs[m.slot].sent = m.sent;
         pq.push(m);
     }
     std::vector<uint32_t> busy; // destination cores that currently hold tracked messages, ascending
@@ -246,7 +292,12 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
             // schedule_handle_message  src/schedule.cpp:306-358
             const double along_route = noc.congestion(m);
             const double capacity = static_cast<double>((m.hops + 1UL) * t.noc_buffer_size);
-            if (along_route > capacity) m.sent += (along_route - capacity) * noc.mean_rx;
+            double blocking = 0.0;
+            if (along_route > capacity)
+            {
+                blocking = (along_route - capacity) * noc.mean_rx;
+                m.sent += blocking;
+            }
             const double congestion_delay = along_route * noc.mean_rx / (static_cast<double>(m.hops) + 1.0);
             const double network_delay = std::max(m.min_hop_delay, congestion_delay);
             const double earliest = m.sent + network_delay;
@@ -260,6 +311,16 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
             noc.received[m.dest_core].push_back(m);
             noc.track(m, true);
             last = std::max(last, m.processed);
+            if (trace != nullptr)
+            {
+                MessageRecord &r = recs[m.slot];
+                r.sent = m.sent;
+                r.received = m.received;
+                r.processed = m.processed;
+                r.network_delay = network_delay;
+                r.blocking_delay = blocking;
+                r.messages_along_route = along_route;
+            }
         }
         auto &q = queues[m.src_core];
         if (!q.empty())
@@ -268,10 +329,12 @@ double DetailedScheduler::schedule_step(const uint8_t *status)
             Msg next = q.front();
             q.pop_front();
             next.sent = m.sent + next.generation_delay;
+            if (trace != nullptr) recs[next.slot].sent = next.sent;
             pq.push(next);
             last = std::max(last, next.sent);
         }
     }
+    finish_trace();
     return last + t.sync_delay;
 }
 

@@ -183,6 +183,7 @@ def lib():
         "sfe_chip_tables": (C.POINTER(Tables), [vp]), "sfe_chip_engine": (vp, [vp]),
         "sfe_chip_neuron_index": (i64, [vp, cstr, u64]),
         "sfe_chip_set_neuron_attribute": (C.c_int, [vp, cstr, u64, cstr, dbl]),
+        "sfe_chip_format_messages": (sz, [vp, vp, i64, i64, C.c_int, C.c_char_p, sz]),
         "sfe_chip_format_spikes": (sz, [vp, vp, i64, i64, C.c_char_p, sz]),
         "sfe_chip_probe_names": (sz, [vp, C.c_char_p, sz]),
     }
@@ -335,14 +336,28 @@ class SpikingChip:
         lib().sfe_chip_format_spikes(self._h, fired_bits.ctypes.data, steps, timestep_start, buf, n + 1)
         return buf.value.decode()
 
+    MESSAGE_HEADER = ("timestep,mid,src_neuron,src_hw,dest_hw,hops,spikes,send_timestamp,received_timestamp,"
+                      "processed_timestamp,generation_delay,processing_delay,network_delay,blocking_delay,"
+                      "min_hop_delay,messages_along_route\n")
+
+    def format_messages(self, status, timestep_start, timing_model="simple"):
+        """Rows of messages.csv for the steps whose status bytes are given (src/chip.cpp:1731-1764)."""
+        status = np.ascontiguousarray(status, dtype=np.uint8)
+        steps = status.shape[0]
+        tm = TIMING[timing_model] if isinstance(timing_model, str) else int(timing_model)
+        n = lib().sfe_chip_format_messages(self._h, status.ctypes.data, steps, timestep_start, tm, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().sfe_chip_format_messages(self._h, status.ctypes.data, steps, timestep_start, tm, buf, n + 1)
+        return buf.value.decode()
+
     def sim(self, timesteps=1, timing_model="detailed", processing_threads=0, scheduler_threads=0,
             spike_trace=None, potential_trace=None, neuron_trace=None, perf_trace=None, message_trace=None,
             write_trace_headers=True):
         """sanafe.SpikingChip.sim (src/pymodule.cpp:549-706): returns the same result dict."""
-        if neuron_trace or message_trace:
-            raise SanafeError("neuron_trace / message_trace are not implemented yet")
+        if neuron_trace:
+            raise SanafeError("neuron_trace is not implemented yet")
         rd, tr = self.sim_raw(timesteps, timing_model, steps=bool(perf_trace), fired=bool(spike_trace),
-                              potentials=bool(potential_trace))
+                              potentials=bool(potential_trace), status=bool(message_trace))
         result = {
             "timestep_start": rd.timestep_start, "timesteps_executed": rd.timesteps_executed,
             "energy": {"total": rd.total_energy, "synapse": rd.synapse_energy, "dendrite": rd.dendrite_energy,
@@ -371,6 +386,12 @@ class SpikingChip:
                 body = "".join(f"{rd.timestep_start + s}," + "".join(f"{v:g}," for v in pots[s]) + "\n"
                                for s in range(timesteps)) if names else ""
                 self._write_text(potential_trace, (hdr if write_trace_headers else "") + body)
+        if message_trace:
+            text = self.format_messages(tr["status"], rd.timestep_start, timing_model)
+            if message_trace is True:
+                result["message_trace"] = [r.split(",") for r in text.split("\n") if r]
+            else:
+                self._write_text(message_trace, (self.MESSAGE_HEADER if write_trace_headers else "") + text)
         if perf_trace:
             st = tr["steps"]
             if perf_trace is True:

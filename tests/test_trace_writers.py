@@ -1,0 +1,105 @@
+"""Trace writers: messages.csv and perf.csv byte-for-byte against the files the
+reference's own writers produced (tests/golden/traces/, made by `oracle/_ref/sanafe_ref --traces
+--threads 1`; regenerate with tests/golden/make_goldens.py --traces).
+CPU tests: message rows rebuilt from the oracle's status bytes; GPU tests: SpikingChip.sim()."""
+import gzip
+import io
+import os
+
+import numpy as np
+import pytest
+
+import sanafe_b200 as sfe
+from helpers import GOLDEN, Oracle, load_chip
+
+CASES = [("example", "simple", 100), ("example", "detailed", 100), ("synth_small", "detailed", 12),
+         ("synth_delay", "simple", 12), ("truenorth", "detailed", 20)]
+
+
+def golden_messages(name, timing):
+    with gzip.open(os.path.join(GOLDEN, "traces", f"{name}.{timing}.messages.csv.gz"), "rt") as f:
+        return f.read()
+
+
+def split_rows(text):
+    """(ordinary rows in file order, placeholder rows as a sorted list): the reference sorts with
+    std::sort and a comparator under which all placeholders are equal, so only the set of
+    placeholder rows of a step is defined."""
+    normal, holders = [], []
+    for row in text.splitlines()[1:]:
+        (holders if ",x.x," in row else normal).append(row)
+    return normal, sorted(holders)
+
+
+@pytest.mark.parametrize("name,timing,steps", CASES)
+def test_message_trace_from_status_bytes(name, timing, steps):
+    chip = load_chip(name, device=-1)
+    rd, out = Oracle(chip).run(steps, status=True)
+    text = chip.MESSAGE_HEADER + chip.format_messages(out["status"], 1, timing)
+    want = golden_messages(name, timing)
+    got_n, got_p = split_rows(text)
+    want_n, want_p = split_rows(want)
+    assert got_n == want_n
+    assert got_p == want_p
+    if text != want:  # placeholder order: same std::sort on the same sequence should agree too
+        pytest.xfail("placeholder rows in a different (unspecified) order")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,timing,steps", CASES)
+def test_sim_writes_reference_traces(name, timing, steps):
+    chip = load_chip(name, device=0)
+    perf, msgs = io.StringIO(), io.StringIO()
+    chip.sim(steps, timing_model=timing, perf_trace=perf, message_trace=msgs)
+    with open(os.path.join(GOLDEN, "traces", f"{name}.{timing}.perf.csv")) as f:
+        want_perf = f.read()
+    assert perf.getvalue() == want_perf
+    got_n, got_p = split_rows(msgs.getvalue())
+    want_n, want_p = split_rows(golden_messages(name, timing))
+    assert got_n == want_n and got_p == want_p
+
+
+@pytest.mark.gpu
+def test_sim_command_line_writes_the_reference_files(tmp_path):
+    """`sim -s -t simple -o DIR arch.yaml snn.yaml 200` (src/main.cpp:27-98): the four CSV traces
+    equal the reference's own files for the Hodgkin-Huxley case, run_summary.yaml has its keys."""
+    import subprocess
+    from helpers import ROOT
+    sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
+    src = os.path.join(GOLDEN, "src")
+    res = subprocess.run([sim, "-s", "-t", "simple", "-o", str(tmp_path), os.path.join(src, "hh_arch.yaml"),
+                          os.path.join(src, "hh_snn.yaml"), "200"], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+    def want(kind):
+        with gzip.open(os.path.join(GOLDEN, "traces", f"hh.simple.{kind}.csv.gz"), "rt") as f:
+            return f.read()
+
+    assert (tmp_path / "spikes.csv").read_text() == want("spikes")
+    assert (tmp_path / "perf.csv").read_text() == want("perf")
+    got_n, got_p = split_rows((tmp_path / "messages.csv").read_text())
+    want_n, want_p = split_rows(want("messages"))
+    assert got_n == want_n and got_p == want_p
+    # potentials: the ODE soma goes through CUDA's exp/pow, 6 printed digits can differ in the last
+    got = np.genfromtxt(io.StringIO((tmp_path / "potentials.csv").read_text()), delimiter=",", skip_header=1)[:, :-1]
+    ref = np.genfromtxt(io.StringIO(want("potentials")), delimiter=",", skip_header=1)[:, :-1]
+    assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-5, atol=1e-9)
+    assert (tmp_path / "potentials.csv").read_text().splitlines()[0] == want("potentials").splitlines()[0]
+    summary = (tmp_path / "run_summary.yaml").read_text()
+    for key in ("timesteps_executed: 200", "total_spikes:", "total_messages_sent:", "total_neurons_fired:", "sim_time:",
+                "energy:", "  total:"):
+        assert key in summary
+    assert "Run finished." in res.stdout
+
+
+def test_sim_command_line_usage_and_errors(tmp_path):
+    """No GPU needed: usage text, bad flags and the no-fallback rule."""
+    import subprocess
+    from helpers import ROOT
+    sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
+    res = subprocess.run([sim], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0 and "Usage: ./sim [-mnopstvNS]" in res.stdout
+    res = subprocess.run([sim, "-t", "bogus", "a.yaml", "b.yaml", "10"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 1 and "Timing model not recognized" in res.stderr
+    res = subprocess.run([sim, "missing_arch.yaml", "missing_net.yaml", "10"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 1
