@@ -87,12 +87,14 @@ public:
             const py::object &potential_trace, const py::object &neuron_trace, const py::object &perf_trace,
             const py::object &message_trace, bool write_trace_headers)
     {
-        if (!neuron_trace.is_none() || !message_trace.is_none())
-            throw std::runtime_error("neuron_trace / message_trace are not implemented by the B200 engine yet");
+        if (!neuron_trace.is_none())
+            throw std::runtime_error("neuron_trace (model-defined traces) is not implemented by the B200 engine yet");
         const sfe_tables *t = sfe_chip_tables(h_);
         if (t == nullptr) throw std::runtime_error("no network loaded");
         const size_t words = (static_cast<size_t>(t->n_neurons) + 31) / 32;
         const bool want_spikes = !spike_trace.is_none(), want_pot = !potential_trace.is_none(), want_perf = !perf_trace.is_none();
+        const bool want_msgs = !message_trace.is_none();
+        std::vector<uint8_t> status(want_msgs ? static_cast<size_t>(t->n_neurons) * timesteps : 0);
         std::vector<uint32_t> fired(want_spikes ? words * timesteps : 0);
         std::vector<double> pots(want_pot ? static_cast<size_t>(t->n_probes) * timesteps : 0);
         std::vector<sfe_step_record> steps(want_perf ? timesteps : 0);
@@ -100,6 +102,7 @@ public:
         req.fired_bits = fired.empty() ? nullptr : fired.data();
         req.potentials = pots.empty() ? nullptr : pots.data();
         req.steps = steps.empty() ? nullptr : steps.data();
+        req.status = status.empty() ? nullptr : status.data();
         sfe_run_data rd{};
         const int timing = parse_timing(timing_model);
         int rc = 0;
@@ -184,6 +187,28 @@ public:
                         text << "\n";
                     }
                 write_sink(potential_trace, text.str());
+            }
+        }
+        if (want_msgs)
+        {
+            // messages.csv rows  src/chip.cpp:1586-1608, 1731-1764
+            const size_t need = sfe_chip_format_messages(h_, status.data(), timesteps, rd.timestep_start, timing, nullptr, 0);
+            std::string text(need + 1, '\0');
+            sfe_chip_format_messages(h_, status.data(), timesteps, rd.timestep_start, timing, text.data(), text.size());
+            text.resize(need);
+            if (py::isinstance<py::bool_>(message_trace))
+            {
+                py::list rows;
+                std::istringstream in(text);
+                for (std::string line; std::getline(in, line);) rows.append(py::str(line).attr("split")(","));
+                out["message_trace"] = rows;
+            }
+            else
+            {
+                const std::string header = "timestep,mid,src_neuron,src_hw,dest_hw,hops,spikes,send_timestamp,received_timestamp,"
+                                           "processed_timestamp,generation_delay,processing_delay,network_delay,blocking_delay,"
+                                           "min_hop_delay,messages_along_route\n";
+                write_sink(message_trace, (write_trace_headers ? header : std::string()) + text);
             }
         }
         if (want_perf)
