@@ -225,7 +225,6 @@ def main():
     assert L.sfe_engine_enqueue(eng, args.steps) == 0, L.sfe_last_error()
     assert L.sfe_engine_time_end(eng, C.byref(ms_total), None) == 0, L.sfe_last_error()
     launches = L.sfe_engine_launch_count(eng) - launches0
-    clocks = sampler.stop()
     assert L.sfe_engine_collect(eng, C.byref(rd)) == 0, L.sfe_last_error()
     events, messages = rd.spikes, rd.packets_sent
     seconds = ms_total.value / 1e3
@@ -240,6 +239,7 @@ def main():
     assert L.sfe_engine_enqueue(eng, args.steps) == 0, L.sfe_last_error()
     assert L.sfe_engine_time_end(eng, C.byref(ms_total2), C.byref(ms_fan)) == 0, L.sfe_last_error()
     assert L.sfe_engine_collect(eng, C.byref(rd2)) == 0, L.sfe_last_error()
+    clocks = sampler.stop()  # sampled from before the timed region to the end of the roofline pass
     # canonical algorithmic bytes = 12 B per synaptic event (fp64 weight + post index)
     # + 16 B per message. The engine stores certified cores' synapses as lossless 4-byte records,
     # so the canonical figure can exceed the peak; `moved` is what the kernel really pulls from HBM.
@@ -252,7 +252,7 @@ def main():
     traffic = ncu_traffic() if args.cores == FULL["cores"] else None
     roofline = {"bound": "hbm", "kernel": "fanout_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_source": "profiles/r1_ncu_full_summary.json (ncu --set full, bytes per launch)",
+                "traffic_source": "profiles/r1_ncu_full_summary.json (ncu --set full, DRAM read+write bytes per launch)",
                 "peak_source": peak_src,
                 "kernel_ms_per_launch": ms_fan.value / max(args.steps, 1),
                 "kernel_share_of_step": ms_fan.value / ms_total2.value if ms_total2.value > 0 else None,
