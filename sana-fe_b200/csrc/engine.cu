@@ -431,6 +431,7 @@ __device__ __forceinline__ int hh_update(double *hh, const uint32_t n_hh, const 
 // TrueNorth instantiation so the common case stays at low register pressure).
 // ---------------------------------------------------------------------------
 constexpr int kSomaThreads = 256;
+constexpr int kSomaPerThread = 2; // neurons per thread: a segment is kSomaThreads * kSomaPerThread neurons
 
 constexpr int kClassCache = 24; // soma parameter classes cached in shared memory (160 B each)
 
@@ -468,32 +469,47 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
     const uint32_t slot = core.ring > 1 ? static_cast<uint32_t>(T % core.ring) : 0u;
 
+    // Every global load of the step is issued before the first use, speculatively: which of them
+    // a neuron needs depends on its class, but waiting for the class first would put three
+    // dependent memory round trips where one suffices (the unused ones cost little: the neuron
+    // phase is latency-bound, not bandwidth-bound). A thread owns kSomaPerThread neurons
+    // (kSomaThreads apart) and has the loads of all of them in flight at once.
+    uint32_t cid_r[kSomaPerThread], a0_r[kSomaPerThread], a1_r[kSomaPerThread], sum_r[kSomaPerThread], cnt_r[kSomaPerThread];
+    double v_r[kSomaPerThread], u_r[kSomaPerThread], bias_r[kSomaPerThread];
+    int refr_r[kSomaPerThread];
+#pragma unroll
+    for (int r = 0; r < kSomaPerThread; ++r)
     {
-        const uint32_t k = core.k0 + threadIdx.x;
-        const bool valid = k < core.neuron_count;
-        int st = SFE_STATUS_IDLE;
-        // Every global load of the step is issued before the first use, speculatively: which of
-        // them a neuron needs depends on its class, but waiting for the class first would put
-        // three dependent memory round trips where one suffices (the unused ones cost little:
-        // the neuron phase is latency-bound, not bandwidth-bound).
-        uint32_t cid = 0u, a0 = 0u, a1 = 0u, raw_sum = 0u, raw_cnt = 0u;
-        double v0 = 0.0, u0 = 0.0, bias0 = 0.0;
-        int refr0 = 0;
-        const uint32_t d = core.dend_base + slot * core.neuron_count + k;
-        if (valid)
+        const uint32_t k = core.k0 + r * kSomaThreads + threadIdx.x;
+        cid_r[r] = a0_r[r] = a1_r[r] = sum_r[r] = cnt_r[r] = 0u;
+        v_r[r] = u_r[r] = bias_r[r] = 0.0;
+        refr_r[r] = 0;
+        if (k < core.neuron_count)
         {
             const uint32_t i = core.neuron_begin + k;
-            cid = __ldg(t.neuron_class + i);
-            a0 = __ldg(t.axon_out_begin + i);
-            a1 = __ldg(t.axon_out_begin + i + 1);
-            v0 = s.v[i];
-            u0 = s.u[i];
-            bias0 = s.bias[i];
-            refr0 = s.refractory[i];
-            raw_sum = s.din32[d];
-            if (core.acc_mode != SFE_ACC_PACKED32) raw_cnt = s.dcnt32[d];
+            const uint32_t d = core.dend_base + slot * core.neuron_count + k;
+            cid_r[r] = __ldg(t.neuron_class + i);
+            a0_r[r] = __ldg(t.axon_out_begin + i);
+            a1_r[r] = __ldg(t.axon_out_begin + i + 1);
+            v_r[r] = s.v[i];
+            u_r[r] = s.u[i];
+            bias_r[r] = s.bias[i];
+            refr_r[r] = s.refractory[i];
+            sum_r[r] = s.din32[d];
+            if (core.acc_mode != SFE_ACC_PACKED32) cnt_r[r] = s.dcnt32[d];
         }
-        __syncthreads(); // class cache filled
+    }
+    __syncthreads(); // class cache filled
+#pragma unroll
+    for (int r = 0; r < kSomaPerThread; ++r)
+    {
+        const uint32_t k = core.k0 + r * kSomaThreads + threadIdx.x;
+        const bool valid = k < core.neuron_count;
+        int st = SFE_STATUS_IDLE;
+        const uint32_t cid = cid_r[r], a0 = a0_r[r], a1 = a1_r[r], raw_sum = sum_r[r], raw_cnt = cnt_r[r];
+        const double v0 = v_r[r], u0 = u_r[r], bias0 = bias_r[r];
+        const int refr0 = refr_r[r];
+        const uint32_t d = core.dend_base + slot * core.neuron_count + k;
         if (valid)
         {
             const uint32_t i = core.neuron_begin + k;
@@ -2099,7 +2115,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         {
             e->h_cores[c].seg_begin = static_cast<uint32_t>(segs.size());
             const CoreDev &d = e->h_cores[c];
-            for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += kSomaThreads)
+            for (uint32_t k0 = 0; k0 < tb->cores[c].neuron_count; k0 += kSomaThreads * kSomaPerThread)
             {
                 SomaSegment g;
                 g.k0 = k0;
