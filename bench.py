@@ -449,14 +449,5 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     return 0
 
 
-def read_graph_records(L, eng, steps, sfe):
-    """Step records written by graph replays (they bypass the host-side step counter)."""
-    import numpy as np
-    buf = np.zeros(steps, dtype=sfe.STEP_DTYPE)
-    got = L.sfe_engine_read_log_tail(eng, buf.ctypes.data, steps)
-    assert got == steps, L.sfe_last_error()
-    return buf
-
-
 if __name__ == "__main__":
     sys.exit(main())
