@@ -1,21 +1,29 @@
 // engine.cu — the per-timestep hot path of SANA-FE as hand-written sm_100a kernels.
 //
 // Replaces SpikingChip::sim_hw_timestep and everything under it (reference
-// src/chip.cpp:1053-1108): one timestep = three kernels on one stream, no host
-// synchronisation inside a run.
+// src/chip.cpp:1053-1108): one timestep = three kernels on one stream, launched with
+// programmatic dependent launch, no host synchronisation inside a run.
 //
 //   soma_kernel      neuron phase           (src/chip.cpp:624-654,710-736,802-834; models.cpp)
-//                    CTA per simulated core; SoA state; warp-ballot spike raster; fired
-//                    neurons raise the inbox bits of their axons; block reductions give
-//                    the per-core counters / energy / generation-delay sum
+//                    CTA per segment of 512 neurons of a core, two neurons per thread, every
+//                    load issued before the first use; SoA state; warp-ballot spike raster;
+//                    fired neurons raise the inbox bits of their axons; warp/block reductions
+//                    give the per-segment counters / energy / generation-delay sum
 //   fanout_kernel    message phase          (src/chip.cpp:656-764,1127-1169; models.cpp:29-131)
-//                    CTA per destination core; walks the inbox bitmask (= message arrival
-//                    order), streams each active axon's CSR segment (fp64 weight + u32
-//                    meta) from HBM and accumulates into shared-memory dendrite
-//                    accumulators (exact fixed point, or ordered fp64 when the weights
-//                    are not provably order-independent)
+//                    persistent CTAs draw work items (inbox slices of destination cores) from
+//                    a ticket; inbox bitmask (= message arrival order) -> CTA-wide list of
+//                    active axons -> their CSR segments streamed from HBM (4-byte lossless
+//                    records through per-warp cp.async rings, or fp64 weight + u32 meta through
+//                    TMA bulk copies) -> shared-memory dendrite accumulators (exact fixed point,
+//                    or ordered fp64 when the weights are not provably order-independent).
+//                    On a partitioned chip the kernel starts with the raster exchange over
+//                    peer memory and gathers its inbox from the exchanged raster.
 //   finalize_kernel  energy, counters, simple timing (src/chip.cpp:1028-1051,1171-1261;
 //                    src/schedule.cpp:61-102); appends one sfe_step_record to the device log
+//
+// Load-time kernels: synth_generate_kernel, certify_kernel (exactness certificate),
+// pack_q4_kernel (4-byte records). The host half of the engine (tables, work items, streams,
+// the C ABI of include/sanafe_b200.h, NCCL / CUDA-IPC plumbing) follows the kernels.
 //
 // All arithmetic that decides a spike is IEEE fp64 without FMA contraction
 // (compiled with -fmad=false), so rasters are bit-identical to the reference.
