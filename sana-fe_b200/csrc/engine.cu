@@ -128,7 +128,7 @@ struct DevTables
     uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
     // fused finalize: cores with work items fold themselves; the others are folded at the end
     const uint32_t *soma_only_list;
-    uint32_t n_soma_only, n_fold_cores, fused_finalize;
+    uint32_t n_soma_only, n_fold_cores, fused_finalize, n_soma_segments;
     double sync_delay;
 };
 
@@ -174,6 +174,9 @@ struct DevState
     // Steps enqueued on this engine so far (host-side counter, passed by value with every launch):
     // parity / flag value of the raster exchange and base of the monotonic work-ticket counter.
     unsigned long long step_seq;
+    long long steps_done;   // timesteps simulated before this step (host counter; T = steps_done + 1)
+    uint32_t fold_parity;   // parity of the step the stand-alone / piggy-backed fold works on
+    uint32_t pad_fold;
     uint32_t *work;        // ticket counter of the message phase: never reset, see fanout_kernel
     uint32_t *final_ticket;
     uint32_t *core_done;    // [n_cores] work items of the core finished in this step (fused finalize)
@@ -190,6 +193,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// Fire-and-forget OR into global memory. Written in PTX: when a kernel also contains atomics whose
+// result is used, the compiler may emit the returning form (ATOMG) for plain atomicOr calls too,
+// and a neuron-phase thread would then wait for every inbox bit it raises.
+__device__ __forceinline__ void red_or(uint32_t *p, const uint32_t v)
+{
+    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(uint32_t *p, const uint32_t v)
+{
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p)
 {
@@ -433,6 +447,248 @@ __device__ __forceinline__ int hh_update(double *hh, const uint32_t n_hh, const 
 }
 
 // ---------------------------------------------------------------------------
+// K5: energy, counters, simple timing model. One thread per active core; the last
+// CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
+// step record, so every floating-point sum is formed in the same order on every run.
+// ---------------------------------------------------------------------------
+constexpr int kFinalThreads = 256;
+
+struct StepPartial
+{
+    unsigned long long fired, updated, packets, hops, events;
+    double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
+};
+
+__device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
+{
+    StepPartial r;
+    r.fired = __ldcg(&p->fired);
+    r.updated = __ldcg(&p->updated);
+    r.packets = __ldcg(&p->packets);
+    r.hops = __ldcg(&p->hops);
+    r.events = __ldcg(&p->events);
+    r.syn_e = __ldcg(&p->syn_e);
+    r.den_e = __ldcg(&p->den_e);
+    r.soma_e = __ldcg(&p->soma_e);
+    r.net_e = __ldcg(&p->net_e);
+    r.max_gen = __ldcg(&p->max_gen);
+    r.max_proc = __ldcg(&p->max_proc);
+    return r;
+}
+
+__device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &x)
+{
+    b.fired += x.fired;
+    b.updated += x.updated;
+    b.packets += x.packets;
+    b.hops += x.hops;
+    b.events += x.events;
+    b.syn_e += x.syn_e;
+    b.den_e += x.den_e;
+    b.soma_e += x.soma_e;
+    b.net_e += x.net_e;
+    b.max_gen = fmax(b.max_gen, x.max_gen);
+    b.max_proc = fmax(b.max_proc, x.max_proc);
+}
+
+__device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly: a fixed order
+{
+    p.fired = warp_sum(p.fired);
+    p.updated = warp_sum(p.updated);
+    p.packets = warp_sum(p.packets);
+    p.hops = warp_sum(p.hops);
+    p.events = warp_sum(p.events);
+    p.syn_e = warp_sum(p.syn_e);
+    p.den_e = warp_sum(p.den_e);
+    p.soma_e = warp_sum(p.soma_e);
+    p.net_e = warp_sum(p.net_e);
+    p.max_gen = warp_max(p.max_gen);
+    p.max_proc = warp_max(p.max_proc);
+    return p;
+}
+
+// Step statistics of one core, computed by a full warp: the lanes fetch the core's segment /
+// work-item statistics in parallel (one round trip instead of seg_count + item_count dependent
+// ones) and fold them with a butterfly; every sum is formed in the same order on every run.
+// The result is valid in every lane. L2 loads: the statistics may come from other CTAs of the
+// running kernel (fused finalize).
+__device__ __forceinline__ StepPartial fold_core(
+        const DevTables &t, const DevState &s, const uint32_t ci, const int lane, const uint32_t parity)
+{
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const CoreDev &core = t.cores[ci];
+    StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+    for (uint32_t g = lane; g < core.seg_count; g += 32)
+    {
+        const StatsN *x = s.stats_n + static_cast<size_t>(parity) * t.n_soma_segments + core.seg_begin + g;
+        n.updated += __ldcg(&x->updated);
+        n.fired += __ldcg(&x->fired);
+        n.packets += __ldcg(&x->packets);
+        n.soma_e += __ldcg(&x->soma_e);
+        n.dend_e += __ldcg(&x->dend_e);
+        n.gen_sum += __ldcg(&x->gen_sum);
+    }
+    StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+    for (uint32_t g = lane; g < core.item_count; g += 32)
+    {
+        const StatsM *x = s.stats_m + core.item_begin + g;
+        m.msgs += __ldcg(&x->msgs);
+        m.events += __ldcg(&x->events);
+        m.hop_e += __ldcg(&x->hop_e);
+        m.hop_w += __ldcg(&x->hop_w);
+        m.hop_n += __ldcg(&x->hop_n);
+        m.hop_s += __ldcg(&x->hop_s);
+        m.syn_e += __ldcg(&x->syn_e);
+        m.den_e += __ldcg(&x->den_e);
+        m.proc += __ldcg(&x->proc);
+    }
+    n.updated = warp_sum(n.updated);
+    n.fired = warp_sum(n.fired);
+    n.packets = warp_sum(n.packets);
+    n.soma_e = warp_sum(n.soma_e);
+    n.dend_e = warp_sum(n.dend_e);
+    n.gen_sum = warp_sum(n.gen_sum);
+    m.msgs = warp_sum(m.msgs);
+    m.events = warp_sum(m.events);
+    m.hop_e = warp_sum(m.hop_e);
+    m.hop_w = warp_sum(m.hop_w);
+    m.hop_n = warp_sum(m.hop_n);
+    m.hop_s = warp_sum(m.hop_s);
+    m.syn_e = warp_sum(m.syn_e);
+    m.den_e = warp_sum(m.den_e);
+    m.proc = warp_sum(m.proc);
+    n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
+    p.fired = n.fired;
+    p.updated = n.updated;
+    p.packets = n.packets;
+    p.hops = m.hop_e + m.hop_w + m.hop_n + m.hop_s;
+    p.events = m.events;
+    p.syn_e = m.syn_e;
+    p.den_e = n.dend_e + m.den_e;
+    p.soma_e = n.soma_e;
+    // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
+    double hop = static_cast<double>(m.hop_e) * core.e_east;
+    hop += static_cast<double>(m.hop_w) * core.e_west;
+    hop += static_cast<double>(m.hop_s) * core.e_south;
+    hop += static_cast<double>(m.hop_n) * core.e_north;
+    p.net_e = hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
+    p.max_gen = n.gen_sum;
+    p.max_proc = m.proc;
+    return p;
+}
+
+// Appends the step record (one thread). schedule_messages_timestep_simple  src/schedule.cpp:61-102
+__device__ __forceinline__ void append_step_record(const DevTables &t, const DevState &s, const StepPartial &b)
+{
+    sfe_step_record r;
+    r.neurons_fired = static_cast<long long>(b.fired);
+    r.neurons_updated = static_cast<long long>(b.updated);
+    r.packets_sent = static_cast<long long>(b.packets);
+    r.total_hops = static_cast<long long>(b.hops);
+    r.spike_count = static_cast<long long>(b.events);
+    r.synapse_energy = b.syn_e;
+    r.dendrite_energy = b.den_e;
+    r.soma_energy = b.soma_e;
+    r.network_energy = b.net_e;
+    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
+    r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
+    const long long cursor = s.step[1];
+    s.log[cursor % s.log_cap] = r;
+    s.step[1] = cursor + 1;
+    s.step[0] = s.step[0] + 1;
+}
+
+// Chip-wide fold by one warp: cores without work items first, then all per-core partials.
+__device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const int lane)
+{
+    for (uint32_t k = 0; k < t.n_soma_only; ++k)
+    {
+        const uint32_t c2 = t.soma_only_list[k];
+        const StepPartial q = fold_core(t, s, c2, lane, static_cast<uint32_t>(s.step_seq & 1ull));
+        if (lane == 0) s.core_partials[t.cores[c2].active_idx] = q;
+    }
+    __syncwarp();
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&s.core_partials[k]));
+    b = warp_fold(b);
+    if (lane == 0) append_step_record(t, s, b);
+}
+
+// Fused finalize (engines whose message phase has work items): called by warp 0 of a CTA after it
+// has published the statistics of a work item of core `ci`. The CTA that completes a core's last
+// item folds the core; the CTA that folds the last core folds the chip and appends the step
+// record - no separate kernel, and the per-core folds overlap the other CTAs' streaming.
+__device__ __forceinline__ void fused_finalize(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
+{
+    uint32_t done = 0u;
+    if (lane == 0)
+    {
+        __threadfence(); // this item's statistics before the count
+        done = atomicAdd(&s.core_done[ci], 1u) + 1u;
+    }
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done != t.cores[ci].item_count) return;
+    __threadfence();
+    const StepPartial p = fold_core(t, s, ci, lane, static_cast<uint32_t>(s.step_seq & 1ull));
+    uint32_t folded = 0u;
+    if (lane == 0)
+    {
+        s.core_partials[t.cores[ci].active_idx] = p;
+        s.core_done[ci] = 0u; // ready for the next step
+        __threadfence();
+        folded = atomicAdd(s.cores_folded, 1u) + 1u;
+    }
+    folded = __shfl_sync(0xffffffffu, folded, 0);
+    if (folded != t.n_fold_cores) return;
+    __threadfence();
+    if (lane == 0) *s.cores_folded = 0u;
+    fold_chip(t, s, lane);
+}
+
+// The stand-alone form of the fold: one WARP per active core, `nblocks` CTAs numbered `block`.
+// Runs as its own kernel (finalize_kernel) or as extra CTAs of the NEXT step's neuron-phase kernel
+// (the step's statistics are complete by then and nothing on the critical path waits for the fold).
+// `scratch`: (kFinalThreads / 32) StepPartial + one uint32 of shared memory, supplied by the caller
+// (the neuron-phase kernel lends its class cache: an extra static array would push three of its
+// CTAs past the 16 KB shared-memory carve-out and cost it a third of its occupancy).
+constexpr size_t kFinalScratchBytes = (kFinalThreads / 32) * sizeof(StepPartial) + 16;
+__device__ __forceinline__ void finalize_body(
+        const DevTables &t, const DevState &s, const uint32_t block, const uint32_t nblocks, unsigned char *scratch)
+{
+    StepPartial *warp_part = reinterpret_cast<StepPartial *>(scratch);
+    uint32_t &ticket_s = *reinterpret_cast<uint32_t *>(scratch + (kFinalThreads / 32) * sizeof(StepPartial));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const uint32_t a = block * (kFinalThreads / 32) + warp;
+    if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane, s.fold_parity);
+    if (lane == 0) warp_part[warp] = p;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        StepPartial b = warp_part[0];
+        for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
+        s.partials[block] = b;
+        __threadfence();
+        ticket_s = atomicAdd(s.final_ticket, 1u);
+    }
+    __syncthreads();
+    if (ticket_s != nblocks - 1) return;
+    // ---- last CTA: fold the per-CTA partials and append the step record ------------------
+    __threadfence();
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (uint32_t k = threadIdx.x; k < nblocks; k += kFinalThreads) fold_partial(b, load_partial(&s.partials[k]));
+    b = warp_fold(b);
+    __syncthreads(); // warp_part is reused
+    if (lane == 0) warp_part[warp] = b;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    b = warp_part[0];
+    for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
+    append_step_record(t, s, b);
+    *s.final_ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------
 // K1: neuron phase. One CTA per segment of kSomaThreads consecutive neurons of a core
 // (one neuron per thread: every load of the step is issued at once).
 // kExotic = the chip maps input / Hodgkin-Huxley somas (kept out of the LIF /
@@ -459,6 +715,16 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
 {
     __shared__ sfe_soma_class class_cache[kClassCache];
     griddep_launch_dependents();
+    if (blockIdx.x >= t.n_soma_segments)
+    {
+        // extra CTAs: the fold of the PREVIOUS step (its statistics are complete once the previous
+        // message phase has finished), off the critical path of this step
+        griddep_wait();
+        static_assert(sizeof(class_cache) >= kFinalScratchBytes, "the class cache doubles as the fold's scratch");
+        finalize_body(t, s, blockIdx.x - t.n_soma_segments, gridDim.x - t.n_soma_segments,
+                reinterpret_cast<unsigned char *>(class_cache));
+        return;
+    }
     const SomaSegment core = t.soma_segments[blockIdx.x];
     const int lane = threadIdx.x & 31;
     const bool classes_cached = t.n_soma_classes <= kClassCache;
@@ -470,7 +736,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
     }
     griddep_wait(); // everything above reads load-time tables only
-    const long long steps_done = s.step[0];
+    const long long steps_done = s.steps_done;
     const long long T = steps_done + 1;
 
     uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
@@ -626,7 +892,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                     if (base + x < a1) bit[x] = __ldg(t.axon_out_bit + base + x);
 #pragma unroll
                 for (int x = 0; x < 8; ++x)
-                    if (base + x < a1) atomicOr(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
+                    if (base + x < a1) red_or(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
             }
         }
     }
@@ -664,7 +930,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         }
         // gen_sum: sum of generation delays incl. the trailing placeholder message
         // (src/chip.cpp:640-652, 821-823; src/schedule.cpp:81)
-        s.stats_n[blockIdx.x] = out;
+        s.stats_n[(s.step_seq & 1ull) * t.n_soma_segments + blockIdx.x] = out; // double-buffered by step parity
     }
 }
 
@@ -813,204 +1079,6 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
                  : "memory");
 }
 
-// ---------------------------------------------------------------------------
-// K5: energy, counters, simple timing model. One thread per active core; the last
-// CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
-// step record, so every floating-point sum is formed in the same order on every run.
-// ---------------------------------------------------------------------------
-constexpr int kFinalThreads = 256;
-
-struct StepPartial
-{
-    unsigned long long fired, updated, packets, hops, events;
-    double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
-};
-
-__device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
-{
-    StepPartial r;
-    r.fired = __ldcg(&p->fired);
-    r.updated = __ldcg(&p->updated);
-    r.packets = __ldcg(&p->packets);
-    r.hops = __ldcg(&p->hops);
-    r.events = __ldcg(&p->events);
-    r.syn_e = __ldcg(&p->syn_e);
-    r.den_e = __ldcg(&p->den_e);
-    r.soma_e = __ldcg(&p->soma_e);
-    r.net_e = __ldcg(&p->net_e);
-    r.max_gen = __ldcg(&p->max_gen);
-    r.max_proc = __ldcg(&p->max_proc);
-    return r;
-}
-
-__device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &x)
-{
-    b.fired += x.fired;
-    b.updated += x.updated;
-    b.packets += x.packets;
-    b.hops += x.hops;
-    b.events += x.events;
-    b.syn_e += x.syn_e;
-    b.den_e += x.den_e;
-    b.soma_e += x.soma_e;
-    b.net_e += x.net_e;
-    b.max_gen = fmax(b.max_gen, x.max_gen);
-    b.max_proc = fmax(b.max_proc, x.max_proc);
-}
-
-__device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly: a fixed order
-{
-    p.fired = warp_sum(p.fired);
-    p.updated = warp_sum(p.updated);
-    p.packets = warp_sum(p.packets);
-    p.hops = warp_sum(p.hops);
-    p.events = warp_sum(p.events);
-    p.syn_e = warp_sum(p.syn_e);
-    p.den_e = warp_sum(p.den_e);
-    p.soma_e = warp_sum(p.soma_e);
-    p.net_e = warp_sum(p.net_e);
-    p.max_gen = warp_max(p.max_gen);
-    p.max_proc = warp_max(p.max_proc);
-    return p;
-}
-
-// Step statistics of one core, computed by a full warp: the lanes fetch the core's segment /
-// work-item statistics in parallel (one round trip instead of seg_count + item_count dependent
-// ones) and fold them with a butterfly; every sum is formed in the same order on every run.
-// The result is valid in every lane. L2 loads: the statistics may come from other CTAs of the
-// running kernel (fused finalize).
-__device__ __forceinline__ StepPartial fold_core(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
-{
-    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const CoreDev &core = t.cores[ci];
-    StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
-    for (uint32_t g = lane; g < core.seg_count; g += 32)
-    {
-        const StatsN *x = s.stats_n + core.seg_begin + g;
-        n.updated += __ldcg(&x->updated);
-        n.fired += __ldcg(&x->fired);
-        n.packets += __ldcg(&x->packets);
-        n.soma_e += __ldcg(&x->soma_e);
-        n.dend_e += __ldcg(&x->dend_e);
-        n.gen_sum += __ldcg(&x->gen_sum);
-    }
-    StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
-    for (uint32_t g = lane; g < core.item_count; g += 32)
-    {
-        const StatsM *x = s.stats_m + core.item_begin + g;
-        m.msgs += __ldcg(&x->msgs);
-        m.events += __ldcg(&x->events);
-        m.hop_e += __ldcg(&x->hop_e);
-        m.hop_w += __ldcg(&x->hop_w);
-        m.hop_n += __ldcg(&x->hop_n);
-        m.hop_s += __ldcg(&x->hop_s);
-        m.syn_e += __ldcg(&x->syn_e);
-        m.den_e += __ldcg(&x->den_e);
-        m.proc += __ldcg(&x->proc);
-    }
-    n.updated = warp_sum(n.updated);
-    n.fired = warp_sum(n.fired);
-    n.packets = warp_sum(n.packets);
-    n.soma_e = warp_sum(n.soma_e);
-    n.dend_e = warp_sum(n.dend_e);
-    n.gen_sum = warp_sum(n.gen_sum);
-    m.msgs = warp_sum(m.msgs);
-    m.events = warp_sum(m.events);
-    m.hop_e = warp_sum(m.hop_e);
-    m.hop_w = warp_sum(m.hop_w);
-    m.hop_n = warp_sum(m.hop_n);
-    m.hop_s = warp_sum(m.hop_s);
-    m.syn_e = warp_sum(m.syn_e);
-    m.den_e = warp_sum(m.den_e);
-    m.proc = warp_sum(m.proc);
-    n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
-    p.fired = n.fired;
-    p.updated = n.updated;
-    p.packets = n.packets;
-    p.hops = m.hop_e + m.hop_w + m.hop_n + m.hop_s;
-    p.events = m.events;
-    p.syn_e = m.syn_e;
-    p.den_e = n.dend_e + m.den_e;
-    p.soma_e = n.soma_e;
-    // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
-    double hop = static_cast<double>(m.hop_e) * core.e_east;
-    hop += static_cast<double>(m.hop_w) * core.e_west;
-    hop += static_cast<double>(m.hop_s) * core.e_south;
-    hop += static_cast<double>(m.hop_n) * core.e_north;
-    p.net_e = hop + static_cast<double>(m.msgs) * core.e_axon_in + static_cast<double>(n.packets) * core.e_axon_out;
-    p.max_gen = n.gen_sum;
-    p.max_proc = m.proc;
-    return p;
-}
-
-// Appends the step record (one thread). schedule_messages_timestep_simple  src/schedule.cpp:61-102
-__device__ __forceinline__ void append_step_record(const DevTables &t, const DevState &s, const StepPartial &b)
-{
-    sfe_step_record r;
-    r.neurons_fired = static_cast<long long>(b.fired);
-    r.neurons_updated = static_cast<long long>(b.updated);
-    r.packets_sent = static_cast<long long>(b.packets);
-    r.total_hops = static_cast<long long>(b.hops);
-    r.spike_count = static_cast<long long>(b.events);
-    r.synapse_energy = b.syn_e;
-    r.dendrite_energy = b.den_e;
-    r.soma_energy = b.soma_e;
-    r.network_energy = b.net_e;
-    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
-    r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
-    const long long cursor = s.step[1];
-    s.log[cursor % s.log_cap] = r;
-    s.step[1] = cursor + 1;
-    s.step[0] = s.step[0] + 1;
-}
-
-// Chip-wide fold by one warp: cores without work items first, then all per-core partials.
-__device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const int lane)
-{
-    for (uint32_t k = 0; k < t.n_soma_only; ++k)
-    {
-        const uint32_t c2 = t.soma_only_list[k];
-        const StepPartial q = fold_core(t, s, c2, lane);
-        if (lane == 0) s.core_partials[t.cores[c2].active_idx] = q;
-    }
-    __syncwarp();
-    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&s.core_partials[k]));
-    b = warp_fold(b);
-    if (lane == 0) append_step_record(t, s, b);
-}
-
-// Fused finalize (engines whose message phase has work items): called by warp 0 of a CTA after it
-// has published the statistics of a work item of core `ci`. The CTA that completes a core's last
-// item folds the core; the CTA that folds the last core folds the chip and appends the step
-// record - no separate kernel, and the per-core folds overlap the other CTAs' streaming.
-__device__ __forceinline__ void fused_finalize(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
-{
-    uint32_t done = 0u;
-    if (lane == 0)
-    {
-        __threadfence(); // this item's statistics before the count
-        done = atomicAdd(&s.core_done[ci], 1u) + 1u;
-    }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != t.cores[ci].item_count) return;
-    __threadfence();
-    const StepPartial p = fold_core(t, s, ci, lane);
-    uint32_t folded = 0u;
-    if (lane == 0)
-    {
-        s.core_partials[t.cores[ci].active_idx] = p;
-        s.core_done[ci] = 0u; // ready for the next step
-        __threadfence();
-        folded = atomicAdd(s.cores_folded, 1u) + 1u;
-    }
-    folded = __shfl_sync(0xffffffffu, folded, 0);
-    if (folded != t.n_fold_cores) return;
-    __threadfence();
-    if (lane == 0) *s.cores_folded = 0u;
-    fold_chip(t, s, lane);
-}
-
 // Streaming variants of the exact-mode message phase (selected at engine creation,
 // SFE_FANOUT=scalar|vector|tma):
 //   kStreamScalar  8 scalar loads per 128-synapse chunk, next chunk's loads issued
@@ -1058,7 +1126,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
     (void) tma_phase;
     griddep_wait(); // everything above reads load-time tables / initialises shared memory only
-    const long long T = s.step[0] + 1;
+    const long long T = s.steps_done + 1;
 
     // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory
     // exchange the collective is fused into this kernel: CTA 0 pushes this rank's raster slice
@@ -1472,15 +1540,15 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
         if (acc_mode == SFE_ACC_PACKED32)
         {
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
-                if (acc32[x] != 0u) atomicAdd(&s.din32[base + x], acc32[x]);
+                if (acc32[x] != 0u) red_add(&s.din32[base + x], acc32[x]);
         }
         else if (acc_mode == SFE_ACC_DUAL32)
         {
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
                 if (cnt32[x] != 0u)
                 {
-                    atomicAdd(&s.din32[base + x], acc32[x]);
-                    atomicAdd(&s.dcnt32[base + x], cnt32[x]);
+                    red_add(&s.din32[base + x], acc32[x]);
+                    red_add(&s.dcnt32[base + x], cnt32[x]);
                 }
         }
         else
@@ -1542,39 +1610,10 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
 // Stand-alone finalize (engines without message-phase work items): one WARP per active core.
 __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
 {
-    __shared__ StepPartial warp_part[kFinalThreads / 32];
-    __shared__ uint32_t ticket_s;
+    __shared__ __align__(16) unsigned char scratch[kFinalScratchBytes];
     griddep_launch_dependents();
     griddep_wait();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const uint32_t a = blockIdx.x * (kFinalThreads / 32) + warp;
-    if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane);
-    if (lane == 0) warp_part[warp] = p;
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        StepPartial b = warp_part[0];
-        for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
-        s.partials[blockIdx.x] = b;
-        __threadfence();
-        ticket_s = atomicAdd(s.final_ticket, 1u);
-    }
-    __syncthreads();
-    if (ticket_s != gridDim.x - 1) return;
-    // ---- last CTA: fold the per-CTA partials and append the step record ------------------
-    __threadfence();
-    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (uint32_t k = threadIdx.x; k < gridDim.x; k += kFinalThreads) fold_partial(b, load_partial(&s.partials[k]));
-    b = warp_fold(b);
-    __syncthreads(); // warp_part is reused
-    if (lane == 0) warp_part[warp] = b;
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    b = warp_part[0];
-    for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
-    append_step_record(t, s, b);
-    *s.final_ticket = 0u;
+    finalize_body(t, s, blockIdx.x, gridDim.x, scratch);
 }
 
 // ---------------------------------------------------------------------------
@@ -1774,6 +1813,10 @@ struct sfe_engine
     // per-launch timing of the message-phase kernel between time_begin/time_end
     bool timing{false};
     bool time_launches{true};
+    // The fold of a step (finalize) rides on the next step's neuron-phase kernel; the last step of
+    // a batch is folded by the stand-alone kernel when somebody needs the records (flush_fold).
+    bool piggyback{true}, pending_fold{false};
+    uint32_t pending_parity{0};
     // whole-vector bias uploads are double-buffered and travel on their own stream, so that the
     // upload for the next step overlaps the kernels of the current one
     double *bias_buf[2] = {nullptr, nullptr};
@@ -2140,6 +2183,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             e->h_cores[c].seg_count = static_cast<uint32_t>(segs.size()) - e->h_cores[c].seg_begin;
         }
         e->n_segments = static_cast<uint32_t>(segs.size());
+        e->t.n_soma_segments = e->n_segments;
         if (e->upload(&e->t.soma_segments, segs.data(), segs.size()) != 0) return -1;
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
@@ -2166,7 +2210,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.din64, e->ordered_any ? dend_cells : 1) != 0) return -1;
     if (e->alloc(&e->s.hh, 5 * static_cast<size_t>(tb->n_hh)) != 0) return -1;
     e->s.n_hh = tb->n_hh;
-    if (e->alloc(&e->s.stats_n, e->n_segments) != 0) return -1;
+    if (e->alloc(&e->s.stats_n, 2 * static_cast<size_t>(e->n_segments)) != 0) return -1; // double-buffered by step parity
     e->log_cap = 4096;
     e->s.log_cap = e->log_cap;
     if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
@@ -2307,6 +2351,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         {
             const char *fused = std::getenv("SFE_FUSED_FINALIZE");
             e->t.fused_finalize = (fused != nullptr && std::atoi(fused) != 0) ? 1u : 0u;
+            const char *piggy = std::getenv("SFE_PIGGYBACK_FINALIZE"); // 0: a finalize kernel per step
+            e->piggyback = piggy == nullptr || std::atoi(piggy) != 0;
         }
     }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
@@ -2407,12 +2453,31 @@ static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned
 
 static void launch_soma(sfe_engine *e)
 {
-    if (e->exotic) launch_step_kernel(e, soma_kernel<true>, e->n_segments, kSomaThreads, 0, e->t, e->s);
-    else launch_step_kernel(e, soma_kernel<false>, e->n_segments, kSomaThreads, 0, e->t, e->s);
+    e->s.steps_done = e->total_timesteps;
+    unsigned grid = e->n_segments;
+    if (e->pending_fold)
+    {
+        grid += e->final_grid; // extra CTAs fold the previous step
+        e->s.fold_parity = e->pending_parity;
+        e->pending_fold = false;
+    }
+    if (e->exotic) launch_step_kernel(e, soma_kernel<true>, grid, kSomaThreads, 0, e->t, e->s);
+    else launch_step_kernel(e, soma_kernel<false>, grid, kSomaThreads, 0, e->t, e->s);
+}
+
+// The stand-alone fold of a step whose records are needed now (end of a batch, collect, reset...).
+static void flush_fold(sfe_engine *e)
+{
+    if (!e->pending_fold) return;
+    e->s.fold_parity = e->pending_parity;
+    launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
+    ++e->launches;
+    e->pending_fold = false;
 }
 
 static void launch_fanout(sfe_engine *e)
 {
+    e->s.steps_done = e->total_timesteps;
     const unsigned grid = e->fanout_grid;
     const bool fused = e->t.fused_finalize != 0u;
     if (e->fanout_variant == kStreamQ4)
@@ -2435,8 +2500,19 @@ static void launch_fanout(sfe_engine *e)
 static void launch_finalize(sfe_engine *e)
 {
     const bool fanout_ran = !e->fanout_list.empty() || e->p2p_on;
-    if (!(e->t.fused_finalize != 0u && fanout_ran))
+    if (e->t.fused_finalize != 0u && fanout_ran)
     {
+        // the message phase folded the step itself
+    }
+    else if (e->piggyback && !e->soma_list.empty())
+    {
+        // folded by extra CTAs of the next neuron-phase kernel (or by flush_fold)
+        e->pending_fold = true;
+        e->pending_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
+    }
+    else
+    {
+        e->s.fold_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
         launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
         ++e->launches;
     }
@@ -2522,6 +2598,7 @@ static int collect_records(sfe_engine *e, std::vector<sfe_step_record> &out)
 {
     const int64_t pending = e->total_timesteps - e->log_read;
     out.resize(static_cast<size_t>(pending));
+    flush_fold(e);
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     int64_t done = 0;
     while (done < pending)
@@ -2666,6 +2743,7 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
     // SpikingChip::reset  src/chip.cpp:576-600: pipeline buffers and model state are
     // zeroed (LIF: u and v only; HH: V, m, n, h); timestep counters keep running
     SFE_CUDA(cudaSetDevice(e->device));
+    flush_fold(e);
     SFE_CUDA(cudaMemsetAsync(e->s.v, 0, e->n_neurons * sizeof(double), e->stream));
     SFE_CUDA(cudaMemsetAsync(e->s.u, 0, e->n_neurons * sizeof(double), e->stream));
     SFE_CUDA(cudaMemsetAsync(e->s.status, 0, e->n_neurons, e->stream));
@@ -2837,6 +2915,7 @@ extern "C" int sfe_engine_time_begin(sfe_engine *e)
 extern "C" int sfe_engine_time_end(sfe_engine *e, float *ms_total, float *ms_fanout)
 {
     SFE_CUDA(cudaSetDevice(e->device));
+    flush_fold(e); // the timed region ends with the last step's record written
     SFE_CUDA(cudaEventRecord(e->ev_end, e->stream));
     SFE_CUDA(cudaEventSynchronize(e->ev_end));
     float ms = 0.f;
@@ -3052,6 +3131,7 @@ extern "C" int sfe_engine_partition_info(const sfe_engine *e, uint32_t *rank, ui
 extern "C" int sfe_engine_synchronize(sfe_engine *e)
 {
     SFE_CUDA(cudaSetDevice(e->device));
+    flush_fold(e);
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -3099,6 +3179,7 @@ extern "C" void sfe_host_free(void *p)
 extern "C" int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n)
 {
     if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    flush_fold(e);
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) return -1;
     long long counters[2] = {0, 0};
     if (cudaMemcpy(counters, e->s.step, sizeof(counters), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
