@@ -349,6 +349,8 @@ typedef struct sfe_chip sfe_chip;
 /* load_arch / load_net  (src/arch.cpp:106-117, src/network.cpp:194-222) */
 sfe_arch *sfe_arch_load_yaml(const char *path);
 sfe_net *sfe_net_load_yaml(const char *path, sfe_arch *arch);
+/* the legacy netlist format (`sim -n`; load_net(..., use_netlist_format=true), src/netlist.cpp:38-617) */
+sfe_net *sfe_net_load_netlist(const char *path, sfe_arch *arch);
 /* flat JSON-lines description (oracle/yaml_to_flat.py); returns both objects */
 int sfe_load_flat(const char *path, sfe_arch **arch, sfe_net **net);
 void sfe_arch_free(sfe_arch *a);

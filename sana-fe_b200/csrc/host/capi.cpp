@@ -122,6 +122,19 @@ extern "C" sfe_net *sfe_net_load_yaml(const char *path, sfe_arch *arch)
             nullptr);
 }
 
+// load_net(path, arch, use_netlist_format = true)  src/network.cpp:194-222, src/netlist.cpp:38-69
+extern "C" sfe_net *sfe_net_load_netlist(const char *path, sfe_arch *arch)
+{
+    return guarded(
+            [&]() -> sfe_net * {
+                if (arch == nullptr || !arch->arch) throw std::invalid_argument("sfe_net_load_netlist: null architecture");
+                auto n = std::make_unique<sfe_net>();
+                n->net = sfe::load_net_netlist(path, *arch->arch);
+                return n.release();
+            },
+            nullptr);
+}
+
 extern "C" int sfe_load_flat(const char *path, sfe_arch **arch, sfe_net **net)
 {
     return guarded(

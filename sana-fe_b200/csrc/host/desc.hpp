@@ -356,6 +356,7 @@ void load_flat_file(const std::string &path, std::unique_ptr<Architecture> &arch
         std::unique_ptr<SpikingNetwork> &net, std::optional<SynthRequest> &synth);
 std::unique_ptr<Architecture> load_arch_yaml(const std::string &path);
 std::unique_ptr<SpikingNetwork> load_net_yaml(const std::string &path, Architecture &arch);
+std::unique_ptr<SpikingNetwork> load_net_netlist(const std::string &path, Architecture &arch); // legacy format
 
 } // namespace sfe
 #endif

@@ -290,9 +290,8 @@ PYBIND11_MODULE(sanafecpp_b200, m)
     m.def(
             "load_net",
             [](const std::string &path, const std::shared_ptr<ArchHandle> &arch, bool use_netlist_format) {
-                if (use_netlist_format) throw std::runtime_error("legacy netlist format is not implemented yet");
                 auto n = std::make_shared<NetHandle>();
-                n->h = sfe_net_load_yaml(path.c_str(), arch->h);
+                n->h = use_netlist_format ? sfe_net_load_netlist(path.c_str(), arch->h) : sfe_net_load_yaml(path.c_str(), arch->h);
                 if (n->h == nullptr) raise_last();
                 return n;
             },

@@ -86,14 +86,13 @@ int main(int argc, char *argv[])
     try { timesteps = std::stol(args[idx + 2]); }
     catch (const std::exception &) { std::fprintf(stderr, "Error: invalid argument thrown: Error: Invalid time-step format: %s\n", args[idx + 2].c_str()); return 1; }
     if (timesteps <= 0) { std::fprintf(stderr, "Error: invalid argument thrown: Time-steps must be > 0\n"); return 1; }
-    if (flags.use_netlist) fail("the legacy netlist format (-n) is not supported by this build; use the YAML format");
     if (flags.record_neuron_state) fail("model-defined neuron traces (-x) are not supported by this build");
 
     std::printf("Running SANA-FE simulation (B200 engine, ABI %d)\n", sfe_abi_version());
     sfe_arch *arch = sfe_arch_load_yaml(arch_file.c_str());
     if (arch == nullptr) { std::fprintf(stderr, "%s\n", sfe_last_error()); return 1; }
     std::printf("Architecture initialized.\n");
-    sfe_net *net = sfe_net_load_yaml(net_file.c_str(), arch);
+    sfe_net *net = flags.use_netlist ? sfe_net_load_netlist(net_file.c_str(), arch) : sfe_net_load_yaml(net_file.c_str(), arch);
     if (net == nullptr) { std::fprintf(stderr, "%s\n", sfe_last_error()); return 1; }
     std::printf("Network initialized.\n");
     sfe_chip *chip = sfe_chip_create(arch, 0);

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <cerrno>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
 
 #include "desc.hpp"
 #include "yaml.hpp"
@@ -640,6 +642,203 @@ std::unique_ptr<SpikingNetwork> load_net_yaml(const std::string &path, Architect
                 n.map_to_core(arch.tiles[tile_id].cores[core_off]);
             }
         }
+    }
+    return net;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Legacy netlist front-end (`sim -n`, sanafe.load_net(path, arch, use_netlist_format=True)):
+// one entry per line, `g <count> <attrs>` / `n <group>.<neuron> <attrs>` / `e <g>.<n>-><g>.<n> <attrs>`
+// / `& <g>.<n>@<tile>.<core>`; attributes are whitespace-separated key=value fields or one embedded
+// YAML flow collection. Restates src/netlist.cpp:38-617 (reader only).
+// ---------------------------------------------------------------------------------------------
+namespace
+{
+std::vector<std::string> netlist_fields(const std::string &line) // netlist_get_fields  src/netlist.cpp:71-94
+{
+    std::vector<std::string> fields;
+    const char *delim = " \t\r\n";
+    size_t start = line.find_first_not_of(delim);
+    while (start != std::string::npos)
+    {
+        const size_t end = line.find_first_of(delim, start);
+        fields.push_back(line.substr(start, end == std::string::npos ? std::string::npos : end - start));
+        start = end == std::string::npos ? std::string::npos : line.find_first_not_of(delim, end);
+    }
+    return fields;
+}
+
+size_t netlist_to_index(const std::string &s) // field_to_int  src/netlist.cpp (std::from_chars on the whole field)
+{
+    size_t pos = 0;
+    unsigned long long v = 0;
+    try
+    {
+        v = std::stoull(s, &pos);
+    }
+    catch (const std::exception &)
+    {
+        pos = 0;
+    }
+    if (pos != s.size() || s.empty()) throw std::runtime_error("Error: Invalid integer field in netlist (" + s + ")");
+    return static_cast<size_t>(v);
+}
+
+// netlist_parse_attribute_value  src/netlist.cpp:286-320: int, then double, then bool (0/1 only,
+// i.e. never reached), then string - each must consume the whole value
+Attr netlist_value(const std::string &text)
+{
+    {
+        std::stringstream ss(text);
+        int v = 0;
+        if ((ss >> v) && ss.eof()) return Attr::of(v);
+    }
+    {
+        std::stringstream ss(text);
+        double v = 0.0;
+        if ((ss >> v) && ss.eof()) return Attr::of(v);
+    }
+    return Attr::of(text);
+}
+
+AttrMap netlist_attributes(const std::vector<std::string> &fields, const size_t first, const int line_number)
+{
+    AttrMap out;
+    if (first >= fields.size() || fields[first].empty()) return out;
+    const char open = fields[first][0];
+    if (open == '[' || open == '{')
+    {
+        // netlist_parse_embedded_json  src/netlist.cpp:378-414: the fields are glued back together and
+        // parsed as one YAML flow collection up to its closing bracket
+        std::string all;
+        for (size_t k = first; k < fields.size(); ++k) all += fields[k] + ' ';
+        const char close = open == '[' ? ']' : '}';
+        int depth = 0;
+        size_t end = std::string::npos;
+        for (size_t k = 0; k < all.size(); ++k)
+        {
+            if (all[k] == open) ++depth;
+            else if (all[k] == close && --depth == 0)
+            {
+                end = k;
+                break;
+            }
+        }
+        if (end == std::string::npos)
+            throw std::runtime_error("Error: Line " + std::to_string(line_number) + ": embedded attributes are not terminated");
+        return model_attributes(yaml::parse(all.substr(0, end + 1)));
+    }
+    for (size_t k = first; k < fields.size(); ++k)
+    {
+        const std::string &field = fields[k];
+        const size_t eq = field.find('=');
+        if (field.size() < 3 || eq == std::string::npos || eq == 0 || eq + 1 >= field.size()) continue; // logged and skipped
+        Attr a = netlist_value(field.substr(eq + 1));
+        a.name = field.substr(0, eq);
+        out.insert({field.substr(0, eq), a}); // the first occurrence of a key wins (std::map::insert)
+    }
+    return out;
+}
+
+std::pair<std::string, size_t> netlist_neuron(const std::string &field) // netlist_parse_neuron_field  :96-110
+{
+    const size_t dot = field.find('.');
+    if (dot == std::string::npos) throw std::runtime_error("Error: Invalid neuron format");
+    return {field.substr(0, dot), netlist_to_index(field.substr(dot + 1))};
+}
+
+NeuronConfiguration netlist_neuron_config(const AttrMap &attrs) // the reserved names  :421-446, 491-515
+{
+    NeuronConfiguration cfg;
+    auto get = [&](const char *key) -> const Attr * {
+        auto it = attrs.find(key);
+        return it == attrs.end() ? nullptr : &it->second;
+    };
+    if (const Attr *a = get("synapse_hw_name")) cfg.default_synapse_hw_name = a->as_string();
+    if (const Attr *a = get("dendrite_hw_name")) cfg.dendrite_hw_name = a->as_string();
+    if (const Attr *a = get("soma_hw_name")) cfg.soma_hw_name = a->as_string();
+    if (const Attr *a = get("log_spikes")) cfg.log_spikes = a->as_bool();
+    if (const Attr *a = get("log_v")) cfg.log_potential = a->as_bool();
+    return cfg;
+}
+
+Neuron &netlist_lookup(SpikingNetwork &net, const std::string &group, const size_t id, const int line_number)
+{
+    if (net.groups.find(group) == net.groups.end())
+        throw std::invalid_argument("Error: Line " + std::to_string(line_number) + ": Group (" + group + ") not in groups.");
+    NeuronGroup &g = net.group(group);
+    if (id >= g.neurons.size())
+        throw std::invalid_argument("Error: Line " + std::to_string(line_number) + ": Trying to access neuron (" + group + "." +
+                std::to_string(id) + ") but group " + group + " only allocates " + std::to_string(g.neurons.size()) +
+                " neuron(s).");
+    return g.neurons[id];
+}
+} // namespace
+
+std::unique_ptr<SpikingNetwork> load_net_netlist(const std::string &path, Architecture &arch)
+{
+    std::ifstream fp(path);
+    if (!fp.is_open()) throw std::invalid_argument("Error: Network file: failed to open (" + path + ")."); // src/network.cpp:200-205
+    auto net = std::make_unique<SpikingNetwork>("");
+    std::string line;
+    int line_number = 1;
+    for (; std::getline(fp, line); ++line_number)
+    {
+        const std::vector<std::string> fields = netlist_fields(line);
+        if (fields.empty()) continue;
+        const char type = fields[0][0];
+        if (type == '#') continue; // comment (netlist_read_network_entry  src/netlist.cpp:186-194)
+        if (fields.size() < 2) throw std::invalid_argument("Error: Line " + std::to_string(line_number) + ": fields < 2");
+        if (type == 'g')
+        {
+            // groups are named by their position  :416-465
+            AttrMap attrs = netlist_attributes(fields, 2, line_number);
+            NeuronConfiguration cfg = netlist_neuron_config(attrs);
+            for (auto it = attrs.begin(); it != attrs.end();)
+                it = is_reserved_neuron_attribute(it->first) ? attrs.erase(it) : std::next(it);
+            cfg.model_attributes = attrs;
+            net->create_neuron_group(std::to_string(net->groups.size()), netlist_to_index(fields[1]), cfg);
+        }
+        else if (type == 'n')
+        {
+            // per-neuron attributes; the reserved names stay in model_attributes here (:467-517), so a
+            // netlist that names e.g. soma_hw_name per neuron fails at load like it does in the reference
+            const auto [group, id] = netlist_neuron(fields[1]);
+            Neuron &n = netlist_lookup(*net, group, id, line_number);
+            const AttrMap attrs = netlist_attributes(fields, 2, line_number);
+            NeuronConfiguration cfg = netlist_neuron_config(attrs);
+            cfg.model_attributes = attrs;
+            n.set_attributes(cfg);
+        }
+        else if (type == 'e')
+        {
+            const size_t arrow = fields[1].find("->");
+            if (arrow == std::string::npos) throw std::runtime_error("Invalid edge format");
+            const auto [sg, sn] = netlist_neuron(fields[1].substr(0, arrow));
+            const auto [dg, dn] = netlist_neuron(fields[1].substr(arrow + 2));
+            Neuron &src = netlist_lookup(*net, sg, sn, line_number);
+            Neuron &dst = netlist_lookup(*net, dg, dn, line_number);
+            const AttrMap attrs = netlist_attributes(fields, 2, line_number);
+            const size_t idx = src.connect_to_neuron(dst);
+            src.edges_out[idx].synapse_attributes = attrs;
+            src.edges_out[idx].dendrite_attributes = attrs;
+        }
+        else if (type == '&')
+        {
+            const size_t at = fields[1].find('@');
+            if (at == std::string::npos) throw std::runtime_error("Invalid mapping format");
+            const auto [group, id] = netlist_neuron(fields[1].substr(0, at));
+            const std::string core = fields[1].substr(at + 1);
+            const size_t dot = core.find('.');
+            if (dot == std::string::npos) throw std::runtime_error("Error: Invalid neuron format");
+            const size_t tile_id = netlist_to_index(core.substr(0, dot)), core_off = netlist_to_index(core.substr(dot + 1));
+            if (tile_id >= arch.tiles.size() || core_off >= arch.tiles[tile_id].cores.size())
+                throw std::runtime_error("Error: Couldn't parse mapping.");
+            netlist_lookup(*net, group, id, line_number).map_to_core(arch.tiles[tile_id].cores[core_off]);
+        }
+        else
+            throw std::invalid_argument("Invalid description entry type");
     }
     return net;
 }

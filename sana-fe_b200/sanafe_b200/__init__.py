@@ -172,6 +172,7 @@ def lib():
         "sfe_engine_fired_local_ptr": (vp, [vp, C.POINTER(sz)]), "sfe_engine_fired_global_ptr": (vp, [vp, C.POINTER(sz)]),
         "sfe_engine_device_bytes": (sz, [vp]),
         "sfe_arch_load_yaml": (vp, [cstr]), "sfe_net_load_yaml": (vp, [cstr, vp]),
+        "sfe_net_load_netlist": (vp, [cstr, vp]),
         "sfe_load_flat": (C.c_int, [cstr, C.POINTER(vp), C.POINTER(vp)]),
         "sfe_arch_free": (None, [vp]), "sfe_net_free": (None, [vp]),
         "sfe_chip_create": (vp, [vp, C.c_int]), "sfe_chip_destroy": (None, [vp]),
@@ -244,7 +245,7 @@ def load_arch(path):
 def load_net(path, arch, use_netlist_format=False):
     """sanafe.load_net (src/network.cpp:194-222)."""
     if use_netlist_format:
-        raise SanafeError("legacy netlist format is not implemented yet")
+        return Network(_ptr(lib().sfe_net_load_netlist(os.fsencode(path), arch._h)))
     return Network(_ptr(lib().sfe_net_load_yaml(os.fsencode(path), arch._h)))
 
 

@@ -1,0 +1,78 @@
+"""Legacy netlist reader (csrc/host/yaml_frontend.cpp, restating src/netlist.cpp:38-617): the same
+network written as a netlist and as YAML must lower to identical tables and behave identically
+(the reference's own netlist.cpp cannot be compiled here - it needs RapidYAML - so the check is
+against the YAML front-end, which is pinned against the reference separately)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import sanafe_b200 as sfe
+from helpers import GOLDEN, ROOT, Oracle
+
+SRC = os.path.join(GOLDEN, "src")
+ARCH = os.path.join(SRC, "hh_arch.yaml")
+
+
+def lowered(net_file, netlist):
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch = sfe.load_arch(ARCH)
+        net = sfe.load_net(os.path.join(SRC, net_file), arch, use_netlist_format=netlist)
+        chip = sfe.SpikingChip(arch, device=-1)
+        chip.load(net)
+    finally:
+        os.chdir(cwd)
+    return chip
+
+
+def test_netlist_equals_yaml_description():
+    a, b = lowered("example_equiv.net", True), lowered("example_equiv.yaml", False)
+    ta, tb = a.tables, b.tables
+    for field in ("n_neurons", "n_synapses", "n_axons_in", "n_axons_out", "n_soma_classes", "n_probes", "mapped_cores"):
+        assert getattr(ta, field) == getattr(tb, field), field
+    n, m = ta.n_neurons, ta.n_synapses
+    for name, count in (("neuron_class", n), ("neuron_bias", n), ("axon_out_begin", n + 1), ("syn_weight", m), ("syn_meta", m)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(ta, name), shape=(count,)),
+                              np.ctypeslib.as_array(getattr(tb, name), shape=(count,))), name
+    assert a.probe_names() == b.probe_names() == ["0.0", "0.1", "0.2", "1.0", "1.1", "1.2"]
+    rd_a, out_a = Oracle(a).run(50)
+    rd_b, out_b = Oracle(b).run(50)
+    assert rd_a.neurons_fired == rd_b.neurons_fired > 0 and rd_a.spikes == rd_b.spikes > 0
+    assert np.array_equal(out_a["fired_bits"], out_b["fired_bits"])
+    assert np.array_equal(out_a["potentials"], out_b["potentials"])
+    assert rd_a.total_energy == rd_b.total_energy
+
+
+def test_netlist_value_typing_and_errors(tmp_path):
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch = sfe.load_arch(ARCH)
+        bad = tmp_path / "bad.net"
+        bad.write_text("g 2 threshold=1.0\nn 0.5 bias=1\n")
+        with pytest.raises(sfe.SanafeError, match=r"Trying to access neuron \(0\.5\) but group 0 only allocates 2"):
+            sfe.load_net(str(bad), arch, use_netlist_format=True)
+        bad.write_text("g 2 threshold=1.0\nx 0.0 bias=1\n")
+        with pytest.raises(sfe.SanafeError, match="Invalid description entry type"):
+            sfe.load_net(str(bad), arch, use_netlist_format=True)
+        bad.write_text("g 2 threshold=1.0\n& 0.0@9.0\n")
+        with pytest.raises(sfe.SanafeError, match="Couldn't parse mapping"):
+            sfe.load_net(str(bad), arch, use_netlist_format=True)
+        with pytest.raises(sfe.SanafeError, match="failed to open"):
+            sfe.load_net(str(tmp_path / "missing.net"), arch, use_netlist_format=True)
+        # a per-neuron soma_hw_name is a reserved attribute: Neuron::set_attributes rejects it, like the reference does
+        # with its own snn/hh_example.net
+        bad.write_text("g 1 threshold=1.0\nn 0.0 soma_hw_name=lif\n& 0.0@0.0\n")
+        with pytest.raises(sfe.SanafeError, match="Reserved neuron attribute 'soma_hw_name'"):
+            sfe.load_net(str(bad), arch, use_netlist_format=True)
+    finally:
+        os.chdir(cwd)
+
+
+def test_sim_command_line_accepts_netlists_flag():
+    sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
+    res = subprocess.run([sim, "-n", ARCH, os.path.join(SRC, "missing.net"), "5"], cwd=ROOT, capture_output=True, text=True, timeout=60)
+    assert res.returncode == 1 and "failed to open" in res.stderr
