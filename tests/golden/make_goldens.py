@@ -119,8 +119,38 @@ def make_case(name, spec):
           f"energy={s['total_energy']!r} sim_time={s['sim_time']!r}")
 
 
+# Trace files written by the reference's OWN writers (sim_trace_* in src/chip.cpp) with one
+# processing thread (message ids follow the creation order): tests/golden/traces/<case>.<timing>.*
+TRACE_CASES = [("example", "simple", 100), ("example", "detailed", 100), ("synth_small", "detailed", 12),
+               ("synth_delay", "simple", 12), ("truenorth", "detailed", 20), ("hh", "simple", 200)]
+
+
+def make_traces():
+    import subprocess
+    out_root = os.path.join(HERE, "traces")
+    os.makedirs(out_root, exist_ok=True)
+    for name, timing, steps in TRACE_CASES:
+        flat = os.path.join(HERE, name + ".jsonl")
+        tmp = tempfile.mkdtemp(prefix=f"traces_{name}_{timing}_")
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "sanafe_ref"), flat, "--steps", str(steps), "--timing", timing,
+                        "--threads", "1", "--out", tmp, "--traces"], check=True, stdout=subprocess.DEVNULL)
+        kinds = ("messages", "perf", "potentials", "spikes") if name == "hh" else ("messages", "perf")
+        for kind in kinds:
+            src = os.path.join(tmp, kind + ".csv")
+            if kind == "perf" and name != "hh":
+                shutil.copy(src, os.path.join(out_root, f"{name}.{timing}.perf.csv"))
+            else:
+                with open(src, "rb") as fi, gzip.open(os.path.join(out_root, f"{name}.{timing}.{kind}.csv.gz"), "wb", compresslevel=9) as fo:
+                    shutil.copyfileobj(fi, fo)
+        shutil.rmtree(tmp)
+        print(f"traces: {name} {timing} {steps} steps")
+
+
 if __name__ == "__main__":
     os.chdir(ROOT)  # plugin paths in the flat files are relative to the repo root
+    if "--traces" in sys.argv[1:]:
+        make_traces()
+        sys.exit(0)
     only = sys.argv[1:]
     for case_name, case_spec in CASES.items():
         if only and case_name not in only:
