@@ -3137,9 +3137,13 @@ extern "C" int sfe_engine_synchronize(sfe_engine *e)
 }
 
 // plain cudaMemcpy (any direction, unified addressing); for tests and small exchanges
+// Copy between any two of host / device memory, complete on return. (cudaMemcpy alone does not
+// wait for a device-to-device copy, and the engines' streams are non-blocking: without the
+// synchronisation a kernel enqueued right after could read the destination too early.)
 extern "C" int sfe_device_memcpy(void *dst, const void *src, size_t bytes)
 {
     SFE_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    SFE_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     return 0;
 }
 
