@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 1
+#define SFE_ABI_VERSION 2
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -168,7 +168,10 @@ typedef struct sfe_input_desc /* "input" soma: state is per hardware UNIT (src/m
     uint32_t spikes_off, spikes_len; /* into sfe_tables.input_spikes (1 byte per step) */
     uint32_t share_count, share_rank;/* neurons sharing the unit, this neuron's rank among them */
     double rate;
-    double poisson;                  /* must be 0 (mt19937 stream not reproduced yet) */
+    double poisson;                  /* spike when poisson > U(0,1) drawn from the UNIT's std::mt19937 (src/models.cpp:880-885) */
+    uint32_t unit;                   /* ordinal of the unit among the chip's "input" units in hardware order: its generator is
+                                      * seeded with input_seed_base + unit + 1 (InputModel::instance_counter, src/models.hpp:347,366) */
+    uint32_t poisson_col;            /* column of this neuron in the per-step Poisson overlay, or 0xFFFFFFFF (poisson == 0) */
 } sfe_input_desc;
 
 typedef struct sfe_hh_init /* Hodgkin-Huxley plugin initial state, one neuron per unit */
@@ -213,6 +216,10 @@ typedef struct sfe_tables
     const double *syn_weight;
     const uint32_t *syn_meta;
     const sfe_synth_spec *synth;     /* non-NULL: generate synapses from this spec */
+
+    /* Poisson inputs: "input" units created in this process before this chip (the reference's counter is a
+     * process-wide static) and the number of neurons with poisson > 0 (= columns of the overlay) */
+    uint32_t input_seed_base, n_poisson_cols;
 } sfe_tables;
 
 /* one record per simulated timestep (src/timestep.hpp:21-42) */
@@ -273,6 +280,19 @@ int sfe_engine_reset(sfe_engine *e);
  * stream into the inactive device buffer (overlapping the steps already enqueued) and takes
  * effect with the next step that is enqueued; keep the host buffer unchanged until then. */
 int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n);
+/* Poisson inputs are drawn on the host (the reference's generator is libstdc++'s std::mt19937 +
+ * uniform_real_distribution, one draw per update of a neuron of the unit, src/models.cpp:863-903) and reach
+ * the device as an overlay: bits[step][col] != 0 makes the input neuron with that poisson_col spike in that
+ * step. Covers the next `n_steps` steps to be enqueued; sfe_chip_sim does this itself. */
+int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_steps, uint32_t n_cols);
+/* Host-only source of that overlay (no device needed): one std::mt19937 per Poisson unit, seeded
+ * tables->input_seed_base + unit + 1. sfe_poisson_fill writes bits[n_steps][sfe_poisson_cols] for the next
+ * n_steps steps and advances the streams (they are not rewound by a reset: InputModel::reset, src/models.hpp:358). */
+typedef struct sfe_poisson sfe_poisson;
+sfe_poisson *sfe_poisson_create(const sfe_tables *tables);
+void sfe_poisson_destroy(sfe_poisson *p);
+uint32_t sfe_poisson_cols(const sfe_poisson *p);
+int sfe_poisson_fill(sfe_poisson *p, uint8_t *bits, int64_t n_steps);
 int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias);
 int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n);
 int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words);
@@ -361,6 +381,10 @@ void sfe_net_free(sfe_net *n);
 sfe_chip *sfe_chip_create(const sfe_arch *arch, int device);
 /* before load(): this chip object simulates partition `rank` of `world` (multi-GPU) */
 int sfe_chip_set_partition(sfe_chip *c, uint32_t rank, uint32_t world);
+/* Poisson inputs are seeded by how many "input" units the PROCESS created before this chip's (the reference's
+ * InputModel::instance_counter is a process-wide static, src/models.hpp:366); sfe_chip_create keeps that count.
+ * This overrides it for the chip (0 = as if the chip were the first one of a fresh process). Call before load. */
+int sfe_chip_set_input_seed_base(sfe_chip *c, uint32_t base);
 void sfe_chip_destroy(sfe_chip *c);
 /* SpikingChip::load  src/chip.cpp:129-138 */
 int sfe_chip_load(sfe_chip *c, const sfe_net *net);

@@ -54,7 +54,56 @@ typedef struct sfe_oracle
     int64_t *core_msgs;
     double *core_syn_e, *core_den_e, *core_soma_e, *core_axout_e;
     double total_sim_time, total_energy;
+    /* Poisson inputs: one MT19937 per input unit (own restatement, below), or an external overlay */
+    struct mt19937 *poisson_gen; /* [n_poisson_units], indexed by sfe_input_desc.unit */
+    uint32_t n_poisson_units;
+    const uint8_t *overlay;      /* caller-owned [overlay_steps][overlay_cols], NULL: draw here */
+    int64_t overlay_step0, overlay_steps;
+    uint32_t overlay_cols;
 } sfe_oracle;
+
+/* MT19937 (Matsumoto & Nishimura 1998) as std::mt19937 specifies it, and the 53-bit canonical
+ * double libstdc++'s std::uniform_real_distribution<double>{0,1} builds from two 32-bit outputs
+ * (lo first): U = (lo + hi * 2^32) / 2^64, nudged below 1.0. InputModel: src/models.hpp:347-366. */
+struct mt19937
+{
+    uint32_t mt[624];
+    int idx;
+    int seeded;
+};
+static void mt_seed(struct mt19937 *g, uint32_t seed)
+{
+    g->mt[0] = seed;
+    for (int i = 1; i < 624; ++i) g->mt[i] = 1812433253u * (g->mt[i - 1] ^ (g->mt[i - 1] >> 30)) + (uint32_t) i;
+    g->idx = 624;
+    g->seeded = 1;
+}
+static uint32_t mt_next(struct mt19937 *g)
+{
+    if (g->idx >= 624)
+    {
+        for (int i = 0; i < 624; ++i)
+        {
+            const uint32_t y = (g->mt[i] & 0x80000000u) | (g->mt[(i + 1) % 624] & 0x7fffffffu);
+            g->mt[i] = g->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->idx = 0;
+    }
+    uint32_t y = g->mt[g->idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+static double mt_canonical(struct mt19937 *g)
+{
+    const double lo = (double) mt_next(g);
+    const double hi = (double) mt_next(g);
+    double u = (lo + hi * 4294967296.0) / 18446744073709551616.0;
+    if (u >= 1.0) u = nextafter(1.0, 0.0);
+    return u;
+}
 
 #define RING 6 /* max_delay 5 + 1  (src/models.hpp:158) */
 
@@ -103,6 +152,9 @@ sfe_oracle *sfe_oracle_create(const sfe_tables *t)
         o->bias[i] = t->neuron_bias[i];
         o->v[i] = t->neuron_potential0[i];
     }
+    for (uint32_t k = 0; k < t->n_inputs; ++k)
+        if (t->inputs[k].poisson > 0.0 && t->inputs[k].unit + 1 > o->n_poisson_units) o->n_poisson_units = t->inputs[k].unit + 1;
+    o->poisson_gen = (struct mt19937 *) zalloc(o->n_poisson_units, sizeof(struct mt19937));
     for (size_t i = 0; i < t->n_hh; ++i)
     {
         o->hh_m[i] = t->hh[i].m;
@@ -122,7 +174,18 @@ void sfe_oracle_destroy(sfe_oracle *o)
     free(o->axon_active); free(o->core_gen); free(o->core_proc);
     free(o->tile_e); free(o->tile_w); free(o->tile_n); free(o->tile_s); free(o->core_msgs);
     free(o->core_syn_e); free(o->core_den_e); free(o->core_soma_e); free(o->core_axout_e);
+    free(o->poisson_gen);
     free(o);
+}
+
+/* Use an externally drawn Poisson overlay (the product's sfe_poisson_fill) for the next n_steps steps
+ * instead of the oracle's own generator: lets the tests check the product's draws on the CPU. */
+void sfe_oracle_set_input_overlay(sfe_oracle *o, const uint8_t *bits, int64_t n_steps, uint32_t n_cols)
+{
+    o->overlay = bits;
+    o->overlay_step0 = o->total_timesteps;
+    o->overlay_steps = n_steps;
+    o->overlay_cols = n_cols;
 }
 
 void sfe_oracle_set_bias(sfe_oracle *o, const double *bias, size_t n)
@@ -221,11 +284,29 @@ static int truenorth_update(sfe_oracle *o, const sfe_soma_class *c, size_t i, in
 /* InputModel::update  src/models.cpp:863-903. The unit's spike-train cursor is
  * shared by the share_count neurons mapped to it: at step index s (0-based) the
  * neuron of rank r consumes element s*share_count + r. */
-static int input_update(const sfe_tables *t, const sfe_input_desc *d, int64_t step_idx, int64_t timestep)
+static int input_update(sfe_oracle *o, const sfe_input_desc *d, int64_t step_idx, int64_t timestep)
 {
+    const sfe_tables *t = o->t;
     int send = 0;
     const uint64_t cursor = (uint64_t) step_idx * d->share_count + d->share_rank;
     if (cursor < d->spikes_len) send = t->input_spikes[d->spikes_off + cursor] != 0;
+    /* `poisson_probability > uniform_distribution(gen)`: one draw per update of the unit; the neurons
+     * of a unit are updated in rank order, so drawing as we go reproduces the unit's stream. Draws of
+     * units with probability 0 can never be observed and are skipped. */
+    if (d->poisson > 0.0)
+    {
+        if (o->overlay != NULL)
+        {
+            const int64_t row = step_idx - o->overlay_step0;
+            if (row >= 0 && row < o->overlay_steps && o->overlay[(size_t) row * o->overlay_cols + d->poisson_col]) send = 1;
+        }
+        else
+        {
+            struct mt19937 *g = &o->poisson_gen[d->unit];
+            if (!g->seeded) mt_seed(g, t->input_seed_base + d->unit + 1u);
+            if (d->poisson > mt_canonical(g)) send = 1;
+        }
+    }
     if ((d->rate > 0.0) && ((timestep % (long int) (1.0 / d->rate)) == 0)) send = 1;
     return send ? SFE_STATUS_FIRED : SFE_STATUS_IDLE;
 }
@@ -337,7 +418,7 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
             {
             case SFE_SOMA_LIF: st = lif_update(o, c, i, has_in, in, steps_done); break;
             case SFE_SOMA_TRUENORTH: st = truenorth_update(o, c, i, has_in, in); break;
-            case SFE_SOMA_INPUT: st = input_update(t, &t->inputs[t->neuron_aux[i]], steps_done, T); break;
+            case SFE_SOMA_INPUT: st = input_update(o, &t->inputs[t->neuron_aux[i]], steps_done, T); break;
             default: st = hh_update(o, t->neuron_aux[i]); break;
             }
             o->status[i] = (uint8_t) st;

@@ -116,6 +116,10 @@ struct DevTables
     const uint32_t *axon_src;
     const sfe_input_desc *inputs;
     const uint8_t *input_spikes;
+    // Poisson inputs: host-drawn overlay (sfe_engine_set_input_overlay), row = step index - overlay_step0
+    const uint8_t *overlay;
+    long long overlay_step0, overlay_steps;
+    uint32_t overlay_cols, pad_overlay;
     const sfe_axon_in *axons_in;
     const double *syn_w;
     const uint32_t *syn_meta;
@@ -400,12 +404,19 @@ __device__ __forceinline__ int truenorth_update(
 }
 
 // InputModel::update  src/models.cpp:863-903 (per-unit cursor shared by share_count neurons)
-__device__ __forceinline__ int input_update(
-        const sfe_input_desc &d, const uint8_t *spikes, const long long step_idx, const long long timestep)
+__device__ __forceinline__ int input_update(const DevTables &t, const sfe_input_desc &d, const long long step_idx,
+        const long long timestep)
 {
     bool send = false;
     const unsigned long long cursor = static_cast<unsigned long long>(step_idx) * d.share_count + d.share_rank;
-    if (cursor < d.spikes_len) send = spikes[d.spikes_off + cursor] != 0;
+    if (cursor < d.spikes_len) send = t.input_spikes[d.spikes_off + cursor] != 0;
+    // poisson > U(0,1): the draw was made on the host with the reference's generator (poisson.cpp)
+    if (d.poisson > 0.0) // (engine creation checked poisson_col; check_overlay() that the overlay covers this step)
+    {
+        const long long row = step_idx - t.overlay_step0;
+        if (row >= 0 && row < t.overlay_steps && t.overlay[static_cast<size_t>(row) * t.overlay_cols + d.poisson_col] != 0)
+            send = true;
+    }
     if ((d.rate > 0.0) && ((timestep % static_cast<long long>(1.0 / d.rate)) == 0)) send = true;
     return send ? SFE_STATUS_FIRED : SFE_STATUS_IDLE;
 }
@@ -855,7 +866,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             }
             else if constexpr (kExotic)
             {
-                if (c.model == SFE_SOMA_INPUT) st = input_update(t.inputs[t.neuron_aux[i]], t.input_spikes, steps_done, T);
+                if (c.model == SFE_SOMA_INPUT) st = input_update(t, t.inputs[t.neuron_aux[i]], steps_done, T);
                 else st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
             }
             s.status[i] = static_cast<uint8_t>(st);
@@ -1826,6 +1837,10 @@ struct sfe_engine
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used{0};
     bool ordered_any{false}, dual_any{false};
+    // Poisson overlay (host-drawn, see poisson.cpp)
+    uint32_t n_poisson_cols{0};
+    uint8_t *d_overlay{nullptr};
+    size_t overlay_cap{0};
 
     template <typename T> int alloc(T **p, size_t count)
     {
@@ -2009,6 +2024,13 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     }
     if (e->upload(&e->t.inputs, tb->inputs, tb->n_inputs) != 0) return -1;
     if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
+    e->n_poisson_cols = tb->n_poisson_cols;
+    for (uint32_t k = 0; k < tb->n_inputs; ++k)
+        if (tb->inputs[k].poisson > 0.0 && tb->inputs[k].poisson_col >= tb->n_poisson_cols)
+        {
+            sfe::set_last_error("sfe_engine_create: Poisson input neuron with poisson_col >= n_poisson_cols");
+            return -1;
+        }
     // Device synapse layout: every axon segment starts on a multiple of 4 synapses
     // (32-byte aligned weights, 16-byte aligned meta words) so the message phase can
     // use 128-bit loads; the axon records carry the padded offsets.
@@ -2411,6 +2433,7 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
         }
     }
     for (void *p : e->allocs) cudaFree(p);
+    if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
     if (e->ev_end != nullptr) cudaEventDestroy(e->ev_end);
@@ -2521,8 +2544,20 @@ static void launch_finalize(sfe_engine *e)
 
 static int apply_pending_bias(sfe_engine *e);
 
+// A chip with Poisson inputs can only step through timesteps its overlay covers: stepping past it
+// would silently drop the random spikes.
+static int check_overlay(const sfe_engine *e)
+{
+    if (e->n_poisson_cols == 0) return 0;
+    if (e->total_timesteps >= e->t.overlay_step0 && e->total_timesteps < e->t.overlay_step0 + e->t.overlay_steps) return 0;
+    sfe::set_last_error("this chip has Poisson inputs: call sfe_engine_set_input_overlay (see sfe_poisson_fill) for the "
+                        "steps to be simulated first; sfe_chip_sim does it itself");
+    return -1;
+}
+
 static int enqueue_step(sfe_engine *e, bool probes)
 {
+    if (check_overlay(e) != 0) return -1;
     if (apply_pending_bias(e) != 0) return -1;
     if (!e->soma_list.empty())
     {
@@ -2574,8 +2609,38 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
                 " uncollected steps; call sfe_engine_collect");
         return -1;
     }
-    for (int64_t i = 0; i < timesteps; ++i) enqueue_step(e, false);
+    for (int64_t i = 0; i < timesteps; ++i)
+        if (enqueue_step(e, false) != 0) return -1;
     SFE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_steps, uint32_t n_cols)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n_cols != e->n_poisson_cols || n_steps < 0 || (bits == nullptr && n_steps > 0 && n_cols > 0))
+    {
+        sfe::set_last_error("sfe_engine_set_input_overlay: need bits[n_steps][" + std::to_string(e->n_poisson_cols) + "]");
+        return -1;
+    }
+    // steps already enqueued may still be reading the previous overlay
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    const size_t bytes = static_cast<size_t>(n_steps) * n_cols;
+    if (bytes > e->overlay_cap)
+    {
+        if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
+        e->d_overlay = nullptr;
+        e->overlay_cap = 0;
+        void *q = nullptr;
+        SFE_CUDA(cudaMalloc(&q, bytes));
+        e->d_overlay = static_cast<uint8_t *>(q);
+        e->overlay_cap = bytes;
+    }
+    if (bytes > 0) SFE_CUDA(cudaMemcpy(e->d_overlay, bits, bytes, cudaMemcpyHostToDevice));
+    e->t.overlay = e->d_overlay;
+    e->t.overlay_cols = n_cols;
+    e->t.overlay_step0 = e->total_timesteps;
+    e->t.overlay_steps = n_steps;
     return 0;
 }
 
@@ -2661,6 +2726,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
         if (per_step > 0 && e->ensure_pinned(per_step * static_cast<size_t>(batch)) != 0) return -1;
         for (int64_t b = 0; b < batch; ++b)
         {
+            if (check_overlay(e) != 0) return -1;
             if (apply_pending_bias(e) != 0) return -1;
             if (!e->soma_list.empty())
             {
@@ -3028,6 +3094,7 @@ extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
         sfe::set_last_error("more than " + std::to_string(e->log_cap) + " uncollected steps; call sfe_engine_collect_records");
         return -1;
     }
+    if (check_overlay(e) != 0) return -1;
     if (apply_pending_bias(e) != 0) return -1;
     if (!e->soma_list.empty())
     {

@@ -4,6 +4,7 @@
 // from an Architecture, load() lowers a SpikingNetwork to device tables, sim()
 // runs timesteps and returns RunData; state persists across sim() calls and
 // reset() zeroes model state without rewinding the timestep counter.
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -52,6 +53,10 @@ struct sfe_chip
     uint32_t rank{0}, world{1};
     std::unique_ptr<sfe::DetailedScheduler> scheduler; // built on first use
     long next_mid{0};                                  // total_messages_sent (src/chip.hpp:126): ids of traced messages
+    // Poisson inputs: "input" units this process had created before this chip (InputModel::instance_counter is a
+    // process-wide static, src/models.hpp:366) and the host generators of this chip's Poisson units
+    uint32_t input_seed_base{0};
+    sfe_poisson *poisson{nullptr};
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -74,12 +79,24 @@ template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f(
     return on_error;
 }
 
+std::atomic<uint32_t> g_input_units_created{0};
+
 int attach_engine(sfe_chip *c)
 {
     if (c->engine != nullptr)
     {
         sfe_engine_destroy(c->engine);
         c->engine = nullptr;
+    }
+    // (a second load() restarts the Poisson streams; the reference's generators would run on)
+    sfe_poisson_destroy(c->poisson);
+    c->poisson = nullptr;
+    c->tables.input_seed_base = c->input_seed_base;
+    c->tables.view.input_seed_base = c->input_seed_base;
+    if (c->tables.view.n_poisson_cols > 0)
+    {
+        c->poisson = sfe_poisson_create(&c->tables.view);
+        if (c->poisson == nullptr) return -1;
     }
     c->total_energy = 0.0;
     c->total_sim_time = 0.0;
@@ -166,7 +183,9 @@ extern "C" sfe_chip *sfe_chip_create(const sfe_arch *arch, int device)
                 if (device >= 0 && sfe_device_count() <= 0)
                     throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback "
                                              "(pass device < 0 for a host-only chip that can only lower/export tables)");
-                return new sfe_chip(*arch->arch, device);
+                auto *chip = new sfe_chip(*arch->arch, device);
+                chip->input_seed_base = g_input_units_created.fetch_add(sfe::count_input_units(chip->arch));
+                return chip;
             },
             nullptr);
 }
@@ -183,10 +202,22 @@ extern "C" int sfe_chip_set_partition(sfe_chip *c, uint32_t rank, uint32_t world
     return 0;
 }
 
+extern "C" int sfe_chip_set_input_seed_base(sfe_chip *c, uint32_t base)
+{
+    if (c->loaded)
+    {
+        sfe::set_last_error("sfe_chip_set_input_seed_base: call before load");
+        return -1;
+    }
+    c->input_seed_base = base;
+    return 0;
+}
+
 extern "C" void sfe_chip_destroy(sfe_chip *c)
 {
     if (c == nullptr) return;
     if (c->engine != nullptr) sfe_engine_destroy(c->engine);
+    sfe_poisson_destroy(c->poisson);
     delete c;
 }
 
@@ -233,36 +264,54 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                     throw std::runtime_error("the cycle-accurate timing model needs Booksim2 (third-party, not "
                                              "available): out of scope");
                 sfe_run_data rd;
-                if (timing_model == SFE_TIMING_SIMPLE)
+                const bool detailed = timing_model != SFE_TIMING_SIMPLE;
+                if (!detailed && c->poisson == nullptr)
                 {
                     if (sfe_engine_run(c->engine, timesteps, req, &rd) != 0) return -1;
                 }
                 else
                 {
-                    // Detailed model: the device runs the timesteps and hands back one status
-                    // byte per neuron and step; the host scheduler (src/schedule.cpp:208-620
-                    // restated in schedule.cpp) turns them into per-step sim_time.
-                    if (c->world > 1) throw std::runtime_error("detailed timing is not available on a partitioned chip");
-                    if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
+                    // Chunked run with per-step records.
+                    // Detailed model: the device runs the timesteps and hands back one status byte per neuron and
+                    // step; the host scheduler (src/schedule.cpp:208-620 restated in schedule.cpp) turns them into
+                    // per-step sim_time.
+                    // Poisson inputs: the host draws the chunk's random spikes with the reference's generator
+                    // (poisson.cpp) and uploads them as an overlay before the chunk is enqueued.
+                    if (detailed && c->world > 1) throw std::runtime_error("detailed timing is not available on a partitioned chip");
+                    if (detailed && !c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
                     const size_t n = c->tables.view.n_neurons;
                     const size_t words = (n + 31) / 32;
-                    const int64_t batch_cap = std::max<int64_t>(1, std::min<int64_t>(4096, (64ll << 20) / static_cast<int64_t>(std::max<size_t>(n, 1))));
-                    std::vector<uint8_t> status;
+                    const uint32_t cols = c->poisson != nullptr ? sfe_poisson_cols(c->poisson) : 0u;
+                    int64_t batch_cap = 4096;
+                    if (detailed) batch_cap = std::min<int64_t>(batch_cap, (64ll << 20) / static_cast<int64_t>(std::max<size_t>(n, 1)));
+                    if (cols > 0) batch_cap = std::min<int64_t>(batch_cap, (32ll << 20) / static_cast<int64_t>(cols));
+                    batch_cap = std::max<int64_t>(1, batch_cap);
+                    std::vector<uint8_t> status, overlay;
                     std::vector<sfe_step_record> recs;
                     std::memset(&rd, 0, sizeof(rd));
                     double sched_s = 0.0;
                     for (int64_t done = 0; done < timesteps;)
                     {
                         const int64_t batch = std::min<int64_t>(batch_cap, timesteps - done);
-                        status.resize(static_cast<size_t>(batch) * n);
                         recs.resize(static_cast<size_t>(batch));
                         sfe_trace_request sub{};
                         sub.steps = recs.data();
-                        sub.status = status.data();
+                        if (detailed)
+                        {
+                            status.resize(static_cast<size_t>(batch) * n);
+                            sub.status = status.data();
+                        }
+                        else if (req != nullptr && req->status != nullptr) sub.status = req->status + static_cast<size_t>(done) * n;
                         if (req != nullptr)
                         {
                             if (req->fired_bits != nullptr) sub.fired_bits = req->fired_bits + static_cast<size_t>(done) * words;
                             if (req->potentials != nullptr) sub.potentials = req->potentials + static_cast<size_t>(done) * c->tables.view.n_probes;
+                        }
+                        if (c->poisson != nullptr)
+                        {
+                            overlay.resize(static_cast<size_t>(batch) * cols);
+                            if (sfe_poisson_fill(c->poisson, overlay.data(), batch) != 0) return -1;
+                            if (sfe_engine_set_input_overlay(c->engine, overlay.data(), batch, cols) != 0) return -1;
                         }
                         sfe_run_data part;
                         if (sfe_engine_run(c->engine, batch, &sub, &part) != 0) return -1;
@@ -271,7 +320,7 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                         for (int64_t b = 0; b < batch; ++b)
                         {
                             sfe_step_record &r = recs[static_cast<size_t>(b)];
-                            r.sim_time = c->scheduler->schedule_step(status.data() + static_cast<size_t>(b) * n);
+                            if (detailed) r.sim_time = c->scheduler->schedule_step(status.data() + static_cast<size_t>(b) * n);
                             // update_run_data  src/chip.cpp:462-475
                             rd.total_energy += r.total_energy;
                             rd.synapse_energy += r.synapse_energy;
@@ -284,10 +333,10 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                             rd.neurons_updated += r.neurons_updated;
                             rd.neurons_fired += r.neurons_fired;
                             if (req != nullptr && req->steps != nullptr) req->steps[done + b] = r;
-                            if (req != nullptr && req->status != nullptr)
+                            if (detailed && req != nullptr && req->status != nullptr)
                                 std::memcpy(req->status + static_cast<size_t>(done + b) * n, status.data() + static_cast<size_t>(b) * n, n);
                         }
-                        sched_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
+                        if (detailed) sched_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - s0).count();
                         done += batch;
                     }
                     rd.timesteps_executed = timesteps;

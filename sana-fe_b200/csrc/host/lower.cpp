@@ -111,6 +111,34 @@ UnitModel parse_model(const PipelineUnitConfiguration &u)
     throw std::invalid_argument("Pipeline model not supported (" + m + ")\n"); // src/models.cpp:964-966
 }
 
+// Number of "input"-model soma units created before unit `key` of core `core_id` when the chip is
+// built (SpikingChip::SpikingChip, src/chip.cpp:61-92: tiles, cores, pipeline units in order;
+// name[a..b] families expand ascending). The reference seeds every InputModel's std::mt19937 with
+// a running instance counter (src/models.hpp:347,366), so this ordinal fixes the Poisson stream.
+bool is_builtin_input(const PipelineUnitConfiguration &u)
+{
+    return !u.model_info.plugin_library_path.has_value() && u.model_info.name == "input";
+}
+
+uint32_t input_unit_ordinal(const Architecture &arch, const size_t core_id, const UnitKey &key)
+{
+    uint32_t ordinal = 0;
+    for (const TileConfiguration &tile : arch.tiles)
+        for (const CoreConfiguration &core : tile.cores)
+        {
+            const bool here = core.address.id == core_id;
+            for (size_t f = 0; f < core.pipeline_hw.size(); ++f)
+            {
+                const PipelineUnitConfiguration &u = core.pipeline_hw[f];
+                if (here && static_cast<int>(f) == key.family)
+                    return ordinal + static_cast<uint32_t>(key.instance - u.first_instance());
+                if (is_builtin_input(u)) ordinal += u.is_range ? static_cast<uint32_t>(u.range_last - u.range_first + 1) : 1u;
+            }
+            if (here) throw std::logic_error("input_unit_ordinal: unit not found in its core");
+        }
+    throw std::logic_error("input_unit_ordinal: core not found");
+}
+
 // Core::get_hw  src/core.cpp:61-97
 UnitKey get_hw(const CoreConfiguration &core, const std::string &hw_name, const bool is_synapse,
         const bool is_dendrite, const bool is_soma)
@@ -250,9 +278,6 @@ void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, con
         else if (key == "poisson")
         {
             unit.poisson = a.as_double();
-            if (unit.poisson > 0.0)
-                throw std::runtime_error("input model 'poisson' (libstdc++ mt19937 stream) is not implemented by "
-                                         "the B200 engine yet");
         }
         else if (key == "rate") unit.rate = a.as_double();
     }
@@ -420,6 +445,8 @@ void HostTables::finalize_view(const Architecture &arch)
     v.n_soma_classes = static_cast<uint32_t>(soma_classes.size());
     v.n_cost_classes = static_cast<uint32_t>(cost_classes.size());
     v.n_inputs = static_cast<uint32_t>(inputs.size());
+    v.input_seed_base = input_seed_base;
+    v.n_poisson_cols = n_poisson_cols;
     v.n_hh = static_cast<uint32_t>(hh.size());
     v.n_probes = static_cast<uint32_t>(probes.size());
     v.n_axons_out = axon_out_target.size();
@@ -459,6 +486,16 @@ void HostTables::finalize_view(const Architecture &arch)
     v.syn_weight = syn_weight.empty() ? nullptr : syn_weight.data();
     v.syn_meta = syn_meta.empty() ? nullptr : syn_meta.data();
     v.synth = synth.has_value() ? &*synth : nullptr;
+}
+
+uint32_t count_input_units(const Architecture &arch)
+{
+    uint32_t n = 0;
+    for (const TileConfiguration &tile : arch.tiles)
+        for (const CoreConfiguration &core : tile.cores)
+            for (const PipelineUnitConfiguration &u : core.pipeline_hw)
+                if (is_builtin_input(u)) n += u.is_range ? static_cast<uint32_t>(u.range_last - u.range_first + 1) : 1u;
+    return n;
 }
 
 void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTables &out)
@@ -679,6 +716,8 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                         std::find(soma.sharing.begin(), soma.sharing.end(), dev) - soma.sharing.begin());
                 d.rate = soma.rate;
                 d.poisson = soma.poisson;
+                d.unit = input_unit_ordinal(arch, c, ln.soma);
+                d.poisson_col = soma.poisson > 0.0 ? out.n_poisson_cols++ : 0xFFFFFFFFu;
                 out.neuron_aux[dev] = static_cast<uint32_t>(out.inputs.size());
                 out.inputs.push_back(d);
             }

@@ -37,6 +37,8 @@ struct HostTables
     std::vector<double> syn_weight;
     std::vector<uint32_t> syn_meta;
     std::optional<sfe_synth_spec> synth;
+    uint32_t input_seed_base{0}; // "input" units created in this process before this chip (set by the chip)
+    uint32_t n_poisson_cols{0};
     sfe_tables view{};
 
     // host-only naming: device index <-> (group, offset); groups in lexicographic order
@@ -63,6 +65,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
 // synapse arrays on the host (tests, CPU oracle); otherwise they are generated
 // on the device from the spec.
 void lower_synthetic(const Architecture &arch, const SynthRequest &req, bool materialize, HostTables &out);
+
+// Number of built-in "input" soma units an architecture instantiates (every InputModel the
+// reference's SpikingChip constructor creates advances the process-wide seed counter,
+// src/chip.cpp:61-92, src/models.hpp:347,366).
+uint32_t count_input_units(const Architecture &arch);
 
 // MappedNeuron.set_attributes for one numeric soma attribute: patches the host
 // tables (splitting the neuron's parameter class when needed). Returns true if

@@ -68,7 +68,8 @@ class AxonIn(C.Structure):
 
 class InputDesc(C.Structure):
     _fields_ = [("spikes_off", C.c_uint32), ("spikes_len", C.c_uint32), ("share_count", C.c_uint32),
-                ("share_rank", C.c_uint32), ("rate", C.c_double), ("poisson", C.c_double)]
+                ("share_rank", C.c_uint32), ("rate", C.c_double), ("poisson", C.c_double),
+                ("unit", C.c_uint32), ("poisson_col", C.c_uint32)]
 
 
 class HHInit(C.Structure):
@@ -93,7 +94,7 @@ class Tables(C.Structure):
                 ("n_input_spikes", C.c_uint64), ("hh", C.POINTER(HHInit)), ("probes", C.POINTER(C.c_uint32)),
                 ("axons_in", C.POINTER(AxonIn)), ("axon_src", C.POINTER(C.c_uint32)),
                 ("syn_weight", C.POINTER(C.c_double)), ("syn_meta", C.POINTER(C.c_uint32)),
-                ("synth", C.POINTER(SynthSpec))]
+                ("synth", C.POINTER(SynthSpec)), ("input_seed_base", C.c_uint32), ("n_poisson_cols", C.c_uint32)]
 
 
 class StepRecord(C.Structure):
@@ -154,6 +155,10 @@ def lib():
         "sfe_engine_collect_records": (i64, [vp, vp, i64]),
         "sfe_engine_partition_info": (C.c_int, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
         "sfe_chip_set_partition": (C.c_int, [vp, u32, u32]),
+        "sfe_chip_set_input_seed_base": (C.c_int, [vp, u32]),
+        "sfe_engine_set_input_overlay": (C.c_int, [vp, vp, i64, u32]),
+        "sfe_poisson_create": (vp, [C.POINTER(Tables)]), "sfe_poisson_destroy": (None, [vp]),
+        "sfe_poisson_cols": (u32, [vp]), "sfe_poisson_fill": (C.c_int, [vp, vp, i64]),
         "sfe_engine_read_log_tail": (i64, [vp, vp, i64]),
         "sfe_nccl_get_unique_id": (C.c_int, [vp, cstr]),
         "sfe_engine_comm_init": (C.c_int, [vp, vp, cstr]),
@@ -272,6 +277,11 @@ class SpikingChip:
     def set_partition(self, rank, world):
         """Multi-GPU: this chip simulates core range `rank` of `world` (call before load)."""
         _check(lib().sfe_chip_set_partition(self._h, rank, world))
+
+    def set_input_seed_base(self, base=0):
+        """Poisson inputs: seed the generators as if `base` "input" units had been created in this
+        process before this chip's (the reference counts them process-wide). Call before load."""
+        _check(lib().sfe_chip_set_input_seed_base(self._h, base))
 
     def load(self, net, overwrite=False):
         _check(lib().sfe_chip_load(self._h, net._h))

@@ -62,6 +62,8 @@ CASES = {
     "truenorth": dict(arch=f"{REF}/arch/truenorth.yaml", net=f"{SRC}/tn_snn.yaml", max_tiles=8, steps=120),
     # ordered fp64 accumulation
     "frac": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/frac_snn.yaml", steps=200),
+    # Poisson inputs: libstdc++ mt19937 streams seeded by the InputModel construction order
+    "poisson": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/poisson_snn.yaml", steps=300),
 }
 
 

@@ -1,0 +1,43 @@
+"""Device tests of the models added after this round's GPU budget was spent (their CPU side — lowering, host
+draws, restatement vs the reference's goldens — is pinned in test_oracle_vs_reference.py and
+test_poisson_inputs.py). Collected last on purpose: see helpers.NEW_GOLDEN_CASES."""
+import numpy as np
+import pytest
+
+import sanafe_b200 as sfe
+from helpers import NEW_GOLDEN_CASES, Oracle, check_against_golden, golden, load_chip
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", NEW_GOLDEN_CASES)
+def test_engine_matches_reference_new_cases(name):
+    chip = load_chip(name, device=0)
+    g = golden(name)
+    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+    check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
+
+
+def test_poisson_sim_calls_continue_the_streams():
+    """sim(100) + reset() + sim(200) draws the same random spikes as one sim(300): neither the generators nor
+    the spike-train cursor are rewound by reset (InputModel::reset, src/models.hpp:358)."""
+    a = load_chip("poisson", device=0)
+    b = load_chip("poisson", device=0)
+    _, out_a = a.sim_raw(300, steps=True, fired=True)
+    _, out_b1 = b.sim_raw(100, "detailed", steps=True, fired=True)
+    _, out_b2 = b.sim_raw(200, steps=True, fired=True)
+    n_in = 3  # in.0..2 are device neurons of cores 0.0 / 1.2; compare the input neurons' raster columns only
+    t = a.tables
+    in_idx = [a.neuron_index("in", k) for k in range(n_in)]
+    whole = out_a["fired_bits"]
+    parts = np.concatenate([out_b1["fired_bits"], out_b2["fired_bits"]])
+    for i in in_idx:
+        assert np.array_equal((whole[:, i >> 5] >> (i & 31)) & 1, (parts[:, i >> 5] >> (i & 31)) & 1)
+    assert np.array_equal(whole, parts)
+    assert t.n_poisson_cols == 3
+
+
+def test_poisson_engine_refuses_to_step_without_an_overlay():
+    chip = load_chip("poisson", device=0)
+    assert sfe.lib().sfe_engine_enqueue(chip.engine, 1) != 0
+    assert b"Poisson" in sfe.lib().sfe_last_error()
