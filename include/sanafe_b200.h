@@ -385,6 +385,17 @@ int sfe_chip_set_partition(sfe_chip *c, uint32_t rank, uint32_t world);
  * InputModel::instance_counter is a process-wide static, src/models.hpp:366); sfe_chip_create keeps that count.
  * This overrides it for the chip (0 = as if the chip were the first one of a fresh process). Call before load. */
 int sfe_chip_set_input_seed_base(sfe_chip *c, uint32_t base);
+
+/* ---- design-space exploration: independent chips side by side on one GPU (BASELINE config 5) ----------
+ * The reference runs a sweep as separate processes (scripts/, one `sim` per design point). Here the n chips of a
+ * sweep live in one process; every chip owns a stream, and `host_threads` worker threads (0 = min(n, 32)) drive
+ * sfe_chip_load / sfe_chip_sim of different chips concurrently, so the kernels of that many chips overlap on the
+ * device. Each chip goes through exactly the code path of a lone chip: its results are those of running it alone.
+ * reqs: NULL or n trace requests; out: NULL or n records. Returns 0, or -1 with sfe_last_error() naming the first
+ * chip that failed (the others still ran). */
+int sfe_batch_load(sfe_chip *const *chips, const sfe_net *const *nets, uint32_t n, uint32_t host_threads);
+int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timesteps, int timing_model,
+        const sfe_trace_request *reqs, sfe_run_data *out, uint32_t host_threads);
 void sfe_chip_destroy(sfe_chip *c);
 /* SpikingChip::load  src/chip.cpp:129-138 */
 int sfe_chip_load(sfe_chip *c, const sfe_net *net);

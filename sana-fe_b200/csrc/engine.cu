@@ -36,6 +36,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -2285,12 +2286,26 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         sfe::set_last_error("a core needs more than 200 KB of shared-memory dendrite accumulators");
         return -1;
     }
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
-    SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(std::max<size_t>(smem_max, 1024))));
+    // The opt-in limit is a property of the FUNCTION (per device), not of this engine: several engines
+    // live in one process (design-space batches, emulated partitions), so it only ever grows — an engine
+    // with a small need must not lower it under one that needs more.
+    {
+        static std::mutex mu;
+        static int raised[64] = {};
+        const std::lock_guard<std::mutex> lock(mu);
+        const int dev = std::max(0, std::min(e->device, 63));
+        const int need = static_cast<int>(std::max<size_t>(smem_max, 1024));
+        if (need > raised[dev])
+        {
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            raised[dev] = need;
+        }
+    }
     {
         int per_sm = 1, sms = 1;
         if (e->fanout_variant == kStreamQ4)

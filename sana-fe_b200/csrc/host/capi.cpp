@@ -12,6 +12,8 @@
 #include <memory>
 #include <mutex>
 #include <sstream>
+#include <thread>
+#include <vector>
 
 #include "../engine.hpp"
 #include "desc.hpp"
@@ -349,6 +351,83 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                 return 0;
             },
             -1);
+}
+
+namespace
+{
+// n independent jobs over a pool of host threads; job(k) returns 0 or -1 (+ the thread's last error)
+template <typename Job> int run_batch(const uint32_t n, uint32_t host_threads, const char *what, Job &&job)
+{
+    if (host_threads == 0) host_threads = std::min<uint32_t>(n, 32u);
+    host_threads = std::max<uint32_t>(1u, std::min<uint32_t>(host_threads, n));
+    std::atomic<uint32_t> next{0};
+    std::mutex mu;
+    uint32_t first_bad = UINT32_MAX;
+    std::string first_msg;
+    auto worker = [&]() {
+        for (uint32_t k = next.fetch_add(1); k < n; k = next.fetch_add(1))
+        {
+            int rc = -1;
+            try
+            {
+                rc = job(k);
+            }
+            catch (const std::exception &e)
+            {
+                sfe::set_last_error(e.what());
+            }
+            if (rc != 0)
+            {
+                const std::lock_guard<std::mutex> lock(mu);
+                if (k < first_bad)
+                {
+                    first_bad = k;
+                    first_msg = sfe_last_error();
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t w = 1; w < host_threads; ++w) pool.emplace_back(worker);
+    worker();
+    for (std::thread &t : pool) t.join();
+    if (first_bad == UINT32_MAX) return 0;
+    sfe::set_last_error(std::string(what) + ": chip " + std::to_string(first_bad) + ": " + first_msg);
+    return -1;
+}
+} // namespace
+
+extern "C" int sfe_batch_load(sfe_chip *const *chips, const sfe_net *const *nets, uint32_t n, uint32_t host_threads)
+{
+    if (n == 0) return 0;
+    if (chips == nullptr || nets == nullptr)
+    {
+        sfe::set_last_error("sfe_batch_load: null argument");
+        return -1;
+    }
+    return run_batch(n, host_threads, "sfe_batch_load", [&](uint32_t k) { return sfe_chip_load(chips[k], nets[k]); });
+}
+
+extern "C" int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timesteps, int timing_model,
+        const sfe_trace_request *reqs, sfe_run_data *out, uint32_t host_threads)
+{
+    if (n == 0) return 0;
+    if (chips == nullptr)
+    {
+        sfe::set_last_error("sfe_batch_sim: null argument");
+        return -1;
+    }
+    for (uint32_t a = 0; a < n; ++a)
+        for (uint32_t b = a + 1; b < n; ++b)
+            if (chips[a] == chips[b])
+            {
+                sfe::set_last_error("sfe_batch_sim: the same chip appears twice");
+                return -1;
+            }
+    return run_batch(n, host_threads, "sfe_batch_sim", [&](uint32_t k) {
+        return sfe_chip_sim(chips[k], timesteps, timing_model, reqs != nullptr ? &reqs[k] : nullptr,
+                out != nullptr ? &out[k] : nullptr);
+    });
 }
 
 extern "C" int sfe_chip_reset(sfe_chip *c)

@@ -1,0 +1,80 @@
+"""BASELINE config 5 (design-space sweep), CPU side: the generated TrueNorth-shaped chip equals the
+reference's arch/truenorth.yaml when its costs are zeroed, the conv SNN lowers to the expected shape, the batch
+loader (worker threads) produces the tables of a sequential load, and cost multipliers scale energies while leaving
+the spikes alone (checked on the CPU restatement)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import sanafe_b200 as sfe
+from helpers import REFERENCE_ROOT, Oracle
+from sanafe_b200 import dse
+
+
+def table_bytes(t):
+    """The lowered tables that decide the simulation, as bytes."""
+    parts = [C.string_at(t.cores, C.sizeof(t.cores.contents) * t.n_cores),
+             C.string_at(t.neuron_class, 4 * t.n_neurons), C.string_at(t.neuron_bias, 8 * t.n_neurons),
+             C.string_at(t.soma_classes, C.sizeof(t.soma_classes.contents) * t.n_soma_classes),
+             C.string_at(t.cost_classes, C.sizeof(t.cost_classes.contents) * t.n_cost_classes),
+             C.string_at(t.axons_in, C.sizeof(t.axons_in.contents) * t.n_axons_in),
+             C.string_at(t.syn_weight, 8 * t.n_synapses), C.string_at(t.syn_meta, 4 * t.n_synapses)]
+    return b"".join(parts)
+
+
+def test_sweep_points():
+    pts = dse.sweep_points()
+    assert len(pts) == 1024 and len(set(pts)) == 1024
+    assert {p[0] for p in pts} == {8 * k for k in range(1, 33)}
+    assert max(dse.cores_needed(p[0]) for p in pts) <= 4096
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE_ROOT, "arch", "truenorth.yaml")),
+                    reason="reference tree not present")
+def test_generated_chip_has_the_shape_of_truenorth_yaml(tmp_path):
+    """Same network on arch/truenorth.yaml and on the generated chip with every cost multiplied by 0:
+    identical lowered tables (the shipped file has all costs 0)."""
+    text, cores = dse.snn_yaml(192)
+    (tmp_path / "snn.yaml").write_text(text)
+    (tmp_path / "arch.yaml").write_text(dse.arch_yaml(0.0, tiles=4096))
+    tabs = []
+    for arch_path in (os.path.join(REFERENCE_ROOT, "arch", "truenorth.yaml"), str(tmp_path / "arch.yaml")):
+        arch = sfe.load_arch(arch_path)
+        chip = sfe.SpikingChip(arch, device=-1)
+        chip.load(sfe.load_net(str(tmp_path / "snn.yaml"), arch))
+        tabs.append((chip, table_bytes(chip.tables)))
+    assert tabs[0][1] == tabs[1][1]
+    t = tabs[0][0].tables
+    assert t.n_neurons == sum(dse.LAYERS.values()) == 10043
+    assert t.n_synapses == 3600 * 9 + 5408 * 144 + 5408 * 11
+    assert t.mapped_cores == cores == dse.cores_needed(192)
+
+
+def test_batch_load_equals_sequential_load_and_costs_only_scale_energy(tmp_path):
+    points = [(64, 1.0), (64, 2.0), (200, 1.0), (256, 0.5)]
+    sweep = dse.Sweep(points, str(tmp_path), device=-1, host_threads=3)
+    # sequential load of the same design points
+    for (npc, mult), chip in zip(points, sweep.chips):
+        (tmp_path / "a.yaml").write_text(dse.arch_yaml(mult, tiles=dse.cores_needed(npc)))
+        (tmp_path / "n.yaml").write_text(dse.snn_yaml(npc)[0])
+        arch = sfe.load_arch(str(tmp_path / "a.yaml"))
+        lone = sfe.SpikingChip(arch, device=-1)
+        lone.load(sfe.load_net(str(tmp_path / "n.yaml"), arch))
+        assert table_bytes(lone.tables) == table_bytes(chip.tables), (npc, mult)
+    steps = 24
+    runs = [Oracle(chip).run(steps) for chip in sweep.chips]
+    (rd1, o1), (rd2, o2), (rd3, o3), _ = runs
+    # a cost multiplier changes no spike; energy and simulated time scale with it (powers of two: exactly)
+    assert np.array_equal(o1["fired_bits"], o2["fired_bits"]) and rd1.spikes == rd2.spikes > 0
+    assert rd2.total_energy == 2.0 * rd1.total_energy and rd2.sim_time == 2.0 * rd1.sim_time
+    # a different mapping changes messages and time, not the network's behaviour
+    assert rd3.neurons_fired == rd1.neurons_fired and rd3.spikes == rd1.spikes
+    assert rd3.packets_sent != rd1.packets_sent
+
+
+def test_batch_sim_needs_a_device(tmp_path):
+    sweep = dse.Sweep([(128, 1.0), (128, 2.0)], str(tmp_path), device=-1)
+    with pytest.raises(sfe.SanafeError, match="sfe_batch_sim: chip 0: .*no CUDA device"):
+        sweep.sim(3)

@@ -41,3 +41,29 @@ def test_poisson_engine_refuses_to_step_without_an_overlay():
     chip = load_chip("poisson", device=0)
     assert sfe.lib().sfe_engine_enqueue(chip.engine, 1) != 0
     assert b"Poisson" in sfe.lib().sfe_last_error()
+
+
+def test_dse_batch_equals_lone_runs_and_the_restatement(tmp_path):
+    """BASELINE config 5: chips stepped side by side by sfe_batch_sim give, bit for bit, what each gives when
+    run alone, and what the CPU restatement gives for the same design point."""
+    from sanafe_b200 import dse
+    points = [(64, 1.0), (64, 2.0), (200, 1.0), (200, 0.5), (32, 1.5), (32, 1.0)]
+    steps = 40
+    batch = dse.Sweep(points, str(tmp_path / "batch"), device=0, host_threads=4)
+    rds = batch.sim(steps)
+    rds2 = batch.sim(steps)  # state persists across batched calls like across sim() calls
+    lone = dse.Sweep(points, str(tmp_path / "lone"), device=0, host_threads=4, share=batch)
+    host = dse.Sweep(points, str(tmp_path / "host"), device=-1, host_threads=4, share=batch)
+    for k, point in enumerate(points):
+        rd_l, _ = lone.chips[k].sim_raw(steps)
+        rd_l2, _ = lone.chips[k].sim_raw(steps)
+        oracle = Oracle(host.chips[k])
+        rd_o, _ = oracle.run(steps)
+        rd_o2, _ = oracle.run(steps)
+        for got, alone, want in ((rds[k], rd_l, rd_o), (rds2[k], rd_l2, rd_o2)):
+            for key in ("timestep_start", "spikes", "packets_sent", "neurons_updated", "neurons_fired"):
+                assert getattr(got, key) == getattr(alone, key) == getattr(want, key), (point, key)
+            for key in ("total_energy", "synapse_energy", "soma_energy", "network_energy", "sim_time"):
+                assert getattr(got, key) == getattr(alone, key), (point, key)
+                assert abs(getattr(got, key) - getattr(want, key)) <= 1e-9 * abs(getattr(want, key)), (point, key)
+        assert rds[k].spikes > 0
