@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 2
+#define SFE_ABI_VERSION 3
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -85,6 +85,7 @@ enum
 #define SFE_SOMA_FORCE_UPDATE 1u
 #define SFE_SOMA_LEAK_TOWARDS_ZERO 2u
 #define SFE_SOMA_LOG_U 4u
+#define SFE_SOMA_NOISE 8u /* LIF unit with a file noise stream: neuron_aux indexes sfe_tables.noise */
 
 /* ---- lowered tables ------------------------------------------------------ */
 typedef struct sfe_tile_desc
@@ -174,6 +175,16 @@ typedef struct sfe_input_desc /* "input" soma: state is per hardware UNIT (src/m
     uint32_t poisson_col;            /* column of this neuron in the per-step Poisson overlay, or 0xFFFFFFFF (poisson == 0) */
 } sfe_input_desc;
 
+/* LIF file noise (LoihiLifModel::loihi_generate_noise, src/models.cpp:589-650): the unit reads one entry of its
+ * file per update of any of its compartments and rewinds at the end of the file. The entries, already masked and
+ * sign-extended, sit in sfe_tables.noise_values[off .. off+len); at step index s the neuron of rank share_rank among
+ * the share_count neurons of the unit consumes entry (s * share_count + share_rank) mod len. */
+typedef struct sfe_noise_desc
+{
+    uint32_t off, len;
+    uint32_t share_count, share_rank;
+} sfe_noise_desc;
+
 typedef struct sfe_hh_init /* Hodgkin-Huxley plugin initial state, one neuron per unit */
 {
     double m, n, h, current;
@@ -220,6 +231,16 @@ typedef struct sfe_tables
     /* Poisson inputs: "input" units created in this process before this chip (the reference's counter is a
      * process-wide static) and the number of neurons with poisson > 0 (= columns of the overlay) */
     uint32_t input_seed_base, n_poisson_cols;
+
+    /* LIF file noise streams */
+    const sfe_noise_desc *noise;
+    const double *noise_values;
+    uint64_t n_noise_values;
+    uint32_t n_noise;
+    /* model-defined neuron traces (src/chip.cpp:1478-1517, 1664-1702): device indices of the LIF neurons with
+     * log_u, whose input current `u` is traced each step, in trace order */
+    uint32_t n_u_probes;
+    const uint32_t *u_probes;
 } sfe_tables;
 
 /* one record per simulated timestep (src/timestep.hpp:21-42) */
@@ -248,6 +269,7 @@ typedef struct sfe_trace_request
     uint32_t *fired_bits;     /* [timesteps][ceil(n_neurons/32)] fired bitmask per step, device index order */
     double *potentials;       /* [timesteps][n_probes] */
     uint8_t *status;          /* [timesteps][n_neurons] SFE_STATUS_* (detailed-timing feed / debugging) */
+    double *neuron_traces;    /* [timesteps][n_u_probes] model-defined traces (LIF `u` of the log_u neurons) */
 } sfe_trace_request;
 
 const char *sfe_last_error(void);
@@ -432,6 +454,9 @@ size_t sfe_chip_format_messages(sfe_chip *chip, const uint8_t *status, int64_t t
         int timing_model, char *buf, size_t cap);
 /* "group.offset\n" of every potential probe, in potentials.csv column order (src/chip.cpp:1454-1476) */
 size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap);
+/* header cells of neurons.csv (src/chip.cpp:1478-1517): "group.offset/trace" of every model-defined trace column
+ * (sfe_trace_request.neuron_traces), one per line */
+size_t sfe_chip_trace_names(const sfe_chip *c, char *buf, size_t cap);
 
 #ifdef __cplusplus
 }

@@ -224,6 +224,14 @@ static int lif_update(sfe_oracle *o, const sfe_soma_class *c, size_t i, int has_
         v *= c->leak;
     }
     v = (double) ((int) (v * 64.0)) / 64.0; /* loihi_quantize: C cast, truncation toward zero */
+    if (c->flags & SFE_SOMA_NOISE)
+    {
+        /* loihi_generate_noise  src/models.cpp:535-539, 589-650: the unit consumes one file entry per
+         * update of any of its compartments (in-core order) and rewinds at the end of the file */
+        const sfe_noise_desc *nd = &o->t->noise[o->t->neuron_aux[i]];
+        const uint64_t cursor = (uint64_t) steps_done * nd->share_count + nd->share_rank;
+        v += o->t->noise_values[nd->off + cursor % nd->len];
+    }
     if (o->refractory[i] <= 0)
     {
         v += bias;
@@ -349,7 +357,8 @@ static double potential_of(const sfe_oracle *o, size_t i)
     return o->v[i];
 }
 
-static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, double *potentials, uint8_t *status_out)
+static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, double *potentials, uint8_t *status_out,
+        double *neuron_traces)
 {
     const sfe_tables *t = o->t;
     const int64_t T = ++o->total_timesteps;   /* SpikingChip::step  src/chip.cpp:549-560 */
@@ -459,6 +468,8 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
     if (status_out) memcpy(status_out, o->status, t->n_neurons);
     if (potentials)
         for (uint32_t p = 0; p < t->n_probes; ++p) potentials[p] = potential_of(o, t->probes[p]);
+    if (neuron_traces) /* sim_trace_record_neuron_traces  src/chip.cpp:1664-1702: LIF `u` of the log_u neurons */
+        for (uint32_t p = 0; p < t->n_u_probes; ++p) neuron_traces[p] = o->u[t->u_probes[p]];
 
     /* ---- process_messages ------------------------------------------------ */
     for (uint32_t ci = 0; ci < t->n_cores; ++ci)
@@ -578,7 +589,8 @@ int sfe_oracle_run(sfe_oracle *o, int64_t timesteps, const sfe_trace_request *re
         sfe_step_record rec;
         one_step(o, &rec, (req && req->fired_bits) ? req->fired_bits + (size_t) s * words : NULL,
                 (req && req->potentials) ? req->potentials + (size_t) s * t->n_probes : NULL,
-                (req && req->status) ? req->status + (size_t) s * t->n_neurons : NULL);
+                (req && req->status) ? req->status + (size_t) s * t->n_neurons : NULL,
+                (req && req->neuron_traces) ? req->neuron_traces + (size_t) s * t->n_u_probes : NULL);
         if (req && req->steps) req->steps[s] = rec;
         /* update_run_data  src/chip.cpp:462-475 */
         rd.total_energy += rec.total_energy;

@@ -130,6 +130,10 @@ struct DevTables
     // syn_w / syn_meta; a third of their bytes per synaptic event.
     const uint32_t *syn_q4;
     const uint32_t *probes;
+    const uint32_t *u_probes;         // LIF neurons whose input current u is traced (log_u)
+    const sfe_noise_desc *noise;      // LIF file noise: per neuron of a unit with a stream
+    const double *noise_values;
+    uint32_t n_u_probes, pad_probes;
     uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
     // fused finalize: cores with work items fold themselves; the others are folded at the end
     const uint32_t *soma_only_list;
@@ -340,8 +344,9 @@ template <typename T> __device__ __forceinline__ T block_sum(T x, T *scratch)
 // Soma models (device functors). Same operation order as the reference; no FMA.
 // ---------------------------------------------------------------------------
 // LoihiLifModel::update  src/models.cpp:497-567
+template <bool kNoise = false>
 __device__ __forceinline__ int lif_update(const sfe_soma_class &c, double &v, double &u, int &refractory,
-        const double bias, const bool has_in, const double in, const long long steps_done)
+        const double bias, const bool has_in, const double in, const long long steps_done, const double noise = 0.0)
 {
     int state = SFE_STATUS_IDLE;
     if ((fabs(v) > 0.0) || has_in || (fabs(bias) > 0.0) || (c.flags & SFE_SOMA_FORCE_UPDATE)) state = SFE_STATUS_UPDATED;
@@ -351,6 +356,7 @@ __device__ __forceinline__ int lif_update(const sfe_soma_class &c, double &v, do
         v = v * c.leak;
     }
     v = static_cast<double>(__double2int_rz(v * 64.0)) / 64.0; // loihi_quantize (C int cast)
+    if constexpr (kNoise) v = v + noise;                        // src/models.cpp:535-539
     if (refractory <= 0)
     {
         v = v + bias;
@@ -854,7 +860,17 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             {
                 double v = v0, u = u0;
                 int refr = refr0;
-                st = lif_update(c, v, u, refr, bias, has_in, in, steps_done);
+                bool noisy = false;
+                if constexpr (kExotic) noisy = (c.flags & SFE_SOMA_NOISE) != 0u;
+                if (noisy)
+                {
+                    // the unit's stream: one entry per update of any of its neurons, rewinding at the end
+                    const sfe_noise_desc nd = t.noise[t.neuron_aux[i]];
+                    const unsigned long long cursor =
+                            static_cast<unsigned long long>(steps_done) * nd.share_count + nd.share_rank;
+                    st = lif_update<true>(c, v, u, refr, bias, has_in, in, steps_done, t.noise_values[nd.off + cursor % nd.len]);
+                }
+                else st = lif_update(c, v, u, refr, bias, has_in, in, steps_done);
                 s.v[i] = v;
                 s.u[i] = u;
                 s.refractory[i] = refr;
@@ -950,7 +966,13 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
 __global__ void probe_kernel(const DevTables t, const DevState s)
 {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= t.n_probes) return;
+    if (p >= t.n_probes + t.n_u_probes) return;
+    if (p >= t.n_probes)
+    {
+        // model-defined trace: LIF input current (LoihiLifModel::get_neuron_traces, src/models.cpp:653-662)
+        s.probe_out[p] = s.u[t.u_probes[p - t.n_probes]];
+        return;
+    }
     const uint32_t i = t.probes[p];
     const uint32_t model = t.classes[t.neuron_class[i]].model;
     double v = s.v[i];
@@ -1810,7 +1832,7 @@ struct sfe_engine
     uint32_t *d_fired_local{nullptr}; // this rank's raster slice (slice_words)
     uint32_t *d_fired_global{nullptr};// world * slice_words
     bool external_exchange{false};
-    uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0};
+    uint32_t n_neurons{0}, n_probes{0}, n_cores{0}, n_hh{0}, n_u_probes{0};
     int64_t total_timesteps{0};
     int64_t launches{0};
     int64_t log_read{0}; // steps already collected from the device log
@@ -1915,11 +1937,14 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     SFE_CUDA(cudaEventCreate(&e->ev_end));
     e->n_neurons = tb->n_neurons;
     e->n_probes = tb->n_probes;
+    e->n_u_probes = tb->n_u_probes;
     e->n_cores = tb->n_cores;
     e->n_hh = tb->n_hh;
     e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
-        if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH) e->exotic = true;
+        if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH ||
+                (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
+            e->exotic = true;
     e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
     if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
 
@@ -2059,6 +2084,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->upload(&e->t.axons_in, dev_axons.data(), dev_axons.size()) != 0) return -1;
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     if (e->upload(&e->t.probes, tb->probes, tb->n_probes) != 0) return -1;
+    if (e->upload(&e->t.u_probes, tb->u_probes, tb->n_u_probes) != 0) return -1;
+    if (e->upload(&e->t.noise, tb->noise, tb->n_noise) != 0) return -1;
+    if (e->upload(&e->t.noise_values, tb->noise_values, tb->n_noise_values) != 0) return -1;
+    for (uint32_t k = 0; k < tb->n_noise; ++k)
+        if (tb->noise[k].len == 0 || tb->noise[k].share_count == 0 ||
+                static_cast<uint64_t>(tb->noise[k].off) + tb->noise[k].len > tb->n_noise_values)
+        {
+            sfe::set_last_error("sfe_engine_create: malformed sfe_noise_desc");
+            return -1;
+        }
     // heaviest destination cores first (longest-processing-time order for the ticket queue)
     std::stable_sort(e->fanout_list.begin(), e->fanout_list.end(),
             [&](uint32_t a, uint32_t b) { return tb->cores[a].syn_count > tb->cores[b].syn_count; });
@@ -2090,6 +2125,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     }
     e->t.n_cores = tb->n_cores;
     e->t.n_probes = tb->n_probes;
+    e->t.n_u_probes = tb->n_u_probes;
     e->t.n_neurons = tb->n_neurons;
     e->t.n_cost_classes = tb->n_cost_classes;
     e->t.n_soma_classes = tb->n_soma_classes;
@@ -2237,7 +2273,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->log_cap = 4096;
     e->s.log_cap = e->log_cap;
     if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
-    if (e->alloc(&e->s.probe_out, tb->n_probes) != 0) return -1;
+    if (e->alloc(&e->s.probe_out, static_cast<size_t>(tb->n_probes) + tb->n_u_probes) != 0) return -1;
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->s.work, 1) != 0) return -1;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
@@ -2579,9 +2615,9 @@ static int enqueue_step(sfe_engine *e, bool probes)
         launch_soma(e);
         ++e->launches;
     }
-    if (probes && e->n_probes > 0)
+    if (probes && e->n_probes + e->n_u_probes > 0)
     {
-        probe_kernel<<<(e->n_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
+        probe_kernel<<<(e->n_probes + e->n_u_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
         ++e->launches;
     }
     if (!e->fanout_list.empty())
@@ -2727,10 +2763,12 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
     const bool want_fired = req != nullptr && req->fired_bits != nullptr;
     const bool want_pot = req != nullptr && req->potentials != nullptr && e->n_probes > 0;
     const bool want_status = req != nullptr && req->status != nullptr;
+    const bool want_u = req != nullptr && req->neuron_traces != nullptr && e->n_u_probes > 0;
     const size_t words = (static_cast<size_t>(e->n_neurons) + 31) / 32;
     // per-step staging in pinned memory, drained once per batch (no per-step host sync)
     const size_t per_step = (want_fired ? e->fired_words * sizeof(uint32_t) : 0) +
-            (want_pot ? e->n_probes * sizeof(double) : 0) + (want_status ? e->n_neurons : 0);
+            (want_pot ? e->n_probes * sizeof(double) : 0) + (want_u ? e->n_u_probes * sizeof(double) : 0) +
+            (want_status ? e->n_neurons : 0);
     const int64_t batch_cap = per_step == 0 ? e->log_cap
                                             : std::max<int64_t>(1, std::min<int64_t>(e->log_cap, (256ll << 20) / static_cast<int64_t>(per_step)));
     std::vector<sfe_step_record> recs;
@@ -2754,12 +2792,20 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 SFE_CUDA(cudaMemcpyAsync(stage, e->d_fired_global, e->fired_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
                 stage += e->fired_words * sizeof(uint32_t);
             }
+            if (want_pot || want_u)
+            {
+                probe_kernel<<<(e->n_probes + e->n_u_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
+                ++e->launches;
+            }
             if (want_pot)
             {
-                probe_kernel<<<(e->n_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
-                ++e->launches;
                 SFE_CUDA(cudaMemcpyAsync(stage, e->s.probe_out, e->n_probes * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
                 stage += e->n_probes * sizeof(double);
+            }
+            if (want_u)
+            {
+                SFE_CUDA(cudaMemcpyAsync(stage, e->s.probe_out + e->n_probes, e->n_u_probes * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+                stage += e->n_u_probes * sizeof(double);
             }
             if (want_status)
                 SFE_CUDA(cudaMemcpyAsync(stage, e->s.status, e->n_neurons, cudaMemcpyDeviceToHost, e->stream));
@@ -2810,6 +2856,11 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
             {
                 std::memcpy(req->potentials + static_cast<size_t>(done + b) * e->n_probes, stage, e->n_probes * sizeof(double));
                 stage += e->n_probes * sizeof(double);
+            }
+            if (want_u)
+            {
+                std::memcpy(req->neuron_traces + static_cast<size_t>(done + b) * e->n_u_probes, stage, e->n_u_probes * sizeof(double));
+                stage += e->n_u_probes * sizeof(double);
             }
             if (want_status) std::memcpy(req->status + static_cast<size_t>(done + b) * e->n_neurons, stage, e->n_neurons);
         }

@@ -308,6 +308,8 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                         {
                             if (req->fired_bits != nullptr) sub.fired_bits = req->fired_bits + static_cast<size_t>(done) * words;
                             if (req->potentials != nullptr) sub.potentials = req->potentials + static_cast<size_t>(done) * c->tables.view.n_probes;
+                            if (req->neuron_traces != nullptr)
+                                sub.neuron_traces = req->neuron_traces + static_cast<size_t>(done) * c->tables.view.n_u_probes;
                         }
                         if (c->poisson != nullptr)
                         {
@@ -575,6 +577,26 @@ extern "C" size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap)
         out += '.';
         out += std::to_string(t.names[i].offset);
         out += '\n';
+    }
+    if (buf != nullptr && cap > 0)
+    {
+        const size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = '\0';
+    }
+    return out.size();
+}
+
+extern "C" size_t sfe_chip_trace_names(const sfe_chip *c, char *buf, size_t cap)
+{
+    const sfe::HostTables &t = c->tables;
+    std::string out;
+    for (uint32_t i : t.u_probes)
+    {
+        out += t.group_names[t.names[i].group];
+        out += '.';
+        out += std::to_string(t.names[i].offset);
+        out += "/u\n";
     }
     if (buf != nullptr && cap > 0)
     {

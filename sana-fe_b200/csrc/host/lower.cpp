@@ -1,6 +1,9 @@
 // lower.cpp — see lower.hpp.
 #include "lower.hpp"
 
+#include <fstream>
+#include <sstream>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -48,6 +51,8 @@ struct UnitState // one used hardware unit instance of one core
     double rate{0.0};
     double poisson{0.0};
     double hh_m{0.0}, hh_n{0.0}, hh_h{0.0}, hh_i{0.0};
+    uint32_t noise_off{0}, noise_len{0}; // LIF unit with a noise file: its entries in HostTables::noise_values
+    bool noise_loaded{false};
     std::vector<uint32_t> sharing; // device-order list of neurons mapped to this unit (filled later)
 };
 
@@ -218,8 +223,34 @@ void soma_defaults(const PipelineUnitConfiguration &u, const UnitModel model, sf
     c.latency_access = unit_double(u, "latency_access_neuron", "Soma");
     c.latency_update = unit_double(u, "latency_update_neuron", "Soma");
     c.latency_spike_out = unit_double(u, "latency_spike_out", "Soma");
-    if (model == UnitModel::lif && u.model_info.model_attributes.count("noise") != 0)
-        throw std::runtime_error("LIF file noise stream is not implemented by the B200 engine yet");
+}
+
+// One pass over a LIF unit's noise file, entry by entry as LoihiLifModel::loihi_read_noise_stream /
+// loihi_generate_noise (src/models.cpp:589-650) would deliver them before rewinding: a line is consumed per
+// update (an unparsable line yields 0), the stream rewinds when the next read would hit the end of the file,
+// and the value is cut to `noise_bits` bits with bit 8 as the sign (src/models.hpp:273-275).
+std::vector<double> read_noise_file(const std::string &path, const int noise_bits)
+{
+    std::ifstream f(path);
+    if (!f.is_open()) throw std::runtime_error("Failed to open noise stream"); // src/models.cpp:360-365
+    const long sign_mask = 0x100;
+    const long random_mask = (1L << noise_bits) - 1L;
+    std::vector<double> values;
+    while (!(f.eof() || f.peek() == std::ifstream::traits_type::eof()))
+    {
+        std::string line;
+        if (!std::getline(f, line)) break;
+        int parsed = 0;
+        std::istringstream iss(line);
+        if (!(iss >> parsed)) parsed = 0;
+        long v = parsed;
+        const long sign_bit = v & sign_mask;
+        v &= random_mask;
+        if (sign_bit != 0) v |= ~random_mask;
+        values.push_back(static_cast<double>(v));
+    }
+    if (values.empty()) throw std::runtime_error("Couldn't read noise entry from file"); // src/models.cpp:620-624
+    return values;
 }
 
 // LoihiLifModel / TrueNorthModel / InputModel / HodgkinHuxley ::set_attribute_neuron
@@ -447,6 +478,12 @@ void HostTables::finalize_view(const Architecture &arch)
     v.n_inputs = static_cast<uint32_t>(inputs.size());
     v.input_seed_base = input_seed_base;
     v.n_poisson_cols = n_poisson_cols;
+    v.noise = noise.data();
+    v.noise_values = noise_values.data();
+    v.n_noise = static_cast<uint32_t>(noise.size());
+    v.n_noise_values = noise_values.size();
+    v.u_probes = u_probes.data();
+    v.n_u_probes = static_cast<uint32_t>(u_probes.size());
     v.n_hh = static_cast<uint32_t>(hh.size());
     v.n_probes = static_cast<uint32_t>(probes.size());
     v.n_axons_out = axon_out_target.size();
@@ -519,6 +556,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         const Neuron *n;
         uint32_t group;
     };
+    std::map<std::string, std::pair<uint32_t, uint32_t>> noise_files; // (path, bits) -> (offset, length)
     std::vector<Pending> order;
     for (size_t gi = 0; gi < groups.size(); ++gi)
         for (const Neuron &n : groups[gi]->neurons) order.push_back({&n, static_cast<uint32_t>(gi)});
@@ -566,6 +604,27 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 (soma.model == UnitModel::truenorth && ln.soma_addr >= kTrueNorthMaxNeurons))
             throw std::out_of_range("soma unit '" + soma_cfg.name + "' is full");
         soma_defaults(soma_cfg, soma.model, ln.cls);
+        if (soma.model == UnitModel::lif && soma_cfg.model_info.model_attributes.count("noise") != 0)
+        {
+            // LoihiLifModel::set_attribute_hw  src/models.cpp:351-373
+            if (!soma.noise_loaded)
+            {
+                const auto bits = soma_cfg.model_info.model_attributes.find("noise_bits");
+                const int noise_bits = bits != soma_cfg.model_info.model_attributes.end() ? bits->second.as_int() : 7;
+                const std::string path = soma_cfg.model_info.model_attributes.at("noise").as_string();
+                auto [it, fresh] = noise_files.try_emplace(path + "\n" + std::to_string(noise_bits), 0u, 0u);
+                if (fresh)
+                {
+                    const std::vector<double> values = read_noise_file(path, noise_bits);
+                    it->second = {static_cast<uint32_t>(out.noise_values.size()), static_cast<uint32_t>(values.size())};
+                    out.noise_values.insert(out.noise_values.end(), values.begin(), values.end());
+                }
+                soma.noise_off = it->second.first;
+                soma.noise_len = it->second.second;
+                soma.noise_loaded = true;
+            }
+            ln.cls.flags |= SFE_SOMA_NOISE;
+        }
         ln.cls.dend_model =
                 dend.model == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR : SFE_DEND_ACCUMULATOR_DELAY;
         ln.cls.dend_in_neuron = cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit ? 1 : 0;
@@ -721,6 +780,17 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 out.neuron_aux[dev] = static_cast<uint32_t>(out.inputs.size());
                 out.inputs.push_back(d);
             }
+            else if (soma.model == UnitModel::lif && soma.noise_len > 0)
+            {
+                sfe_noise_desc d{};
+                d.off = soma.noise_off;
+                d.len = soma.noise_len;
+                d.share_count = static_cast<uint32_t>(soma.sharing.size());
+                d.share_rank = static_cast<uint32_t>(
+                        std::find(soma.sharing.begin(), soma.sharing.end(), dev) - soma.sharing.begin());
+                out.neuron_aux[dev] = static_cast<uint32_t>(out.noise.size());
+                out.noise.push_back(d);
+            }
             else if (soma.model == UnitModel::hodgkin_huxley)
             {
                 if (soma.sharing.size() != 1)
@@ -735,6 +805,15 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
     for (size_t gi = 0; gi < groups.size(); ++gi)
         for (const Neuron &n : groups[gi]->neurons)
             if (n.log_potential) out.probes.push_back(out.group_to_device[gi][n.offset]);
+    // model-defined traces, same order: the only built-in producer is LIF's `u` for log_u neurons
+    // (LoihiLifModel::get_neuron_traces, src/models.cpp:653-662)
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+        for (const Neuron &n : groups[gi]->neurons)
+        {
+            const uint32_t dev = out.group_to_device[gi][n.offset];
+            const sfe_soma_class &cls = out.soma_classes[out.neuron_class[dev]];
+            if (cls.model == SFE_SOMA_LIF && (cls.flags & SFE_SOMA_LOG_U) != 0) out.u_probes.push_back(dev);
+        }
 
     // ---- emit axons-out (per neuron, in sending order) -------------------------
     std::vector<uint32_t> core_axon_base(lcores.size());

@@ -87,13 +87,13 @@ public:
             const py::object &potential_trace, const py::object &neuron_trace, const py::object &perf_trace,
             const py::object &message_trace, bool write_trace_headers)
     {
-        if (!neuron_trace.is_none())
-            throw std::runtime_error("neuron_trace (model-defined traces) is not implemented by the B200 engine yet");
         const sfe_tables *t = sfe_chip_tables(h_);
         if (t == nullptr) throw std::runtime_error("no network loaded");
         const size_t words = (static_cast<size_t>(t->n_neurons) + 31) / 32;
         const bool want_spikes = !spike_trace.is_none(), want_pot = !potential_trace.is_none(), want_perf = !perf_trace.is_none();
         const bool want_msgs = !message_trace.is_none();
+        const bool want_traces = !neuron_trace.is_none();
+        std::vector<double> utraces(want_traces ? static_cast<size_t>(t->n_u_probes) * timesteps : 0);
         std::vector<uint8_t> status(want_msgs ? static_cast<size_t>(t->n_neurons) * timesteps : 0);
         std::vector<uint32_t> fired(want_spikes ? words * timesteps : 0);
         std::vector<double> pots(want_pot ? static_cast<size_t>(t->n_probes) * timesteps : 0);
@@ -103,6 +103,7 @@ public:
         req.potentials = pots.empty() ? nullptr : pots.data();
         req.steps = steps.empty() ? nullptr : steps.data();
         req.status = status.empty() ? nullptr : status.data();
+        req.neuron_traces = utraces.empty() ? nullptr : utraces.data();
         sfe_run_data rd{};
         const int timing = parse_timing(timing_model);
         int rc = 0;
@@ -187,6 +188,50 @@ public:
                         text << "\n";
                     }
                 write_sink(potential_trace, text.str());
+            }
+        }
+        if (want_traces)
+        {
+            const uint32_t n_tr = t->n_u_probes;
+            if (py::isinstance<py::bool_>(neuron_trace))
+            {
+                // in memory: {trace name: [values of the traced neurons, per timestep]}  src/pytrace.hpp:205-223
+                py::dict data;
+                if (n_tr > 0)
+                {
+                    py::list all;
+                    for (long s = 0; s < timesteps; ++s)
+                    {
+                        py::list row;
+                        for (uint32_t p = 0; p < n_tr; ++p) row.append(utraces[static_cast<size_t>(s) * n_tr + p]);
+                        all.append(row);
+                    }
+                    data["u"] = all;
+                }
+                out["neuron_trace"] = data;
+            }
+            else
+            {
+                std::ostringstream text; // src/chip.cpp:1478-1517, 1664-1702
+                if (write_trace_headers)
+                {
+                    const size_t need = sfe_chip_trace_names(h_, nullptr, 0);
+                    std::string names(need + 1, '\0');
+                    sfe_chip_trace_names(h_, names.data(), need + 1);
+                    names.resize(need);
+                    text << "timestep,";
+                    std::istringstream in(names);
+                    std::string nm;
+                    while (std::getline(in, nm)) text << "neuron " << nm << ",";
+                    text << "\n";
+                }
+                for (long s = 0; s < timesteps; ++s)
+                {
+                    text << (rd.timestep_start + s) << ",";
+                    for (uint32_t p = 0; p < n_tr; ++p) text << utraces[static_cast<size_t>(s) * n_tr + p] << ",";
+                    if (n_tr > 0) text << "\n";
+                }
+                write_sink(neuron_trace, text.str());
             }
         }
         if (want_msgs)

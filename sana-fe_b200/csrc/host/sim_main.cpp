@@ -6,8 +6,8 @@
 // ABI: same flags, same five outputs in the output directory (spikes.csv, potentials.csv,
 // perf.csv, messages.csv, run_summary.yaml; writers src/chip.cpp:849-899,1447-1764), including
 // the reference's quirk that `-s` alone switches on the spike, potential, perf and message traces
-// (src/main.cpp:63-67) while -p / -v / -m are parsed but not consulted. Not available: -n (legacy
-// netlist format), -x (model-defined neuron traces), the `cycle` timing model (Booksim2).
+// (src/main.cpp:63-67) while -p / -v / -m are parsed but not consulted; -x writes neurons.csv (model-defined
+// neuron traces: LIF `u` of the log_u neurons). Not available: the `cycle` timing model (Booksim2).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -86,7 +86,6 @@ int main(int argc, char *argv[])
     try { timesteps = std::stol(args[idx + 2]); }
     catch (const std::exception &) { std::fprintf(stderr, "Error: invalid argument thrown: Error: Invalid time-step format: %s\n", args[idx + 2].c_str()); return 1; }
     if (timesteps <= 0) { std::fprintf(stderr, "Error: invalid argument thrown: Time-steps must be > 0\n"); return 1; }
-    if (flags.record_neuron_state) fail("model-defined neuron traces (-x) are not supported by this build");
 
     std::printf("Running SANA-FE simulation (B200 engine, ABI %d)\n", sfe_abi_version());
     sfe_arch *arch = sfe_arch_load_yaml(arch_file.c_str());
@@ -102,7 +101,20 @@ int main(int argc, char *argv[])
     // src/main.cpp:63-67: every trace hangs off -s
     const bool traces = flags.record_spikes;
     std::filesystem::create_directories(flags.output_dir);
-    std::ofstream spikes, potentials, perf, messages;
+    std::ofstream spikes, potentials, perf, messages, neuron_trace;
+    size_t n_traces = 0;
+    if (flags.record_neuron_state)
+    {
+        // sim_trace_open_neuron_trace / sim_trace_write_neuron_trace_header  src/chip.cpp:916-929, 1478-1517
+        neuron_trace.open(flags.output_dir / "neurons.csv");
+        std::string names(sfe_chip_trace_names(chip, nullptr, 0) + 1, '\0');
+        sfe_chip_trace_names(chip, names.data(), names.size());
+        names.resize(std::strlen(names.c_str()));
+        neuron_trace << "timestep,";
+        std::istringstream lines(names);
+        for (std::string line; std::getline(lines, line); ++n_traces) neuron_trace << "neuron " << line << ",";
+        neuron_trace << "\n";
+    }
     std::string probe_names;
     if (traces)
     {
@@ -133,7 +145,7 @@ int main(int argc, char *argv[])
     sfe_run_data total{};
     bool first = true;
     std::vector<uint32_t> fired;
-    std::vector<double> pots;
+    std::vector<double> pots, utraces;
     std::vector<uint8_t> status;
     std::vector<sfe_step_record> steps;
     std::string text;
@@ -152,8 +164,21 @@ int main(int argc, char *argv[])
             req.status = status.data();
             req.steps = steps.data();
         }
+        if (n_traces > 0)
+        {
+            utraces.assign(static_cast<size_t>(batch) * n_traces, 0.0);
+            req.neuron_traces = utraces.data();
+        }
         sfe_run_data rd{};
-        if (sfe_chip_sim(chip, batch, flags.timing_model, traces ? &req : nullptr, &rd) != 0) fail(sfe_last_error());
+        if (sfe_chip_sim(chip, batch, flags.timing_model, (traces || n_traces > 0) ? &req : nullptr, &rd) != 0) fail(sfe_last_error());
+        if (flags.record_neuron_state)
+            for (long s = 0; s < batch; ++s)
+            {
+                // sim_trace_record_neuron_traces  src/chip.cpp:1664-1702 (default ostream precision)
+                neuron_trace << (rd.timestep_start + s) << ",";
+                for (size_t p = 0; p < n_traces; ++p) neuron_trace << utraces[static_cast<size_t>(s) * n_traces + p] << ',';
+                if (n_traces > 0) neuron_trace << "\n";
+            }
         if (traces)
         {
             text.resize(sfe_chip_format_spikes(chip, fired.data(), batch, rd.timestep_start, nullptr, 0) + 1);

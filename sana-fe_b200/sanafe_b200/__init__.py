@@ -72,6 +72,10 @@ class InputDesc(C.Structure):
                 ("unit", C.c_uint32), ("poisson_col", C.c_uint32)]
 
 
+class NoiseDesc(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("len", C.c_uint32), ("share_count", C.c_uint32), ("share_rank", C.c_uint32)]
+
+
 class HHInit(C.Structure):
     _fields_ = [("m", C.c_double), ("n", C.c_double), ("h", C.c_double), ("current", C.c_double)]
 
@@ -94,7 +98,10 @@ class Tables(C.Structure):
                 ("n_input_spikes", C.c_uint64), ("hh", C.POINTER(HHInit)), ("probes", C.POINTER(C.c_uint32)),
                 ("axons_in", C.POINTER(AxonIn)), ("axon_src", C.POINTER(C.c_uint32)),
                 ("syn_weight", C.POINTER(C.c_double)), ("syn_meta", C.POINTER(C.c_uint32)),
-                ("synth", C.POINTER(SynthSpec)), ("input_seed_base", C.c_uint32), ("n_poisson_cols", C.c_uint32)]
+                ("synth", C.POINTER(SynthSpec)), ("input_seed_base", C.c_uint32), ("n_poisson_cols", C.c_uint32),
+                ("noise", C.POINTER(NoiseDesc)), ("noise_values", C.POINTER(C.c_double)),
+                ("n_noise_values", C.c_uint64), ("n_noise", C.c_uint32), ("n_u_probes", C.c_uint32),
+                ("u_probes", C.POINTER(C.c_uint32))]
 
 
 class StepRecord(C.Structure):
@@ -120,7 +127,7 @@ class RunData(C.Structure):
 
 class TraceRequest(C.Structure):
     _fields_ = [("steps", C.c_void_p), ("fired_bits", C.c_void_p), ("potentials", C.c_void_p),
-                ("status", C.c_void_p)]
+                ("status", C.c_void_p), ("neuron_traces", C.c_void_p)]
 
 
 _lib = None
@@ -192,6 +199,7 @@ def lib():
         "sfe_chip_format_messages": (sz, [vp, vp, i64, i64, C.c_int, C.c_char_p, sz]),
         "sfe_chip_format_spikes": (sz, [vp, vp, i64, i64, C.c_char_p, sz]),
         "sfe_chip_probe_names": (sz, [vp, C.c_char_p, sz]),
+        "sfe_chip_trace_names": (sz, [vp, C.c_char_p, sz]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the ABI header and the library disagree
@@ -318,7 +326,15 @@ class SpikingChip:
         lib().sfe_chip_probe_names(self._h, buf, n + 1)
         return buf.value.decode().split("\n")[:-1] if n else []
 
-    def sim_raw(self, timesteps, timing_model="simple", steps=False, fired=False, potentials=False, status=False):
+    def trace_names(self):
+        """Columns of the model-defined neuron traces ("group.offset/trace"), in trace order."""
+        n = lib().sfe_chip_trace_names(self._h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib().sfe_chip_trace_names(self._h, buf, n + 1)
+        return buf.value.decode().split("\n")[:-1] if n else []
+
+    def sim_raw(self, timesteps, timing_model="simple", steps=False, fired=False, potentials=False, status=False,
+                neuron_traces=False):
         """One sfe_chip_sim call; returns (RunData, dict of numpy traces)."""
         t = self.tables
         req = TraceRequest()
@@ -335,6 +351,9 @@ class SpikingChip:
         if status:
             out["status"] = np.zeros((timesteps, t.n_neurons), dtype=np.uint8)
             req.status = out["status"].ctypes.data
+        if neuron_traces and t.n_u_probes:
+            out["neuron_traces"] = np.zeros((timesteps, t.n_u_probes), dtype=np.float64)
+            req.neuron_traces = out["neuron_traces"].ctypes.data
         rd = RunData()
         _check(lib().sfe_chip_sim(self._h, timesteps, TIMING[timing_model], C.byref(req), C.byref(rd)))
         return rd, out
@@ -365,10 +384,9 @@ class SpikingChip:
             spike_trace=None, potential_trace=None, neuron_trace=None, perf_trace=None, message_trace=None,
             write_trace_headers=True):
         """sanafe.SpikingChip.sim (src/pymodule.cpp:549-706): returns the same result dict."""
-        if neuron_trace:
-            raise SanafeError("neuron_trace is not implemented yet")
         rd, tr = self.sim_raw(timesteps, timing_model, steps=bool(perf_trace), fired=bool(spike_trace),
-                              potentials=bool(potential_trace), status=bool(message_trace))
+                              potentials=bool(potential_trace), status=bool(message_trace),
+                              neuron_traces=bool(neuron_trace))
         result = {
             "timestep_start": rd.timestep_start, "timesteps_executed": rd.timesteps_executed,
             "energy": {"total": rd.total_energy, "synapse": rd.synapse_energy, "dendrite": rd.dendrite_energy,
@@ -397,6 +415,17 @@ class SpikingChip:
                 body = "".join(f"{rd.timestep_start + s}," + "".join(f"{v:g}," for v in pots[s]) + "\n"
                                for s in range(timesteps)) if names else ""
                 self._write_text(potential_trace, (hdr if write_trace_headers else "") + body)
+        if neuron_trace:
+            # src/pymodule.cpp:664-668 / src/chip.cpp:1478-1517, 1664-1702
+            vals = tr.get("neuron_traces", np.zeros((timesteps, 0)))
+            if neuron_trace is True:
+                result["neuron_trace"] = {"u": vals.tolist()} if vals.shape[1] else {}  # src/pytrace.hpp:205-212
+            else:
+                names = self.trace_names()
+                hdr = "timestep," + "".join(f"neuron {n}," for n in names) + "\n"
+                body = "".join(f"{rd.timestep_start + s}," + "".join(f"{v:g}," for v in vals[s]) + ("\n" if names else "")
+                               for s in range(timesteps))
+                self._write_text(neuron_trace, (hdr if write_trace_headers else "") + body)
         if message_trace:
             text = self.format_messages(tr["status"], rd.timestep_start, timing_model)
             if message_trace is True:

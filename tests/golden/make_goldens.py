@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import yaml_to_flat  # noqa: E402
-from helpers import load_ref_potentials, load_ref_spikes, load_ref_steps, run_reference  # noqa: E402
+from helpers import load_ref_potentials, load_ref_spikes, load_ref_steps, load_ref_traces, run_reference  # noqa: E402
 
 REF = "/root/reference"
 SRC = os.path.join(HERE, "src")
@@ -63,6 +63,8 @@ CASES = {
     # ordered fp64 accumulation
     "frac": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/frac_snn.yaml", steps=200),
     # Poisson inputs: libstdc++ mt19937 streams seeded by the InputModel construction order
+    # LIF file noise stream + model-defined traces (log_u)
+    "noise": dict(arch=f"{SRC}/noise_arch.yaml", net=f"{SRC}/noise_snn.yaml", steps=150),
     "poisson": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/poisson_snn.yaml", steps=300),
 }
 
@@ -96,6 +98,10 @@ def make_case(name, spec):
             np.save(os.path.join(HERE, name + ".potentials_head.npy"), pots[:25])
         else:
             np.save(os.path.join(HERE, name + ".potentials.npy"), pots)
+    trs = load_ref_traces(out_dir)
+    if trs is not None:
+        golden["neuron_traces_shape"] = list(trs.shape)
+        np.save(os.path.join(HERE, name + ".neuron_traces.npy"), trs)
     # detailed timing totals for the same run (host scheduler parity, NEXT row f-1)
     if name in ("example", "dvs", "frac", "truenorth", "synth_delay"):
         out2 = tempfile.mkdtemp(prefix="golden_det_" + name)

@@ -77,6 +77,9 @@ class Oracle:
         if status:
             out["status"] = np.zeros((timesteps, t.n_neurons), dtype=np.uint8)
             req.status = out["status"].ctypes.data
+        if t.n_u_probes:
+            out["neuron_traces"] = np.zeros((timesteps, t.n_u_probes), dtype=np.float64)
+            req.neuron_traces = out["neuron_traces"].ctypes.data
         rd = sfe.RunData()
         rc = oracle_lib().sfe_oracle_run(self.h, timesteps, C.byref(req), C.byref(rd))
         assert rc == 0
@@ -130,6 +133,19 @@ def load_ref_potentials(out_dir):
     return arr[:, 1:]
 
 
+def load_ref_traces(out_dir):
+    """traces_full.csv of a --per-step reference run (rows "t,name=value,..." from SpikingChip::get_traces):
+    the values per step, in file order, or None when the run has no model-defined traces."""
+    path = os.path.join(out_dir, "traces_full.csv")
+    if not os.path.exists(path) or os.path.getsize(path) == 0:
+        return None
+    rows = []
+    with open(path) as f:
+        for line in f:
+            rows.append([float(x.split("=", 1)[1]) for x in line.strip().split(",")[1:]])
+    return np.asarray(rows, dtype=np.float64)
+
+
 def load_ref_spikes(out_dir):
     with open(os.path.join(out_dir, "spikes_full.csv")) as f:
         return f.read()
@@ -147,10 +163,10 @@ import hashlib
 import tempfile
 
 GOLDEN_CASES = ["example", "dvs", "hh", "synth_small", "synth_delay", "synth_quirk", "synth_soma", "truenorth", "frac"]
-# Cases added after the round's GPU budget was spent: pinned on the CPU against the reference here; their
-# device tests live in tests/test_zz_new_models_gpu.py (collected last, so that a failure there cannot
-# hide the verified suite behind `pytest -x`).
-NEW_GOLDEN_CASES = ["poisson"]
+# Cases added late in round 1 (Poisson inputs, LIF file noise + model-defined traces): pinned on the CPU against
+# the reference here; their device tests live in tests/test_zz_new_models_gpu.py (collected last; green on a
+# B200, profiles/r1_pytest_new_models_gpu.log).
+NEW_GOLDEN_CASES = ["poisson", "noise"]
 _flat_cache = {}
 
 
@@ -222,6 +238,10 @@ def check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e
     assert text.count("\n") == g["spike_rows"], (name, text.count("\n"), g["spike_rows"])
     assert hashlib.md5(text.encode()).hexdigest() == g["spikes_md5"], name
     assert text == golden_spikes(name), name
+    if "neuron_traces_shape" in g and "neuron_traces" in out:
+        ref = np.load(os.path.join(GOLDEN, name + ".neuron_traces.npy"))
+        assert list(out["neuron_traces"].shape) == g["neuron_traces_shape"], (name, out["neuron_traces"].shape)
+        assert np.array_equal(out["neuron_traces"], ref), (name, "model-defined traces (u) differ")
     if "potentials_shape" in g:
         pots = out["potentials"]
         assert list(pots.shape) == g["potentials_shape"], (name, pots.shape)

@@ -1,6 +1,7 @@
-"""Device tests of the models added after this round's GPU budget was spent (their CPU side — lowering, host
-draws, restatement vs the reference's goldens — is pinned in test_oracle_vs_reference.py and
-test_poisson_inputs.py). Collected last on purpose: see helpers.NEW_GOLDEN_CASES."""
+"""Device tests of what was added late in round 1: Poisson inputs, LIF file noise, model-defined neuron traces
+(sim(neuron_trace=...), `sim -x`) and the batched design-space sweep. Their CPU side — lowering, host draws,
+restatement vs the reference's goldens — is pinned in test_oracle_vs_reference.py, test_poisson_inputs.py and
+test_dse_batch.py. Collected last (see helpers.NEW_GOLDEN_CASES)."""
 import numpy as np
 import pytest
 
@@ -14,7 +15,8 @@ pytestmark = pytest.mark.gpu
 def test_engine_matches_reference_new_cases(name):
     chip = load_chip(name, device=0)
     g = golden(name)
-    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True, neuron_traces=True)
+    assert ("neuron_traces" in out) == ("neuron_traces_shape" in g)
     check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
 
 
@@ -67,3 +69,42 @@ def test_dse_batch_equals_lone_runs_and_the_restatement(tmp_path):
                 assert getattr(got, key) == getattr(alone, key), (point, key)
                 assert abs(getattr(got, key) - getattr(want, key)) <= 1e-9 * abs(getattr(want, key)), (point, key)
         assert rds[k].spikes > 0
+
+
+def test_neuron_trace_surfaces(tmp_path):
+    """Model-defined traces (LIF `u` of log_u neurons) through the three user surfaces: the ctypes binding's and the
+    pybind11 module's sim(neuron_trace=...) and the command line's -x (neurons.csv, src/chip.cpp:1478-1517, 1664-1702)."""
+    import os
+    import subprocess
+    from helpers import GOLDEN, ROOT, golden_flat
+    ref = np.load(os.path.join(GOLDEN, "noise.neuron_traces.npy"))
+    chip = load_chip("noise", device=0)
+    assert chip.trace_names() == ["a.0/u", "a.1/u", "a.2/u", "a.3/u", "a.4/u", "b.0/u", "q.0/u"]
+    res = chip.sim(150, timing_model="detailed", neuron_trace=True, spike_trace=True)
+    assert np.array_equal(np.asarray(res["neuron_trace"]["u"]), ref)
+    # pybind11 module, file sink
+    from sanafe_b200 import sanafecpp_b200 as m
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch, net = m.load_flat(golden_flat("noise"))
+        pchip = m.SpikingChip(arch)
+        pchip.load(net)
+        path = str(tmp_path / "neurons.csv")
+        out = pchip.sim(150, timing_model="simple", neuron_trace=path)
+        mem = pchip.sim(5, timing_model="simple", neuron_trace=True)
+    finally:
+        os.chdir(cwd)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "timestep," + "".join(f"neuron {n}," for n in chip.trace_names())
+    got = np.asarray([[float(x) for x in ln.split(",")[1:-1]] for ln in lines[1:]])
+    assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-5, atol=1e-12)  # CSV keeps 6 digits
+    assert out["timesteps_executed"] == 150 and len(mem["neuron_trace"]["u"]) == 5
+    # command line: -x next to the YAML descriptions
+    src = os.path.join(GOLDEN, "src")
+    sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
+    cli = subprocess.run([sim, "-x", "-o", str(tmp_path / "cli"), os.path.join(src, "noise_arch.yaml"),
+                          os.path.join(src, "noise_snn.yaml"), "150"], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert cli.returncode == 0, cli.stderr
+    cli_lines = (tmp_path / "cli" / "neurons.csv").read_text().splitlines()
+    assert cli_lines == lines
