@@ -273,6 +273,9 @@ typedef struct sfe_trace_request
 } sfe_trace_request;
 
 const char *sfe_last_error(void);
+/* class of the C++ exception behind sfe_last_error() (the reference reports errors as exceptions) */
+enum { SFE_ERROR_RUNTIME = 0, SFE_ERROR_INVALID_ARGUMENT = 1, SFE_ERROR_OUT_OF_RANGE = 2, SFE_ERROR_HARDWARE_MAPPING = 3 };
+int sfe_last_error_kind(void);
 int sfe_abi_version(void);
 /* number of CUDA devices visible; 0 when there is no GPU (never a CPU fallback) */
 int sfe_device_count(void);
@@ -457,6 +460,13 @@ size_t sfe_chip_probe_names(const sfe_chip *c, char *buf, size_t cap);
 /* header cells of neurons.csv (src/chip.cpp:1478-1517): "group.offset/trace" of every model-defined trace column
  * (sfe_trace_request.neuron_traces), one per line */
 size_t sfe_chip_trace_names(const sfe_chip *c, char *buf, size_t cap);
+/* SpikingChip::mapped_neuron_groups (src/chip.hpp:104): "group name<TAB>neuron count" per line, lexicographic */
+size_t sfe_chip_group_names(const sfe_chip *c, char *buf, size_t cap);
+/* MappedNeuron::set_attributes(..., log_spikes) (src/mapped.cpp:113-124) */
+int sfe_chip_set_neuron_log_spikes(sfe_chip *c, const char *group, uint64_t offset, int on);
+/* an empty network for the object-by-object builders, and Network.save (src/network.cpp:693-712; YAML) */
+sfe_net *sfe_net_create(const char *name);
+int sfe_net_save_yaml(const sfe_net *net, const char *path);
 
 #ifdef __cplusplus
 }

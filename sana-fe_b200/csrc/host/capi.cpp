@@ -17,6 +17,7 @@
 
 #include "../engine.hpp"
 #include "desc.hpp"
+#include "handles.hpp"
 #include "lower.hpp"
 #include "schedule.hpp"
 #include "sanafe_b200.h"
@@ -26,22 +27,15 @@ namespace sfe
 namespace
 {
 thread_local std::string g_last_error;
+thread_local int g_last_error_kind = SFE_ERROR_RUNTIME;
 }
 void set_last_error(const std::string &msg)
 {
     g_last_error = msg;
+    g_last_error_kind = SFE_ERROR_RUNTIME;
 }
 } // namespace sfe
 
-struct sfe_arch
-{
-    std::unique_ptr<sfe::Architecture> arch;
-};
-struct sfe_net
-{
-    std::unique_ptr<sfe::SpikingNetwork> net;
-    std::optional<sfe::SynthRequest> synth;
-};
 struct sfe_chip
 {
     sfe::Architecture arch;
@@ -69,6 +63,24 @@ template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f(
     try
     {
         return f();
+    }
+    // the reference reports errors as C++ exceptions; the class survives the ABI as a "kind" so that bindings can
+    // raise what the reference's would (pybind11: invalid_argument -> ValueError, out_of_range -> IndexError,
+    // HardwareMappingError registered by name, src/pymodule.cpp:870-871)
+    catch (const sfe::HardwareMappingError &e)
+    {
+        sfe::set_last_error(e.what());
+        sfe::g_last_error_kind = SFE_ERROR_HARDWARE_MAPPING;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        sfe::set_last_error(e.what());
+        sfe::g_last_error_kind = SFE_ERROR_INVALID_ARGUMENT;
+    }
+    catch (const std::out_of_range &e)
+    {
+        sfe::set_last_error(e.what());
+        sfe::g_last_error_kind = SFE_ERROR_OUT_OF_RANGE;
     }
     catch (const std::exception &e)
     {
@@ -111,6 +123,11 @@ int attach_engine(sfe_chip *c)
 extern "C" const char *sfe_last_error(void)
 {
     return sfe::g_last_error.c_str();
+}
+
+extern "C" int sfe_last_error_kind(void)
+{
+    return sfe::g_last_error_kind;
 }
 
 extern "C" int sfe_abi_version(void)
@@ -460,6 +477,57 @@ extern "C" sfe_engine *sfe_chip_engine(sfe_chip *c)
 extern "C" int64_t sfe_chip_neuron_index(const sfe_chip *c, const char *group, uint64_t offset)
 {
     return c->tables.find_neuron(group, offset);
+}
+
+// MappedNeuron::set_attributes(..., log_spikes)  src/mapped.cpp:113-124
+extern "C" int sfe_chip_set_neuron_log_spikes(sfe_chip *c, const char *group, uint64_t offset, int on)
+{
+    return guarded(
+            [&]() -> int {
+                const int64_t idx = c->tables.find_neuron(group, offset);
+                if (idx < 0) throw std::out_of_range(std::string("no mapped neuron ") + group + "." + std::to_string(offset));
+                c->tables.names[static_cast<size_t>(idx)].log_spikes = on != 0;
+                return 0;
+            },
+            -1);
+}
+
+// SpikingChip::mapped_neuron_groups  src/chip.hpp:104: "name<TAB>neuron count" per line, lexicographic order
+extern "C" size_t sfe_chip_group_names(const sfe_chip *c, char *buf, size_t cap)
+{
+    const sfe::HostTables &t = c->tables;
+    std::string out;
+    for (size_t g = 0; g < t.group_names.size(); ++g)
+        out += t.group_names[g] + "\t" + std::to_string(t.group_to_device[g].size()) + "\n";
+    if (buf != nullptr && cap > 0)
+    {
+        const size_t n = std::min(cap - 1, out.size());
+        std::memcpy(buf, out.data(), n);
+        buf[n] = '\0';
+    }
+    return out.size();
+}
+
+extern "C" sfe_net *sfe_net_create(const char *name)
+{
+    return guarded(
+            [&]() -> sfe_net * {
+                auto n = std::make_unique<sfe_net>();
+                n->net = std::make_unique<sfe::SpikingNetwork>(name != nullptr ? name : "");
+                return n.release();
+            },
+            nullptr);
+}
+
+extern "C" int sfe_net_save_yaml(const sfe_net *net, const char *path)
+{
+    return guarded(
+            [&]() -> int {
+                if (net == nullptr || !net->net) throw std::invalid_argument("sfe_net_save_yaml: no described network");
+                sfe::save_net_yaml(*net->net, path);
+                return 0;
+            },
+            -1);
 }
 
 extern "C" int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offset, const char *name,

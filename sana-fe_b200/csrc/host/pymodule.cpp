@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 
+#include "handles.hpp"
 #include "sanafe_b200.h"
 
 namespace py = pybind11;
@@ -39,8 +40,162 @@ struct NetHandle
 
 [[noreturn]] void raise_last()
 {
-    throw std::runtime_error(sfe_last_error());
+    // the exception class the reference would have thrown (pybind11's default translation then matches:
+    // invalid_argument -> ValueError, out_of_range -> IndexError, HardwareMappingError registered below)
+    const std::string msg = sfe_last_error();
+    switch (sfe_last_error_kind())
+    {
+    case SFE_ERROR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+    case SFE_ERROR_OUT_OF_RANGE: throw std::out_of_range(msg);
+    case SFE_ERROR_HARDWARE_MAPPING: throw sfe::HardwareMappingError(msg);
+    default: throw std::runtime_error(msg);
+    }
 }
+
+// ---- Python values <-> attributes (src/pymodule.cpp:119-248) -------------------------------------
+// Note the reference's narrowing: a Python float becomes a C float first, and a
+// Python bool is an int.
+sfe::Attr to_attr(const py::object &value)
+{
+    sfe::Attr a;
+    bool is_int = false, is_float = false;
+    if (py::hasattr(value, "dtype"))
+    {
+        const std::string kind = value.attr("dtype").attr("kind").cast<std::string>();
+        is_int = kind == "i" || kind == "u";
+        is_float = kind == "f";
+    }
+    else
+    {
+        is_int = py::isinstance<py::int_>(value);
+        is_float = py::isinstance<py::float_>(value);
+    }
+    if (py::isinstance<py::str>(value)) a.value = value.cast<std::string>();
+    else if (is_int) a.value = value.cast<int>();
+    else if (is_float) a.value = static_cast<double>(value.cast<float>());
+    else if (py::isinstance<py::dict>(value))
+    {
+        std::vector<sfe::Attr> list;
+        for (auto item : value.cast<py::dict>())
+        {
+            sfe::Attr e = to_attr(py::reinterpret_borrow<py::object>(item.second));
+            e.name = item.first.cast<std::string>();
+            list.push_back(std::move(e));
+        }
+        a.value = std::move(list);
+    }
+    else if (py::isinstance<py::iterable>(value))
+    {
+        std::vector<sfe::Attr> list;
+        for (auto it = py::iter(value); it != py::iterator::sentinel(); ++it)
+            list.push_back(to_attr(py::reinterpret_borrow<py::object>(*it)));
+        a.value = std::move(list);
+    }
+    else throw std::invalid_argument("Error: dict has unsupported type");
+    return a;
+}
+
+sfe::AttrMap to_attr_map(const py::dict &d, bool to_synapse = true, bool to_dendrite = true, bool to_soma = true)
+{
+    sfe::AttrMap m;
+    for (auto kv : d)
+    {
+        const std::string key = kv.first.cast<std::string>();
+        sfe::Attr a = to_attr(py::reinterpret_borrow<py::object>(kv.second));
+        a.forward_to_synapse = to_synapse;
+        a.forward_to_dendrite = to_dendrite;
+        a.forward_to_soma = to_soma;
+        a.name = key;
+        m[key] = std::move(a);
+    }
+    return m;
+}
+
+sfe::NeuronGroup::AttrLists to_attr_lists(const py::dict &d) // src/pymodule.cpp:90-117
+{
+    sfe::NeuronGroup::AttrLists lists;
+    for (auto kv : d)
+    {
+        const std::string key = kv.first.cast<std::string>();
+        if (!py::isinstance<py::iterable>(kv.second))
+            throw std::invalid_argument("Error: Each attribute must be provided as a 1D list/array of values. "
+                                        "Multi-dimensional arrays must be flattened in C-order and storing channels as "
+                                        "the last dim");
+        std::vector<sfe::Attr> &list = lists[key];
+        for (auto it = py::iter(kv.second); it != py::iterator::sentinel(); ++it)
+            list.push_back(to_attr(py::reinterpret_borrow<py::object>(*it)));
+    }
+    return lists;
+}
+
+py::object from_attr(const sfe::Attr &a)
+{
+    if (const bool *b = std::get_if<bool>(&a.value)) return py::cast(*b);
+    if (const int *i = std::get_if<int>(&a.value)) return py::cast(*i);
+    if (const double *d = std::get_if<double>(&a.value)) return py::cast(*d);
+    if (const std::string *s = std::get_if<std::string>(&a.value)) return py::cast(*s);
+    const std::vector<sfe::Attr> &list = a.as_list();
+    if (!list.empty() && list[0].name.has_value())
+    {
+        py::dict d;
+        for (const sfe::Attr &e : list)
+        {
+            if (!e.name.has_value()) throw std::runtime_error("Error: Sub-attribute is unnamed.\n");
+            d[py::str(*e.name)] = from_attr(e);
+        }
+        return d;
+    }
+    py::list l;
+    for (const sfe::Attr &e : list) l.append(from_attr(e));
+    return l;
+}
+
+py::dict from_attr_map(const sfe::AttrMap &m)
+{
+    py::dict d;
+    for (const auto &[key, a] : m) d[py::str(key)] = from_attr(a);
+    return d;
+}
+
+// ---- builder objects (src/pymodule.cpp:873-1173). References into a description keep its handle alive. ----
+struct GroupRef
+{
+    std::shared_ptr<NetHandle> owner;
+    sfe::NeuronGroup *g;
+};
+struct NeuronRef
+{
+    std::shared_ptr<NetHandle> owner;
+    sfe::Neuron *n;
+};
+
+sfe::SpikingNetwork &described(const std::shared_ptr<NetHandle> &net)
+{
+    if (net->h == nullptr || !net->h->net) throw std::runtime_error("this network has no object description (generated networks are built on the device)");
+    return *net->h->net;
+}
+
+std::string group_info(const sfe::NeuronGroup &g)
+{
+    return "sanafe::NeuronGroup(name=" + g.name + " neurons=" + std::to_string(g.neurons.size()) + ")";
+}
+std::string neuron_info(const sfe::Neuron &n)
+{
+    std::string s = "sanafe::Neuron(nid=" + n.parent_group_name + "." + std::to_string(n.offset) + " connections_out=" +
+            std::to_string(n.edges_out.size());
+    if (n.core_address.has_value())
+        s += " core=" + std::to_string(n.core_address->parent_tile_id) + "." + std::to_string(n.core_address->offset_within_tile);
+    return s + ")";
+}
+
+class Chip;
+// A mapped neuron of a chip (src/mapped.hpp): only what Python can do with it — set_attributes
+struct MappedRef
+{
+    std::shared_ptr<Chip> chip;
+    std::string group;
+    size_t offset;
+};
 
 int parse_timing(const std::string &s) // parse_timing_model  src/chip.cpp:1833-1858
 {
@@ -61,9 +216,29 @@ void write_sink(const py::object &sink, const std::string &text)
     else sink.attr("write")(text);
 }
 
-class Chip
+class Chip : public std::enable_shared_from_this<Chip>
 {
 public:
+    sfe_chip *handle() { return h_; }
+    // SpikingChip.mapped_neuron_groups  src/pymodule.cpp:1183-1191: {group name: [MappedNeuron, ...]}
+    py::dict mapped_neuron_groups()
+    {
+        py::dict groups;
+        std::string text(sfe_chip_group_names(h_, nullptr, 0) + 1, '\0');
+        sfe_chip_group_names(h_, text.data(), text.size());
+        std::istringstream in(text.c_str());
+        for (std::string line; std::getline(in, line);)
+        {
+            const size_t tab = line.rfind('\t');
+            const std::string name = line.substr(0, tab);
+            const size_t count = std::stoul(line.substr(tab + 1));
+            py::list neurons;
+            for (size_t k = 0; k < count; ++k) neurons.append(MappedRef{shared_from_this(), name, k});
+            groups[py::str(name)] = neurons;
+        }
+        return groups;
+    }
+
     explicit Chip(const std::shared_ptr<ArchHandle> &arch, int device) : arch_(arch)
     {
         h_ = sfe_chip_create(arch->h, device);
@@ -321,8 +496,303 @@ private:
 PYBIND11_MODULE(sanafecpp_b200, m)
 {
     m.doc() = "SANA-FE time-step engine on B200 (drop-in for the sanafecpp surface it covers)";
-    py::class_<ArchHandle, std::shared_ptr<ArchHandle>>(m, "Architecture");
-    py::class_<NetHandle, std::shared_ptr<NetHandle>>(m, "Network");
+    py::register_exception<sfe::HardwareMappingError>(m, "HardwareMappingError");
+    py::enum_<sfe::BufferPosition>(m, "BufferPosition") // src/pymodule.cpp:862-868
+            .value("buffer_before_dendrite_unit", sfe::buffer_before_dendrite_unit)
+            .value("buffer_before_soma_unit", sfe::buffer_before_soma_unit)
+            .value("buffer_before_axon_out_unit", sfe::buffer_before_axon_out_unit);
+    {
+        // attribute documentation tables (src/pipeline.hpp:182-205, src/models.cpp:969-987): names as in the
+        // reference, descriptions in this module's own words
+        py::dict fw;
+        for (const char *k : {"force_update", "synapse_hw_name", "dendrite_hw_name", "soma_hw_name", "model", "plugin",
+                     "energy_message_in", "latency_message_in", "energy_access_neuron", "latency_access_neuron",
+                     "energy_update_neuron", "latency_update_neuron", "energy_spike_out", "latency_spike_out",
+                     "energy_process_spike", "latency_process_spike", "energy_update", "latency_update",
+                     "energy_message_out", "latency_message_out"})
+            fw[k] = "framework attribute (see the architecture description format)";
+        m.attr("framework_attributes") = fw;
+        py::dict models;
+        auto doc = [](std::initializer_list<const char *> names) {
+            py::dict d;
+            for (const char *n : names) d[n] = "model attribute";
+            return d;
+        };
+        models["current_based"] = doc({"weight", "w"});
+        models["accumulator"] = py::none();
+        models["accumulator_with_delay"] = py::none();
+        models["input"] = doc({"rate", "poisson", "spikes"});
+        models["leaky_integrate_and_fire"] = doc({"bias", "force_update", "force_update_every_timestep", "leak_decay", "log_u",
+                "noise", "noise_bits", "refractory_delay", "reset_mode", "reverse_reset_mode", "reset", "reverse_reset",
+                "reverse_threshold", "threshold"});
+        models["truenorth"] = doc({"bias", "force_update", "leak", "leak_towards_zero", "reset_mode", "reverse_reset_mode",
+                "reset", "reverse_reset", "reverse_threshold", "threshold"});
+        m.attr("model_attributes") = models;
+    }
+
+    // ---- architecture (src/pymodule.cpp:1114-1172) ----------------------------------------------------
+    py::class_<sfe::CoreConfiguration>(m, "Core")
+            .def_readonly("name", &sfe::CoreConfiguration::name)
+            .def_property_readonly("id", [](const sfe::CoreConfiguration &c) { return c.address.id; })
+            .def_property_readonly("parent_tile_id", [](const sfe::CoreConfiguration &c) { return c.address.parent_tile_id; })
+            .def_property_readonly("offset_within_tile", [](const sfe::CoreConfiguration &c) { return c.address.offset_within_tile; })
+            .def("__repr__", [](const sfe::CoreConfiguration &c) {
+                return "sanafe::Core(name=" + c.name + " address=" + std::to_string(c.address.parent_tile_id) + "." +
+                        std::to_string(c.address.offset_within_tile) + ")";
+            });
+    py::class_<sfe::TileConfiguration>(m, "Tile")
+            .def_readonly("name", &sfe::TileConfiguration::name)
+            .def_readonly("id", &sfe::TileConfiguration::id)
+            .def_readwrite("cores", &sfe::TileConfiguration::cores)
+            .def("__repr__", [](const sfe::TileConfiguration &t) {
+                return "sanafe::Tile(name=" + t.name + " cores=" + std::to_string(t.cores.size()) + ")";
+            });
+    py::class_<ArchHandle, std::shared_ptr<ArchHandle>>(m, "Architecture")
+            .def("__repr__", [](const ArchHandle &a) {
+                return "sanafe::Architecture(name=" + a.h->arch->name + ", tiles=" + std::to_string(a.h->arch->tiles.size()) + ")";
+            })
+            // as in the reference these hand out COPIES (std::vector members bound by value): all a script does
+            // with a Core is Neuron.map_to_core(core), which reads its address
+            .def_property_readonly("tiles", [](const ArchHandle &a) { return a.h->arch->tiles; })
+            .def("cores", [](const ArchHandle &a) {
+                std::vector<sfe::CoreConfiguration> out;
+                for (const sfe::CoreConfiguration *c : static_cast<const sfe::Architecture &>(*a.h->arch).cores()) out.push_back(*c);
+                return out;
+            })
+            .def(
+                    "create_tile",
+                    [](ArchHandle &a, std::string name, double en, double ln, double ee, double le, double es, double ls,
+                            double ew, double lw, bool log_energy) {
+                        sfe::TilePowerMetrics pm;
+                        pm.energy_north_hop = en; pm.latency_north_hop = ln;
+                        pm.energy_east_hop = ee; pm.latency_east_hop = le;
+                        pm.energy_south_hop = es; pm.latency_south_hop = ls;
+                        pm.energy_west_hop = ew; pm.latency_west_hop = lw;
+                        pm.log_energy = log_energy;
+                        return a.h->arch->create_tile(std::move(name), pm);
+                    },
+                    py::arg("name"), py::arg("energy_north_hop") = 0.0, py::arg("latency_north_hop") = 0.0,
+                    py::arg("energy_east_hop") = 0.0, py::arg("latency_east_hop") = 0.0, py::arg("energy_south_hop") = 0.0,
+                    py::arg("latency_south_hop") = 0.0, py::arg("energy_west_hop") = 0.0, py::arg("latency_west_hop") = 0.0,
+                    py::arg("log_energy") = false)
+            .def(
+                    "create_core",
+                    [](ArchHandle &a, std::string name, size_t parent_tile_id, const std::string &buffer_position,
+                            bool buffer_inside_unit, size_t max_neurons_supported, bool log_energy) {
+                        sfe::CorePipelineConfiguration pc{};
+                        pc.buffer_position = sfe::parse_buffer_position(buffer_position, buffer_inside_unit);
+                        pc.max_neurons_supported = max_neurons_supported;
+                        pc.log_energy = log_energy;
+                        return a.h->arch->create_core(std::move(name), parent_tile_id, pc);
+                    },
+                    py::arg("name"), py::arg("parent_tile_id"), py::arg("buffer_position") = "soma",
+                    py::arg("buffer_inside_unit") = false, py::arg("max_neurons_supported") = 1024, py::arg("log_energy") = false);
+
+    // ---- network (src/pymodule.cpp:873-1112) --------------------------------------------------------------
+    py::class_<sfe::NeuronAddress>(m, "NeuronAddress")
+            .def_readonly("group_name", &sfe::NeuronAddress::group_name)
+            .def_readonly("neuron_offset", &sfe::NeuronAddress::neuron_offset)
+            .def("__repr__", [](const sfe::NeuronAddress &a) {
+                return a.group_name + "." + (a.neuron_offset ? std::to_string(*a.neuron_offset) : std::string("*"));
+            })
+            .def(py::pickle([](const sfe::NeuronAddress &a) { return py::make_tuple(a.group_name, a.neuron_offset); },
+                    [](const py::tuple &t) {
+                        sfe::NeuronAddress a;
+                        a.group_name = t[0].cast<std::string>();
+                        a.neuron_offset = t[1].cast<std::optional<size_t>>();
+                        return a;
+                    }));
+    py::class_<sfe::Connection>(m, "Connection")
+            .def_readonly("pre_neuron", &sfe::Connection::pre_neuron)
+            .def_readonly("post_neuron", &sfe::Connection::post_neuron)
+            .def_readonly("synapse_hw_name", &sfe::Connection::synapse_hw_name)
+            .def_property_readonly("synapse_attributes", [](const sfe::Connection &c) { return from_attr_map(c.synapse_attributes); })
+            .def("__repr__", [](const sfe::Connection &c) {
+                return "sanafe::Connection(pre_neuron=" + c.pre_neuron.group_name + "." + std::to_string(c.pre_neuron.neuron_offset.value_or(0)) +
+                        " post_neuron=" + c.post_neuron.group_name + "." + std::to_string(c.post_neuron.neuron_offset.value_or(0)) + ")";
+            });
+    py::class_<NeuronRef>(m, "Neuron")
+            .def("__repr__", [](const NeuronRef &r) { return neuron_info(*r.n); })
+            .def("get_id", [](const NeuronRef &r) { return r.n->offset; })
+            .def("map_to_core", [](const NeuronRef &r, const sfe::CoreConfiguration &core) { r.n->map_to_core(core); })
+            .def(
+                    "set_attributes",
+                    // The reference binds the keyword names `soma_attributes` / `dendrite_attributes` to the C++
+                    // parameters in swapped order (src/pymodule.cpp:1016-1042 vs :466-490):
+                    // what a script passes as soma_attributes= is forwarded to the DENDRITE unit and vice versa.
+                    // A drop-in keeps that.
+                    [](const NeuronRef &r, std::optional<std::string> soma_hw_name, std::optional<std::string> default_synapse_hw_name,
+                            std::optional<std::string> dendrite_hw_name, std::optional<bool> log_spikes, std::optional<bool> log_potential,
+                            const py::dict &model_attributes, const py::dict &bound_as_soma_attributes,
+                            const py::dict &bound_as_dendrite_attributes) {
+                        sfe::NeuronConfiguration c;
+                        c.soma_hw_name = std::move(soma_hw_name);
+                        c.default_synapse_hw_name = std::move(default_synapse_hw_name);
+                        c.dendrite_hw_name = std::move(dendrite_hw_name);
+                        c.log_spikes = log_spikes;
+                        c.log_potential = log_potential;
+                        c.model_attributes = to_attr_map(model_attributes);
+                        for (auto &kv : to_attr_map(bound_as_soma_attributes, false, true, false)) c.model_attributes.insert(kv);
+                        for (auto &kv : to_attr_map(bound_as_dendrite_attributes, false, false, true)) c.model_attributes.insert(kv);
+                        r.n->set_attributes(c);
+                    },
+                    py::arg("soma_hw_name") = py::none(), py::arg("default_synapse_hw_name") = py::none(),
+                    py::arg("dendrite_hw_name") = py::none(), py::arg("log_spikes") = py::none(), py::arg("log_potential") = py::none(),
+                    py::arg("model_attributes") = py::dict(), py::arg("soma_attributes") = py::dict(),
+                    py::arg("dendrite_attributes") = py::dict())
+            .def(
+                    "connect_to_neuron",
+                    [](const NeuronRef &r, const NeuronRef &dest, std::optional<py::dict> attr) -> size_t {
+                        const size_t idx = r.n->connect_to_neuron(*dest.n);
+                        sfe::Connection &con = r.n->edges_out[idx];
+                        for (const auto &[key, a] : to_attr_map(attr.value_or(py::dict())))
+                        {
+                            if (a.forward_to_synapse) con.synapse_attributes[key] = a;
+                            if (a.forward_to_dendrite) con.dendrite_attributes[key] = a;
+                        }
+                        return idx;
+                    },
+                    py::arg("dest"), py::arg("attributes") = py::none())
+            .def_property_readonly("edges_out", [](const NeuronRef &r) { return r.n->edges_out; });
+    py::class_<GroupRef>(m, "NeuronGroup")
+            .def("__repr__", [](const GroupRef &g) { return group_info(*g.g); })
+            .def("get_name", [](const GroupRef &g) { return g.g->name; })
+            .def("connect_neurons_dense",
+                    [](const GroupRef &g, const GroupRef &dest, const py::dict &attributes) {
+                        g.g->connect_neurons_dense(*dest.g, to_attr_lists(attributes));
+                    },
+                    py::arg("dest_group"), py::arg("attributes"))
+            .def("connect_neurons_sparse",
+                    [](const GroupRef &g, const GroupRef &dest, const py::dict &attributes, const py::object &pairs) {
+                        if (!py::isinstance<py::iterable>(pairs))
+                            throw std::invalid_argument("Error: must provide connectivity as a list of source/destination pairs, "
+                                                        "providing the offsets within the groups.");
+                        std::vector<std::pair<size_t, size_t>> vec;
+                        for (auto it = py::iter(pairs); it != py::iterator::sentinel(); ++it)
+                        {
+                            if (!py::isinstance<py::iterable>(*it)) throw py::value_error("Error: each entry in the src/dest id list must be a 2-tuple");
+                            const auto seq = py::reinterpret_borrow<py::object>(*it).cast<py::sequence>();
+                            if (seq.size() != 2) throw py::value_error("Expected a 2-tuple");
+                            vec.emplace_back(seq[0].cast<size_t>(), seq[1].cast<size_t>());
+                        }
+                        g.g->connect_neurons_sparse(*dest.g, to_attr_lists(attributes), vec);
+                    },
+                    py::arg("dest_group"), py::arg("attributes"), py::arg("src_dest_id_pairs"))
+            .def("connect_neurons_conv2d",
+                    [](const GroupRef &g, const GroupRef &dest, const py::dict &attributes, int input_width, int input_height,
+                            int input_channels, int kernel_width, int kernel_height, int kernel_count, int stride_width, int stride_height) {
+                        sfe::Conv2DParameters cv;
+                        cv.input_width = input_width; cv.input_height = input_height; cv.input_channels = input_channels;
+                        cv.kernel_width = kernel_width; cv.kernel_height = kernel_height; cv.kernel_count = kernel_count;
+                        cv.stride_width = stride_width; cv.stride_height = stride_height;
+                        g.g->connect_neurons_conv2d(*dest.g, to_attr_lists(attributes), cv);
+                    },
+                    py::arg("dest_group"), py::arg("attributes"), py::arg("input_width"), py::arg("input_height"),
+                    py::arg("input_channels"), py::arg("kernel_width"), py::arg("kernel_height"), py::arg("kernel_count") = 1,
+                    py::arg("stride_width") = 1, py::arg("stride_height") = 1)
+            .def_property_readonly("neurons",
+                    [](const GroupRef &g) {
+                        py::list l;
+                        for (sfe::Neuron &n : g.g->neurons) l.append(NeuronRef{g.owner, &n});
+                        return l;
+                    })
+            .def("__getitem__",
+                    [](const GroupRef &g, const py::object &index) -> py::object {
+                        if (py::isinstance<py::int_>(index))
+                        {
+                            const size_t i = index.cast<size_t>();
+                            if (i >= g.g->neurons.size()) throw py::index_error();
+                            return py::cast(NeuronRef{g.owner, &g.g->neurons[i]});
+                        }
+                        if (py::isinstance<py::slice>(index))
+                        {
+                            size_t start = 0, stop = 0, step = 0, len = 0;
+                            if (!index.cast<py::slice>().compute(g.g->neurons.size(), &start, &stop, &step, &len)) throw py::error_already_set();
+                            py::list l;
+                            for (size_t k = 0; k < len; ++k) l.append(NeuronRef{g.owner, &g.g->neurons[start + k * step]});
+                            return l;
+                        }
+                        throw py::type_error("Index must be int or slice");
+                    })
+            .def("__len__", [](const GroupRef &g) { return g.g->neurons.size(); })
+            .def("__iter__", [](const GroupRef &g) {
+                py::list l;
+                for (sfe::Neuron &n : g.g->neurons) l.append(NeuronRef{g.owner, &n});
+                return py::iter(l);
+            });
+    py::class_<NetHandle, std::shared_ptr<NetHandle>>(m, "Network")
+            .def(py::init([]() {
+                auto n = std::make_shared<NetHandle>();
+                n->h = sfe_net_create("");
+                if (n->h == nullptr) raise_last();
+                return n;
+            }))
+            .def("__repr__", [](const std::shared_ptr<NetHandle> &n) {
+                return "sanafe::SpikingNetwork(groups=" + std::to_string(described(n).groups.size()) + ")";
+            })
+            .def(
+                    "create_neuron_group",
+                    [](const std::shared_ptr<NetHandle> &n, const std::string &group_name, int neuron_count, const py::dict &model_attributes,
+                            const std::string &default_synapse_hw_name, const std::string &default_dendrite_hw_name, bool log_potential,
+                            bool log_spikes, const std::string &soma_hw_name) {
+                        sfe::NeuronConfiguration c;
+                        c.default_synapse_hw_name = default_synapse_hw_name;
+                        c.dendrite_hw_name = default_dendrite_hw_name;
+                        c.log_potential = log_potential;
+                        c.log_spikes = log_spikes;
+                        c.soma_hw_name = soma_hw_name;
+                        c.model_attributes = to_attr_map(model_attributes);
+                        return GroupRef{n, &described(n).create_neuron_group(group_name, static_cast<size_t>(neuron_count), c)};
+                    },
+                    py::arg("group_name"), py::arg("neuron_count"), py::arg("model_attributes") = py::dict(),
+                    py::arg("default_synapse_hw_name") = "", py::arg("default_dendrite_hw_name") = "", py::arg("log_potential") = false,
+                    py::arg("log_spikes") = false, py::arg("soma_hw_name") = "")
+            .def(
+                    "save",
+                    [](const std::shared_ptr<NetHandle> &n, const std::string &path, bool use_netlist_format) {
+                        if (use_netlist_format) throw std::runtime_error("Network.save: only the YAML format is written by this build");
+                        if (sfe_net_save_yaml(n->h, path.c_str()) != 0) raise_last();
+                    },
+                    py::arg("path"), py::arg("use_netlist_format") = false)
+            .def_property_readonly("groups",
+                    [](const std::shared_ptr<NetHandle> &n) {
+                        py::dict d;
+                        for (auto &[name, g] : described(n).groups) d[py::str(name)] = GroupRef{n, g.get()};
+                        return d;
+                    })
+            .def("__getitem__", [](const std::shared_ptr<NetHandle> &n, const std::string &name) {
+                auto it = described(n).groups.find(name);
+                if (it == described(n).groups.end()) throw py::index_error();
+                return GroupRef{n, it->second.get()};
+            });
+    py::class_<MappedRef>(m, "MappedNeuron")
+            .def("__repr__", [](const MappedRef &r) { return "sanafe::MappedNeuron(" + r.group + "." + std::to_string(r.offset) + ")"; })
+            .def(
+                    "set_attributes",
+                    // MappedNeuron::set_attributes  src/mapped.cpp:113-166 via pyset_attributes_mapped (src/pymodule.cpp:502-527).
+                    // The running engine takes numeric soma parameters (per-neuron bias on a fast path, the others by
+                    // re-classing the neuron); anything structural has to be set before load().
+                    [](const MappedRef &r, const py::dict &model_attributes, const py::dict &bound_as_soma_attributes,
+                            const py::dict &bound_as_dendrite_attributes, std::optional<bool> log_spikes) {
+                        sfe::AttrMap all = to_attr_map(model_attributes);
+                        for (auto &kv : to_attr_map(bound_as_soma_attributes, false, true, false)) all.insert(kv);
+                        for (auto &kv : to_attr_map(bound_as_dendrite_attributes, false, false, true)) all.insert(kv);
+                        sfe_chip *chip = r.chip->handle();
+                        if (log_spikes.has_value() && sfe_chip_set_neuron_log_spikes(chip, r.group.c_str(), r.offset, *log_spikes ? 1 : 0) != 0) raise_last();
+                        for (const auto &[key, a] : all)
+                        {
+                            if (sfe::is_reserved_neuron_attribute(key))
+                                throw std::invalid_argument("Reserved neuron attribute '" + key + "' cannot be used as a model attribute. "
+                                        "Pass it as a direct argument instead (if supported).");
+                            if (!a.forward_to_soma) continue; // the built-in dendrite models take no per-neuron attributes
+                            if (a.is_list() || a.is_string())
+                                throw std::runtime_error("MappedNeuron.set_attributes: '" + key + "' is not a numeric soma parameter; set it on the "
+                                        "Neuron before SpikingChip.load()");
+                            if (sfe_chip_set_neuron_attribute(chip, r.group.c_str(), r.offset, key.c_str(), a.as_double()) != 0) raise_last();
+                        }
+                    },
+                    py::arg("model_attributes") = py::dict(), py::arg("soma_attributes") = py::dict(),
+                    py::arg("dendrite_attributes") = py::dict(), py::arg("log_spikes") = py::none());
     m.def(
             "load_arch",
             [](const std::string &path) {
@@ -350,8 +820,11 @@ PYBIND11_MODULE(sanafecpp_b200, m)
                 return py::make_tuple(a, n);
             },
             py::arg("path"));
-    py::class_<Chip>(m, "SpikingChip")
+    py::class_<Chip, std::shared_ptr<Chip>>(m, "SpikingChip")
             .def(py::init<const std::shared_ptr<ArchHandle> &, int>(), py::arg("arch"), py::arg("device") = 0)
+            .def_property_readonly("mapped_neuron_groups", &Chip::mapped_neuron_groups)
+            // the C-ABI handle (an address), for callers that mix this module with the C ABI
+            .def_property_readonly("_handle", [](Chip &c) { return reinterpret_cast<uintptr_t>(c.handle()); })
             .def("load", &Chip::load, py::arg("net"), py::arg("overwrite") = false)
             .def("sim", &Chip::sim, py::arg("timesteps") = 1, py::arg("timing_model") = "detailed",
                     py::arg("processing_threads") = 0, py::arg("scheduler_threads") = 0, py::arg("spike_trace") = py::none(),

@@ -1,0 +1,220 @@
+// yaml_writer.cpp — Network.save(path): writes a SpikingNetwork as the SNN YAML format.
+//
+// Same document layout as the reference's writer (src/yaml_snn.cpp:1058-1416 network section,
+// :1418-1555 mappings section): `network: {name, groups: [{name, attributes, neurons: [run: {...}]}],
+// edges: [{"g.i -> h.j": {attrs}}]}` followed by `mappings: [{"g.i": {core: "t.c", synapse, dendrite,
+// soma}}]` in mapping order; neurons with identical settings are written as one `a..b` run; attributes
+// that are forwarded to some hardware units only go under `synapse:` / `dendrite:` / `soma:`.
+// Differences, on purpose: a neuron attribute is omitted when it EQUALS the group default (the
+// reference's test is inverted, src/yaml_snn.cpp:1320-1326, and drops exactly the overrides), doubles
+// are written with 17 significant digits, and the file is rewritten rather than merged with previous
+// content. What is written loads back (here and in the reference) to a network that lowers to the same
+// tables: tests/test_python_builders.py.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <sstream>
+
+#include "handles.hpp"
+
+namespace sfe
+{
+namespace
+{
+bool same_attr(const Attr &a, const Attr &b)
+{
+    if (a.forward_to_synapse != b.forward_to_synapse || a.forward_to_dendrite != b.forward_to_dendrite ||
+            a.forward_to_soma != b.forward_to_soma || a.value.index() != b.value.index())
+        return false;
+    if (a.is_list())
+    {
+        const std::vector<Attr> &x = a.as_list(), &y = b.as_list();
+        if (x.size() != y.size()) return false;
+        for (size_t i = 0; i < x.size(); ++i)
+            if (x[i].name != y[i].name || !same_attr(x[i], y[i])) return false;
+        return true;
+    }
+    if (const bool *v = std::get_if<bool>(&a.value)) return *v == std::get<bool>(b.value);
+    if (const int *v = std::get_if<int>(&a.value)) return *v == std::get<int>(b.value);
+    if (const double *v = std::get_if<double>(&a.value)) return *v == std::get<double>(b.value);
+    return a.as_string() == b.as_string();
+}
+
+bool same_attrs(const AttrMap &a, const AttrMap &b)
+{
+    if (a.size() != b.size()) return false;
+    auto ia = a.begin();
+    auto ib = b.begin();
+    for (; ia != a.end(); ++ia, ++ib)
+        if (ia->first != ib->first || !same_attr(ia->second, ib->second)) return false;
+    return true;
+}
+
+std::string scalar(const std::string &s) // a string that must read back as this string
+{
+    bool plain = !s.empty() && s.front() != ' ' && s.back() != ' ';
+    for (const char ch : s)
+        if (std::string("[]{},:#&*!|>'\"%@`\n\t").find(ch) != std::string::npos) plain = false;
+    if (plain)
+    {
+        // would it be typed as a number or a bool by the reader (src/yaml_common.cpp:205-263)?
+        char *end = nullptr;
+        std::strtod(s.c_str(), &end);
+        if (end != nullptr && *end == '\0') plain = false;
+        if (s == "true" || s == "false" || s == "True" || s == "False" || s == "null" || s == "~" || s == "-") plain = false;
+    }
+    if (plain) return s;
+    std::string out = "\"";
+    for (const char ch : s)
+    {
+        if (ch == '"' || ch == '\\') out += '\\';
+        if (ch == '\n') out += "\\n";
+        else if (ch == '\t') out += "\\t";
+        else out += ch;
+    }
+    return out + "\"";
+}
+
+std::string number(const double v)
+{
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), "%.17g", v);
+    std::string s = buf;
+    // keep the type: a double must not read back as an int
+    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+    return s;
+}
+
+void write_value(std::ostream &out, const Attr &a) // flow style
+{
+    if (const bool *b = std::get_if<bool>(&a.value)) out << (*b ? "true" : "false");
+    else if (const int *i = std::get_if<int>(&a.value)) out << *i;
+    else if (const double *d = std::get_if<double>(&a.value)) out << number(*d);
+    else if (const std::string *s = std::get_if<std::string>(&a.value)) out << scalar(*s);
+    else
+    {
+        const std::vector<Attr> &list = a.as_list();
+        out << "[";
+        for (size_t k = 0; k < list.size(); ++k)
+        {
+            if (k != 0) out << ", ";
+            if (list[k].name.has_value() && !list[k].name->empty())
+            {
+                out << "{" << scalar(*list[k].name) << ": ";
+                write_value(out, list[k]);
+                out << "}";
+            }
+            else write_value(out, list[k]);
+        }
+        out << "]";
+    }
+}
+
+// "key: value" items of a flow mapping; unit-specific attributes nest under synapse/dendrite/soma
+std::vector<std::string> flow_items(const AttrMap &attrs, const AttrMap *defaults)
+{
+    std::vector<std::string> items;
+    std::map<std::string, std::vector<std::string>> sections;
+    for (const auto &[key, a] : attrs)
+    {
+        if (defaults != nullptr)
+        {
+            const auto d = defaults->find(key);
+            if (d != defaults->end() && same_attr(d->second, a)) continue;
+        }
+        std::ostringstream v;
+        v << scalar(key) << ": ";
+        write_value(v, a);
+        if (a.forward_to_synapse && a.forward_to_dendrite && a.forward_to_soma) items.push_back(v.str());
+        else
+        {
+            if (a.forward_to_synapse) sections["synapse"].push_back(v.str());
+            if (a.forward_to_dendrite) sections["dendrite"].push_back(v.str());
+            if (a.forward_to_soma) sections["soma"].push_back(v.str());
+        }
+    }
+    for (const auto &[name, sub] : sections)
+    {
+        std::string s = name + ": {";
+        for (size_t k = 0; k < sub.size(); ++k) s += (k != 0 ? ", " : "") + sub[k];
+        items.push_back(s + "}");
+    }
+    return items;
+}
+
+std::string flow_map(const std::vector<std::string> &items)
+{
+    std::string s = "{";
+    for (size_t k = 0; k < items.size(); ++k) s += (k != 0 ? ", " : "") + items[k];
+    return s + "}";
+}
+
+std::string address(const NeuronAddress &a)
+{
+    return a.neuron_offset.has_value() ? a.group_name + "." + std::to_string(*a.neuron_offset) : a.group_name;
+}
+} // namespace
+
+void save_net_yaml(const SpikingNetwork &net, const std::string &path)
+{
+    std::ostringstream out;
+    out << "network:\n  name: " << (net.name.empty() ? std::string("\" \"") : scalar(net.name)) << "\n  groups:\n";
+    for (const auto &[gname, gptr] : net.groups)
+    {
+        const NeuronGroup &g = *gptr;
+        const NeuronConfiguration &def = g.default_neuron_config;
+        std::vector<std::string> items = flow_items(def.model_attributes, nullptr);
+        if (def.log_spikes.has_value()) items.push_back(std::string("log_spikes: ") + (*def.log_spikes ? "true" : "false"));
+        if (def.log_potential.has_value()) items.push_back(std::string("log_potential: ") + (*def.log_potential ? "true" : "false"));
+        out << "  - name: " << scalar(g.name) << "\n    attributes: " << flow_map(items) << "\n    neurons:\n";
+        const bool def_spikes = def.log_spikes.value_or(false), def_pot = def.log_potential.value_or(false);
+        size_t run_start = 0;
+        for (size_t i = 1; i <= g.neurons.size(); ++i)
+        {
+            if (i < g.neurons.size())
+            {
+                const Neuron &a = g.neurons[run_start], &b = g.neurons[i];
+                if (same_attrs(a.model_attributes, b.model_attributes) && a.log_spikes == b.log_spikes &&
+                        a.log_potential == b.log_potential)
+                    continue;
+            }
+            const Neuron &n = g.neurons[run_start];
+            std::vector<std::string> nitems = flow_items(n.model_attributes, &def.model_attributes);
+            if (n.log_spikes != def_spikes) nitems.push_back(std::string("log_spikes: ") + (n.log_spikes ? "true" : "false"));
+            if (n.log_potential != def_pot) nitems.push_back(std::string("log_potential: ") + (n.log_potential ? "true" : "false"));
+            out << "    - {" << run_start;
+            if (i - 1 > run_start) out << ".." << (i - 1);
+            out << ": " << flow_map(nitems) << "}\n";
+            run_start = i;
+        }
+    }
+    out << "  edges:\n";
+    for (const auto &[gname, gptr] : net.groups)
+        for (const Neuron &n : gptr->neurons)
+            for (const Connection &con : n.edges_out)
+                out << "  - {" << scalar(address(con.pre_neuron) + " -> " + address(con.post_neuron)) << ": "
+                    << flow_map(flow_items(con.synapse_attributes, nullptr)) << "}\n";
+    // mappings, in mapping order (src/yaml_snn.cpp:1477-1490)
+    std::vector<const Neuron *> all;
+    for (const auto &[gname, gptr] : net.groups)
+        for (const Neuron &n : gptr->neurons) all.push_back(&n);
+    std::stable_sort(all.begin(), all.end(), [](const Neuron *a, const Neuron *b) { return a->mapping_order < b->mapping_order; });
+    out << "mappings:\n";
+    for (const Neuron *n : all)
+    {
+        if (!n->core_address.has_value()) throw std::runtime_error("Error: Neuron not mapped, can't save."); // :1509-1514
+        out << "- {" << scalar(n->parent_group_name + "." + std::to_string(n->offset)) << ": {core: \""
+            << n->core_address->parent_tile_id << "." << n->core_address->offset_within_tile << "\"";
+        if (!n->default_synapse_hw_name.empty()) out << ", synapse: " << scalar(n->default_synapse_hw_name);
+        if (!n->dendrite_hw_name.empty()) out << ", dendrite: " << scalar(n->dendrite_hw_name);
+        if (!n->soma_hw_name.empty()) out << ", soma: " << scalar(n->soma_hw_name);
+        out << "}}\n";
+    }
+    std::ofstream fp(path);
+    if (!fp.is_open()) throw std::runtime_error("Failed to open YAML file for writing: " + path);
+    fp << out.str();
+}
+
+} // namespace sfe

@@ -13,15 +13,24 @@ from helpers import REFERENCE_ROOT, Oracle
 from sanafe_b200 import dse
 
 
+def _records(ptr, count):
+    """Field values of a ctypes struct array (padding bytes are not part of the comparison)."""
+    def value(x):
+        return tuple(value(getattr(x, name)) for name, _ in x._fields_) if hasattr(x, "_fields_") else x
+    return tuple(value(ptr[k]) for k in range(count))
+
+
 def table_bytes(t):
-    """The lowered tables that decide the simulation, as bytes."""
-    parts = [C.string_at(t.cores, C.sizeof(t.cores.contents) * t.n_cores),
-             C.string_at(t.neuron_class, 4 * t.n_neurons), C.string_at(t.neuron_bias, 8 * t.n_neurons),
-             C.string_at(t.soma_classes, C.sizeof(t.soma_classes.contents) * t.n_soma_classes),
-             C.string_at(t.cost_classes, C.sizeof(t.cost_classes.contents) * t.n_cost_classes),
-             C.string_at(t.axons_in, C.sizeof(t.axons_in.contents) * t.n_axons_in),
-             C.string_at(t.syn_weight, 8 * t.n_synapses), C.string_at(t.syn_meta, 4 * t.n_synapses)]
-    return b"".join(parts)
+    """The lowered tables that decide the simulation, in a comparable form."""
+    return (_records(t.cores, t.n_cores), _records(t.soma_classes, t.n_soma_classes),
+            _records(t.cost_classes, t.n_cost_classes), _records(t.axons_in, t.n_axons_in),
+            _records(t.inputs, t.n_inputs), _records(t.noise, t.n_noise),
+            C.string_at(t.neuron_class, 4 * t.n_neurons), C.string_at(t.neuron_aux, 4 * t.n_neurons),
+            C.string_at(t.neuron_bias, 8 * t.n_neurons), C.string_at(t.neuron_potential0, 8 * t.n_neurons),
+            C.string_at(t.axon_out_begin, 4 * (t.n_neurons + 1)), C.string_at(t.axon_out_target, 4 * t.n_axons_out),
+            C.string_at(t.input_spikes, t.n_input_spikes), C.string_at(t.probes, 4 * t.n_probes),
+            C.string_at(t.u_probes, 4 * t.n_u_probes), C.string_at(t.noise_values, 8 * t.n_noise_values),
+            C.string_at(t.syn_weight, 8 * t.n_synapses), C.string_at(t.syn_meta, 4 * t.n_synapses))
 
 
 def test_sweep_points():
