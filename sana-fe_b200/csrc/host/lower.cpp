@@ -706,6 +706,13 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                         }
                     }
                 }
+                // InputModel::update throws the moment a non-zero current reaches an input neuron
+                // (src/models.cpp:866-874); a device engine cannot raise mid-step, so the edge is refused here
+                if (lcn.weight != 0.0 && pc.units[post.soma].model == UnitModel::input)
+                    throw std::runtime_error("Current sent to input neuron which cannot be processed (" +
+                            std::to_string(lcn.weight) + "): edge " + con.pre_neuron.group_name + "." +
+                            std::to_string(con.pre_neuron.neuron_offset.value_or(0)) + " -> " + con.post_neuron.group_name + "." +
+                            std::to_string(*con.post_neuron.neuron_offset));
                 pre.out.push_back(lcn);
             }
         }

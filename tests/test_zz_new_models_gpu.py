@@ -108,3 +108,11 @@ def test_neuron_trace_surfaces(tmp_path):
     assert cli.returncode == 0, cli.stderr
     cli_lines = (tmp_path / "cli" / "neurons.csv").read_text().splitlines()
     assert cli_lines == lines
+
+
+def test_reference_unit_vectors_on_the_device(tmp_path):
+    """The reference's per-model unit-test expectations (tests/unit/test_*.cpp), restated on a one-neuron rig, on
+    the device (the CPU restatement passes the same list in test_reference_unit_vectors.py)."""
+    import reference_unit_vectors as vectors
+    import unit_rig as rig
+    vectors.check_all(tmp_path, 0, rig.device_runner)
