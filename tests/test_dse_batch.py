@@ -87,3 +87,14 @@ def test_batch_sim_needs_a_device(tmp_path):
     sweep = dse.Sweep([(128, 1.0), (128, 2.0)], str(tmp_path), device=-1)
     with pytest.raises(sfe.SanafeError, match="sfe_batch_sim: chip 0: .*no CUDA device"):
         sweep.sim(3)
+
+
+def test_sweep_is_dealt_round_robin_to_ranks():
+    """More GPUs = replicas only: every design point lands on exactly one rank, 128 per rank at 8 GPUs."""
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import dse_sweep
+    pts = dse.sweep_points()
+    parts = [dse_sweep.points_of_rank(pts, r, 8) for r in range(8)]
+    assert sorted(sum(parts, [])) == sorted(pts) and all(len(p) == 128 for p in parts)

@@ -6,7 +6,12 @@ chip, worker threads keep that many chips in flight) and, for comparison, one ch
     python tools/dse_sweep.py --mappings 4 --multipliers 8 --steps 200 --threads 16
 
 Prints one JSON line: simulations/s, timesteps/s and synaptic events/s over all design points, batched and
-sequential (wall clock around the sim calls; loading is reported separately)."""
+sequential (wall clock around the sim calls; loading is reported separately).
+
+More GPUs: replicas only (independent simulations, no exchange). Under
+`python -m torch.distributed.run --nproc-per-node N tools/dse_sweep.py ...` rank r takes design points r, r+N, ...
+on device LOCAL_RANK; the ranks meet at a gloo barrier on both sides of the timed region and rank 0 prints the
+line with the maximum wall time and the summed counts."""
 import argparse
 import json
 import os
@@ -18,6 +23,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "sana-fe_b200"))
 import sanafe_b200 as sfe  # noqa: E402
 from sanafe_b200 import dse  # noqa: E402
+
+
+def points_of_rank(points, rank, world):
+    """Design points dealt round-robin (mappings and multipliers both vary fastest across ranks)."""
+    return points[rank::world]
 
 
 def main():
@@ -36,24 +46,43 @@ def main():
     pick_n = [npcs[(i * len(npcs)) // args.mappings] for i in range(args.mappings)]
     pick_m = [mults[(i * len(mults)) // args.multipliers] for i in range(args.multipliers)]
     points = [(n, m) for n in pick_n for m in pick_m]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # control plane only (barriers, gathering the ranks' numbers)
+        dist.init_process_group("gloo")
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))
+    all_points = len(points)
+    points = points_of_rank(points, rank, world)
     work = tempfile.mkdtemp(prefix="dse_")
     t0 = time.time()
     sweep = dse.Sweep(points, work, device=args.device, host_threads=args.threads)
     load_s = time.time() - t0
     sweep.sim(10)  # warm-up (first launches, pinned buffers)
-    out = {"workload": "config 5 slice", "design_points": len(points), "steps": args.steps,
+    out = {"workload": "config 5 slice", "design_points": all_points, "n_gpus": world, "steps": args.steps,
            "neurons_per_core": pick_n, "host_threads": args.threads, "load_s": round(load_s, 2)}
     for label, threads in (("sequential", 1), ("batched", args.threads)):
         sweep.host_threads = threads
+        if dist is not None:
+            dist.barrier()
         t0 = time.time()
         rds = sweep.sim(args.steps)
         wall = time.time() - t0
         events = sum(r.spikes for r in rds)
-        out[label] = {"wall_s": round(wall, 4), "sims_per_s": round(len(points) / wall, 2),
-                      "timesteps_per_s": round(len(points) * args.steps / wall, 1),
+        if dist is not None:
+            dist.barrier()
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (wall, events))
+            wall = max(g[0] for g in gathered)
+            events = sum(g[1] for g in gathered)
+        out[label] = {"wall_s": round(wall, 4), "sims_per_s": round(all_points / wall, 2),
+                      "timesteps_per_s": round(all_points * args.steps / wall, 1),
                       "synaptic_events_per_s": round(events / wall, 1)}
     out["batched_over_sequential"] = round(out["sequential"]["wall_s"] / out["batched"]["wall_s"], 2)
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
