@@ -310,6 +310,10 @@ int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n);
  * the device as an overlay: bits[step][col] != 0 makes the input neuron with that poisson_col spike in that
  * step. Covers the next `n_steps` steps to be enqueued; sfe_chip_sim does this itself. */
 int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_steps, uint32_t n_cols);
+/* Cooperative cancellation, callable from another thread: a running sfe_engine_run / sfe_chip_sim returns -1
+ * ("simulation interrupted") at its next batch boundary (at most 4096 steps); the steps done so far stay done.
+ * The reference polls PyErr_CheckSignals every 100 ms inside its loop (src/pymodule.cpp:629-652). on = 0 re-arms. */
+void sfe_engine_request_stop(sfe_engine *e, int on);
 /* Host-only source of that overlay (no device needed): one std::mt19937 per Poisson unit, seeded
  * tables->input_seed_base + unit + 1. sfe_poisson_fill writes bits[n_steps][sfe_poisson_cols] for the next
  * n_steps steps and advances the streams (they are not rewound by a reset: InputModel::reset, src/models.hpp:358). */
@@ -464,6 +468,8 @@ size_t sfe_chip_trace_names(const sfe_chip *c, char *buf, size_t cap);
 size_t sfe_chip_group_names(const sfe_chip *c, char *buf, size_t cap);
 /* MappedNeuron::set_attributes(..., log_spikes) (src/mapped.cpp:113-124) */
 int sfe_chip_set_neuron_log_spikes(sfe_chip *c, const char *group, uint64_t offset, int on);
+/* sfe_engine_request_stop for a chip; sfe_chip_sim re-arms it when it starts */
+void sfe_chip_request_stop(sfe_chip *c);
 /* an empty network for the object-by-object builders, and Network.save (src/network.cpp:693-712; YAML) */
 sfe_net *sfe_net_create(const char *name);
 int sfe_net_save_yaml(const sfe_net *net, const char *path);

@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1860,6 +1861,8 @@ struct sfe_engine
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used{0};
     bool ordered_any{false}, dual_any{false};
+    // cooperative cancellation of a long sfe_engine_run (Ctrl-C in the Python binding): checked between batches
+    std::atomic<bool> stop_requested{false};
     // Poisson overlay (host-drawn, see poisson.cpp)
     uint32_t n_poisson_cols{0};
     uint8_t *d_overlay{nullptr};
@@ -2666,6 +2669,11 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
     return 0;
 }
 
+extern "C" void sfe_engine_request_stop(sfe_engine *e, int on)
+{
+    e->stop_requested.store(on != 0, std::memory_order_relaxed);
+}
+
 extern "C" int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_steps, uint32_t n_cols)
 {
     SFE_CUDA(cudaSetDevice(e->device));
@@ -2775,6 +2783,12 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
     int64_t done = 0;
     while (done < timesteps)
     {
+        if (e->stop_requested.load(std::memory_order_relaxed))
+        {
+            // the steps simulated so far stay simulated (state and timestep counter), like an interrupted reference run
+            sfe::set_last_error("simulation interrupted after " + std::to_string(done) + " of " + std::to_string(timesteps) + " timesteps");
+            return -1;
+        }
         const int64_t batch = std::min<int64_t>(batch_cap, timesteps - done);
         if (per_step > 0 && e->ensure_pinned(per_step * static_cast<size_t>(batch)) != 0) return -1;
         for (int64_t b = 0; b < batch; ++b)

@@ -279,6 +279,7 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                 if (c->engine == nullptr)
                     throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback");
                 const auto wall0 = std::chrono::steady_clock::now();
+                sfe_engine_request_stop(c->engine, 0);
                 if (timing_model == SFE_TIMING_CYCLE)
                     throw std::runtime_error("the cycle-accurate timing model needs Booksim2 (third-party, not "
                                              "available): out of scope");
@@ -447,6 +448,11 @@ extern "C" int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timeste
         return sfe_chip_sim(chips[k], timesteps, timing_model, reqs != nullptr ? &reqs[k] : nullptr,
                 out != nullptr ? &out[k] : nullptr);
     });
+}
+
+extern "C" void sfe_chip_request_stop(sfe_chip *c)
+{
+    if (c != nullptr && c->engine != nullptr) sfe_engine_request_stop(c->engine, 1);
 }
 
 extern "C" int sfe_chip_reset(sfe_chip *c)

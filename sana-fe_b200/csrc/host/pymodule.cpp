@@ -13,7 +13,11 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <fstream>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -281,12 +285,57 @@ public:
         req.neuron_traces = utraces.empty() ? nullptr : utraces.data();
         sfe_run_data rd{};
         const int timing = parse_timing(timing_model);
-        int rc = 0;
+        // The device loop runs on a worker thread with the GIL released; this thread wakes every 100 ms to let
+        // Python deliver signals (Ctrl-C), as the reference's loop does (src/pymodule.cpp:629-652), and asks the
+        // engine to stop at its next batch boundary when one arrives.
+        int rc = 0, kind = SFE_ERROR_RUNTIME;
+        std::string error;
+        bool interrupted = false;
         {
-            py::gil_scoped_release release;
-            rc = sfe_chip_sim(h_, timesteps, timing, &req, &rd);
+            std::mutex mu;
+            std::condition_variable cv;
+            bool finished = false;
+            std::thread worker([&]() {
+                const int r = sfe_chip_sim(h_, timesteps, timing, &req, &rd);
+                const std::lock_guard<std::mutex> lock(mu);
+                rc = r;
+                if (r != 0)
+                {
+                    error = sfe_last_error(); // thread-local: carry it over
+                    kind = sfe_last_error_kind();
+                }
+                finished = true;
+                cv.notify_all();
+            });
+            for (;;)
+            {
+                {
+                    py::gil_scoped_release release;
+                    std::unique_lock<std::mutex> lock(mu);
+                    if (cv.wait_for(lock, std::chrono::milliseconds(100), [&] { return finished; })) break;
+                }
+                if (!interrupted && PyErr_CheckSignals() != 0)
+                {
+                    interrupted = true;
+                    sfe_chip_request_stop(h_);
+                }
+            }
+            {
+                py::gil_scoped_release release;
+                worker.join();
+            }
         }
-        if (rc != 0) raise_last();
+        if (interrupted) throw py::error_already_set();
+        if (rc != 0)
+        {
+            switch (kind)
+            {
+            case SFE_ERROR_INVALID_ARGUMENT: throw std::invalid_argument(error);
+            case SFE_ERROR_OUT_OF_RANGE: throw std::out_of_range(error);
+            case SFE_ERROR_HARDWARE_MAPPING: throw sfe::HardwareMappingError(error);
+            default: throw std::runtime_error(error);
+            }
+        }
         // result dictionary  src/pymodule.cpp:268-288, 698-705
         py::dict energy;
         energy["total"] = rd.total_energy;

@@ -236,3 +236,14 @@ def test_mapped_neuron_set_attributes():
         groups["out"][0].set_attributes(model_attributes={"log_spikes": True})
     with pytest.raises(RuntimeError, match="before SpikingChip.load"):
         groups["in"][1].set_attributes(model_attributes={"spikes": [1, 1]})
+
+
+def test_sim_errors_cross_the_worker_thread():
+    """sim() runs the device loop on a worker thread (signal polling on the caller's): errors raised there must
+    arrive as the exception the caller sees — here the no-fallback rule on a host-only chip."""
+    m = module()
+    arch = m.load_arch(example_arch_path())
+    chip = m.SpikingChip(arch, device=-1)
+    chip.load(build_example(m, arch))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        chip.sim(10, timing_model="simple")

@@ -116,3 +116,31 @@ def test_reference_unit_vectors_on_the_device(tmp_path):
     import reference_unit_vectors as vectors
     import unit_rig as rig
     vectors.check_all(tmp_path, 0, rig.device_runner)
+
+
+@pytest.mark.timeout(180)
+def test_ctrl_c_interrupts_a_long_sim():
+    """The reference's Python loop polls for signals every 100 ms (src/pymodule.cpp:629-652): a KeyboardInterrupt
+    must surface while the device runs, and the chip must stay usable afterwards."""
+    import os
+    import signal
+    import threading
+    import time
+    from helpers import ROOT, golden_flat
+    from sanafe_b200 import sanafecpp_b200 as m
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch, net = m.load_flat(golden_flat("example"))
+        chip = m.SpikingChip(arch)
+        chip.load(net)
+    finally:
+        os.chdir(cwd)
+    chip.sim(100, timing_model="simple")  # warm-up
+    threading.Timer(0.5, lambda: os.kill(os.getpid(), signal.SIGINT)).start()
+    t0 = time.time()
+    with pytest.raises(KeyboardInterrupt):
+        chip.sim(3_000_000, timing_model="simple")
+    assert time.time() - t0 < 60.0
+    res = chip.sim(10, timing_model="simple")
+    assert res["timesteps_executed"] == 10 and res["timestep_start"] > 101
