@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cores", type=int, default=FULL["cores"], help="scale the workload down (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dse", action="store_true", help="skip the design-space-sweep side measurement (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -306,6 +307,7 @@ def main():
            "note": "C-ABI calls with pinned host buffers; step t+1's bias upload overlaps step t (double-buffered set_bias)"}
 
     cpu = None if args.no_cpu_baseline else run_reference_sample(20, 1)
+    dse = None if args.no_dse else dse_side_measurement()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -318,9 +320,27 @@ def main():
         "roofline": roofline,
         "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        # BASELINE configs[4] (design-space sweep batched on one GPU): a side measurement, not the headline metric
+        "dse": dse,
     }
     print(json.dumps(line))
     return 0
+
+
+def dse_side_measurement():
+    """A 16-point slice of the config-5 sweep (tools/dse_sweep.py) in a child process, so that nothing it does can
+    cost the headline line; returns its JSON or the reason it is missing."""
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "dse_sweep.py"), "--mappings", "2", "--multipliers", "8",
+           "--steps", "200", "--threads", "16"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+        if res.returncode != 0:
+            return {"error": (res.stderr or res.stdout)[-300:]}
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 - a side measurement must never fail the bench
+        return {"error": repr(e)[:300]}
 
 
 def nccl_library_path():
