@@ -20,17 +20,21 @@ def _records(ptr, count):
     return tuple(value(ptr[k]) for k in range(count))
 
 
+def _bytes(ptr, n_bytes):
+    return C.string_at(ptr, n_bytes) if n_bytes else b""  # an empty table may be a NULL pointer
+
+
 def table_bytes(t):
     """The lowered tables that decide the simulation, in a comparable form."""
     return (_records(t.cores, t.n_cores), _records(t.soma_classes, t.n_soma_classes),
             _records(t.cost_classes, t.n_cost_classes), _records(t.axons_in, t.n_axons_in),
             _records(t.inputs, t.n_inputs), _records(t.noise, t.n_noise),
-            C.string_at(t.neuron_class, 4 * t.n_neurons), C.string_at(t.neuron_aux, 4 * t.n_neurons),
-            C.string_at(t.neuron_bias, 8 * t.n_neurons), C.string_at(t.neuron_potential0, 8 * t.n_neurons),
-            C.string_at(t.axon_out_begin, 4 * (t.n_neurons + 1)), C.string_at(t.axon_out_target, 4 * t.n_axons_out),
-            C.string_at(t.input_spikes, t.n_input_spikes), C.string_at(t.probes, 4 * t.n_probes),
-            C.string_at(t.u_probes, 4 * t.n_u_probes), C.string_at(t.noise_values, 8 * t.n_noise_values),
-            C.string_at(t.syn_weight, 8 * t.n_synapses), C.string_at(t.syn_meta, 4 * t.n_synapses))
+            _bytes(t.neuron_class, 4 * t.n_neurons), _bytes(t.neuron_aux, 4 * t.n_neurons),
+            _bytes(t.neuron_bias, 8 * t.n_neurons), _bytes(t.neuron_potential0, 8 * t.n_neurons),
+            _bytes(t.axon_out_begin, 4 * (t.n_neurons + 1)), _bytes(t.axon_out_target, 4 * t.n_axons_out),
+            _bytes(t.input_spikes, t.n_input_spikes), _bytes(t.probes, 4 * t.n_probes),
+            _bytes(t.u_probes, 4 * t.n_u_probes), _bytes(t.noise_values, 8 * t.n_noise_values),
+            _bytes(t.syn_weight, 8 * t.n_synapses), _bytes(t.syn_meta, 4 * t.n_synapses))
 
 
 def test_sweep_points():
