@@ -1,6 +1,9 @@
 // lower.cpp — see lower.hpp.
 #include "lower.hpp"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 
@@ -70,6 +73,7 @@ struct LNeuron
     const Neuron *n;
     uint32_t group;
     UnitKey dend, soma;
+    UnitState *dend_unit{nullptr}, *soma_unit{nullptr}; // into LCore::units (stable addresses)
     size_t dend_addr, soma_addr;
     sfe_soma_class cls;
     double bias{0.0};
@@ -89,8 +93,9 @@ struct LCore
 {
     const CoreConfiguration *cfg;
     std::vector<LNeuron> neurons;
-    std::map<UnitKey, UnitState> units;
+    std::map<UnitKey, UnitState> units; // (node-based: element addresses are stable)
     std::vector<LAxonIn> axons_in;
+    std::unordered_map<std::string, std::pair<UnitKey, UnitState *>> synapse_hw; // get_hw results by unit name
 };
 
 UnitModel parse_model(const PipelineUnitConfiguration &u)
@@ -535,8 +540,10 @@ uint32_t count_input_units(const Architecture &arch)
     return n;
 }
 
+#define SFE_PHASE_MARK(x) do { if (std::getenv("SFE_LOWER_PROFILE")) { auto now_ = std::chrono::steady_clock::now(); std::fprintf(stderr, "phase %s: %.3f\n", x, std::chrono::duration<double>(now_ - t_phase_).count()); t_phase_ = now_; } } while (0)
 void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTables &out)
 {
+    auto t_phase_ = std::chrono::steady_clock::now();
     out = HostTables{};
     fill_arch_tables(arch, out);
     const std::vector<const CoreConfiguration *> core_cfgs = arch.cores();
@@ -550,6 +557,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         out.group_names.push_back(name);
         groups.push_back(g.get());
     }
+    SFE_PHASE_MARK("0");
     // ---- map_neurons: mapping_order fixes the in-core order (src/chip.cpp:186-234)
     struct Pending
     {
@@ -595,6 +603,8 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         UnitState &soma = lc.units[ln.soma];
         soma.model = parse_model(soma_cfg);
         ln.soma_addr = soma.neuron_count++;
+        ln.dend_unit = &lc.units[ln.dend]; // (looked up again: inserting the soma unit cannot move it, but `dend` may alias)
+        ln.soma_unit = &soma;
         if (dend.model != UnitModel::accumulator && dend.model != UnitModel::accumulator_with_delay)
             throw std::runtime_error("Unit '" + dend_cfg.name + "' is not a dendrite model");
         // capacity of the built-in models' state tables (src/models.hpp:29,283)
@@ -646,6 +656,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         lc.neurons.push_back(std::move(ln));
     }
 
+    SFE_PHASE_MARK("1");
     // ---- device indices: cores in id order, neurons in in-core order --------
     uint32_t next = 0;
     for (size_t c = 0; c < lcores.size(); ++c)
@@ -656,7 +667,9 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
     }
     const uint32_t n_neurons = next;
 
+    SFE_PHASE_MARK("2");
     // ---- map_connections  src/chip.cpp:334-380 --------------------------------
+    size_t last_post_group = SIZE_MAX;
     for (size_t gi = 0; gi < groups.size(); ++gi)
     {
         for (const Neuron &src : groups[gi]->neurons)
@@ -668,9 +681,14 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             {
                 if (!con.post_neuron.neuron_offset.has_value())
                     throw std::invalid_argument("Post neuron doesn't specify group offset");
-                const auto git = std::lower_bound(out.group_names.begin(), out.group_names.end(), con.post_neuron.group_name);
-                if (git == out.group_names.end() || *git != con.post_neuron.group_name) throw std::out_of_range("map::at");
-                const size_t pg = static_cast<size_t>(git - out.group_names.begin());
+                // consecutive edges mostly stay in one post group: remember the last lookup
+                if (last_post_group == SIZE_MAX || out.group_names[last_post_group] != con.post_neuron.group_name)
+                {
+                    const auto git = std::lower_bound(out.group_names.begin(), out.group_names.end(), con.post_neuron.group_name);
+                    if (git == out.group_names.end() || *git != con.post_neuron.group_name) throw std::out_of_range("map::at");
+                    last_post_group = static_cast<size_t>(git - out.group_names.begin());
+                }
+                const size_t pg = last_post_group;
                 const auto [post_core, post_idx] = where[pg].at(*con.post_neuron.neuron_offset);
                 LCore &pc = lcores[post_core];
                 LNeuron &post = pc.neurons[post_idx];
@@ -680,16 +698,24 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 LConn lcn{};
                 lcn.post_core = post_core;
                 lcn.post_in_core = post_idx;
-                lcn.syn = get_hw(*pc.cfg, hw_name, true, false, false);
-                const PipelineUnitConfiguration &syn_cfg = pc.cfg->pipeline_hw[lcn.syn.family];
-                check_unit_shape(syn_cfg);
-                UnitState &syn = pc.units[lcn.syn];
-                syn.model = parse_model(syn_cfg);
-                if (syn.model != UnitModel::current_based)
-                    throw std::runtime_error("Unit '" + syn_cfg.name + "' is not a synapse model");
+                // Core::get_hw + the unit checks once per (core, synapse unit name), not per connection
+                auto cached = pc.synapse_hw.find(hw_name);
+                if (cached == pc.synapse_hw.end())
+                {
+                    const UnitKey key = get_hw(*pc.cfg, hw_name, true, false, false);
+                    const PipelineUnitConfiguration &syn_cfg = pc.cfg->pipeline_hw[key.family];
+                    check_unit_shape(syn_cfg);
+                    UnitState &fresh = pc.units[key];
+                    fresh.model = parse_model(syn_cfg);
+                    if (fresh.model != UnitModel::current_based)
+                        throw std::runtime_error("Unit '" + syn_cfg.name + "' is not a synapse model");
+                    cached = pc.synapse_hw.emplace(hw_name, std::make_pair(key, &fresh)).first;
+                }
+                lcn.syn = cached->second.first;
+                UnitState &syn = *cached->second.second;
                 lcn.syn_addr = static_cast<uint32_t>(syn.connection_count++);
                 lcn.weight = 0.0;
-                UnitState &dend = pc.units[post.dend];
+                UnitState &dend = *post.dend_unit;
                 // MappedConnection::set_attributes  src/mapped.cpp:60-89
                 for (const auto &[key, a] : con.synapse_attributes)
                 {
@@ -708,7 +734,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 }
                 // InputModel::update throws the moment a non-zero current reaches an input neuron
                 // (src/models.cpp:866-874); a device engine cannot raise mid-step, so the edge is refused here
-                if (lcn.weight != 0.0 && pc.units[post.soma].model == UnitModel::input)
+                if (lcn.weight != 0.0 && post.soma_unit->model == UnitModel::input)
                     throw std::runtime_error("Current sent to input neuron which cannot be processed (" +
                             std::to_string(lcn.weight) + "): edge " + con.pre_neuron.group_name + "." +
                             std::to_string(con.pre_neuron.neuron_offset.value_or(0)) + " -> " + con.post_neuron.group_name + "." +
@@ -718,6 +744,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         }
     }
 
+    SFE_PHASE_MARK("3");
     // ---- map_axons  src/chip.cpp:382-408, 1263-1391 -----------------------------
     // One axon per (pre-neuron, destination core). The reference visits a
     // neuron's destination cores in std::set<Core*> (heap address) order; that
@@ -746,6 +773,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         }
     }
 
+    SFE_PHASE_MARK("4");
     // ---- emit neuron arrays ---------------------------------------------------
     out.neuron_class.resize(n_neurons);
     out.neuron_aux.assign(n_neurons, 0);
@@ -822,6 +850,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             if (cls.model == SFE_SOMA_LIF && (cls.flags & SFE_SOMA_LOG_U) != 0) out.u_probes.push_back(dev);
         }
 
+    SFE_PHASE_MARK("5");
     // ---- emit axons-out (per neuron, in sending order) -------------------------
     std::vector<uint32_t> core_axon_base(lcores.size());
     uint32_t axon_total = 0;
@@ -843,6 +872,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         }
     out.axon_out_begin[n_neurons] = static_cast<uint32_t>(out.axon_out_target.size());
 
+    SFE_PHASE_MARK("6");
     // ---- emit axons-in + synapses, per destination core -------------------------
     out.axons_in.resize(axon_total);
     out.axon_src.resize(axon_total);
@@ -858,6 +888,12 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         sfe_core_desc &cd = out.cores[c];
         cd.syn_begin = out.syn_weight.size();
         uint32_t max_delay = 0;
+        const size_t n_families = lc.cfg->pipeline_hw.size();
+        std::vector<CostKey> pair_key(n_families * n_families);
+        std::vector<uint8_t> pair_known(n_families * n_families, 0);
+        // dendrite delay tables of the core's units, by family/instance (looked up once per unit, not per synapse)
+        const UnitState *last_dend = nullptr;
+        UnitKey last_dend_key{-1, -1};
         for (size_t ai = 0; ai < lc.axons_in.size(); ++ai)
         {
             const LAxonIn &a = lc.axons_in[ai];
@@ -875,16 +911,24 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             {
                 const LConn &k = pre.out[a.syn[s].first];
                 const LNeuron &post = lc.neurons[k.post_in_core];
-                const PipelineUnitConfiguration &syn_cfg = lc.cfg->pipeline_hw[k.syn.family];
-                const PipelineUnitConfiguration &den_cfg = lc.cfg->pipeline_hw[post.dend.family];
-                CostKey key{};
-                key.v[0] = unit_double(syn_cfg, "energy_process_spike", "Synapse");
-                key.v[1] = unit_double(syn_cfg, "latency_process_spike", "Synapse");
-                if (cd.dend_in_msg != 0)
+                // default costs depend on the (synapse unit, dendrite unit) families only: looked up once per pair
+                const size_t pair = static_cast<size_t>(k.syn.family) * n_families + static_cast<size_t>(post.dend.family);
+                if (!pair_known[pair])
                 {
-                    key.v[2] = unit_double(den_cfg, "energy_update", "Dendrite");
-                    key.v[3] = unit_double(den_cfg, "latency_update", "Dendrite");
+                    const PipelineUnitConfiguration &syn_cfg = lc.cfg->pipeline_hw[k.syn.family];
+                    const PipelineUnitConfiguration &den_cfg = lc.cfg->pipeline_hw[post.dend.family];
+                    CostKey fresh{};
+                    fresh.v[0] = unit_double(syn_cfg, "energy_process_spike", "Synapse");
+                    fresh.v[1] = unit_double(syn_cfg, "latency_process_spike", "Synapse");
+                    if (cd.dend_in_msg != 0)
+                    {
+                        fresh.v[2] = unit_double(den_cfg, "energy_update", "Dendrite");
+                        fresh.v[3] = unit_double(den_cfg, "latency_update", "Dendrite");
+                    }
+                    pair_key[pair] = fresh;
+                    pair_known[pair] = 1;
                 }
+                const CostKey key = pair_key[pair];
                 if (s == 0) first = key;
                 else if (std::memcmp(first.v, key.v, sizeof(key.v)) != 0) uniform = false;
                 // per-message totals in the reference's summation order
@@ -892,7 +936,12 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 total.v[0] += key.v[0];
                 total.v[2] += key.v[2];
                 total.v[1] += (0.0 + key.v[1]) + key.v[3];
-                const UnitState &dend = lc.units[post.dend];
+                if (last_dend == nullptr || !(last_dend_key == post.dend))
+                {
+                    last_dend = &lc.units[post.dend];
+                    last_dend_key = post.dend;
+                }
+                const UnitState &dend = *last_dend;
                 uint32_t delay = 0;
                 if (dend.model == UnitModel::accumulator_with_delay && k.syn_addr < dend.delays.size())
                     delay = dend.delays[k.syn_addr];
@@ -935,6 +984,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
     }
     if (out.cost_classes.empty()) out.cost_classes.push_back(sfe_cost_class{});
     if (out.soma_classes.empty()) out.soma_classes.push_back(sfe_soma_class{});
+    SFE_PHASE_MARK("end");
     out.finalize_view(arch);
 }
 

@@ -175,27 +175,39 @@ class Sweep:
         os.makedirs(workdir, exist_ok=True)
         self._arch, self._net = (share._arch, share._net) if share is not None else ({}, {})
         self.chips = []
-        nets = []
+        # Descriptions first, in parallel: the C library drops the GIL while it parses, and parsing the conv net
+        # (about a second) is what a sweep spends most of its host time on.
+        arch_jobs, net_jobs = {}, {}
         for npc, mult in self.points:
             tiles = cores_needed(npc)
             akey = (mult, tiles)
-            if akey not in self._arch:
-                path = os.path.join(workdir, f"arch_m{len(self._arch)}.yaml")
+            if akey not in self._arch and akey not in arch_jobs:
+                path = os.path.join(workdir, f"arch_m{len(self._arch) + len(arch_jobs)}.yaml")
                 with open(path, "w") as f:
                     f.write(arch_yaml(mult, tiles=tiles))
-                self._arch[akey] = load_arch(path)
+                arch_jobs[akey] = path
             # a parsed network only keeps core ADDRESSES (Neuron::map_to_core, src/network.cpp:141-149), so one
             # parse serves every cost variant of the chip
-            nkey = npc
-            if nkey not in self._net:
+            if npc not in self._net and npc not in net_jobs:
                 path = os.path.join(workdir, f"snn_n{npc}.yaml")
                 if not os.path.exists(path):
                     with open(path, "w") as f:
                         f.write(snn_yaml(npc, seed)[0])
-                self._net[nkey] = load_net(path, self._arch[akey])
-            chip = SpikingChip(self._arch[akey], device=device)
+                net_jobs[npc] = (path, akey)
+        for akey, path in arch_jobs.items():
+            self._arch[akey] = load_arch(path)
+        if net_jobs:
+            from concurrent.futures import ThreadPoolExecutor
+            workers = max(1, min(len(net_jobs), host_threads or (os.cpu_count() or 8)))
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                parsed = pool.map(lambda job: load_net(job[0], self._arch[job[1]]), net_jobs.values())
+                for npc, net in zip(net_jobs, parsed):
+                    self._net[npc] = net
+        nets = []
+        for npc, mult in self.points:
+            chip = SpikingChip(self._arch[(mult, cores_needed(npc))], device=device)
             self.chips.append(chip)
-            nets.append(self._net[nkey])
+            nets.append(self._net[npc])
         n = len(self.chips)
         chip_arr = (C.c_void_p * n)(*[c._h for c in self.chips])
         net_arr = (C.c_void_p * n)(*[x._h for x in nets])
