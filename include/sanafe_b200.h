@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 3
+#define SFE_ABI_VERSION 4
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -72,7 +72,9 @@ enum
 enum
 {
     SFE_DEND_ACCUMULATOR = 0,      /* src/models.cpp:71-94  */
-    SFE_DEND_ACCUMULATOR_DELAY = 1 /* src/models.cpp:96-131 */
+    SFE_DEND_ACCUMULATOR_DELAY = 1,/* src/models.cpp:96-131 */
+    SFE_DEND_TAPS = 2              /* "taps" MultiTapModel1D  src/models.cpp:167-259 (lowered and run by the CPU
+                                    * restatement; the device engine refuses it for now) */
 };
 /* how one core's message phase accumulates synaptic charge */
 enum
@@ -163,6 +165,7 @@ typedef struct sfe_axon_in
 /* synapse meta word: post-neuron offset within core | delay << 16 */
 #define SFE_SYN_POST(m) ((m) & 0xffffu)
 #define SFE_SYN_DELAY(m) (((m) >> 16) & 0x7u)
+#define SFE_SYN_TAP(m) ((m) >> 16) /* "taps" dendrites: the field holds the tap index instead of a delay */
 
 typedef struct sfe_input_desc /* "input" soma: state is per hardware UNIT (src/models.cpp:832-903) */
 {
@@ -184,6 +187,15 @@ typedef struct sfe_noise_desc
     uint32_t off, len;
     uint32_t share_count, share_rank;
 } sfe_noise_desc;
+
+/* "taps" dendrite (MultiTapModel1D, src/models.cpp:167-259): a 1-D RC line of n_taps compartments, ONE neuron per
+ * unit. taps_values[const_off .. +n_taps) are the time constants, the next n_taps-1 values the space constants.
+ * A synapse names its tap in the delay field of syn_meta. */
+typedef struct sfe_taps_desc
+{
+    uint32_t n_taps;
+    uint32_t const_off;
+} sfe_taps_desc;
 
 typedef struct sfe_hh_init /* Hodgkin-Huxley plugin initial state, one neuron per unit */
 {
@@ -241,6 +253,12 @@ typedef struct sfe_tables
      * log_u, whose input current `u` is traced each step, in trace order */
     uint32_t n_u_probes;
     const uint32_t *u_probes;
+
+    /* "taps" dendrites: per neuron the index of its sfe_taps_desc (0xFFFFFFFF: none); NULL when n_taps_units == 0 */
+    const uint32_t *neuron_taps;
+    const sfe_taps_desc *taps;
+    const double *taps_values;
+    uint32_t n_taps_units, n_taps_values;
 } sfe_tables;
 
 /* one record per simulated timestep (src/timestep.hpp:21-42) */

@@ -57,6 +57,10 @@ typedef struct sfe_oracle
     /* Poisson inputs: one MT19937 per input unit (own restatement, below), or an external overlay */
     struct mt19937 *poisson_gen; /* [n_poisson_units], indexed by sfe_input_desc.unit */
     uint32_t n_poisson_units;
+    /* "taps" dendrites (MultiTapModel1D): voltages of every line, a scratch line, steps simulated per line */
+    double *tap_v, *tap_next;
+    uint32_t *tap_off;           /* [n_taps_units] offset of the unit's line in tap_v */
+    int64_t *tap_steps;          /* [n_taps_units] timesteps_simulated */
     const uint8_t *overlay;      /* caller-owned [overlay_steps][overlay_cols], NULL: draw here */
     int64_t overlay_step0, overlay_steps;
     uint32_t overlay_cols;
@@ -152,6 +156,19 @@ sfe_oracle *sfe_oracle_create(const sfe_tables *t)
         o->bias[i] = t->neuron_bias[i];
         o->v[i] = t->neuron_potential0[i];
     }
+    {
+        size_t total = 0, widest = 1;
+        o->tap_off = (uint32_t *) zalloc(t->n_taps_units, sizeof(uint32_t));
+        o->tap_steps = (int64_t *) zalloc(t->n_taps_units, sizeof(int64_t));
+        for (uint32_t k = 0; k < t->n_taps_units; ++k)
+        {
+            o->tap_off[k] = (uint32_t) total;
+            total += t->taps[k].n_taps;
+            if (t->taps[k].n_taps > widest) widest = t->taps[k].n_taps;
+        }
+        o->tap_v = (double *) zalloc(total, sizeof(double));
+        o->tap_next = (double *) zalloc(widest, sizeof(double));
+    }
     for (uint32_t k = 0; k < t->n_inputs; ++k)
         if (t->inputs[k].poisson > 0.0 && t->inputs[k].unit + 1 > o->n_poisson_units) o->n_poisson_units = t->inputs[k].unit + 1;
     o->poisson_gen = (struct mt19937 *) zalloc(o->n_poisson_units, sizeof(struct mt19937));
@@ -175,6 +192,7 @@ void sfe_oracle_destroy(sfe_oracle *o)
     free(o->tile_e); free(o->tile_w); free(o->tile_n); free(o->tile_s); free(o->core_msgs);
     free(o->core_syn_e); free(o->core_den_e); free(o->core_soma_e); free(o->core_axout_e);
     free(o->poisson_gen);
+    free(o->tap_v); free(o->tap_next); free(o->tap_off); free(o->tap_steps);
     free(o);
 }
 
@@ -208,6 +226,11 @@ void sfe_oracle_reset(sfe_oracle *o)
     for (size_t i = 0; i < o->t->n_hh; ++i)
     {
         o->hh_v[i] = o->hh_m[i] = o->hh_n[i] = o->hh_h[i] = 0.0; /* plugins/hodgkin_huxley.cpp:71-87 */
+    }
+    if (o->t->n_taps_units != 0) /* MultiTapModel1D::reset  src/models.cpp:340-348: voltages only */
+    {
+        const sfe_taps_desc *last = &o->t->taps[o->t->n_taps_units - 1];
+        memset(o->tap_v, 0, ((size_t) o->tap_off[o->t->n_taps_units - 1] + last->n_taps) * sizeof(double));
     }
 }
 
@@ -347,6 +370,40 @@ static int hh_update(sfe_oracle *o, size_t k)
     h = ph + (h - ph) * exp(-1 * dt / tau_h);
     o->hh_v[k] = V; o->hh_m[k] = m; o->hh_n[k] = n; o->hh_h[k] = h;
     return ((prev_V < 25) && (V > 25)) ? SFE_STATUS_FIRED : SFE_STATUS_UPDATED;
+}
+
+/* MultiTapModel1D::update  src/models.cpp:237-257 with calculate_next_state (:167-202) and input_current
+ * (:215-235): catch the line up to timestep T (one RC step per elapsed timestep), add the current to the
+ * synapse's tap, return the voltage of tap 0. */
+static double taps_update(sfe_oracle *o, uint32_t unit, int64_t T, double current, uint32_t tap)
+{
+    const sfe_taps_desc *d = &o->t->taps[unit];
+    const size_t n = d->n_taps;
+    double *v = o->tap_v + o->tap_off[unit], *next = o->tap_next;
+    const double *tc = o->t->taps_values + d->const_off, *sc = tc + n;
+    while (o->tap_steps[unit] < T)
+    {
+        ++o->tap_steps[unit];
+        for (size_t k = 0; k < n; ++k) next[k] = v[k] * tc[k];
+        for (size_t src = 0; src < n; ++src)
+        {
+            if (src > 0)
+            {
+                const double proximal = v[src] * sc[src - 1];
+                next[src - 1] += proximal;
+                next[src] -= proximal;
+            }
+            if (src < n - 1)
+            {
+                const double distal = v[src] * sc[src];
+                next[src + 1] += distal;
+                next[src] -= distal;
+            }
+        }
+        for (size_t k = 0; k < n; ++k) v[k] = next[k];
+    }
+    v[tap] += current;
+    return v[0];
 }
 
 static double potential_of(const sfe_oracle *o, size_t i)
@@ -501,7 +558,13 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
                 if (core->dend_in_msg)
                 {
                     const sfe_soma_class *pc = &t->soma_classes[t->neuron_class[post]];
-                    if (pc->dend_model == SFE_DEND_ACCUMULATOR)
+                    if (pc->dend_model == SFE_DEND_TAPS)
+                    {
+                        /* buffer before the soma: the value the last event of the step returns is what the soma reads */
+                        o->buf[post] = taps_update(o, t->neuron_taps[post], T, weight, SFE_SYN_TAP(m));
+                        o->buf_has[post] = 1;
+                    }
+                    else if (pc->dend_model == SFE_DEND_ACCUMULATOR)
                     {
                         if (o->acc_step[post] < T) { o->acc[post] = 0.0; o->acc_step[post] = T; }
                         o->acc[post] = o->acc[post] + weight;

@@ -2053,6 +2053,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     }
     if (e->upload(&e->t.inputs, tb->inputs, tb->n_inputs) != 0) return -1;
     if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
+    if (tb->n_taps_units != 0)
+    {
+        sfe::set_last_error("'taps' dendrites (MultiTapModel1D) are lowered but not implemented on the device yet: they need "
+                            "one in-order accumulator per tap in the message phase");
+        return -1;
+    }
     e->n_poisson_cols = tb->n_poisson_cols;
     for (uint32_t k = 0; k < tb->n_inputs; ++k)
         if (tb->inputs[k].poisson > 0.0 && tb->inputs[k].poisson_col >= tb->n_poisson_cols)

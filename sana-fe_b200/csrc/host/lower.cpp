@@ -29,7 +29,8 @@ enum class UnitModel
     lif,
     truenorth,
     input,
-    hodgkin_huxley
+    hodgkin_huxley,
+    taps
 };
 
 struct UnitKey
@@ -54,6 +55,10 @@ struct UnitState // one used hardware unit instance of one core
     double rate{0.0};
     double poisson{0.0};
     double hh_m{0.0}, hh_n{0.0}, hh_h{0.0}, hh_i{0.0};
+    // "taps" (MultiTapModel1D): vector sizes evolve exactly as set_attribute_neuron leaves them (src/models.cpp:259-318)
+    size_t n_taps{1};
+    std::vector<double> time_constants{0.0}, space_constants{};
+    std::vector<int> synapse_to_tap; // by synapse address (set_attribute_edge "tap", src/models.cpp:320-332)
     uint32_t noise_off{0}, noise_len{0}; // LIF unit with a noise file: its entries in HostTables::noise_values
     bool noise_loaded{false};
     std::vector<uint32_t> sharing; // device-order list of neurons mapped to this unit (filled later)
@@ -116,8 +121,7 @@ UnitModel parse_model(const PipelineUnitConfiguration &u)
     if (m == "leaky_integrate_fire") return UnitModel::lif;
     if (m == "truenorth") return UnitModel::truenorth;
     if (m == "input") return UnitModel::input;
-    if (m == "taps")
-        throw std::runtime_error("Pipeline model 'taps' is not implemented by the B200 engine yet");
+    if (m == "taps") return UnitModel::taps;
     throw std::invalid_argument("Pipeline model not supported (" + m + ")\n"); // src/models.cpp:964-966
 }
 
@@ -256,6 +260,42 @@ std::vector<double> read_noise_file(const std::string &path, const int noise_bit
     }
     if (values.empty()) throw std::runtime_error("Couldn't read noise entry from file"); // src/models.cpp:620-624
     return values;
+}
+
+// MultiTapModel1D::set_attribute_neuron  src/models.cpp:259-318, branch for branch (the vectors' sizes depend on
+// the order in which the attributes arrive, which is the std::map order of the attribute names)
+void set_taps_attribute(UnitState &u, const std::string &key, const Attr &a)
+{
+    auto doubles = [](const Attr &list) {
+        std::vector<double> v;
+        for (const Attr &e : list.as_list()) v.push_back(e.as_double());
+        return v;
+    };
+    if (key == "taps")
+    {
+        const size_t n = static_cast<size_t>(a.as_int());
+        if (n == 0) throw std::invalid_argument("Number of taps must be > 0\n");
+        u.n_taps = n;
+        u.time_constants.resize(n);
+        u.space_constants.resize(n - 1);
+    }
+    else if (key == "time_constants")
+    {
+        u.time_constants = doubles(a);
+        if (u.time_constants.size() < u.n_taps)
+            throw std::invalid_argument("Expected " + std::to_string(u.n_taps) + " but received " +
+                    std::to_string(u.time_constants.size()) + "time constants.");
+        if (u.time_constants.size() > u.n_taps) u.space_constants.resize(u.n_taps - 1);
+    }
+    else if (key == "space_constants")
+    {
+        const size_t previous = u.time_constants.size();
+        u.space_constants = doubles(a);
+        if (u.space_constants.size() < u.n_taps - 1)
+            throw std::invalid_argument("Expected " + std::to_string(u.n_taps - 1) + " but received " +
+                    std::to_string(previous) + "time constants.");
+        if (u.space_constants.size() > u.n_taps - 1) u.time_constants.resize(u.n_taps);
+    }
 }
 
 // LoihiLifModel / TrueNorthModel / InputModel / HodgkinHuxley ::set_attribute_neuron
@@ -489,6 +529,11 @@ void HostTables::finalize_view(const Architecture &arch)
     v.n_noise_values = noise_values.size();
     v.u_probes = u_probes.data();
     v.n_u_probes = static_cast<uint32_t>(u_probes.size());
+    v.neuron_taps = taps.empty() ? nullptr : neuron_taps.data();
+    v.taps = taps.data();
+    v.taps_values = taps_values.data();
+    v.n_taps_units = static_cast<uint32_t>(taps.size());
+    v.n_taps_values = static_cast<uint32_t>(taps_values.size());
     v.n_hh = static_cast<uint32_t>(hh.size());
     v.n_probes = static_cast<uint32_t>(probes.size());
     v.n_axons_out = axon_out_target.size();
@@ -605,8 +650,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         ln.soma_addr = soma.neuron_count++;
         ln.dend_unit = &lc.units[ln.dend]; // (looked up again: inserting the soma unit cannot move it, but `dend` may alias)
         ln.soma_unit = &soma;
-        if (dend.model != UnitModel::accumulator && dend.model != UnitModel::accumulator_with_delay)
+        if (dend.model != UnitModel::accumulator && dend.model != UnitModel::accumulator_with_delay &&
+                dend.model != UnitModel::taps)
             throw std::runtime_error("Unit '" + dend_cfg.name + "' is not a dendrite model");
+        if (dend.model == UnitModel::taps && cfg.pipeline.buffer_position != buffer_before_soma_unit)
+            throw std::runtime_error("a 'taps' dendrite is only supported with the buffer before the soma unit");
         // capacity of the built-in models' state tables (src/models.hpp:29,283)
         if (ln.dend_addr >= kLifMaxCompartments)
             throw std::out_of_range("dendrite unit '" + dend_cfg.name + "' holds at most 1024 neurons");
@@ -635,8 +683,9 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             }
             ln.cls.flags |= SFE_SOMA_NOISE;
         }
-        ln.cls.dend_model =
-                dend.model == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR : SFE_DEND_ACCUMULATOR_DELAY;
+        ln.cls.dend_model = dend.model == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR
+                : dend.model == UnitModel::taps                  ? SFE_DEND_TAPS
+                                                                 : SFE_DEND_ACCUMULATOR_DELAY;
         ln.cls.dend_in_neuron = cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit ? 1 : 0;
         if (ln.cls.dend_in_neuron != 0)
         {
@@ -649,7 +698,8 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             if (is_reserved_neuron_attribute(key))
                 throw std::invalid_argument("Reserved neuron attribute '" + key +
                         "' cannot be used as a model attribute. Pass it as a direct argument instead (if supported).");
-            // dendrite models take no per-neuron attributes (src/models.hpp:80,133)
+            // the accumulators take no per-neuron attributes (src/models.hpp:80,133); "taps" does
+            if (a.forward_to_dendrite && dend.model == UnitModel::taps) set_taps_attribute(dend, key, a);
             if (a.forward_to_soma) set_soma_attribute(ln, soma, soma.model, key, a);
         }
         where[p.group][n.offset] = {static_cast<uint32_t>(n.core_address->id), static_cast<uint32_t>(lc.neurons.size())};
@@ -720,6 +770,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 for (const auto &[key, a] : con.synapse_attributes)
                 {
                     if (a.forward_to_synapse && (key == "w" || key == "weight")) lcn.weight = a.as_double();
+                    if (a.forward_to_dendrite && dend.model == UnitModel::taps && key == "tap")
+                    {
+                        if (dend.synapse_to_tap.size() <= lcn.syn_addr) dend.synapse_to_tap.resize(lcn.syn_addr + 1, 0);
+                        dend.synapse_to_tap[lcn.syn_addr] = a.as_int();
+                    }
                     if (a.forward_to_dendrite && dend.model == UnitModel::accumulator_with_delay)
                     {
                         // the dendrite's delay table is addressed by the SYNAPSE address
@@ -836,6 +891,25 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             }
         }
     }
+    // "taps" dendrites keep ONE state per hardware unit: one neuron per unit
+    for (size_t c = 0; c < lcores.size(); ++c)
+        for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
+        {
+            const LNeuron &ln = lcores[c].neurons[i];
+            const UnitState &dend = *ln.dend_unit;
+            if (dend.model != UnitModel::taps) continue;
+            if (dend.neuron_count != 1)
+                throw std::runtime_error("a 'taps' dendrite keeps one line of state per hardware unit "
+                                         "(src/models.hpp:186-193); map one neuron per unit");
+            if (out.neuron_taps.empty()) out.neuron_taps.assign(n_neurons, 0xFFFFFFFFu);
+            sfe_taps_desc d{};
+            d.n_taps = static_cast<uint32_t>(dend.n_taps);
+            d.const_off = static_cast<uint32_t>(out.taps_values.size());
+            for (size_t k = 0; k < dend.n_taps; ++k) out.taps_values.push_back(dend.time_constants.at(k));
+            for (size_t k = 0; k + 1 < dend.n_taps; ++k) out.taps_values.push_back(dend.space_constants.at(k));
+            out.neuron_taps[out.cores[c].neuron_begin + i] = static_cast<uint32_t>(out.taps.size());
+            out.taps.push_back(d);
+        }
     // potential probes in trace order: lexicographic group, offset (src/chip.cpp:1632-1662)
     for (size_t gi = 0; gi < groups.size(); ++gi)
         for (const Neuron &n : groups[gi]->neurons)
@@ -888,6 +962,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         sfe_core_desc &cd = out.cores[c];
         cd.syn_begin = out.syn_weight.size();
         uint32_t max_delay = 0;
+        bool core_has_taps = false;
         const size_t n_families = lc.cfg->pipeline_hw.size();
         std::vector<CostKey> pair_key(n_families * n_families);
         std::vector<uint8_t> pair_known(n_families * n_families, 0);
@@ -946,6 +1021,16 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 if (dend.model == UnitModel::accumulator_with_delay && k.syn_addr < dend.delays.size())
                     delay = dend.delays[k.syn_addr];
                 max_delay = std::max(max_delay, delay);
+                if (dend.model == UnitModel::taps)
+                {
+                    // MultiTapModel1D::input_current  src/models.cpp:215-235: tap of the synapse address, default 0;
+                    // a tap outside the line throws when the first current arrives — refused here
+                    const int tap = k.syn_addr < dend.synapse_to_tap.size() ? dend.synapse_to_tap[k.syn_addr] : 0;
+                    if (tap < 0 || static_cast<size_t>(tap) >= dend.n_taps)
+                        throw std::logic_error("Tap should be >= 0 and less than taps.\n");
+                    delay = static_cast<uint32_t>(tap); // rides in the delay field of syn_meta
+                    core_has_taps = true;
+                }
                 out.syn_weight.push_back(k.weight);
                 out.syn_meta.push_back(k.post_in_core | (delay << 16));
             }
@@ -960,7 +1045,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         const int shift = exact_shift(out.syn_weight, cd.syn_begin, cd.syn_begin + cd.syn_count);
         cd.acc_mode = SFE_ACC_ORDERED;
         cd.weight_shift = 0;
-        if (shift >= 0)
+        if (shift >= 0 && !core_has_taps) // a tap line adds onto evolving fp64 state: in-order adds only
         {
             std::vector<double> sum_abs(lc.neurons.size(), 0.0);
             std::vector<uint64_t> fan_in(lc.neurons.size(), 0);

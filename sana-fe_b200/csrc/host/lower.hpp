@@ -40,6 +40,9 @@ struct HostTables
     std::vector<sfe_noise_desc> noise;  // LIF file noise: one record per neuron of a unit with a stream
     std::vector<double> noise_values;
     std::vector<uint32_t> u_probes;     // LIF neurons with log_u, in trace order
+    std::vector<uint32_t> neuron_taps;  // "taps" dendrites (empty when the network has none)
+    std::vector<sfe_taps_desc> taps;
+    std::vector<double> taps_values;
     uint32_t input_seed_base{0}; // "input" units created in this process before this chip (set by the chip)
     uint32_t n_poisson_cols{0};
     sfe_tables view{};

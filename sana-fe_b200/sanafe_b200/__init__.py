@@ -76,6 +76,10 @@ class NoiseDesc(C.Structure):
     _fields_ = [("off", C.c_uint32), ("len", C.c_uint32), ("share_count", C.c_uint32), ("share_rank", C.c_uint32)]
 
 
+class TapsDesc(C.Structure):
+    _fields_ = [("n_taps", C.c_uint32), ("const_off", C.c_uint32)]
+
+
 class HHInit(C.Structure):
     _fields_ = [("m", C.c_double), ("n", C.c_double), ("h", C.c_double), ("current", C.c_double)]
 
@@ -101,7 +105,9 @@ class Tables(C.Structure):
                 ("synth", C.POINTER(SynthSpec)), ("input_seed_base", C.c_uint32), ("n_poisson_cols", C.c_uint32),
                 ("noise", C.POINTER(NoiseDesc)), ("noise_values", C.POINTER(C.c_double)),
                 ("n_noise_values", C.c_uint64), ("n_noise", C.c_uint32), ("n_u_probes", C.c_uint32),
-                ("u_probes", C.POINTER(C.c_uint32))]
+                ("u_probes", C.POINTER(C.c_uint32)), ("neuron_taps", C.POINTER(C.c_uint32)),
+                ("taps", C.POINTER(TapsDesc)), ("taps_values", C.POINTER(C.c_double)),
+                ("n_taps_units", C.c_uint32), ("n_taps_values", C.c_uint32)]
 
 
 class StepRecord(C.Structure):

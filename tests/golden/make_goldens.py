@@ -65,6 +65,8 @@ CASES = {
     # Poisson inputs: libstdc++ mt19937 streams seeded by the InputModel construction order
     # LIF file noise stream + model-defined traces (log_u)
     "noise": dict(arch=f"{SRC}/noise_arch.yaml", net=f"{SRC}/noise_snn.yaml", steps=150),
+    # "taps" dendrites (MultiTapModel1D): 1-D RC lines, synapses addressed to taps
+    "taps": dict(arch=f"{SRC}/taps_arch.yaml", net=f"{SRC}/taps_snn.yaml", steps=200),
     "poisson": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/poisson_snn.yaml", steps=300),
 }
 

@@ -151,6 +151,42 @@ def check_input(tmp_path, device, runner):
             arch=open(rig.demo_arch()).read().replace("model: accumulator", "model: invalid_model"))
 
 
+def taps_arch():
+    return open(rig.demo_arch()).read().replace("model: accumulator", "model: taps")
+
+
+def check_taps(tmp_path, device, runner):
+    """test_multitap.cpp — CPU restatement only: the device engine refuses `taps` dendrites for now."""
+    line = "dendrite: {taps: 2, time_constants: [1.0, 1.0], space_constants: [0.0]}"
+    # InputCurrentAdds (:86-96): the current lands on tap 0 and is what the soma receives
+    st, v = lif(tmp_path, device, runner, {"threshold": 100.0, line.split(":")[0]: line.split(": ", 1)[1]}, [1.5], arch=taps_arch())
+    assert v[1] == 1.5
+    # CalculateNextStateChangesVoltages (:128-139): time constant 0.5 halves the line per step (a zero-weight event
+    # at the next step makes the lazily updated line catch up and report tap 0)
+    half = {"threshold": 100.0, "leak_decay": 0.0, "dendrite": "{taps: 2, time_constants: [0.5, 0.5], space_constants: [0.0]}"}
+    st, v = lif(tmp_path, device, runner, half, [2.0, 0.0], arch=taps_arch())
+    assert v[1] == 2.0 and v[2] == 1.0 and v[2] < v[1]
+    # InputCurrentToMappedTap (:97-107): a current addressed to tap 1 reaches tap 0 only through the space constant
+    net = rig.lif_network({"threshold": 100.0, "leak_decay": 0.0,
+                           "dendrite": "{taps: 2, time_constants: [1.0, 1.0], space_constants: [0.25]}"}, [2.0, 0.0])
+    net = net.replace("{weight: 2.0}", "{weight: 2.0, tap: 1}")
+    chip = rig.load(tmp_path, taps_arch(), net, device)
+    st, v = rig.run(chip, 3, runner)
+    assert v[1] == 0.0 and v[2] == 0.5  # step 2: tap 1 holds 2.0; step 3: a quarter of it has moved to tap 0
+    # TapsZeroThrows (:37-43), TimeConstantsTooFewThrows (:152-158), InvalidTapThrows (:108-118)
+    with pytest.raises(sfe.SanafeError, match="Number of taps must be > 0"):
+        lif(tmp_path, device, runner, {"dendrite": "{taps: 0}"}, [1.0], arch=taps_arch())
+    with pytest.raises(sfe.SanafeError, match="time constants"):
+        lif(tmp_path, device, runner, {"dendrite": "{taps: 3, time_constants: [0.9, 0.8]}"}, [1.0], arch=taps_arch())
+    bad = rig.lif_network({"dendrite": "{taps: 1}"}, [1.0]).replace("{weight: 1.0}", "{weight: 1.0, tap: 5}")
+    with pytest.raises(sfe.SanafeError, match="Tap should be >= 0 and less than taps"):
+        rig.load(tmp_path, taps_arch(), bad, device)
+    # TimeConstantsResizeLargerVector / SpaceConstantsResizeLargerVector (:62-85): longer lists are accepted
+    st, v = lif(tmp_path, device, runner, {"threshold": 100.0, "dendrite": "{taps: 2, time_constants: [0.5, 0.5, 0.5], space_constants: [0.4, 0.4, 0.4]}"},
+                [1.0], arch=taps_arch())
+    assert v[1] == 1.0
+
+
 def check_all(tmp_path, device, runner):
     check_lif(tmp_path, device, runner)
     check_truenorth(tmp_path, device, runner)

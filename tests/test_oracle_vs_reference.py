@@ -4,10 +4,10 @@ load-time lowering, which it shares — against outputs of the reference itself
 engine). Runs without a GPU."""
 import pytest
 
-from helpers import GOLDEN_CASES, NEW_GOLDEN_CASES, Oracle, check_against_golden, golden, load_chip
+from helpers import GOLDEN_CASES, NEW_GOLDEN_CASES, ORACLE_ONLY_CASES, Oracle, check_against_golden, golden, load_chip
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES + NEW_GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + NEW_GOLDEN_CASES + ORACLE_ONLY_CASES)
 def test_restatement_matches_reference(name):
     chip = load_chip(name, device=-1)
     g = golden(name)

@@ -22,3 +22,7 @@ def test_synapse_and_dendrite_vectors(tmp_path):
 
 def test_input_vectors(tmp_path):
     vectors.check_input(tmp_path, -1, poisson_aware_oracle)
+
+
+def test_multitap_vectors(tmp_path):
+    vectors.check_taps(tmp_path, -1, poisson_aware_oracle)

@@ -144,3 +144,10 @@ def test_ctrl_c_interrupts_a_long_sim():
     assert time.time() - t0 < 60.0
     res = chip.sim(10, timing_model="simple")
     assert res["timesteps_executed"] == 10 and res["timestep_start"] > 101
+
+
+def test_taps_dendrites_are_refused_loudly():
+    """`taps` dendrites are lowered and pinned on the CPU (restatement vs the reference's golden) but have no device
+    implementation yet: loading one onto a device must fail with a message, never run something else."""
+    with pytest.raises(sfe.SanafeError, match="taps"):
+        load_chip("taps", device=0)
