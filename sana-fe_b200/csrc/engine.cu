@@ -94,6 +94,24 @@ struct StatsM // written by fanout_kernel, one per work item
 };
 
 struct SomaSegment;
+// "taps" dendrites (MultiTapModel1D, src/models.cpp:167-259), EXPERIMENTAL device path (SFE_DEVICE_TAPS=1): the
+// currents of a tap line are added onto evolving fp64 state in arrival order, so each line is replayed by one
+// thread of a small kernel of its own (taps_kernel) from the step's fired raster; the message phase still does
+// the accounting of those events and the neuron phase reads the line's output instead of its accumulator cell.
+struct TapsUnit
+{
+    uint32_t n_taps, const_off; // time constants [n_taps] then space constants [n_taps-1] in taps_values
+    uint32_t state_off;         // the line's voltages in DevState::tap_v / tap_next
+    uint32_t syn_begin, syn_count; // its incoming synapses in arrival order (taps_syn)
+    uint32_t pad;
+};
+struct TapsSyn
+{
+    double weight;
+    uint32_t src_bit; // raster bit of the source neuron
+    uint32_t tap;
+};
+
 struct DevTables
 {
     const CoreDev *cores;
@@ -131,6 +149,11 @@ struct DevTables
     // syn_w / syn_meta; a third of their bytes per synaptic event.
     const uint32_t *syn_q4;
     const uint32_t *probes;
+    const TapsUnit *taps_units;       // "taps" dendrites (experimental)
+    const TapsSyn *taps_syn;
+    const double *taps_values;
+    const uint32_t *neuron_taps;      // per neuron: its taps unit or 0xFFFFFFFF
+    uint32_t n_taps_units, pad_taps;
     const uint32_t *u_probes;         // LIF neurons whose input current u is traced (log_u)
     const sfe_noise_desc *noise;      // LIF file noise: per neuron of a unit with a stream
     const double *noise_values;
@@ -173,6 +196,10 @@ struct DevState
     uint32_t *din32;       // PACKED32: packed | DUAL32: sum
     uint32_t *dcnt32;      // DUAL32: count | ORDERED: has flag
     double *din64;         // ORDERED: value
+    double *tap_v, *tap_next; // "taps": voltages of every line, scratch of the same shape
+    long long *tap_steps;     // [n_taps_units] timesteps the line has been advanced to
+    double *tap_buf;          // [n_taps_units] tap 0 after the last event of the step
+    uint32_t *tap_has;        // [n_taps_units] the soma has an input waiting
     double *hh;            // [5][n_hh]: V, m, n, h, I
     uint32_t n_hh;
     StatsN *stats_n;
@@ -810,7 +837,21 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             // ---- dendrite output for this step ------------------------------
             bool has_in = false;
             double in = 0.0;
-            if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR)
+            bool tap_line = false;
+            if constexpr (kExotic) tap_line = c.dend_model == SFE_DEND_TAPS;
+            if (tap_line)
+            {
+                // the line's tap 0 after the last event of the previous step (taps_kernel); the accumulator cell
+                // the message phase filled for this neuron is ignored
+                const uint32_t unit = t.neuron_taps[i];
+                if (s.tap_has[unit] != 0u)
+                {
+                    has_in = true;
+                    in = s.tap_buf[unit];
+                    s.tap_has[unit] = 0u;
+                }
+            }
+            else if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR)
             {
                 // buffer inside a plain accumulator: the charge is zeroed before it is
                 // read (src/models.cpp:78-82)
@@ -980,6 +1021,57 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
     if (model == SFE_SOMA_HH) v = s.hh[t.neuron_aux[i]];
     else if (model == SFE_SOMA_INPUT) v = 0.0; // PipelineUnit::get_potential default
     s.probe_out[p] = v;
+}
+
+// One thread per tap line: MultiTapModel1D::update (src/models.cpp:237-257) for every event of the step that
+// targets the line, in arrival order (the list is sorted that way at load): catch the line up to this timestep
+// (calculate_next_state, :167-202, one RC step per elapsed timestep), add the current to the synapse's tap
+// (input_current, :215-235); the value of tap 0 after the last event is what the soma reads next step.
+__global__ void taps_kernel(const DevTables t, const DevState s)
+{
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= t.n_taps_units) return;
+    const TapsUnit d = t.taps_units[u];
+    const long long T = s.steps_done + 1;
+    const uint32_t n = d.n_taps;
+    double *v = s.tap_v + d.state_off, *next = s.tap_next + d.state_off;
+    const double *tc = t.taps_values + d.const_off, *sc = tc + n;
+    long long steps = s.tap_steps[u];
+    bool any = false;
+    for (uint32_t e = d.syn_begin; e < d.syn_begin + d.syn_count; ++e)
+    {
+        const TapsSyn y = t.taps_syn[e];
+        if (((s.fired_global[y.src_bit >> 5] >> (y.src_bit & 31u)) & 1u) == 0u) continue;
+        while (steps < T)
+        {
+            ++steps;
+            for (uint32_t k = 0; k < n; ++k) next[k] = v[k] * tc[k];
+            for (uint32_t src = 0; src < n; ++src)
+            {
+                if (src > 0)
+                {
+                    const double proximal = v[src] * sc[src - 1];
+                    next[src - 1] = next[src - 1] + proximal;
+                    next[src] = next[src] - proximal;
+                }
+                if (src + 1 < n)
+                {
+                    const double distal = v[src] * sc[src];
+                    next[src + 1] = next[src + 1] + distal;
+                    next[src] = next[src] - distal;
+                }
+            }
+            for (uint32_t k = 0; k < n; ++k) v[k] = next[k];
+        }
+        v[y.tap] = v[y.tap] + y.weight;
+        any = true;
+    }
+    s.tap_steps[u] = steps;
+    if (any)
+    {
+        s.tap_buf[u] = v[0];
+        s.tap_has[u] = 1u;
+    }
 }
 
 // Multi-GPU: a rank sees the spikes of the whole chip as a fired-bit raster (SURVEY 8e:
@@ -1863,6 +1955,8 @@ struct sfe_engine
     bool ordered_any{false}, dual_any{false};
     // cooperative cancellation of a long sfe_engine_run (Ctrl-C in the Python binding): checked between batches
     std::atomic<bool> stop_requested{false};
+    uint32_t n_taps_units{0}; // "taps" dendrites (experimental device path)
+    size_t tap_cells{0};
     // Poisson overlay (host-drawn, see poisson.cpp)
     uint32_t n_poisson_cols{0};
     uint8_t *d_overlay{nullptr};
@@ -2055,9 +2149,73 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
     if (tb->n_taps_units != 0)
     {
-        sfe::set_last_error("'taps' dendrites (MultiTapModel1D) are lowered but not implemented on the device yet: they need "
-                            "one in-order accumulator per tap in the message phase");
-        return -1;
+        const char *opt_in = std::getenv("SFE_DEVICE_TAPS");
+        if (opt_in == nullptr || std::atoi(opt_in) == 0)
+        {
+            sfe::set_last_error("'taps' dendrites (MultiTapModel1D) are lowered, but their device path has not been verified on "
+                                "hardware yet and is off by default (SFE_DEVICE_TAPS=1 enables it)");
+            return -1;
+        }
+        if (e->world > 1 || tb->syn_weight == nullptr || tb->syn_meta == nullptr)
+        {
+            sfe::set_last_error("'taps' dendrites need an unpartitioned chip with host synapse tables");
+            return -1;
+        }
+        // raster bit of every neuron, and every line's incoming synapses in arrival order (axons-in of its core
+        // in order, synapses of an axon in order: exactly the order the message phase of the reference visits)
+        std::vector<uint32_t> raster_bit(tb->n_neurons);
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+            for (uint32_t k = 0; k < tb->cores[c].neuron_count; ++k)
+                raster_bit[tb->cores[c].neuron_begin + k] = e->fired_word_begin[c] * 32u + k;
+        std::vector<std::vector<TapsSyn>> incoming(tb->n_taps_units);
+        for (uint32_t c = 0; c < tb->n_cores; ++c)
+        {
+            const sfe_core_desc &cd = tb->cores[c];
+            for (uint32_t a = 0; a < cd.axon_in_count; ++a)
+            {
+                const sfe_axon_in &ax = tb->axons_in[cd.axon_in_begin + a];
+                const uint32_t src = tb->axon_src[cd.axon_in_begin + a];
+                for (uint32_t j = 0; j < ax.syn_count; ++j)
+                {
+                    const uint64_t at = cd.syn_begin + ax.syn_off + j;
+                    const uint32_t post = cd.neuron_begin + SFE_SYN_POST(tb->syn_meta[at]);
+                    const uint32_t unit = tb->neuron_taps[post];
+                    if (unit == 0xFFFFFFFFu) continue;
+                    incoming[unit].push_back({tb->syn_weight[at], raster_bit[src], SFE_SYN_TAP(tb->syn_meta[at])});
+                }
+            }
+        }
+        std::vector<TapsUnit> units(tb->n_taps_units);
+        std::vector<TapsSyn> flat;
+        uint32_t cells = 0;
+        for (uint32_t u = 0; u < tb->n_taps_units; ++u)
+        {
+            units[u] = {tb->taps[u].n_taps, tb->taps[u].const_off, cells, static_cast<uint32_t>(flat.size()),
+                    static_cast<uint32_t>(incoming[u].size()), 0u};
+            cells += tb->taps[u].n_taps;
+            for (const TapsSyn &y : incoming[u])
+            {
+                if (y.tap >= tb->taps[u].n_taps)
+                {
+                    sfe::set_last_error("sfe_engine_create: synapse addressed to a tap outside its line");
+                    return -1;
+                }
+                flat.push_back(y);
+            }
+        }
+        if (e->upload(&e->t.taps_units, units.data(), units.size()) != 0) return -1;
+        if (e->upload(&e->t.taps_syn, flat.data(), flat.size()) != 0) return -1;
+        if (e->upload(&e->t.taps_values, tb->taps_values, tb->n_taps_values) != 0) return -1;
+        if (e->upload(&e->t.neuron_taps, tb->neuron_taps, tb->n_neurons) != 0) return -1;
+        e->t.n_taps_units = tb->n_taps_units;
+        e->n_taps_units = tb->n_taps_units;
+        e->tap_cells = cells;
+        if (e->alloc(&e->s.tap_v, cells) != 0) return -1;
+        if (e->alloc(&e->s.tap_next, cells) != 0) return -1;
+        if (e->alloc(&e->s.tap_steps, tb->n_taps_units) != 0) return -1;
+        if (e->alloc(&e->s.tap_buf, tb->n_taps_units) != 0) return -1;
+        if (e->alloc(&e->s.tap_has, tb->n_taps_units) != 0) return -1;
+        e->exotic = true; // the neuron phase reads the lines' outputs in its `exotic` instantiation
     }
     e->n_poisson_cols = tb->n_poisson_cols;
     for (uint32_t k = 0; k < tb->n_inputs; ++k)
@@ -2548,6 +2706,16 @@ static void launch_soma(sfe_engine *e)
     else launch_step_kernel(e, soma_kernel<false>, grid, kSomaThreads, 0, e->t, e->s);
 }
 
+// "taps" lines of the step (experimental): after the neuron phase has written the raster, before the message
+// phase; a plain launch, i.e. fully ordered after the neuron phase like the probe kernel
+static void launch_taps(sfe_engine *e)
+{
+    if (e->n_taps_units == 0) return;
+    e->s.steps_done = e->total_timesteps;
+    taps_kernel<<<(e->n_taps_units + 127) / 128, 128, 0, e->stream>>>(e->t, e->s);
+    ++e->launches;
+}
+
 // The stand-alone fold of a step whose records are needed now (end of a batch, collect, reset...).
 static void flush_fold(sfe_engine *e)
 {
@@ -2624,6 +2792,7 @@ static int enqueue_step(sfe_engine *e, bool probes)
         launch_soma(e);
         ++e->launches;
     }
+    launch_taps(e);
     if (probes && e->n_probes + e->n_u_probes > 0)
     {
         probe_kernel<<<(e->n_probes + e->n_u_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
@@ -2806,6 +2975,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 launch_soma(e);
                 ++e->launches;
             }
+            launch_taps(e);
             unsigned char *stage = static_cast<unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
             if (want_fired)
             {
@@ -2903,6 +3073,12 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
     if (e->ordered_any || e->dual_any) SFE_CUDA(cudaMemsetAsync(e->s.dcnt32, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(uint32_t), e->stream));
     if (e->ordered_any) SFE_CUDA(cudaMemsetAsync(e->s.din64, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(double), e->stream));
     if (e->n_hh > 0) SFE_CUDA(cudaMemsetAsync(e->s.hh, 0, 4 * static_cast<size_t>(e->n_hh) * sizeof(double), e->stream));
+    if (e->n_taps_units > 0)
+    {
+        // MultiTapModel1D::reset  src/models.cpp:340-348: voltages only (the lines' step counters run on)
+        SFE_CUDA(cudaMemsetAsync(e->s.tap_v, 0, std::max<size_t>(e->tap_cells, 1) * sizeof(double), e->stream));
+        SFE_CUDA(cudaMemsetAsync(e->s.tap_has, 0, e->n_taps_units * sizeof(uint32_t), e->stream));
+    }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }

@@ -151,3 +151,16 @@ def test_taps_dendrites_are_refused_loudly():
     implementation yet: loading one onto a device must fail with a message, never run something else."""
     with pytest.raises(sfe.SanafeError, match="taps"):
         load_chip("taps", device=0)
+
+
+@pytest.mark.xfail(reason="experimental device path of `taps` dendrites (SFE_DEVICE_TAPS=1): written after the round's GPU "
+                          "budget was spent, never run on hardware; an XPASS here means it can become the default",
+                   strict=False)
+def test_taps_device_path_experimental(monkeypatch):
+    """taps_kernel + the neuron phase's tap-line read-out against the reference's golden (the CPU restatement
+    passes it in test_oracle_vs_reference.py)."""
+    monkeypatch.setenv("SFE_DEVICE_TAPS", "1")
+    chip = load_chip("taps", device=0)
+    g = golden("taps")
+    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+    check_against_golden("taps", chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
