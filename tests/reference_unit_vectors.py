@@ -128,7 +128,9 @@ def check_input(tmp_path, device, runner):
     def input_net(attr):
         return ("network:\n  name: in\n  groups:\n"
                 f"  - {{name: target, attributes: {{log_spikes: true, log_potential: true}}, neurons: [{{0: {attr}}}]}}\n"
-                "  edges: []\nmappings:\n- {target.0: {core: '0.0', soma: demo_input}}\n")
+                "  - {name: sink, attributes: {threshold: 1000000.0}, neurons: [{0: {}}]}\n"
+                "  edges:\n  - {target.0 -> sink.0: {weight: 0.125}}\n"
+                "mappings:\n- {target.0: {core: '0.0', soma: demo_input}}\n- {sink.0: {core: '0.1', soma: demo_soma_default}}\n")
     # GeneratesSpikeWhenSpikeValueSet / NoSpikeWhenSpikeValueZero (test_inputmodel.cpp:30-42); the train ends -> idle
     st, _ = rig.run(rig.load(tmp_path, rig.demo_arch(), input_net("{spikes: [1]}"), device), 3, runner)
     assert st == ["fired", "idle", "idle"]

@@ -23,10 +23,13 @@ def _attrs(d):
 def lif_network(attrs, currents, soma="demo_soma_default"):
     """Target on core 0.0 of the demo chip, drivers on the `demo_input` units of cores 0.1 .. 1.3 (an input unit
     holds ONE spike train)."""
-    assert len(currents) <= 7
+    assert len(currents) <= 6
     lines = ["network:", "  name: unit_rig", "  groups:",
              f"  - {{name: target, attributes: {_attrs(dict(attrs, log_spikes='true', log_potential='true'))}, neurons: [{{0: {{}}}}]}}"]
-    edges, maps = [], [f"- {{target.0: {{core: '0.0', soma: {soma}}}}}"]
+    # (a far-from-threshold sink behind the target keeps at least one synapse on the chip in every case)
+    lines.append("  - {name: sink, attributes: {threshold: 1000000.0}, neurons: [{0: {}}]}")
+    edges = ["  - {target.0 -> sink.0: {weight: 0.125}}"]
+    maps = [f"- {{target.0: {{core: '0.0', soma: {soma}}}}}", "- {sink.0: {core: '1.3', soma: demo_soma_default}}"]  # its own core: soma / dendrite units hold per-unit state
     for k, c in enumerate(currents):
         if c is None:
             continue
@@ -43,7 +46,10 @@ def truenorth_network(attrs, currents):
     hard reset far below zero)."""
     lines = ["network:", "  name: unit_rig", "  groups:",
              f"  - {{name: target, attributes: {_attrs(dict(attrs, log_spikes='true', log_potential='true'))}, neurons: [{{0: {{}}}}]}}"]
-    edges, maps = [], ["- {target.0: {core: '0.0'}}"]
+    lines.append("  - {name: sink, attributes: {threshold: 1000000.0}, neurons: [{0: {}}]}")
+    edges = ["  - {target.0 -> sink.0: {weight: 0.125}}"]
+    assert len(currents) <= 6
+    maps = ["- {target.0: {core: '0.0'}}", "- {sink.0: {core: '7.0'}}"]
     for k, c in enumerate(currents):
         if c is None:
             continue
