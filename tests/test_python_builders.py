@@ -119,7 +119,8 @@ def test_save_round_trip(tmp_path):
     path = str(tmp_path / "saved.yaml")
     net.save(path)
     again = m.load_net(path, arch)
-    assert table_bytes(HostChip(arch, net).tables) == table_bytes(HostChip(arch, again).tables)
+    first, second = HostChip(arch, net), HostChip(arch, again)  # (the tables live as long as their chip)
+    assert table_bytes(first.tables) == table_bytes(second.tables)
     text = open(path).read()
     assert "network:" in text and "mappings:" in text and '"out.1 -> out.1"' in text
     # a loaded network with hyper-edges, unit-specific attributes, non-default units and float weights
@@ -131,7 +132,8 @@ def test_save_round_trip(tmp_path):
         n1 = m.load_net(os.path.join(src, net_file), a)
         n1.save(path)
         n2 = m.load_net(path, a)
-        t1, t2 = HostChip(a, n1).tables, HostChip(a, n2).tables
+        c1, c2 = HostChip(a, n1), HostChip(a, n2)
+        t1, t2 = c1.tables, c2.tables
         assert table_bytes(t1) == table_bytes(t2), net_file
         assert t1.n_poisson_cols == t2.n_poisson_cols and t1.n_noise == t2.n_noise and t1.n_u_probes == t2.n_u_probes
     # the saved file read by an independent YAML parser (PyYAML, oracle/yaml_to_flat.py) and run by the REFERENCE
