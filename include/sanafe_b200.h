@@ -332,6 +332,9 @@ int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_s
  * ("simulation interrupted") at its next batch boundary (at most 4096 steps); the steps done so far stay done.
  * The reference polls PyErr_CheckSignals every 100 ms inside its loop (src/pymodule.cpp:629-652). on = 0 re-arms. */
 void sfe_engine_request_stop(sfe_engine *e, int on);
+/* EXPERIMENTAL (not yet verified on hardware): the same overlay drawn on the device by one MT19937 per input unit
+ * (csrc/mt19937.cuh, checked on the host against libstdc++); sfe_chip_sim uses it when SFE_DEVICE_POISSON=1. */
+int sfe_engine_fill_input_overlay(sfe_engine *e, int64_t n_steps);
 /* Host-only source of that overlay (no device needed): one std::mt19937 per Poisson unit, seeded
  * tables->input_seed_base + unit + 1. sfe_poisson_fill writes bits[n_steps][sfe_poisson_cols] for the next
  * n_steps steps and advances the streams (they are not rewound by a reset: InputModel::reset, src/models.hpp:358). */
@@ -340,6 +343,10 @@ sfe_poisson *sfe_poisson_create(const sfe_tables *tables);
 void sfe_poisson_destroy(sfe_poisson *p);
 uint32_t sfe_poisson_cols(const sfe_poisson *p);
 int sfe_poisson_fill(sfe_poisson *p, uint8_t *bits, int64_t n_steps);
+/* cross-check hooks: n draws of U(0,1) from seed through libstdc++'s std::mt19937 + uniform_real_distribution, and
+ * through the engine's own host/device MT19937 (csrc/mt19937.cuh, state interleaved with `stride`) */
+void sfe_poisson_reference_draws(uint32_t seed, double *out, size_t n);
+void sfe_mt19937_draws(uint32_t seed, double *out, size_t n, size_t stride);
 int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias);
 int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n);
 int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words);

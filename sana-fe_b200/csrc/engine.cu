@@ -42,6 +42,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "mt19937.cuh"
 #include "sanafe_b200.h"
 
 namespace sfe
@@ -111,6 +112,34 @@ struct TapsSyn
     uint32_t src_bit; // raster bit of the source neuron
     uint32_t tap;
 };
+
+// Poisson inputs drawn on the device, EXPERIMENTAL (SFE_DEVICE_POISSON=1): one MT19937 per Poisson input unit
+// (csrc/mt19937.cuh, states interleaved), one thread per unit filling the unit's columns of the overlay for a
+// chunk of timesteps. The default path draws on the host with libstdc++ (csrc/host/poisson.cpp).
+struct PoissonUnit
+{
+    double probability;
+    uint32_t share_count;
+    uint32_t col_begin; // the unit's col_of_rank[share_count] in poisson_cols
+};
+
+__global__ void poisson_kernel(const PoissonUnit *units, const uint32_t *cols, uint32_t n_units, uint32_t *mt, uint32_t *idx,
+        uint8_t *overlay, const long long n_steps, const uint32_t n_cols)
+{
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const PoissonUnit d = units[u];
+    uint32_t cursor = idx[u];
+    for (long long step = 0; step < n_steps; ++step)
+        for (uint32_t r = 0; r < d.share_count; ++r)
+        {
+            // InputModel::update draws on every update of the unit (src/models.cpp:880-885)
+            const double x = sfe::mt_canonical(mt + u, n_units, &cursor);
+            const uint32_t col = cols[d.col_begin + r];
+            if (col != 0xFFFFFFFFu) overlay[static_cast<size_t>(step) * n_cols + col] = d.probability > x ? 1 : 0;
+        }
+    idx[u] = cursor;
+}
 
 struct DevTables
 {
@@ -1955,6 +1984,10 @@ struct sfe_engine
     bool ordered_any{false}, dual_any{false};
     // cooperative cancellation of a long sfe_engine_run (Ctrl-C in the Python binding): checked between batches
     std::atomic<bool> stop_requested{false};
+    // device-side Poisson draws (experimental)
+    PoissonUnit *d_poisson_units{nullptr};
+    uint32_t *d_poisson_cols{nullptr}, *d_mt{nullptr}, *d_mt_idx{nullptr};
+    uint32_t n_poisson_units{0};
     uint32_t n_taps_units{0}; // "taps" dendrites (experimental device path)
     size_t tap_cells{0};
     // Poisson overlay (host-drawn, see poisson.cpp)
@@ -2224,6 +2257,41 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             sfe::set_last_error("sfe_engine_create: Poisson input neuron with poisson_col >= n_poisson_cols");
             return -1;
         }
+    if (tb->n_poisson_cols > 0)
+    {
+        // generators for sfe_engine_fill_input_overlay: one per input unit with poisson > 0, seeded like the
+        // reference's (input_seed_base + unit + 1), states interleaved word-major
+        std::vector<PoissonUnit> units;
+        std::vector<uint32_t> cols, seeds;
+        std::vector<uint32_t> unit_of; // unit ordinal of units[k]
+        for (uint32_t k = 0; k < tb->n_inputs; ++k)
+        {
+            const sfe_input_desc &d = tb->inputs[k];
+            if (!(d.poisson > 0.0)) continue;
+            size_t slot = 0;
+            while (slot < unit_of.size() && unit_of[slot] != d.unit) ++slot;
+            if (slot == unit_of.size())
+            {
+                unit_of.push_back(d.unit);
+                seeds.push_back(tb->input_seed_base + d.unit + 1u);
+                units.push_back({d.poisson, d.share_count, static_cast<uint32_t>(cols.size())});
+                cols.insert(cols.end(), d.share_count, 0xFFFFFFFFu);
+            }
+            if (d.share_rank < units[slot].share_count) cols[units[slot].col_begin + d.share_rank] = d.poisson_col;
+        }
+        const uint32_t n_units = static_cast<uint32_t>(units.size());
+        std::vector<uint32_t> mt(static_cast<size_t>(sfe::kMtWords) * n_units), idx(n_units);
+        for (uint32_t u = 0; u < n_units; ++u) sfe::mt_seed(mt.data() + u, n_units, &idx[u], seeds[u]);
+        e->n_poisson_units = n_units;
+        if (e->alloc(&e->d_poisson_units, n_units) != 0 || e->alloc(&e->d_poisson_cols, cols.size()) != 0 ||
+                e->alloc(&e->d_mt, mt.size()) != 0 || e->alloc(&e->d_mt_idx, n_units) != 0)
+            return -1;
+        SFE_CUDA(cudaMemcpyAsync(e->d_poisson_units, units.data(), n_units * sizeof(PoissonUnit), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaMemcpyAsync(e->d_poisson_cols, cols.data(), cols.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaMemcpyAsync(e->d_mt, mt.data(), mt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaMemcpyAsync(e->d_mt_idx, idx.data(), n_units * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream)); // the host vectors go out of scope
+    }
     // Device synapse layout: every axon segment starts on a multiple of 4 synapses
     // (32-byte aligned weights, 16-byte aligned meta words) so the message phase can
     // use 128-bit loads; the axon records carry the padded offsets.
@@ -2841,6 +2909,43 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
     for (int64_t i = 0; i < timesteps; ++i)
         if (enqueue_step(e, false) != 0) return -1;
     SFE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// EXPERIMENTAL: the overlay of the next n_steps steps drawn on the device (poisson_kernel) instead of uploaded.
+// Advances the device generators; do not mix with host-drawn overlays on one engine (two streams of draws).
+extern "C" int sfe_engine_fill_input_overlay(sfe_engine *e, int64_t n_steps)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->n_poisson_cols == 0 || n_steps < 0)
+    {
+        sfe::set_last_error("sfe_engine_fill_input_overlay: this chip has no Poisson inputs");
+        return -1;
+    }
+    SFE_CUDA(cudaStreamSynchronize(e->stream)); // steps already enqueued may still be reading the previous overlay
+    const size_t bytes = static_cast<size_t>(n_steps) * e->n_poisson_cols;
+    if (bytes > e->overlay_cap)
+    {
+        if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
+        e->d_overlay = nullptr;
+        e->overlay_cap = 0;
+        void *q = nullptr;
+        SFE_CUDA(cudaMalloc(&q, bytes));
+        e->d_overlay = static_cast<uint8_t *>(q);
+        e->overlay_cap = bytes;
+    }
+    if (bytes > 0)
+    {
+        SFE_CUDA(cudaMemsetAsync(e->d_overlay, 0, bytes, e->stream));
+        poisson_kernel<<<(e->n_poisson_units + 63) / 64, 64, 0, e->stream>>>(e->d_poisson_units, e->d_poisson_cols,
+                e->n_poisson_units, e->d_mt, e->d_mt_idx, e->d_overlay, n_steps, e->n_poisson_cols);
+        ++e->launches;
+        SFE_CUDA(cudaGetLastError());
+    }
+    e->t.overlay = e->d_overlay;
+    e->t.overlay_cols = e->n_poisson_cols;
+    e->t.overlay_step0 = e->total_timesteps;
+    e->t.overlay_steps = n_steps;
     return 0;
 }
 

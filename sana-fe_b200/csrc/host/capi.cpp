@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -329,7 +330,13 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                             if (req->neuron_traces != nullptr)
                                 sub.neuron_traces = req->neuron_traces + static_cast<size_t>(done) * c->tables.view.n_u_probes;
                         }
-                        if (c->poisson != nullptr)
+                        const char *opt = std::getenv("SFE_DEVICE_POISSON"); // experimental, see sfe_engine_fill_input_overlay
+                        const bool device_draws = opt != nullptr && std::atoi(opt) != 0;
+                        if (c->poisson != nullptr && device_draws)
+                        {
+                            if (sfe_engine_fill_input_overlay(c->engine, batch) != 0) return -1;
+                        }
+                        else if (c->poisson != nullptr)
                         {
                             overlay.resize(static_cast<size_t>(batch) * cols);
                             if (sfe_poisson_fill(c->poisson, overlay.data(), batch) != 0) return -1;

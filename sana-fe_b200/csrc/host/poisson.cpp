@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "mt19937.cuh"
 #include "sanafe_b200.h"
 
 struct sfe_poisson
@@ -100,4 +101,21 @@ extern "C" int sfe_poisson_fill(sfe_poisson *p, uint8_t *bits, int64_t n_steps)
                 if (col != 0xFFFFFFFFu) bits[static_cast<size_t>(s) * cols + col] = spike ? 1 : 0;
             }
     return 0;
+}
+
+// ---- cross-check hooks (tests): the same seed through libstdc++ and through mt19937.cuh's host compilation ----
+extern "C" void sfe_poisson_reference_draws(uint32_t seed, double *out, size_t n)
+{
+    std::mt19937 gen(seed);
+    std::uniform_real_distribution<double> uniform{0.0, 1.0};
+    for (size_t k = 0; k < n; ++k) out[k] = uniform(gen);
+}
+
+extern "C" void sfe_mt19937_draws(uint32_t seed, double *out, size_t n, size_t stride)
+{
+    if (stride == 0) stride = 1;
+    std::vector<uint32_t> mt(static_cast<size_t>(sfe::kMtWords) * stride, 0u);
+    uint32_t idx = 0;
+    sfe::mt_seed(mt.data(), stride, &idx, seed);
+    for (size_t k = 0; k < n; ++k) out[k] = sfe::mt_canonical(mt.data(), stride, &idx);
 }

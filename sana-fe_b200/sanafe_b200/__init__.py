@@ -170,8 +170,10 @@ def lib():
         "sfe_chip_set_partition": (C.c_int, [vp, u32, u32]),
         "sfe_chip_set_input_seed_base": (C.c_int, [vp, u32]),
         "sfe_engine_set_input_overlay": (C.c_int, [vp, vp, i64, u32]),
+        "sfe_engine_fill_input_overlay": (C.c_int, [vp, i64]),
         "sfe_poisson_create": (vp, [C.POINTER(Tables)]), "sfe_poisson_destroy": (None, [vp]),
         "sfe_poisson_cols": (u32, [vp]), "sfe_poisson_fill": (C.c_int, [vp, vp, i64]),
+        "sfe_poisson_reference_draws": (None, [u32, vp, sz]), "sfe_mt19937_draws": (None, [u32, vp, sz, sz]),
         "sfe_engine_read_log_tail": (i64, [vp, vp, i64]),
         "sfe_nccl_get_unique_id": (C.c_int, [vp, cstr]),
         "sfe_engine_comm_init": (C.c_int, [vp, vp, cstr]),

@@ -89,3 +89,16 @@ def test_seed_base_shifts_the_streams():
     with_overlay.set_input_overlay(shifted)
     _, o2 = with_overlay.run(64)
     assert np.array_equal(o1["fired_bits"], o2["fired_bits"])
+
+
+def test_engine_generator_equals_libstdcxx():
+    """csrc/mt19937.cuh (one source for host and device; the experimental device-side draws use it) against
+    std::mt19937 + std::uniform_real_distribution<double>: same doubles, with the state interleaved or not."""
+    L = sfe.lib()
+    for seed in (1, 2, 7, 1000, 4294967295):
+        for stride in (1, 3, 128):
+            want, got = np.zeros(5000), np.zeros(5000)
+            L.sfe_poisson_reference_draws(seed, want.ctypes.data, want.size)
+            L.sfe_mt19937_draws(seed, got.ctypes.data, got.size, stride)
+            assert np.array_equal(want, got), (seed, stride)
+            assert 0.0 <= got.min() and got.max() < 1.0
