@@ -248,3 +248,58 @@ def test_serialize_network(tmp_path):
     assert text.count('core: "1.0"') == 6
     again = mod.load_net(path, arch)
     assert len(again["g"]) == 6 and again["g"][0].edges_out[0].post_neuron.neuron_offset == 5
+
+
+# ---- test_connect_neurons_sparse.cpp ----------------------------------------------------------------------------
+def sparse_groups(n_src, n_dst):
+    net = m().Network()
+    return net, net.create_neuron_group("src", n_src), net.create_neuron_group("dst", n_dst)
+
+
+def weight_of(connection):
+    return connection.synapse_attributes["weight"]
+
+
+def test_sparse_attributes_are_indexed_by_edge_position():
+    """AttributesIndexedByEdgePositionNotSourceId (:40-70)"""
+    net, src, dst = sparse_groups(3, 3)
+    src.connect_neurons_sparse(dst, {"weight": [10.0, 20.0, 30.0]}, [(2, 0), (0, 1), (1, 2)])
+    assert [weight_of(src[i].edges_out[0]) for i in (2, 0, 1)] == [10.0, 20.0, 30.0]
+
+
+def test_sparse_edges_from_one_source_get_distinct_attributes():
+    """MultipleEdgesFromSameSourceGetDistinctAttributes (:75-100)"""
+    net, src, dst = sparse_groups(2, 3)
+    src.connect_neurons_sparse(dst, {"weight": [1.0, 2.0, 3.0]}, [(0, 0), (0, 1), (1, 2)])
+    assert [weight_of(e) for e in src[0].edges_out] == [1.0, 2.0] and weight_of(src[1].edges_out[0]) == 3.0
+
+
+def test_sparse_large_source_id_small_edge_count():
+    """LargeSourceIdSmallEdgeCountDoesNotOverrun (:103-120)"""
+    net, src, dst = sparse_groups(8, 2)
+    src.connect_neurons_sparse(dst, {"weight": [100.0, 200.0]}, [(5, 0), (7, 1)])
+    assert weight_of(src[5].edges_out[0]) == 100.0 and weight_of(src[7].edges_out[0]) == 200.0
+    with pytest.raises(ValueError):
+        src.connect_neurons_sparse(dst, {"weight": [1.0]}, [(8, 0)])  # source id out of range
+
+
+# ---- test_basic_input.cpp (the command line's required arguments) -------------------------------------------------
+def run_sim(*args):
+    import subprocess
+    from helpers import ROOT
+    sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
+    return subprocess.run([sim, *args], capture_output=True, text=True, timeout=60)
+
+
+@pytest.mark.parametrize("case,args,needle", [
+    ("MissingArguments (:23-27)", ["arch.yaml"], "Usage: ./sim"),
+    ("InvalidTimestepNonNumeric (:29-33)", ["arch.yaml", "net.yaml", "abc"], "Invalid time-step format"),
+    ("InvalidTimestepNegative (:35-39)", ["arch.yaml", "net.yaml", "-10"], "Time-steps must be > 0"),
+    ("InvalidTimestepZero (:41-45)", ["arch.yaml", "net.yaml", "0"], "Time-steps must be > 0"),
+    ("FileDoesNotExist (:47-55)", ["nonexistent_arch.yaml", "net.yaml", "100"], "nonexistent_arch.yaml"),
+])
+def test_command_line_required_arguments(case, args, needle):
+    res = run_sim(*args)
+    assert needle in (res.stdout + res.stderr), (case, res.stdout, res.stderr)
+    if "Usage" not in needle:
+        assert res.returncode != 0, case
