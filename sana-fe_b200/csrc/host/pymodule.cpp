@@ -252,9 +252,15 @@ public:
     Chip(const Chip &) = delete;
     Chip &operator=(const Chip &) = delete;
 
-    void load(const std::shared_ptr<NetHandle> &net, bool /*overwrite*/)
+    void load(const std::shared_ptr<NetHandle> &net, bool overwrite)
     {
+        // SpikingChip::load  src/chip.cpp:129-138: overwrite=false maps the network NEXT TO what is already on the
+        // chip. This engine lowers one description per load: a second load has to replace the first.
+        if (loaded_ && !overwrite)
+            throw std::runtime_error("SpikingChip.load: mapping a second network next to the loaded one is not supported by "
+                                     "the B200 engine; pass overwrite=True to replace it");
         if (sfe_chip_load(h_, net->h) != 0) raise_last();
+        loaded_ = true;
     }
     void reset()
     {
@@ -539,6 +545,7 @@ public:
 private:
     std::shared_ptr<ArchHandle> arch_;
     sfe_chip *h_{nullptr};
+    bool loaded_{false};
 };
 } // namespace
 

@@ -300,7 +300,13 @@ class SpikingChip:
         _check(lib().sfe_chip_set_input_seed_base(self._h, base))
 
     def load(self, net, overwrite=False):
+        """SpikingChip.load (src/chip.cpp:129-138). overwrite=False on a loaded chip would map a second network
+        next to the first in the reference; this engine lowers one description per load and refuses that."""
+        if getattr(self, "_loaded", False) and not overwrite:
+            raise SanafeError("SpikingChip.load: mapping a second network next to the loaded one is not supported by "
+                              "the B200 engine; pass overwrite=True to replace it")
         _check(lib().sfe_chip_load(self._h, net._h))
+        self._loaded = True
 
     def load_synthetic(self, spec, generate_on_device=True):
         _check(lib().sfe_chip_load_synthetic(self._h, C.byref(spec), 1 if generate_on_device else 0))

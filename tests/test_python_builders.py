@@ -249,3 +249,16 @@ def test_sim_errors_cross_the_worker_thread():
     chip.load(build_example(m, arch))
     with pytest.raises(RuntimeError, match="no CUDA device"):
         chip.sim(10, timing_model="simple")
+
+
+def test_second_load_needs_overwrite():
+    """SpikingChip.load(net, overwrite=False) on a loaded chip maps a second network next to the first in the
+    reference (src/chip.cpp:129-138); this engine refuses instead of silently replacing."""
+    m = module()
+    arch = m.load_arch(example_arch_path())
+    chip = m.SpikingChip(arch, device=-1)
+    chip.load(build_example(m, arch))
+    with pytest.raises(RuntimeError, match="overwrite=True"):
+        chip.load(build_example(m, arch))
+    chip.load(build_example(m, arch), overwrite=True)
+    assert sorted(chip.mapped_neuron_groups) == ["in", "out"]
