@@ -442,7 +442,7 @@ int sfe_chip_set_input_seed_base(sfe_chip *c, uint32_t base);
 
 /* ---- design-space exploration: independent chips side by side on one GPU (BASELINE config 5) ----------
  * The reference runs a sweep as separate processes (scripts/, one `sim` per design point). Here the n chips of a
- * sweep live in one process; every chip owns a stream, and `host_threads` worker threads (0 = min(n, 32)) drive
+ * sweep live in one process; every chip owns a stream, and `host_threads` worker threads (0 = one per host core, at most n) drive
  * sfe_chip_load / sfe_chip_sim of different chips concurrently, so the kernels of that many chips overlap on the
  * device. Each chip goes through exactly the code path of a lone chip: its results are those of running it alone.
  * reqs: NULL or n trace requests; out: NULL or n records. Returns 0, or -1 with sfe_last_error() naming the first

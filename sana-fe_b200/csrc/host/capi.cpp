@@ -385,7 +385,8 @@ namespace
 // n independent jobs over a pool of host threads; job(k) returns 0 or -1 (+ the thread's last error)
 template <typename Job> int run_batch(const uint32_t n, uint32_t host_threads, const char *what, Job &&job)
 {
-    if (host_threads == 0) host_threads = std::min<uint32_t>(n, 32u);
+    // default: one worker per host core (a worker spins in cudaStreamSynchronize while its chip's batch runs)
+    if (host_threads == 0) host_threads = std::min<uint32_t>(n, std::max(1u, std::thread::hardware_concurrency()));
     host_threads = std::max<uint32_t>(1u, std::min<uint32_t>(host_threads, n));
     std::atomic<uint32_t> next{0};
     std::mutex mu;
