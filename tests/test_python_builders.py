@@ -262,3 +262,19 @@ def test_second_load_needs_overwrite():
         chip.load(build_example(m, arch))
     chip.load(build_example(m, arch), overwrite=True)
     assert sorted(chip.mapped_neuron_groups) == ["in", "out"]
+
+
+def test_import_sanafe_shim():
+    """`import sanafe` (PYTHONPATH=sana-fe_b200) gives the reference's top-level names."""
+    import sanafe
+    for name in ("load_arch", "load_net", "Network", "SpikingChip", "Architecture", "HardwareMappingError"):
+        assert hasattr(sanafe, name), name
+    arch = sanafe.load_arch(example_arch_path())
+    net = sanafe.Network()
+    group = net.create_neuron_group("g", 2, model_attributes={"threshold": 1.0})
+    group[0].connect_to_neuron(group[1], {"weight": 1})
+    for n in group:
+        n.map_to_core(arch.tiles[0].cores[0])
+    chip = sanafe.SpikingChip(arch, device=-1)
+    chip.load(net)
+    assert list(chip.mapped_neuron_groups) == ["g"]
