@@ -358,6 +358,8 @@ public:
         out["packets_sent"] = rd.packets_sent;
         out["neurons_updated"] = rd.neurons_updated;
         out["neurons_fired"] = rd.neurons_fired;
+        // the five trace entries always exist; they stay None unless the trace was kept in memory (src/pymodule.cpp:691-702)
+        for (const char *key : {"spike_trace", "potential_trace", "neuron_trace", "perf_trace", "message_trace"}) out[key] = py::none();
         if (want_spikes)
         {
             const size_t need = sfe_chip_format_spikes(h_, fired.data(), timesteps, rd.timestep_start, nullptr, 0);
@@ -366,7 +368,7 @@ public:
             text.resize(need);
             if (py::isinstance<py::bool_>(spike_trace))
             {
-                // in-memory: one list of (group, offset) per timestep (src/pytrace.hpp)
+                // in-memory: one list of NeuronAddress per timestep (src/pytrace.hpp:98-141)
                 std::vector<py::list> per_step(timesteps);
                 std::istringstream in(text);
                 std::string row;
@@ -374,7 +376,10 @@ public:
                 {
                     const size_t comma = row.rfind(','), dot = row.rfind('.', comma);
                     const long ts = std::stol(row.substr(comma + 1));
-                    per_step[ts - rd.timestep_start].append(py::make_tuple(row.substr(0, dot), std::stoul(row.substr(dot + 1, comma - dot - 1))));
+                    sfe::NeuronAddress address; // PySpikeTrace hands out NeuronAddress objects (src/pytrace.hpp:121-141)
+                    address.group_name = row.substr(0, dot);
+                    address.neuron_offset = std::stoul(row.substr(dot + 1, comma - dot - 1));
+                    per_step[ts - rd.timestep_start].append(py::cast(address));
                 }
                 py::list all;
                 for (auto &l : per_step) all.append(l);
@@ -473,10 +478,53 @@ public:
             text.resize(need);
             if (py::isinstance<py::bool_>(message_trace))
             {
-                py::list rows;
+                // in memory: per timestep a list of message dictionaries (message_to_dict, src/pytrace.cpp:17-53) with
+                // the fields the device trace carries (those of messages.csv, at its 6-digit precision); tile
+                // coordinates, global core ids and axon ids are not reconstructed
+                std::vector<py::list> per_step(timesteps);
                 std::istringstream in(text);
-                for (std::string line; std::getline(in, line);) rows.append(py::str(line).attr("split")(","));
-                out["message_trace"] = rows;
+                for (std::string line; std::getline(in, line);)
+                {
+                    std::vector<std::string> f;
+                    std::istringstream cells(line);
+                    for (std::string cell; std::getline(cells, cell, ',');) f.push_back(cell);
+                    if (f.size() < 16) continue;
+                    auto split = [](const std::string &x) {
+                        const size_t dot = x.rfind('.');
+                        return std::make_pair(x.substr(0, dot), x.substr(dot + 1));
+                    };
+                    py::dict msg;
+                    const long ts = std::stol(f[0]);
+                    msg["timestep"] = ts;
+                    msg["mid"] = std::stol(f[1]);
+                    const auto src_neuron = split(f[2]);
+                    msg["src_neuron_group_id"] = src_neuron.first;
+                    msg["src_neuron_offset"] = std::stoul(src_neuron.second);
+                    const auto src_hw = split(f[3]);
+                    msg["src_tile_id"] = std::stoul(src_hw.first);
+                    msg["src_core_offset"] = std::stoul(src_hw.second);
+                    const bool placeholder = f[4] == "x.x";
+                    msg["placeholder"] = placeholder;
+                    if (!placeholder)
+                    {
+                        const auto dest_hw = split(f[4]);
+                        msg["dest_tile_id"] = std::stoul(dest_hw.first);
+                        msg["dest_core_offset"] = std::stoul(dest_hw.second);
+                    }
+                    msg["hops"] = std::stol(f[5]);
+                    msg["spikes"] = std::stol(f[6]);
+                    msg["send_timestamp"] = std::stod(f[7]);
+                    msg["received_timestamp"] = std::stod(f[8]);
+                    msg["processed_timestamp"] = std::stod(f[9]);
+                    msg["generation_delay"] = std::stod(f[10]);
+                    msg["processing_delay"] = std::stod(f[11]);
+                    msg["network_delay"] = std::stod(f[12]);
+                    msg["blocking_delay"] = std::stod(f[13]);
+                    if (ts >= rd.timestep_start && ts < rd.timestep_start + timesteps) per_step[ts - rd.timestep_start].append(msg);
+                }
+                py::list all;
+                for (auto &l : per_step) all.append(l);
+                out["message_trace"] = all;
             }
             else
             {

@@ -278,3 +278,16 @@ def test_import_sanafe_shim():
     chip = sanafe.SpikingChip(arch, device=-1)
     chip.load(net)
     assert list(chip.mapped_neuron_groups) == ["g"]
+
+
+def test_neuron_address_objects():
+    """NeuronAddress (what in-memory spike traces hold, src/pytrace.hpp:121-141) is picklable as in the reference."""
+    import pickle
+    m = module()
+    net = m.Network()
+    g = net.create_neuron_group("grp", 2)
+    g[0].connect_to_neuron(g[1])
+    address = g[0].edges_out[0].post_neuron
+    assert (address.group_name, address.neuron_offset) == ("grp", 1)
+    again = pickle.loads(pickle.dumps(address))
+    assert (again.group_name, again.neuron_offset) == ("grp", 1)

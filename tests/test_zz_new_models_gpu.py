@@ -110,6 +110,38 @@ def test_neuron_trace_surfaces(tmp_path):
     assert cli_lines == lines
 
 
+def test_pybind_in_memory_trace_formats():
+    """In-memory traces of the pybind11 module have the reference's shapes (src/pytrace.hpp): spike_trace = per step a
+    list of NeuronAddress, potential_trace = per step a list of floats, neuron_trace = {name: per step values},
+    perf_trace = {column: per step value}, message_trace = per step a list of message dicts; entries not asked for
+    are None (src/pymodule.cpp:691-702)."""
+    import os
+    from helpers import ROOT, golden_flat
+    from sanafe_b200 import sanafecpp_b200 as m
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch, net = m.load_flat(golden_flat("noise"))
+        chip = m.SpikingChip(arch)
+        chip.load(net)
+    finally:
+        os.chdir(cwd)
+    res = chip.sim(20, timing_model="simple", spike_trace=True, potential_trace=True, perf_trace=True, message_trace=True)
+    assert res["neuron_trace"] is None
+    spikes = res["spike_trace"]
+    assert len(spikes) == 20 and all(isinstance(step, list) for step in spikes)
+    first = next(a for step in spikes for a in step)
+    assert isinstance(first, m.NeuronAddress) and isinstance(first.group_name, str) and first.neuron_offset >= 0
+    assert len(res["potential_trace"]) == 20 and len(res["potential_trace"][0]) == 8
+    assert set(res["perf_trace"]) >= {"timestep", "fired", "updated", "hops", "spikes", "sim_time", "total_energy"}
+    msgs = res["message_trace"]
+    assert len(msgs) == 20 and sum(len(step) for step in msgs) > 0
+    one = next(msg for step in msgs for msg in step)
+    assert {"timestep", "mid", "spikes", "hops", "generation_delay", "placeholder", "src_neuron_group_id"} <= set(one)
+    none = chip.sim(1, timing_model="simple")
+    assert all(none[k] is None for k in ("spike_trace", "potential_trace", "neuron_trace", "perf_trace", "message_trace"))
+
+
 def test_reference_unit_vectors_on_the_device(tmp_path):
     """The reference's per-model unit-test expectations (tests/unit/test_*.cpp), restated on a one-neuron rig, on
     the device (the CPU restatement passes the same list in test_reference_unit_vectors.py)."""
