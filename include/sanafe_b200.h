@@ -468,7 +468,9 @@ const sfe_tables *sfe_chip_tables(const sfe_chip *c);
 sfe_engine *sfe_chip_engine(sfe_chip *c);
 /* group/offset <-> device index, trace order (lexicographic group, offset; src/chip.cpp:1616-1629) */
 int64_t sfe_chip_neuron_index(const sfe_chip *c, const char *group, uint64_t offset);
-/* MappedNeuron.set_attributes for a numeric soma attribute (bias, threshold, ...) */
+/* MappedNeuron.set_attributes for a numeric soma attribute (bias, threshold, ...). Bias patches are collected in the
+ * host table and reach the device as one vector before the next sfe_chip_sim (or sfe_chip_engine) call, so a
+ * per-frame loop over a thousand input neurons costs one upload, not a thousand. */
 int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offset, const char *name,
         double value);
 /* Spike rows of a fired-bit raster in the reference's trace order and format,

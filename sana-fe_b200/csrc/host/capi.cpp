@@ -54,6 +54,9 @@ struct sfe_chip
     // process-wide static, src/models.hpp:366) and the host generators of this chip's Poisson units
     uint32_t input_seed_base{0};
     sfe_poisson *poisson{nullptr};
+    // per-neuron bias patches (MappedNeuron.set_attributes in a per-frame loop, scripts/tcad2025/dvs_gesture.py) are
+    // collected in the host table and uploaded as ONE vector before the next step instead of one copy per neuron
+    bool bias_dirty{false};
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -95,6 +98,13 @@ template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f(
 }
 
 std::atomic<uint32_t> g_input_units_created{0};
+
+int flush_bias(sfe_chip *c)
+{
+    if (!c->bias_dirty || c->engine == nullptr) return 0;
+    c->bias_dirty = false;
+    return sfe_engine_set_bias(c->engine, c->tables.neuron_bias.data(), c->tables.neuron_bias.size());
+}
 
 int attach_engine(sfe_chip *c)
 {
@@ -281,6 +291,7 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                     throw std::runtime_error("no CUDA device: the B200 engine has no CPU fallback");
                 const auto wall0 = std::chrono::steady_clock::now();
                 sfe_engine_request_stop(c->engine, 0);
+                if (flush_bias(c) != 0) return -1;
                 if (timing_model == SFE_TIMING_CYCLE)
                     throw std::runtime_error("the cycle-accurate timing model needs Booksim2 (third-party, not "
                                              "available): out of scope");
@@ -485,6 +496,7 @@ extern "C" const sfe_tables *sfe_chip_tables(const sfe_chip *c)
 
 extern "C" sfe_engine *sfe_chip_engine(sfe_chip *c)
 {
+    if (c != nullptr) flush_bias(c); // callers that step the engine themselves see the patched biases
     return c->engine;
 }
 
@@ -553,7 +565,11 @@ extern "C" int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uin
                 if (idx < 0) throw std::out_of_range(std::string("no mapped neuron ") + group + "." + std::to_string(offset));
                 const bool classes_changed = sfe::patch_neuron_attribute(c->tables, static_cast<uint32_t>(idx), name, value);
                 if (c->engine == nullptr) return 0;
-                if (std::string(name) == "bias") return sfe_engine_set_neuron_bias(c->engine, static_cast<uint32_t>(idx), value);
+                if (std::string(name) == "bias")
+                {
+                    c->bias_dirty = true; // uploaded with the next sfe_chip_sim / sfe_chip_engine call
+                    return 0;
+                }
                 if (classes_changed)
                     return sfe_engine_update_classes(c->engine, c->tables.soma_classes.data(),
                             static_cast<uint32_t>(c->tables.soma_classes.size()), c->tables.neuron_class.data());

@@ -207,3 +207,29 @@ def test_poisson_device_draws_experimental(monkeypatch):
     g = golden("poisson")
     rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
     check_against_golden("poisson", chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
+
+
+def test_per_neuron_bias_patches_between_sim_calls():
+    """The DVS-gesture loop of the reference (scripts/tcad2025/dvs_gesture.py): MappedNeuron.set_attributes(bias)
+    on many neurons, then sim(). The patches are collected on the host and uploaded as one vector before the next
+    step; results must equal the CPU restatement given the same biases."""
+    dev = load_chip("synth_soma", device=0)
+    host = load_chip("synth_soma", device=-1)
+    oracle = Oracle(host)
+    t = host.tables
+    n = t.n_neurons
+    bias = np.array([t.neuron_bias[i] for i in range(n)])
+    rng = np.random.default_rng(3)
+    for round_ in range(3):
+        rd_d, out_d = dev.sim_raw(8, steps=True, fired=True, potentials=True)
+        rd_h, out_h = oracle.run(8)
+        assert np.array_equal(out_d["fired_bits"], out_h["fired_bits"]), round_
+        assert np.array_equal(out_d["potentials"], out_h["potentials"]), round_
+        assert rd_d.spikes == rd_h.spikes
+        for i in rng.choice(n, size=200, replace=False):
+            group, offset = "pop", int(i)
+            if dev.neuron_index(group, offset) != i:
+                continue  # (device order = group order for this single-group network; be safe)
+            bias[i] = float(rng.integers(0, 3)) * 64.0
+            dev.set_neuron_attribute(group, offset, "bias", bias[i])
+        oracle.set_bias(bias)
