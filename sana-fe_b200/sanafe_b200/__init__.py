@@ -208,6 +208,13 @@ def lib():
         "sfe_chip_format_spikes": (sz, [vp, vp, i64, i64, C.c_char_p, sz]),
         "sfe_chip_probe_names": (sz, [vp, C.c_char_p, sz]),
         "sfe_chip_trace_names": (sz, [vp, C.c_char_p, sz]),
+        "sfe_chip_group_names": (sz, [vp, C.c_char_p, sz]),
+        "sfe_chip_set_neuron_log_spikes": (C.c_int, [vp, cstr, u64, C.c_int]),
+        "sfe_chip_request_stop": (None, [vp]), "sfe_engine_request_stop": (None, [vp, C.c_int]),
+        "sfe_last_error_kind": (C.c_int, []),
+        "sfe_net_create": (vp, [cstr]), "sfe_net_save_yaml": (C.c_int, [vp, cstr]),
+        "sfe_batch_load": (C.c_int, [vp, vp, u32, u32]),
+        "sfe_batch_sim": (C.c_int, [vp, u32, i64, C.c_int, vp, vp, u32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the ABI header and the library disagree
