@@ -3,7 +3,8 @@
 restatement vs the reference's goldens — is pinned in test_oracle_vs_reference.py, test_poisson_inputs.py and
 test_dse_batch.py. Collected last (see helpers.NEW_GOLDEN_CASES).
 
-The first six tests have run green on a B200 (profiles/r1_pytest_new_models_gpu.log). The ones after them were written
+The first nine tests have run green on a B200 (profiles/r1_pytest_new_models_gpu.log, r1_pytest_new_models_gpu_2.log).
+The ones after them (the reference's unit-test vectors on the device, Ctrl-C, the two experimental paths) were written
 once the round's GPU minutes were spent: their CPU halves are pinned (tests/test_reference_unit_vectors.py,
 test_python_builders.py, test_poisson_inputs.py), the device halves have not executed yet; the two marked xfail drive
 code paths that are off by default."""
