@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--threads", type=int, default=16)
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--csv", default=None, help="write one row per design point (the sweep's actual result) to this file")
     args = ap.parse_args()
     if sfe.lib().sfe_device_count() <= 0:
         raise SystemExit("no CUDA device: the engine has no CPU fallback")
@@ -79,6 +80,20 @@ def main():
                       "timesteps_per_s": round(all_points * args.steps / wall, 1),
                       "synaptic_events_per_s": round(events / wall, 1)}
     out["batched_over_sequential"] = round(out["sequential"]["wall_s"] / out["batched"]["wall_s"], 2)
+    if args.csv:
+        # what a design-space exploration is after: energy, simulated time and activity of every design point
+        # (totals over everything this process has simulated on the chip: warm-up + both timed runs)
+        rows = [(npc, mult, r.total_energy, r.sim_time, r.spikes, r.packets_sent, r.neurons_fired)
+                for (npc, mult), r in zip(points, rds)]
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, rows)
+            rows = [row for part in gathered for row in part]
+        if rank == 0:
+            with open(args.csv, "w") as f:
+                f.write("neurons_per_core,cost_multiplier,energy_j,sim_time_s,synaptic_events,messages,neurons_fired\n")
+                for row in sorted(rows):
+                    f.write(",".join(repr(x) for x in row) + "\n")
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:
