@@ -82,7 +82,7 @@ def main():
     out["batched_over_sequential"] = round(out["sequential"]["wall_s"] / out["batched"]["wall_s"], 2)
     if args.csv:
         # what a design-space exploration is after: energy, simulated time and activity of every design point
-        # (totals over everything this process has simulated on the chip: warm-up + both timed runs)
+        # (of the last, batched, run of --steps timesteps)
         rows = [(npc, mult, r.total_energy, r.sim_time, r.spikes, r.packets_sent, r.neurons_fired)
                 for (npc, mult), r in zip(points, rds)]
         if dist is not None:
