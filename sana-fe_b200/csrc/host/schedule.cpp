@@ -52,7 +52,6 @@ struct BySentTime // CompareMessagesBySentTime  src/message.cpp:61-65
 struct Noc // NocInfo  src/schedule.hpp:170-202
 {
     size_t width, height, links_per_router;
-    std::vector<std::list<Msg>> received;
     std::vector<double> density;
     std::vector<double> core_free;
     double mean_rx{0.0};
@@ -113,9 +112,34 @@ struct Noc // NocInfo  src/schedule.hpp:170-202
         }
     }
 };
+struct InFlight // a message between being sent and being fully received
+{
+    double received;
+    uint32_t dest_core;
+    uint32_t seq; // arrival order (global counter: monotonic, hence also the order within a core)
+    uint32_t msg;
+};
+
+struct NeuronLatency // per soma class: what a neuron adds to its core's generation delay, by status
+{
+    double dend, access, update, spike_out;
+    bool dend_in_neuron;
+};
 } // namespace
 
-DetailedScheduler::DetailedScheduler(const sfe_tables &t) : t_(t)
+struct DetailedScheduler::Scratch // reused from step to step
+{
+    std::vector<Msg> msgs;
+    std::vector<uint32_t> core_begin, head;
+    std::vector<InFlight> in_flight, due;
+    std::vector<NeuronLatency> neuron_latency;
+    uint32_t n_classes_seen{0};
+    Noc noc;
+};
+
+DetailedScheduler::~DetailedScheduler() = default;
+
+DetailedScheduler::DetailedScheduler(const sfe_tables &t) : t_(t), scratch_(std::make_unique<Scratch>())
 {
     axon_core_.resize(t.n_axons_in);
     axon_proc_.resize(t.n_axons_in);
@@ -162,9 +186,27 @@ double DetailedScheduler::run_step(
         return static_cast<uint32_t>(recs.size() - 1);
     };
     // ---- rebuild the per-sending-core message lists ------------------------------
-    std::vector<std::list<Msg>> queues(t.n_cores);
+    // (one flat array in creation order; a core's messages are contiguous, `head` walks them)
+    Scratch &sc = *scratch_;
+    std::vector<Msg> &msgs = sc.msgs;
+    std::vector<uint32_t> &core_begin_ = sc.core_begin, &head_ = sc.head;
+    msgs.clear();
+    core_begin_.assign(t.n_cores + 1, 0);
+    if (sc.n_classes_seen != t.n_soma_classes) // (MappedNeuron.set_attributes can add classes between runs)
+    {
+        sc.neuron_latency.resize(t.n_soma_classes);
+        for (uint32_t k = 0; k < t.n_soma_classes; ++k)
+        {
+            const sfe_soma_class &cls = t.soma_classes[k];
+            sc.neuron_latency[k] = {cls.dend_latency_update, cls.latency_access, cls.latency_update, cls.latency_spike_out,
+                    cls.dend_in_neuron != 0};
+        }
+        sc.n_classes_seen = t.n_soma_classes;
+    }
+    const std::vector<NeuronLatency> &neuron_latency_ = sc.neuron_latency;
     for (uint32_t c = 0; c < t.n_cores; ++c)
     {
+        core_begin_[c] = static_cast<uint32_t>(msgs.size());
         const sfe_core_desc &cd = t.cores[c];
         if (cd.neuron_count == 0) continue;
         const sfe_tile_desc &src_tile = t.tiles[cd.tile];
@@ -172,13 +214,14 @@ double DetailedScheduler::run_step(
         for (uint32_t k = 0; k < cd.neuron_count; ++k)
         {
             const uint32_t i = cd.neuron_begin + k;
-            const sfe_soma_class &cls = t.soma_classes[t.neuron_class[i]];
             const uint8_t st = status[i];
+            const NeuronLatency &nl = neuron_latency_[t.neuron_class[i]];
+            // dendrite (when it runs in the neuron pipeline) then soma: access, + update, + spike out
             double lat = 0.0;
-            if (cls.dend_in_neuron) lat += cls.dend_latency_update;
-            double soma = cls.latency_access;
-            if (st == SFE_STATUS_UPDATED || st == SFE_STATUS_FIRED) soma += cls.latency_update;
-            if (st == SFE_STATUS_FIRED) soma += cls.latency_spike_out;
+            if (nl.dend_in_neuron) lat += nl.dend;
+            double soma = nl.access;
+            if (st == SFE_STATUS_UPDATED || st == SFE_STATUS_FIRED) soma += nl.update;
+            if (st == SFE_STATUS_FIRED) soma += nl.spike_out;
             lat += soma;
             next_delay += lat;
             if (st != SFE_STATUS_FIRED) continue;
@@ -208,7 +251,7 @@ double DetailedScheduler::run_step(
                 m.src_core = c;
                 m.dest_core = dc;
                 if (trace != nullptr) m.slot = new_record(m, i, ax.syn_count);
-                queues[c].push_back(m);
+                msgs.push_back(m);
             }
         }
         if (next_delay != 0.0)
@@ -220,9 +263,10 @@ double DetailedScheduler::run_step(
             m.src_core_offset = cd.offset;
             m.src_core = c;
             if (trace != nullptr) m.slot = new_record(m, cd.neuron_begin + cd.neuron_count - 1, 0u);
-            queues[c].push_back(m);
+            msgs.push_back(m);
         }
     }
+    core_begin_[t.n_cores] = static_cast<uint32_t>(msgs.size());
     auto finish_trace = [&]() {
         if (trace == nullptr) return;
         // sim_sort_and_record_messages: the same std::sort on the same sequence with the same
@@ -247,45 +291,70 @@ double DetailedScheduler::run_step(
     }
 
     // ---- schedule_messages_timestep_detailed  src/schedule.cpp:208-292 -----------------
-    Noc noc;
+    // Same event order and the same floating-point operations in the same order as the reference; only the
+    // containers differ. The reference keeps a std::list of in-flight messages per destination core and, for every
+    // event, walks ALL of them to find those received by then (noc_update_all_tracked_messages, :380-400). Here the
+    // in-flight messages sit in a min-heap by received time: the ones that are due are popped and then retired in
+    // the order the reference's walk would meet them (destination core ascending, arrival order within a core).
+    Noc &noc = sc.noc;
     noc.width = t.noc_width;
     noc.height = t.noc_height;
     noc.links_per_router = t.max_cores_per_tile + ndirections;
-    noc.received.resize(t.n_cores);
     noc.core_free.assign(t.n_cores, 0.0);
     noc.density.assign(static_cast<size_t>(t.noc_width) * t.noc_height * noc.links_per_router, 0.0);
-    std::priority_queue<Msg, std::vector<Msg>, BySentTime> pq;
-    for (auto &q : queues)
+    noc.mean_rx = 0.0;
+    noc.in_noc = 0;
+    head_.assign(core_begin_.begin(), core_begin_.end() - 1);
+    // event queue: std::priority_queue over (sent time, message) with the reference's comparator on the sent
+    // time alone — the heap's tie behaviour depends only on the sequence of pushes and pops, which is the same
+    struct Event
     {
-        if (q.empty()) continue;
-        Msg m = q.front();
-        q.pop_front();
+        double sent;
+        uint32_t msg;
+    };
+    struct LaterFirst
+    {
+        bool operator()(const Event &a, const Event &b) const noexcept { return a.sent > b.sent; }
+    };
+    std::priority_queue<Event, std::vector<Event>, LaterFirst> pq;
+    for (uint32_t c = 0; c < t.n_cores; ++c)
+    {
+        if (head_[c] == core_begin_[c + 1]) continue;
+        Msg &m = msgs[head_[c]++];
         m.sent = m.generation_delay;
         if (trace != nullptr) recs[m.slot].sent = m.sent;
-        pq.push(m);
+        pq.push({m.sent, static_cast<uint32_t>(&m - msgs.data())});
     }
-    std::vector<uint32_t> busy; // destination cores that currently hold tracked messages, ascending
+    auto later_received = [](const InFlight &a, const InFlight &b) { return a.received > b.received; };
+    std::vector<InFlight> &in_flight = sc.in_flight;
+    std::vector<InFlight> &due = sc.due;
+    in_flight.clear();
+    uint32_t seq = 0;
     double last = 0.0;
     while (!pq.empty())
     {
-        Msg m = pq.top();
+        const Event ev = pq.top();
         pq.pop();
+        Msg &m = msgs[ev.msg];
         last = std::max(last, m.sent);
-        // noc_update_all_tracked_messages: destination cores in id order, FIFO order within
-        for (size_t b = 0; b < busy.size();)
+        // noc_update_all_tracked_messages(m.sent): retire what has been received by now
+        if (!in_flight.empty() && m.sent >= in_flight.front().received)
         {
-            auto &q = noc.received[busy[b]];
-            q.remove_if([&](Msg &x) {
-                if (x.in_noc && (m.sent >= x.received))
-                {
-                    x.in_noc = false;
-                    noc.track(x, false);
-                    return true;
-                }
-                return false;
+            due.clear();
+            while (!in_flight.empty() && m.sent >= in_flight.front().received)
+            {
+                std::pop_heap(in_flight.begin(), in_flight.end(), later_received);
+                due.push_back(in_flight.back());
+                in_flight.pop_back();
+            }
+            std::sort(due.begin(), due.end(), [](const InFlight &a, const InFlight &b) {
+                return a.dest_core != b.dest_core ? a.dest_core < b.dest_core : a.seq < b.seq;
             });
-            if (q.empty()) busy.erase(busy.begin() + static_cast<long>(b));
-            else ++b;
+            for (const InFlight &x : due)
+            {
+                msgs[x.msg].in_noc = false;
+                noc.track(msgs[x.msg], false);
+            }
         }
         if (!m.placeholder)
         {
@@ -306,9 +375,8 @@ double DetailedScheduler::run_step(
                     std::max(noc.core_free[m.dest_core] + m.processing_delay, earliest + m.processing_delay);
             m.processed = noc.core_free[m.dest_core];
             m.in_noc = true;
-            if (noc.received[m.dest_core].empty())
-                busy.insert(std::lower_bound(busy.begin(), busy.end(), m.dest_core), m.dest_core);
-            noc.received[m.dest_core].push_back(m);
+            in_flight.push_back({m.received, m.dest_core, seq++, ev.msg});
+            std::push_heap(in_flight.begin(), in_flight.end(), later_received);
             noc.track(m, true);
             last = std::max(last, m.processed);
             if (trace != nullptr)
@@ -322,15 +390,14 @@ double DetailedScheduler::run_step(
                 r.messages_along_route = along_route;
             }
         }
-        auto &q = queues[m.src_core];
-        if (!q.empty())
+        const uint32_t c = m.src_core;
+        if (head_[c] != core_begin_[c + 1])
         {
             // schedule_push_next_message  src/schedule.cpp:360-378
-            Msg next = q.front();
-            q.pop_front();
+            Msg &next = msgs[head_[c]++];
             next.sent = m.sent + next.generation_delay;
             if (trace != nullptr) recs[next.slot].sent = next.sent;
-            pq.push(next);
+            pq.push({next.sent, static_cast<uint32_t>(&next - msgs.data())});
             last = std::max(last, next.sent);
         }
     }

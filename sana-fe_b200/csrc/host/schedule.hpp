@@ -3,6 +3,7 @@
 #define SFE_SCHEDULE_HPP_
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "sanafe_b200.h"
@@ -26,6 +27,7 @@ class DetailedScheduler
 {
 public:
     explicit DetailedScheduler(const sfe_tables &t);
+    ~DetailedScheduler();
     // sim_time of one timestep from the per-neuron status bytes of that step
     double schedule_step(const uint8_t *status) { return run_step(status, true, nullptr, nullptr); }
     // The step's messages in the order the reference traces them (sim_sort_and_record_messages,
@@ -42,6 +44,8 @@ private:
     const sfe_tables &t_;
     std::vector<uint32_t> axon_core_; // destination core of every axon-in
     std::vector<double> axon_proc_;   // processing delay of the message that targets it
+    struct Scratch;                   // per-step work arrays, kept between steps (schedule.cpp)
+    std::unique_ptr<Scratch> scratch_;
 };
 } // namespace sfe
 #endif
