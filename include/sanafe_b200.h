@@ -462,6 +462,9 @@ int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, const sfe_tra
 /* host-side detailed timing model (src/schedule.cpp:208-620) over a status trace
  * ([timesteps][n_neurons] SFE_STATUS_* bytes): per-step sim_time */
 int sfe_chip_schedule_detailed(sfe_chip *c, const uint8_t *status, int64_t timesteps, double *sim_time);
+/* Host threads of the detailed timing model (the reference's -S / scheduler_threads): timesteps are scheduled
+ * independently, a batch of them is spread over this many threads. 0 (default) = one per host core. */
+int sfe_chip_set_scheduler_threads(sfe_chip *c, uint32_t threads);
 int sfe_chip_reset(sfe_chip *c);       /* src/chip.cpp:576-600 */
 double sfe_chip_get_power(sfe_chip *c);/* src/chip.cpp:607-621 */
 const sfe_tables *sfe_chip_tables(const sfe_chip *c);

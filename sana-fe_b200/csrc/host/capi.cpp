@@ -49,6 +49,11 @@ struct sfe_chip
     double total_sim_time{0.0};
     uint32_t rank{0}, world{1};
     std::unique_ptr<sfe::DetailedScheduler> scheduler; // built on first use
+    // Timesteps are scheduled independently of each other (the NoC state starts empty every step,
+    // src/schedule.cpp:208-232), so a batch of steps is spread over host threads: the reference's `-S` /
+    // scheduler_threads. 0 = one per host core.
+    std::vector<std::unique_ptr<sfe::DetailedScheduler>> scheduler_pool;
+    uint32_t scheduler_threads{0};
     long next_mid{0};                                  // total_messages_sent (src/chip.hpp:126): ids of traced messages
     // Poisson inputs: "input" units this process had created before this chip (InputModel::instance_counter is a
     // process-wide static, src/models.hpp:366) and the host generators of this chip's Poisson units
@@ -99,6 +104,43 @@ template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f(
 
 std::atomic<uint32_t> g_input_units_created{0};
 
+// sim_time of `steps` consecutive timesteps from their status bytes, spread over the chip's scheduler threads
+void schedule_steps(sfe_chip *c, const uint8_t *status, const int64_t steps, double *sim_time)
+{
+    const size_t n = c->tables.view.n_neurons;
+    uint32_t threads = c->scheduler_threads != 0 ? c->scheduler_threads : std::max(1u, std::thread::hardware_concurrency());
+    threads = static_cast<uint32_t>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(threads, 64), steps / 4)));
+    while (c->scheduler_pool.size() < threads)
+        c->scheduler_pool.push_back(std::make_unique<sfe::DetailedScheduler>(c->tables.view));
+    if (threads == 1)
+    {
+        for (int64_t s = 0; s < steps; ++s) sim_time[s] = c->scheduler_pool[0]->schedule_step(status + static_cast<size_t>(s) * n);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    std::exception_ptr failure;
+    std::mutex mu;
+    auto worker = [&](sfe::DetailedScheduler *sched) {
+        try
+        {
+            // small blocks of consecutive steps, handed out dynamically (steps differ in their message counts)
+            for (int64_t s0 = next.fetch_add(8); s0 < steps; s0 = next.fetch_add(8))
+                for (int64_t s = s0; s < std::min<int64_t>(steps, s0 + 8); ++s)
+                    sim_time[s] = sched->schedule_step(status + static_cast<size_t>(s) * n);
+        }
+        catch (...)
+        {
+            const std::lock_guard<std::mutex> lock(mu);
+            if (!failure) failure = std::current_exception();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t w = 1; w < threads; ++w) pool.emplace_back(worker, c->scheduler_pool[w].get());
+    worker(c->scheduler_pool[0].get());
+    for (std::thread &th : pool) th.join();
+    if (failure) std::rethrow_exception(failure);
+}
+
 int flush_bias(sfe_chip *c)
 {
     if (!c->bias_dirty || c->engine == nullptr) return 0;
@@ -113,6 +155,9 @@ int attach_engine(sfe_chip *c)
         sfe_engine_destroy(c->engine);
         c->engine = nullptr;
     }
+    // the host schedulers cache per-axon tables of the previous network
+    c->scheduler.reset();
+    c->scheduler_pool.clear();
     // (a second load() restarts the Poisson streams; the reference's generators would run on)
     sfe_poisson_destroy(c->poisson);
     c->poisson = nullptr;
@@ -310,7 +355,6 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                     // Poisson inputs: the host draws the chunk's random spikes with the reference's generator
                     // (poisson.cpp) and uploads them as an overlay before the chunk is enqueued.
                     if (detailed && c->world > 1) throw std::runtime_error("detailed timing is not available on a partitioned chip");
-                    if (detailed && !c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
                     const size_t n = c->tables.view.n_neurons;
                     const size_t words = (n + 31) / 32;
                     const uint32_t cols = c->poisson != nullptr ? sfe_poisson_cols(c->poisson) : 0u;
@@ -319,6 +363,7 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                     if (cols > 0) batch_cap = std::min<int64_t>(batch_cap, (32ll << 20) / static_cast<int64_t>(cols));
                     batch_cap = std::max<int64_t>(1, batch_cap);
                     std::vector<uint8_t> status, overlay;
+                    std::vector<double> sched_time;
                     std::vector<sfe_step_record> recs;
                     std::memset(&rd, 0, sizeof(rd));
                     double sched_s = 0.0;
@@ -357,10 +402,15 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                         if (sfe_engine_run(c->engine, batch, &sub, &part) != 0) return -1;
                         if (done == 0) rd.timestep_start = part.timestep_start;
                         const auto s0 = std::chrono::steady_clock::now();
+                        if (detailed)
+                        {
+                            sched_time.resize(static_cast<size_t>(batch));
+                            schedule_steps(c, status.data(), batch, sched_time.data());
+                        }
                         for (int64_t b = 0; b < batch; ++b)
                         {
                             sfe_step_record &r = recs[static_cast<size_t>(b)];
-                            if (detailed) r.sim_time = c->scheduler->schedule_step(status.data() + static_cast<size_t>(b) * n);
+                            if (detailed) r.sim_time = sched_time[static_cast<size_t>(b)];
                             // update_run_data  src/chip.cpp:462-475
                             rd.total_energy += r.total_energy;
                             rd.synapse_energy += r.synapse_energy;
@@ -467,6 +517,12 @@ extern "C" int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timeste
         return sfe_chip_sim(chips[k], timesteps, timing_model, reqs != nullptr ? &reqs[k] : nullptr,
                 out != nullptr ? &out[k] : nullptr);
     });
+}
+
+extern "C" int sfe_chip_set_scheduler_threads(sfe_chip *c, uint32_t threads)
+{
+    c->scheduler_threads = threads;
+    return 0;
 }
 
 extern "C" void sfe_chip_request_stop(sfe_chip *c)
@@ -714,10 +770,7 @@ extern "C" int sfe_chip_schedule_detailed(sfe_chip *c, const uint8_t *status, in
     return guarded(
             [&]() -> int {
                 if (!c->loaded) throw std::runtime_error("sfe_chip_schedule_detailed: no network loaded");
-                if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
-                const size_t n = c->tables.view.n_neurons;
-                for (int64_t s = 0; s < timesteps; ++s)
-                    sim_time[s] = c->scheduler->schedule_step(status + static_cast<size_t>(s) * n);
+                schedule_steps(c, status, timesteps, sim_time);
                 return 0;
             },
             -1);

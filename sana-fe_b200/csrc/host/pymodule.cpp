@@ -268,12 +268,15 @@ public:
     }
     double get_power() { return sfe_chip_get_power(h_); }
 
-    py::dict sim(long timesteps, const std::string &timing_model, int, int, const py::object &spike_trace,
+    py::dict sim(long timesteps, const std::string &timing_model, int /*processing_threads: the device has its own*/,
+            int scheduler_threads, const py::object &spike_trace,
             const py::object &potential_trace, const py::object &neuron_trace, const py::object &perf_trace,
             const py::object &message_trace, bool write_trace_headers)
     {
         const sfe_tables *t = sfe_chip_tables(h_);
         if (t == nullptr) throw std::runtime_error("no network loaded");
+        // host threads of the detailed timing model (src/pymodule.cpp:549-560); 0 = one per host core
+        sfe_chip_set_scheduler_threads(h_, scheduler_threads > 0 ? static_cast<uint32_t>(scheduler_threads) : 0u);
         const size_t words = (static_cast<size_t>(t->n_neurons) + 31) / 32;
         const bool want_spikes = !spike_trace.is_none(), want_pot = !potential_trace.is_none(), want_perf = !perf_trace.is_none();
         const bool want_msgs = !message_trace.is_none();

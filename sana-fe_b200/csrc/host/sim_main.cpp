@@ -31,6 +31,7 @@ struct Flags
     bool record_neuron_state{false}, use_netlist{false};
     int timing_model{SFE_TIMING_DETAILED}; // the reference's default (src/arg_parsing.hpp)
     int consumed{0};
+    int scheduler_threads{0}; // -S: host threads of the detailed timing model (0 = one per host core)
 };
 
 int parse_timing(const std::string &name)
@@ -71,7 +72,12 @@ int main(int argc, char *argv[])
         case 'v': flags.record_potentials = true; break;
         case 'x': flags.record_neuron_state = true; break;
         case 'N': used = 2; std::printf("Processing threads: the device engine ignores -N\n"); break;
-        case 'S': used = 2; std::printf("Scheduler threads: the host scheduler is single-threaded, -S ignored\n"); break;
+        case 'S':
+            try { flags.scheduler_threads = std::stoi(args.at(idx + 1)); }
+            catch (const std::exception &) { std::fprintf(stderr, "Error: invalid scheduler thread count: %s\n", args.at(idx + 1).c_str()); return 1; }
+            used = 2;
+            std::printf("Scheduler threads: %d\n", flags.scheduler_threads);
+            break;
         default: std::printf("Error: Flag %c not recognized.\n", args[idx][1]); break;
         }
         idx += static_cast<size_t>(used);
@@ -97,6 +103,7 @@ int main(int argc, char *argv[])
     sfe_chip *chip = sfe_chip_create(arch, 0);
     if (chip == nullptr || sfe_chip_load(chip, net) != 0) fail(sfe_last_error());
     const sfe_tables *t = sfe_chip_tables(chip);
+    sfe_chip_set_scheduler_threads(chip, flags.scheduler_threads > 0 ? static_cast<uint32_t>(flags.scheduler_threads) : 0u);
 
     // src/main.cpp:63-67: every trace hangs off -s
     const bool traces = flags.record_spikes;

@@ -200,6 +200,7 @@ def lib():
         "sfe_chip_load_synthetic": (C.c_int, [vp, C.POINTER(SynthSpec), C.c_int]),
         "sfe_chip_sim": (C.c_int, [vp, i64, C.c_int, C.POINTER(TraceRequest), C.POINTER(RunData)]),
         "sfe_chip_schedule_detailed": (C.c_int, [vp, vp, i64, vp]),
+        "sfe_chip_set_scheduler_threads": (C.c_int, [vp, u32]),
         "sfe_chip_reset": (C.c_int, [vp]), "sfe_chip_get_power": (dbl, [vp]),
         "sfe_chip_tables": (C.POINTER(Tables), [vp]), "sfe_chip_engine": (vp, [vp]),
         "sfe_chip_neuron_index": (i64, [vp, cstr, u64]),

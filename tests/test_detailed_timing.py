@@ -35,3 +35,20 @@ def test_engine_detailed_timing(name):
     assert rel_err(rd.sim_time, g["detailed"]["sim_time"]) <= 1e-9
     assert rd.neurons_fired == g["summary"]["neurons_fired"] and rd.spikes == g["summary"]["spikes"]
     assert rd.scheduler_wall_time > 0.0
+
+
+def test_scheduler_threads_do_not_change_results():
+    """Timesteps are scheduled independently (the reference's scheduler threads, `-S`): any number of host threads
+    gives bit-identical per-step sim_time."""
+    chip = load_chip("synth_delay", device=-1)
+    steps = 80
+    rd, out = Oracle(chip).run(steps, status=True)
+    status = np.ascontiguousarray(out["status"])
+    results = []
+    for threads in (1, 3, 8, 0):
+        assert sfe.lib().sfe_chip_set_scheduler_threads(chip._h, threads) == 0
+        sim_time = np.zeros(steps)
+        assert sfe.lib().sfe_chip_schedule_detailed(chip._h, status.ctypes.data, steps, sim_time.ctypes.data) == 0
+        results.append(sim_time)
+    assert all(np.array_equal(results[0], r) for r in results[1:])
+    assert rel_err(results[0], golden("synth_delay")["detailed"]["per_step_sim_time"][:steps]) <= 1e-9
