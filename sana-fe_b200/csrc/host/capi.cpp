@@ -5,6 +5,7 @@
 // runs timesteps and returns RunData; state persists across sim() calls and
 // reset() zeroes model state without rewinding the timestep counter.
 #include <atomic>
+#include <charconv>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -62,6 +63,13 @@ struct sfe_chip
     // per-neuron bias patches (MappedNeuron.set_attributes in a per-frame loop, scripts/tcad2025/dvs_gesture.py) are
     // collected in the host table and uploaded as ONE vector before the next step instead of one copy per neuron
     bool bias_dirty{false};
+    // sfe_chip_format_messages: text of the last sizing call (see there)
+    std::string sized_messages;
+    bool sized_messages_valid{false};
+    const uint8_t *sized_status{nullptr};
+    int64_t sized_steps{0}, sized_start{0};
+    int sized_timing{0};
+    long sized_first_mid{0}, sized_next_mid{0};
     explicit sfe_chip(const sfe::Architecture &a, int dev) : arch(a), device(dev) {}
 };
 
@@ -687,7 +695,37 @@ extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, i
                 if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
                 const sfe::HostTables &t = c->tables;
                 const size_t n = t.view.n_neurons;
-                std::ostringstream out;
+                // The sizing call (buf == NULL) and the call that fetches the text do the same work: keep the text of
+                // the sizing call and hand it out if the very next call asks for the same rows.
+                const bool same_as_sized = c->sized_messages_valid && c->sized_status == status && c->sized_steps == timesteps &&
+                        c->sized_start == timestep_start && c->sized_timing == timing_model && c->sized_first_mid == c->next_mid;
+                if (buf != nullptr && cap > 0 && same_as_sized)
+                {
+                    const std::string &text = c->sized_messages;
+                    const size_t k = std::min(cap - 1, text.size());
+                    std::memcpy(buf, text.data(), k);
+                    buf[k] = '\0';
+                    c->next_mid = c->sized_next_mid;
+                    c->sized_messages_valid = false;
+                    const size_t size = text.size();
+                    c->sized_messages.clear();
+                    c->sized_messages.shrink_to_fit();
+                    return size;
+                }
+                c->sized_messages_valid = false;
+                std::string out;
+                // numbers exactly as an ostream with default settings prints them (src/chip.cpp:1731-1764 streams the
+                // fields with operator<<): integers in decimal, doubles as %g with 6 significant digits
+                auto put_int = [&out](const long long v) {
+                    char tmp[24];
+                    const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);
+                    out.append(tmp, r.ptr);
+                };
+                auto put_double = [&out](const double v) {
+                    char tmp[40];
+                    const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, 6);
+                    out.append(tmp, r.ptr);
+                };
                 std::vector<sfe::MessageRecord> recs;
                 const long first_mid = c->next_mid;
                 for (int64_t s = 0; s < timesteps; ++s)
@@ -698,23 +736,56 @@ extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, i
                     for (const sfe::MessageRecord &m : recs)
                     {
                         const sfe::HostTables::NeuronName &nm = t.names[m.src_neuron];
-                        out << (timestep_start + s) << "," << m.mid << "," << t.group_names[nm.group] << "." << nm.offset << ","
-                            << t.core_names[m.src_core] << ",";
-                        if (m.placeholder) out << "x.x,";
-                        else out << t.core_names[m.dest_core] << ",";
-                        out << m.hops << "," << m.spikes << "," << m.sent << "," << m.received << "," << m.processed << ","
-                            << m.generation_delay << "," << m.processing_delay << "," << m.network_delay << ","
-                            << m.blocking_delay << "," << m.min_hop_delay << "," << m.messages_along_route << "\n";
+                        put_int(timestep_start + s);
+                        out += ',';
+                        put_int(m.mid);
+                        out += ',';
+                        out += t.group_names[nm.group];
+                        out += '.';
+                        put_int(nm.offset);
+                        out += ',';
+                        out += t.core_names[m.src_core];
+                        out += ',';
+                        if (m.placeholder) out += "x.x,";
+                        else
+                        {
+                            out += t.core_names[m.dest_core];
+                            out += ',';
+                        }
+                        put_int(m.hops);
+                        out += ',';
+                        put_int(m.spikes);
+                        for (const double v : {m.sent, m.received, m.processed, m.generation_delay, m.processing_delay,
+                                     m.network_delay, m.blocking_delay, m.min_hop_delay, m.messages_along_route})
+                        {
+                            out += ',';
+                            put_double(v);
+                        }
+                        out += '\n';
                     }
                 }
-                const std::string text = out.str();
+                const std::string &text = out;
                 if (buf != nullptr && cap > 0)
                 {
                     const size_t k = std::min(cap - 1, text.size());
                     std::memcpy(buf, text.data(), k);
                     buf[k] = '\0';
                 }
-                else c->next_mid = first_mid; // sizing call: the ids are not consumed
+                else
+                {
+                    // sizing call: the ids are not consumed; remember the text for the call that fetches it
+                    c->sized_next_mid = c->next_mid;
+                    c->next_mid = first_mid;
+                    c->sized_status = status;
+                    c->sized_steps = timesteps;
+                    c->sized_start = timestep_start;
+                    c->sized_timing = timing_model;
+                    c->sized_first_mid = first_mid;
+                    const size_t size = out.size();
+                    c->sized_messages = std::move(out);
+                    c->sized_messages_valid = true;
+                    return size;
+                }
                 return text.size();
             },
             static_cast<size_t>(0));
