@@ -7,17 +7,19 @@
  * Parity status: PINNED. This restatement is checked against outputs of the
  * reference itself (oracle/_ref/sanafe_ref, the unmodified reference engine
  * compiled from /root/reference/src) on the fixtures under tests/golden/ —
- * spike rasters, per-step counters and potentials bit-exact, energies/latencies
- * to 1e-12 relative (tests/test_oracle_vs_reference.py).
+ * spike rasters, per-step counters, potentials and model-defined traces bit-exact,
+ * energies/latencies to 1e-12 relative (tests/test_oracle_vs_reference.py, 12 cases) —
+ * and against the expectations of the reference's own per-model unit tests
+ * (tests/test_reference_unit_vectors.py).
  *
  * It walks the same lowered tables (include/sanafe_b200.h) as the CUDA engine,
  * strictly sequentially and in the reference's own order, so every floating-point
  * sum that decides a spike is formed exactly as the reference forms it:
  *   neuron phase    src/chip.cpp:624-654, 710-736, 802-834
  *   message phase   src/chip.cpp:656-764, 1127-1169
- *   soma models     src/models.cpp:441-567 (LIF), 724-830 (TrueNorth), 863-903 (input),
- *                   plugins/hodgkin_huxley.cpp:116-170
- *   dendrites       src/models.cpp:71-94 (accumulator), 96-131 (accumulator_with_delay)
+ *   soma models     src/models.cpp:441-567 (LIF, incl. the file noise stream :589-650), 724-830 (TrueNorth),
+ *                   863-903 (input: spike trains, rate, Poisson with an own MT19937), plugins/hodgkin_huxley.cpp:116-170
+ *   dendrites       src/models.cpp:71-94 (accumulator), 96-131 (accumulator_with_delay), 167-259 (taps)
  *   default costs   src/pipeline.hpp:511-731
  *   energy/counters src/chip.cpp:1028-1051, 1171-1261
  *   simple timing   src/schedule.cpp:61-102
