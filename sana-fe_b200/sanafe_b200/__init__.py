@@ -252,7 +252,10 @@ class Architecture:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().sfe_arch_free(self._h)
+            try:
+                lib().sfe_arch_free(self._h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown: the module may already be torn down
+                pass
             self._h = None
 
 
@@ -262,7 +265,10 @@ class Network:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().sfe_net_free(self._h)
+            try:
+                lib().sfe_net_free(self._h)
+            except Exception:  # noqa: BLE001
+                pass
             self._h = None
 
 
@@ -295,7 +301,10 @@ class SpikingChip:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().sfe_chip_destroy(self._h)
+            try:
+                lib().sfe_chip_destroy(self._h)
+            except Exception:  # noqa: BLE001
+                pass
             self._h = None
 
     def set_partition(self, rank, world):

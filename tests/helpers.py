@@ -200,11 +200,27 @@ def golden_spikes(name):
         return f.read()
 
 
+_description_cache = {}
+
+
+def golden_description(name):
+    """(Architecture, Network) of a golden case, parsed once per process: descriptions are only read by load()
+    (the DVS net alone takes seconds to parse and several tests put it on more than one chip)."""
+    if name not in _description_cache:
+        cwd = os.getcwd()
+        os.chdir(ROOT)  # plugin / noise-file paths inside flat files are relative to the repo root
+        try:
+            _description_cache[name] = sfe.load_flat(golden_flat(name))
+        finally:
+            os.chdir(cwd)
+    return _description_cache[name]
+
+
 def load_chip(name, device):
     cwd = os.getcwd()
     os.chdir(ROOT)  # plugin paths inside flat files are relative to the repo root
     try:
-        arch, net = sfe.load_flat(golden_flat(name))
+        arch, net = golden_description(name)
         chip = sfe.SpikingChip(arch, device=device)
         chip.set_input_seed_base(0)  # the goldens come from a fresh reference process each
         chip.load(net)

@@ -104,11 +104,11 @@ def test_partitioned_engines_match_reference(name, world):
 
     def make(device, rank, w):
         import os
-        from helpers import ROOT, golden_flat
+        from helpers import ROOT, golden_description
         cwd = os.getcwd()
         os.chdir(ROOT)
         try:
-            arch, net = sfe.load_flat(golden_flat(name))
+            arch, net = golden_description(name)
             chip = sfe.SpikingChip(arch, device=device)
             chip.set_partition(rank, w)
             chip.load(net)
