@@ -112,17 +112,17 @@ template <typename F> auto guarded(F &&f, decltype(f()) on_error) -> decltype(f(
 
 std::atomic<uint32_t> g_input_units_created{0};
 
-// sim_time of `steps` consecutive timesteps from their status bytes, spread over the chip's scheduler threads
-void schedule_steps(sfe_chip *c, const uint8_t *status, const int64_t steps, double *sim_time)
+// Runs job(scheduler, s) for s in [0, steps) on the chip's scheduler threads (each thread owns a scheduler);
+// timesteps are independent for the timing model (the NoC state starts empty every step).
+template <typename Job> void parallel_steps(sfe_chip *c, const int64_t steps, Job &&job)
 {
-    const size_t n = c->tables.view.n_neurons;
     uint32_t threads = c->scheduler_threads != 0 ? c->scheduler_threads : std::max(1u, std::thread::hardware_concurrency());
     threads = static_cast<uint32_t>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(threads, 64), steps / 4)));
     while (c->scheduler_pool.size() < threads)
         c->scheduler_pool.push_back(std::make_unique<sfe::DetailedScheduler>(c->tables.view));
     if (threads == 1)
     {
-        for (int64_t s = 0; s < steps; ++s) sim_time[s] = c->scheduler_pool[0]->schedule_step(status + static_cast<size_t>(s) * n);
+        for (int64_t s = 0; s < steps; ++s) job(*c->scheduler_pool[0], s);
         return;
     }
     std::atomic<int64_t> next{0};
@@ -133,8 +133,7 @@ void schedule_steps(sfe_chip *c, const uint8_t *status, const int64_t steps, dou
         {
             // small blocks of consecutive steps, handed out dynamically (steps differ in their message counts)
             for (int64_t s0 = next.fetch_add(8); s0 < steps; s0 = next.fetch_add(8))
-                for (int64_t s = s0; s < std::min<int64_t>(steps, s0 + 8); ++s)
-                    sim_time[s] = sched->schedule_step(status + static_cast<size_t>(s) * n);
+                for (int64_t s = s0; s < std::min<int64_t>(steps, s0 + 8); ++s) job(*sched, s);
         }
         catch (...)
         {
@@ -147,6 +146,15 @@ void schedule_steps(sfe_chip *c, const uint8_t *status, const int64_t steps, dou
     worker(c->scheduler_pool[0].get());
     for (std::thread &th : pool) th.join();
     if (failure) std::rethrow_exception(failure);
+}
+
+// sim_time of `steps` consecutive timesteps from their status bytes
+void schedule_steps(sfe_chip *c, const uint8_t *status, const int64_t steps, double *sim_time)
+{
+    const size_t n = c->tables.view.n_neurons;
+    parallel_steps(c, steps, [&](sfe::DetailedScheduler &sched, const int64_t s) {
+        sim_time[s] = sched.schedule_step(status + static_cast<size_t>(s) * n);
+    });
 }
 
 int flush_bias(sfe_chip *c)
@@ -692,7 +700,6 @@ extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, i
     return guarded(
             [&]() -> size_t {
                 if (!c->loaded) throw std::runtime_error("sfe_chip_format_messages: no network loaded");
-                if (!c->scheduler) c->scheduler = std::make_unique<sfe::DetailedScheduler>(c->tables.view);
                 const sfe::HostTables &t = c->tables;
                 const size_t n = t.view.n_neurons;
                 // The sizing call (buf == NULL) and the call that fetches the text do the same work: keep the text of
@@ -713,26 +720,40 @@ extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, i
                     return size;
                 }
                 c->sized_messages_valid = false;
-                std::string out;
-                // numbers exactly as an ostream with default settings prints them (src/chip.cpp:1731-1764 streams the
-                // fields with operator<<): integers in decimal, doubles as %g with 6 significant digits
-                auto put_int = [&out](const long long v) {
-                    char tmp[24];
-                    const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);
-                    out.append(tmp, r.ptr);
-                };
-                auto put_double = [&out](const double v) {
-                    char tmp[40];
-                    const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, 6);
-                    out.append(tmp, r.ptr);
-                };
-                std::vector<sfe::MessageRecord> recs;
+                // Message ids run on from step to step (total_messages_sent, src/chip.cpp:815): the id a step starts
+                // with is known from the spikes alone (one message per axon-out of every fired neuron), so the steps
+                // can be traced and formatted independently, on the scheduler threads, and concatenated.
                 const long first_mid = c->next_mid;
+                std::vector<long> start_mid(static_cast<size_t>(timesteps) + 1, first_mid);
                 for (int64_t s = 0; s < timesteps; ++s)
                 {
+                    const uint8_t *st = status + static_cast<size_t>(s) * n;
+                    long messages = 0;
+                    for (size_t i = 0; i < n; ++i)
+                        if (st[i] == SFE_STATUS_FIRED) messages += t.view.axon_out_begin[i + 1] - t.view.axon_out_begin[i];
+                    start_mid[static_cast<size_t>(s) + 1] = start_mid[static_cast<size_t>(s)] + messages;
+                }
+                std::vector<std::string> texts(static_cast<size_t>(timesteps));
+                parallel_steps(c, timesteps, [&](sfe::DetailedScheduler &sched, const int64_t s) {
+                    std::string &out = texts[static_cast<size_t>(s)];
+                    // numbers exactly as an ostream with default settings prints them (src/chip.cpp:1731-1764 streams
+                    // the fields with operator<<): integers in decimal, doubles as %g with 6 significant digits
+                    auto put_int = [&out](const long long v) {
+                        char tmp[24];
+                        const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v);
+                        out.append(tmp, r.ptr);
+                    };
+                    auto put_double = [&out](const double v) {
+                        char tmp[40];
+                        const auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, 6);
+                        out.append(tmp, r.ptr);
+                    };
+                    thread_local std::vector<sfe::MessageRecord> recs; // capacity kept from step to step
                     recs.clear();
-                    c->scheduler->trace_step(status + static_cast<size_t>(s) * n, timing_model == SFE_TIMING_DETAILED, recs,
-                            c->next_mid);
+                    long mid = start_mid[static_cast<size_t>(s)];
+                    sched.trace_step(status + static_cast<size_t>(s) * n, timing_model == SFE_TIMING_DETAILED, recs, mid);
+                    if (mid != start_mid[static_cast<size_t>(s) + 1]) throw std::logic_error("message count of a step disagrees with its spikes");
+                    out.reserve(recs.size() * 128);
                     for (const sfe::MessageRecord &m : recs)
                     {
                         const sfe::HostTables::NeuronName &nm = t.names[m.src_neuron];
@@ -763,6 +784,14 @@ extern "C" size_t sfe_chip_format_messages(sfe_chip *c, const uint8_t *status, i
                         }
                         out += '\n';
                     }
+                });
+                c->next_mid = start_mid[static_cast<size_t>(timesteps)];
+                std::string out;
+                {
+                    size_t total = 0;
+                    for (const std::string &x : texts) total += x.size();
+                    out.reserve(total);
+                    for (const std::string &x : texts) out += x;
                 }
                 const std::string &text = out;
                 if (buf != nullptr && cap > 0)

@@ -133,6 +133,8 @@ struct DetailedScheduler::Scratch // reused from step to step
     std::vector<uint32_t> core_begin, head;
     std::vector<InFlight> in_flight, due;
     std::vector<NeuronLatency> neuron_latency;
+    std::vector<MessageRecord> recs;
+    std::vector<const MessageRecord *> order;
     uint32_t n_classes_seen{0};
     Noc noc;
 };
@@ -168,7 +170,10 @@ double DetailedScheduler::run_step(
 {
     const sfe_tables &t = t_;
     const double ninf = -std::numeric_limits<double>::infinity();
-    std::vector<MessageRecord> recs; // creation order = cores ascending, in-core send order
+    // creation order = cores ascending, in-core send order (kept in the scratch: a few hundred KB per step that
+    // would otherwise be mapped and unmapped every step, which serialises the scheduler threads in the kernel)
+    std::vector<MessageRecord> &recs = scratch_->recs;
+    recs.clear();
     auto new_record = [&](const Msg &m, const uint32_t src_neuron, const uint32_t spikes) -> uint32_t {
         MessageRecord r;
         r.placeholder = m.placeholder;
@@ -271,8 +276,10 @@ double DetailedScheduler::run_step(
         if (trace == nullptr) return;
         // sim_sort_and_record_messages: the same std::sort on the same sequence with the same
         // comparator (placeholders compare equal, so their order is whatever the sort leaves)
-        std::vector<const MessageRecord *> order;
+        std::vector<const MessageRecord *> &order = scratch_->order;
+        order.clear();
         order.reserve(recs.size());
+        trace->reserve(trace->size() + recs.size());
         for (const MessageRecord &r : recs) order.push_back(&r);
         std::sort(order.begin(), order.end(), [](const MessageRecord *a, const MessageRecord *b) {
             if (a->placeholder && b->placeholder) return a->mid < b->mid; // CompareMessagesByID  src/message.cpp:70-91
