@@ -354,9 +354,10 @@ double DetailedScheduler::run_step(
                 due.push_back(in_flight.back());
                 in_flight.pop_back();
             }
-            std::sort(due.begin(), due.end(), [](const InFlight &a, const InFlight &b) {
-                return a.dest_core != b.dest_core ? a.dest_core < b.dest_core : a.seq < b.seq;
-            });
+            if (due.size() > 1)
+                std::sort(due.begin(), due.end(), [](const InFlight &a, const InFlight &b) {
+                    return a.dest_core != b.dest_core ? a.dest_core < b.dest_core : a.seq < b.seq;
+                });
             for (const InFlight &x : due)
             {
                 msgs[x.msg].in_noc = false;
