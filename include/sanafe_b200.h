@@ -188,8 +188,8 @@ typedef struct sfe_noise_desc
     uint32_t share_count, share_rank;
 } sfe_noise_desc;
 
-/* "taps" dendrite (MultiTapModel1D, src/models.cpp:167-259): a 1-D RC line of n_taps compartments, ONE neuron per
- * unit. taps_values[const_off .. +n_taps) are the time constants, the next n_taps-1 values the space constants.
+/* "taps" dendrite (MultiTapModel1D, src/models.cpp:167-259): a 1-D RC line of n_taps compartments, ONE line per
+ * hardware unit whatever neuron is updated (neurons mapped to the same unit share their descriptor). taps_values[const_off .. +n_taps) are the time constants, the next n_taps-1 values the space constants.
  * A synapse names its tap in the delay field of syn_meta. */
 typedef struct sfe_taps_desc
 {

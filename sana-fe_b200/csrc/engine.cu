@@ -111,6 +111,8 @@ struct TapsSyn
     double weight;
     uint32_t src_bit; // raster bit of the source neuron
     uint32_t tap;
+    uint32_t post;    // device index of the neuron the synapse belongs to (neurons of a unit share its line)
+    uint32_t pad;
 };
 
 // Poisson inputs drawn on the device, EXPERIMENTAL (SFE_DEVICE_POISSON=1): one MT19937 per Poisson input unit
@@ -227,8 +229,8 @@ struct DevState
     double *din64;         // ORDERED: value
     double *tap_v, *tap_next; // "taps": voltages of every line, scratch of the same shape
     long long *tap_steps;     // [n_taps_units] timesteps the line has been advanced to
-    double *tap_buf;          // [n_taps_units] tap 0 after the last event of the step
-    uint32_t *tap_has;        // [n_taps_units] the soma has an input waiting
+    double *tap_buf;          // [n_neurons] tap 0 of the neuron's line after the last event that targeted the neuron
+    uint32_t *tap_has;        // [n_neurons] the soma has an input waiting
     double *hh;            // [5][n_hh]: V, m, n, h, I
     uint32_t n_hh;
     StatsN *stats_n;
@@ -872,12 +874,11 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             {
                 // the line's tap 0 after the last event of the previous step (taps_kernel); the accumulator cell
                 // the message phase filled for this neuron is ignored
-                const uint32_t unit = t.neuron_taps[i];
-                if (s.tap_has[unit] != 0u)
+                if (s.tap_has[i] != 0u)
                 {
                     has_in = true;
-                    in = s.tap_buf[unit];
-                    s.tap_has[unit] = 0u;
+                    in = s.tap_buf[i];
+                    s.tap_has[i] = 0u;
                 }
             }
             else if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR)
@@ -1066,7 +1067,6 @@ __global__ void taps_kernel(const DevTables t, const DevState s)
     double *v = s.tap_v + d.state_off, *next = s.tap_next + d.state_off;
     const double *tc = t.taps_values + d.const_off, *sc = tc + n;
     long long steps = s.tap_steps[u];
-    bool any = false;
     for (uint32_t e = d.syn_begin; e < d.syn_begin + d.syn_count; ++e)
     {
         const TapsSyn y = t.taps_syn[e];
@@ -1093,14 +1093,11 @@ __global__ void taps_kernel(const DevTables t, const DevState s)
             for (uint32_t k = 0; k < n; ++k) v[k] = next[k];
         }
         v[y.tap] = v[y.tap] + y.weight;
-        any = true;
+        // what the event returns is buffered for ITS neuron (src/chip.cpp:738-764: timestep_buffer[post] = result)
+        s.tap_buf[y.post] = v[0];
+        s.tap_has[y.post] = 1u;
     }
     s.tap_steps[u] = steps;
-    if (any)
-    {
-        s.tap_buf[u] = v[0];
-        s.tap_has[u] = 1u;
-    }
 }
 
 // Multi-GPU: a rank sees the spikes of the whole chip as a fired-bit raster (SURVEY 8e:
@@ -2214,7 +2211,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                     const uint32_t post = cd.neuron_begin + SFE_SYN_POST(tb->syn_meta[at]);
                     const uint32_t unit = tb->neuron_taps[post];
                     if (unit == 0xFFFFFFFFu) continue;
-                    incoming[unit].push_back({tb->syn_weight[at], raster_bit[src], SFE_SYN_TAP(tb->syn_meta[at])});
+                    incoming[unit].push_back({tb->syn_weight[at], raster_bit[src], SFE_SYN_TAP(tb->syn_meta[at]), post, 0u});
                 }
             }
         }
@@ -2246,8 +2243,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         if (e->alloc(&e->s.tap_v, cells) != 0) return -1;
         if (e->alloc(&e->s.tap_next, cells) != 0) return -1;
         if (e->alloc(&e->s.tap_steps, tb->n_taps_units) != 0) return -1;
-        if (e->alloc(&e->s.tap_buf, tb->n_taps_units) != 0) return -1;
-        if (e->alloc(&e->s.tap_has, tb->n_taps_units) != 0) return -1;
+        if (e->alloc(&e->s.tap_buf, tb->n_neurons) != 0) return -1;
+        if (e->alloc(&e->s.tap_has, tb->n_neurons) != 0) return -1;
         e->exotic = true; // the neuron phase reads the lines' outputs in its `exotic` instantiation
     }
     e->n_poisson_cols = tb->n_poisson_cols;
@@ -3182,7 +3179,7 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
     {
         // MultiTapModel1D::reset  src/models.cpp:340-348: voltages only (the lines' step counters run on)
         SFE_CUDA(cudaMemsetAsync(e->s.tap_v, 0, std::max<size_t>(e->tap_cells, 1) * sizeof(double), e->stream));
-        SFE_CUDA(cudaMemsetAsync(e->s.tap_has, 0, e->n_taps_units * sizeof(uint32_t), e->stream));
+        SFE_CUDA(cudaMemsetAsync(e->s.tap_has, 0, e->n_neurons * sizeof(uint32_t), e->stream));
     }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;

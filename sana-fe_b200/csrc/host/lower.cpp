@@ -891,25 +891,31 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
             }
         }
     }
-    // "taps" dendrites keep ONE state per hardware unit: one neuron per unit
+    // "taps" dendrites keep ONE line of state per hardware unit, whatever neuron is being updated (SURVEY Appendix
+    // B-6; the shipped snn/dendrite.yaml maps its input neurons to the same unit as the neuron with the line): one
+    // descriptor per unit, shared by the neurons mapped to it
     for (size_t c = 0; c < lcores.size(); ++c)
+    {
+        std::map<UnitKey, uint32_t> unit_index;
         for (size_t i = 0; i < lcores[c].neurons.size(); ++i)
         {
             const LNeuron &ln = lcores[c].neurons[i];
             const UnitState &dend = *ln.dend_unit;
             if (dend.model != UnitModel::taps) continue;
-            if (dend.neuron_count != 1)
-                throw std::runtime_error("a 'taps' dendrite keeps one line of state per hardware unit "
-                                         "(src/models.hpp:186-193); map one neuron per unit");
             if (out.neuron_taps.empty()) out.neuron_taps.assign(n_neurons, 0xFFFFFFFFu);
-            sfe_taps_desc d{};
-            d.n_taps = static_cast<uint32_t>(dend.n_taps);
-            d.const_off = static_cast<uint32_t>(out.taps_values.size());
-            for (size_t k = 0; k < dend.n_taps; ++k) out.taps_values.push_back(dend.time_constants.at(k));
-            for (size_t k = 0; k + 1 < dend.n_taps; ++k) out.taps_values.push_back(dend.space_constants.at(k));
-            out.neuron_taps[out.cores[c].neuron_begin + i] = static_cast<uint32_t>(out.taps.size());
-            out.taps.push_back(d);
+            auto [it, fresh] = unit_index.try_emplace(ln.dend, static_cast<uint32_t>(out.taps.size()));
+            if (fresh)
+            {
+                sfe_taps_desc d{};
+                d.n_taps = static_cast<uint32_t>(dend.n_taps);
+                d.const_off = static_cast<uint32_t>(out.taps_values.size());
+                for (size_t k = 0; k < dend.n_taps; ++k) out.taps_values.push_back(dend.time_constants.at(k));
+                for (size_t k = 0; k + 1 < dend.n_taps; ++k) out.taps_values.push_back(dend.space_constants.at(k));
+                out.taps.push_back(d);
+            }
+            out.neuron_taps[out.cores[c].neuron_begin + i] = it->second;
         }
+    }
     // potential probes in trace order: lexicographic group, offset (src/chip.cpp:1632-1662)
     for (size_t gi = 0; gi < groups.size(); ++gi)
         for (const Neuron &n : groups[gi]->neurons)
