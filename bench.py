@@ -306,7 +306,7 @@ def main():
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "note": "C-ABI calls with pinned host buffers; step t+1's bias upload overlaps step t (double-buffered set_bias)"}
 
-    cpu = None if args.no_cpu_baseline else run_reference_sample(20, 1)
+    cpu = None if args.no_cpu_baseline else run_reference_sample(100, 1)  # ~1 s timed; loading its 8 M synapses dominates
     dse = None if args.no_dse else dse_side_measurement()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
