@@ -73,15 +73,16 @@ enum
 {
     SFE_DEND_ACCUMULATOR = 0,      /* src/models.cpp:71-94  */
     SFE_DEND_ACCUMULATOR_DELAY = 1,/* src/models.cpp:96-131 */
-    SFE_DEND_TAPS = 2              /* "taps" MultiTapModel1D  src/models.cpp:167-259 (lowered and run by the CPU
-                                    * restatement; the device engine refuses it for now) */
+    SFE_DEND_TAPS = 2              /* "taps" MultiTapModel1D  src/models.cpp:167-259 */
 };
 /* how one core's message phase accumulates synaptic charge */
 enum
 {
     SFE_ACC_PACKED32 = 0, /* exact fixed point: 20-bit sum + 12-bit count in one u32 smem atomic */
     SFE_ACC_DUAL32 = 1,   /* exact fixed point: int32 sum + u32 count, two smem atomics */
-    SFE_ACC_ORDERED = 2   /* sequential fp64 adds in message arrival order (any weights) */
+    SFE_ACC_ORDERED = 2,  /* sequential fp64 adds in message arrival order (any weights) */
+    SFE_ACC_PACKED17 = 3  /* exact fixed point: cell = sum + count * 2^17 (|sum| < 2^16, count < 2^15): one u32 smem atomic
+                           * whose addend is a plain shift of the 4-byte synapse record (see syn_q4 in engine.cu) */
 };
 /* sfe_soma_class.flags */
 #define SFE_SOMA_FORCE_UPDATE 1u
@@ -332,8 +333,9 @@ int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_s
  * ("simulation interrupted") at its next batch boundary (at most 4096 steps); the steps done so far stay done.
  * The reference polls PyErr_CheckSignals every 100 ms inside its loop (src/pymodule.cpp:629-652). on = 0 re-arms. */
 void sfe_engine_request_stop(sfe_engine *e, int on);
-/* EXPERIMENTAL (not yet verified on hardware): the same overlay drawn on the device by one MT19937 per input unit
- * (csrc/mt19937.cuh, checked on the host against libstdc++); sfe_chip_sim uses it when SFE_DEVICE_POISSON=1. */
+/* The same overlay drawn on the device by one MT19937 per input unit (csrc/mt19937.cuh, checked on the host against
+ * libstdc++ and on a B200 against the reference's golden); sfe_chip_sim uses it unless SFE_DEVICE_POISSON=0. Do not
+ * mix host-drawn and device-drawn overlays on one engine: they are two separate streams of draws. */
 int sfe_engine_fill_input_overlay(sfe_engine *e, int64_t n_steps);
 /* Host-only source of that overlay (no device needed): one std::mt19937 per Poisson unit, seeded
  * tables->input_seed_base + unit + 1. sfe_poisson_fill writes bits[n_steps][sfe_poisson_cols] for the next

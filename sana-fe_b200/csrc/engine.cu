@@ -69,7 +69,9 @@ struct CoreDev
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
     uint32_t q4;                      // synapses of this core also exist as 4-byte records (syn_q4)
-    uint32_t active_idx, pad1;        // position in the active-core list (per-core step partials)
+    uint32_t active_idx;              // position in the active-core list (per-core step partials)
+    uint32_t acc_global;              // 1: the core's dendrite cells do not fit in shared memory - the message phase
+                                      // accumulates straight into the HBM arrays (din32 / dcnt32 / din64)
     unsigned long long syn_begin;
     double scale, inv_scale;          // 2^shift, 2^-shift
     double lat_axon_in, e_axon_in, lat_axon_out, e_axon_out;
@@ -95,7 +97,7 @@ struct StatsM // written by fanout_kernel, one per work item
 };
 
 struct SomaSegment;
-// "taps" dendrites (MultiTapModel1D, src/models.cpp:167-259), EXPERIMENTAL device path (SFE_DEVICE_TAPS=1): the
+// "taps" dendrites (MultiTapModel1D, src/models.cpp:167-259): the
 // currents of a tap line are added onto evolving fp64 state in arrival order, so each line is replayed by one
 // thread of a small kernel of its own (taps_kernel) from the step's fired raster; the message phase still does
 // the accounting of those events and the neuron phase reads the line's output instead of its accumulator cell.
@@ -115,9 +117,9 @@ struct TapsSyn
     uint32_t pad;
 };
 
-// Poisson inputs drawn on the device, EXPERIMENTAL (SFE_DEVICE_POISSON=1): one MT19937 per Poisson input unit
-// (csrc/mt19937.cuh, states interleaved), one thread per unit filling the unit's columns of the overlay for a
-// chunk of timesteps. The default path draws on the host with libstdc++ (csrc/host/poisson.cpp).
+// Poisson inputs drawn on the device (the default; SFE_DEVICE_POISSON=0 draws on the host with libstdc++,
+// csrc/host/poisson.cpp, the cross-check): one MT19937 per Poisson input unit (csrc/mt19937.cuh, states
+// interleaved), one thread per unit filling the unit's columns of the overlay for a chunk of timesteps.
 struct PoissonUnit
 {
     double probability;
@@ -180,7 +182,7 @@ struct DevTables
     // syn_w / syn_meta; a third of their bytes per synaptic event.
     const uint32_t *syn_q4;
     const uint32_t *probes;
-    const TapsUnit *taps_units;       // "taps" dendrites (experimental)
+    const TapsUnit *taps_units;       // "taps" dendrites
     const TapsSyn *taps_syn;
     const double *taps_values;
     const uint32_t *neuron_taps;      // per neuron: its taps unit or 0xFFFFFFFF
@@ -847,7 +849,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             bias_r[r] = s.bias[i];
             refr_r[r] = s.refractory[i];
             sum_r[r] = s.din32[d];
-            if (core.acc_mode != SFE_ACC_PACKED32) cnt_r[r] = s.dcnt32[d];
+            if (core.acc_mode != SFE_ACC_PACKED32 && core.acc_mode != SFE_ACC_PACKED17) cnt_r[r] = s.dcnt32[d];
         }
     }
     __syncthreads(); // class cache filled
@@ -887,6 +889,17 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 // read (src/models.cpp:78-82)
                 has_in = true;
             }
+            else if (core.acc_mode == SFE_ACC_PACKED17)
+            {
+                if (raw_sum != 0u)
+                {
+                    // cell = sum + count * 2^17 with |sum| < 2^16: the count is the cell rounded to 2^17
+                    const uint32_t count = (raw_sum + 0x10000u) >> 17;
+                    has_in = true; // a non-zero cell has count >= 1 (count * 2^17 - |sum| > 0)
+                    in = static_cast<double>(static_cast<int>(raw_sum - (count << 17))) * core.inv_scale;
+                    s.din32[d] = 0u; // consumed (the message phase accumulates into zeroed slots)
+                }
+            }
             else if (core.acc_mode == SFE_ACC_PACKED32)
             {
                 if (raw_sum != 0u)
@@ -913,11 +926,10 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 {
                     has_in = true;
                     in = s.din64[d];
-                    if (core.ring > 1)
-                    {
-                        s.din64[d] = 0.0;
-                        s.dcnt32[d] = 0u;
-                    }
+                    // consumed: a delay-ring slot is reused ring steps later, and a core that accumulates in HBM
+                    // (acc_global) adds onto these cells directly
+                    s.din64[d] = 0.0;
+                    s.dcnt32[d] = 0u;
                 }
             }
             double lat = 0.0;
@@ -1146,6 +1158,7 @@ __device__ __forceinline__ uint32_t gather_inbox_word(const uint32_t *__restrict
 constexpr int kFanoutThreads = 256;
 constexpr int kFanoutWarps = kFanoutThreads / 32;
 constexpr int kListCap = 2048; // active axons listed per round (16 KB of shared memory)
+constexpr int kListExtra = 512; // of which, for cores with 4-byte records: extra chunks of axons with > 128 synapses
 constexpr int kCostCache = 32;  // cost classes cached in shared memory
 
 struct FanoutCounters
@@ -1186,12 +1199,13 @@ struct ChunkCursor
 };
 
 __device__ __forceinline__ void accumulate_one(uint32_t *acc32, uint32_t *cnt32, const uint32_t P, const uint32_t ring,
-        const long long T, const double scale, const bool packed, const double w, const uint32_t m)
+        const long long T, const double scale, const uint32_t packed_one, const double w, const uint32_t m)
 {
     const uint32_t post = SFE_SYN_POST(m);
     const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
     const int fixed = __double2int_rn(w * scale);
-    if (packed) atomicAdd(&acc32[sl * P + post], (1u << 20) + static_cast<uint32_t>(fixed));
+    // packed cells: sum + count * 2^20 (PACKED32) or sum + count * 2^17 (PACKED17)
+    if (packed_one != 0u) atomicAdd(&acc32[sl * P + post], packed_one + static_cast<uint32_t>(fixed));
     else
     {
         atomicAdd(&acc32[sl * P + post], static_cast<uint32_t>(fixed));
@@ -1256,7 +1270,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     __shared__ double part_d[kFanoutWarps][3];
     __shared__ unsigned long long part_l[kFanoutWarps][6];
     __shared__ sfe_cost_class cost_cache[kCostCache];
-    __shared__ uint32_t next_item, list_n;
+    __shared__ uint32_t next_item, list_n, list_total;
     __shared__ uint32_t scan_w[kFanoutWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1319,7 +1333,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     const CoreDev core = t.cores[ci];
     // kStreamQ4 instantiation: every core of the engine is certified for 4-byte records, the
     // other accumulation modes and streaming variants are compiled out (fewer registers)
-    const uint32_t acc_mode = V == kStreamQ4 ? static_cast<uint32_t>(SFE_ACC_PACKED32) : core.acc_mode;
+    const uint32_t acc_mode = V == kStreamQ4 ? static_cast<uint32_t>(SFE_ACC_PACKED17) : core.acc_mode;
     const bool is_q4 = V == kStreamQ4 || core.q4 != 0u;
     const uint32_t P = core.neuron_count;
     const uint32_t cells = P * core.ring;
@@ -1331,10 +1345,19 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     uint32_t *cnt32 = acc32 + cells;                                   // DUAL32 count / ORDERED has
     double *acc64 = reinterpret_cast<double *>(smem_raw);              // ORDERED (cnt32 placed after)
     if (acc_mode == SFE_ACC_ORDERED) cnt32 = reinterpret_cast<uint32_t *>(acc64 + cells);
-
-    if (accumulate)
+    // a core too large for shared-memory accumulators works on the HBM arrays directly: the exact modes add with
+    // global atomics (sums commute), the ordered mode is one warp that owns the core's cells for the whole phase
+    const bool in_hbm = V != kStreamQ4 && core.acc_global != 0u;
+    if (in_hbm)
     {
-        if (acc_mode == SFE_ACC_PACKED32)
+        acc32 = s.din32 + core.dend_base;
+        cnt32 = s.dcnt32 + core.dend_base;
+        acc64 = s.din64 + core.dend_base;
+    }
+
+    if (accumulate && !in_hbm)
+    {
+        if (acc_mode == SFE_ACC_PACKED32 || acc_mode == SFE_ACC_PACKED17)
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads) acc32[x] = 0u;
         else if (acc_mode == SFE_ACC_DUAL32)
             for (uint32_t x = threadIdx.x; x < 2 * cells; x += kFanoutThreads) acc32[x] = 0u;
@@ -1365,7 +1388,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
         //           loads (one global latency for the whole core), accounted, and the
         //           list is rewritten as (segment offset, synapse count)
         //   stream  warp w takes entries w, w+8, ... and streams their CSR segments
-        const bool packed = acc_mode == SFE_ACC_PACKED32;
+        const uint32_t packed = acc_mode == SFE_ACC_PACKED32 ? (1u << 20) : acc_mode == SFE_ACC_PACKED17 ? (1u << 17) : 0u;
         uint2 *list = reinterpret_cast<uint2 *>(smem_raw + list_off);
         for (uint32_t wb = item.word_lo; wb < n_words;)
         {
@@ -1392,10 +1415,11 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 if (w < warp) base += x;
                 total += x;
             }
-            const bool ok = base + pc <= kListCap;
+            // 4-byte records: the tail of the list is kept for the extra chunks of axons with more than 128 synapses
+            const bool ok = base + pc <= (is_q4 ? kListCap - kListExtra : kListCap);
             const uint32_t accepted = __syncthreads_count(ok); // ok is monotone in the word index
             if (threadIdx.x == accepted || (accepted == kFanoutThreads && threadIdx.x == 0))
-                list_n = accepted == kFanoutThreads ? total : base;
+                list_n = list_total = accepted == kFanoutThreads ? total : base;
             if (ok && word != 0u)
             {
                 if (!gather) s.inbox[core.inbox_word_begin + wi] = 0u; // consume
@@ -1418,7 +1442,31 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 ax.hop = raw.z;
                 ax.cost_class = raw.w;
                 account_axon(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
-                list[e] = make_uint2(ax.syn_off, ax.syn_count);
+                if (!is_q4) list[e] = make_uint2(ax.syn_off, ax.syn_count);
+                else
+                {
+                    // 4-byte records: the stream works on chunks of <= 128 records, entry = (first record, number of
+                    // 16-byte pieces). The further chunks of a long axon go to the tail of the list (the order of
+                    // exact accumulation is free); chunks that do not fit there are added right here, record by record.
+                    list[e] = make_uint2(ax.syn_off, (min(ax.syn_count, 128u) + 3u) >> 2);
+                    if (ax.syn_count > 128u && accumulate)
+                    {
+                        const uint32_t extra = (ax.syn_count - 1u) >> 7;
+                        const uint32_t at = atomicAdd(&list_total, extra);
+                        for (uint32_t k = 0; k < extra; ++k)
+                        {
+                            const uint32_t off = ax.syn_off + 128u * (k + 1u);
+                            const uint32_t w4 = (min(ax.syn_count - 128u * (k + 1u), 128u) + 3u) >> 2;
+                            if (at + k < kListCap) list[at + k] = make_uint2(off, w4);
+                            else
+                                for (uint32_t j = 0; j < 4u * w4; ++j)
+                                {
+                                    const uint32_t qv = __ldg(t.syn_q4 + core.syn_begin + off + j);
+                                    atomicAdd(&acc32[(qv & 0x3FFCu) >> 2], qv >> 14);
+                                }
+                        }
+                    }
+                }
             }
             __syncthreads();
             wb += accepted;
@@ -1434,87 +1482,63 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             cur.ent = list[warp];
             if (is_q4)
             {
-                // 4-byte records. Each warp owns a ring of kQ4Stages 512-byte chunks in shared memory
-                // filled by cp.async: lane l moves the l-th 16 bytes of a chunk and, thanks to the
-                // lane-major layout of the table (q4_position), those are the four records it
-                // accumulates - it waits for its own copies only (no warp barrier), reads them back
-                // with one 16-byte load and adds each with one red.shared on a 32-bit shared
-                // address. Nothing is held in registers while in flight: seven chunks per warp are
-                // always on their way.
-                const uint32_t *__restrict__ q_base = t.syn_q4 + core.syn_begin;
-                uint32_t acc_s = smem_addr(acc32), ring_s = smem_addr(
+                // 4-byte records (q4_record). Each warp owns a ring of kQ4Stages 512-byte chunks in shared
+                // memory filled by cp.async: lane l moves the l-th 16 bytes of a chunk and, thanks to the
+                // lane-major layout of the table (q4_position), those are the four records it accumulates
+                // - it waits for its own copies only (no warp barrier), reads them back with one 16-byte
+                // load and adds each with one red.shared: address = record & 0x3FFC (+ the accumulators'
+                // base as an immediate), addend = record >> 14. Pad records are zero words (add 0 to cell
+                // 0), so a lane never tests its records one by one. Nothing is held in registers while in
+                // flight: seven chunks per warp are always on their way.
+                const uint32_t acc_s = smem_addr(acc32);
+                const uint32_t ring_s = smem_addr(
                         tma_base + warp * (V == kStreamTma ? kTmaStages * kTmaStageBytes : kQ4Stages * kQ4StageBytes) + 16 * lane);
-                // opaque copies: keeps the two shared-window addresses in registers (the compiler
-                // otherwise re-derives them from the generic pointer before every access)
-                asm volatile("mov.u32 %0, %0;" : "+r"(acc_s));
-                asm volatile("mov.u32 %0, %0;" : "+r"(ring_s));
+                const uint32_t *q_lane = t.syn_q4 + core.syn_begin + 4u * lane;
+                // opaque copy: keeps the lane's base pointer in a register pair, so that the address of a chunk is one
+                // wide multiply-add of the entry's record offset (the compiler otherwise re-derives it from the
+                // kernel parameters for every chunk)
+                asm volatile("mov.u64 %0, %0;" : "+l"(q_lane));
+                const uint32_t n_total = min(list_total, static_cast<uint32_t>(kListCap));
+                // this warp's chunks: list entries warp, warp + 8, ...; chunk c lives in stage c % kQ4Stages
+                const uint32_t my_chunks = (n_total - warp + kFanoutWarps - 1u) / kFanoutWarps;
+                const uint2 *my_list = list + warp;
                 auto add_q4 = [&](const uint32_t qv) {
-                    uint32_t addr;
-                    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(qv & 0xFFFu), "r"(acc_s));
-                    const uint32_t val = 0x100000u + static_cast<uint32_t>(static_cast<int>(qv) >> 12);
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + (qv & 0x3FFCu)), "r"(qv >> 14) : "memory");
                 };
-                auto issue = [&](const int st) -> uint32_t {
-                    uint32_t rem = 0u;
-                    if (cur.e < cur.count)
+                auto issue = [&](const uint32_t c, const int st) {
+                    if (c < my_chunks)
                     {
-                        rem = cur.ent.y - cur.j0;
-                        const uint32_t n4 = (min(rem, 128u) + 3u) & ~3u; // segments are padded to 4 records
-                        if (4u * lane < n4)
+                        const uint2 ent = my_list[c * kFanoutWarps];
+                        if (lane < ent.y)
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + st * kQ4StageBytes),
-                                         "l"(q_base + cur.ent.x + cur.j0 + 4u * lane)
+                                         "l"(q_lane + ent.x)
                                          : "memory");
-                        cur.j0 += 128u;
-                        if (cur.j0 >= cur.ent.y)
-                        {
-                            cur.j0 = 0u;
-                            cur.e += cur.stride;
-                            if (cur.e < cur.count) cur.ent = list[cur.e];
-                        }
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory"); // empty groups keep the count uniform
-                    return rem;
                 };
-                uint32_t rem_q[kQ4Stages];
 #pragma unroll
-                for (int st = 0; st < kQ4Stages; ++st) rem_q[st] = issue(st);
-                bool done = false;
-                while (!done)
+                for (int st = 0; st < kQ4Stages; ++st) issue(st, st);
+                for (uint32_t c0 = 0; c0 < my_chunks; c0 += kQ4Stages)
                 {
 #pragma unroll
                     for (int st = 0; st < kQ4Stages; ++st)
                     {
-                        if (rem_q[st] == 0u)
-                        {
-                            done = true;
-                            break;
-                        }
+                        const uint32_t c = c0 + st;
+                        if (c >= my_chunks) break;
                         asm volatile("cp.async.wait_group %0;" ::"n"(kQ4Stages - 1) : "memory");
-                        const uint32_t n = min(rem_q[st], 128u), w = ((n + 3u) & ~3u) >> 2;
-                        if (lane < w)
+                        if (lane < my_list[c * kFanoutWarps].y)
                         {
                             uint4 rec;
                             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                          : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w)
                                          : "r"(ring_s + st * kQ4StageBytes)
                                          : "memory");
-                            // up to 3 pad records close the chunk: with W >= 3 they all sit in the last quarter
-                            if (w >= 3u)
-                            {
-                                add_q4(rec.x);
-                                add_q4(rec.y);
-                                add_q4(rec.z);
-                                if (3u * w + lane < n) add_q4(rec.w);
-                            }
-                            else
-                            {
-                                if (lane < n) add_q4(rec.x);
-                                if (w + lane < n) add_q4(rec.y);
-                                if (2u * w + lane < n) add_q4(rec.z);
-                                if (3u * w + lane < n) add_q4(rec.w);
-                            }
+                            add_q4(rec.x);
+                            add_q4(rec.y);
+                            add_q4(rec.z);
+                            add_q4(rec.w);
                         }
-                        rem_q[st] = issue(st); // the lane refills its own 16 bytes: no barrier needed
+                        issue(c + kQ4Stages, st); // the lane refills its own 16 bytes: no barrier needed
                     }
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1672,8 +1696,17 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                     {
                         if (valid && rank == r)
                         {
-                            acc64[cell] = acc64[cell] + w;
-                            cnt32[cell] = 1u;
+                            if (in_hbm)
+                            {
+                                // L2 accesses: a cell may have been written by another lane a moment ago
+                                __stcg(&acc64[cell], __ldcg(&acc64[cell]) + w);
+                                __stcg(&cnt32[cell], 1u);
+                            }
+                            else
+                            {
+                                acc64[cell] = acc64[cell] + w;
+                                cnt32[cell] = 1u;
+                            }
                         }
                         __syncwarp();
                     }
@@ -1684,13 +1717,13 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     __syncthreads();
 
     // ---- write the dendrite state back (coalesced) ------------------------------
-    if (accumulate)
+    if (accumulate && !in_hbm)
     {
         const uint32_t base = core.dend_base;
         // Exact modes: several items (inbox slices) of one core may run on different CTAs,
         // and integer sums commute, so partial sums are merged with fire-and-forget global
         // atomics; the neuron phase zeroes a slot when it consumes it.
-        if (acc_mode == SFE_ACC_PACKED32)
+        if (acc_mode == SFE_ACC_PACKED32 || acc_mode == SFE_ACC_PACKED17)
         {
             for (uint32_t x = threadIdx.x; x < cells; x += kFanoutThreads)
                 if (acc32[x] != 0u) red_add(&s.din32[base + x], acc32[x]);
@@ -1772,13 +1805,27 @@ __global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables
 // ---------------------------------------------------------------------------
 // Bulk synthetic network: synapse generation + exactness certificate on device
 // ---------------------------------------------------------------------------
+// Device synapse layout: a segment (the synapses of one axon-in) is padded to a multiple of 4 records, and a segment
+// of 64 or more records starts on a multiple of 16 records: its 4-byte records then begin on a 64-byte boundary,
+// the granularity at which HBM is read (a 500-byte segment at an arbitrary 16-byte offset touches 8.6 such blocks on
+// average, an aligned one 8).
+__host__ __device__ __forceinline__ unsigned long long segment_start(const unsigned long long off, const uint32_t count)
+{
+    return count >= 64u ? (off + 15ull) & ~15ull : off;
+}
+__host__ __device__ __forceinline__ uint32_t segment_stride(const uint32_t count) // of equal segments laid end to end
+{
+    const uint32_t padded = (count + 3u) & ~3u;
+    return count >= 64u ? (padded + 15u) & ~15u : padded;
+}
+
 __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restrict__ syn_w,
         uint32_t *__restrict__ syn_meta, const unsigned long long total, const uint32_t first_core)
 {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const uint32_t C = sp.cores, P = sp.neurons_per_core, D = sp.dest_cores, S = sp.syn_per_axon;
-    const uint32_t Sp = (S + 3u) & ~3u; // device layout: every axon segment padded to 4 synapses
-    const unsigned long long per_core = static_cast<unsigned long long>(P) * D * Sp;
+    const uint32_t Sp = segment_stride(S); // device layout of equal segments
+    const unsigned long long per_core = (static_cast<unsigned long long>(P) * D * Sp + 15ull) & ~15ull; // cores start 64-byte aligned
     for (unsigned long long g = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < total;
             g += stride)
     {
@@ -1786,7 +1833,7 @@ __global__ void synth_generate_kernel(const sfe_synth_spec sp, double *__restric
         const unsigned long long rem = g % per_core;
         const uint32_t slot = static_cast<uint32_t>(rem / Sp);
         const uint32_t j = static_cast<uint32_t>(rem % Sp);
-        if (j >= S)
+        if (j >= S || slot >= P * D)
         {
             syn_w[g] = 0.0;
             syn_meta[g] = 0u;
@@ -1856,7 +1903,8 @@ __global__ void __launch_bounds__(256) certify_kernel(
         uint32_t mode = SFE_ACC_ORDERED;
         if (bad == 0u)
         {
-            if (worst_sum < 524288ull && worst_fan < 4096u) mode = SFE_ACC_PACKED32;
+            if (worst_sum < 65536ull && worst_fan < 32768u) mode = SFE_ACC_PACKED17;
+            else if (worst_sum < 524288ull && worst_fan < 4096u) mode = SFE_ACC_PACKED32;
             else if (worst_sum < 2147483648ull) mode = SFE_ACC_DUAL32;
         }
         core.acc_mode = mode;
@@ -1873,6 +1921,15 @@ __host__ __device__ __forceinline__ uint32_t q4_position(const uint32_t j, const
 {
     const uint32_t chunk = j & ~127u, n = min(count - chunk, 128u), w = ((n + 3u) & ~3u) >> 2, r = j - chunk;
     return chunk + 4u * (r % w) + r / w;
+}
+
+// The 4-byte record of a synapse of a PACKED17 core: bits 14..31 = weight * 2^shift + 2^17 (the certificate bounds
+// |weight * 2^shift| below 2^16, so the field is never 0), bits 2..13 = post-synaptic neuron * 4 (its byte offset in
+// the core's shared-memory accumulators), bits 0..1 = 0. The message phase needs one AND for the address and one
+// shift for the addend (sum + count * 2^17 in one atomic). An all-zero word is a pad record: it adds 0 to cell 0.
+__host__ __device__ __forceinline__ uint32_t q4_record(const int fixed, const uint32_t post)
+{
+    return (static_cast<uint32_t>(fixed + (1 << 17)) << 14) | ((post & 0xFFFu) << 2);
 }
 
 // 4-byte records of the certified cores (one CTA column per core, warps stride over its axons)
@@ -1892,8 +1949,7 @@ __global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, cons
             const int fixed = __double2int_rn(syn_w[at] * core.scale);
             // lane-major inside every 128-record chunk: the lane that copies 16 bytes of a chunk
             // owns records l, l+W, l+2W, l+3W of it (W = quarter width), see q4_position
-            syn_q4[core.syn_begin + ax.syn_off + q4_position(j, ax.syn_count)] =
-                    (static_cast<uint32_t>(fixed) << 12) | (SFE_SYN_POST(syn_meta[at]) & 0xFFFu);
+            syn_q4[core.syn_begin + ax.syn_off + q4_position(j, ax.syn_count)] = q4_record(fixed, SFE_SYN_POST(syn_meta[at]));
         }
     }
 }
@@ -1981,11 +2037,11 @@ struct sfe_engine
     bool ordered_any{false}, dual_any{false};
     // cooperative cancellation of a long sfe_engine_run (Ctrl-C in the Python binding): checked between batches
     std::atomic<bool> stop_requested{false};
-    // device-side Poisson draws (experimental)
+    // device-side Poisson draws
     PoissonUnit *d_poisson_units{nullptr};
     uint32_t *d_poisson_cols{nullptr}, *d_mt{nullptr}, *d_mt_idx{nullptr};
     uint32_t n_poisson_units{0};
-    uint32_t n_taps_units{0}; // "taps" dendrites (experimental device path)
+    uint32_t n_taps_units{0}; // "taps" dendrites
     size_t tap_cells{0};
     // Poisson overlay (host-drawn, see poisson.cpp)
     uint32_t n_poisson_cols{0};
@@ -2115,6 +2171,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.e_west = tile.energy_west;
         d.e_south = tile.energy_south;
         d.e_north = tile.energy_north;
+        if (cd.neuron_count > 0x10000u)
+        {
+            sfe::set_last_error("core " + std::to_string(c) + " maps " + std::to_string(cd.neuron_count) +
+                    " neurons: the synapse records address at most 65536 neurons per core");
+            return -1;
+        }
         inbox_word_begin[c] = inbox_words;
         if (is_local(c) && cd.axon_in_count > 0)
         {
@@ -2179,13 +2241,6 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->upload(&e->t.input_spikes, tb->input_spikes, tb->n_input_spikes) != 0) return -1;
     if (tb->n_taps_units != 0)
     {
-        const char *opt_in = std::getenv("SFE_DEVICE_TAPS");
-        if (opt_in == nullptr || std::atoi(opt_in) == 0)
-        {
-            sfe::set_last_error("'taps' dendrites (MultiTapModel1D) are lowered, but their device path has not been verified on "
-                                "hardware yet and is off by default (SFE_DEVICE_TAPS=1 enables it)");
-            return -1;
-        }
         if (e->world > 1 || tb->syn_weight == nullptr || tb->syn_meta == nullptr)
         {
             sfe::set_last_error("'taps' dendrites need an unpartitioned chip with host synapse tables");
@@ -2308,10 +2363,11 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                 sfe::set_last_error("more than 2^32 padded synapses on one core");
                 return -1;
             }
+            off = segment_start(off, ax.syn_count);
             ax.syn_off = static_cast<uint32_t>(off);
             off += (static_cast<uint64_t>(ax.syn_count) + 3u) & ~3ull;
         }
-        padded_total += off;
+        padded_total += (off + 15ull) & ~15ull; // every core starts on a 64-byte boundary of the 4-byte table
     }
     if (e->upload(&e->t.axons_in, dev_axons.data(), dev_axons.size()) != 0) return -1;
     SFE_CUDA(cudaStreamSynchronize(e->stream));
@@ -2433,7 +2489,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         for (uint32_t c : e->fanout_list)
         {
             CoreDev &d = e->h_cores[c];
-            d.q4 = (want && d.acc_mode == SFE_ACC_PACKED32 && d.ring == 1 && d.neuron_count <= 4096 && d.dend_in_msg != 0) ? 1u : 0u;
+            d.q4 = (want && d.acc_mode == SFE_ACC_PACKED17 && d.ring == 1 && d.neuron_count <= 4096 && d.dend_in_msg != 0) ? 1u : 0u;
             any = any || d.q4 != 0u;
         }
         e->q4_any = any;
@@ -2519,12 +2575,29 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (engine_init_state(e) != 0) return -1;
 
     // ---- shared memory of the message phase ------------------------------------------
+    // A core whose dendrite cells exceed the shared-memory budget accumulates in HBM instead (acc_global): slower,
+    // but such a core is rare (an ordered core with delays beyond ~2.8k neurons, an exact one beyond ~24k) and the
+    // reference has no such limit. SFE_ACC_SMEM_LIMIT (bytes) lowers the budget (tests).
+    size_t acc_budget = 160 * 1024;
+    if (const char *v = std::getenv("SFE_ACC_SMEM_LIMIT")) acc_budget = static_cast<size_t>(std::max(0, std::atoi(v)));
+    bool any_global = false;
     for (uint32_t c : e->fanout_list)
     {
-        const CoreDev &d = e->h_cores[c];
+        CoreDev &d = e->h_cores[c];
         const size_t cells = static_cast<size_t>(d.neuron_count) * d.ring;
-        const size_t need = d.acc_mode == SFE_ACC_PACKED32 ? cells * 4 : d.acc_mode == SFE_ACC_DUAL32 ? cells * 8 : cells * 12;
+        const size_t need = (d.acc_mode == SFE_ACC_PACKED32 || d.acc_mode == SFE_ACC_PACKED17) ? cells * 4 : d.acc_mode == SFE_ACC_DUAL32 ? cells * 8 : cells * 12;
+        if (need > acc_budget && d.q4 == 0u)
+        {
+            d.acc_global = 1u;
+            any_global = true;
+            continue;
+        }
         smem_max = std::max(smem_max, need);
+    }
+    if (any_global)
+    {
+        SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
     if (const char *v = std::getenv("SFE_FANOUT"))
     {
@@ -2551,7 +2624,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->fanout_smem = smem_max;
     if (smem_max > 200 * 1024)
     {
-        sfe::set_last_error("a core needs more than 200 KB of shared-memory dendrite accumulators");
+        sfe::set_last_error("the message phase needs more than 200 KB of shared memory (SFE_ACC_SMEM_LIMIT too high?)");
         return -1;
     }
     // The opt-in limit is a property of the FUNCTION (per device), not of this engine: several engines
@@ -2771,7 +2844,7 @@ static void launch_soma(sfe_engine *e)
     else launch_step_kernel(e, soma_kernel<false>, grid, kSomaThreads, 0, e->t, e->s);
 }
 
-// "taps" lines of the step (experimental): after the neuron phase has written the raster, before the message
+// "taps" lines of the step: after the neuron phase has written the raster, before the message
 // phase; a plain launch, i.e. fully ordered after the neuron phase like the probe kernel
 static void launch_taps(sfe_engine *e)
 {
@@ -2909,7 +2982,7 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
     return 0;
 }
 
-// EXPERIMENTAL: the overlay of the next n_steps steps drawn on the device (poisson_kernel) instead of uploaded.
+// The overlay of the next n_steps steps drawn on the device (poisson_kernel) instead of uploaded.
 // Advances the device generators; do not mix with host-drawn overlays on one engine (two streams of draws).
 extern "C" int sfe_engine_fill_input_overlay(sfe_engine *e, int64_t n_steps)
 {

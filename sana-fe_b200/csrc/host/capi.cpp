@@ -402,8 +402,10 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                             if (req->neuron_traces != nullptr)
                                 sub.neuron_traces = req->neuron_traces + static_cast<size_t>(done) * c->tables.view.n_u_probes;
                         }
-                        const char *opt = std::getenv("SFE_DEVICE_POISSON"); // experimental, see sfe_engine_fill_input_overlay
-                        const bool device_draws = opt != nullptr && std::atoi(opt) != 0;
+                        // draws on the device by default (sfe_engine_fill_input_overlay); SFE_DEVICE_POISSON=0: on the
+                        // host with libstdc++'s generator, the cross-check
+                        const char *opt = std::getenv("SFE_DEVICE_POISSON");
+                        const bool device_draws = opt == nullptr || std::atoi(opt) != 0;
                         if (c->poisson != nullptr && device_draws)
                         {
                             if (sfe_engine_fill_input_overlay(c->engine, batch) != 0) return -1;

@@ -1069,7 +1069,8 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 worst_fan = std::max(worst_fan, fan_in[i]);
             }
             cd.weight_shift = shift;
-            if (worst_sum < 524288.0 && worst_fan < 4096) cd.acc_mode = SFE_ACC_PACKED32;
+            if (worst_sum < 65536.0 && worst_fan < 32768) cd.acc_mode = SFE_ACC_PACKED17;
+            else if (worst_sum < 524288.0 && worst_fan < 4096) cd.acc_mode = SFE_ACC_PACKED32;
             else if (worst_sum < 2147483648.0) cd.acc_mode = SFE_ACC_DUAL32;
         }
     }
@@ -1246,7 +1247,8 @@ void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bo
     {
         const double wmax = static_cast<double>(std::max(std::abs(s.w_min), std::abs(s.w_max)));
         const double fan_bound = static_cast<double>(P) * D; // axons into the core; each hits a post <= once
-        const uint32_t mode = (fan_bound < 4096.0 && fan_bound * wmax < 524288.0) ? SFE_ACC_PACKED32
+        const uint32_t mode = (fan_bound < 32768.0 && fan_bound * wmax < 65536.0)  ? SFE_ACC_PACKED17
+                : (fan_bound < 4096.0 && fan_bound * wmax < 524288.0)              ? SFE_ACC_PACKED32
                 : (fan_bound * wmax < 2147483648.0)                                ? SFE_ACC_DUAL32
                                                                                    : SFE_ACC_ORDERED;
         for (uint32_t c = 0; c < C; ++c) out.cores[c].acc_mode = mode;

@@ -217,25 +217,33 @@ def test_ctrl_c_interrupts_a_long_sim():
     assert res["timesteps_executed"] == 10 and res["timestep_start"] > 101
 
 
-@pytest.mark.xfail(reason="experimental device path of `taps` dendrites (SFE_DEVICE_TAPS=1): written after the round's GPU "
-                          "budget was spent, never run on hardware; an XPASS here means it can become the default",
-                   strict=False)
-def test_taps_device_path_experimental(monkeypatch):
+def test_taps_device_path():
     """taps_kernel + the neuron phase's tap-line read-out against the reference's golden (the CPU restatement
-    passes it in test_oracle_vs_reference.py)."""
-    monkeypatch.setenv("SFE_DEVICE_TAPS", "1")
+    passes it in test_oracle_vs_reference.py). The device path is the default since it passed on a B200 in round 1."""
     chip = load_chip("taps", device=0)
     g = golden("taps")
     rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
     check_against_golden("taps", chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
 
 
-@pytest.mark.xfail(reason="experimental device-side Poisson draws (SFE_DEVICE_POISSON=1): the generator is checked on the host "
-                          "against libstdc++ (test_poisson_inputs.py) but the kernel has never run on hardware",
-                   strict=False)
-def test_poisson_device_draws_experimental(monkeypatch):
-    monkeypatch.setenv("SFE_DEVICE_POISSON", "1")
+@pytest.mark.parametrize("device_draws", ["1", "0"])
+def test_poisson_draws_device_and_host(monkeypatch, device_draws):
+    """Poisson inputs against the reference's golden with the draws made on the device (poisson_kernel, the default)
+    and on the host with libstdc++'s generator (SFE_DEVICE_POISSON=0, the cross-check): the same spikes either way."""
+    monkeypatch.setenv("SFE_DEVICE_POISSON", device_draws)
     chip = load_chip("poisson", device=0)
     g = golden("poisson")
     rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
     check_against_golden("poisson", chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
+
+
+def test_oversized_core_accumulates_in_hbm(monkeypatch):
+    """A core whose dendrite cells do not fit the shared-memory budget accumulates in HBM (acc_global). Forced here
+    with a zero budget on goldens of every accumulation mode: ordered fp64 (frac), exact with a delay ring
+    (synth_delay), the charge-loss quirk; cores with 4-byte records keep their shared-memory path (synth_small)."""
+    monkeypatch.setenv("SFE_ACC_SMEM_LIMIT", "0")
+    for name in ("frac", "synth_delay", "synth_quirk", "synth_small", "dvs"):
+        chip = load_chip(name, device=0)
+        g = golden(name)
+        rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+        check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
