@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 4
+#define SFE_ABI_VERSION 5
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -66,14 +66,20 @@ enum
     SFE_SOMA_LIF = 0,       /* "leaky_integrate_fire"   src/models.cpp:497-567 */
     SFE_SOMA_TRUENORTH = 1, /* "truenorth"              src/models.cpp:799-830 */
     SFE_SOMA_INPUT = 2,     /* "input"                  src/models.cpp:863-903 */
-    SFE_SOMA_HH = 3         /* "hodgkin_huxley" plugin  plugins/hodgkin_huxley.cpp:116-170 */
+    SFE_SOMA_HH = 3,        /* "hodgkin_huxley" plugin  plugins/hodgkin_huxley.cpp:116-170 */
+    SFE_SOMA_NEUROFEM = 4,  /* "neurofem" plugin (combined dendrite + soma unit)  plugins/neurofem.cpp:192-317, sigma_v = 0 */
+    SFE_SOMA_DEVICE_MODEL = 5 /* a soma model registered with sfe_register_device_model: its update runs as a kernel of
+                               * its own device code image before the neuron phase, see sfe_device_model.h */
 };
 /* dendrite models */
 enum
 {
     SFE_DEND_ACCUMULATOR = 0,      /* src/models.cpp:71-94  */
     SFE_DEND_ACCUMULATOR_DELAY = 1,/* src/models.cpp:96-131 */
-    SFE_DEND_TAPS = 2              /* "taps" MultiTapModel1D  src/models.cpp:167-259 */
+    SFE_DEND_TAPS = 2,             /* "taps" MultiTapModel1D  src/models.cpp:167-259 */
+    SFE_DEND_NEUROFEM = 3          /* dendrite half of the combined "neurofem" unit: two accumulators per neuron (u1, u2),
+                                    * double-buffered over the timestep; a synapse names its compartment (0/1) in the
+                                    * delay field of syn_meta  plugins/neurofem.cpp:120-136, 227-248 */
 };
 /* how one core's message phase accumulates synaptic charge */
 enum
@@ -89,6 +95,8 @@ enum
 #define SFE_SOMA_LEAK_TOWARDS_ZERO 2u
 #define SFE_SOMA_LOG_U 4u
 #define SFE_SOMA_NOISE 8u /* LIF unit with a file noise stream: neuron_aux indexes sfe_tables.noise */
+#define SFE_SOMA_IS_DENDRITE 16u /* the soma unit is also the neuron's dendrite unit (a combined unit): its energy counts in the
+                                  * dendrite AND the soma bucket of a step, once in the total (src/chip.cpp:1224-1245) */
 
 /* ---- lowered tables ------------------------------------------------------ */
 typedef struct sfe_tile_desc
@@ -112,6 +120,9 @@ typedef struct sfe_core_desc
     int32_t weight_shift; /* exact modes: every weight is k * 2^-weight_shift */
     uint32_t ring;        /* dendrite ring slots = max synaptic delay + 1 */
     uint32_t dend_in_msg; /* 1: dendrite unit is in the message pipeline (buffer_pos >= 1) */
+    uint32_t fixed_slots; /* 1: the delay field of a synapse IS its dendrite slot (compartment of a "neurofem" unit); the
+                           * neuron phase reads slots 0..ring-1 of the step instead of the rotating slot of a delay line */
+    uint32_t pad;
     /* axon units with the reference's quirks folded in:
      * latency: axon_in_hw[0] / axon_out_hw[0]; energy: only when the core has
      * exactly one such unit (the reference counts the LAST unit's energy while
@@ -138,6 +149,8 @@ typedef struct sfe_soma_class
     double latency_access, latency_update, latency_spike_out;
     /* default costs of the dendrite unit when it runs in the neuron pipeline */
     double dend_energy_update, dend_latency_update;
+    /* "neurofem" (plugins/neurofem.cpp:64-84): lambda_v rides in `leak`, lambda_d in `input_decay`; kp, ki, dt here */
+    double nf_kp, nf_ki, nf_dt;
 } sfe_soma_class;
 
 /* per-event default costs of one (synapse unit, dendrite unit) pairing; an axon
@@ -147,7 +160,8 @@ typedef struct sfe_cost_class
     double syn_energy, syn_latency; /* src/pipeline.hpp:511-572 */
     double den_energy, den_latency; /* src/pipeline.hpp:574-629 (0 if dendrite not in message pipeline) */
     uint32_t per_message;
-    uint32_t pad;
+    uint32_t den_is_soma; /* 1: the "dendrite" of the pairing is a combined dendrite + soma unit: every event costs it one soma
+                           * access (src/pipeline.hpp:631-667 with status unset), counted in the dendrite and soma buckets */
 } sfe_cost_class;
 
 /* one axon-in = one (pre-neuron, destination core) pair = one message per spike */
@@ -324,6 +338,8 @@ int sfe_engine_reset(sfe_engine *e);
  * stream into the inactive device buffer (overlapping the steps already enqueued) and takes
  * effect with the next step that is enqueued; keep the host buffer unchanged until then. */
 int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n);
+/* the same from pageable memory: staged through an engine-owned pinned buffer; the caller's vector is free on return */
+int sfe_engine_set_bias_staged(sfe_engine *e, const double *bias, size_t n);
 /* Poisson inputs are drawn on the host (the reference's generator is libstdc++'s std::mt19937 +
  * uniform_real_distribution, one draw per update of a neuron of the unit, src/models.cpp:863-903) and reach
  * the device as an overlay: bits[step][col] != 0 makes the input neuron with that poisson_col spike in that
@@ -350,6 +366,8 @@ int sfe_poisson_fill(sfe_poisson *p, uint8_t *bits, int64_t n_steps);
 void sfe_poisson_reference_draws(uint32_t seed, double *out, size_t n);
 void sfe_mt19937_draws(uint32_t seed, double *out, size_t n, size_t stride);
 int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias);
+/* LIF "potential" attribute after load (src/models.cpp:433-436): sets the membrane potential of one neuron */
+int sfe_engine_set_neuron_potential(sfe_engine *e, uint32_t neuron, double potential);
 int sfe_engine_read_potentials(sfe_engine *e, double *out, size_t n);
 int sfe_engine_read_fired(sfe_engine *e, uint32_t *bits, size_t n_words);
 /* the last step's raster in the device's padded layout (world * slice words; every core starts on

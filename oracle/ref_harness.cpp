@@ -13,7 +13,11 @@
 //
 // usage: sanafe_ref <flat.jsonl> --steps N [--timing simple|detailed]
 //                   [--threads N] [--out DIR] [--traces] [--per-step]
-//                   [--dump-map] [--reps R]
+//                   [--dump-map] [--reps R] [--hash-steps H]
+// --hash-steps H: before the timed calls, H timesteps are run one by one and the spikes of each (get_spikes, i.e.
+// neurons with log_spikes) are folded into an order-independent 64-bit raster hash, sum of
+// sfe_mix64(timestep << 32 | neuron offset) mod 2^64, written to summary.json with the counters of those H steps:
+// bench.py runs the GPU engine on the same network and steps and compares (parity at the benchmark's own shape).
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -702,6 +706,7 @@ int main(int argc, char **argv)
     bool per_step = false;
     bool want_map = false;
     int reps = 1;
+    long hash_steps = 0;
     for (int i = 2; i < argc; ++i)
     {
         const std::string a = argv[i];
@@ -713,6 +718,7 @@ int main(int argc, char **argv)
         else if (a == "--per-step") per_step = true;
         else if (a == "--dump-map") want_map = true;
         else if (a == "--reps") reps = std::atoi(argv[++i]);
+        else if (a == "--hash-steps") hash_steps = std::atol(argv[++i]);
         else { std::fprintf(stderr, "unknown flag %s\n", a.c_str()); return 2; }
     }
 #ifdef HAVE_OPENMP
@@ -746,6 +752,22 @@ int main(int argc, char **argv)
         sanafe::RunData total(1);
         double best_wall = 1e300;
         double wall_sum = 0.0;
+        std::string calls_json;
+        unsigned long long raster_hash = 0ull;
+        sanafe::RunData hashed(1);
+        for (long t = 1; t <= hash_steps; ++t)
+        {
+            const sanafe::RunData rd = chip.sim(1, tm, 0, tf, out_dir);
+            for (const auto &addr : chip.get_spikes())
+                raster_hash += sfe_mix64((static_cast<unsigned long long>(t) << 32) |
+                        static_cast<unsigned long long>(addr.neuron_offset.value()));
+            hashed.total_energy += rd.total_energy;
+            hashed.sim_time += rd.sim_time;
+            hashed.spikes += rd.spikes;
+            hashed.packets_sent += rd.packets_sent;
+            hashed.neurons_updated += rd.neurons_updated;
+            hashed.neurons_fired += rd.neurons_fired;
+        }
         if (per_step)
         {
             // Full-precision per-step records through the public getters
@@ -819,6 +841,9 @@ int main(int argc, char **argv)
                 walls.push_back(w);
                 wall_sum += w;
                 best_wall = w; // earlier calls are warm-up: report the LAST call (its RunData is what we print)
+                char cb[96];
+                std::snprintf(cb, sizeof(cb), "%s[%ld, %.6f]", r == 0 ? "" : ", ", total.spikes, w);
+                calls_json += cb; // every call's synaptic events and wall: the caller takes the best rate
             }
         }
         std::ofstream sf(out_dir + "/summary.json");
@@ -829,11 +854,21 @@ int main(int argc, char **argv)
                 ", \"power\": %.17g, \"timing\": \"%s\", \"threads\": %d, \"neurons\": %zu, "
                 "\"synapses\": %zu, \"mapped_cores\": %zu, \"mapped_tiles\": %zu, "
                 "\"build_s\": %.6f, \"load_s\": %.6f, \"sim_wall_s\": %.6f, \"sim_wall_total_s\": %.6f, "
-                "\"reps\": %d}\n",
+                "\"reps\": %d",
                 chip.get_power(), timing.c_str(), threads, neurons, L.synapses, chip.mapped_cores,
                 chip.mapped_tiles, std::chrono::duration<double>(t1 - t0).count(),
                 std::chrono::duration<double>(t2 - t1).count(), best_wall, wall_sum, reps);
         sf << buf;
+        if (hash_steps > 0)
+        {
+            std::snprintf(buf, sizeof(buf),
+                    ", \"hash_steps\": %ld, \"raster_hash\": \"%016llx\", \"hash_spikes\": %ld, \"hash_packets\": %ld, "
+                    "\"hash_updated\": %ld, \"hash_fired\": %ld, \"hash_energy\": %.17g, \"hash_sim_time\": %.17g",
+                    hash_steps, raster_hash, hashed.spikes, hashed.packets_sent, hashed.neurons_updated,
+                    hashed.neurons_fired, hashed.total_energy, hashed.sim_time);
+            sf << buf;
+        }
+        sf << ", \"calls\": [" << calls_json << "]}\n";
         sf.close();
         std::ifstream back(out_dir + "/summary.json");
         std::cout << back.rdbuf();

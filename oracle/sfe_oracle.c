@@ -18,7 +18,8 @@
  *   neuron phase    src/chip.cpp:624-654, 710-736, 802-834
  *   message phase   src/chip.cpp:656-764, 1127-1169
  *   soma models     src/models.cpp:441-567 (LIF, incl. the file noise stream :589-650), 724-830 (TrueNorth),
- *                   863-903 (input: spike trains, rate, Poisson with an own MT19937), plugins/hodgkin_huxley.cpp:116-170
+ *                   863-903 (input: spike trains, rate, Poisson with an own MT19937), plugins/hodgkin_huxley.cpp:116-170,
+ *                   plugins/neurofem.cpp:192-317 (combined dendrite + soma unit, sigma_v = 0)
  *   dendrites       src/models.cpp:71-94 (accumulator), 96-131 (accumulator_with_delay), 167-259 (taps)
  *   default costs   src/pipeline.hpp:511-731
  *   energy/counters src/chip.cpp:1028-1051, 1171-1261
@@ -48,6 +49,9 @@ typedef struct sfe_oracle
     uint8_t *ring_has;
     /* HH state */
     double *hh_v, *hh_m, *hh_n, *hh_h, *hh_i;
+    /* NeuroFEM (plugins/neurofem.cpp:62-90): potential = v, u1 = u; u2, u_integrated and the two accumulators that the
+     * message phase of a step fills for the neuron phase of the next (next_u1/u2_dendritic_accumulator.value_or(0)) */
+    double *nf_u2, *nf_uint, *nf_acc;
     /* inbox */
     uint8_t *axon_active;
     /* per-step scratch */
@@ -55,6 +59,7 @@ typedef struct sfe_oracle
     int64_t *tile_e, *tile_w, *tile_n, *tile_s;
     int64_t *core_msgs;
     double *core_syn_e, *core_den_e, *core_soma_e, *core_axout_e;
+    double *core_dup_e; /* energy of combined dendrite + soma units: in both buckets, once in the total */
     double total_sim_time, total_energy;
     /* Poisson inputs: one MT19937 per input unit (own restatement, below), or an external overlay */
     struct mt19937 *poisson_gen; /* [n_poisson_units], indexed by sfe_input_desc.unit */
@@ -141,6 +146,10 @@ sfe_oracle *sfe_oracle_create(const sfe_tables *t)
     o->hh_n = (double *) zalloc(t->n_hh, sizeof(double));
     o->hh_h = (double *) zalloc(t->n_hh, sizeof(double));
     o->hh_i = (double *) zalloc(t->n_hh, sizeof(double));
+    o->nf_u2 = (double *) zalloc(n, sizeof(double));
+    o->nf_uint = (double *) zalloc(n, sizeof(double));
+    o->nf_acc = (double *) zalloc(2 * n, sizeof(double));
+    o->core_dup_e = (double *) zalloc(t->n_cores, sizeof(double));
     o->axon_active = (uint8_t *) zalloc(t->n_axons_in, 1);
     o->core_gen = (double *) zalloc(t->n_cores, sizeof(double));
     o->core_proc = (double *) zalloc(t->n_cores, sizeof(double));
@@ -190,6 +199,7 @@ void sfe_oracle_destroy(sfe_oracle *o)
     free(o->v); free(o->u); free(o->bias); free(o->refractory); free(o->status);
     free(o->buf); free(o->buf_has); free(o->acc); free(o->acc_step); free(o->ring); free(o->ring_has);
     free(o->hh_v); free(o->hh_m); free(o->hh_n); free(o->hh_h); free(o->hh_i);
+    free(o->nf_u2); free(o->nf_uint); free(o->nf_acc); free(o->core_dup_e);
     free(o->axon_active); free(o->core_gen); free(o->core_proc);
     free(o->tile_e); free(o->tile_w); free(o->tile_n); free(o->tile_s); free(o->core_msgs);
     free(o->core_syn_e); free(o->core_den_e); free(o->core_soma_e); free(o->core_axout_e);
@@ -225,6 +235,9 @@ void sfe_oracle_reset(sfe_oracle *o)
     memset(o->acc, 0, n * sizeof(double));
     memset(o->ring_has, 0, n * RING);
     memset(o->ring, 0, n * RING * sizeof(double));
+    memset(o->nf_u2, 0, n * sizeof(double)); /* NeuroFEMModel::reset  plugins/neurofem.cpp:319-335 */
+    memset(o->nf_uint, 0, n * sizeof(double));
+    memset(o->nf_acc, 0, 2 * n * sizeof(double));
     for (size_t i = 0; i < o->t->n_hh; ++i)
     {
         o->hh_v[i] = o->hh_m[i] = o->hh_n[i] = o->hh_h[i] = 0.0; /* plugins/hodgkin_huxley.cpp:71-87 */
@@ -374,6 +387,34 @@ static int hh_update(sfe_oracle *o, size_t k)
     return ((prev_V < 25) && (V > 25)) ? SFE_STATUS_FIRED : SFE_STATUS_UPDATED;
 }
 
+/* NeuroFEMModel::update + process_fem  plugins/neurofem.cpp:192-317 for the call of the neuron phase (the first call of
+ * a timestep): the accumulators filled by the previous message phase are consumed, then the compartment is updated.
+ * sigma_v = 0 (enforced at load): the noise term is +-0 and leaves the potential unchanged. */
+static int neurofem_update(sfe_oracle *o, const sfe_soma_class *c, size_t i)
+{
+    const double lambda_d = c->input_decay, lambda_v = c->leak, dt = c->nf_dt;
+    const double acc1 = o->nf_acc[2 * i], acc2 = o->nf_acc[2 * i + 1];
+    o->nf_acc[2 * i] = 0.0;
+    o->nf_acc[2 * i + 1] = 0.0;
+    double u1 = o->u[i], u2 = o->nf_u2[i], u_int = o->nf_uint[i], v = o->v[i];
+    u1 -= lambda_d * dt * u1;
+    u2 -= lambda_d * dt * u2;
+    u1 += acc1;
+    u2 += lambda_d * acc2;
+    const double u_err = u1 + o->bias[i];
+    u_int += dt * u_err;
+    v = v - (lambda_v * dt * v);
+    v = v + (dt * c->nf_kp * u_err) + (dt * c->nf_ki * u_int) + (dt * u2) + (0.0 * 0.0) - acc2;
+    int state = SFE_STATUS_UPDATED;
+    if (v > c->threshold)
+    {
+        v = c->reset;
+        state = SFE_STATUS_FIRED;
+    }
+    o->u[i] = u1; o->nf_u2[i] = u2; o->nf_uint[i] = u_int; o->v[i] = v;
+    return state;
+}
+
 /* MultiTapModel1D::update  src/models.cpp:237-257 with calculate_next_state (:167-202) and input_current
  * (:215-235): catch the line up to timestep T (one RC step per elapsed timestep), add the current to the
  * synapse's tap, return the voltage of tap 0. */
@@ -435,6 +476,7 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
     memset(o->core_den_e, 0, t->n_cores * sizeof(double));
     memset(o->core_soma_e, 0, t->n_cores * sizeof(double));
     memset(o->core_axout_e, 0, t->n_cores * sizeof(double));
+    memset(o->core_dup_e, 0, t->n_cores * sizeof(double));
     if (fired_bits) memset(fired_bits, 0, ((t->n_neurons + 31) / 32) * sizeof(uint32_t));
 
     /* ---- process_neurons ------------------------------------------------ */
@@ -450,7 +492,11 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
             int has_in = 0;
             double in = 0.0;
             double lat = 0.0; /* execute_pipeline: total_latency{0.0}, += per unit */
-            if (c->dend_in_neuron)
+            if (c->model == SFE_SOMA_NEUROFEM)
+            {
+                /* combined unit: its own double-buffered accumulators, read inside neurofem_update */
+            }
+            else if (c->dend_in_neuron)
             {
                 /* buffer inside the dendrite unit: dendrite.update(addr, nullopt, nullopt, T) */
                 if (c->dend_model == SFE_DEND_ACCUMULATOR)
@@ -487,6 +533,7 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
             case SFE_SOMA_LIF: st = lif_update(o, c, i, has_in, in, steps_done); break;
             case SFE_SOMA_TRUENORTH: st = truenorth_update(o, c, i, has_in, in); break;
             case SFE_SOMA_INPUT: st = input_update(o, &t->inputs[t->neuron_aux[i]], steps_done, T); break;
+            case SFE_SOMA_NEUROFEM: st = neurofem_update(o, c, i); break;
             default: st = hh_update(o, t->neuron_aux[i]); break;
             }
             o->status[i] = (uint8_t) st;
@@ -505,6 +552,11 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
                 rec->neurons_fired++;
             }
             o->core_soma_e[ci] += e;
+            if (c->flags & SFE_SOMA_IS_DENDRITE) /* src/chip.cpp:1224-1245: the unit's energy in both buckets */
+            {
+                o->core_den_e[ci] += e;
+                o->core_dup_e[ci] += e;
+            }
             lat += l;
             next_delay += lat;
             if (st == SFE_STATUS_FIRED)
@@ -560,7 +612,13 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
                 if (core->dend_in_msg)
                 {
                     const sfe_soma_class *pc = &t->soma_classes[t->neuron_class[post]];
-                    if (pc->dend_model == SFE_DEND_TAPS)
+                    if (pc->dend_model == SFE_DEND_NEUROFEM)
+                    {
+                        /* next_u{1,2}_dendritic_accumulator.value_or(0.0) + current  plugins/neurofem.cpp:227-248 */
+                        double *cell = &o->nf_acc[2 * post + (SFE_SYN_DELAY(m) & 1u)];
+                        *cell = *cell + weight;
+                    }
+                    else if (pc->dend_model == SFE_DEND_TAPS)
                     {
                         /* buffer before the soma: the value the last event of the step returns is what the soma reads */
                         o->buf[post] = taps_update(o, t->neuron_taps[post], T, weight, SFE_SYN_TAP(m));
@@ -584,6 +642,11 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
                 {
                     o->core_syn_e[ci] += cc->syn_energy;
                     o->core_den_e[ci] += cc->den_energy;
+                    if (cc->den_is_soma)
+                    {
+                        o->core_soma_e[ci] += cc->den_energy;
+                        o->core_dup_e[ci] += cc->den_energy;
+                    }
                     lat += (0.0 + cc->syn_latency) + cc->den_latency;
                 }
             }
@@ -591,6 +654,11 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
             {
                 o->core_syn_e[ci] += cc->syn_energy;
                 o->core_den_e[ci] += cc->den_energy;
+                if (cc->den_is_soma)
+                {
+                    o->core_soma_e[ci] += cc->den_energy;
+                    o->core_dup_e[ci] += cc->den_energy;
+                }
                 lat += cc->syn_latency;
             }
             o->core_proc[ci] += lat; /* message_processing_latencies[dest_core_id]  src/schedule.cpp:82 */
@@ -613,7 +681,7 @@ static void one_step(sfe_oracle *o, sfe_step_record *rec, uint32_t *fired_bits, 
                 const sfe_core_desc *core = &t->cores[ci];
                 const double axon_in_energy = (double) o->core_msgs[ci] * core->energy_axon_in;
                 rec->network_energy += axon_in_energy;
-                const double pipeline = (o->core_syn_e[ci] + o->core_den_e[ci]) + o->core_soma_e[ci];
+                const double pipeline = ((o->core_syn_e[ci] + o->core_den_e[ci]) + o->core_soma_e[ci]) - o->core_dup_e[ci];
                 rec->synapse_energy += o->core_syn_e[ci];
                 rec->dendrite_energy += o->core_den_e[ci];
                 rec->soma_energy += o->core_soma_e[ci];

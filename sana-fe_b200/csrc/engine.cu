@@ -65,6 +65,7 @@ struct CoreDev
     uint32_t ring;                    // delay-ring slots
     uint32_t acc_mode;                // SFE_ACC_*
     uint32_t dend_in_msg;
+    uint32_t fixed_slots;             // the delay field of a synapse is its dendrite slot ("neurofem" compartments)
     uint32_t tile;
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
@@ -82,6 +83,7 @@ struct StatsN // written by soma_kernel, one per core
 {
     uint32_t updated, fired, packets, pad;
     double soma_e, dend_e, gen_sum;
+    double dup_e; // energy of combined dendrite + soma units: part of soma_e AND dend_e, counted once in the total
 };
 
 struct FanItem // one unit of message-phase work: a slice of one core's inbox
@@ -94,6 +96,7 @@ struct StatsM // written by fanout_kernel, one per work item
     uint32_t msgs, pad;
     unsigned long long events, hop_e, hop_w, hop_n, hop_s;
     double syn_e, den_e, proc;
+    double dup_e; // part of den_e spent in combined dendrite + soma units (also soma energy)
 };
 
 struct SomaSegment;
@@ -235,6 +238,7 @@ struct DevState
     uint32_t *tap_has;        // [n_neurons] the soma has an input waiting
     double *hh;            // [5][n_hh]: V, m, n, h, I
     uint32_t n_hh;
+    double *nf_u2, *nf_uint; // "neurofem" neurons: u2 and the integrated error (potential = v, u1 = u)
     StatsN *stats_n;
     StatsM *stats_m;
     sfe_step_record *log;  // ring of step records
@@ -525,6 +529,30 @@ __device__ __forceinline__ int hh_update(double *hh, const uint32_t n_hh, const 
     return ((prev_V < 25) && (V > 25)) ? SFE_STATUS_FIRED : SFE_STATUS_UPDATED;
 }
 
+// NeuroFEMModel::update + process_fem  plugins/neurofem.cpp:192-317 — the reference plugin compiled as a device functor,
+// for the call of the neuron phase (the first update of a timestep): the two accumulators filled by the previous
+// message phase are consumed, then the compartment is advanced. sigma_v = 0 is enforced at load: the noise term
+// sigma_v * N(0,1) is +-0 and leaves the potential unchanged. lambda_v rides in c.leak, lambda_d in c.input_decay.
+__device__ __forceinline__ int neurofem_update(const sfe_soma_class &c, double &v, double &u1, double &u2, double &u_int,
+        const double bias, const double acc1, const double acc2)
+{
+    const double lambda_d = c.input_decay, lambda_v = c.leak, dt = c.nf_dt;
+    u1 = u1 - lambda_d * dt * u1;
+    u2 = u2 - lambda_d * dt * u2;
+    u1 = u1 + acc1;
+    u2 = u2 + lambda_d * acc2;
+    const double u_err = u1 + bias;
+    u_int = u_int + dt * u_err;
+    v = v - (lambda_v * dt * v);
+    v = v + (dt * c.nf_kp * u_err) + (dt * c.nf_ki * u_int) + (dt * u2) + 0.0 - acc2;
+    if (v > c.threshold)
+    {
+        v = c.reset;
+        return SFE_STATUS_FIRED;
+    }
+    return SFE_STATUS_UPDATED;
+}
+
 // ---------------------------------------------------------------------------
 // K5: energy, counters, simple timing model. One thread per active core; the last
 // CTA to finish (ticket) folds the per-CTA partials in a fixed order and appends the
@@ -536,6 +564,7 @@ struct StepPartial
 {
     unsigned long long fired, updated, packets, hops, events;
     double syn_e, den_e, soma_e, net_e, max_gen, max_proc;
+    double dup_e;
 };
 
 __device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 (coherent) loads
@@ -552,6 +581,7 @@ __device__ __forceinline__ StepPartial load_partial(const StepPartial *p) // L2 
     r.net_e = __ldcg(&p->net_e);
     r.max_gen = __ldcg(&p->max_gen);
     r.max_proc = __ldcg(&p->max_proc);
+    r.dup_e = __ldcg(&p->dup_e);
     return r;
 }
 
@@ -566,6 +596,7 @@ __device__ __forceinline__ void fold_partial(StepPartial &b, const StepPartial &
     b.den_e += x.den_e;
     b.soma_e += x.soma_e;
     b.net_e += x.net_e;
+    b.dup_e += x.dup_e;
     b.max_gen = fmax(b.max_gen, x.max_gen);
     b.max_proc = fmax(b.max_proc, x.max_proc);
 }
@@ -581,6 +612,7 @@ __device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly
     p.den_e = warp_sum(p.den_e);
     p.soma_e = warp_sum(p.soma_e);
     p.net_e = warp_sum(p.net_e);
+    p.dup_e = warp_sum(p.dup_e);
     p.max_gen = warp_max(p.max_gen);
     p.max_proc = warp_max(p.max_proc);
     return p;
@@ -594,9 +626,9 @@ __device__ __forceinline__ StepPartial warp_fold(StepPartial p) // xor butterfly
 __device__ __forceinline__ StepPartial fold_core(
         const DevTables &t, const DevState &s, const uint32_t ci, const int lane, const uint32_t parity)
 {
-    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const CoreDev &core = t.cores[ci];
-    StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+    StatsN n = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0, 0.0};
     for (uint32_t g = lane; g < core.seg_count; g += 32)
     {
         const StatsN *x = s.stats_n + static_cast<size_t>(parity) * t.n_soma_segments + core.seg_begin + g;
@@ -606,8 +638,9 @@ __device__ __forceinline__ StepPartial fold_core(
         n.soma_e += __ldcg(&x->soma_e);
         n.dend_e += __ldcg(&x->dend_e);
         n.gen_sum += __ldcg(&x->gen_sum);
+        n.dup_e += __ldcg(&x->dup_e);
     }
-    StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+    StatsM m = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0};
     for (uint32_t g = lane; g < core.item_count; g += 32)
     {
         const StatsM *x = s.stats_m + core.item_begin + g;
@@ -620,6 +653,7 @@ __device__ __forceinline__ StepPartial fold_core(
         m.syn_e += __ldcg(&x->syn_e);
         m.den_e += __ldcg(&x->den_e);
         m.proc += __ldcg(&x->proc);
+        m.dup_e += __ldcg(&x->dup_e);
     }
     n.updated = warp_sum(n.updated);
     n.fired = warp_sum(n.fired);
@@ -627,6 +661,7 @@ __device__ __forceinline__ StepPartial fold_core(
     n.soma_e = warp_sum(n.soma_e);
     n.dend_e = warp_sum(n.dend_e);
     n.gen_sum = warp_sum(n.gen_sum);
+    n.dup_e = warp_sum(n.dup_e);
     m.msgs = warp_sum(m.msgs);
     m.events = warp_sum(m.events);
     m.hop_e = warp_sum(m.hop_e);
@@ -636,6 +671,7 @@ __device__ __forceinline__ StepPartial fold_core(
     m.syn_e = warp_sum(m.syn_e);
     m.den_e = warp_sum(m.den_e);
     m.proc = warp_sum(m.proc);
+    m.dup_e = warp_sum(m.dup_e);
     n.gen_sum += static_cast<double>(n.packets) * core.lat_axon_out;
     p.fired = n.fired;
     p.updated = n.updated;
@@ -644,7 +680,8 @@ __device__ __forceinline__ StepPartial fold_core(
     p.events = m.events;
     p.syn_e = m.syn_e;
     p.den_e = n.dend_e + m.den_e;
-    p.soma_e = n.soma_e;
+    p.soma_e = n.soma_e + m.dup_e; // events through a combined dendrite + soma unit cost it a neuron access each
+    p.dup_e = n.dup_e + m.dup_e;
     // sim_calculate_tile_energy / sim_calculate_core_energy  src/chip.cpp:1189-1261
     double hop = static_cast<double>(m.hop_e) * core.e_east;
     hop += static_cast<double>(m.hop_w) * core.e_west;
@@ -669,7 +706,7 @@ __device__ __forceinline__ void append_step_record(const DevTables &t, const Dev
     r.dendrite_energy = b.den_e;
     r.soma_energy = b.soma_e;
     r.network_energy = b.net_e;
-    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e;
+    r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e - b.dup_e; // a unit's energy once (src/chip.cpp:1224-1261)
     r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
     const long long cursor = s.step[1];
     s.log[cursor % s.log_cap] = r;
@@ -687,7 +724,7 @@ __device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s,
         if (lane == 0) s.core_partials[t.cores[c2].active_idx] = q;
     }
     __syncwarp();
-    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&s.core_partials[k]));
     b = warp_fold(b);
     if (lane == 0) append_step_record(t, s, b);
@@ -737,7 +774,7 @@ __device__ __forceinline__ void finalize_body(
     StepPartial *warp_part = reinterpret_cast<StepPartial *>(scratch);
     uint32_t &ticket_s = *reinterpret_cast<uint32_t *>(scratch + (kFinalThreads / 32) * sizeof(StepPartial));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const uint32_t a = block * (kFinalThreads / 32) + warp;
     if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane, s.fold_parity);
     if (lane == 0) warp_part[warp] = p;
@@ -754,7 +791,7 @@ __device__ __forceinline__ void finalize_body(
     if (ticket_s != nblocks - 1) return;
     // ---- last CTA: fold the per-CTA partials and append the step record ------------------
     __threadfence();
-    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (uint32_t k = threadIdx.x; k < nblocks; k += kFinalThreads) fold_partial(b, load_partial(&s.partials[k]));
     b = warp_fold(b);
     __syncthreads(); // warp_part is reused
@@ -785,7 +822,7 @@ struct SomaSegment
     uint32_t k0;               // first neuron of the segment within the core
     uint32_t neuron_begin, neuron_count;
     uint32_t fired_word_begin;
-    uint32_t dend_base, ring, acc_mode, pad;
+    uint32_t dend_base, ring, acc_mode, fixed_slots;
     double inv_scale;
 };
 
@@ -819,8 +856,9 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     const long long T = steps_done + 1;
 
     uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
-    double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
-    const uint32_t slot = core.ring > 1 ? static_cast<uint32_t>(T % core.ring) : 0u;
+    double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0, dup_e = 0.0;
+    // the dendrite slot read this step: the rotating slot of a delay line, or slot 0 of fixed slots ("neurofem" cores)
+    const uint32_t slot = (core.ring > 1 && core.fixed_slots == 0u) ? static_cast<uint32_t>(T % core.ring) : 0u;
 
     // Every global load of the step is issued before the first use, speculatively: which of them
     // a neuron needs depends on its class, but waiting for the class first would put three
@@ -872,7 +910,57 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             double in = 0.0;
             bool tap_line = false;
             if constexpr (kExotic) tap_line = c.dend_model == SFE_DEND_TAPS;
-            if (tap_line)
+            bool neurofem = false;
+            if constexpr (kExotic) neurofem = c.model == SFE_SOMA_NEUROFEM;
+            double nf_acc1 = 0.0, nf_acc2 = 0.0;
+            if (neurofem)
+            {
+                // combined dendrite + soma unit: two accumulators (slot 0: u1, slot 1: u2) filled by the previous
+                // message phase, consumed here (next_*_dendritic_accumulator.value_or(0.0), plugins/neurofem.cpp:204-215)
+                const uint32_t d1 = d + core.neuron_count;
+                if (core.acc_mode == SFE_ACC_ORDERED)
+                {
+                    if (raw_cnt != 0u)
+                    {
+                        nf_acc1 = s.din64[d];
+                        s.din64[d] = 0.0;
+                        s.dcnt32[d] = 0u;
+                    }
+                    if (s.dcnt32[d1] != 0u)
+                    {
+                        nf_acc2 = s.din64[d1];
+                        s.din64[d1] = 0.0;
+                        s.dcnt32[d1] = 0u;
+                    }
+                }
+                else
+                {
+                    const uint32_t raw1 = s.din32[d1];
+                    int sum0, sum1;
+                    if (core.acc_mode == SFE_ACC_PACKED17)
+                    {
+                        sum0 = static_cast<int>(raw_sum - (((raw_sum + 0x10000u) >> 17) << 17));
+                        sum1 = static_cast<int>(raw1 - (((raw1 + 0x10000u) >> 17) << 17));
+                    }
+                    else if (core.acc_mode == SFE_ACC_PACKED32)
+                    {
+                        sum0 = (static_cast<int>(raw_sum << 12)) >> 12;
+                        sum1 = (static_cast<int>(raw1 << 12)) >> 12;
+                    }
+                    else
+                    {
+                        sum0 = static_cast<int>(raw_sum);
+                        sum1 = static_cast<int>(raw1);
+                        if (raw_cnt != 0u) s.dcnt32[d] = 0u;
+                        if (s.dcnt32[d1] != 0u) s.dcnt32[d1] = 0u;
+                    }
+                    nf_acc1 = static_cast<double>(sum0) * core.inv_scale;
+                    nf_acc2 = static_cast<double>(sum1) * core.inv_scale;
+                    if (raw_sum != 0u) s.din32[d] = 0u;
+                    if (raw1 != 0u) s.din32[d1] = 0u;
+                }
+            }
+            else if (tap_line)
             {
                 // the line's tap 0 after the last event of the previous step (taps_kernel); the accumulator cell
                 // the message phase filled for this neuron is ignored
@@ -968,6 +1056,15 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             else if constexpr (kExotic)
             {
                 if (c.model == SFE_SOMA_INPUT) st = input_update(t, t.inputs[t.neuron_aux[i]], steps_done, T);
+                else if (c.model == SFE_SOMA_NEUROFEM)
+                {
+                    double v = v0, u1 = u0, u2 = s.nf_u2[i], u_int = s.nf_uint[i];
+                    st = neurofem_update(c, v, u1, u2, u_int, bias, nf_acc1, nf_acc2);
+                    s.v[i] = v;
+                    s.u[i] = u1;
+                    s.nf_u2[i] = u2;
+                    s.nf_uint[i] = u_int;
+                }
                 else st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
             }
             s.status[i] = static_cast<uint8_t>(st);
@@ -986,6 +1083,12 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                 ++n_fired;
             }
             soma_e += e;
+            if constexpr (kExotic)
+                if ((c.flags & SFE_SOMA_IS_DENDRITE) != 0u)
+                {
+                    dend_e += e; // a combined unit's energy counts in the dendrite and the soma bucket, once in the total
+                    dup_e += e;
+                }
             lat_sum += lat + l;
         }
         // spike raster: one ballot per 32 neurons
@@ -1009,7 +1112,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         }
     }
     // ---- per-segment reductions: warp shuffles, one barrier -------------------------
-    __shared__ double part_d[kSomaThreads / 32][3];
+    __shared__ double part_d[kSomaThreads / 32][4];
     __shared__ uint32_t part_u[kSomaThreads / 32][3];
     n_updated = warp_sum(n_updated);
     n_fired = warp_sum(n_fired);
@@ -1017,6 +1120,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     soma_e = warp_sum(soma_e);
     dend_e = warp_sum(dend_e);
     lat_sum = warp_sum(lat_sum);
+    if constexpr (kExotic) dup_e = warp_sum(dup_e);
     const int warp = threadIdx.x >> 5;
     if (lane == 0)
     {
@@ -1026,11 +1130,12 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         part_d[warp][0] = soma_e;
         part_d[warp][1] = dend_e;
         part_d[warp][2] = lat_sum;
+        part_d[warp][3] = dup_e;
     }
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        StatsN out = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0};
+        StatsN out = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0, 0.0};
         for (int w = 0; w < kSomaThreads / 32; ++w) // fixed order: deterministic sums
         {
             out.updated += part_u[w][0];
@@ -1039,6 +1144,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             out.soma_e += part_d[w][0];
             out.dend_e += part_d[w][1];
             out.gen_sum += part_d[w][2]; // finalize adds packets * latency_axon_out per core
+            out.dup_e += part_d[w][3];
         }
         // gen_sum: sum of generation delays incl. the trailing placeholder message
         // (src/chip.cpp:640-652, 821-823; src/schedule.cpp:81)
@@ -1166,8 +1272,10 @@ struct FanoutCounters
     uint32_t msgs;
     unsigned long long events, hop_e, hop_w, hop_n, hop_s;
     double syn_e, den_e, proc;
+    double dup_e; // part of den_e spent in combined dendrite + soma units (only tracked outside the q4-only kernel)
 };
 
+template <bool kDup>
 __device__ __forceinline__ void account_axon(
         FanoutCounters &c, const sfe_axon_in &ax, const sfe_cost_class &cc, const double lat_axon_in)
 {
@@ -1181,6 +1289,7 @@ __device__ __forceinline__ void account_axon(
     {
         c.syn_e += cc.syn_energy;
         c.den_e += cc.den_energy;
+        if (kDup && cc.den_is_soma != 0u) c.dup_e += cc.den_energy;
         c.proc += lat_axon_in + cc.syn_latency;
     }
     else
@@ -1188,6 +1297,7 @@ __device__ __forceinline__ void account_axon(
         const double n = static_cast<double>(ax.syn_count);
         c.syn_e += n * cc.syn_energy;
         c.den_e += n * cc.den_energy;
+        if (kDup && cc.den_is_soma != 0u) c.dup_e += n * cc.den_energy;
         c.proc += lat_axon_in + n * (cc.syn_latency + cc.den_latency);
     }
 }
@@ -1198,11 +1308,19 @@ struct ChunkCursor
     uint2 ent; // (padded segment offset, synapse count) of list entry e
 };
 
+// dendrite slot of a synaptic event: the slot of a delay line that is read at timestep T + 1 + delay, or - fixed slots -
+// the compartment the synapse names in its delay field
+__device__ __forceinline__ uint32_t dendrite_slot(const uint32_t ring, const bool fixed, const long long T, const uint32_t m)
+{
+    if (ring <= 1u) return 0u;
+    return fixed ? SFE_SYN_DELAY(m) : static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring);
+}
+
 __device__ __forceinline__ void accumulate_one(uint32_t *acc32, uint32_t *cnt32, const uint32_t P, const uint32_t ring,
-        const long long T, const double scale, const uint32_t packed_one, const double w, const uint32_t m)
+        const bool fixed_slots, const long long T, const double scale, const uint32_t packed_one, const double w, const uint32_t m)
 {
     const uint32_t post = SFE_SYN_POST(m);
-    const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
+    const uint32_t sl = dendrite_slot(ring, fixed_slots, T, m);
     const int fixed = __double2int_rn(w * scale);
     // packed cells: sum + count * 2^20 (PACKED32) or sum + count * 2^17 (PACKED17)
     if (packed_one != 0u) atomicAdd(&acc32[sl * P + post], packed_one + static_cast<uint32_t>(fixed));
@@ -1257,8 +1375,19 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 //                  stream only (it is also a branch of the other two for mixed engines)
 constexpr int kStreamScalar = 0, kStreamTma = 2, kStreamQ4 = 3;
 constexpr int kQ4CtasPerSm = 4;
-constexpr int kQ4Stages = 8;        // per-warp ring of 512-byte chunks filled by cp.async (4-byte records)
-constexpr int kQ4StageBytes = 512;  // 128 records
+#ifndef SFE_Q4_STAGES
+#define SFE_Q4_STAGES 8
+#endif
+#ifndef SFE_Q4_BULK
+#define SFE_Q4_BULK 0
+#endif
+constexpr int kQ4Stages = SFE_Q4_STAGES; // per-warp ring of 512-byte chunks (4-byte records)
+constexpr int kQ4StageBytes = 512;       // 128 records
+// SFE_Q4_BULK: the q4-only instantiation fills its rings with cp.async.bulk (one TMA copy per chunk, issued by lane 0,
+// mbarrier completion) instead of one 16-byte cp.async per lane
+constexpr bool kQ4Bulk = SFE_Q4_BULK != 0;
+constexpr int kQ4BarBytes = kQ4Bulk ? kFanoutWarps * kQ4Stages * 8 : 0;
+static_assert(kQ4Stages * kQ4StageBytes <= 6144, "a warp's 4-byte-record ring reuses its TMA stages in mixed engines");
 constexpr int kTmaStages = 4;
 constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta words
 
@@ -1267,7 +1396,7 @@ template <int V, bool kFused>
 __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double part_d[kFanoutWarps][3];
+    __shared__ double part_d[kFanoutWarps][4];
     __shared__ unsigned long long part_l[kFanoutWarps][6];
     __shared__ sfe_cost_class cost_cache[kCostCache];
     __shared__ uint32_t next_item, list_n, list_total;
@@ -1284,10 +1413,19 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     // staging area at tma_off: the TMA stages + mbarriers (kStreamTma; a warp's 4-byte-record ring
     // reuses its stages), or the cp.async rings alone when the engine has 4-byte records
     const uint32_t list_off = tma_off + (V == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8)
-                                                          : (t.syn_q4 != nullptr ? kFanoutWarps * kQ4Stages * kQ4StageBytes : 0));
+                                                          : (t.syn_q4 != nullptr ? kFanoutWarps * kQ4Stages * kQ4StageBytes + kQ4BarBytes : 0));
     if constexpr (V == kStreamTma)
     {
         if (threadIdx.x < kFanoutWarps * kTmaStages) mbar_init(smem_addr(tma_bars + threadIdx.x), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned long long *q4_bars = reinterpret_cast<unsigned long long *>(tma_base + kFanoutWarps * kQ4Stages * kQ4StageBytes);
+    uint32_t q4_phase = 0u;
+    (void) q4_phase;
+    (void) q4_bars;
+    if constexpr (V == kStreamQ4 && kQ4Bulk)
+    {
+        if (threadIdx.x < kFanoutWarps * kQ4Stages) mbar_init(smem_addr(q4_bars + threadIdx.x), 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
@@ -1372,11 +1510,12 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     }
     __syncthreads();
 
-    FanoutCounters cnt = {0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+    FanoutCounters cnt = {0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0};
     const uint32_t n_words = item.word_hi; // this item's slice of the core's inbox: [word_lo, word_hi)
     const double *__restrict__ w_base = t.syn_w + core.syn_begin;
     const uint32_t *__restrict__ m_base = t.syn_meta + core.syn_begin;
     const uint32_t ring = V == kStreamQ4 ? 1u : core.ring;
+    const bool fixed_slots = V != kStreamQ4 && core.fixed_slots != 0u;
 
     if (acc_mode != SFE_ACC_ORDERED)
     {
@@ -1441,7 +1580,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 ax.syn_count = raw.y;
                 ax.hop = raw.z;
                 ax.cost_class = raw.w;
-                account_axon(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
+                account_axon<V != kStreamQ4>(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
                 if (!is_q4) list[e] = make_uint2(ax.syn_off, ax.syn_count);
                 else
                 {
@@ -1480,7 +1619,58 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             cur.count = n_list;
             cur.stride = kFanoutWarps;
             cur.ent = list[warp];
-            if (is_q4)
+            if constexpr (V == kStreamQ4 && kQ4Bulk)
+            {
+                // 4-byte records through the TMA engine: lane 0 issues ONE bulk copy per chunk into the warp's ring
+                // (mbarrier completion), every lane reads back its 16 bytes (lane-major layout, q4_position) and adds
+                // its four records; a warp barrier precedes the refill of a stage.
+                const uint32_t acc_s = smem_addr(acc32);
+                const uint32_t ring_w = smem_addr(tma_base + warp * kQ4Stages * kQ4StageBytes);
+                const uint32_t bar0 = smem_addr(q4_bars + warp * kQ4Stages);
+                const uint32_t *q_core = t.syn_q4 + core.syn_begin;
+                const uint32_t n_total = min(list_total, static_cast<uint32_t>(kListCap));
+                const uint32_t my_chunks = (n_total - warp + kFanoutWarps - 1u) / kFanoutWarps;
+                const uint2 *my_list = list + warp;
+                auto add_q4 = [&](const uint32_t qv) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + (qv & 0x3FFCu)), "r"(qv >> 14) : "memory");
+                };
+                auto issue = [&](const uint32_t c, const int st) {
+                    if (c < my_chunks && lane == 0)
+                    {
+                        const uint2 ent = my_list[c * kFanoutWarps];
+                        mbar_expect_tx(bar0 + 8u * st, ent.y * 16u);
+                        bulk_g2s(ring_w + st * kQ4StageBytes, q_core + ent.x, ent.y * 16u, bar0 + 8u * st);
+                    }
+                };
+#pragma unroll
+                for (int st = 0; st < kQ4Stages; ++st) issue(st, st);
+                for (uint32_t c0 = 0; c0 < my_chunks; c0 += kQ4Stages)
+                {
+#pragma unroll
+                    for (int st = 0; st < kQ4Stages; ++st)
+                    {
+                        const uint32_t c = c0 + st;
+                        if (c >= my_chunks) break;
+                        mbar_wait(bar0 + 8u * st, (q4_phase >> st) & 1u);
+                        q4_phase ^= 1u << st;
+                        if (lane < my_list[c * kFanoutWarps].y)
+                        {
+                            uint4 rec;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w)
+                                         : "r"(ring_w + st * kQ4StageBytes + 16 * lane)
+                                         : "memory");
+                            add_q4(rec.x);
+                            add_q4(rec.y);
+                            add_q4(rec.z);
+                            add_q4(rec.w);
+                        }
+                        __syncwarp(); // every lane has read the stage before it is refilled
+                        issue(c + kQ4Stages, st);
+                    }
+                }
+            }
+            else if (is_q4)
             {
                 // 4-byte records (q4_record). Each warp owns a ring of kQ4Stages 512-byte chunks in shared
                 // memory filled by cp.async: lane l moves the l-th 16 bytes of a chunk and, thanks to the
@@ -1594,7 +1784,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                         for (int u = 0; u < 4; ++u)
                         {
                             const uint32_t j = lane + 32u * u;
-                            if (j < rem_s[st]) accumulate_one(acc32, cnt32, P, ring, T, core.scale, packed, ws[j], ms[j]);
+                            if (j < rem_s[st]) accumulate_one(acc32, cnt32, P, ring, fixed_slots, T, core.scale, packed, ws[j], ms[j]);
                         }
                         __syncwarp(); // every lane is done with the stage before it is refilled
                         rem_s[st] = issue(st);
@@ -1634,7 +1824,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (cvalid & (1u << u)) accumulate_one(acc32, cnt32, P, ring, T, core.scale, packed, cw[u], cm[u]);
+                        if (cvalid & (1u << u)) accumulate_one(acc32, cnt32, P, ring, fixed_slots, T, core.scale, packed, cw[u], cm[u]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                     {
@@ -1673,7 +1863,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 const uint32_t b = __ffs(word) - 1;
                 word &= word - 1u;
                 const sfe_axon_in ax = t.axons_in[core.axon_begin + (wi << 5) + b];
-                if (lane == 0) account_axon(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
+                if (lane == 0) account_axon<true>(cnt, ax, cost_table[ax.cost_class], core.lat_axon_in);
                 if (!accumulate) continue;
                 for (uint32_t j0 = 0; j0 < ax.syn_count; j0 += 32)
                 {
@@ -1685,8 +1875,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                     {
                         w = __ldg(w_base + ax.syn_off + j);
                         const uint32_t m = __ldg(m_base + ax.syn_off + j);
-                        const uint32_t sl = ring > 1 ? static_cast<uint32_t>((T + 1 + SFE_SYN_DELAY(m)) % ring) : 0u;
-                        cell = sl * P + SFE_SYN_POST(m);
+                        cell = dendrite_slot(ring, fixed_slots, T, m) * P + SFE_SYN_POST(m);
                     }
                     // lanes that hit the same cell add one after the other, lowest lane first
                     const uint32_t peers = __match_any_sync(0xffffffffu, cell);
@@ -1758,8 +1947,11 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
         const double v_se = warp_sum(cnt.syn_e);
         const double v_de = warp_sum(cnt.den_e);
         const double v_pr = warp_sum(cnt.proc);
+        double v_dup = 0.0;
+        if constexpr (V != kStreamQ4) v_dup = warp_sum(cnt.dup_e);
         if (lane == 0)
         {
+            part_d[warp][3] = v_dup;
             part_l[warp][0] = v_msgs;
             part_l[warp][1] = v_events;
             part_l[warp][2] = v_he;
@@ -1773,7 +1965,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
         __syncthreads();
         if (threadIdx.x == 0)
         {
-            StatsM out = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0};
+            StatsM out = {0u, 0u, 0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0};
             for (int w = 0; w < kFanoutWarps; ++w)
             {
                 out.msgs += static_cast<uint32_t>(part_l[w][0]);
@@ -1785,6 +1977,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 out.syn_e += part_d[w][0];
                 out.den_e += part_d[w][1];
                 out.proc += part_d[w][2];
+                out.dup_e += part_d[w][3];
             }
             s.stats_m[item_id] = out;
         }
@@ -2000,6 +2193,7 @@ struct sfe_engine
     unsigned final_grid{1};
     uint32_t n_segments{0};
     bool exotic{false};
+    bool neurofem{false}; // the chip maps "neurofem" neurons (extra state arrays)
     // multi-GPU partition (contiguous core ranges)
     uint32_t rank{0}, world{1};
     std::vector<uint32_t> owner;      // rank that simulates each core
@@ -2029,6 +2223,7 @@ struct sfe_engine
     // whole-vector bias uploads are double-buffered and travel on their own stream, so that the
     // upload for the next step overlaps the kernels of the current one
     double *bias_buf[2] = {nullptr, nullptr};
+    double *bias_stage{nullptr}; // pinned staging of sfe_engine_set_bias_staged
     int bias_cur{0}, bias_pending{-1};
     cudaStream_t copy_stream{nullptr};
     cudaEvent_t bias_ready[2] = {nullptr, nullptr}, bias_free[2] = {nullptr, nullptr};
@@ -2126,8 +2321,10 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
         if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH ||
-                (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
+                tb->soma_classes[k].model == SFE_SOMA_NEUROFEM || (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
             e->exotic = true;
+    for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
+        if (tb->soma_classes[k].model == SFE_SOMA_NEUROFEM) e->neurofem = true;
     e->potential0.assign(tb->neuron_potential0, tb->neuron_potential0 + tb->n_neurons);
     if (tb->n_hh > 0) e->hh_init.assign(tb->hh, tb->hh + tb->n_hh);
 
@@ -2158,6 +2355,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         d.ring = cd.ring == 0 ? 1 : cd.ring;
         d.acc_mode = cd.acc_mode;
         d.dend_in_msg = cd.dend_in_msg;
+        d.fixed_slots = cd.fixed_slots;
         d.tile = cd.tile;
         d.syn_begin = cd.syn_begin;
         d.scale = std::ldexp(1.0, cd.weight_shift);
@@ -2523,7 +2721,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                 g.dend_base = d.dend_base;
                 g.ring = d.ring;
                 g.acc_mode = d.acc_mode;
-                g.pad = 0;
+                g.fixed_slots = d.fixed_slots;
                 g.inv_scale = d.inv_scale;
                 segs.push_back(g);
             }
@@ -2557,6 +2755,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.din64, e->ordered_any ? dend_cells : 1) != 0) return -1;
     if (e->alloc(&e->s.hh, 5 * static_cast<size_t>(tb->n_hh)) != 0) return -1;
     e->s.n_hh = tb->n_hh;
+    if (e->alloc(&e->s.nf_u2, e->neurofem ? tb->n_neurons : 1) != 0) return -1;
+    if (e->alloc(&e->s.nf_uint, e->neurofem ? tb->n_neurons : 1) != 0) return -1;
     if (e->alloc(&e->s.stats_n, 2 * static_cast<size_t>(e->n_segments)) != 0) return -1; // double-buffered by step parity
     e->log_cap = 4096;
     e->s.log_cap = e->log_cap;
@@ -2619,7 +2819,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->tma_off = static_cast<uint32_t>((smem_max + 127) & ~static_cast<size_t>(127));
     smem_max = e->tma_off +
             (e->fanout_variant == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8)
-                                             : (e->q4_any ? kFanoutWarps * kQ4Stages * kQ4StageBytes : 0)) +
+                                             : (e->q4_any ? kFanoutWarps * kQ4Stages * kQ4StageBytes + kQ4BarBytes : 0)) +
             kListCap * sizeof(uint2);
     e->fanout_smem = smem_max;
     if (smem_max > 200 * 1024)
@@ -2791,6 +2991,7 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
+    if (e->bias_stage != nullptr) cudaFreeHost(e->bias_stage);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
     if (e->ev_end != nullptr) cudaEventDestroy(e->ev_end);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
@@ -3248,6 +3449,12 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
     if (e->ordered_any || e->dual_any) SFE_CUDA(cudaMemsetAsync(e->s.dcnt32, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(uint32_t), e->stream));
     if (e->ordered_any) SFE_CUDA(cudaMemsetAsync(e->s.din64, 0, std::max<size_t>(e->dend_cells, 1) * sizeof(double), e->stream));
     if (e->n_hh > 0) SFE_CUDA(cudaMemsetAsync(e->s.hh, 0, 4 * static_cast<size_t>(e->n_hh) * sizeof(double), e->stream));
+    if (e->neurofem)
+    {
+        // NeuroFEMModel::reset  plugins/neurofem.cpp:319-335 (the accumulators are the dendrite cells cleared above)
+        SFE_CUDA(cudaMemsetAsync(e->s.nf_u2, 0, e->n_neurons * sizeof(double), e->stream));
+        SFE_CUDA(cudaMemsetAsync(e->s.nf_uint, 0, e->n_neurons * sizeof(double), e->stream));
+    }
     if (e->n_taps_units > 0)
     {
         // MultiTapModel1D::reset  src/models.cpp:340-348: voltages only (the lines' step counters run on)
@@ -3303,6 +3510,23 @@ extern "C" int sfe_engine_set_bias(sfe_engine *e, const double *bias, size_t n)
     return 0;
 }
 
+// The same from pageable host memory (the chip object's bias table after MappedNeuron.set_attributes patches): the
+// vector is first copied into an engine-owned pinned buffer, so the host->device transfer is a DMA like the one above
+// and the caller's memory is free again on return.
+extern "C" int sfe_engine_set_bias_staged(sfe_engine *e, const double *bias, size_t n)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n != e->n_neurons)
+    {
+        sfe::set_last_error("sfe_engine_set_bias_staged: expected one bias per neuron");
+        return -1;
+    }
+    if (e->bias_stage == nullptr) SFE_CUDA(cudaMallocHost(reinterpret_cast<void **>(&e->bias_stage), std::max<size_t>(n, 1) * sizeof(double)));
+    if (e->copy_stream != nullptr) SFE_CUDA(cudaStreamSynchronize(e->copy_stream)); // the previous upload has left the buffer
+    std::memcpy(e->bias_stage, bias, n * sizeof(double));
+    return sfe_engine_set_bias(e, e->bias_stage, n);
+}
+
 extern "C" int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double bias)
 {
     SFE_CUDA(cudaSetDevice(e->device));
@@ -3313,6 +3537,19 @@ extern "C" int sfe_engine_set_neuron_bias(sfe_engine *e, uint32_t neuron, double
     }
     if (apply_pending_bias(e) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias + neuron, &bias, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int sfe_engine_set_neuron_potential(sfe_engine *e, uint32_t neuron, double potential)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (neuron >= e->n_neurons)
+    {
+        sfe::set_last_error("sfe_engine_set_neuron_potential: neuron out of range");
+        return -1;
+    }
+    SFE_CUDA(cudaMemcpyAsync(e->s.v + neuron, &potential, sizeof(double), cudaMemcpyHostToDevice, e->stream));
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -3361,6 +3598,8 @@ extern "C" int sfe_engine_read_raster(sfe_engine *e, uint32_t *words, size_t n_w
         return -1;
     }
     const uint32_t *src = e->world > 1 ? e->d_fired_global : e->d_fired_local;
+    // peer-memory exchange: the ranks store their slices straight into this rank's double-buffered raster
+    if (e->p2p_on && e->s.step_seq > 0) src = e->p2p_block + ((e->s.step_seq - 1ull) & 1ull) * e->fired_words;
     SFE_CUDA(cudaMemcpyAsync(words, src, n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;

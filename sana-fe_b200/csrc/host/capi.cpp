@@ -161,7 +161,7 @@ int flush_bias(sfe_chip *c)
 {
     if (!c->bias_dirty || c->engine == nullptr) return 0;
     c->bias_dirty = false;
-    return sfe_engine_set_bias(c->engine, c->tables.neuron_bias.data(), c->tables.neuron_bias.size());
+    return sfe_engine_set_bias_staged(c->engine, c->tables.neuron_bias.data(), c->tables.neuron_bias.size());
 }
 
 int attach_engine(sfe_chip *c)
@@ -637,16 +637,14 @@ extern "C" int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uin
             [&]() -> int {
                 const int64_t idx = c->tables.find_neuron(group, offset);
                 if (idx < 0) throw std::out_of_range(std::string("no mapped neuron ") + group + "." + std::to_string(offset));
-                const bool classes_changed = sfe::patch_neuron_attribute(c->tables, static_cast<uint32_t>(idx), name, value);
+                const sfe::PatchKind kind = sfe::patch_neuron_attribute(c->tables, static_cast<uint32_t>(idx), name, value);
                 if (c->engine == nullptr) return 0;
-                if (std::string(name) == "bias")
-                {
-                    c->bias_dirty = true; // uploaded with the next sfe_chip_sim / sfe_chip_engine call
-                    return 0;
-                }
-                if (classes_changed)
+                if (kind == sfe::PatchKind::bias) c->bias_dirty = true; // uploaded with the next sfe_chip_sim / sfe_chip_engine call
+                else if (kind == sfe::PatchKind::classes)
                     return sfe_engine_update_classes(c->engine, c->tables.soma_classes.data(),
                             static_cast<uint32_t>(c->tables.soma_classes.size()), c->tables.neuron_class.data());
+                else if (kind == sfe::PatchKind::potential)
+                    return sfe_engine_set_neuron_potential(c->engine, static_cast<uint32_t>(idx), value);
                 return 0;
             },
             -1);

@@ -30,7 +30,8 @@ enum class UnitModel
     truenorth,
     input,
     hodgkin_huxley,
-    taps
+    taps,
+    neurofem
 };
 
 struct UnitKey
@@ -59,6 +60,7 @@ struct UnitState // one used hardware unit instance of one core
     size_t n_taps{1};
     std::vector<double> time_constants{0.0}, space_constants{};
     std::vector<int> synapse_to_tap; // by synapse address (set_attribute_edge "tap", src/models.cpp:320-332)
+    std::vector<uint8_t> synapse_to_compartment; // "neurofem": by synapse address (plugins/neurofem.cpp:120-136), default 0
     uint32_t noise_off{0}, noise_len{0}; // LIF unit with a noise file: its entries in HostTables::noise_values
     bool noise_loaded{false};
     std::vector<uint32_t> sharing; // device-order list of neurons mapped to this unit (filled later)
@@ -112,6 +114,7 @@ UnitModel parse_model(const PipelineUnitConfiguration &u)
         // The device path needs a device functor; the models shipped with the
         // reference are compiled in. Anything else cannot run "with no CPU fallback".
         if (m == "hodgkin_huxley") return UnitModel::hodgkin_huxley;
+        if (m == "neurofem") return UnitModel::neurofem;
         throw std::runtime_error("Plugin model '" + m + "' (" + *u.model_info.plugin_library_path +
                 ") has no device functor registered; host-only plugins are not supported by the B200 engine");
     }
@@ -191,13 +194,23 @@ uint32_t parse_reset_mode(const std::string &s) // src/models.cpp:905-931
     throw std::invalid_argument("Reset mode not recognized");
 }
 
+// A unit that appears in several sections of a core implements several pipeline functions (src/pipeline.hpp:307-420:
+// its input interface is that of the first function, its output interface that of the last). The built-in models each
+// implement one function; the combined unit among the shipped models is the "neurofem" plugin (dendrite + soma,
+// plugins/neurofem.cpp:33-37, arch/neurofem.yaml).
 void check_unit_shape(const PipelineUnitConfiguration &u)
 {
     const int functions = int(u.implements_synapse) + int(u.implements_dendrite) + int(u.implements_soma);
-    if (functions != 1)
-        throw std::runtime_error("Hardware unit '" + u.name +
-                "' implements several pipeline functions at once; combined units are not implemented by the B200 "
-                "engine yet");
+    if (functions == 1) return;
+    if (u.implements_synapse && u.implements_soma && !u.implements_dendrite) // src/pipeline.hpp:343-350
+        throw std::logic_error("Invalid pipeline configuration: h/w supports synapse and soma but not dendrite functionality. "
+                               "To fix this, either add this to the core's dendrite section, or remove from either the "
+                               "synapse or soma sections.");
+    const bool neurofem = u.model_info.plugin_library_path.has_value() && u.model_info.name == "neurofem";
+    if (neurofem && u.implements_dendrite && u.implements_soma && !u.implements_synapse) return;
+    throw std::runtime_error("Hardware unit '" + u.name + "' (model " + u.model_info.name +
+            ") is listed in several sections of its core: of the models this engine carries only 'neurofem' is a combined "
+            "(dendrite + soma) unit");
 }
 
 void soma_defaults(const PipelineUnitConfiguration &u, const UnitModel model, sfe_soma_class &c)
@@ -221,6 +234,11 @@ void soma_defaults(const PipelineUnitConfiguration &u, const UnitModel model, sf
         break;
     case UnitModel::hodgkin_huxley:
         c.model = SFE_SOMA_HH;
+        break;
+    case UnitModel::neurofem:
+        c.model = SFE_SOMA_NEUROFEM; // NeuroFEMNeuron defaults  plugins/neurofem.cpp:64-84: everything 0 but dt
+        c.nf_dt = 1.0e-3;
+        c.flags = SFE_SOMA_IS_DENDRITE;
         break;
     default:
         throw std::runtime_error("Unit '" + u.name + "' is not a soma model");
@@ -357,6 +375,27 @@ void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, con
         }
         else if (key == "rate") unit.rate = a.as_double();
     }
+    else if (model == UnitModel::neurofem)
+    {
+        // NeuroFEMModel::set_attribute_neuron  plugins/neurofem.cpp:138-190
+        if (key == "threshold") c.threshold = a.as_double();
+        else if (key == "reset") c.reset = a.as_double();
+        else if (key == "lambda_d") c.input_decay = a.as_double();
+        else if (key == "lambda_v") c.leak = a.as_double();
+        else if (key == "bias") ln.bias = a.as_double();
+        else if (key == "dt") c.nf_dt = a.as_double();
+        else if (key == "kp") c.nf_kp = a.as_double();
+        else if (key == "ki") c.nf_ki = a.as_double();
+        else if (key == "sigma_v")
+        {
+            // the noise term is sigma_v * N(0,1) drawn from a generator seeded by std::random_device
+            // (plugins/neurofem.cpp:26-29, 303): only sigma_v = 0 has a reference result to match
+            if (a.as_double() != 0.0)
+                throw std::runtime_error("neurofem sigma_v != 0 adds noise from a std::random_device-seeded generator "
+                                         "(plugins/neurofem.cpp:26-29), which no run of the reference reproduces; use sigma_v: 0");
+        }
+        // force_update / force_soma_update are stored but never read by the model's update()
+    }
     else if (model == UnitModel::hodgkin_huxley)
     {
         if (key == "m") unit.hh_m = a.as_double();
@@ -400,10 +439,12 @@ struct CostKey
 {
     double v[4];
     uint32_t per_message;
+    uint32_t den_is_soma;
     bool operator<(const CostKey &o) const
     {
         const int c = std::memcmp(v, o.v, sizeof(v));
-        return c != 0 ? c < 0 : per_message < o.per_message;
+        if (c != 0) return c < 0;
+        return per_message != o.per_message ? per_message < o.per_message : den_is_soma < o.den_is_soma;
     }
 };
 
@@ -421,6 +462,7 @@ uint32_t intern_cost(std::map<CostKey, uint32_t> &index, std::vector<sfe_cost_cl
     c.den_energy = k.v[2];
     c.den_latency = k.v[3];
     c.per_message = k.per_message;
+    c.den_is_soma = k.den_is_soma;
     classes.push_back(c);
     const uint32_t id = static_cast<uint32_t>(classes.size() - 1);
     if (share) index[k] = id;
@@ -484,15 +526,23 @@ void fill_arch_tables(const Architecture &arch, HostTables &out)
     }
 }
 
+// Where the time-step buffer sits decides which units run in the message pipeline and which in the neuron pipeline
+// (src/mapped.cpp:40-58, 171-187). Supported: inside the dendrite unit, before the soma unit, and inside the soma unit
+// for neurons whose soma keeps its own double-buffered inputs (the combined "neurofem" unit; "input" somas, which
+// take no input). The other combinations have no meaningful result in the reference either:
+//  * inside the soma unit / before axon_out with a separate soma unit put the soma in the MESSAGE pipeline: it is
+//    updated once per synaptic event; the LIF model throws at the second update of a step or a skipped step
+//    (src/models.cpp:502-511), so such a chip stops at the first neuron that receives two spikes;
+//  * before the dendrite unit keeps only the LAST synaptic current of a step in the buffer
+//    (core.timestep_buffer[post] = pipeline_output, src/chip.cpp:759) - an order-dependent loss, not a model.
 void check_buffer_position(const CoreConfiguration &c)
 {
-    if (c.pipeline.buffer_position == buffer_inside_soma_unit ||
-            c.pipeline.buffer_position == buffer_before_axon_out_unit ||
-            c.pipeline.buffer_position == buffer_before_dendrite_unit)
+    if (c.pipeline.buffer_position == buffer_before_axon_out_unit || c.pipeline.buffer_position == buffer_before_dendrite_unit)
     {
         throw std::runtime_error("Core '" + c.name +
-                "': buffer positions before the dendrite unit, inside the soma unit and before axon_out are not "
-                "implemented by the B200 engine yet (supported: dendrite+buffer_inside_unit, soma)");
+                "': the buffer positions before the dendrite unit (keeps only the last synaptic current of a step) and "
+                "before axon_out (updates the soma once per synaptic event; the built-in LIF model throws on it) are not "
+                "supported by the B200 engine (supported: dendrite+buffer_inside_unit, soma, soma+buffer_inside_unit)");
     }
 }
 } // namespace
@@ -651,10 +701,36 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         ln.dend_unit = &lc.units[ln.dend]; // (looked up again: inserting the soma unit cannot move it, but `dend` may alias)
         ln.soma_unit = &soma;
         if (dend.model != UnitModel::accumulator && dend.model != UnitModel::accumulator_with_delay &&
-                dend.model != UnitModel::taps)
+                dend.model != UnitModel::taps && dend.model != UnitModel::neurofem)
             throw std::runtime_error("Unit '" + dend_cfg.name + "' is not a dendrite model");
-        if (dend.model == UnitModel::taps && cfg.pipeline.buffer_position != buffer_before_soma_unit)
-            throw std::runtime_error("a 'taps' dendrite is only supported with the buffer before the soma unit");
+        const bool combined = soma.model == UnitModel::neurofem;
+        if (combined)
+        {
+            // the combined unit double-buffers its two accumulators itself (plugins/neurofem.cpp:204-215): with the
+            // buffer inside the dendrite unit, before or inside the soma unit it runs once per synaptic event in the
+            // message pipeline and once per timestep in the neuron pipeline, and the chip-managed buffer carries nothing
+            if (!(ln.dend == ln.soma))
+                throw std::runtime_error("a 'neurofem' unit is a combined dendrite + soma unit: map the neuron's dendrite "
+                                         "and soma to the same unit (dendrite_hw_name = soma_hw_name)");
+            // Core::map_neuron maps a neuron to a combined unit once (src/core.cpp:155-165): one address
+            --soma.neuron_count;
+            ln.soma_addr = ln.dend_addr;
+        }
+        else if (dend.model == UnitModel::neurofem)
+        {
+            // e.g. the "input" neurons of arch/neurofem.yaml, whose default dendrite unit is the first one of the core:
+            // they take a slot of the combined unit, which never runs for them as long as no edge reaches them
+            if (soma.model != UnitModel::input || cfg.pipeline.buffer_position < buffer_before_soma_unit)
+                throw std::runtime_error("a 'neurofem' unit as the dendrite of another soma model is only supported for "
+                                         "'input' neurons with the buffer before or inside the soma unit");
+        }
+        else if (cfg.pipeline.buffer_position == buffer_inside_soma_unit && soma.model != UnitModel::input)
+            throw std::runtime_error("Core '" + cfg.name + "': with the buffer inside the soma unit a separate soma unit is "
+                    "updated once per synaptic event (src/mapped.cpp:52-57); the built-in LIF model throws on that "
+                    "(src/models.cpp:502-511). Supported somas there: 'neurofem' (combined unit) and 'input'");
+        if (dend.model == UnitModel::neurofem && ln.dend_addr >= 1024)
+            throw std::runtime_error("Error: Mapped too many neurons for NeuroFEM (" + std::to_string(ln.dend_addr + 1) +
+                    "> 1024)"); // plugins/neurofem.cpp:99-112
         // capacity of the built-in models' state tables (src/models.hpp:29,283)
         if (ln.dend_addr >= kLifMaxCompartments)
             throw std::out_of_range("dendrite unit '" + dend_cfg.name + "' holds at most 1024 neurons");
@@ -685,8 +761,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         }
         ln.cls.dend_model = dend.model == UnitModel::accumulator ? SFE_DEND_ACCUMULATOR
                 : dend.model == UnitModel::taps                  ? SFE_DEND_TAPS
+                : dend.model == UnitModel::neurofem              ? SFE_DEND_NEUROFEM
                                                                  : SFE_DEND_ACCUMULATOR_DELAY;
-        ln.cls.dend_in_neuron = cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit ? 1 : 0;
+        // a combined unit is pushed once into the neuron pipeline (src/mapped.cpp:171-187) and its output interface is
+        // the soma's: no separate dendrite cost
+        ln.cls.dend_in_neuron = (cfg.pipeline.buffer_position <= buffer_inside_dendrite_unit && !combined) ? 1 : 0;
         if (ln.cls.dend_in_neuron != 0)
         {
             ln.cls.dend_energy_update = unit_double(dend_cfg, "energy_update", "Dendrite");
@@ -700,7 +779,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                         "' cannot be used as a model attribute. Pass it as a direct argument instead (if supported).");
             // the accumulators take no per-neuron attributes (src/models.hpp:80,133); "taps" does
             if (a.forward_to_dendrite && dend.model == UnitModel::taps) set_taps_attribute(dend, key, a);
-            if (a.forward_to_soma) set_soma_attribute(ln, soma, soma.model, key, a);
+            if (a.forward_to_soma || (combined && a.forward_to_dendrite)) set_soma_attribute(ln, soma, soma.model, key, a);
         }
         where[p.group][n.offset] = {static_cast<uint32_t>(n.core_address->id), static_cast<uint32_t>(lc.neurons.size())};
         lc.neurons.push_back(std::move(ln));
@@ -775,6 +854,14 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                         if (dend.synapse_to_tap.size() <= lcn.syn_addr) dend.synapse_to_tap.resize(lcn.syn_addr + 1, 0);
                         dend.synapse_to_tap[lcn.syn_addr] = a.as_int();
                     }
+                    if (a.forward_to_dendrite && dend.model == UnitModel::neurofem && key == "compartment")
+                    {
+                        // NeuroFEMModel::set_attribute_edge  plugins/neurofem.cpp:114-136 (by SYNAPSE address)
+                        const int compartment = a.as_int();
+                        if (compartment < 0 || compartment > 1) throw std::runtime_error("Error: compartment must be 0 or 1");
+                        if (dend.synapse_to_compartment.size() <= lcn.syn_addr) dend.synapse_to_compartment.resize(lcn.syn_addr + 1, 0);
+                        dend.synapse_to_compartment[lcn.syn_addr] = static_cast<uint8_t>(compartment);
+                    }
                     if (a.forward_to_dendrite && dend.model == UnitModel::accumulator_with_delay)
                     {
                         // the dendrite's delay table is addressed by the SYNAPSE address
@@ -789,6 +876,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 }
                 // InputModel::update throws the moment a non-zero current reaches an input neuron
                 // (src/models.cpp:866-874); a device engine cannot raise mid-step, so the edge is refused here
+                if (post.soma_unit->model == UnitModel::input &&
+                        (dend.model == UnitModel::neurofem || pc.cfg->pipeline.buffer_position == buffer_inside_soma_unit))
+                    throw std::runtime_error("edge into an 'input' neuron of a core whose buffer sits inside the soma unit (or "
+                            "whose dendrite is a combined unit): the reference would update the input unit once per synaptic "
+                            "event, advancing its spike train; not supported");
                 if (lcn.weight != 0.0 && post.soma_unit->model == UnitModel::input)
                     throw std::runtime_error("Current sent to input neuron which cannot be processed (" +
                             std::to_string(lcn.weight) + "): edge " + con.pre_neuron.group_name + "." +
@@ -968,7 +1060,7 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         sfe_core_desc &cd = out.cores[c];
         cd.syn_begin = out.syn_weight.size();
         uint32_t max_delay = 0;
-        bool core_has_taps = false;
+        bool core_has_taps = false, core_fixed_slots = false, core_has_delay = false;
         const size_t n_families = lc.cfg->pipeline_hw.size();
         std::vector<CostKey> pair_key(n_families * n_families);
         std::vector<uint8_t> pair_known(n_families * n_families, 0);
@@ -1001,7 +1093,16 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                     CostKey fresh{};
                     fresh.v[0] = unit_double(syn_cfg, "energy_process_spike", "Synapse");
                     fresh.v[1] = unit_double(syn_cfg, "latency_process_spike", "Synapse");
-                    if (cd.dend_in_msg != 0)
+                    const bool den_combined = den_cfg.model_info.plugin_library_path.has_value() && den_cfg.model_info.name == "neurofem";
+                    if (cd.dend_in_msg != 0 && den_combined)
+                    {
+                        // a combined dendrite + soma unit in the message pipeline: its output interface is the soma's, and
+                        // with the status unset an event costs one neuron access (src/pipeline.hpp:631-667)
+                        fresh.v[2] = unit_double(den_cfg, "energy_access_neuron", "Soma");
+                        fresh.v[3] = unit_double(den_cfg, "latency_access_neuron", "Soma");
+                        fresh.den_is_soma = 1;
+                    }
+                    else if (cd.dend_in_msg != 0)
                     {
                         fresh.v[2] = unit_double(den_cfg, "energy_update", "Dendrite");
                         fresh.v[3] = unit_double(den_cfg, "latency_update", "Dendrite");
@@ -1011,7 +1112,11 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 }
                 const CostKey key = pair_key[pair];
                 if (s == 0) first = key;
-                else if (std::memcmp(first.v, key.v, sizeof(key.v)) != 0) uniform = false;
+                else if (std::memcmp(first.v, key.v, sizeof(key.v)) != 0 || first.den_is_soma != key.den_is_soma) uniform = false;
+                if (s == 0) total.den_is_soma = key.den_is_soma;
+                else if (total.den_is_soma != key.den_is_soma)
+                    throw std::runtime_error("an axon whose synapses reach both a combined (dendrite + soma) unit and a plain "
+                                             "dendrite unit is not supported");
                 // per-message totals in the reference's summation order
                 // (src/chip.cpp:766-789: per synapse (0.0 + syn) + den, then message += that)
                 total.v[0] += key.v[0];
@@ -1026,6 +1131,13 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 uint32_t delay = 0;
                 if (dend.model == UnitModel::accumulator_with_delay && k.syn_addr < dend.delays.size())
                     delay = dend.delays[k.syn_addr];
+                if (dend.model == UnitModel::accumulator_with_delay && delay > 0) core_has_delay = true;
+                if (dend.model == UnitModel::neurofem)
+                {
+                    // the compartment (0: u1, 1: u2) rides in the delay field: the dendrite slot of the synapse
+                    delay = k.syn_addr < dend.synapse_to_compartment.size() ? dend.synapse_to_compartment[k.syn_addr] : 0u;
+                    core_fixed_slots = true;
+                }
                 max_delay = std::max(max_delay, delay);
                 if (dend.model == UnitModel::taps)
                 {
@@ -1045,6 +1157,16 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
         }
         cd.syn_count = out.syn_weight.size() - cd.syn_begin;
         cd.ring = max_delay + 1;
+        for (const LNeuron &ln : lc.neurons)
+            if (ln.soma_unit->model == UnitModel::neurofem) core_fixed_slots = true;
+        if (core_fixed_slots)
+        {
+            if (core_has_delay || core_has_taps)
+                throw std::runtime_error("Core '" + lc.cfg->name + "': 'neurofem' units cannot share a core with synapses that "
+                                         "carry accumulator delays or dendritic taps");
+            cd.fixed_slots = 1;
+            cd.ring = 2; // u1 and u2
+        }
         if (cd.syn_count > 0xffffffffull) throw std::runtime_error("more than 2^32 synapses on one core");
         // exactness certificate: every weight is k * 2^-s and the
         // per-post-neuron sums stay small enough for integer smem accumulators
@@ -1256,36 +1378,93 @@ void lower_synthetic(const Architecture &arch, const SynthRequest &req, const bo
     out.finalize_view(arch);
 }
 
-bool patch_neuron_attribute(HostTables &t, const uint32_t neuron, const std::string &name, const double value)
+// Post-load MappedNeuron::set_attributes (src/mapped.cpp:113-166) for one numeric attribute: the reference forwards
+// it to the neuron's soma (and dendrite) unit, whose set_attribute_neuron knows a model-specific key set
+// (src/models.cpp:375-439 LIF, 664-722 TrueNorth, 832-853 input; plugins/hodgkin_huxley.cpp:94-114;
+// plugins/neurofem.cpp:138-190). Keys a model does not know are ignored there and here; keys it honours but this
+// engine cannot change once the tables are on the device raise instead of being dropped silently.
+PatchKind patch_neuron_attribute(HostTables &t, const uint32_t neuron, const std::string &name, const double value)
 {
     if (neuron >= t.neuron_class.size()) throw std::out_of_range("neuron index out of range");
-    if (name == "bias")
-    {
-        t.neuron_bias[neuron] = value;
-        return false;
-    }
     sfe_soma_class c = t.soma_classes[t.neuron_class[neuron]];
-    if (name == "threshold") c.threshold = value;
-    else if (name == "reverse_threshold") c.reverse_threshold = value;
-    else if (name == "reset") c.reset = value;
-    else if (name == "reverse_reset") c.reverse_reset = value;
-    else if (name == "leak_decay" || name == "leak") c.leak = value;
-    else if (name == "input_decay") c.input_decay = value;
-    else return false; // unknown attributes are ignored by the built-in models (SURVEY B-13)
+    auto set_flag = [&](const uint32_t flag) { c.flags = value != 0.0 ? (c.flags | flag) : (c.flags & ~flag); };
+    auto frozen = [&](const char *why) -> PatchKind {
+        throw std::runtime_error("attribute '" + name + "' cannot be changed after load(): " + why);
+    };
+    switch (c.model)
+    {
+    case SFE_SOMA_LIF:
+        if (name == "bias") { t.neuron_bias[neuron] = value; return PatchKind::bias; }
+        if (name == "potential") { t.neuron_potential0[neuron] = value; return PatchKind::potential; }
+        if (name == "threshold") c.threshold = value;
+        else if (name == "reverse_threshold") c.reverse_threshold = value;
+        else if (name == "reset") c.reset = value;
+        else if (name == "reverse_reset") c.reverse_reset = value;
+        else if (name == "leak_decay") c.leak = value;
+        else if (name == "input_decay") c.input_decay = value;
+        else if (name == "refractory_delay") c.refractory_delay = static_cast<int32_t>(value);
+        else if (name == "force_update" || name == "force_update_every_timestep") set_flag(SFE_SOMA_FORCE_UPDATE);
+        else if (name == "log_u") return frozen("the model-defined trace columns are fixed when the network is loaded");
+        else return PatchKind::ignored; // e.g. "leak" (a TrueNorth key)
+        break;
+    case SFE_SOMA_TRUENORTH:
+        if (name == "bias") { t.neuron_bias[neuron] = value; return PatchKind::bias; }
+        if (name == "threshold") c.threshold = value;
+        else if (name == "reverse_threshold") c.reverse_threshold = value;
+        else if (name == "reset") c.reset = value;
+        else if (name == "reverse_reset") c.reverse_reset = value;
+        else if (name == "leak") c.leak = value;
+        else if (name == "force_update" || name == "force_update_every_timestep") set_flag(SFE_SOMA_FORCE_UPDATE);
+        else if (name == "leak_towards_zero") set_flag(SFE_SOMA_LEAK_TOWARDS_ZERO);
+        else if (name == "random_mask")
+        {
+            if (value < 0.0) throw std::invalid_argument("random_mask < 0; must be unsigned.");
+            if (value != 0.0) return frozen("random_mask != 0 draws from the process-global std::rand() (src/models.cpp:757)");
+            c.random_mask = 0;
+        }
+        else return PatchKind::ignored; // e.g. "leak_decay" (a LIF key)
+        break;
+    case SFE_SOMA_NEUROFEM:
+        if (name == "bias") { t.neuron_bias[neuron] = value; return PatchKind::bias; }
+        if (name == "threshold") c.threshold = value;
+        else if (name == "reset") c.reset = value;
+        else if (name == "lambda_d") c.input_decay = value;
+        else if (name == "lambda_v") c.leak = value;
+        else if (name == "dt") c.nf_dt = value;
+        else if (name == "kp") c.nf_kp = value;
+        else if (name == "ki") c.nf_ki = value;
+        else if (name == "sigma_v")
+        {
+            if (value != 0.0) return frozen("sigma_v != 0 adds std::random_device noise that no reference run reproduces");
+            return PatchKind::ignored;
+        }
+        else return PatchKind::ignored;
+        break;
+    case SFE_SOMA_INPUT:
+        if (name == "rate" || name == "poisson" || name == "spikes")
+            return frozen("an 'input' unit keeps one spike source per hardware unit, lowered at load()");
+        return PatchKind::ignored;
+    case SFE_SOMA_HH:
+        if (name == "m" || name == "n" || name == "h" || name == "current")
+            return frozen("the Hodgkin-Huxley state of a unit is initialised at load()");
+        return PatchKind::ignored;
+    default:
+        return frozen("the neuron's soma is an out-of-tree device model");
+    }
     // split the class: find an identical one or append
     for (size_t i = 0; i < t.soma_classes.size(); ++i)
     {
         if (std::memcmp(&t.soma_classes[i], &c, sizeof(c)) == 0)
         {
             t.neuron_class[neuron] = static_cast<uint32_t>(i);
-            return true;
+            return PatchKind::classes;
         }
     }
     t.soma_classes.push_back(c);
     t.neuron_class[neuron] = static_cast<uint32_t>(t.soma_classes.size() - 1);
     t.view.soma_classes = t.soma_classes.data();
     t.view.n_soma_classes = static_cast<uint32_t>(t.soma_classes.size());
-    return true;
+    return PatchKind::classes;
 }
 
 } // namespace sfe

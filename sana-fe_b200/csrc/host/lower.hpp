@@ -80,7 +80,14 @@ uint32_t count_input_units(const Architecture &arch);
 // MappedNeuron.set_attributes for one numeric soma attribute: patches the host
 // tables (splitting the neuron's parameter class when needed). Returns true if
 // the class table changed (device must re-upload classes + neuron_class).
-bool patch_neuron_attribute(HostTables &t, uint32_t neuron, const std::string &name, double value);
+enum class PatchKind
+{
+    ignored,  // the neuron's model does not know the key (the reference ignores it too)
+    bias,     // host bias table changed: upload the vector before the next step
+    classes,  // soma class table / per-neuron class ids changed
+    potential // the membrane potential itself was set (LIF "potential")
+};
+PatchKind patch_neuron_attribute(HostTables &t, uint32_t neuron, const std::string &name, double value);
 
 } // namespace sfe
 #endif

@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libsanafe_b200.so")
+# SFE_LIB_PATH: an experiment build of the same library (sana-fe_b200/Makefile, target `variant`)
+_LIB_PATH = os.environ.get("SFE_LIB_PATH") or os.path.join(_HERE, "libsanafe_b200.so")
 
 
 class SynthSpec(C.Structure):
@@ -41,7 +42,7 @@ class CoreDesc(C.Structure):
                 ("axon_in_begin", C.c_uint32), ("axon_in_count", C.c_uint32),
                 ("syn_begin", C.c_uint64), ("syn_count", C.c_uint64),
                 ("acc_mode", C.c_uint32), ("weight_shift", C.c_int32), ("ring", C.c_uint32),
-                ("dend_in_msg", C.c_uint32),
+                ("dend_in_msg", C.c_uint32), ("fixed_slots", C.c_uint32), ("pad", C.c_uint32),
                 ("energy_axon_in", C.c_double), ("latency_axon_in", C.c_double),
                 ("energy_axon_out", C.c_double), ("latency_axon_out", C.c_double)]
 
@@ -54,12 +55,13 @@ class SomaClass(C.Structure):
                 ("reverse_reset", C.c_double), ("leak", C.c_double), ("input_decay", C.c_double),
                 ("energy_access", C.c_double), ("energy_update", C.c_double), ("energy_spike_out", C.c_double),
                 ("latency_access", C.c_double), ("latency_update", C.c_double), ("latency_spike_out", C.c_double),
-                ("dend_energy_update", C.c_double), ("dend_latency_update", C.c_double)]
+                ("dend_energy_update", C.c_double), ("dend_latency_update", C.c_double),
+                ("nf_kp", C.c_double), ("nf_ki", C.c_double), ("nf_dt", C.c_double)]
 
 
 class CostClass(C.Structure):
     _fields_ = [("syn_energy", C.c_double), ("syn_latency", C.c_double), ("den_energy", C.c_double),
-                ("den_latency", C.c_double), ("per_message", C.c_uint32), ("pad", C.c_uint32)]
+                ("den_latency", C.c_double), ("per_message", C.c_uint32), ("den_is_soma", C.c_uint32)]
 
 
 class AxonIn(C.Structure):
@@ -156,6 +158,7 @@ def lib():
         "sfe_engine_run": (C.c_int, [vp, i64, C.POINTER(TraceRequest), C.POINTER(RunData)]),
         "sfe_engine_enqueue": (C.c_int, [vp, i64]), "sfe_engine_collect": (C.c_int, [vp, C.POINTER(RunData)]),
         "sfe_engine_reset": (C.c_int, [vp]), "sfe_engine_set_bias": (C.c_int, [vp, vp, sz]),
+        "sfe_engine_set_bias_staged": (C.c_int, [vp, vp, sz]),
         "sfe_engine_set_neuron_bias": (C.c_int, [vp, u32, dbl]),
         "sfe_engine_read_potentials": (C.c_int, [vp, vp, sz]), "sfe_engine_read_fired": (C.c_int, [vp, vp, sz]),
         "sfe_engine_read_raster": (C.c_int, [vp, vp, sz]),

@@ -68,6 +68,8 @@ CASES = {
     # "taps" dendrites (MultiTapModel1D): 1-D RC lines, synapses addressed to taps
     "taps": dict(arch=f"{SRC}/taps_arch.yaml", net=f"{SRC}/taps_snn.yaml", steps=200),
     "poisson": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/poisson_snn.yaml", steps=300),
+    # the NeuroFEM plugin: a combined dendrite + soma unit with two compartments, buffer inside the soma unit, sigma_v = 0
+    "neurofem": dict(arch=f"{SRC}/neurofem_arch.yaml", net=f"{SRC}/neurofem_snn.yaml", steps=400),
 }
 
 

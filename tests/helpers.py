@@ -166,9 +166,8 @@ GOLDEN_CASES = ["example", "dvs", "hh", "synth_small", "synth_delay", "synth_qui
 # Cases added late in round 1 (Poisson inputs, LIF file noise + model-defined traces): pinned on the CPU against
 # the reference here; their device tests live in tests/test_zz_new_models_gpu.py (collected last; green on a
 # B200, profiles/r1_pytest_new_models_gpu.log).
-NEW_GOLDEN_CASES = ["poisson", "noise"]
-# Lowered and run by the CPU restatement, refused by the device engine for now ("taps" dendrites)
-ORACLE_ONLY_CASES = ["taps"]
+NEW_GOLDEN_CASES = ["poisson", "noise", "taps", "neurofem"]
+ORACLE_ONLY_CASES = []
 _flat_cache = {}
 
 
@@ -216,13 +215,15 @@ def golden_description(name):
     return _description_cache[name]
 
 
-def load_chip(name, device):
+def load_chip(name, device, partition=None):
     cwd = os.getcwd()
     os.chdir(ROOT)  # plugin paths inside flat files are relative to the repo root
     try:
         arch, net = golden_description(name)
         chip = sfe.SpikingChip(arch, device=device)
         chip.set_input_seed_base(0)  # the goldens come from a fresh reference process each
+        if partition is not None:
+            chip.set_partition(*partition)
         chip.load(net)
     finally:
         os.chdir(cwd)

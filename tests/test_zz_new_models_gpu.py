@@ -116,11 +116,11 @@ def test_neuron_trace_surfaces(tmp_path):
     assert cli_lines == lines
 
 
-def test_taps_dendrites_are_refused_loudly():
-    """`taps` dendrites are lowered and pinned on the CPU (restatement vs the reference's golden) but have no device
-    implementation yet: loading one onto a device must fail with a message, never run something else."""
+def test_taps_on_a_partitioned_chip_are_refused_loudly():
+    """`taps` lines are replayed from the whole chip's raster by one kernel: a partitioned chip must refuse them with
+    a message, never run something else."""
     with pytest.raises(sfe.SanafeError, match="taps"):
-        load_chip("taps", device=0)
+        load_chip("taps", device=0, partition=(0, 2))
 
 
 def test_per_neuron_bias_patches_between_sim_calls():
@@ -215,15 +215,6 @@ def test_ctrl_c_interrupts_a_long_sim():
     assert time.time() - t0 < 60.0
     res = chip.sim(10, timing_model="simple")
     assert res["timesteps_executed"] == 10 and res["timestep_start"] > 101
-
-
-def test_taps_device_path():
-    """taps_kernel + the neuron phase's tap-line read-out against the reference's golden (the CPU restatement
-    passes it in test_oracle_vs_reference.py). The device path is the default since it passed on a B200 in round 1."""
-    chip = load_chip("taps", device=0)
-    g = golden("taps")
-    rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
-    check_against_golden("taps", chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
 
 
 @pytest.mark.parametrize("device_draws", ["1", "0"])
