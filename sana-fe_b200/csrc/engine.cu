@@ -154,6 +154,7 @@ struct DevTables
     const struct SomaSegment *soma_segments; // one record per neuron-phase segment (local cores)
     uint32_t partitioned;             // 1: this engine simulates a core range; spikes arrive via the exchanged raster
     uint32_t inbox_lo, inbox_hi;      // local inbox word range [lo, hi)
+    uint32_t inbox_words, pad_inbox;  // words of one inbox (the inbox is double-buffered by step parity)
     uint32_t n_soma_classes;
     const uint32_t *fanout_core_list; // cores that have axons-in
     const FanItem *fan_items;         // message-phase work items, grouped by core
@@ -195,9 +196,7 @@ struct DevTables
     const double *noise_values;
     uint32_t n_u_probes, pad_probes;
     uint32_t n_cores, n_probes, n_neurons, n_cost_classes, n_fanout_cores;
-    // fused finalize: cores with work items fold themselves; the others are folded at the end
-    const uint32_t *soma_only_list;
-    uint32_t n_soma_only, n_fold_cores, fused_finalize, n_soma_segments;
+    uint32_t n_soma_segments, pad_segments;
     double sync_delay;
 };
 
@@ -251,17 +250,30 @@ struct DevState
     long long steps_done;   // timesteps simulated before this step (host counter; T = steps_done + 1)
     uint32_t fold_parity;   // parity of the step the stand-alone / piggy-backed fold works on
     uint32_t pad_fold;
+    long long fold_step;    // 0-based index of the step whose record this launch appends (slot of the device log)
     uint32_t *work;        // ticket counter of the message phase: never reset, see fanout_kernel
     uint32_t *final_ticket;
-    uint32_t *core_done;    // [n_cores] work items of the core finished in this step (fused finalize)
-    uint32_t *cores_folded; // cores whose step statistics have been folded in this step
-    struct StepPartial *core_partials; // [n_active_cores]
+    // fused step kernel: a core is complete when all its work items of the step are done; the CTA that completes
+    // it folds its statistics and runs its neuron phase of the NEXT step; the CTA that completes the last core
+    // publishes the next step's raster (ready flag / peer exchange) and folds the chip
+    uint32_t *core_done;      // [n_cores] work items of the core finished in this step
+    uint32_t *cores_finished; // cores completed in this step
+    uint32_t *ready;          // [0] = e + 1 once the neuron phase of step epoch e is complete on this GPU (unpartitioned chip)
+    uint32_t fuse_next;       // 1: this launch also runs the neuron phase of the next step (not the last step of a batch)
+    uint32_t pad_fuse;
+    struct StepPartial *core_partials; // [2][n_active_cores], double-buffered by step parity
     struct StepPartial *partials;
 };
 
 // ---------------------------------------------------------------------------
 // Small device helpers
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
 {
     uint32_t v;
@@ -366,6 +378,15 @@ __device__ __forceinline__ const uint32_t *exchange_wait(const Exchange &x, cons
     __syncthreads();
     return x.raster[x.rank] + (epoch & 1ull) * x.fired_words;
 }
+// Unpartitioned chip, fused step kernel: the launch that ran the neuron phase of step epoch e raises ready = e + 1
+// (release); the launch that processes step e's messages waits for it (acquire). Bounded like exchange_wait.
+__device__ __forceinline__ void ready_publish(uint32_t *ready, const unsigned long long epoch)
+{
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ready), "r"(static_cast<uint32_t>(epoch) + 1u) : "memory");
+}
+__device__ __forceinline__ void ready_wait(const DevState &s, const unsigned long long epoch);
+
 __device__ __forceinline__ double warp_sum(double x)
 {
 #pragma unroll
@@ -708,57 +729,21 @@ __device__ __forceinline__ void append_step_record(const DevTables &t, const Dev
     r.network_energy = b.net_e;
     r.total_energy = b.net_e + b.syn_e + b.den_e + b.soma_e - b.dup_e; // a unit's energy once (src/chip.cpp:1224-1261)
     r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
-    const long long cursor = s.step[1];
-    s.log[cursor % s.log_cap] = r;
-    s.step[1] = cursor + 1;
-    s.step[0] = s.step[0] + 1;
+    // the record's slot follows from the step number the host passed with the launch (the folds of consecutive
+    // steps may overlap in the fused step kernel: nothing here reads what another fold writes)
+    s.log[s.fold_step % s.log_cap] = r;
+    s.step[1] = s.fold_step + 1;
+    s.step[0] = s.fold_step + 1;
 }
 
-// Chip-wide fold by one warp: cores without work items first, then all per-core partials.
+// Chip-wide fold by one warp over the per-core partials of the step (fused step kernel).
 __device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const int lane)
 {
-    for (uint32_t k = 0; k < t.n_soma_only; ++k)
-    {
-        const uint32_t c2 = t.soma_only_list[k];
-        const StepPartial q = fold_core(t, s, c2, lane, static_cast<uint32_t>(s.step_seq & 1ull));
-        if (lane == 0) s.core_partials[t.cores[c2].active_idx] = q;
-    }
-    __syncwarp();
+    const StepPartial *partials = s.core_partials + static_cast<size_t>(s.step_seq & 1ull) * t.n_active_cores;
     StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&s.core_partials[k]));
+    for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&partials[k]));
     b = warp_fold(b);
     if (lane == 0) append_step_record(t, s, b);
-}
-
-// Fused finalize (engines whose message phase has work items): called by warp 0 of a CTA after it
-// has published the statistics of a work item of core `ci`. The CTA that completes a core's last
-// item folds the core; the CTA that folds the last core folds the chip and appends the step
-// record - no separate kernel, and the per-core folds overlap the other CTAs' streaming.
-__device__ __forceinline__ void fused_finalize(const DevTables &t, const DevState &s, const uint32_t ci, const int lane)
-{
-    uint32_t done = 0u;
-    if (lane == 0)
-    {
-        __threadfence(); // this item's statistics before the count
-        done = atomicAdd(&s.core_done[ci], 1u) + 1u;
-    }
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (done != t.cores[ci].item_count) return;
-    __threadfence();
-    const StepPartial p = fold_core(t, s, ci, lane, static_cast<uint32_t>(s.step_seq & 1ull));
-    uint32_t folded = 0u;
-    if (lane == 0)
-    {
-        s.core_partials[t.cores[ci].active_idx] = p;
-        s.core_done[ci] = 0u; // ready for the next step
-        __threadfence();
-        folded = atomicAdd(s.cores_folded, 1u) + 1u;
-    }
-    folded = __shfl_sync(0xffffffffu, folded, 0);
-    if (folded != t.n_fold_cores) return;
-    __threadfence();
-    if (lane == 0) *s.cores_folded = 0u;
-    fold_chip(t, s, lane);
 }
 
 // The stand-alone form of the fold: one WARP per active core, `nblocks` CTAs numbered `block`.
@@ -826,33 +811,24 @@ struct SomaSegment
     double inv_scale;
 };
 
-template <bool kExotic>
-__global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
+struct SomaScratch // per-CTA reduction scratch of the neuron phase
 {
-    __shared__ sfe_soma_class class_cache[kClassCache];
-    griddep_launch_dependents();
-    if (blockIdx.x >= t.n_soma_segments)
-    {
-        // extra CTAs: the fold of the PREVIOUS step (its statistics are complete once the previous
-        // message phase has finished), off the critical path of this step
-        griddep_wait();
-        static_assert(sizeof(class_cache) >= kFinalScratchBytes, "the class cache doubles as the fold's scratch");
-        finalize_body(t, s, blockIdx.x - t.n_soma_segments, gridDim.x - t.n_soma_segments,
-                reinterpret_cast<unsigned char *>(class_cache));
-        return;
-    }
-    const SomaSegment core = t.soma_segments[blockIdx.x];
+    double part_d[kSomaThreads / 32][4];
+    uint32_t part_u[kSomaThreads / 32][3];
+};
+
+// The neuron phase of one segment (kSomaThreads * kSomaPerThread consecutive neurons of a core) by a whole CTA of
+// kSomaThreads threads: the body of soma_kernel, also run by the fused step kernel for the cores whose message
+// phase has just finished. `steps_done` = timesteps simulated before this step, `parity` = parity of the step (the
+// per-segment statistics and the inbox are double-buffered by it). class_cache: shared copy of the class table or null.
+template <bool kExotic>
+__device__ __forceinline__ void soma_segment(const DevTables &t, const DevState &s, const uint32_t seg_idx,
+        const sfe_soma_class *class_cache, SomaScratch &scr, const long long steps_done, const uint32_t parity)
+{
+    uint32_t *const inbox = s.inbox + static_cast<size_t>(parity) * t.inbox_words;
+    const SomaSegment core = t.soma_segments[seg_idx];
     const int lane = threadIdx.x & 31;
-    const bool classes_cached = t.n_soma_classes <= kClassCache;
-    if (classes_cached)
-    {
-        // 8-byte words of the class table, cooperatively
-        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(t.classes);
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_cache);
-        for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
-    }
-    griddep_wait(); // everything above reads load-time tables only
-    const long long steps_done = s.steps_done;
+    const bool classes_cached = class_cache != nullptr;
     const long long T = steps_done + 1;
 
     uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
@@ -1107,13 +1083,13 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
                     if (base + x < a1) bit[x] = __ldg(t.axon_out_bit + base + x);
 #pragma unroll
                 for (int x = 0; x < 8; ++x)
-                    if (base + x < a1) red_or(&s.inbox[bit[x] >> 5], 1u << (bit[x] & 31));
+                    if (base + x < a1) red_or(&inbox[bit[x] >> 5], 1u << (bit[x] & 31));
             }
         }
     }
     // ---- per-segment reductions: warp shuffles, one barrier -------------------------
-    __shared__ double part_d[kSomaThreads / 32][4];
-    __shared__ uint32_t part_u[kSomaThreads / 32][3];
+    double(*part_d)[4] = scr.part_d;
+    uint32_t(*part_u)[3] = scr.part_u;
     n_updated = warp_sum(n_updated);
     n_fired = warp_sum(n_fired);
     n_packets = warp_sum(n_packets);
@@ -1148,8 +1124,46 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         }
         // gen_sum: sum of generation delays incl. the trailing placeholder message
         // (src/chip.cpp:640-652, 821-823; src/schedule.cpp:81)
-        s.stats_n[(s.step_seq & 1ull) * t.n_soma_segments + blockIdx.x] = out; // double-buffered by step parity
+        s.stats_n[static_cast<size_t>(parity) * t.n_soma_segments + seg_idx] = out; // double-buffered by step parity
     }
+    __syncthreads(); // the scratch is free again (a CTA may run several segments in a row)
+}
+
+template <bool kExotic>
+__global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
+{
+    __shared__ sfe_soma_class class_cache[kClassCache];
+    __shared__ SomaScratch scr;
+    griddep_launch_dependents();
+    if (blockIdx.x >= t.n_soma_segments)
+    {
+        // extra CTAs: the fold of the PREVIOUS step (its statistics are complete once the previous
+        // message phase has finished), off the critical path of this step
+        griddep_wait();
+        static_assert(sizeof(class_cache) >= kFinalScratchBytes, "the class cache doubles as the fold's scratch");
+        finalize_body(t, s, blockIdx.x - t.n_soma_segments, gridDim.x - t.n_soma_segments,
+                reinterpret_cast<unsigned char *>(class_cache));
+        return;
+    }
+    const bool classes_cached = t.n_soma_classes <= kClassCache;
+    if (classes_cached)
+    {
+        // 8-byte words of the class table, cooperatively
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(t.classes);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_cache);
+        for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
+    }
+    griddep_wait(); // everything above reads load-time tables only
+    soma_segment<kExotic>(t, s, blockIdx.x, classes_cached ? class_cache : nullptr, scr, s.steps_done,
+            static_cast<uint32_t>(s.step_seq & 1ull));
+}
+
+// Out-of-line copy for the fused step kernel: the neuron phase runs once per core and launch there, and keeping it out
+// of the kernel's body keeps its ~80 registers from squeezing the message-phase stream loop (64-register budget).
+__device__ __noinline__ void soma_segment_outlined(const DevTables &t, const DevState &s, const uint32_t seg_idx,
+        const sfe_soma_class *class_cache, SomaScratch &scr, const long long steps_done, const uint32_t parity)
+{
+    soma_segment<false>(t, s, seg_idx, class_cache, scr, steps_done, parity);
 }
 
 // potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
@@ -1216,6 +1230,25 @@ __global__ void taps_kernel(const DevTables t, const DevState s)
         s.tap_has[y.post] = 1u;
     }
     s.tap_steps[u] = steps;
+}
+
+__device__ __forceinline__ void ready_wait(const DevState &s, const unsigned long long epoch)
+{
+    if (threadIdx.x == 0 && ld_relaxed_sys(s.x.error) == 0u)
+    {
+        const uint32_t want = static_cast<uint32_t>(epoch) + 1u;
+        const long long t0 = clock64();
+        while (static_cast<int32_t>(ld_acquire_gpu(s.ready) - want) < 0)
+        {
+            __nanosleep(64);
+            if (clock64() - t0 > 2000000000ll) // ~1 s: the producing launch never came (a host-side sequencing bug)
+            {
+                atomicExch(s.x.error, 2u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // Multi-GPU: a rank sees the spikes of the whole chip as a fired-bit raster (SURVEY 8e:
@@ -1399,7 +1432,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     __shared__ double part_d[kFanoutWarps][4];
     __shared__ unsigned long long part_l[kFanoutWarps][6];
     __shared__ sfe_cost_class cost_cache[kCostCache];
-    __shared__ uint32_t next_item, list_n, list_total;
+    __shared__ uint32_t next_item, list_n, list_total, core_event;
     __shared__ uint32_t scan_w[kFanoutWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1430,38 +1463,52 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     }
     uint32_t tma_phase = 0u; // bit st = parity the next wait on stage st of this warp expects
     (void) tma_phase;
-    griddep_wait(); // everything above reads load-time tables / initialises shared memory only
+    // Two-kernel step: everything above reads load-time tables / initialises shared memory only; the data of the
+    // neuron-phase kernel is awaited here. Fused step kernel (kFused): no grid dependency at all - the kernel waits,
+    // below, for the READY FLAG of its step (raised by the launch that ran the step's neuron phase: the previous
+    // fused launch, or the publish kernel after a stand-alone neuron phase), so its CTAs start on the SMs the
+    // previous launch frees while that launch still folds its step.
+    if constexpr (!kFused) griddep_wait();
     const long long T = s.steps_done + 1;
+    uint32_t *const inbox = s.inbox + static_cast<size_t>(s.step_seq & 1ull) * t.inbox_words;
 
     // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory
     // exchange the collective is fused into this kernel: CTA 0 pushes this rank's raster slice
     // to every rank over NVLink and raises the arrival flags, every CTA (the grid is one
     // resident wave) waits for the slices of all ranks before it touches the raster.
     const uint32_t *raster = s.fired_global;
-    if (s.x.n_peers > 0u)
+    if constexpr (!kFused)
     {
-        const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-        unsigned long long *st = stamp ? s.x.stamps + (s.step_seq & 4095ull) * 4ull : nullptr;
-        if (stamp) st[0] = global_timer_ns();
-        if (blockIdx.x == 0) exchange_publish(s.x, s.step_seq);
-        if (stamp) st[1] = global_timer_ns();
-        raster = exchange_wait(s.x, s.step_seq);
-        if (stamp) st[2] = global_timer_ns();
+        if (s.x.n_peers > 0u)
+        {
+            const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+            unsigned long long *st = stamp ? s.x.stamps + (s.step_seq & 4095ull) * 4ull : nullptr;
+            if (stamp) st[0] = global_timer_ns();
+            if (blockIdx.x == 0) exchange_publish(s.x, s.step_seq);
+            if (stamp) st[1] = global_timer_ns();
+            raster = exchange_wait(s.x, s.step_seq);
+            if (stamp) st[2] = global_timer_ns();
+        }
     }
     const bool gather = t.partitioned != 0u;
-    const uint32_t ticket_base = static_cast<uint32_t>(s.step_seq) * (t.n_fan_items + gridDim.x);
-    // a rank without work items (it still takes part in the exchange) has nothing that would
-    // trigger the fused finalize: its first warp folds the chip right away
-    if (kFused && t.n_fold_cores == 0u && blockIdx.x == 0 && warp == 0) fold_chip(t, s, lane);
+    // Work items are handed out through an atomic ticket that is never reset. Two-kernel step: a step draws
+    // n_fan_items + gridDim.x tickets (every CTA ends on one failed draw). Fused step kernel: the first item of a
+    // CTA is its block index (no atomic, and its descriptors are fetched before the ready flag is awaited), so a
+    // step draws n_fan_items tickets: the items beyond the first wave plus one failed draw per CTA.
+    const uint32_t ticket_base = static_cast<uint32_t>(s.step_seq) * (kFused ? t.n_fan_items : t.n_fan_items + gridDim.x);
+    bool first_item = true;
+    (void) first_item;
 
     // Persistent CTAs: cores (heaviest first) are handed out through an atomic ticket,
     // so the grid is one resident wave and no SM idles behind a wave boundary.
     for (;;)
     {
     __syncthreads(); // previous core fully retired (smem accumulators, next_item)
-    // the ticket counter is never reset: a step draws n_fan_items + gridDim.x tickets (every CTA
-    // ends on one failed draw), so step k's tickets start at k times that (mod 2^32)
-    if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) - ticket_base;
+    if (kFused && first_item)
+    {
+        if (threadIdx.x == 0) next_item = blockIdx.x;
+    }
+    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) - ticket_base + (kFused ? gridDim.x : 0u);
     __syncthreads();
     const uint32_t ticket = next_item;
     if (ticket >= t.n_fan_items) break;
@@ -1469,6 +1516,13 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     const FanItem item = t.fan_items[item_id];
     const uint32_t ci = item.core;
     const CoreDev core = t.cores[ci];
+    if (kFused && first_item)
+    {
+        // the descriptors of the first item are in registers: now wait for the step's raster / inbox to be complete
+        if (s.x.n_peers > 0u) raster = exchange_wait(s.x, s.step_seq);
+        else ready_wait(s, s.step_seq);
+        first_item = false;
+    }
     // kStreamQ4 instantiation: every core of the engine is certified for 4-byte records, the
     // other accumulation modes and streaming variants are compiled out (fewer registers)
     const uint32_t acc_mode = V == kStreamQ4 ? static_cast<uint32_t>(SFE_ACC_PACKED17) : core.acc_mode;
@@ -1535,7 +1589,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             uint32_t word = 0u;
             if (wi < n_words)
                 word = gather ? gather_inbox_word(t.axon_src + (static_cast<size_t>(core.inbox_word_begin + wi - t.inbox_lo) << 5), raster)
-                              : s.inbox[core.inbox_word_begin + wi];
+                              : inbox[core.inbox_word_begin + wi];
             const uint32_t pc = __popc(word);
             uint32_t incl = pc;
 #pragma unroll
@@ -1561,7 +1615,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 list_n = list_total = accepted == kFanoutThreads ? total : base;
             if (ok && word != 0u)
             {
-                if (!gather) s.inbox[core.inbox_word_begin + wi] = 0u; // consume
+                if (!gather) inbox[core.inbox_word_begin + wi] = 0u; // consume
                 uint32_t bits = word, slot = base;
                 while (bits != 0u)
                 {
@@ -1680,43 +1734,50 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 // base as an immediate), addend = record >> 14. Pad records are zero words (add 0 to cell
                 // 0), so a lane never tests its records one by one. Nothing is held in registers while in
                 // flight: seven chunks per warp are always on their way.
-                const uint32_t acc_s = smem_addr(acc32);
-                const uint32_t ring_s = smem_addr(
+                uint32_t acc_s = smem_addr(acc32);
+                uint32_t ring_s = smem_addr(
                         tma_base + warp * (V == kStreamTma ? kTmaStages * kTmaStageBytes : kQ4Stages * kQ4StageBytes) + 16 * lane);
                 const uint32_t *q_lane = t.syn_q4 + core.syn_begin + 4u * lane;
-                // opaque copy: keeps the lane's base pointer in a register pair, so that the address of a chunk is one
-                // wide multiply-add of the entry's record offset (the compiler otherwise re-derives it from the
-                // kernel parameters for every chunk)
-                asm volatile("mov.u64 %0, %0;" : "+l"(q_lane));
                 const uint32_t n_total = min(list_total, static_cast<uint32_t>(kListCap));
                 // this warp's chunks: list entries warp, warp + 8, ...; chunk c lives in stage c % kQ4Stages
                 const uint32_t my_chunks = (n_total - warp + kFanoutWarps - 1u) / kFanoutWarps;
-                const uint2 *my_list = list + warp;
+                uint32_t list_s = smem_addr(list + warp); // entry of chunk c: list_s + 64 * c
+                uint32_t lane_r = lane;
+                // opaque copies: the five values the loop lives on stay in registers (the compiler otherwise re-derives
+                // the shared-window addresses and the lane's base pointer from the kernel parameters for every chunk)
+                asm volatile("mov.u64 %0, %0;" : "+l"(q_lane));
+                asm volatile("mov.u32 %0, %0;" : "+r"(acc_s));
+                asm volatile("mov.u32 %0, %0;" : "+r"(ring_s));
+                asm volatile("mov.u32 %0, %0;" : "+r"(list_s));
+                asm volatile("mov.u32 %0, %0;" : "+r"(lane_r));
                 auto add_q4 = [&](const uint32_t qv) {
                     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + (qv & 0x3FFCu)), "r"(qv >> 14) : "memory");
                 };
-                auto issue = [&](const uint32_t c, const int st) {
-                    if (c < my_chunks)
+                // copy of chunk c (entry at list_s + 64 * (c - c_base) + off) into stage st
+                auto issue = [&](const bool live, const uint32_t entry_s, const int st) {
+                    if (live)
                     {
-                        const uint2 ent = my_list[c * kFanoutWarps];
-                        if (lane < ent.y)
+                        uint32_t ex, ey;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(entry_s) : "memory");
+                        if (lane_r < ey)
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + st * kQ4StageBytes),
-                                         "l"(q_lane + ent.x)
+                                         "l"(q_lane + ex)
                                          : "memory");
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory"); // empty groups keep the count uniform
                 };
 #pragma unroll
-                for (int st = 0; st < kQ4Stages; ++st) issue(st, st);
-                for (uint32_t c0 = 0; c0 < my_chunks; c0 += kQ4Stages)
+                for (int st = 0; st < kQ4Stages; ++st) issue(static_cast<uint32_t>(st) < my_chunks, list_s + 64u * st, st);
+                for (uint32_t left = my_chunks; left != 0u;)
                 {
 #pragma unroll
                     for (int st = 0; st < kQ4Stages; ++st)
                     {
-                        const uint32_t c = c0 + st;
-                        if (c >= my_chunks) break;
+                        if (left == 0u) break;
                         asm volatile("cp.async.wait_group %0;" ::"n"(kQ4Stages - 1) : "memory");
-                        if (lane < my_list[c * kFanoutWarps].y)
+                        uint32_t w4;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w4) : "r"(list_s + 64u * st + 4u) : "memory");
+                        if (lane_r < w4)
                         {
                             uint4 rec;
                             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -1728,8 +1789,11 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                             add_q4(rec.z);
                             add_q4(rec.w);
                         }
-                        issue(c + kQ4Stages, st); // the lane refills its own 16 bytes: no barrier needed
+                        // the lane refills its own 16 bytes: no barrier needed
+                        issue(left > static_cast<uint32_t>(kQ4Stages), list_s + 64u * (st + kQ4Stages), st);
+                        --left;
                     }
+                    list_s += 64u * kQ4Stages;
                 }
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
@@ -1853,8 +1917,8 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             {
                 if (lane == 0)
                 {
-                    word = s.inbox[core.inbox_word_begin + wi];
-                    if (word != 0u) s.inbox[core.inbox_word_begin + wi] = 0u;
+                    word = inbox[core.inbox_word_begin + wi];
+                    if (word != 0u) inbox[core.inbox_word_begin + wi] = 0u;
                 }
                 word = __shfl_sync(0xffffffffu, word, 0);
             }
@@ -1981,9 +2045,71 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
             }
             s.stats_m[item_id] = out;
         }
-        if (kFused && warp == 0) fused_finalize(t, s, ci, lane); // thread 0 wrote the statistics
+    }
+    if constexpr (kFused)
+    {
+        // ---- core completion: the CTA that retires the last work item of a core folds the core's step statistics
+        // and runs the core's neuron phase of the NEXT step; the CTA that completes the last core publishes that
+        // step's raster (ready flag, or the peer-memory exchange) and folds the chip
+        if (threadIdx.x == 0)
+        {
+            __threadfence(); // this item's statistics and merged charge before the count
+            const uint32_t done = atomicAdd(&s.core_done[ci], 1u) + 1u;
+            core_event = done == core.item_count ? 1u : 0u;
+            if (core_event != 0u) s.core_done[ci] = 0u; // ready for the next step
+        }
+        __syncthreads();
+        if (core_event != 0u)
+        {
+            __threadfence();
+            const uint32_t parity = static_cast<uint32_t>(s.step_seq & 1ull);
+            if (warp == 0)
+            {
+                const StepPartial p = fold_core(t, s, ci, lane, parity);
+                if (lane == 0) s.core_partials[static_cast<size_t>(parity) * t.n_active_cores + core.active_idx] = p;
+            }
+            if (s.fuse_next != 0u && core.seg_count > 0u)
+            {
+                // the class table goes into the (now idle) list region, the reduction scratch behind it
+                sfe_soma_class *class_cache = reinterpret_cast<sfe_soma_class *>(smem_raw + list_off);
+                SomaScratch *scr = reinterpret_cast<SomaScratch *>(smem_raw + list_off + kClassCache * sizeof(sfe_soma_class));
+                const bool classes_cached = t.n_soma_classes <= kClassCache;
+                if (classes_cached)
+                {
+                    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(t.classes);
+                    unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_cache);
+                    for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kFanoutThreads) dst[x] = __ldg(src + x);
+                }
+                __syncthreads();
+                for (uint32_t g = 0; g < core.seg_count; ++g)
+                    soma_segment_outlined(t, s, core.seg_begin + g, classes_cached ? class_cache : nullptr, *scr, s.steps_done + 1,
+                            parity ^ 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                __threadfence(); // the core's partial, state, raster words and inbox bits before the count
+                const uint32_t finished = atomicAdd(s.cores_finished, 1u) + 1u;
+                core_event = finished == t.n_active_cores ? 2u : 0u;
+                if (core_event != 0u) *s.cores_finished = 0u;
+            }
+            __syncthreads();
+            if (core_event == 2u)
+            {
+                __threadfence();
+                if (s.fuse_next != 0u)
+                {
+                    if (s.x.n_peers > 0u) exchange_publish(s.x, s.step_seq + 1ull);
+                    else if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq + 1ull);
+                }
+                if (warp == 0) fold_chip(t, s, lane);
+            }
+        }
     }
     } // persistent loop
+    // completion of this launch implies completion of the one before it (whose last CTA may still be folding when
+    // this one's work is done): stream order as seen by the host and by the next non-fused launch stays transitive
+    if constexpr (kFused) griddep_wait();
 }
 
 // Stand-alone finalize (engines without message-phase work items): one WARP per active core.
@@ -2182,7 +2308,8 @@ struct sfe_engine
     sfe_soma_class *d_classes{nullptr};
     uint32_t n_classes_cap{0};
     std::vector<CoreDev> h_cores;
-    std::vector<uint32_t> soma_list, fanout_list, all_soma_list;
+    std::vector<uint32_t> soma_list, fanout_list, all_soma_list, active_list;
+    bool fused_ok{false}; // the fused step kernel can run this engine's enqueue-only batches
     std::vector<uint32_t> fired_word_begin; // per core
     uint32_t fired_words{0}, inbox_words{0};
     uint32_t dend_cells{0};
@@ -2198,6 +2325,13 @@ struct sfe_engine
     uint32_t rank{0}, world{1};
     std::vector<uint32_t> owner;      // rank that simulates each core
     uint32_t slice_words{0};          // raster words per rank slice (equal for all ranks)
+    // traced runs (sfe_engine_run with fired_bits): every step of a batch writes its raster into its own slot of a
+    // device ring, copied to the host once per batch - no copy between the two kernels of a step
+    uint32_t *d_fired_ring{nullptr};
+    size_t fired_ring_steps{0};
+    void *pinned_fired{nullptr};
+    size_t pinned_fired_bytes{0};
+    bool raster_identity{false}; // the padded raster layout equals device-index bit order (every core starts on a word)
     uint32_t *d_fired_local{nullptr}; // this rank's raster slice (slice_words)
     uint32_t *d_fired_global{nullptr};// world * slice_words
     bool external_exchange{false};
@@ -2220,6 +2354,7 @@ struct sfe_engine
     // a batch is folded by the stand-alone kernel when somebody needs the records (flush_fold).
     bool piggyback{true}, pending_fold{false};
     uint32_t pending_parity{0};
+    int64_t pending_step{0};
     // whole-vector bias uploads are double-buffered and travel on their own stream, so that the
     // upload for the next step overlaps the kernels of the current one
     double *bias_buf[2] = {nullptr, nullptr};
@@ -2586,21 +2721,17 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
 
     if (e->upload(&e->t.fanout_core_list, e->fanout_list.data(), e->fanout_list.size()) != 0) return -1;
     {
-        // this rank's cores that do anything in a step; those with axons-in fold their own step
-        // statistics at the end of their last work item (fused finalize), the rest are folded last
-        std::vector<uint32_t> active, soma_only;
+        // this rank's cores that do anything in a step (ascending id)
+        std::vector<uint32_t> active;
         for (uint32_t c = 0; c < tb->n_cores; ++c)
         {
             if (!is_local(c) || (tb->cores[c].neuron_count == 0 && tb->cores[c].axon_in_count == 0)) continue;
             e->h_cores[c].active_idx = static_cast<uint32_t>(active.size());
             active.push_back(c);
-            if (tb->cores[c].axon_in_count == 0) soma_only.push_back(c);
         }
         e->t.n_active_cores = static_cast<uint32_t>(active.size());
-        e->t.n_soma_only = static_cast<uint32_t>(soma_only.size());
-        e->t.n_fold_cores = static_cast<uint32_t>(e->fanout_list.size());
+        e->active_list = active;
         if (e->upload(&e->t.active_core_list, active.data(), active.size()) != 0) return -1;
-        if (e->upload(&e->t.soma_only_list, soma_only.data(), soma_only.size()) != 0) return -1;
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
     {
@@ -2749,7 +2880,11 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     // base so that this rank's slice lands at the start of its local buffer
     e->s.fired_bits = e->d_fired_local - static_cast<size_t>(e->rank) * e->slice_words * (e->world > 1 ? 1 : 0);
     e->s.fired_global = e->d_fired_global;
-    if (e->alloc(&e->s.inbox, inbox_words) != 0) return -1;
+    e->raster_identity = e->world == 1;
+    for (uint32_t c : e->soma_list)
+        if (e->fired_word_begin[c] * 32ull != tb->cores[c].neuron_begin) e->raster_identity = false;
+    if (e->alloc(&e->s.inbox, 2 * static_cast<size_t>(inbox_words)) != 0) return -1; // double-buffered by step parity
+    e->t.inbox_words = inbox_words;
     if (e->alloc(&e->s.din32, dend_cells) != 0) return -1;
     if (e->alloc(&e->s.dcnt32, (e->ordered_any || e->dual_any) ? dend_cells : 1) != 0) return -1;
     if (e->alloc(&e->s.din64, e->ordered_any ? dend_cells : 1) != 0) return -1;
@@ -2766,8 +2901,9 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.work, 1) != 0) return -1;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
-    if (e->alloc(&e->s.cores_folded, 1) != 0) return -1;
-    if (e->alloc(&e->s.core_partials, e->t.n_active_cores) != 0) return -1;
+    if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
+    if (e->alloc(&e->s.ready, 1) != 0) return -1;
+    if (e->alloc(&e->s.core_partials, 2 * static_cast<size_t>(e->t.n_active_cores)) != 0) return -1;
     if (e->alloc(&e->s.x.error, 1) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
     if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
@@ -2913,6 +3049,16 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                 weight.push_back(static_cast<double>(tb->cores[c].syn_count) / parts);
             }
         }
+        // active cores without axons-in get one empty item each: in the fused step kernel every core passes through
+        // the same completion path (fold, neuron phase of the next step), and an empty item costs next to nothing
+        for (uint32_t c : e->active_list)
+        {
+            if (e->h_cores[c].axon_count != 0) continue;
+            e->h_cores[c].item_begin = static_cast<uint32_t>(items.size());
+            e->h_cores[c].item_count = 1;
+            items.push_back(FanItem{c, 0u, 0u, 0u});
+            weight.push_back(0.0);
+        }
         std::vector<uint32_t> order(items.size());
         for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
@@ -2923,12 +3069,13 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         SFE_CUDA(cudaMemcpyAsync(e->d_cores, e->h_cores.data(), e->h_cores.size() * sizeof(CoreDev), cudaMemcpyHostToDevice, e->stream));
         SFE_CUDA(cudaStreamSynchronize(e->stream));
         e->fanout_grid = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>(items.size(), slots)));
-        // SFE_FUSED_FINALIZE=1: fold the step inside the message phase instead of a third kernel.
-        // Measured (C4 on 1/2/4/8 GPUs): no faster than the PDL-overlapped finalize kernel - the fold
-        // of the last core and of the chip is a serial tail either way - so it is off by default.
+        // The fused step kernel (one launch per step, see enqueue_fused) serves enqueue-only batches of engines whose
+        // somas are all LIF / TrueNorth (the kernel carries the plain neuron-phase instantiation); SFE_FUSED_STEP=0
+        // keeps the two-kernel step everywhere.
         {
-            const char *fused = std::getenv("SFE_FUSED_FINALIZE");
-            e->t.fused_finalize = (fused != nullptr && std::atoi(fused) != 0) ? 1u : 0u;
+            const char *fused = std::getenv("SFE_FUSED_STEP");
+            e->fused_ok = (fused == nullptr || std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0 &&
+                    !e->soma_list.empty() && !e->fanout_list.empty();
             const char *piggy = std::getenv("SFE_PIGGYBACK_FINALIZE"); // 0: a finalize kernel per step
             e->piggyback = piggy == nullptr || std::atoi(piggy) != 0;
         }
@@ -2991,6 +3138,8 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
+    if (e->pinned_fired != nullptr) cudaFreeHost(e->pinned_fired);
+    if (e->d_fired_ring != nullptr) cudaFree(e->d_fired_ring);
     if (e->bias_stage != nullptr) cudaFreeHost(e->bias_stage);
     if (e->ev_begin != nullptr) cudaEventDestroy(e->ev_begin);
     if (e->ev_end != nullptr) cudaEventDestroy(e->ev_end);
@@ -3039,6 +3188,7 @@ static void launch_soma(sfe_engine *e)
     {
         grid += e->final_grid; // extra CTAs fold the previous step
         e->s.fold_parity = e->pending_parity;
+        e->s.fold_step = e->pending_step;
         e->pending_fold = false;
     }
     if (e->exotic) launch_step_kernel(e, soma_kernel<true>, grid, kSomaThreads, 0, e->t, e->s);
@@ -3060,16 +3210,16 @@ static void flush_fold(sfe_engine *e)
 {
     if (!e->pending_fold) return;
     e->s.fold_parity = e->pending_parity;
+    e->s.fold_step = e->pending_step;
     launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
     ++e->launches;
     e->pending_fold = false;
 }
 
-static void launch_fanout(sfe_engine *e)
+static void launch_fanout(sfe_engine *e, const bool fused = false)
 {
     e->s.steps_done = e->total_timesteps;
     const unsigned grid = e->fanout_grid;
-    const bool fused = e->t.fused_finalize != 0u;
     if (e->fanout_variant == kStreamQ4)
     {
         if (fused) launch_step_kernel(e, fanout_kernel<kStreamQ4, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
@@ -3087,22 +3237,74 @@ static void launch_fanout(sfe_engine *e)
     }
 }
 
+// Raises the ready flag of the step whose neuron phase a stand-alone soma_kernel has just run (unpartitioned chip), or
+// pushes the rank's raster slice to every peer and raises the arrival flags there: what the fused step kernel does
+// itself for every later step of a batch.
+__global__ void __launch_bounds__(256) publish_kernel(const DevTables t, const DevState s)
+{
+    (void) t;
+    griddep_launch_dependents();
+    griddep_wait();
+    if (s.x.n_peers > 0u) exchange_publish(s.x, s.step_seq);
+    else if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq);
+}
+
+static int apply_pending_bias(sfe_engine *e);
+static int check_overlay(const sfe_engine *e);
+
+// `timesteps` steps of the fused step kernel (enqueue-only paths: no per-step traces): one stand-alone neuron phase
+// for the first step, then ONE launch per step that processes the step's messages, folds it and - all but the last -
+// runs the neuron phase of the next step core by core as the cores' message phases finish. timesteps + 2 launches.
+static int enqueue_fused(sfe_engine *e, const int64_t timesteps)
+{
+    if (check_overlay(e) != 0) return -1;
+    if (apply_pending_bias(e) != 0) return -1;
+    launch_soma(e); // (the fold of an earlier two-kernel step rides along)
+    ++e->launches;
+    launch_step_kernel(e, publish_kernel, 1u, 256u, 0, e->t, e->s);
+    ++e->launches;
+    for (int64_t i = 0; i < timesteps; ++i)
+    {
+        const bool timed = e->timing && e->time_launches && e->ev_used + 2 <= 8192;
+        if (timed)
+        {
+            while (e->ev_pool.size() < e->ev_used + 2)
+            {
+                cudaEvent_t ev;
+                cudaEventCreate(&ev);
+                e->ev_pool.push_back(ev);
+            }
+            cudaEventRecord(e->ev_pool[e->ev_used], e->stream);
+        }
+        e->s.fuse_next = i + 1 < timesteps ? 1u : 0u;
+        e->s.fold_step = e->total_timesteps;
+        launch_fanout(e, true);
+        ++e->launches;
+        if (timed)
+        {
+            cudaEventRecord(e->ev_pool[e->ev_used + 1], e->stream);
+            e->ev_used += 2;
+        }
+        ++e->s.step_seq;
+        ++e->total_timesteps;
+    }
+    e->s.fuse_next = 0u;
+    return 0;
+}
+
 static void launch_finalize(sfe_engine *e)
 {
-    const bool fanout_ran = !e->fanout_list.empty() || e->p2p_on;
-    if (e->t.fused_finalize != 0u && fanout_ran)
-    {
-        // the message phase folded the step itself
-    }
-    else if (e->piggyback && !e->soma_list.empty())
+    if (e->piggyback && !e->soma_list.empty())
     {
         // folded by extra CTAs of the next neuron-phase kernel (or by flush_fold)
         e->pending_fold = true;
         e->pending_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
+        e->pending_step = e->total_timesteps;
     }
     else
     {
         e->s.fold_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
+        e->s.fold_step = e->total_timesteps;
         launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
         ++e->launches;
     }
@@ -3177,8 +3379,13 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
                 " uncollected steps; call sfe_engine_collect");
         return -1;
     }
-    for (int64_t i = 0; i < timesteps; ++i)
-        if (enqueue_step(e, false) != 0) return -1;
+    if (e->fused_ok && timesteps >= 2)
+    {
+        if (enqueue_fused(e, timesteps) != 0) return -1;
+    }
+    else
+        for (int64_t i = 0; i < timesteps; ++i)
+            if (enqueue_step(e, false) != 0) return -1;
     SFE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -3325,11 +3532,12 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
     const bool want_u = req != nullptr && req->neuron_traces != nullptr && e->n_u_probes > 0;
     const size_t words = (static_cast<size_t>(e->n_neurons) + 31) / 32;
     // per-step staging in pinned memory, drained once per batch (no per-step host sync)
-    const size_t per_step = (want_fired ? e->fired_words * sizeof(uint32_t) : 0) +
-            (want_pot ? e->n_probes * sizeof(double) : 0) + (want_u ? e->n_u_probes * sizeof(double) : 0) +
+    const size_t fired_bytes = e->fired_words * sizeof(uint32_t);
+    const size_t per_step = (want_pot ? e->n_probes * sizeof(double) : 0) + (want_u ? e->n_u_probes * sizeof(double) : 0) +
             (want_status ? e->n_neurons : 0);
-    const int64_t batch_cap = per_step == 0 ? e->log_cap
-                                            : std::max<int64_t>(1, std::min<int64_t>(e->log_cap, (256ll << 20) / static_cast<int64_t>(per_step)));
+    const size_t per_step_all = per_step + (want_fired ? fired_bytes : 0);
+    const int64_t batch_cap = per_step_all == 0 ? e->log_cap
+                                                : std::max<int64_t>(1, std::min<int64_t>(e->log_cap, (256ll << 20) / static_cast<int64_t>(per_step_all)));
     std::vector<sfe_step_record> recs;
     int64_t done = 0;
     while (done < timesteps)
@@ -3342,8 +3550,35 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
         }
         const int64_t batch = std::min<int64_t>(batch_cap, timesteps - done);
         if (per_step > 0 && e->ensure_pinned(per_step * static_cast<size_t>(batch)) != 0) return -1;
+        if (want_fired)
+        {
+            if (static_cast<size_t>(batch) > e->fired_ring_steps)
+            {
+                if (e->d_fired_ring != nullptr) cudaFree(e->d_fired_ring);
+                e->d_fired_ring = nullptr;
+                e->fired_ring_steps = 0;
+                void *q = nullptr;
+                SFE_CUDA(cudaMalloc(&q, fired_bytes * static_cast<size_t>(batch)));
+                e->d_fired_ring = static_cast<uint32_t *>(q);
+                e->fired_ring_steps = static_cast<size_t>(batch);
+            }
+            if (fired_bytes * static_cast<size_t>(batch) > e->pinned_fired_bytes)
+            {
+                if (e->pinned_fired != nullptr) cudaFreeHost(e->pinned_fired);
+                e->pinned_fired = nullptr;
+                e->pinned_fired_bytes = 0;
+                SFE_CUDA(cudaMallocHost(&e->pinned_fired, fired_bytes * static_cast<size_t>(batch)));
+                e->pinned_fired_bytes = fired_bytes * static_cast<size_t>(batch);
+            }
+        }
         for (int64_t b = 0; b < batch; ++b)
         {
+            if (want_fired)
+            {
+                // this step's raster slot (an unpartitioned engine: the neuron phase writes it, taps lines read it)
+                e->s.fired_bits = e->d_fired_ring + static_cast<size_t>(b) * e->fired_words;
+                e->s.fired_global = e->s.fired_bits;
+            }
             if (check_overlay(e) != 0) return -1;
             if (apply_pending_bias(e) != 0) return -1;
             if (!e->soma_list.empty())
@@ -3353,11 +3588,6 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
             }
             launch_taps(e);
             unsigned char *stage = static_cast<unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
-            if (want_fired)
-            {
-                SFE_CUDA(cudaMemcpyAsync(stage, e->d_fired_global, e->fired_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-                stage += e->fired_words * sizeof(uint32_t);
-            }
             if (want_pot || want_u)
             {
                 probe_kernel<<<(e->n_probes + e->n_u_probes + 255) / 256, 256, 0, e->stream>>>(e->t, e->s);
@@ -3383,6 +3613,15 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
             launch_finalize(e);
             ++e->total_timesteps;
         }
+        if (want_fired)
+        {
+            // the batch's rasters in one copy; the last one stays readable through sfe_engine_read_raster
+            SFE_CUDA(cudaMemcpyAsync(e->pinned_fired, e->d_fired_ring, fired_bytes * static_cast<size_t>(batch), cudaMemcpyDeviceToHost, e->stream));
+            SFE_CUDA(cudaMemcpyAsync(e->d_fired_global, e->d_fired_ring + static_cast<size_t>(batch - 1) * e->fired_words, fired_bytes,
+                    cudaMemcpyDeviceToDevice, e->stream));
+            e->s.fired_bits = e->d_fired_local;
+            e->s.fired_global = e->d_fired_global;
+        }
         SFE_CUDA(cudaGetLastError());
         if (collect_records(e, recs) != 0) return -1;
         for (int64_t b = 0; b < batch; ++b)
@@ -3391,10 +3630,15 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
             add_record(rd, r);
             if (req != nullptr && req->steps != nullptr) req->steps[done + b] = r;
             const unsigned char *stage = static_cast<const unsigned char *>(e->pinned) + per_step * static_cast<size_t>(b);
-            if (want_fired)
+            if (want_fired && e->raster_identity)
+            {
+                std::memcpy(req->fired_bits + static_cast<size_t>(done + b) * words,
+                        static_cast<const uint32_t *>(e->pinned_fired) + static_cast<size_t>(b) * e->fired_words, words * sizeof(uint32_t));
+            }
+            else if (want_fired)
             {
                 // un-pad: per-core word-aligned raster -> device-index bit order
-                const uint32_t *padded = reinterpret_cast<const uint32_t *>(stage);
+                const uint32_t *padded = static_cast<const uint32_t *>(e->pinned_fired) + static_cast<size_t>(b) * e->fired_words;
                 uint32_t *dst = req->fired_bits + static_cast<size_t>(done + b) * words;
                 std::memset(dst, 0, words * sizeof(uint32_t));
                 for (uint32_t c : e->soma_list)
@@ -3416,7 +3660,6 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                             }
                     }
                 }
-                stage += e->fired_words * sizeof(uint32_t);
             }
             if (want_pot)
             {
@@ -4076,6 +4319,14 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
     // each (diagnostic only)
     static const bool profile = std::getenv("SFE_PHASE_PROFILE") != nullptr;
     const int64_t prof_steps = profile ? std::min<int64_t>(timesteps, 128) : 0;
+    if (e->fused_ok && e->p2p_on && timesteps >= 2 && !profile)
+    {
+        // the fused step kernel: the raster exchange of step t + 1 is published by the launch of step t as soon as
+        // the rank's last core has run its neuron phase; every rank launches the same sequence
+        if (enqueue_fused(e, timesteps) != 0) return -1;
+        SFE_CUDA(cudaGetLastError());
+        return 0;
+    }
     for (int64_t s = 0; s < timesteps; ++s)
     {
         g_prof_on = s < prof_steps;

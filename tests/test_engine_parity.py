@@ -139,3 +139,53 @@ def test_partitioned_engines_match_reference(name, world):
     text = part.chips[0].format_spikes(bits.view(np.uint32), 1)
     want = "".join(line + "\n" for line in golden_spikes(name).split("\n") if line and int(line.rsplit(",", 1)[1]) <= steps)
     assert text == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["synth_small", "synth_delay", "synth_soma", "synth_quirk"])
+def test_fused_step_kernel_equals_two_kernel_step(name):
+    """sfe_engine_enqueue(K >= 2) runs the fused step kernel (one launch per step: message phase of step t, fold of
+    step t, neuron phase of step t + 1 core by core, ready flag) where sfe_chip_sim runs the two-kernel step. Same
+    per-step records, final potentials and last raster, also across two consecutive batches and a reset."""
+    import ctypes as C
+    import sanafe_b200 as sfe
+    L = sfe.lib()
+    g = golden(name)
+    steps = g["steps"]
+    ref = load_chip(name, device=0)
+    rd_ref, out_ref = ref.sim_raw(steps, "simple", steps=True, fired=True)
+    chip = load_chip(name, device=0)
+    eng = chip.engine
+    n = chip.tables.n_neurons
+    first = steps // 3
+    launches0 = L.sfe_engine_launch_count(eng)
+    recs = []
+    for count in (first, steps - first):
+        assert L.sfe_engine_enqueue(eng, count) == 0, L.sfe_last_error()
+        buf = np.zeros(count, dtype=sfe.STEP_DTYPE)
+        got = L.sfe_engine_collect_records(eng, buf.ctypes.data, count)
+        assert got == count, L.sfe_last_error()
+        recs.append(buf)
+    assert L.sfe_engine_launch_count(eng) - launches0 == steps + 4, "the fused step kernel did not run (steps + 2 launches per batch)"
+    assert L.sfe_engine_exchange_error(eng) == 0
+    got = np.concatenate(recs)
+    for key in ("neurons_fired", "neurons_updated", "packets_sent", "total_hops", "spike_count"):
+        assert np.array_equal(got[key], out_ref["steps"][key]), (name, key)
+    for key in ("sim_time", "synapse_energy", "dendrite_energy", "soma_energy", "network_energy", "total_energy"):
+        assert rel_err(got[key], out_ref["steps"][key]) <= 1e-12, (name, key)
+    pa, pb = np.zeros(n), np.zeros(n)
+    assert L.sfe_engine_read_potentials(eng, pa.ctypes.data, n) == 0
+    assert L.sfe_engine_read_potentials(ref.engine, pb.ctypes.data, n) == 0
+    assert np.array_equal(pa, pb), name
+    words = (n + 31) // 32
+    fa = np.zeros(words, dtype=np.uint32)
+    assert L.sfe_engine_read_fired(eng, fa.ctypes.data, words) == 0
+    assert np.array_equal(fa, out_ref["fired_bits"][-1]), name
+    # and the golden itself through the fused path after a reset of both engines: same evolution again
+    chip.reset()
+    ref.reset()
+    assert L.sfe_engine_enqueue(eng, 10) == 0, L.sfe_last_error()
+    buf = np.zeros(10, dtype=sfe.STEP_DTYPE)
+    assert L.sfe_engine_collect_records(eng, buf.ctypes.data, 10) == 10
+    _, out2 = ref.sim_raw(10, "simple", steps=True)
+    assert np.array_equal(buf["spike_count"], out2["steps"]["spike_count"]) and np.array_equal(buf["neurons_fired"], out2["steps"]["neurons_fired"])
