@@ -251,7 +251,7 @@ struct DevState
     uint32_t fold_parity;   // parity of the step the stand-alone / piggy-backed fold works on
     uint32_t pad_fold;
     long long fold_step;    // 0-based index of the step whose record this launch appends (slot of the device log)
-    uint32_t *work;        // ticket counter of the message phase: never reset, see fanout_kernel
+    uint32_t *work;        // ticket counter of this step's message phase (a slot of the engine's pool, see prepare_tickets)
     uint32_t *final_ticket;
     // fused step kernel: a core is complete when all its work items of the step are done; the CTA that completes
     // it folds its statistics and runs its neuron phase of the NEXT step; the CTA that completes the last core
@@ -1158,14 +1158,6 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             static_cast<uint32_t>(s.step_seq & 1ull));
 }
 
-// Out-of-line copy for the fused step kernel: the neuron phase runs once per core and launch there, and keeping it out
-// of the kernel's body keeps its ~80 registers from squeezing the message-phase stream loop (64-register budget).
-__device__ __noinline__ void soma_segment_outlined(const DevTables &t, const DevState &s, const uint32_t seg_idx,
-        const sfe_soma_class *class_cache, SomaScratch &scr, const long long steps_done, const uint32_t parity)
-{
-    soma_segment<false>(t, s, seg_idx, class_cache, scr, steps_done, parity);
-}
-
 // potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
 __global__ void probe_kernel(const DevTables t, const DevState s)
 {
@@ -1491,11 +1483,10 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
         }
     }
     const bool gather = t.partitioned != 0u;
-    // Work items are handed out through an atomic ticket that is never reset. Two-kernel step: a step draws
-    // n_fan_items + gridDim.x tickets (every CTA ends on one failed draw). Fused step kernel: the first item of a
-    // CTA is its block index (no atomic, and its descriptors are fetched before the ready flag is awaited), so a
-    // step draws n_fan_items tickets: the items beyond the first wave plus one failed draw per CTA.
-    const uint32_t ticket_base = static_cast<uint32_t>(s.step_seq) * (kFused ? t.n_fan_items : t.n_fan_items + gridDim.x);
+    // Work items are handed out through an atomic ticket counter of the step's own (s.work points at the step's slot
+    // of a pool the host clears per batch: launches of consecutive steps overlap in the fused step kernel, and a
+    // straggler's last, failed draw must not eat a ticket of a later step). Fused step kernel: the first item of a CTA
+    // is its block index - no atomic, and its descriptors are fetched before the ready flag is awaited.
     bool first_item = true;
     (void) first_item;
 
@@ -1508,7 +1499,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
     {
         if (threadIdx.x == 0) next_item = blockIdx.x;
     }
-    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) - ticket_base + (kFused ? gridDim.x : 0u);
+    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) + (kFused ? gridDim.x : 0u);
     __syncthreads();
     const uint32_t ticket = next_item;
     if (ticket >= t.n_fan_items) break;
@@ -2082,7 +2073,7 @@ __global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm 
                 }
                 __syncthreads();
                 for (uint32_t g = 0; g < core.seg_count; ++g)
-                    soma_segment_outlined(t, s, core.seg_begin + g, classes_cached ? class_cache : nullptr, *scr, s.steps_done + 1,
+                    soma_segment<false>(t, s, core.seg_begin + g, classes_cached ? class_cache : nullptr, *scr, s.steps_done + 1,
                             parity ^ 1u);
             }
             __syncthreads();
@@ -2290,6 +2281,8 @@ __global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, cons
         }                                                                                           \
     } while (0)
 
+constexpr uint32_t kWorkPool = 8192; // >= 2 x the device log capacity (steps that can be enqueued before a collect)
+
 struct sfe_engine
 {
     uint32_t *p2p_block{nullptr};        // [2][fired_words] raster + [kMaxPeers] flags, exported over CUDA IPC
@@ -2310,6 +2303,8 @@ struct sfe_engine
     std::vector<CoreDev> h_cores;
     std::vector<uint32_t> soma_list, fanout_list, all_soma_list, active_list;
     bool fused_ok{false}; // the fused step kernel can run this engine's enqueue-only batches
+    bool tickets_prepared{false}; // a batch entry point has cleared the ticket counters of the steps it enqueues
+    uint32_t *d_work_pool{nullptr}; // kWorkPool ticket counters, one per step in flight (slot = step_seq % kWorkPool)
     std::vector<uint32_t> fired_word_begin; // per core
     uint32_t fired_words{0}, inbox_words{0};
     uint32_t dend_cells{0};
@@ -2898,7 +2893,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.log, e->log_cap) != 0) return -1;
     if (e->alloc(&e->s.probe_out, static_cast<size_t>(tb->n_probes) + tb->n_u_probes) != 0) return -1;
     if (e->alloc(&e->s.step, 2) != 0) return -1;
-    if (e->alloc(&e->s.work, 1) != 0) return -1;
+    if (e->alloc(&e->d_work_pool, kWorkPool) != 0) return -1;
+    e->s.work = e->d_work_pool;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
     if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
@@ -3216,9 +3212,23 @@ static void flush_fold(sfe_engine *e)
     e->pending_fold = false;
 }
 
+// Clears the ticket counters of the next `count` steps (one memset per batch, ahead of its first kernel: it waits for
+// every earlier launch, stragglers included, and nothing of the batch has started).
+static int prepare_tickets(sfe_engine *e, const int64_t count)
+{
+    if (count <= 0 || e->d_work_pool == nullptr) return 0;
+    const uint32_t first = static_cast<uint32_t>(e->s.step_seq % kWorkPool);
+    const uint32_t n = static_cast<uint32_t>(std::min<int64_t>(count, kWorkPool));
+    const uint32_t head = std::min(n, kWorkPool - first);
+    SFE_CUDA(cudaMemsetAsync(e->d_work_pool + first, 0, head * sizeof(uint32_t), e->stream));
+    if (n > head) SFE_CUDA(cudaMemsetAsync(e->d_work_pool, 0, (n - head) * sizeof(uint32_t), e->stream));
+    return 0;
+}
+
 static void launch_fanout(sfe_engine *e, const bool fused = false)
 {
     e->s.steps_done = e->total_timesteps;
+    e->s.work = e->d_work_pool + (e->s.step_seq % kWorkPool);
     const unsigned grid = e->fanout_grid;
     if (e->fanout_variant == kStreamQ4)
     {
@@ -3257,6 +3267,7 @@ static int check_overlay(const sfe_engine *e);
 // runs the neuron phase of the next step core by core as the cores' message phases finish. timesteps + 2 launches.
 static int enqueue_fused(sfe_engine *e, const int64_t timesteps)
 {
+    if (prepare_tickets(e, timesteps) != 0) return -1;
     if (check_overlay(e) != 0) return -1;
     if (apply_pending_bias(e) != 0) return -1;
     launch_soma(e); // (the fold of an earlier two-kernel step rides along)
@@ -3384,8 +3395,11 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
         if (enqueue_fused(e, timesteps) != 0) return -1;
     }
     else
+    {
+        if (prepare_tickets(e, timesteps) != 0) return -1;
         for (int64_t i = 0; i < timesteps; ++i)
             if (enqueue_step(e, false) != 0) return -1;
+    }
     SFE_CUDA(cudaGetLastError());
     return 0;
 }
@@ -3571,6 +3585,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
                 e->pinned_fired_bytes = fired_bytes * static_cast<size_t>(batch);
             }
         }
+        if (prepare_tickets(e, batch) != 0) return -1;
         for (int64_t b = 0; b < batch; ++b)
         {
             if (want_fired)
@@ -4015,6 +4030,7 @@ extern "C" int sfe_engine_enqueue_neuron_phase(sfe_engine *e)
     }
     if (check_overlay(e) != 0) return -1;
     if (apply_pending_bias(e) != 0) return -1;
+    if (!e->tickets_prepared && prepare_tickets(e, 1) != 0) return -1;
     if (!e->soma_list.empty())
     {
         launch_soma(e);
@@ -4327,6 +4343,8 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
         SFE_CUDA(cudaGetLastError());
         return 0;
     }
+    if (prepare_tickets(e, timesteps) != 0) return -1;
+    e->tickets_prepared = true;
     for (int64_t s = 0; s < timesteps; ++s)
     {
         g_prof_on = s < prof_steps;
@@ -4348,6 +4366,7 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
         prof_mark(e);
     }
     g_prof_on = false;
+    e->tickets_prepared = false;
     if (prof_steps > 0)
     {
         SFE_CUDA(cudaStreamSynchronize(e->stream));
