@@ -1418,7 +1418,7 @@ constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta word
 
 // kFused: the message phase also folds the step (fused_finalize, SFE_FUSED_FINALIZE=1)
 template <int V, bool kFused>
-__global__ void __launch_bounds__(kFanoutThreads, V == kStreamQ4 ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
+__global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double part_d[kFanoutWarps][4];
@@ -2987,6 +2987,20 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamTma, false>, kFanoutThreads, smem_max));
         else
             SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fanout_kernel<kStreamScalar, false>, kFanoutThreads, smem_max));
+        {
+            // the fused step kernel carries the neuron phase too (80 registers, 3 CTAs per SM): one grid size serves
+            // both kernels of an engine, so the smaller occupancy decides
+            const char *fused = std::getenv("SFE_FUSED_STEP");
+            const bool want_fused = (fused == nullptr || std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0;
+            int per_sm_fused = per_sm;
+            if (want_fused && e->fanout_variant == kStreamQ4)
+                SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, fanout_kernel<kStreamQ4, true>, kFanoutThreads, smem_max));
+            else if (want_fused && e->fanout_variant == kStreamTma)
+                SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, fanout_kernel<kStreamTma, true>, kFanoutThreads, smem_max));
+            else if (want_fused)
+                SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, fanout_kernel<kStreamScalar, true>, kFanoutThreads, smem_max));
+            per_sm = std::max(1, std::min(per_sm, per_sm_fused));
+        }
         SFE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
         if (const char *v = std::getenv("SFE_FANOUT_CTAS_PER_SM")) per_sm = std::max(1, std::min(per_sm, std::atoi(v)));
         // ---- message-phase work items: split every core's inbox into slices so that there
