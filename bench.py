@@ -376,6 +376,13 @@ def main():
                                "frac": step_bytes / (ms_total.value / 1e3) / 1e9 / peak,
                                "bytes_per_step": step_bytes / max(args.steps, 1)}}
 
+    # ---- raster checksum (before the end-to-end legs patch the biases) ---------------------------------
+    def step_once():
+        assert L.sfe_engine_enqueue(eng, 1) == 0, L.sfe_last_error()
+
+    rds = sfe.RunData()
+    sha = raster_sha(L, eng, tb, step_once, lambda: L.sfe_engine_collect(eng, C.byref(rds)))
+
     # ---- end to end through the reference's own call, with HOST buffers ---------------------------
     # The loop of scripts/tcad2025/dvs_gesture.py:140-151: per frame, MappedNeuron.set_attributes(bias) on 1024 input
     # neurons (sfe_chip_set_neuron_attribute; the patches reach the device as one bias vector when sim() starts),
@@ -442,10 +449,6 @@ def main():
                                "ms_per_step": 1e3 * ps_s / per_step_n,
                                "call": "sfe_engine_set_bias + sfe_engine_enqueue(1) + sfe_engine_read_raster + sfe_engine_collect per step"}
 
-    def step_once():
-        assert L.sfe_engine_enqueue(eng, 1) == 0, L.sfe_last_error()
-
-    sha = raster_sha(L, eng, tb, step_once, lambda: L.sfe_engine_collect(eng, C.byref(rde)))
     cpu = None if args.no_cpu_baseline else run_reference_sample(100, 1)
     parity = gpu_sample_parity(cpu, local_rank) if cpu else None
     dse = None if args.no_dse else dse_side_measurement()

@@ -66,6 +66,7 @@ struct CoreDev
     uint32_t acc_mode;                // SFE_ACC_*
     uint32_t dend_in_msg;
     uint32_t fixed_slots;             // the delay field of a synapse is its dendrite slot ("neurofem" compartments)
+    uint32_t fast_soma, pad_fast;     // fused step kernel: the core's neuron phase runs through soma_core
     uint32_t tile;
     uint32_t seg_begin, seg_count;    // neuron-phase segments of this core
     uint32_t item_begin, item_count;  // message-phase work items (inbox slices) of this core
@@ -1389,6 +1390,233 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
                  : "memory");
 }
 
+// The neuron phase of a WHOLE core by one CTA of kFanoutThreads threads, for the fused step kernel, where it sits on
+// the step's critical path (it runs when the core's last work item retires, and the next step's raster is published
+// after the last core): ONE memory round trip for the state of all the core's neurons - every array is brought into
+// shared memory (idle at that point: accumulators, rings and list of the message phase) with 16-byte cp.async.cg -
+// then the updates from shared memory, the coalesced write-back, and a second round trip only for the inbox bits of
+// the neurons that fired (compacted, one thread per fired neuron, its axons' loads batched). soma_segment does the same
+// work 512 neurons at a time with two dependent round trips each and relies on thousands of CTAs in flight to hide
+// them. Cores it serves: LIF / TrueNorth somas (no input / plugin / noise / taps), exact accumulation modes, up to
+// kCoreSomaMax neurons, 4-neuron aligned (CoreDev::fast_soma, decided at load).
+constexpr uint32_t kCoreSomaMax = 1024;
+constexpr uint32_t kCoreSomaPerThread = kCoreSomaMax / 256;
+__host__ __device__ constexpr size_t core_soma_smem(const uint32_t P) // v, u, bias (f64); refractory, class, sum, count, axon_out_begin (+1)
+{
+    return static_cast<size_t>(P) * (3 * 8 + 5 * 4) + 16 + kClassCache * sizeof(sfe_soma_class) + 512;
+}
+
+__device__ __forceinline__ void cp_async16(const uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void soma_core(const DevTables &t, const DevState &s, const CoreDev &core, unsigned char *smem,
+        const long long steps_done, const uint32_t parity)
+{
+    const uint32_t P = core.neuron_count, nb = core.neuron_begin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long T = steps_done + 1;
+    const uint32_t slot = (core.ring > 1 && core.fixed_slots == 0u) ? static_cast<uint32_t>(T % core.ring) : 0u;
+    const uint32_t d0 = core.dend_base + slot * P;
+    const bool counted = core.acc_mode == SFE_ACC_DUAL32;
+    // shared-memory layout
+    double *v_s = reinterpret_cast<double *>(smem);
+    double *u_s = v_s + P;
+    double *b_s = u_s + P;
+    int32_t *refr_s = reinterpret_cast<int32_t *>(b_s + P);
+    uint32_t *cid_s = reinterpret_cast<uint32_t *>(refr_s + P);
+    uint32_t *sum_s = cid_s + P;
+    uint32_t *cnt_s = sum_s + P;
+    uint32_t *aob_s = cnt_s + P; // P + 1 entries (+3 pad)
+    sfe_soma_class *class_s = reinterpret_cast<sfe_soma_class *>(aob_s + P + 4);
+    uint32_t *fired_list = reinterpret_cast<uint32_t *>(class_s + kClassCache); // [<= 96] overflow -> direct path
+    __shared__ uint32_t n_fired_s;
+    __shared__ double red_d[kFanoutWarps][3];
+    __shared__ uint32_t red_u[kFanoutWarps][3];
+    if (threadIdx.x == 0) n_fired_s = 0u;
+    // ---- one round trip: everything the core's neurons need ------------------------------------
+    for (uint32_t x = threadIdx.x; x < P / 2; x += kFanoutThreads) // 16 bytes = 2 doubles
+    {
+        cp_async16(smem_addr(v_s + 2 * x), s.v + nb + 2 * x);
+        cp_async16(smem_addr(u_s + 2 * x), s.u + nb + 2 * x);
+        cp_async16(smem_addr(b_s + 2 * x), s.bias + nb + 2 * x);
+    }
+    for (uint32_t x = threadIdx.x; x < P / 4; x += kFanoutThreads) // 16 bytes = 4 words
+    {
+        cp_async16(smem_addr(refr_s + 4 * x), s.refractory + nb + 4 * x);
+        cp_async16(smem_addr(cid_s + 4 * x), t.neuron_class + nb + 4 * x);
+        cp_async16(smem_addr(sum_s + 4 * x), s.din32 + d0 + 4 * x);
+        if (counted) cp_async16(smem_addr(cnt_s + 4 * x), s.dcnt32 + d0 + 4 * x);
+        cp_async16(smem_addr(aob_s + 4 * x), t.axon_out_begin + nb + 4 * x);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x == 0) aob_s[P] = __ldg(t.axon_out_begin + nb + P);
+    const bool classes_cached = t.n_soma_classes <= kClassCache;
+    if (classes_cached)
+    {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(t.classes);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(class_s);
+        for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kFanoutThreads) dst[x] = __ldg(src + x);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    uint32_t *const inbox = s.inbox + static_cast<size_t>(parity) * t.inbox_words;
+    uint32_t n_updated = 0, n_fired = 0, n_packets = 0;
+    double soma_e = 0.0, dend_e = 0.0, lat_sum = 0.0;
+#pragma unroll
+    for (uint32_t r = 0; r < kCoreSomaPerThread; ++r)
+    {
+        const uint32_t k = r * kFanoutThreads + threadIdx.x;
+        const bool valid = k < P;
+        int st = SFE_STATUS_IDLE;
+        if (valid)
+        {
+            const uint32_t i = nb + k;
+            const sfe_soma_class &c = classes_cached ? class_s[cid_s[k]] : t.classes[cid_s[k]];
+            const uint32_t raw_sum = sum_s[k];
+            bool has_in = false;
+            double in = 0.0;
+            if (c.dend_in_neuron && c.dend_model == SFE_DEND_ACCUMULATOR) has_in = true; // charge lost (src/models.cpp:78-82)
+            else if (core.acc_mode == SFE_ACC_PACKED17)
+            {
+                if (raw_sum != 0u)
+                {
+                    const uint32_t count = (raw_sum + 0x10000u) >> 17;
+                    has_in = true;
+                    in = static_cast<double>(static_cast<int>(raw_sum - (count << 17))) * core.inv_scale;
+                    s.din32[d0 + k] = 0u;
+                }
+            }
+            else if (core.acc_mode == SFE_ACC_PACKED32)
+            {
+                if (raw_sum != 0u)
+                {
+                    has_in = true;
+                    in = static_cast<double>((static_cast<int>(raw_sum << 12)) >> 12) * core.inv_scale;
+                    s.din32[d0 + k] = 0u;
+                }
+            }
+            else if (cnt_s[k] != 0u) // DUAL32
+            {
+                has_in = true;
+                in = static_cast<double>(static_cast<int>(raw_sum)) * core.inv_scale;
+                s.din32[d0 + k] = 0u;
+                s.dcnt32[d0 + k] = 0u;
+            }
+            double lat = 0.0;
+            if (c.dend_in_neuron)
+            {
+                dend_e += c.dend_energy_update;
+                lat += c.dend_latency_update;
+            }
+            double v = v_s[k];
+            if (c.model == SFE_SOMA_LIF)
+            {
+                double u = u_s[k];
+                int refr = refr_s[k];
+                st = lif_update(c, v, u, refr, b_s[k], has_in, in, steps_done);
+                s.u[i] = u;
+                s.refractory[i] = refr;
+            }
+            else st = truenorth_update(c, v, b_s[k], has_in, in);
+            s.v[i] = v;
+            s.status[i] = static_cast<uint8_t>(st);
+            double e = c.energy_access, l = c.latency_access;
+            if (st >= SFE_STATUS_UPDATED)
+            {
+                e += c.energy_update;
+                l += c.latency_update;
+                ++n_updated;
+            }
+            if (st == SFE_STATUS_FIRED)
+            {
+                e += c.energy_spike_out;
+                l += c.latency_spike_out;
+                ++n_fired;
+                n_packets += aob_s[k + 1] - aob_s[k];
+            }
+            soma_e += e;
+            lat_sum += lat + l;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, st == SFE_STATUS_FIRED);
+        if (lane == 0 && k < ((P + 31u) & ~31u)) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
+        // unpartitioned chip: the fired neurons are listed, their axons' inbox bits raised below
+        if (t.partitioned == 0u && ballot != 0u)
+        {
+            uint32_t base = 0u;
+            if (lane == 0) base = atomicAdd(&n_fired_s, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (st == SFE_STATUS_FIRED)
+            {
+                const uint32_t at = base + __popc(ballot & ((1u << lane) - 1u));
+                if (at < 96u) fired_list[at] = k;
+                else
+                {
+                    // (more spikes than the list holds: raise this neuron's bits right here)
+                    for (uint32_t a = aob_s[k]; a < aob_s[k + 1]; ++a)
+                    {
+                        const uint32_t bit = __ldg(t.axon_out_bit + a);
+                        red_or(&inbox[bit >> 5], 1u << (bit & 31));
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (t.partitioned == 0u)
+    {
+        // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon of a fired neuron
+        const uint32_t n_list = min(n_fired_s, 96u);
+        // 8 lanes per fired neuron: lane j of the group raises the bits of axons j, j + 8, ... (one batch of loads in
+        // flight for the whole core instead of a dependent chain per neuron)
+        for (uint32_t f = threadIdx.x >> 3; f < n_list; f += kFanoutThreads >> 3)
+        {
+            const uint32_t k = fired_list[f];
+            for (uint32_t a = aob_s[k] + (threadIdx.x & 7u); a < aob_s[k + 1]; a += 8u)
+            {
+                const uint32_t bit = __ldg(t.axon_out_bit + a);
+                red_or(&inbox[bit >> 5], 1u << (bit & 31));
+            }
+        }
+    }
+    // ---- per-core statistics: warp shuffles, one barrier, fixed order ------------------------
+    n_updated = warp_sum(n_updated);
+    n_fired = warp_sum(n_fired);
+    n_packets = warp_sum(n_packets);
+    soma_e = warp_sum(soma_e);
+    dend_e = warp_sum(dend_e);
+    lat_sum = warp_sum(lat_sum);
+    if (lane == 0)
+    {
+        red_u[warp][0] = n_updated;
+        red_u[warp][1] = n_fired;
+        red_u[warp][2] = n_packets;
+        red_d[warp][0] = soma_e;
+        red_d[warp][1] = dend_e;
+        red_d[warp][2] = lat_sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < core.seg_count)
+    {
+        // the core's total goes into its first segment's record, the other segments' records are empty
+        StatsN out = {0u, 0u, 0u, 0u, 0.0, 0.0, 0.0, 0.0};
+        if (threadIdx.x == 0)
+            for (int w = 0; w < kFanoutWarps; ++w)
+            {
+                out.updated += red_u[w][0];
+                out.fired += red_u[w][1];
+                out.packets += red_u[w][2];
+                out.soma_e += red_d[w][0];
+                out.dend_e += red_d[w][1];
+                out.gen_sum += red_d[w][2];
+            }
+        s.stats_n[static_cast<size_t>(parity) * t.n_soma_segments + core.seg_begin + threadIdx.x] = out;
+    }
+    __syncthreads();
+}
+
 // Streaming variants of the exact-mode message phase (selected at engine creation,
 // SFE_FANOUT=scalar|vector|tma):
 //   kStreamScalar  8 scalar loads per 128-synapse chunk, next chunk's loads issued
@@ -2059,7 +2287,12 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
                 const StepPartial p = fold_core(t, s, ci, lane, parity);
                 if (lane == 0) s.core_partials[static_cast<size_t>(parity) * t.n_active_cores + core.active_idx] = p;
             }
-            if (s.fuse_next != 0u && core.seg_count > 0u)
+            if (s.fuse_next != 0u && core.seg_count > 0u && core.fast_soma != 0u)
+            {
+                __syncthreads(); // (warp 0 is done with the fold; the whole dynamic shared memory is idle)
+                soma_core(t, s, core, smem_raw, s.steps_done + 1, parity ^ 1u);
+            }
+            else if (s.fuse_next != 0u && core.seg_count > 0u)
             {
                 // the class table goes into the (now idle) list region, the reduction scratch behind it
                 sfe_soma_class *class_cache = reinterpret_cast<sfe_soma_class *>(smem_raw + list_off);
@@ -2949,10 +3182,28 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         if (all_q4 && std::getenv("SFE_FANOUT") == nullptr) e->fanout_variant = kStreamQ4;
     }
     e->tma_off = static_cast<uint32_t>((smem_max + 127) & ~static_cast<size_t>(127));
+    size_t soma_smem = 0;
+    {
+        // fused step kernel: which cores' neuron phase runs through soma_core (see there), and the shared memory it needs
+        const char *fused = std::getenv("SFE_FUSED_STEP");
+        const char *fast = std::getenv("SFE_FAST_SOMA");
+        const bool want = (fused == nullptr || std::atoi(fused) != 0) && (fast == nullptr || std::atoi(fast) != 0) && !e->exotic &&
+                e->n_taps_units == 0;
+        for (uint32_t c : e->soma_list)
+        {
+            CoreDev &d = e->h_cores[c];
+            d.fast_soma = (want && d.neuron_count <= kCoreSomaMax && (d.neuron_count & 3u) == 0u && (d.neuron_begin & 3u) == 0u &&
+                                  (d.dend_base & 3u) == 0u && d.acc_mode != SFE_ACC_ORDERED)
+                    ? 1u
+                    : 0u;
+            if (d.fast_soma != 0u) soma_smem = std::max(soma_smem, core_soma_smem(d.neuron_count));
+        }
+    }
     smem_max = e->tma_off +
             (e->fanout_variant == kStreamTma ? kFanoutWarps * kTmaStages * (kTmaStageBytes + 8)
                                              : (e->q4_any ? kFanoutWarps * kQ4Stages * kQ4StageBytes + kQ4BarBytes : 0)) +
             kListCap * sizeof(uint2);
+    smem_max = std::max(smem_max, soma_smem);
     e->fanout_smem = smem_max;
     if (smem_max > 200 * 1024)
     {
