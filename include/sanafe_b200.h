@@ -417,6 +417,9 @@ int sfe_engine_p2p_export(sfe_engine *e, void *handle64);
 int sfe_engine_p2p_attach(sfe_engine *e, const void *handles_world_x_64);
 int sfe_engine_p2p_detach(sfe_engine *e);
 int sfe_engine_exchange_error(sfe_engine *e);
+/* diagnostic (SFE_TIMELINE=1 at engine creation): %globaltimer stamps of every CTA of the fused step kernel for the
+ * last 64 steps, out[64][grid][16]; returns the grid size, 0 when nothing was recorded */
+int sfe_engine_read_timeline(sfe_engine *e, unsigned long long *out, size_t cap_words);
 /* last n records of the device log (for steps replayed from a captured CUDA graph) */
 int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
 /* Host-only plan of a chip split over `world` GPUs (no CUDA call): owner[c] = rank of core c

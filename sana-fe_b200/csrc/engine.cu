@@ -262,6 +262,7 @@ struct DevState
     uint32_t *ready;          // [0] = e + 1 once the neuron phase of step epoch e is complete on this GPU (unpartitioned chip)
     uint32_t fuse_next;       // 1: this launch also runs the neuron phase of the next step (not the last step of a batch)
     uint32_t pad_fuse;
+    unsigned long long *timeline; // diagnostic (SFE_TIMELINE=1): [64 steps][grid][16] %globaltimer stamps of every CTA
     struct StepPartial *core_partials; // [2][n_active_cores], double-buffered by step parity
     struct StepPartial *partials;
 };
@@ -1717,6 +1718,14 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     // is its block index - no atomic, and its descriptors are fetched before the ready flag is awaited.
     bool first_item = true;
     (void) first_item;
+    unsigned long long *const tl = (kFused && s.timeline != nullptr)
+            ? s.timeline + ((s.step_seq & 63ull) * gridDim.x + blockIdx.x) * 16ull
+            : nullptr;
+    uint32_t tl_item = 0u;
+    auto stamp = [&](const uint32_t k) {
+        if (kFused && tl != nullptr && threadIdx.x == 0 && k < 16u) tl[k] = global_timer_ns();
+    };
+    stamp(0);
 
     // Persistent CTAs: cores (heaviest first) are handed out through an atomic ticket,
     // so the grid is one resident wave and no SM idles behind a wave boundary.
@@ -1741,7 +1750,9 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
         if (s.x.n_peers > 0u) raster = exchange_wait(s.x, s.step_seq);
         else ready_wait(s, s.step_seq);
         first_item = false;
+        stamp(1);
     }
+    stamp(2u + 4u * tl_item);
     // kStreamQ4 instantiation: every core of the engine is certified for 4-byte records, the
     // other accumulation modes and streaming variants are compiled out (fewer registers)
     const uint32_t acc_mode = V == kStreamQ4 ? static_cast<uint32_t>(SFE_ACC_PACKED17) : core.acc_mode;
@@ -1882,6 +1893,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             }
             __syncthreads();
             wb += accepted;
+            stamp(3u + 4u * tl_item);
             if (!accumulate || static_cast<uint32_t>(warp) >= n_list) continue;
 
             // ---- stream the segments: chunk = 128 consecutive synapses of one axon ------
@@ -2265,6 +2277,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             s.stats_m[item_id] = out;
         }
     }
+    stamp(4u + 4u * tl_item);
     if constexpr (kFused)
     {
         // ---- core completion: the CTA that retires the last work item of a core folds the core's step statistics
@@ -2326,11 +2339,15 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
                     if (s.x.n_peers > 0u) exchange_publish(s.x, s.step_seq + 1ull);
                     else if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq + 1ull);
                 }
+                stamp(14);
                 if (warp == 0) fold_chip(t, s, lane);
             }
         }
     }
+    stamp(5u + 4u * tl_item);
+    if (tl_item < 2u) ++tl_item;
     } // persistent loop
+    stamp(15);
     // completion of this launch implies completion of the one before it (whose last CTA may still be folding when
     // this one's work is done): stream order as seen by the host and by the next non-fused launch stays transitive
     if constexpr (kFused) griddep_wait();
@@ -3132,6 +3149,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
     if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
     if (e->alloc(&e->s.ready, 1) != 0) return -1;
+    if (std::getenv("SFE_TIMELINE") != nullptr)
+        if (e->alloc(&e->s.timeline, 64ull * 1024ull * 16ull) != 0) return -1; // 64 steps x up to 1024 CTAs x 16 stamps
     if (e->alloc(&e->s.core_partials, 2 * static_cast<size_t>(e->t.n_active_cores)) != 0) return -1;
     if (e->alloc(&e->s.x.error, 1) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
@@ -3187,7 +3206,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         // fused step kernel: which cores' neuron phase runs through soma_core (see there), and the shared memory it needs
         const char *fused = std::getenv("SFE_FUSED_STEP");
         const char *fast = std::getenv("SFE_FAST_SOMA");
-        const bool want = (fused == nullptr || std::atoi(fused) != 0) && (fast == nullptr || std::atoi(fast) != 0) && !e->exotic &&
+        const bool want = (fused != nullptr && std::atoi(fused) != 0) && (fast == nullptr || std::atoi(fast) != 0) && !e->exotic &&
                 e->n_taps_units == 0;
         for (uint32_t c : e->soma_list)
         {
@@ -3242,7 +3261,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             // the fused step kernel carries the neuron phase too (80 registers, 3 CTAs per SM): one grid size serves
             // both kernels of an engine, so the smaller occupancy decides
             const char *fused = std::getenv("SFE_FUSED_STEP");
-            const bool want_fused = (fused == nullptr || std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0;
+            const bool want_fused = (fused != nullptr && std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0;
             int per_sm_fused = per_sm;
             if (want_fused && e->fanout_variant == kStreamQ4)
                 SFE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, fanout_kernel<kStreamQ4, true>, kFanoutThreads, smem_max));
@@ -3334,8 +3353,12 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         // somas are all LIF / TrueNorth (the kernel carries the plain neuron-phase instantiation); SFE_FUSED_STEP=0
         // keeps the two-kernel step everywhere.
         {
+            // Measured (profiles/r2_fused_step.md): the neuron phase of a core run by ONE CTA is a chain of memory round
+            // trips (~14 us from a core's last item to its raster words, against ~6 us for the stand-alone kernel that
+            // spreads the same work over hundreds of CTAs), so the two-kernel step wins at every scale tried (C4 on
+            // 1/2/4/8 GPUs, a 128-core chip). The fused kernel stays as an option: SFE_FUSED_STEP=1.
             const char *fused = std::getenv("SFE_FUSED_STEP");
-            e->fused_ok = (fused == nullptr || std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0 &&
+            e->fused_ok = (fused != nullptr && std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0 &&
                     !e->soma_list.empty() && !e->fanout_list.empty();
             const char *piggy = std::getenv("SFE_PIGGYBACK_FINALIZE"); // 0: a finalize kernel per step
             e->piggyback = piggy == nullptr || std::atoi(piggy) != 0;
@@ -4271,6 +4294,19 @@ extern "C" int sfe_engine_p2p_detach(sfe_engine *e)
     e->s.x.n_peers = 0;
     e->p2p_on = false;
     return 0;
+}
+
+// diagnostic: the %globaltimer stamps the CTAs of the fused step kernel left for the last 64 steps (SFE_TIMELINE=1):
+// out[64][grid][16], returns the grid size (0: not recorded)
+extern "C" int sfe_engine_read_timeline(sfe_engine *e, unsigned long long *out, size_t cap_words)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (e->s.timeline == nullptr) return 0;
+    const size_t words = 64ull * e->fanout_grid * 16ull;
+    if (cap_words < words) return -1;
+    SFE_CUDA(cudaStreamSynchronize(e->stream));
+    SFE_CUDA(cudaMemcpy(out, e->s.timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return static_cast<int>(e->fanout_grid);
 }
 
 // 0 = fine, 1 = a peer failed to arrive within the in-kernel time limit (results invalid)

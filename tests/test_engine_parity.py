@@ -143,8 +143,8 @@ def test_partitioned_engines_match_reference(name, world):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["synth_small", "synth_delay", "synth_soma", "synth_quirk"])
-def test_fused_step_kernel_equals_two_kernel_step(name):
-    """sfe_engine_enqueue(K >= 2) runs the fused step kernel (one launch per step: message phase of step t, fold of
+def test_fused_step_kernel_equals_two_kernel_step(name, monkeypatch):
+    """With SFE_FUSED_STEP=1 sfe_engine_enqueue(K >= 2) runs the fused step kernel (one launch per step: message phase of step t, fold of
     step t, neuron phase of step t + 1 core by core, ready flag) where sfe_chip_sim runs the two-kernel step. Same
     per-step records, final potentials and last raster, also across two consecutive batches and a reset."""
     import ctypes as C
@@ -154,6 +154,7 @@ def test_fused_step_kernel_equals_two_kernel_step(name):
     steps = g["steps"]
     ref = load_chip(name, device=0)
     rd_ref, out_ref = ref.sim_raw(steps, "simple", steps=True, fired=True)
+    monkeypatch.setenv("SFE_FUSED_STEP", "1")
     chip = load_chip(name, device=0)
     eng = chip.engine
     n = chip.tables.n_neurons
