@@ -213,7 +213,8 @@ struct Exchange
     uint32_t rank;
     uint32_t fired_words;
     uint32_t slice_words;         // words per rank slice (multiple of 4)
-    uint32_t acquire_mode, pad;
+    uint32_t acquire_mode;
+    uint32_t publish_in_soma;     // 1: the last CTA of the neuron-phase kernel publishes the slice (else CTA 0 of the message phase)
     const uint32_t *local_slice;  // this rank's slice as the neuron phase wrote it
     uint32_t *error;              // sticky: a peer did not arrive in time
     unsigned long long *stamps;   // diagnostic (SFE_PHASE_PROFILE): [4096][4] %globaltimer of CTA 0
@@ -259,6 +260,7 @@ struct DevState
     // publishes the next step's raster (ready flag / peer exchange) and folds the chip
     uint32_t *core_done;      // [n_cores] work items of the core finished in this step
     uint32_t *cores_finished; // cores completed in this step
+    uint32_t *soma_done;      // neuron-phase CTAs finished in this step (the last one publishes the raster slice)
     uint32_t *ready;          // [0] = e + 1 once the neuron phase of step epoch e is complete on this GPU (unpartitioned chip)
     uint32_t fuse_next;       // 1: this launch also runs the neuron phase of the next step (not the last step of a batch)
     uint32_t pad_fuse;
@@ -1158,6 +1160,25 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     griddep_wait(); // everything above reads load-time tables only
     soma_segment<kExotic>(t, s, blockIdx.x, classes_cached ? class_cache : nullptr, scr, s.steps_done,
             static_cast<uint32_t>(s.step_seq & 1ull));
+    // Partitioned chip, peer-memory exchange: the CTA that finishes the rank's last segment pushes the raster slice to
+    // every peer and raises the arrival flags right here, while the message-phase kernel is already being launched
+    // (its CTAs then only wait for the flags) - the publish used to open the message phase, on the critical path.
+    if (s.x.n_peers > 0u && s.x.publish_in_soma != 0u)
+    {
+        __shared__ uint32_t last_cta;
+        if (threadIdx.x == 0)
+        {
+            __threadfence(); // this segment's raster words before the count
+            last_cta = atomicAdd(s.soma_done, 1u) + 1u == t.n_soma_segments ? 1u : 0u;
+            if (last_cta != 0u) *s.soma_done = 0u;
+        }
+        __syncthreads();
+        if (last_cta != 0u)
+        {
+            __threadfence();
+            exchange_publish(s.x, s.step_seq);
+        }
+    }
 }
 
 // potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
@@ -1693,10 +1714,10 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     const long long T = s.steps_done + 1;
     uint32_t *const inbox = s.inbox + static_cast<size_t>(s.step_seq & 1ull) * t.inbox_words;
 
-    // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory
-    // exchange the collective is fused into this kernel: CTA 0 pushes this rank's raster slice
-    // to every rank over NVLink and raises the arrival flags, every CTA (the grid is one
-    // resident wave) waits for the slices of all ranks before it touches the raster.
+    // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory exchange the collective
+    // is fused into the step's kernels: the rank's raster slice is pushed to every rank over NVLink (by the last CTA
+    // of the neuron-phase kernel, or by CTA 0 here), and every CTA of this kernel (one resident wave) waits for the
+    // slices of all ranks before it touches the raster.
     const uint32_t *raster = s.fired_global;
     if constexpr (!kFused)
     {
@@ -1705,7 +1726,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
             unsigned long long *st = stamp ? s.x.stamps + (s.step_seq & 4095ull) * 4ull : nullptr;
             if (stamp) st[0] = global_timer_ns();
-            if (blockIdx.x == 0) exchange_publish(s.x, s.step_seq);
+            if (blockIdx.x == 0 && s.x.publish_in_soma == 0u) exchange_publish(s.x, s.step_seq);
             if (stamp) st[1] = global_timer_ns();
             raster = exchange_wait(s.x, s.step_seq);
             if (stamp) st[2] = global_timer_ns();
@@ -3149,6 +3170,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
     if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
     if (e->alloc(&e->s.ready, 1) != 0) return -1;
+    if (e->alloc(&e->s.soma_done, 1) != 0) return -1;
     if (std::getenv("SFE_TIMELINE") != nullptr)
         if (e->alloc(&e->s.timeline, 64ull * 1024ull * 16ull) != 0) return -1; // 64 steps x up to 1024 CTAs x 16 stamps
     if (e->alloc(&e->s.core_partials, 2 * static_cast<size_t>(e->t.n_active_cores)) != 0) return -1;
@@ -4273,6 +4295,11 @@ extern "C" int sfe_engine_p2p_attach(sfe_engine *e, const void *handles)
     e->s.x.slice_words = e->slice_words;
     e->s.x.local_slice = e->d_fired_local;
     e->s.x.acquire_mode = 1u;
+    {
+        // SFE_PUBLISH_IN_SOMA=0: CTA 0 of the message phase publishes (round-1 behaviour)
+        const char *v = std::getenv("SFE_PUBLISH_IN_SOMA");
+        e->s.x.publish_in_soma = ((v == nullptr || std::atoi(v) != 0) && !e->soma_list.empty()) ? 1u : 0u;
+    }
     if (const char *v = std::getenv("SFE_XCHG_ACQUIRE")) e->s.x.acquire_mode = static_cast<uint32_t>(std::atoi(v));
     if (std::getenv("SFE_PHASE_PROFILE") != nullptr && e->s.x.stamps == nullptr)
         if (e->alloc(&e->s.x.stamps, 4096 * 4) != 0) return -1;
