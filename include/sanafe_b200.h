@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 5
+#define SFE_ABI_VERSION 6
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -217,6 +217,20 @@ typedef struct sfe_hh_init /* Hodgkin-Huxley plugin initial state, one neuron pe
     double m, n, h, current;
 } sfe_hh_init;
 
+/* Out-of-tree soma device models (sfe_device_model.h): one block per model the chip uses. Every neuron whose soma
+ * class has model == SFE_SOMA_DEVICE_MODEL is one instance; its neuron_aux is its index in the concatenation of all
+ * blocks (block b covers [sum of n_instances before b, +n_instances)). */
+struct sfe_device_model_desc;
+typedef struct sfe_device_model_block
+{
+    const struct sfe_device_model_desc *desc;
+    uint32_t n_instances;
+    uint32_t pad;
+    const double *state_init; /* [desc->n_state][n_instances] */
+    const double *params;     /* [desc->n_params][n_instances] */
+    const uint32_t *neurons;  /* [n_instances] device index of every instance */
+} sfe_device_model_block;
+
 typedef struct sfe_tables
 {
     uint32_t abi_version;
@@ -274,6 +288,10 @@ typedef struct sfe_tables
     const sfe_taps_desc *taps;
     const double *taps_values;
     uint32_t n_taps_units, n_taps_values;
+
+    /* out-of-tree soma device models used by this chip */
+    const sfe_device_model_block *device_models;
+    uint32_t n_device_models, n_device_instances;
 } sfe_tables;
 
 /* one record per simulated timestep (src/timestep.hpp:21-42) */

@@ -44,6 +44,7 @@
 #include "engine.hpp"
 #include "mt19937.cuh"
 #include "sanafe_b200.h"
+#include "sfe_device_model.h"
 
 namespace sfe
 {
@@ -240,6 +241,10 @@ struct DevState
     double *hh;            // [5][n_hh]: V, m, n, h, I
     uint32_t n_hh;
     double *nf_u2, *nf_uint; // "neurofem" neurons: u2 and the integrated error (potential = v, u1 = u)
+    // out-of-tree soma device models (sfe_device_model.h), indexed by chip-wide instance (= neuron_aux of the neuron):
+    // what the model's own kernel left for this step, and where get_potential() of the instance lives (or null)
+    const uint8_t *plug_status;
+    const double *const *plug_potential;
     StatsN *stats_n;
     StatsM *stats_m;
     sfe_step_record *log;  // ring of step records
@@ -1045,6 +1050,7 @@ __device__ __forceinline__ void soma_segment(const DevTables &t, const DevState 
                     s.nf_u2[i] = u2;
                     s.nf_uint[i] = u_int;
                 }
+                else if (c.model == SFE_SOMA_DEVICE_MODEL) st = s.plug_status[t.neuron_aux[i]]; // written by the model's own kernel
                 else st = hh_update(s.hh, s.n_hh, t.neuron_aux[i]);
             }
             s.status[i] = static_cast<uint8_t>(st);
@@ -1197,7 +1203,78 @@ __global__ void probe_kernel(const DevTables t, const DevState s)
     double v = s.v[i];
     if (model == SFE_SOMA_HH) v = s.hh[t.neuron_aux[i]];
     else if (model == SFE_SOMA_INPUT) v = 0.0; // PipelineUnit::get_potential default
+    else if (model == SFE_SOMA_DEVICE_MODEL)
+    {
+        const double *where = s.plug_potential[t.neuron_aux[i]];
+        v = where != nullptr ? *where : 0.0;
+    }
     s.probe_out[p] = v;
+}
+
+// Out-of-tree soma device models, first half of their step: the dendrite output of every instance for this timestep
+// (what the neuron phase computes inline for the built-in somas), handed to the model's own kernel as plain arrays.
+// One thread per instance; the accumulator cell is consumed here.
+struct PlugGather
+{
+    uint32_t cell0;       // the neuron's accumulator cell in slot 0
+    uint32_t stride;      // cells per slot (neurons of the core)
+    uint32_t ring;
+    uint32_t acc_mode;
+    uint32_t fixed_slots;
+    uint32_t charge_lost; // plain accumulator with the buffer inside the dendrite unit: a value, but always 0.0
+    double inv_scale;
+};
+__global__ void plug_gather_kernel(const PlugGather *g, const uint32_t n, const DevState s, double *current_in, uint8_t *has_in)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const PlugGather r = g[k];
+    const long long T = s.steps_done + 1;
+    const uint32_t slot = (r.ring > 1 && r.fixed_slots == 0u) ? static_cast<uint32_t>(T % r.ring) : 0u;
+    const uint32_t d = r.cell0 + slot * r.stride;
+    bool has = false;
+    double in = 0.0;
+    if (r.charge_lost != 0u) has = true; // src/models.cpp:78-82
+    else if (r.acc_mode == SFE_ACC_PACKED17)
+    {
+        const uint32_t raw = s.din32[d];
+        if (raw != 0u)
+        {
+            const uint32_t count = (raw + 0x10000u) >> 17;
+            has = true;
+            in = static_cast<double>(static_cast<int>(raw - (count << 17))) * r.inv_scale;
+            s.din32[d] = 0u;
+        }
+    }
+    else if (r.acc_mode == SFE_ACC_PACKED32)
+    {
+        const uint32_t raw = s.din32[d];
+        if (raw != 0u)
+        {
+            has = true;
+            in = static_cast<double>((static_cast<int>(raw << 12)) >> 12) * r.inv_scale;
+            s.din32[d] = 0u;
+        }
+    }
+    else if (r.acc_mode == SFE_ACC_DUAL32)
+    {
+        if (s.dcnt32[d] != 0u)
+        {
+            has = true;
+            in = static_cast<double>(static_cast<int>(s.din32[d])) * r.inv_scale;
+            s.din32[d] = 0u;
+            s.dcnt32[d] = 0u;
+        }
+    }
+    else if (s.dcnt32[d] != 0u)
+    {
+        has = true;
+        in = s.din64[d];
+        s.din64[d] = 0.0;
+        s.dcnt32[d] = 0u;
+    }
+    current_in[k] = in;
+    has_in[k] = has ? 1 : 0;
 }
 
 // One thread per tap line: MultiTapModel1D::update (src/models.cpp:237-257) for every event of the step that
@@ -2637,6 +2714,20 @@ struct sfe_engine
     PoissonUnit *d_poisson_units{nullptr};
     uint32_t *d_poisson_cols{nullptr}, *d_mt{nullptr}, *d_mt_idx{nullptr};
     uint32_t n_poisson_units{0};
+    // out-of-tree soma device models
+    struct PlugModel
+    {
+        const sfe_device_model_desc *desc{nullptr};
+        uint32_t n{0}, first{0}; // instances, chip-wide index of the first
+        double *d_state{nullptr}, *d_params{nullptr};
+        std::vector<double> state_init;
+    };
+    std::vector<PlugModel> plug;
+    uint32_t n_plug{0};
+    bool plug_failed{false}; // a model's launch function reported an error
+    PlugGather *d_plug_gather{nullptr};
+    double *d_plug_in{nullptr};
+    uint8_t *d_plug_has{nullptr}, *d_plug_status{nullptr};
     uint32_t n_taps_units{0}; // "taps" dendrites
     size_t tap_cells{0};
     // Poisson overlay (host-drawn, see poisson.cpp)
@@ -2722,7 +2813,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
         if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH ||
-                tb->soma_classes[k].model == SFE_SOMA_NEUROFEM || (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
+                tb->soma_classes[k].model == SFE_SOMA_NEUROFEM || tb->soma_classes[k].model == SFE_SOMA_DEVICE_MODEL || (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
             e->exotic = true;
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
         if (tb->soma_classes[k].model == SFE_SOMA_NEUROFEM) e->neurofem = true;
@@ -3180,6 +3271,64 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     if (engine_init_state(e) != 0) return -1;
 
+    // ---- out-of-tree soma device models (sfe_device_model.h) -----------------------------------------
+    if (tb->n_device_models > 0)
+    {
+        std::vector<PlugGather> gather(tb->n_device_instances);
+        std::vector<const double *> potential(tb->n_device_instances, nullptr);
+        uint32_t first = 0;
+        for (uint32_t b = 0; b < tb->n_device_models; ++b)
+        {
+            const sfe_device_model_block &blk = tb->device_models[b];
+            if (blk.desc == nullptr || blk.desc->abi_version != SFE_DEVICE_MODEL_ABI || blk.desc->launch == nullptr)
+            {
+                sfe::set_last_error("sfe_engine_create: malformed device-model block");
+                return -1;
+            }
+            sfe_engine::PlugModel m;
+            m.desc = blk.desc;
+            m.n = blk.n_instances;
+            m.first = first;
+            if (e->alloc(&m.d_state, static_cast<size_t>(m.desc->n_state) * m.n) != 0) return -1;
+            if (e->alloc(&m.d_params, static_cast<size_t>(m.desc->n_params) * m.n) != 0) return -1;
+            m.state_init.assign(blk.state_init, blk.state_init + static_cast<size_t>(m.desc->n_state) * m.n);
+            if (!m.state_init.empty())
+                SFE_CUDA(cudaMemcpyAsync(m.d_state, m.state_init.data(), m.state_init.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            if (m.desc->n_params > 0 && m.n > 0)
+                SFE_CUDA(cudaMemcpyAsync(m.d_params, blk.params, static_cast<size_t>(m.desc->n_params) * m.n * sizeof(double),
+                        cudaMemcpyHostToDevice, e->stream));
+            for (uint32_t k = 0; k < m.n; ++k)
+            {
+                const uint32_t i = blk.neurons[k];
+                uint32_t c = 0;
+                while (c + 1 < tb->n_cores && !(i >= tb->cores[c].neuron_begin && i < tb->cores[c].neuron_begin + tb->cores[c].neuron_count)) ++c;
+                const CoreDev &d = e->h_cores[c];
+                const sfe_soma_class &cls = tb->soma_classes[tb->neuron_class[i]];
+                if (cls.model != SFE_SOMA_DEVICE_MODEL || tb->neuron_aux[i] != first + k)
+                {
+                    sfe::set_last_error("sfe_engine_create: device-model block does not match the neuron tables");
+                    return -1;
+                }
+                gather[first + k] = {d.dend_base + (i - d.neuron_begin), d.neuron_count, d.ring, d.acc_mode, d.fixed_slots,
+                        (cls.dend_in_neuron != 0u && cls.dend_model == SFE_DEND_ACCUMULATOR) ? 1u : 0u, d.inv_scale};
+                if (m.desc->potential_state >= 0) potential[first + k] = m.d_state + static_cast<size_t>(m.desc->potential_state) * m.n + k;
+            }
+            first += m.n;
+            e->plug.push_back(std::move(m));
+        }
+        e->n_plug = first;
+        if (e->alloc(&e->d_plug_gather, first) != 0 || e->alloc(&e->d_plug_in, first) != 0 || e->alloc(&e->d_plug_has, first) != 0 ||
+                e->alloc(&e->d_plug_status, first) != 0)
+            return -1;
+        const double **d_pot = nullptr;
+        if (e->alloc(&d_pot, first) != 0) return -1;
+        SFE_CUDA(cudaMemcpyAsync(e->d_plug_gather, gather.data(), first * sizeof(PlugGather), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaMemcpyAsync(d_pot, potential.data(), first * sizeof(double *), cudaMemcpyHostToDevice, e->stream));
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+        e->s.plug_status = e->d_plug_status;
+        e->s.plug_potential = d_pot;
+    }
+
     // ---- shared memory of the message phase ------------------------------------------
     // A core whose dendrite cells exceed the shared-memory budget accumulates in HBM instead (acc_global): slower,
     // but such a core is rare (an ordered core with delays beyond ~2.8k neurons, an exact one beyond ~24k) and the
@@ -3486,9 +3635,35 @@ static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Out-of-tree soma device models: dendrite outputs of their instances, then every model's own update kernel, all
+// ahead of the neuron-phase kernel on the engine's stream (plain launches: fully ordered).
+static void launch_device_models(sfe_engine *e)
+{
+    if (e->plug.empty() || e->n_plug == 0) return;
+    plug_gather_kernel<<<(e->n_plug + 127) / 128, 128, 0, e->stream>>>(e->d_plug_gather, e->n_plug, e->s, e->d_plug_in, e->d_plug_has);
+    ++e->launches;
+    for (const sfe_engine::PlugModel &m : e->plug)
+    {
+        sfe_device_model_launch a{};
+        a.stream = e->stream;
+        a.n_instances = m.n;
+        a.n_state = m.desc->n_state;
+        a.n_params = m.desc->n_params;
+        a.state = m.d_state;
+        a.params = m.d_params;
+        a.current_in = e->d_plug_in + m.first;
+        a.has_in = e->d_plug_has + m.first;
+        a.status = e->d_plug_status + m.first;
+        a.timestep = e->total_timesteps + 1;
+        if (m.desc->launch(&a) != 0) e->plug_failed = true;
+        ++e->launches;
+    }
+}
+
 static void launch_soma(sfe_engine *e)
 {
     e->s.steps_done = e->total_timesteps;
+    launch_device_models(e);
     unsigned grid = e->n_segments;
     if (e->pending_fold)
     {
@@ -3806,6 +3981,11 @@ static int collect_records(sfe_engine *e, std::vector<sfe_step_record> &out)
     out.resize(static_cast<size_t>(pending));
     flush_fold(e);
     SFE_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->plug_failed)
+    {
+        sfe::set_last_error("an out-of-tree device model failed to launch its update kernel; results are invalid");
+        return -1;
+    }
     int64_t done = 0;
     while (done < pending)
     {
@@ -4023,6 +4203,10 @@ extern "C" int sfe_engine_reset(sfe_engine *e)
         SFE_CUDA(cudaMemsetAsync(e->s.nf_u2, 0, e->n_neurons * sizeof(double), e->stream));
         SFE_CUDA(cudaMemsetAsync(e->s.nf_uint, 0, e->n_neurons * sizeof(double), e->stream));
     }
+    for (const sfe_engine::PlugModel &m : e->plug)
+        for (uint32_t w = 0; w < m.desc->n_state; ++w) // the model's reset(): the state words it declared
+            if ((m.desc->reset_mask >> w) & 1u)
+                SFE_CUDA(cudaMemsetAsync(m.d_state + static_cast<size_t>(w) * m.n, 0, m.n * sizeof(double), e->stream));
     if (e->n_taps_units > 0)
     {
         // MultiTapModel1D::reset  src/models.cpp:340-348: voltages only (the lines' step counters run on)

@@ -1,6 +1,9 @@
 // lower.cpp — see lower.hpp.
 #include "lower.hpp"
 
+#include "device_model.hpp"
+#include "sfe_device_model.h"
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +34,8 @@ enum class UnitModel
     input,
     hodgkin_huxley,
     taps,
-    neurofem
+    neurofem,
+    device_model // a soma model registered out of tree (include/sfe_device_model.h)
 };
 
 struct UnitKey
@@ -63,6 +67,7 @@ struct UnitState // one used hardware unit instance of one core
     std::vector<uint8_t> synapse_to_compartment; // "neurofem": by synapse address (plugins/neurofem.cpp:120-136), default 0
     uint32_t noise_off{0}, noise_len{0}; // LIF unit with a noise file: its entries in HostTables::noise_values
     bool noise_loaded{false};
+    const sfe_device_model_desc *device_model{nullptr}; // UnitModel::device_model: the registered descriptor
     std::vector<uint32_t> sharing; // device-order list of neurons mapped to this unit (filled later)
 };
 
@@ -85,6 +90,7 @@ struct LNeuron
     sfe_soma_class cls;
     double bias{0.0};
     double potential0{0.0};
+    std::vector<double> dm_state, dm_params; // out-of-tree device model: this instance's initial state words / parameters
     std::vector<LConn> out;
     std::vector<std::pair<uint32_t, uint32_t>> axons_out; // (dest core, axon index in dest core)
 };
@@ -105,19 +111,38 @@ struct LCore
     std::unordered_map<std::string, std::pair<UnitKey, UnitState *>> synapse_hw; // get_hw results by unit name
 };
 
+// The out-of-tree device model a unit resolves to, or null: plugin_get_hw (src/plugins.cpp:85-98) with device code in
+// place of host virtuals. A model registered under the unit's model name wins (sfe_register_device_model /
+// sfe_load_device_model); otherwise the unit's `plugin:` library is loaded and asked for sfe_device_model_<model>().
+// *why receives the reason a named library did not yield a model.
+const sfe_device_model_desc *resolve_device_model(const PipelineUnitConfiguration &u, std::string *why)
+{
+    const std::string &m = u.model_info.name;
+    if (const sfe_device_model_desc *d = find_device_model(m)) return d;
+    if (!u.model_info.plugin_library_path.has_value()) return nullptr;
+    return load_device_model(m, *u.model_info.plugin_library_path, why);
+}
+
 UnitModel parse_model(const PipelineUnitConfiguration &u)
 {
     const std::string &m = u.model_info.name;
     if (u.model_info.plugin_library_path.has_value())
     {
-        // Plugins are host C++ virtuals in the reference (src/plugins.cpp:45-98).
-        // The device path needs a device functor; the models shipped with the
-        // reference are compiled in. Anything else cannot run "with no CPU fallback".
+        // Plugins are host C++ virtuals in the reference (src/plugins.cpp:45-98). The device path needs device code:
+        // a model registered through include/sfe_device_model.h (also what a `plugin:` library built with that header
+        // provides), else one of the reference's own plugins, whose functors are compiled into the engine.
+        // Anything else cannot run "with no CPU fallback".
+        std::string why;
+        if (resolve_device_model(u, &why) != nullptr) return UnitModel::device_model;
         if (m == "hodgkin_huxley") return UnitModel::hodgkin_huxley;
         if (m == "neurofem") return UnitModel::neurofem;
         throw std::runtime_error("Plugin model '" + m + "' (" + *u.model_info.plugin_library_path +
-                ") has no device functor registered; host-only plugins are not supported by the B200 engine");
+                ") has no device model: " + why + ". Host-only plugins are not supported by the B200 engine; see "
+                "include/sfe_device_model.h");
     }
+    if (find_device_model(m) != nullptr && m != "current_based" && m != "accumulator" && m != "accumulator_with_delay" &&
+            m != "leaky_integrate_fire" && m != "truenorth" && m != "input" && m != "taps")
+        return UnitModel::device_model;
     if (m == "current_based") return UnitModel::current_based;
     if (m == "accumulator") return UnitModel::accumulator;
     if (m == "accumulator_with_delay") return UnitModel::accumulator_with_delay;
@@ -234,6 +259,9 @@ void soma_defaults(const PipelineUnitConfiguration &u, const UnitModel model, sf
         break;
     case UnitModel::hodgkin_huxley:
         c.model = SFE_SOMA_HH;
+        break;
+    case UnitModel::device_model:
+        c.model = SFE_SOMA_DEVICE_MODEL;
         break;
     case UnitModel::neurofem:
         c.model = SFE_SOMA_NEUROFEM; // NeuroFEMNeuron defaults  plugins/neurofem.cpp:64-84: everything 0 but dt
@@ -395,6 +423,17 @@ void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, con
                                          "(plugins/neurofem.cpp:26-29), which no run of the reference reproduces; use sigma_v: 0");
         }
         // force_update / force_soma_update are stored but never read by the model's update()
+    }
+    else if (model == UnitModel::device_model)
+    {
+        // set_attribute_neuron of an out-of-tree model: the attribute initialises the state word / parameter of that
+        // name; names the model does not declare are ignored (as PipelineUnit subclasses ignore unknown keys)
+        const sfe_device_model_desc &d = *unit.device_model;
+        if (!std::holds_alternative<double>(a.value) && !std::holds_alternative<int>(a.value)) return;
+        for (uint32_t w = 0; w < d.n_state; ++w)
+            if (d.state_names[w] != nullptr && key == d.state_names[w]) ln.dm_state[w] = a.as_double();
+        for (uint32_t q = 0; q < d.n_params; ++q)
+            if (d.param_names[q] != nullptr && key == d.param_names[q]) ln.dm_params[q] = a.as_double();
     }
     else if (model == UnitModel::hodgkin_huxley)
     {
@@ -623,6 +662,27 @@ void HostTables::finalize_view(const Architecture &arch)
     v.syn_weight = syn_weight.empty() ? nullptr : syn_weight.data();
     v.syn_meta = syn_meta.empty() ? nullptr : syn_meta.data();
     v.synth = synth.has_value() ? &*synth : nullptr;
+    // out-of-tree device models: instance rows -> SoA blocks; neuron_aux becomes the chip-wide instance index
+    device_model_view.clear();
+    uint32_t first = 0;
+    for (DeviceModelBlock &b : device_models)
+    {
+        const uint32_t n = static_cast<uint32_t>(b.neurons.size());
+        b.state_init.assign(static_cast<size_t>(b.desc->n_state) * n, 0.0);
+        b.params.assign(static_cast<size_t>(b.desc->n_params) * n, 0.0);
+        for (uint32_t k = 0; k < n; ++k)
+        {
+            for (uint32_t w = 0; w < b.desc->n_state; ++w) b.state_init[static_cast<size_t>(w) * n + k] = b.state_rows[k][w];
+            for (uint32_t q = 0; q < b.desc->n_params; ++q) b.params[static_cast<size_t>(q) * n + k] = b.param_rows[k][q];
+            if (!b.numbered) neuron_aux[b.neurons[k]] = first + k;
+        }
+        b.numbered = true;
+        device_model_view.push_back({b.desc, n, 0u, b.state_init.data(), b.params.data(), b.neurons.data()});
+        first += n;
+    }
+    v.device_models = device_model_view.data();
+    v.n_device_models = static_cast<uint32_t>(device_model_view.size());
+    v.n_device_instances = first;
 }
 
 uint32_t count_input_units(const Architecture &arch)
@@ -738,6 +798,21 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 (soma.model == UnitModel::truenorth && ln.soma_addr >= kTrueNorthMaxNeurons))
             throw std::out_of_range("soma unit '" + soma_cfg.name + "' is full");
         soma_defaults(soma_cfg, soma.model, ln.cls);
+        if (soma.model == UnitModel::device_model)
+        {
+            std::string why;
+            soma.device_model = resolve_device_model(soma_cfg, &why);
+            if (soma.device_model == nullptr) throw std::runtime_error("device model '" + soma_cfg.model_info.name + "' vanished: " + why);
+            const sfe_device_model_desc &d = *soma.device_model;
+            ln.dm_state.assign(d.n_state, 0.0);
+            ln.dm_params.assign(d.n_params, 0.0);
+            for (uint32_t w = 0; w < d.n_state; ++w) ln.dm_state[w] = d.state_init != nullptr ? d.state_init[w] : 0.0;
+            for (uint32_t q = 0; q < d.n_params; ++q) ln.dm_params[q] = d.param_init != nullptr ? d.param_init[q] : 0.0;
+            // set_attribute_hw: the unit's own attributes in the architecture description come first (src/pipeline.cpp:87-130)
+            for (const auto &[key, a] : soma_cfg.model_info.model_attributes) set_soma_attribute(ln, soma, soma.model, key, a);
+            if (dend.model == UnitModel::taps)
+                throw std::runtime_error("an out-of-tree soma model behind a 'taps' dendrite is not supported");
+        }
         if (soma.model == UnitModel::lif && soma_cfg.model_info.model_attributes.count("noise") != 0)
         {
             // LoihiLifModel::set_attribute_hw  src/models.cpp:351-373
@@ -972,6 +1047,22 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                         std::find(soma.sharing.begin(), soma.sharing.end(), dev) - soma.sharing.begin());
                 out.neuron_aux[dev] = static_cast<uint32_t>(out.noise.size());
                 out.noise.push_back(d);
+            }
+            else if (soma.model == UnitModel::device_model)
+            {
+                // one instance per neuron; neuron_aux is made chip-wide once every block is complete (below)
+                size_t b = 0;
+                while (b < out.device_models.size() && out.device_models[b].desc != soma.device_model) ++b;
+                if (b == out.device_models.size())
+                {
+                    out.device_models.emplace_back();
+                    out.device_models.back().desc = soma.device_model;
+                }
+                HostTables::DeviceModelBlock &blk = out.device_models[b];
+                out.neuron_aux[dev] = static_cast<uint32_t>(blk.neurons.size());
+                blk.neurons.push_back(dev);
+                blk.state_rows.push_back(ln.dm_state);
+                blk.param_rows.push_back(ln.dm_params);
             }
             else if (soma.model == UnitModel::hodgkin_huxley)
             {

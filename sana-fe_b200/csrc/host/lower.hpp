@@ -43,6 +43,17 @@ struct HostTables
     std::vector<uint32_t> neuron_taps;  // "taps" dendrites (empty when the network has none)
     std::vector<sfe_taps_desc> taps;
     std::vector<double> taps_values;
+    // out-of-tree soma device models (include/sfe_device_model.h): one block per model, instances in device order
+    struct DeviceModelBlock
+    {
+        const sfe_device_model_desc *desc{nullptr};
+        std::vector<uint32_t> neurons;
+        std::vector<std::vector<double>> state_rows, param_rows; // per instance, as the lowering fills them
+        std::vector<double> state_init, params;                  // SoA, built by finalize_view
+        bool numbered{false}; // neuron_aux already rewritten to chip-wide instance indices
+    };
+    std::vector<DeviceModelBlock> device_models;
+    std::vector<sfe_device_model_block> device_model_view;
     uint32_t input_seed_base{0}; // "input" units created in this process before this chip (set by the chip)
     uint32_t n_poisson_cols{0};
     sfe_tables view{};

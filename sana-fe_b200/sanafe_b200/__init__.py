@@ -109,7 +109,8 @@ class Tables(C.Structure):
                 ("n_noise_values", C.c_uint64), ("n_noise", C.c_uint32), ("n_u_probes", C.c_uint32),
                 ("u_probes", C.POINTER(C.c_uint32)), ("neuron_taps", C.POINTER(C.c_uint32)),
                 ("taps", C.POINTER(TapsDesc)), ("taps_values", C.POINTER(C.c_double)),
-                ("n_taps_units", C.c_uint32), ("n_taps_values", C.c_uint32)]
+                ("n_taps_units", C.c_uint32), ("n_taps_values", C.c_uint32),
+                ("device_models", C.c_void_p), ("n_device_models", C.c_uint32), ("n_device_instances", C.c_uint32)]
 
 
 class StepRecord(C.Structure):
@@ -220,6 +221,9 @@ def lib():
         "sfe_net_create": (vp, [cstr]), "sfe_net_save_yaml": (C.c_int, [vp, cstr]),
         "sfe_batch_load": (C.c_int, [vp, vp, u32, u32]),
         "sfe_batch_sim": (C.c_int, [vp, u32, i64, C.c_int, vp, vp, u32]),
+        # out-of-tree device models (include/sfe_device_model.h)
+        "sfe_register_device_model": (C.c_int, [cstr, vp]), "sfe_unregister_device_model": (C.c_int, [cstr]),
+        "sfe_load_device_model": (C.c_int, [cstr, cstr]), "sfe_device_model_registered": (C.c_int, [cstr]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)  # AttributeError if the ABI header and the library disagree
