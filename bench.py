@@ -575,6 +575,12 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     def step_once():
         assert L.sfe_engine_enqueue_partitioned(eng, 1) == 0, L.sfe_last_error()
 
+    if os.environ.get("SFE_TIMELINE"):
+        # diagnostic build (SFE_TIMELINE_ALL): every rank keeps the stamps of its last 64 steps
+        raw = np.zeros(2 * 64 * 1024 * 16, dtype=np.uint64)
+        if L.sfe_engine_read_timeline_raw(eng, raw.ctypes.data, raw.size) > 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            np.save(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}_r{rank}.npy"), raw.reshape(2, 64, 1024, 16)[:, :, :640, :])
     dist.barrier()
     sha = raster_sha(L, eng, tb, step_once, collect)
     shas = [None] * world

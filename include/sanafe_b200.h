@@ -438,6 +438,7 @@ int sfe_engine_exchange_error(sfe_engine *e);
 /* diagnostic (SFE_TIMELINE=1 at engine creation): %globaltimer stamps of every CTA of the fused step kernel for the
  * last 64 steps, out[64][grid][16]; returns the grid size, 0 when nothing was recorded */
 int sfe_engine_read_timeline(sfe_engine *e, unsigned long long *out, size_t cap_words);
+int64_t sfe_engine_read_timeline_raw(sfe_engine *e, unsigned long long *out, size_t cap_words); /* diagnostic builds */
 /* last n records of the device log (for steps replayed from a captured CUDA graph) */
 int64_t sfe_engine_read_log_tail(sfe_engine *e, sfe_step_record *out, int64_t n);
 /* Host-only plan of a chip split over `world` GPUs (no CUDA call): owner[c] = rank of core c

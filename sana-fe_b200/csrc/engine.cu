@@ -804,6 +804,13 @@ __device__ __forceinline__ void finalize_body(
 // kExotic = the chip maps input / Hodgkin-Huxley somas (kept out of the LIF /
 // TrueNorth instantiation so the common case stays at low register pressure).
 // ---------------------------------------------------------------------------
+// Diagnostic build (make variant NAME=tl EXTRA_NVFLAGS=-DSFE_TIMELINE_ALL=1, run with SFE_TIMELINE=1): the two-kernel
+// step leaves %globaltimer stamps too (tools/timeline_partitioned.py). Costs registers: never on in the shipped build.
+#ifndef SFE_TIMELINE_ALL
+#define SFE_TIMELINE_ALL 0
+#endif
+constexpr bool kTimelineAll = SFE_TIMELINE_ALL != 0;
+constexpr size_t kTimelineWords = 64ull * 1024ull * 16ull; // [64 steps][<= 1024 CTAs][16 stamps]; the neuron-phase kernel uses a second block
 constexpr int kSomaThreads = 256;
 constexpr int kSomaPerThread = 2; // neurons per thread: a segment is kSomaThreads * kSomaPerThread neurons
 
@@ -1144,6 +1151,11 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
 {
     __shared__ sfe_soma_class class_cache[kClassCache];
     __shared__ SomaScratch scr;
+    unsigned long long *tl = nullptr;
+    if constexpr (kTimelineAll)
+        if (s.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024u)
+            tl = s.timeline + kTimelineWords + ((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull;
+    if (tl != nullptr) tl[0] = global_timer_ns();
     griddep_launch_dependents();
     if (blockIdx.x >= t.n_soma_segments)
     {
@@ -1164,8 +1176,10 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         for (uint32_t x = threadIdx.x; x < t.n_soma_classes * (sizeof(sfe_soma_class) / 8); x += kSomaThreads) dst[x] = __ldg(src + x);
     }
     griddep_wait(); // everything above reads load-time tables only
+    if (tl != nullptr) tl[1] = global_timer_ns();
     soma_segment<kExotic>(t, s, blockIdx.x, classes_cached ? class_cache : nullptr, scr, s.steps_done,
             static_cast<uint32_t>(s.step_seq & 1ull));
+    if (tl != nullptr) tl[2] = global_timer_ns();
     // Partitioned chip, peer-memory exchange: the CTA that finishes the rank's last segment pushes the raster slice to
     // every peer and raises the arrival flags right here, while the message-phase kernel is already being launched
     // (its CTAs then only wait for the flags) - the publish used to open the message phase, on the critical path.
@@ -1183,6 +1197,7 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
         {
             __threadfence();
             exchange_publish(s.x, s.step_seq);
+            if (tl != nullptr) tl[3] = global_timer_ns();
         }
     }
 }
@@ -1755,6 +1770,8 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     __shared__ uint32_t scan_w[kFanoutWarps];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if constexpr (kTimelineAll && !kFused)
+        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull + 12] = global_timer_ns();
     griddep_launch_dependents();
     const bool costs_cached = t.n_cost_classes <= kCostCache;
     if (costs_cached)
@@ -1788,6 +1805,8 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     // fused launch, or the publish kernel after a stand-alone neuron phase), so its CTAs start on the SMs the
     // previous launch frees while that launch still folds its step.
     if constexpr (!kFused) griddep_wait();
+    if constexpr (kTimelineAll && !kFused)
+        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull + 13] = global_timer_ns();
     const long long T = s.steps_done + 1;
     uint32_t *const inbox = s.inbox + static_cast<size_t>(s.step_seq & 1ull) * t.inbox_words;
 
@@ -1816,12 +1835,12 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     // is its block index - no atomic, and its descriptors are fetched before the ready flag is awaited.
     bool first_item = true;
     (void) first_item;
-    unsigned long long *const tl = (kFused && s.timeline != nullptr)
-            ? s.timeline + ((s.step_seq & 63ull) * gridDim.x + blockIdx.x) * 16ull
+    unsigned long long *const tl = ((kFused || kTimelineAll) && s.timeline != nullptr)
+            ? s.timeline + ((s.step_seq & 63ull) * (kTimelineAll ? 1024ull : gridDim.x) + blockIdx.x) * 16ull
             : nullptr;
     uint32_t tl_item = 0u;
     auto stamp = [&](const uint32_t k) {
-        if (kFused && tl != nullptr && threadIdx.x == 0 && k < 16u) tl[k] = global_timer_ns();
+        if ((kFused || kTimelineAll) && tl != nullptr && threadIdx.x == 0 && k < 16u) tl[k] = global_timer_ns();
     };
     stamp(0);
 
@@ -3263,7 +3282,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.ready, 1) != 0) return -1;
     if (e->alloc(&e->s.soma_done, 1) != 0) return -1;
     if (std::getenv("SFE_TIMELINE") != nullptr)
-        if (e->alloc(&e->s.timeline, 64ull * 1024ull * 16ull) != 0) return -1; // 64 steps x up to 1024 CTAs x 16 stamps
+        if (e->alloc(&e->s.timeline, 2 * kTimelineWords) != 0) return -1; // 64 steps x up to 1024 CTAs x 16 stamps, message + neuron phase
     if (e->alloc(&e->s.core_partials, 2 * static_cast<size_t>(e->t.n_active_cores)) != 0) return -1;
     if (e->alloc(&e->s.x.error, 1) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
@@ -4518,6 +4537,16 @@ extern "C" int sfe_engine_read_timeline(sfe_engine *e, unsigned long long *out, 
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     SFE_CUDA(cudaMemcpy(out, e->s.timeline, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return static_cast<int>(e->fanout_grid);
+}
+
+// diagnostic build (SFE_TIMELINE_ALL): both stamp blocks as they are, [2][64][1024][16]; returns the words copied
+extern "C" int64_t sfe_engine_read_timeline_raw(sfe_engine *e, unsigned long long *out, size_t cap_words)
+{
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    if (e->s.timeline == nullptr || cap_words < 2 * kTimelineWords) return 0;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(out, e->s.timeline, 2 * kTimelineWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return static_cast<int64_t>(2 * kTimelineWords);
 }
 
 // 0 = fine, 1 = a peer failed to arrive within the in-kernel time limit (results invalid)

@@ -189,6 +189,7 @@ def lib():
         "sfe_engine_p2p_detach": (C.c_int, [vp]),
         "sfe_engine_exchange_error": (C.c_int, [vp]),
         "sfe_engine_read_timeline": (C.c_int, [vp, vp, sz]),
+        "sfe_engine_read_timeline_raw": (i64, [vp, vp, sz]),
         "sfe_plan_partition": (C.c_int, [vp, C.c_uint32, vp, vp, vp]),
         "sfe_engine_synchronize": (C.c_int, [vp]),
         "sfe_device_memcpy": (C.c_int, [vp, vp, sz]),
