@@ -586,13 +586,14 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     shas = [None] * world
     dist.all_gather_object(shas, sha)
     xerr = L.sfe_engine_exchange_error(eng)
+    xmsg = L.sfe_last_error().decode() if xerr != 0 else ""
     dist.barrier()
     if exchange == "p2p":
         L.sfe_engine_p2p_detach(eng)
     else:
         L.sfe_engine_comm_destroy(eng)
     if xerr != 0:
-        raise SystemExit("bench.py: a peer did not arrive at the raster exchange in time; results invalid")
+        raise SystemExit(f"bench.py: rank {rank}: {xmsg}; results invalid")
     if rank != 0:
         dist.destroy_process_group()
         return 0

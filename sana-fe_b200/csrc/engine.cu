@@ -32,6 +32,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -173,6 +175,7 @@ struct DevTables
     // partitioned chip: raster bit of the source neuron of every local axon-in, indexed by
     // (inbox bit position - 32 * inbox_lo); 0xFFFFFFFF for padding bits
     const uint32_t *axon_src;
+    const uint32_t *word_src;         // per local inbox word: how it derives from the raster (kWordGather / kWordEmpty / a raster word)
     const sfe_input_desc *inputs;
     const uint8_t *input_spikes;
     // Poisson inputs: host-drawn overlay (sfe_engine_set_input_overlay), row = step index - overlay_step0
@@ -202,23 +205,24 @@ struct DevTables
     double sync_delay;
 };
 
-// Multi-GPU exchange over peer memory (NVLink): every rank's neuron phase stores its raster
-// words straight into every rank's double-buffered raster and then raises an arrival flag
-// there; the message phase of a rank starts by waiting for the flags of all ranks.
+// Multi-GPU exchange over peer memory (NVLink), flag-in-data: a raster word travels as an 8-byte pair (word, epoch + 1)
+// that the neuron-phase warp which produced it stores straight into every rank's double-buffered raster. There is
+// no fence, no separate arrival flag and no publishing step: a reader polls the pair it needs until its epoch matches
+// (an aligned 8-byte store arrives whole), so the exchange costs one NVLink crossing after the segment that fired.
 constexpr int kMaxPeers = 8;
 struct Exchange
 {
-    uint32_t *raster[kMaxPeers];  // [2][fired_words] of every rank (own entry: local memory)
-    uint32_t *flags[kMaxPeers];   // [world] arrival flags of every rank
-    uint32_t n_peers;             // 0: exchange done by the host side (NCCL / device copies)
+    uint2 *ll[kMaxPeers];         // [2][fired_words] (word, epoch + 1) pairs of every rank (own entry: local memory)
+    // Flow control of the two-deep pair buffers: done[q][r] (in rank q's memory) = timesteps rank r has completed.
+    // Words of step t go into the buffer step t - 2 used, so a rank stores them only once every rank has completed
+    // step t - 2 (ranks are tied together only along their data dependencies: without this a rank that needs
+    // nothing from a slow peer would run ahead and overwrite words the peer has not read yet).
+    uint32_t *done[kMaxPeers];
+    uint32_t n_peers;             // 0: exchange done by the host side (NCCL / device copies) into a plain raster
     uint32_t rank;
     uint32_t fired_words;
     uint32_t slice_words;         // words per rank slice (multiple of 4)
-    uint32_t acquire_mode;
-    uint32_t publish_in_soma;     // 1: the last CTA of the neuron-phase kernel publishes the slice (else CTA 0 of the message phase)
-    const uint32_t *local_slice;  // this rank's slice as the neuron phase wrote it
-    uint32_t *error;              // sticky: a peer did not arrive in time
-    unsigned long long *stamps;   // diagnostic (SFE_PHASE_PROFILE): [4096][4] %globaltimer of CTA 0
+    uint32_t *error;              // sticky: a word did not arrive in time
 };
 
 struct StepPartial;
@@ -265,7 +269,6 @@ struct DevState
     // publishes the next step's raster (ready flag / peer exchange) and folds the chip
     uint32_t *core_done;      // [n_cores] work items of the core finished in this step
     uint32_t *cores_finished; // cores completed in this step
-    uint32_t *soma_done;      // neuron-phase CTAs finished in this step (the last one publishes the raster slice)
     uint32_t *ready;          // [0] = e + 1 once the neuron phase of step epoch e is complete on this GPU (unpartitioned chip)
     uint32_t fuse_next;       // 1: this launch also runs the neuron phase of the next step (not the last step of a batch)
     uint32_t pad_fuse;
@@ -281,12 +284,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
 {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 // Fire-and-forget OR into global memory. Written in PTX: when a kernel also contains atomics whose
@@ -306,10 +303,6 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p)
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_sys(uint32_t *p, const uint32_t v)
-{
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Programmatic dependent launch: every kernel of the step lets its successor be scheduled right
 // away (its CTAs fill SM slots as they free up and run their table-only prologue) and waits for
 // its predecessor's completion + memory flush before touching anything a kernel writes.
@@ -328,67 +321,42 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return v;
 }
 
-// Peer-memory exchange, first half (CTA 0 of the kernel that opens the message phase): copy
-// this rank's raster slice into every rank's raster with 16-byte stores over NVLink, fence once
-// at system scope, publish the arrival flags. The neuron phase that wrote the slice is the
-// previous kernel on the stream, so no intra-kernel ordering is needed on the producer side.
-__device__ __forceinline__ void exchange_publish(const Exchange &x, const unsigned long long epoch)
+// One raster word of the current step from this rank's pair buffer: polls until the producer's store has landed
+// (bounded: a missing peer sets the sticky error flag instead of hanging the GPU).
+__device__ __forceinline__ uint32_t ll_word(const uint2 *pairs, const uint32_t index, const uint32_t want, uint32_t *error)
 {
-    const size_t at = (epoch & 1ull) * x.fired_words + static_cast<size_t>(x.rank) * x.slice_words; // 16-byte aligned
-    const uint4 *src = reinterpret_cast<const uint4 *>(x.local_slice);
-    const uint32_t n_vec = x.slice_words / 4u;
-    for (uint32_t i0 = threadIdx.x; i0 < n_vec; i0 += 8u * blockDim.x)
+    const uint2 *p = pairs + index;
+    uint32_t word, flag;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(word), "=r"(flag) : "l"(p) : "memory");
+    if (flag == want) return word;
+    // time limit on the SM's own cycle counter (%globaltimer is a chip-wide register: polling it is slow); ~2 s
+    const long long t0 = clock64();
+    for (;;)
     {
-        uint4 v[8]; // eight independent loads in flight, then the stores (posted)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (i0 + j * blockDim.x < n_vec) v[j] = __ldcg(src + i0 + j * blockDim.x);
-        for (uint32_t q = 0; q < x.n_peers; ++q)
+        __nanosleep(20);
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(word), "=r"(flag) : "l"(p) : "memory");
+        if (flag == want) return word;
+        if (ld_relaxed_sys(error) != 0u) return 0u; // somebody already gave up: the run is invalid, finish it quickly
+        if (clock64() - t0 > 4000000000ll)
         {
-            uint4 *dst = reinterpret_cast<uint4 *>(x.raster[q] + at);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (i0 + j * blockDim.x < n_vec) dst[i0 + j * blockDim.x] = v[j];
+            // error[0] = 1, error[1..3] = which word, the epoch it was expected to carry, what it carried (diagnostics)
+            if (atomicCAS(error, 0u, 1u) == 0u)
+            {
+                error[1] = index;
+                error[2] = want;
+                error[3] = flag;
+            }
+            return 0u;
         }
     }
-    // ONE system-scope fence per step: the barrier orders every thread's stores before thread 0,
-    // its fence is cumulative over them, the flags follow as relaxed stores (a release store per
-    // peer would repeat the fence, which is by far the most expensive instruction here)
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    __threadfence_system();
-    const uint32_t arrive = static_cast<uint32_t>(epoch) + 1u;
-    for (uint32_t q = 0; q < x.n_peers; ++q) st_relaxed_sys(x.flags[q] + x.rank, arrive);
+}
+__device__ __forceinline__ void ll_store(uint2 *p, const uint32_t word, const uint32_t flag)
+{
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(word), "r"(flag) : "memory");
 }
 
-// Message-phase prologue: wait until every rank has published the current step (bounded: a
-// missing peer sets the sticky error flag instead of hanging the GPU). Returns the raster.
-__device__ __forceinline__ const uint32_t *exchange_wait(const Exchange &x, const unsigned long long epoch)
-{
-    if (threadIdx.x < x.n_peers && ld_relaxed_sys(x.error) == 0u)
-    {
-        const uint32_t want = static_cast<uint32_t>(epoch) + 1u;
-        const uint32_t *flag = x.flags[x.rank] + threadIdx.x;
-        // time limit on the SM's own cycle counter (%globaltimer is a chip-wide register: polling it
-        // from every waiting CTA is slow and contended); ~2 s at 2 GHz
-        const long long t0 = clock64();
-        while (static_cast<int32_t>(ld_relaxed_sys(flag) - want) < 0)
-        {
-            __nanosleep(40);
-            if (clock64() - t0 > 4000000000ll)
-            {
-                atomicExch(x.error, 1u);
-                break;
-            }
-        }
-        if (x.acquire_mode == 1u) (void) ld_acquire_sys(flag); // pairs with the publisher's fence + relaxed store
-        else if (x.acquire_mode == 2u) __threadfence();
-    }
-    __syncthreads();
-    return x.raster[x.rank] + (epoch & 1ull) * x.fired_words;
-}
 // Unpartitioned chip, fused step kernel: the launch that ran the neuron phase of step epoch e raises ready = e + 1
-// (release); the launch that processes step e's messages waits for it (acquire). Bounded like exchange_wait.
+// (release); the launch that processes step e's messages waits for it (acquire). Bounded like ll_word.
 __device__ __forceinline__ void ready_publish(uint32_t *ready, const unsigned long long epoch)
 {
     __threadfence();
@@ -1087,6 +1055,11 @@ __device__ __forceinline__ void soma_segment(const DevTables &t, const DevState 
         // spike raster: one ballot per 32 neurons
         const uint32_t ballot = __ballot_sync(0xffffffffu, st == SFE_STATUS_FIRED);
         if (lane == 0 && k < ((core.neuron_count + 31u) & ~31u)) s.fired_bits[core.fired_word_begin + (k >> 5)] = ballot;
+        // Partitioned chip, peer-memory exchange: lane q hands the word to rank q as a (word, epoch + 1) pair - the
+        // whole exchange (ll_word on the reading side)
+        if (static_cast<uint32_t>(lane) < s.x.n_peers && k - lane < ((core.neuron_count + 31u) & ~31u))
+            ll_store(s.x.ll[lane] + (s.step_seq & 1ull) * s.x.fired_words + core.fired_word_begin + ((k - lane) >> 5), ballot,
+                    static_cast<uint32_t>(s.step_seq) + 1u);
         // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon of a fired
         // neuron: raise the inbox bit of every target (loads batched eight at a time).
         if (st == SFE_STATUS_FIRED) n_packets += a1 - a0;
@@ -1177,29 +1150,33 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     }
     griddep_wait(); // everything above reads load-time tables only
     if (tl != nullptr) tl[1] = global_timer_ns();
+    if (s.x.n_peers > 0u && threadIdx.x < s.x.n_peers)
+    {
+        // the message phase of every earlier step has completed on this rank (stream order): tell the peers ...
+        const uint32_t completed = static_cast<uint32_t>(s.step_seq);
+        if (blockIdx.x == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(s.x.done[threadIdx.x] + s.x.rank), "r"(completed) : "memory");
+        // ... and hold this step's words back until every peer has completed the step whose buffer they reuse
+        const uint32_t *peer_done = s.x.done[s.x.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while (static_cast<int32_t>(ld_relaxed_sys(peer_done) + 1u - completed) < 0)
+        {
+            __nanosleep(100);
+            if (ld_relaxed_sys(s.x.error) != 0u) break;
+            if (clock64() - t0 > 4000000000ll)
+            {
+                if (atomicCAS(s.x.error, 0u, 2u) == 0u)
+                {
+                    s.x.error[1] = threadIdx.x;
+                    s.x.error[2] = completed;
+                    s.x.error[3] = ld_relaxed_sys(peer_done);
+                }
+                break;
+            }
+        }
+    }
     soma_segment<kExotic>(t, s, blockIdx.x, classes_cached ? class_cache : nullptr, scr, s.steps_done,
             static_cast<uint32_t>(s.step_seq & 1ull));
     if (tl != nullptr) tl[2] = global_timer_ns();
-    // Partitioned chip, peer-memory exchange: the CTA that finishes the rank's last segment pushes the raster slice to
-    // every peer and raises the arrival flags right here, while the message-phase kernel is already being launched
-    // (its CTAs then only wait for the flags) - the publish used to open the message phase, on the critical path.
-    if (s.x.n_peers > 0u && s.x.publish_in_soma != 0u)
-    {
-        __shared__ uint32_t last_cta;
-        if (threadIdx.x == 0)
-        {
-            __threadfence(); // this segment's raster words before the count
-            last_cta = atomicAdd(s.soma_done, 1u) + 1u == t.n_soma_segments ? 1u : 0u;
-            if (last_cta != 0u) *s.soma_done = 0u;
-        }
-        __syncthreads();
-        if (last_cta != 0u)
-        {
-            __threadfence();
-            exchange_publish(s.x, s.step_seq);
-            if (tl != nullptr) tl[3] = global_timer_ns();
-        }
-    }
 }
 
 // potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
@@ -1366,12 +1343,27 @@ __device__ __forceinline__ void ready_wait(const DevState &s, const unsigned lon
 // arrival flags; every lookup comes after that point, so cached lines are never stale. Not
 // __ldg: the non-coherent path is outside the memory model's guarantees for data written
 // while the kernel runs.
-__device__ __forceinline__ uint32_t ld_raster(const uint32_t *p)
+// How a message-phase thread reads raster word `index` of the current step: from the plain raster (NCCL / host-side
+// exchange: complete before the kernel starts; plain L1-cached loads, never __ldg - the raster is rewritten between
+// kernels), or from this rank's pair buffer of the peer-memory exchange (ll_word: polls until the word has landed).
+struct RasterView
 {
-    return *p;
-}
+    const uint32_t *plain;
+    const uint2 *pairs; // non-null: peer-memory exchange
+    uint32_t want;      // epoch + 1
+    uint32_t *error;
+    __device__ __forceinline__ uint32_t word(const uint32_t index) const
+    {
+        return pairs != nullptr ? ll_word(pairs, index, want, error) : plain[index];
+    }
+};
 
-__device__ __forceinline__ uint32_t gather_inbox_word(const uint32_t *__restrict__ src32, const uint32_t *raster)
+// One inbox word = 32 local axons-in. Load-time table word_src tells how to derive it from the raster: an index
+// below kWordGather = the 32 axons are fed by 32 consecutive neurons that fill one raster word (every dense
+// projection between word-aligned populations: the word is copied), kWordEmpty = padding only, kWordGather = look
+// up the raster bit of each axon's source neuron (axon_src).
+constexpr uint32_t kWordGather = 0xFFFFFFFFu, kWordEmpty = 0xFFFFFFFEu;
+__device__ __forceinline__ uint32_t gather_inbox_word(const uint32_t *__restrict__ src32, const RasterView &raster)
 {
     uint32_t word = 0u;
 #pragma unroll 1
@@ -1389,13 +1381,20 @@ __device__ __forceinline__ uint32_t gather_inbox_word(const uint32_t *__restrict
             for (int k = 0; k < 4; ++k)
             {
                 // padding axons point at 0xFFFFFFFF
-                const uint32_t r = src[k] != 0xFFFFFFFFu ? ld_raster(raster + (src[k] >> 5)) : 0u;
+                const uint32_t r = src[k] != 0xFFFFFFFFu ? raster.word(src[k] >> 5) : 0u;
                 half |= ((r >> (src[k] & 31u)) & 1u) << (4 * q + k);
             }
         }
         word |= half << (16 * h);
     }
     return word;
+}
+__device__ __forceinline__ uint32_t inbox_word_from_raster(const DevTables &t, const size_t local_word, const RasterView &raster)
+{
+    const uint32_t ws = __ldg(t.word_src + local_word);
+    if (ws < kWordEmpty) return raster.word(ws);
+    if (ws == kWordEmpty) return 0u;
+    return gather_inbox_word(t.axon_src + (local_word << 5), raster);
 }
 
 // ---------------------------------------------------------------------------
@@ -1810,24 +1809,13 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     const long long T = s.steps_done + 1;
     uint32_t *const inbox = s.inbox + static_cast<size_t>(s.step_seq & 1ull) * t.inbox_words;
 
-    // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory exchange the collective
-    // is fused into the step's kernels: the rank's raster slice is pushed to every rank over NVLink (by the last CTA
-    // of the neuron-phase kernel, or by CTA 0 here), and every CTA of this kernel (one resident wave) waits for the
-    // slices of all ranks before it touches the raster.
-    const uint32_t *raster = s.fired_global;
-    if constexpr (!kFused)
-    {
-        if (s.x.n_peers > 0u)
-        {
-            const bool stamp = s.x.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-            unsigned long long *st = stamp ? s.x.stamps + (s.step_seq & 4095ull) * 4ull : nullptr;
-            if (stamp) st[0] = global_timer_ns();
-            if (blockIdx.x == 0 && s.x.publish_in_soma == 0u) exchange_publish(s.x, s.step_seq);
-            if (stamp) st[1] = global_timer_ns();
-            raster = exchange_wait(s.x, s.step_seq);
-            if (stamp) st[2] = global_timer_ns();
-        }
-    }
+    // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory exchange there is nothing
+    // to wait for here: every raster word is awaited where it is read (RasterView / ll_word).
+    RasterView raster;
+    raster.plain = s.fired_global;
+    raster.pairs = s.x.n_peers > 0u ? s.x.ll[s.x.rank] + (s.step_seq & 1ull) * s.x.fired_words : nullptr;
+    raster.want = static_cast<uint32_t>(s.step_seq) + 1u;
+    raster.error = s.x.error;
     const bool gather = t.partitioned != 0u;
     // Work items are handed out through an atomic ticket counter of the step's own (s.work points at the step's slot
     // of a pool the host clears per batch: launches of consecutive steps overlap in the fused step kernel, and a
@@ -1864,8 +1852,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     if (kFused && first_item)
     {
         // the descriptors of the first item are in registers: now wait for the step's raster / inbox to be complete
-        if (s.x.n_peers > 0u) raster = exchange_wait(s.x, s.step_seq);
-        else ready_wait(s, s.step_seq);
+        ready_wait(s, s.step_seq);
         first_item = false;
         stamp(1);
     }
@@ -1935,7 +1922,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             const uint32_t wi = wb + threadIdx.x;
             uint32_t word = 0u;
             if (wi < n_words)
-                word = gather ? gather_inbox_word(t.axon_src + (static_cast<size_t>(core.inbox_word_begin + wi - t.inbox_lo) << 5), raster)
+                word = gather ? inbox_word_from_raster(t, core.inbox_word_begin + wi - t.inbox_lo, raster)
                               : inbox[core.inbox_word_begin + wi];
             const uint32_t pc = __popc(word);
             uint32_t incl = pc;
@@ -2258,7 +2245,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             if (gather)
             {
                 const uint32_t src = __ldg(t.axon_src + (static_cast<size_t>(core.inbox_word_begin + wi - t.inbox_lo) << 5) + lane);
-                const uint32_t r = src != 0xFFFFFFFFu ? ld_raster(raster + (src >> 5)) : 0u;
+                const uint32_t r = src != 0xFFFFFFFFu ? raster.word(src >> 5) : 0u;
                 word = __ballot_sync(0xffffffffu, ((r >> (src & 31u)) & 1u) != 0u);
             }
             else
@@ -2453,8 +2440,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
                 __threadfence();
                 if (s.fuse_next != 0u)
                 {
-                    if (s.x.n_peers > 0u) exchange_publish(s.x, s.step_seq + 1ull);
-                    else if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq + 1ull);
+                    if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq + 1ull);
                 }
                 stamp(14);
                 if (warp == 0) fold_chip(t, s, lane);
@@ -2652,7 +2638,7 @@ constexpr uint32_t kWorkPool = 8192; // >= 2 x the device log capacity (steps th
 
 struct sfe_engine
 {
-    uint32_t *p2p_block{nullptr};        // [2][fired_words] raster + [kMaxPeers] flags, exported over CUDA IPC
+    uint2 *p2p_block{nullptr};           // [2][fired_words] (word, epoch + 1) pairs, exported over CUDA IPC
     void *p2p_peer_base[kMaxPeers] = {}; // opened peer blocks (own entry stays null)
     bool p2p_on{false};
     bool q4_any{false};
@@ -2943,6 +2929,21 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
                         if (bits[a] >= lo && bits[a] < hi) src[bits[a] - lo] = e->fired_word_begin[c] * 32u + k;
                 }
             if (e->upload(&e->t.axon_src, src.data(), src.size()) != 0) return -1;
+            // per inbox word: copied raster word, padding only, or gathered bit by bit (see inbox_word_from_raster)
+            std::vector<uint32_t> word_src(src.size() / 32u, kWordGather);
+            for (size_t w = 0; w < word_src.size(); ++w)
+            {
+                const uint32_t *a = src.data() + 32u * w;
+                bool empty = true, copied = a[0] != 0xFFFFFFFFu && (a[0] & 31u) == 0u;
+                for (uint32_t j = 0; j < 32u; ++j)
+                {
+                    empty = empty && a[j] == 0xFFFFFFFFu;
+                    copied = copied && a[j] == a[0] + j;
+                }
+                if (empty) word_src[w] = kWordEmpty;
+                else if (copied) word_src[w] = a[0] >> 5;
+            }
+            if (e->upload(&e->t.word_src, word_src.data(), word_src.size()) != 0) return -1;
         }
         SFE_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -3280,11 +3281,10 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
     if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
     if (e->alloc(&e->s.ready, 1) != 0) return -1;
-    if (e->alloc(&e->s.soma_done, 1) != 0) return -1;
     if (std::getenv("SFE_TIMELINE") != nullptr)
         if (e->alloc(&e->s.timeline, 2 * kTimelineWords) != 0) return -1; // 64 steps x up to 1024 CTAs x 16 stamps, message + neuron phase
     if (e->alloc(&e->s.core_partials, 2 * static_cast<size_t>(e->t.n_active_cores)) != 0) return -1;
-    if (e->alloc(&e->s.x.error, 1) != 0) return -1;
+    if (e->alloc(&e->s.x.error, 4) != 0) return -1;
     e->final_grid = std::max<unsigned>(1u, (e->t.n_active_cores + kFinalThreads / 32 - 1) / (kFinalThreads / 32));
     if (e->alloc(&e->s.partials, e->final_grid) != 0) return -1;
     SFE_CUDA(cudaMemcpyAsync(e->s.bias, tb->neuron_bias, tb->n_neurons * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -3548,7 +3548,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             // spreads the same work over hundreds of CTAs), so the two-kernel step wins at every scale tried (C4 on
             // 1/2/4/8 GPUs, a 128-core chip). The fused kernel stays as an option: SFE_FUSED_STEP=1.
             const char *fused = std::getenv("SFE_FUSED_STEP");
-            e->fused_ok = (fused != nullptr && std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0 &&
+            e->fused_ok = (fused != nullptr && std::atoi(fused) != 0) && !e->exotic && e->n_taps_units == 0 && e->world == 1 &&
                     !e->soma_list.empty() && !e->fanout_list.empty();
             const char *piggy = std::getenv("SFE_PIGGYBACK_FINALIZE"); // 0: a finalize kernel per step
             e->piggyback = piggy == nullptr || std::atoi(piggy) != 0;
@@ -3759,8 +3759,7 @@ __global__ void __launch_bounds__(256) publish_kernel(const DevTables t, const D
     (void) t;
     griddep_launch_dependents();
     griddep_wait();
-    if (s.x.n_peers > 0u) exchange_publish(s.x, s.step_seq);
-    else if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq);
+    if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq);
 }
 
 static int apply_pending_bias(sfe_engine *e);
@@ -4369,8 +4368,37 @@ extern "C" int sfe_engine_read_raster(sfe_engine *e, uint32_t *words, size_t n_w
         return -1;
     }
     const uint32_t *src = e->world > 1 ? e->d_fired_global : e->d_fired_local;
-    // peer-memory exchange: the ranks store their slices straight into this rank's double-buffered raster
-    if (e->p2p_on && e->s.step_seq > 0) src = e->p2p_block + ((e->s.step_seq - 1ull) & 1ull) * e->fired_words;
+    if (e->p2p_on && e->s.step_seq > 0)
+    {
+        // peer-memory exchange: the ranks store (word, epoch + 1) pairs straight into this rank's double-buffered raster.
+        // Ranks are tied together only along their data dependencies, so a peer this rank needs nothing from may still
+        // be working on the step: wait (bounded) until the words of every core carry the step's tag.
+        std::vector<uint2> pairs(n_words);
+        SFE_CUDA(cudaStreamSynchronize(e->stream));
+        const uint32_t want = static_cast<uint32_t>(e->s.step_seq - 1ull) + 1u;
+        const uint2 *from = e->p2p_block + ((e->s.step_seq - 1ull) & 1ull) * e->fired_words;
+        for (int attempt = 0;; ++attempt)
+        {
+            SFE_CUDA(cudaMemcpy(pairs.data(), from, n_words * sizeof(uint2), cudaMemcpyDeviceToHost));
+            bool complete = true;
+            for (size_t c = 0; c < e->core_desc.size() && complete; ++c)
+                for (uint32_t w = 0; w < (e->core_desc[c].neuron_count + 31u) / 32u; ++w)
+                    if (pairs[e->fired_word_begin[c] + w].y != want)
+                    {
+                        complete = false;
+                        break;
+                    }
+            if (complete) break;
+            if (attempt > 20000)
+            {
+                sfe::set_last_error("sfe_engine_read_raster: a peer has not delivered its raster words of the last step");
+                return -1;
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(100));
+        }
+        for (size_t k = 0; k < n_words; ++k) words[k] = pairs[k].y == want ? pairs[k].x : 0u; // (pad words are never written)
+        return 0;
+    }
     SFE_CUDA(cudaMemcpyAsync(words, src, n_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
@@ -4460,7 +4488,7 @@ extern "C" int sfe_engine_p2p_export(sfe_engine *e, void *handle64)
         return -1;
     }
     if (e->p2p_block == nullptr)
-        if (e->alloc(&e->p2p_block, 2 * static_cast<size_t>(e->fired_words) + kMaxPeers) != 0) return -1;
+        if (e->alloc(&e->p2p_block, 2 * static_cast<size_t>(e->fired_words) + kMaxPeers / 2) != 0) return -1; // pairs + done[8]
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     cudaIpcMemHandle_t h;
     SFE_CUDA(cudaIpcGetMemHandle(&h, e->p2p_block));
@@ -4476,10 +4504,16 @@ extern "C" int sfe_engine_p2p_attach(sfe_engine *e, const void *handles)
         sfe::set_last_error("sfe_engine_p2p_attach: call sfe_engine_p2p_export first");
         return -1;
     }
+    if (e->soma_list.empty())
+    {
+        sfe::set_last_error("sfe_engine_p2p_attach: every rank of the peer-memory exchange must own neurons (its neuron phase reports "
+                            "the rank's progress to the peers)");
+        return -1;
+    }
     SFE_CUDA(cudaStreamSynchronize(e->stream));
     for (uint32_t q = 0; q < e->world; ++q)
     {
-        uint32_t *base = e->p2p_block;
+        uint2 *base = e->p2p_block;
         if (q != e->rank)
         {
             cudaIpcMemHandle_t h;
@@ -4487,25 +4521,15 @@ extern "C" int sfe_engine_p2p_attach(sfe_engine *e, const void *handles)
             void *opened = nullptr;
             SFE_CUDA(cudaIpcOpenMemHandle(&opened, h, cudaIpcMemLazyEnablePeerAccess));
             e->p2p_peer_base[q] = opened;
-            base = static_cast<uint32_t *>(opened);
+            base = static_cast<uint2 *>(opened);
         }
-        e->s.x.raster[q] = base;
-        e->s.x.flags[q] = base + 2 * static_cast<size_t>(e->fired_words);
+        e->s.x.ll[q] = base;
+        e->s.x.done[q] = reinterpret_cast<uint32_t *>(base + 2 * static_cast<size_t>(e->fired_words));
     }
     e->s.x.n_peers = e->world;
     e->s.x.rank = e->rank;
     e->s.x.fired_words = e->fired_words;
     e->s.x.slice_words = e->slice_words;
-    e->s.x.local_slice = e->d_fired_local;
-    e->s.x.acquire_mode = 1u;
-    {
-        // SFE_PUBLISH_IN_SOMA=0: CTA 0 of the message phase publishes (round-1 behaviour)
-        const char *v = std::getenv("SFE_PUBLISH_IN_SOMA");
-        e->s.x.publish_in_soma = ((v == nullptr || std::atoi(v) != 0) && !e->soma_list.empty()) ? 1u : 0u;
-    }
-    if (const char *v = std::getenv("SFE_XCHG_ACQUIRE")) e->s.x.acquire_mode = static_cast<uint32_t>(std::atoi(v));
-    if (std::getenv("SFE_PHASE_PROFILE") != nullptr && e->s.x.stamps == nullptr)
-        if (e->alloc(&e->s.x.stamps, 4096 * 4) != 0) return -1;
     e->p2p_on = true;
     return 0;
 }
@@ -4553,10 +4577,17 @@ extern "C" int64_t sfe_engine_read_timeline_raw(sfe_engine *e, unsigned long lon
 extern "C" int sfe_engine_exchange_error(sfe_engine *e)
 {
     SFE_CUDA(cudaSetDevice(e->device));
-    uint32_t v = 0;
+    uint32_t v[4] = {0, 0, 0, 0};
     SFE_CUDA(cudaStreamSynchronize(e->stream));
-    SFE_CUDA(cudaMemcpy(&v, e->s.x.error, sizeof(v), cudaMemcpyDeviceToHost));
-    return static_cast<int>(v);
+    SFE_CUDA(cudaMemcpy(v, e->s.x.error, sizeof(v), cudaMemcpyDeviceToHost));
+    if (v[0] == 2u)
+        sfe::set_last_error("raster exchange: rank " + std::to_string(v[1]) + " did not complete step " + std::to_string(v[2] >= 2 ? v[2] - 2 : 0) +
+                " in time (rank " + std::to_string(e->rank) + " holds its words back; the peer reported " + std::to_string(v[3]) + " completed steps)");
+    else if (v[0] != 0u)
+        sfe::set_last_error("raster exchange: word " + std::to_string(v[1]) + " (slice of rank " +
+                std::to_string(e->slice_words != 0 ? v[1] / e->slice_words : 0) + ") did not arrive at rank " + std::to_string(e->rank) +
+                " in time: expected epoch tag " + std::to_string(v[2]) + ", found " + std::to_string(v[3]));
+    return static_cast<int>(v[0]);
 }
 
 // ---- multi-GPU: one engine per rank, spikes exchanged as a fired-bit raster ---------------
@@ -4876,14 +4907,6 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
     // each (diagnostic only)
     static const bool profile = std::getenv("SFE_PHASE_PROFILE") != nullptr;
     const int64_t prof_steps = profile ? std::min<int64_t>(timesteps, 128) : 0;
-    if (e->fused_ok && e->p2p_on && timesteps >= 2 && !profile)
-    {
-        // the fused step kernel: the raster exchange of step t + 1 is published by the launch of step t as soon as
-        // the rank's last core has run its neuron phase; every rank launches the same sequence
-        if (enqueue_fused(e, timesteps) != 0) return -1;
-        SFE_CUDA(cudaGetLastError());
-        return 0;
-    }
     if (prepare_tickets(e, timesteps) != 0) return -1;
     e->tickets_prepared = true;
     for (int64_t s = 0; s < timesteps; ++s)
@@ -4926,23 +4949,6 @@ extern "C" int sfe_engine_enqueue_partitioned(sfe_engine *e, int64_t timesteps)
         std::fprintf(stderr, "[sfe phase profile] rank %d: soma %.1f us, exchange %.1f us, fanout %.1f us, "
                 "finalize %.1f us, gap %.1f us (mean of %lld steps)\n",
                 e->rank, acc[0] * d, acc[1] * d, acc[2] * d, acc[3] * d, acc[4] * d, static_cast<long long>(prof_steps));
-        if (e->p2p_on && e->s.x.stamps != nullptr)
-        {
-            std::vector<unsigned long long> st(4096 * 4);
-            cudaMemcpy(st.data(), e->s.x.stamps, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-            double pub = 0.0, wait = 0.0;
-            int n = 0;
-            for (int k = 0; k < 4096; ++k)
-                if (st[4 * k + 2] > st[4 * k] && st[4 * k] != 0)
-                {
-                    pub += static_cast<double>(st[4 * k + 1] - st[4 * k]);
-                    wait += static_cast<double>(st[4 * k + 2] - st[4 * k + 1]);
-                    ++n;
-                }
-            if (n > 0)
-                std::fprintf(stderr, "[sfe phase profile] rank %d: inside fanout CTA 0: publish %.1f us, wait for peers %.1f us (%d steps)\n",
-                        e->rank, 1e-3 * pub / n, 1e-3 * wait / n, n);
-        }
         for (cudaEvent_t ev : g_prof_events) cudaEventDestroy(ev);
         g_prof_events.clear();
     }

@@ -6,7 +6,7 @@ for spec in "$@"; do
   label="${spec%%:*}"; envs=""
   if [[ "$spec" == *:* ]]; then envs="${spec#*:}"; fi
   envs="${envs//,/ }"
-  env $envs timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${AB_STEPS:-200} --warmup 20 > gpurun_out/sc_${label}_n$N.json 2> gpurun_out/sc_${label}_n$N.err
+  env $envs timeout ${AB_TIMEOUT:-100} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps ${AB_STEPS:-200} --warmup 20 > gpurun_out/sc_${label}_n$N.json 2> gpurun_out/sc_${label}_n$N.err
   python - "$label" "$N" <<'PY'
 import json, sys
 label, n = sys.argv[1], sys.argv[2]
