@@ -1803,7 +1803,24 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     // below, for the READY FLAG of its step (raised by the launch that ran the step's neuron phase: the previous
     // fused launch, or the publish kernel after a stand-alone neuron phase), so its CTAs start on the SMs the
     // previous launch frees while that launch still folds its step.
-    if constexpr (!kFused) griddep_wait();
+    if constexpr (!kFused)
+    {
+        // Still table-only: walk the descriptor chain of this CTA's first work item (its block index, see below) so
+        // that the lines sit in L1 when the item is opened after the wait - three dependent loads off the critical path.
+        if (blockIdx.x < t.n_fan_items)
+        {
+            const FanItem *it0 = t.fan_items + __ldg(t.fan_order + blockIdx.x);
+            const uint32_t c0 = __ldg(&it0->core), w0 = __ldg(&it0->word_lo);
+            const CoreDev *cd0 = t.cores + c0;
+            if (threadIdx.x < 2u) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(cd0) + 128u * threadIdx.x));
+            if (t.partitioned != 0u)
+            {
+                const size_t local = static_cast<size_t>(__ldg(&cd0->inbox_word_begin)) + w0 - t.inbox_lo + threadIdx.x;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(t.word_src + local));
+            }
+        }
+        griddep_wait();
+    }
     if constexpr (kTimelineAll && !kFused)
         if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull + 13] = global_timer_ns();
     const long long T = s.steps_done + 1;
@@ -1837,11 +1854,12 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     for (;;)
     {
     __syncthreads(); // previous core fully retired (smem accumulators, next_item)
-    if (kFused && first_item)
+    if (first_item)
     {
-        if (threadIdx.x == 0) next_item = blockIdx.x;
+        if (threadIdx.x == 0) next_item = blockIdx.x; // no atomic for the first item; its descriptors are on their way already
+        if constexpr (!kFused) first_item = false;
     }
-    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) + (kFused ? gridDim.x : 0u);
+    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) + gridDim.x;
     __syncthreads();
     const uint32_t ticket = next_item;
     if (ticket >= t.n_fan_items) break;
@@ -3497,15 +3515,23 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             }
         }
         if (const char *v = std::getenv("SFE_FANOUT_SPLIT")) split = std::max(1, std::atoi(v));
+        // parts per core: `split`, capped by the core's inbox size (>= 8 words per slice; an ordered core is one item)
+        std::vector<uint32_t> parts_of(tb->n_cores, 1u);
+        size_t n_items = 0;
+        for (uint32_t c : e->fanout_list)
+        {
+            const CoreDev &d = e->h_cores[c];
+            const uint32_t words = (d.axon_count + 31u) / 32u;
+            parts_of[c] = d.acc_mode == SFE_ACC_ORDERED ? 1u : static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(split, words / 8)));
+            n_items += parts_of[c];
+        }
         std::vector<FanItem> items;
         std::vector<double> weight;
         for (uint32_t c : e->fanout_list)
         {
             const CoreDev &d = e->h_cores[c];
             const uint32_t words = (d.axon_count + 31u) / 32u;
-            const uint32_t parts = d.acc_mode == SFE_ACC_ORDERED
-                    ? 1u
-                    : static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(split, words / 8)));
+            const uint32_t parts = parts_of[c];
             e->h_cores[c].item_begin = static_cast<uint32_t>(items.size());
             e->h_cores[c].item_count = parts;
             for (uint32_t k = 0; k < parts; ++k)

@@ -1,2 +1,1 @@
-AB_TIMEOUT=80 bash tools/ab_scale.sh 8 ll
-grep "bench.py: rank" gpurun_out/sc_ll_n8.err | head -3
+AB_TIMEOUT=80 bash tools/ab_scale.sh 4 bal nobal:SFE_FANOUT_SPLIT=2 bal2
