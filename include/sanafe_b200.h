@@ -346,6 +346,10 @@ int sfe_engine_set_stream(sfe_engine *e, void *stream);
 int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_request *req, sfe_run_data *out);
 /* Enqueue steps without any host synchronisation or read-back (benchmark / graph use). */
 int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps);
+/* `timesteps` steps of n independent chips in lock step with one launch per phase and step for the whole batch
+ * (design-space sweeps; sfe_batch_sim uses it). 0 = enqueued, 1 = these chips cannot run as one batch (nothing enqueued),
+ * -1 = error. Collect every engine afterwards as after sfe_engine_enqueue. */
+int sfe_engine_batch_enqueue(sfe_engine *const *engines, uint32_t n, int64_t timesteps);
 /* Collect per-step records of the steps enqueued since the last collect. */
 int sfe_engine_collect(sfe_engine *e, sfe_run_data *out);
 /* reset(): zero model state, keep the timestep counter (src/chip.cpp:576-600) */

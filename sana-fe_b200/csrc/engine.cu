@@ -225,6 +225,22 @@ struct Exchange
     uint32_t *error;              // sticky: a word did not arrive in time
 };
 
+// What changes from launch to launch (host-side counters, passed by value next to the tables and the state; a batched
+// launch derives a chip's copy from the one its chips - in lock step - share).
+struct StepVars
+{
+    unsigned long long step_seq; // steps enqueued on the engine so far: parity of the double-buffered per-step arrays,
+                                 // tag of the raster exchange
+    long long steps_done;        // timesteps simulated before this step (T = steps_done + 1)
+    long long fold_step;         // 0-based index of the step whose record this launch appends (slot of the device log)
+    uint32_t fold_parity;        // parity of the step the stand-alone / piggy-backed fold works on
+    uint32_t fuse_next;          // fused step kernel: this launch also runs the neuron phase of the next step
+    uint32_t *work;              // ticket counter of this step's message phase (a slot of the engine's pool, see prepare_tickets)
+    // CTAs of THIS chip in the running launch: neuron-phase kernel = segments + fold CTAs, message-phase kernel =
+    // persistent CTAs drawing work items
+    uint32_t soma_grid, fanout_grid;
+};
+
 struct StepPartial;
 struct DevState
 {
@@ -255,14 +271,6 @@ struct DevState
     uint32_t log_cap;
     double *probe_out;     // [n_probes] potentials of the current step
     long long *step;       // [0] = timesteps simulated so far (T-1 during step T), [1] = log cursor
-    // Steps enqueued on this engine so far (host-side counter, passed by value with every launch):
-    // parity / flag value of the raster exchange and base of the monotonic work-ticket counter.
-    unsigned long long step_seq;
-    long long steps_done;   // timesteps simulated before this step (host counter; T = steps_done + 1)
-    uint32_t fold_parity;   // parity of the step the stand-alone / piggy-backed fold works on
-    uint32_t pad_fold;
-    long long fold_step;    // 0-based index of the step whose record this launch appends (slot of the device log)
-    uint32_t *work;        // ticket counter of this step's message phase (a slot of the engine's pool, see prepare_tickets)
     uint32_t *final_ticket;
     // fused step kernel: a core is complete when all its work items of the step are done; the CTA that completes
     // it folds its statistics and runs its neuron phase of the NEXT step; the CTA that completes the last core
@@ -270,8 +278,6 @@ struct DevState
     uint32_t *core_done;      // [n_cores] work items of the core finished in this step
     uint32_t *cores_finished; // cores completed in this step
     uint32_t *ready;          // [0] = e + 1 once the neuron phase of step epoch e is complete on this GPU (unpartitioned chip)
-    uint32_t fuse_next;       // 1: this launch also runs the neuron phase of the next step (not the last step of a batch)
-    uint32_t pad_fuse;
     unsigned long long *timeline; // diagnostic (SFE_TIMELINE=1): [64 steps][grid][16] %globaltimer stamps of every CTA
     struct StepPartial *core_partials; // [2][n_active_cores], double-buffered by step parity
     struct StepPartial *partials;
@@ -692,7 +698,7 @@ __device__ __forceinline__ StepPartial fold_core(
 }
 
 // Appends the step record (one thread). schedule_messages_timestep_simple  src/schedule.cpp:61-102
-__device__ __forceinline__ void append_step_record(const DevTables &t, const DevState &s, const StepPartial &b)
+__device__ __forceinline__ void append_step_record(const DevTables &t, const DevState &s, const StepVars &sv, const StepPartial &b)
 {
     sfe_step_record r;
     r.neurons_fired = static_cast<long long>(b.fired);
@@ -708,19 +714,19 @@ __device__ __forceinline__ void append_step_record(const DevTables &t, const Dev
     r.sim_time = fmax(b.max_proc, b.max_gen) + t.sync_delay;
     // the record's slot follows from the step number the host passed with the launch (the folds of consecutive
     // steps may overlap in the fused step kernel: nothing here reads what another fold writes)
-    s.log[s.fold_step % s.log_cap] = r;
-    s.step[1] = s.fold_step + 1;
-    s.step[0] = s.fold_step + 1;
+    s.log[sv.fold_step % s.log_cap] = r;
+    s.step[1] = sv.fold_step + 1;
+    s.step[0] = sv.fold_step + 1;
 }
 
 // Chip-wide fold by one warp over the per-core partials of the step (fused step kernel).
-__device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const int lane)
+__device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s, const StepVars &sv, const int lane)
 {
-    const StepPartial *partials = s.core_partials + static_cast<size_t>(s.step_seq & 1ull) * t.n_active_cores;
+    const StepPartial *partials = s.core_partials + static_cast<size_t>(sv.step_seq & 1ull) * t.n_active_cores;
     StepPartial b = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (uint32_t k = lane; k < t.n_active_cores; k += 32) fold_partial(b, load_partial(&partials[k]));
     b = warp_fold(b);
-    if (lane == 0) append_step_record(t, s, b);
+    if (lane == 0) append_step_record(t, s, sv, b);
 }
 
 // The stand-alone form of the fold: one WARP per active core, `nblocks` CTAs numbered `block`.
@@ -730,15 +736,15 @@ __device__ __forceinline__ void fold_chip(const DevTables &t, const DevState &s,
 // (the neuron-phase kernel lends its class cache: an extra static array would push three of its
 // CTAs past the 16 KB shared-memory carve-out and cost it a third of its occupancy).
 constexpr size_t kFinalScratchBytes = (kFinalThreads / 32) * sizeof(StepPartial) + 16;
-__device__ __forceinline__ void finalize_body(
-        const DevTables &t, const DevState &s, const uint32_t block, const uint32_t nblocks, unsigned char *scratch)
+__device__ __forceinline__ void finalize_body(const DevTables &t, const DevState &s, const StepVars &sv, const uint32_t block,
+        const uint32_t nblocks, unsigned char *scratch)
 {
     StepPartial *warp_part = reinterpret_cast<StepPartial *>(scratch);
     uint32_t &ticket_s = *reinterpret_cast<uint32_t *>(scratch + (kFinalThreads / 32) * sizeof(StepPartial));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     StepPartial p = {0ull, 0ull, 0ull, 0ull, 0ull, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const uint32_t a = block * (kFinalThreads / 32) + warp;
-    if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane, s.fold_parity);
+    if (a < t.n_active_cores) p = fold_core(t, s, t.active_core_list[a], lane, sv.fold_parity);
     if (lane == 0) warp_part[warp] = p;
     __syncthreads();
     if (threadIdx.x == 0)
@@ -762,7 +768,7 @@ __device__ __forceinline__ void finalize_body(
     if (threadIdx.x != 0) return;
     b = warp_part[0];
     for (int w = 1; w < kFinalThreads / 32; ++w) fold_partial(b, warp_part[w]);
-    append_step_record(t, s, b);
+    append_step_record(t, s, sv, b);
     *s.final_ticket = 0u;
 }
 
@@ -806,7 +812,7 @@ struct SomaScratch // per-CTA reduction scratch of the neuron phase
 // phase has just finished. `steps_done` = timesteps simulated before this step, `parity` = parity of the step (the
 // per-segment statistics and the inbox are double-buffered by it). class_cache: shared copy of the class table or null.
 template <bool kExotic>
-__device__ __forceinline__ void soma_segment(const DevTables &t, const DevState &s, const uint32_t seg_idx,
+__device__ __forceinline__ void soma_segment(const DevTables &t, const DevState &s, const StepVars &sv, const uint32_t seg_idx,
         const sfe_soma_class *class_cache, SomaScratch &scr, const long long steps_done, const uint32_t parity)
 {
     uint32_t *const inbox = s.inbox + static_cast<size_t>(parity) * t.inbox_words;
@@ -1058,8 +1064,8 @@ __device__ __forceinline__ void soma_segment(const DevTables &t, const DevState 
         // Partitioned chip, peer-memory exchange: lane q hands the word to rank q as a (word, epoch + 1) pair - the
         // whole exchange (ll_word on the reading side)
         if (static_cast<uint32_t>(lane) < s.x.n_peers && k - lane < ((core.neuron_count + 31u) & ~31u))
-            ll_store(s.x.ll[lane] + (s.step_seq & 1ull) * s.x.fired_words + core.fired_word_begin + ((k - lane) >> 5), ballot,
-                    static_cast<uint32_t>(s.step_seq) + 1u);
+            ll_store(s.x.ll[lane] + (sv.step_seq & 1ull) * s.x.fired_words + core.fired_word_begin + ((k - lane) >> 5), ballot,
+                    static_cast<uint32_t>(sv.step_seq) + 1u);
         // pipeline_process_axon_out  src/chip.cpp:802-834: one message per axon of a fired
         // neuron: raise the inbox bit of every target (loads batched eight at a time).
         if (st == SFE_STATUS_FIRED) n_packets += a1 - a0;
@@ -1120,23 +1126,24 @@ __device__ __forceinline__ void soma_segment(const DevTables &t, const DevState 
 }
 
 template <bool kExotic>
-__global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s)
+__device__ __forceinline__ void soma_body(const DevTables &t, const DevState &s, const StepVars &sv, const uint32_t block)
 {
     __shared__ sfe_soma_class class_cache[kClassCache];
     __shared__ SomaScratch scr;
     unsigned long long *tl = nullptr;
     if constexpr (kTimelineAll)
-        if (s.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024u)
-            tl = s.timeline + kTimelineWords + ((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull;
+        if (s.timeline != nullptr && threadIdx.x == 0 && block < 1024u)
+            tl = s.timeline + kTimelineWords + ((sv.step_seq & 63ull) * 1024ull + block) * 16ull;
     if (tl != nullptr) tl[0] = global_timer_ns();
     griddep_launch_dependents();
-    if (blockIdx.x >= t.n_soma_segments)
+    if (block >= sv.soma_grid) return;
+    if (block >= t.n_soma_segments)
     {
         // extra CTAs: the fold of the PREVIOUS step (its statistics are complete once the previous
         // message phase has finished), off the critical path of this step
         griddep_wait();
         static_assert(sizeof(class_cache) >= kFinalScratchBytes, "the class cache doubles as the fold's scratch");
-        finalize_body(t, s, blockIdx.x - t.n_soma_segments, gridDim.x - t.n_soma_segments,
+        finalize_body(t, s, sv, block - t.n_soma_segments, sv.soma_grid - t.n_soma_segments,
                 reinterpret_cast<unsigned char *>(class_cache));
         return;
     }
@@ -1153,8 +1160,8 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
     if (s.x.n_peers > 0u && threadIdx.x < s.x.n_peers)
     {
         // the message phase of every earlier step has completed on this rank (stream order): tell the peers ...
-        const uint32_t completed = static_cast<uint32_t>(s.step_seq);
-        if (blockIdx.x == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(s.x.done[threadIdx.x] + s.x.rank), "r"(completed) : "memory");
+        const uint32_t completed = static_cast<uint32_t>(sv.step_seq);
+        if (block == 0) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(s.x.done[threadIdx.x] + s.x.rank), "r"(completed) : "memory");
         // ... and hold this step's words back until every peer has completed the step whose buffer they reuse
         const uint32_t *peer_done = s.x.done[s.x.rank] + threadIdx.x;
         const long long t0 = clock64();
@@ -1174,9 +1181,72 @@ __global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, c
             }
         }
     }
-    soma_segment<kExotic>(t, s, blockIdx.x, classes_cached ? class_cache : nullptr, scr, s.steps_done,
-            static_cast<uint32_t>(s.step_seq & 1ull));
+    soma_segment<kExotic>(t, s, sv, block, classes_cached ? class_cache : nullptr, scr, sv.steps_done,
+            static_cast<uint32_t>(sv.step_seq & 1ull));
     if (tl != nullptr) tl[2] = global_timer_ns();
+}
+
+template <bool kExotic>
+__global__ void __launch_bounds__(kSomaThreads) soma_kernel(const DevTables t, const DevState s, const StepVars sv)
+{
+    soma_body<kExotic>(t, s, sv, blockIdx.x);
+}
+
+// Design-space batches: many independent chips stepped by ONE launch per phase (the reference runs such sweeps as
+// separate processes, scripts/tcad2025/compare_nemo_perf.py:52-101). The grid is the concatenation of the chips' own
+// grids: a per-CTA map says which chip a CTA works for and which of that chip's CTAs it is. A slot carries the chip's
+// tables and state as the single-chip kernels take them by value; the chips are in lock step, so what changes from step
+// to step comes once with the launch.
+struct BatchSlot
+{
+    DevTables t;
+    DevState s;
+    uint32_t tma_off, n_segments, final_grid, fanout_grid;
+    uint32_t *work_pool; // the chip's ticket counters (kWorkPool of them)
+    unsigned long long pad_to_16;
+};
+static_assert(sizeof(BatchSlot) % 16 == 0 || (sizeof(BatchSlot) + 8) % 16 == 0, "slots are copied in 8-byte words");
+
+// A CTA of a batched launch first brings its chip's slot into shared memory (one coalesced read): the tables and the
+// state are then a shared-memory window instead of a chain of dependent global loads behind every pointer.
+__device__ __forceinline__ const BatchSlot &load_slot(const BatchSlot *slots, const uint32_t chip, unsigned long long *window)
+{
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(slots + chip);
+    for (uint32_t x = threadIdx.x; x < sizeof(BatchSlot) / 8; x += blockDim.x) window[x] = __ldg(src + x);
+    __syncthreads();
+    return *reinterpret_cast<const BatchSlot *>(window);
+}
+struct BatchStep
+{
+    long long steps_done;
+    unsigned long long step_seq;
+    long long fold_step;
+    uint32_t fold, fold_parity; // the neuron-phase launch also folds the previous step
+};
+constexpr uint32_t kWorkPool = 8192; // >= 2 x the device log capacity (steps that can be enqueued before a collect)
+
+__device__ __forceinline__ StepVars batch_vars(const BatchSlot &b, const BatchStep &a)
+{
+    StepVars sv;
+    sv.steps_done = a.steps_done;
+    sv.step_seq = a.step_seq;
+    sv.fold_step = a.fold_step;
+    sv.fold_parity = a.fold_parity;
+    sv.fuse_next = 0u;
+    sv.work = b.work_pool + (a.step_seq % kWorkPool);
+    sv.soma_grid = b.n_segments + (a.fold != 0u ? b.final_grid : 0u);
+    sv.fanout_grid = b.fanout_grid;
+    return sv;
+}
+
+template <bool kExotic>
+__global__ void __launch_bounds__(kSomaThreads, 3) soma_kernel_batch(const BatchSlot *__restrict__ slots, const uint2 *__restrict__ cta_map, const BatchStep a)
+{
+    __shared__ __align__(16) unsigned long long window[sizeof(BatchSlot) / 8];
+    const uint2 where = __ldg(cta_map + blockIdx.x); // (chip, CTA of the chip)
+    const BatchSlot &b = load_slot(slots, where.x, window);
+    const StepVars sv = batch_vars(b, a);
+    soma_body<kExotic>(b.t, b.s, sv, where.y);
 }
 
 // potentials of the probed neurons, after the neuron phase (src/chip.cpp:1071-1082)
@@ -1216,12 +1286,12 @@ struct PlugGather
     uint32_t charge_lost; // plain accumulator with the buffer inside the dendrite unit: a value, but always 0.0
     double inv_scale;
 };
-__global__ void plug_gather_kernel(const PlugGather *g, const uint32_t n, const DevState s, double *current_in, uint8_t *has_in)
+__global__ void plug_gather_kernel(const PlugGather *g, const uint32_t n, const DevState s, const StepVars sv, double *current_in, uint8_t *has_in)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const PlugGather r = g[k];
-    const long long T = s.steps_done + 1;
+    const long long T = sv.steps_done + 1;
     const uint32_t slot = (r.ring > 1 && r.fixed_slots == 0u) ? static_cast<uint32_t>(T % r.ring) : 0u;
     const uint32_t d = r.cell0 + slot * r.stride;
     bool has = false;
@@ -1273,12 +1343,12 @@ __global__ void plug_gather_kernel(const PlugGather *g, const uint32_t n, const 
 // targets the line, in arrival order (the list is sorted that way at load): catch the line up to this timestep
 // (calculate_next_state, :167-202, one RC step per elapsed timestep), add the current to the synapse's tap
 // (input_current, :215-235); the value of tap 0 after the last event is what the soma reads next step.
-__global__ void taps_kernel(const DevTables t, const DevState s)
+__global__ void taps_kernel(const DevTables t, const DevState s, const StepVars sv)
 {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= t.n_taps_units) return;
     const TapsUnit d = t.taps_units[u];
-    const long long T = s.steps_done + 1;
+    const long long T = sv.steps_done + 1;
     const uint32_t n = d.n_taps;
     double *v = s.tap_v + d.state_off, *next = s.tap_next + d.state_off;
     const double *tc = t.taps_values + d.const_off, *sc = tc + n;
@@ -1759,7 +1829,7 @@ constexpr int kTmaStageBytes = 128 * 12; // 128 fp64 weights + 128 u32 meta word
 
 // kFused: the message phase also folds the step (fused_finalize, SFE_FUSED_FINALIZE=1)
 template <int V, bool kFused>
-__global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const uint32_t tma_off)
+__device__ __forceinline__ void fanout_body(const DevTables &t, const DevState &s, const StepVars &sv, const uint32_t tma_off, const uint32_t block)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double part_d[kFanoutWarps][4];
@@ -1770,8 +1840,9 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if constexpr (kTimelineAll && !kFused)
-        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull + 12] = global_timer_ns();
+        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((sv.step_seq & 63ull) * 1024ull + block) * 16ull + 12] = global_timer_ns();
     griddep_launch_dependents();
+    if (block >= sv.fanout_grid) return;
     const bool costs_cached = t.n_cost_classes <= kCostCache;
     if (costs_cached)
         for (uint32_t x = threadIdx.x; x < t.n_cost_classes; x += kFanoutThreads) cost_cache[x] = t.costs[x];
@@ -1807,9 +1878,9 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     {
         // Still table-only: walk the descriptor chain of this CTA's first work item (its block index, see below) so
         // that the lines sit in L1 when the item is opened after the wait - three dependent loads off the critical path.
-        if (blockIdx.x < t.n_fan_items)
+        if (block < t.n_fan_items)
         {
-            const FanItem *it0 = t.fan_items + __ldg(t.fan_order + blockIdx.x);
+            const FanItem *it0 = t.fan_items + __ldg(t.fan_order + block);
             const uint32_t c0 = __ldg(&it0->core), w0 = __ldg(&it0->word_lo);
             const CoreDev *cd0 = t.cores + c0;
             if (threadIdx.x < 2u) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(cd0) + 128u * threadIdx.x));
@@ -1822,26 +1893,26 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
         griddep_wait();
     }
     if constexpr (kTimelineAll && !kFused)
-        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((s.step_seq & 63ull) * 1024ull + blockIdx.x) * 16ull + 13] = global_timer_ns();
-    const long long T = s.steps_done + 1;
-    uint32_t *const inbox = s.inbox + static_cast<size_t>(s.step_seq & 1ull) * t.inbox_words;
+        if (s.timeline != nullptr && threadIdx.x == 0) s.timeline[((sv.step_seq & 63ull) * 1024ull + block) * 16ull + 13] = global_timer_ns();
+    const long long T = sv.steps_done + 1;
+    uint32_t *const inbox = s.inbox + static_cast<size_t>(sv.step_seq & 1ull) * t.inbox_words;
 
     // Partitioned chip: the inbox is derived from the exchanged raster. With the peer-memory exchange there is nothing
     // to wait for here: every raster word is awaited where it is read (RasterView / ll_word).
     RasterView raster;
     raster.plain = s.fired_global;
-    raster.pairs = s.x.n_peers > 0u ? s.x.ll[s.x.rank] + (s.step_seq & 1ull) * s.x.fired_words : nullptr;
-    raster.want = static_cast<uint32_t>(s.step_seq) + 1u;
+    raster.pairs = s.x.n_peers > 0u ? s.x.ll[s.x.rank] + (sv.step_seq & 1ull) * s.x.fired_words : nullptr;
+    raster.want = static_cast<uint32_t>(sv.step_seq) + 1u;
     raster.error = s.x.error;
     const bool gather = t.partitioned != 0u;
-    // Work items are handed out through an atomic ticket counter of the step's own (s.work points at the step's slot
+    // Work items are handed out through an atomic ticket counter of the step's own (sv.work points at the step's slot
     // of a pool the host clears per batch: launches of consecutive steps overlap in the fused step kernel, and a
     // straggler's last, failed draw must not eat a ticket of a later step). Fused step kernel: the first item of a CTA
     // is its block index - no atomic, and its descriptors are fetched before the ready flag is awaited.
     bool first_item = true;
     (void) first_item;
     unsigned long long *const tl = ((kFused || kTimelineAll) && s.timeline != nullptr)
-            ? s.timeline + ((s.step_seq & 63ull) * (kTimelineAll ? 1024ull : gridDim.x) + blockIdx.x) * 16ull
+            ? s.timeline + ((sv.step_seq & 63ull) * (kTimelineAll ? 1024ull : sv.fanout_grid) + block) * 16ull
             : nullptr;
     uint32_t tl_item = 0u;
     auto stamp = [&](const uint32_t k) {
@@ -1856,10 +1927,10 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     __syncthreads(); // previous core fully retired (smem accumulators, next_item)
     if (first_item)
     {
-        if (threadIdx.x == 0) next_item = blockIdx.x; // no atomic for the first item; its descriptors are on their way already
+        if (threadIdx.x == 0) next_item = block; // no atomic for the first item; its descriptors are on their way already
         if constexpr (!kFused) first_item = false;
     }
-    else if (threadIdx.x == 0) next_item = atomicAdd(s.work, 1u) + gridDim.x;
+    else if (threadIdx.x == 0) next_item = atomicAdd(sv.work, 1u) + sv.fanout_grid;
     __syncthreads();
     const uint32_t ticket = next_item;
     if (ticket >= t.n_fan_items) break;
@@ -1870,7 +1941,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     if (kFused && first_item)
     {
         // the descriptors of the first item are in registers: now wait for the step's raster / inbox to be complete
-        ready_wait(s, s.step_seq);
+        ready_wait(s, sv.step_seq);
         first_item = false;
         stamp(1);
     }
@@ -2416,18 +2487,18 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
         if (core_event != 0u)
         {
             __threadfence();
-            const uint32_t parity = static_cast<uint32_t>(s.step_seq & 1ull);
+            const uint32_t parity = static_cast<uint32_t>(sv.step_seq & 1ull);
             if (warp == 0)
             {
                 const StepPartial p = fold_core(t, s, ci, lane, parity);
                 if (lane == 0) s.core_partials[static_cast<size_t>(parity) * t.n_active_cores + core.active_idx] = p;
             }
-            if (s.fuse_next != 0u && core.seg_count > 0u && core.fast_soma != 0u)
+            if (sv.fuse_next != 0u && core.seg_count > 0u && core.fast_soma != 0u)
             {
                 __syncthreads(); // (warp 0 is done with the fold; the whole dynamic shared memory is idle)
-                soma_core(t, s, core, smem_raw, s.steps_done + 1, parity ^ 1u);
+                soma_core(t, s, core, smem_raw, sv.steps_done + 1, parity ^ 1u);
             }
-            else if (s.fuse_next != 0u && core.seg_count > 0u)
+            else if (sv.fuse_next != 0u && core.seg_count > 0u)
             {
                 // the class table goes into the (now idle) list region, the reduction scratch behind it
                 sfe_soma_class *class_cache = reinterpret_cast<sfe_soma_class *>(smem_raw + list_off);
@@ -2441,7 +2512,7 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
                 }
                 __syncthreads();
                 for (uint32_t g = 0; g < core.seg_count; ++g)
-                    soma_segment<false>(t, s, core.seg_begin + g, classes_cached ? class_cache : nullptr, *scr, s.steps_done + 1,
+                    soma_segment<false>(t, s, sv, core.seg_begin + g, classes_cached ? class_cache : nullptr, *scr, sv.steps_done + 1,
                             parity ^ 1u);
             }
             __syncthreads();
@@ -2456,12 +2527,12 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
             if (core_event == 2u)
             {
                 __threadfence();
-                if (s.fuse_next != 0u)
+                if (sv.fuse_next != 0u)
                 {
-                    if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq + 1ull);
+                    if (threadIdx.x == 0) ready_publish(s.ready, sv.step_seq + 1ull);
                 }
                 stamp(14);
-                if (warp == 0) fold_chip(t, s, lane);
+                if (warp == 0) fold_chip(t, s, sv, lane);
             }
         }
     }
@@ -2474,13 +2545,31 @@ __global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? 
     if constexpr (kFused) griddep_wait();
 }
 
+template <int V, bool kFused>
+__global__ void __launch_bounds__(kFanoutThreads, (V == kStreamQ4 && !kFused) ? kQ4CtasPerSm : 3) fanout_kernel(const DevTables t, const DevState s, const StepVars sv, const uint32_t tma_off)
+{
+    fanout_body<V, kFused>(t, s, sv, tma_off, blockIdx.x);
+}
+
+// batched launch (see soma_kernel_batch): 3 CTAs per SM - the tables are read through a pointer instead of the
+// constant bank, and the chips of a batch are small and latency-bound, so registers matter more than occupancy
+template <int V>
+__global__ void __launch_bounds__(kFanoutThreads, 3) fanout_kernel_batch(const BatchSlot *__restrict__ slots, const uint2 *__restrict__ cta_map, const BatchStep a)
+{
+    __shared__ __align__(16) unsigned long long window[sizeof(BatchSlot) / 8];
+    const uint2 where = __ldg(cta_map + blockIdx.x); // (chip, CTA of the chip)
+    const BatchSlot &b = load_slot(slots, where.x, window);
+    const StepVars sv = batch_vars(b, a);
+    fanout_body<V, false>(b.t, b.s, sv, b.tma_off, where.y);
+}
+
 // Stand-alone finalize (engines without message-phase work items): one WARP per active core.
-__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s)
+__global__ void __launch_bounds__(kFinalThreads) finalize_kernel(const DevTables t, const DevState s, const StepVars sv)
 {
     __shared__ __align__(16) unsigned char scratch[kFinalScratchBytes];
     griddep_launch_dependents();
     griddep_wait();
-    finalize_body(t, s, blockIdx.x, gridDim.x, scratch);
+    finalize_body(t, s, sv, blockIdx.x, gridDim.x, scratch);
 }
 
 // ---------------------------------------------------------------------------
@@ -2652,8 +2741,6 @@ __global__ void __launch_bounds__(256) pack_q4_kernel(const CoreDev *cores, cons
         }                                                                                           \
     } while (0)
 
-constexpr uint32_t kWorkPool = 8192; // >= 2 x the device log capacity (steps that can be enqueued before a collect)
-
 struct sfe_engine
 {
     uint2 *p2p_block{nullptr};           // [2][fired_words] (word, epoch + 1) pairs, exported over CUDA IPC
@@ -2667,6 +2754,7 @@ struct sfe_engine
     size_t device_bytes{0};
     DevTables t{};
     DevState s{};
+    StepVars sv{};
     CoreDev *d_cores{nullptr};
     uint32_t *d_neuron_class{nullptr};
     sfe_soma_class *d_classes{nullptr};
@@ -2746,6 +2834,10 @@ struct sfe_engine
         std::vector<double> state_init;
     };
     std::vector<PlugModel> plug;
+    BatchSlot *d_batch_slots{nullptr}; // device copy of the slots of the last batch this engine led
+    uint32_t batch_slots_cap{0};
+    uint2 *d_batch_map{nullptr};       // (chip, CTA of the chip) of every CTA of the batched neuron- and message-phase launch
+    size_t batch_map_cap{0};
     uint32_t n_plug{0};
     bool plug_failed{false}; // a model's launch function reported an error
     PlugGather *d_plug_gather{nullptr};
@@ -3294,7 +3386,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     if (e->alloc(&e->s.probe_out, static_cast<size_t>(tb->n_probes) + tb->n_u_probes) != 0) return -1;
     if (e->alloc(&e->s.step, 2) != 0) return -1;
     if (e->alloc(&e->d_work_pool, kWorkPool) != 0) return -1;
-    e->s.work = e->d_work_pool;
+    e->sv.work = e->d_work_pool;
     if (e->alloc(&e->s.final_ticket, 1) != 0) return -1;
     if (e->alloc(&e->s.core_done, tb->n_cores) != 0) return -1;
     if (e->alloc(&e->s.cores_finished, 1) != 0) return -1;
@@ -3454,6 +3546,9 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
             SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamScalar, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
             SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamTma, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
             SFE_CUDA(cudaFuncSetAttribute(fanout_kernel<kStreamQ4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel_batch<kStreamScalar>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel_batch<kStreamTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            SFE_CUDA(cudaFuncSetAttribute(fanout_kernel_batch<kStreamQ4>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
             raised[dev] = need;
         }
     }
@@ -3661,14 +3756,14 @@ extern "C" int sfe_engine_set_stream(sfe_engine *e, void *stream)
 // off): the launch latency and the table-only prologue of a kernel overlap the tail of the
 // kernel before it; griddepcontrol.wait inside the kernel keeps the data dependencies.
 template <typename... KArgs, typename... Args>
-static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, Args... args)
+static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), dim3 grid, unsigned block, size_t smem, Args... args)
 {
     static const bool pdl = [] {
         const char *v = std::getenv("SFE_PDL");
         return v == nullptr || std::atoi(v) != 0;
     }();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = e->stream;
@@ -3685,7 +3780,7 @@ static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned
 static void launch_device_models(sfe_engine *e)
 {
     if (e->plug.empty() || e->n_plug == 0) return;
-    plug_gather_kernel<<<(e->n_plug + 127) / 128, 128, 0, e->stream>>>(e->d_plug_gather, e->n_plug, e->s, e->d_plug_in, e->d_plug_has);
+    plug_gather_kernel<<<(e->n_plug + 127) / 128, 128, 0, e->stream>>>(e->d_plug_gather, e->n_plug, e->s, e->sv, e->d_plug_in, e->d_plug_has);
     ++e->launches;
     for (const sfe_engine::PlugModel &m : e->plug)
     {
@@ -3705,20 +3800,27 @@ static void launch_device_models(sfe_engine *e)
     }
 }
 
+template <typename... KArgs, typename... Args>
+static void launch_step_kernel(sfe_engine *e, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, Args... args)
+{
+    launch_step_kernel(e, kernel, dim3(grid), block, smem, args...);
+}
+
 static void launch_soma(sfe_engine *e)
 {
-    e->s.steps_done = e->total_timesteps;
+    e->sv.steps_done = e->total_timesteps;
     launch_device_models(e);
     unsigned grid = e->n_segments;
     if (e->pending_fold)
     {
         grid += e->final_grid; // extra CTAs fold the previous step
-        e->s.fold_parity = e->pending_parity;
-        e->s.fold_step = e->pending_step;
+        e->sv.fold_parity = e->pending_parity;
+        e->sv.fold_step = e->pending_step;
         e->pending_fold = false;
     }
-    if (e->exotic) launch_step_kernel(e, soma_kernel<true>, grid, kSomaThreads, 0, e->t, e->s);
-    else launch_step_kernel(e, soma_kernel<false>, grid, kSomaThreads, 0, e->t, e->s);
+    e->sv.soma_grid = grid;
+    if (e->exotic) launch_step_kernel(e, soma_kernel<true>, grid, kSomaThreads, 0, e->t, e->s, e->sv);
+    else launch_step_kernel(e, soma_kernel<false>, grid, kSomaThreads, 0, e->t, e->s, e->sv);
 }
 
 // "taps" lines of the step: after the neuron phase has written the raster, before the message
@@ -3726,8 +3828,8 @@ static void launch_soma(sfe_engine *e)
 static void launch_taps(sfe_engine *e)
 {
     if (e->n_taps_units == 0) return;
-    e->s.steps_done = e->total_timesteps;
-    taps_kernel<<<(e->n_taps_units + 127) / 128, 128, 0, e->stream>>>(e->t, e->s);
+    e->sv.steps_done = e->total_timesteps;
+    taps_kernel<<<(e->n_taps_units + 127) / 128, 128, 0, e->stream>>>(e->t, e->s, e->sv);
     ++e->launches;
 }
 
@@ -3735,9 +3837,9 @@ static void launch_taps(sfe_engine *e)
 static void flush_fold(sfe_engine *e)
 {
     if (!e->pending_fold) return;
-    e->s.fold_parity = e->pending_parity;
-    e->s.fold_step = e->pending_step;
-    launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
+    e->sv.fold_parity = e->pending_parity;
+    e->sv.fold_step = e->pending_step;
+    launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s, e->sv);
     ++e->launches;
     e->pending_fold = false;
 }
@@ -3747,7 +3849,7 @@ static void flush_fold(sfe_engine *e)
 static int prepare_tickets(sfe_engine *e, const int64_t count)
 {
     if (count <= 0 || e->d_work_pool == nullptr) return 0;
-    const uint32_t first = static_cast<uint32_t>(e->s.step_seq % kWorkPool);
+    const uint32_t first = static_cast<uint32_t>(e->sv.step_seq % kWorkPool);
     const uint32_t n = static_cast<uint32_t>(std::min<int64_t>(count, kWorkPool));
     const uint32_t head = std::min(n, kWorkPool - first);
     SFE_CUDA(cudaMemsetAsync(e->d_work_pool + first, 0, head * sizeof(uint32_t), e->stream));
@@ -3757,35 +3859,36 @@ static int prepare_tickets(sfe_engine *e, const int64_t count)
 
 static void launch_fanout(sfe_engine *e, const bool fused = false)
 {
-    e->s.steps_done = e->total_timesteps;
-    e->s.work = e->d_work_pool + (e->s.step_seq % kWorkPool);
+    e->sv.steps_done = e->total_timesteps;
+    e->sv.work = e->d_work_pool + (e->sv.step_seq % kWorkPool);
     const unsigned grid = e->fanout_grid;
+    e->sv.fanout_grid = grid;
     if (e->fanout_variant == kStreamQ4)
     {
-        if (fused) launch_step_kernel(e, fanout_kernel<kStreamQ4, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
-        else launch_step_kernel(e, fanout_kernel<kStreamQ4, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamQ4, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamQ4, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
     }
     else if (e->fanout_variant == kStreamTma)
     {
-        if (fused) launch_step_kernel(e, fanout_kernel<kStreamTma, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
-        else launch_step_kernel(e, fanout_kernel<kStreamTma, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamTma, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamTma, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
     }
     else
     {
-        if (fused) launch_step_kernel(e, fanout_kernel<kStreamScalar, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
-        else launch_step_kernel(e, fanout_kernel<kStreamScalar, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->tma_off);
+        if (fused) launch_step_kernel(e, fanout_kernel<kStreamScalar, true>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
+        else launch_step_kernel(e, fanout_kernel<kStreamScalar, false>, grid, kFanoutThreads, e->fanout_smem, e->t, e->s, e->sv, e->tma_off);
     }
 }
 
 // Raises the ready flag of the step whose neuron phase a stand-alone soma_kernel has just run (unpartitioned chip), or
 // pushes the rank's raster slice to every peer and raises the arrival flags there: what the fused step kernel does
 // itself for every later step of a batch.
-__global__ void __launch_bounds__(256) publish_kernel(const DevTables t, const DevState s)
+__global__ void __launch_bounds__(256) publish_kernel(const DevTables t, const DevState s, const StepVars sv)
 {
     (void) t;
     griddep_launch_dependents();
     griddep_wait();
-    if (threadIdx.x == 0) ready_publish(s.ready, s.step_seq);
+    if (threadIdx.x == 0) ready_publish(s.ready, sv.step_seq);
 }
 
 static int apply_pending_bias(sfe_engine *e);
@@ -3801,7 +3904,7 @@ static int enqueue_fused(sfe_engine *e, const int64_t timesteps)
     if (apply_pending_bias(e) != 0) return -1;
     launch_soma(e); // (the fold of an earlier two-kernel step rides along)
     ++e->launches;
-    launch_step_kernel(e, publish_kernel, 1u, 256u, 0, e->t, e->s);
+    launch_step_kernel(e, publish_kernel, 1u, 256u, 0, e->t, e->s, e->sv);
     ++e->launches;
     for (int64_t i = 0; i < timesteps; ++i)
     {
@@ -3816,8 +3919,8 @@ static int enqueue_fused(sfe_engine *e, const int64_t timesteps)
             }
             cudaEventRecord(e->ev_pool[e->ev_used], e->stream);
         }
-        e->s.fuse_next = i + 1 < timesteps ? 1u : 0u;
-        e->s.fold_step = e->total_timesteps;
+        e->sv.fuse_next = i + 1 < timesteps ? 1u : 0u;
+        e->sv.fold_step = e->total_timesteps;
         launch_fanout(e, true);
         ++e->launches;
         if (timed)
@@ -3825,10 +3928,10 @@ static int enqueue_fused(sfe_engine *e, const int64_t timesteps)
             cudaEventRecord(e->ev_pool[e->ev_used + 1], e->stream);
             e->ev_used += 2;
         }
-        ++e->s.step_seq;
+        ++e->sv.step_seq;
         ++e->total_timesteps;
     }
-    e->s.fuse_next = 0u;
+    e->sv.fuse_next = 0u;
     return 0;
 }
 
@@ -3838,17 +3941,17 @@ static void launch_finalize(sfe_engine *e)
     {
         // folded by extra CTAs of the next neuron-phase kernel (or by flush_fold)
         e->pending_fold = true;
-        e->pending_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
+        e->pending_parity = static_cast<uint32_t>(e->sv.step_seq & 1ull);
         e->pending_step = e->total_timesteps;
     }
     else
     {
-        e->s.fold_parity = static_cast<uint32_t>(e->s.step_seq & 1ull);
-        e->s.fold_step = e->total_timesteps;
-        launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s);
+        e->sv.fold_parity = static_cast<uint32_t>(e->sv.step_seq & 1ull);
+        e->sv.fold_step = e->total_timesteps;
+        launch_step_kernel(e, finalize_kernel, e->final_grid, kFinalThreads, 0, e->t, e->s, e->sv);
         ++e->launches;
     }
-    ++e->s.step_seq;
+    ++e->sv.step_seq;
 }
 
 static int apply_pending_bias(sfe_engine *e);
@@ -3930,6 +4033,105 @@ extern "C" int sfe_engine_enqueue(sfe_engine *e, int64_t timesteps)
             if (enqueue_step(e, false) != 0) return -1;
     }
     SFE_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// `timesteps` steps of n independent chips with ONE launch per phase and step (blockIdx.y = chip) instead of one per
+// chip: design-space sweeps of small chips are bound by the number of launches, not by the work in them. The chips
+// must be in lock step (same timestep counters) on one device, unpartitioned, with plain LIF / TrueNorth / ... somas of
+// one kernel instantiation, no 'taps', no out-of-tree models, no Poisson inputs, no pending bias upload.
+// Returns 0 = enqueued (collect every engine as usual), 1 = this set of chips cannot run as one batch (nothing was
+// enqueued: step them one by one), -1 = error.
+extern "C" int sfe_engine_batch_enqueue(sfe_engine *const *engines, uint32_t n, int64_t timesteps)
+{
+    if (n == 0 || timesteps <= 0) return 0;
+    if (engines == nullptr || engines[0] == nullptr) return 1;
+    sfe_engine *lead = engines[0];
+    for (uint32_t k = 0; k < n; ++k)
+    {
+        const sfe_engine *e = engines[k];
+        if (e == nullptr || e->device != lead->device || e->world != 1 || e->n_taps_units != 0 || !e->plug.empty() ||
+                e->exotic != lead->exotic || e->fanout_variant != lead->fanout_variant || e->fused_ok || !e->piggyback ||
+                e->total_timesteps != lead->total_timesteps || e->sv.step_seq != lead->sv.step_seq ||
+                e->pending_fold != lead->pending_fold || (e->pending_fold && (e->pending_parity != lead->pending_parity || e->pending_step != lead->pending_step)) ||
+                e->bias_pending >= 0 || e->n_poisson_cols != 0 || e->soma_list.empty() || e->fanout_list.empty() || e->timing ||
+                e->total_timesteps - e->log_read + timesteps > e->log_cap)
+            return 1;
+        for (uint32_t j = 0; j < k; ++j)
+            if (engines[j] == e) return 1;
+    }
+    SFE_CUDA(cudaSetDevice(lead->device));
+    if (lead->batch_slots_cap < n)
+    {
+        if (lead->alloc(&lead->d_batch_slots, n) != 0) return -1;
+        lead->batch_slots_cap = n;
+    }
+    std::vector<BatchSlot> slots(n);
+    std::vector<uint2> map; // neuron-phase CTAs of all chips (segments, then fold CTAs), then the message-phase CTAs
+    size_t max_smem = 0;
+    for (uint32_t k = 0; k < n; ++k)
+    {
+        sfe_engine *e = engines[k];
+        if (prepare_tickets(e, timesteps) != 0) return -1;
+        BatchSlot &b = slots[k];
+        std::memset(&b, 0, sizeof(b));
+        b.t = e->t;
+        b.s = e->s;
+        b.tma_off = e->tma_off;
+        b.n_segments = e->n_segments;
+        b.final_grid = e->final_grid;
+        b.fanout_grid = e->fanout_grid;
+        b.work_pool = e->d_work_pool;
+        max_smem = std::max(max_smem, e->fanout_smem);
+        for (uint32_t x = 0; x < e->n_segments + e->final_grid; ++x) map.push_back(make_uint2(k, x));
+    }
+    const unsigned soma_ctas = static_cast<unsigned>(map.size());
+    for (uint32_t k = 0; k < n; ++k)
+        for (uint32_t x = 0; x < engines[k]->fanout_grid; ++x) map.push_back(make_uint2(k, x));
+    const unsigned fan_ctas = static_cast<unsigned>(map.size()) - soma_ctas;
+    if (lead->batch_map_cap < map.size())
+    {
+        if (lead->alloc(&lead->d_batch_map, map.size()) != 0) return -1;
+        lead->batch_map_cap = map.size();
+    }
+    // everything the chips' own streams hold (loads, ticket memsets, earlier steps) before the batch touches their state
+    for (uint32_t k = 0; k < n; ++k) SFE_CUDA(cudaStreamSynchronize(engines[k]->stream));
+    SFE_CUDA(cudaMemcpy(lead->d_batch_slots, slots.data(), n * sizeof(BatchSlot), cudaMemcpyHostToDevice));
+    SFE_CUDA(cudaMemcpy(lead->d_batch_map, map.data(), map.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    const uint2 *soma_map = lead->d_batch_map, *fan_map = lead->d_batch_map + soma_ctas;
+    for (int64_t i = 0; i < timesteps; ++i)
+    {
+        BatchStep a{};
+        a.steps_done = lead->total_timesteps;
+        a.step_seq = lead->sv.step_seq;
+        a.fold = lead->pending_fold ? 1u : 0u;
+        a.fold_parity = lead->pending_parity;
+        a.fold_step = lead->pending_step;
+        // (without a step to fold - the first launch after a collect - the chips' fold CTAs leave at once)
+        if (lead->exotic) launch_step_kernel(lead, soma_kernel_batch<true>, soma_ctas, kSomaThreads, 0, lead->d_batch_slots, soma_map, a);
+        else launch_step_kernel(lead, soma_kernel_batch<false>, soma_ctas, kSomaThreads, 0, lead->d_batch_slots, soma_map, a);
+        if (lead->fanout_variant == kStreamQ4) launch_step_kernel(lead, fanout_kernel_batch<kStreamQ4>, fan_ctas, kFanoutThreads, max_smem, lead->d_batch_slots, fan_map, a);
+        else if (lead->fanout_variant == kStreamTma) launch_step_kernel(lead, fanout_kernel_batch<kStreamTma>, fan_ctas, kFanoutThreads, max_smem, lead->d_batch_slots, fan_map, a);
+        else launch_step_kernel(lead, fanout_kernel_batch<kStreamScalar>, fan_ctas, kFanoutThreads, max_smem, lead->d_batch_slots, fan_map, a);
+        lead->launches += 2;
+        for (uint32_t k = 0; k < n; ++k)
+        {
+            sfe_engine *e = engines[k];
+            // (launch_finalize: the fold of this step rides on the next neuron-phase launch, or on flush_fold)
+            e->pending_fold = true;
+            e->pending_parity = static_cast<uint32_t>(e->sv.step_seq & 1ull);
+            e->pending_step = e->total_timesteps;
+            ++e->sv.step_seq;
+            ++e->total_timesteps;
+        }
+    }
+    SFE_CUDA(cudaGetLastError());
+    // whatever the chips' own streams do next (the fold of the last step, collects) comes after the batch
+    cudaEvent_t done;
+    SFE_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    SFE_CUDA(cudaEventRecord(done, lead->stream));
+    for (uint32_t k = 1; k < n; ++k) SFE_CUDA(cudaStreamWaitEvent(engines[k]->stream, done, 0));
+    SFE_CUDA(cudaEventDestroy(done));
     return 0;
 }
 
@@ -4394,15 +4596,15 @@ extern "C" int sfe_engine_read_raster(sfe_engine *e, uint32_t *words, size_t n_w
         return -1;
     }
     const uint32_t *src = e->world > 1 ? e->d_fired_global : e->d_fired_local;
-    if (e->p2p_on && e->s.step_seq > 0)
+    if (e->p2p_on && e->sv.step_seq > 0)
     {
         // peer-memory exchange: the ranks store (word, epoch + 1) pairs straight into this rank's double-buffered raster.
         // Ranks are tied together only along their data dependencies, so a peer this rank needs nothing from may still
         // be working on the step: wait (bounded) until the words of every core carry the step's tag.
         std::vector<uint2> pairs(n_words);
         SFE_CUDA(cudaStreamSynchronize(e->stream));
-        const uint32_t want = static_cast<uint32_t>(e->s.step_seq - 1ull) + 1u;
-        const uint2 *from = e->p2p_block + ((e->s.step_seq - 1ull) & 1ull) * e->fired_words;
+        const uint32_t want = static_cast<uint32_t>(e->sv.step_seq - 1ull) + 1u;
+        const uint2 *from = e->p2p_block + ((e->sv.step_seq - 1ull) & 1ull) * e->fired_words;
         for (int attempt = 0;; ++attempt)
         {
             SFE_CUDA(cudaMemcpy(pairs.data(), from, n_words * sizeof(uint2), cudaMemcpyDeviceToHost));

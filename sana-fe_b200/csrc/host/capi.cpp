@@ -531,6 +531,77 @@ extern "C" int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timeste
                 sfe::set_last_error("sfe_batch_sim: the same chip appears twice");
                 return -1;
             }
+    // The whole batch as an outer grid dimension of the step kernels (one launch per phase and step for all chips,
+    // sfe_engine_batch_enqueue) when only totals are asked for and the chips are in lock step; SFE_BATCH_GRID=0 keeps
+    // one stream per chip.
+    {
+        const char *opt = std::getenv("SFE_BATCH_GRID");
+        bool grid = (opt == nullptr || std::atoi(opt) != 0) && n > 1 && timing_model == SFE_TIMING_SIMPLE && timesteps > 0;
+        for (uint32_t k = 0; k < n && grid; ++k)
+        {
+            const sfe_chip *c = chips[k];
+            grid = c != nullptr && c->loaded && c->engine != nullptr && c->poisson == nullptr && c->world == 1;
+            if (grid && reqs != nullptr)
+                grid = reqs[k].steps == nullptr && reqs[k].fired_bits == nullptr && reqs[k].potentials == nullptr &&
+                        reqs[k].status == nullptr && reqs[k].neuron_traces == nullptr;
+        }
+        if (grid)
+        {
+            const int rc = guarded(
+                    [&]() -> int {
+                        const auto wall0 = std::chrono::steady_clock::now();
+                        std::vector<sfe_engine *> engines(n);
+                        std::vector<sfe_run_data> total(n);
+                        for (uint32_t k = 0; k < n; ++k)
+                        {
+                            sfe_engine_request_stop(chips[k]->engine, 0);
+                            if (flush_bias(chips[k]) != 0) return -1;
+                            engines[k] = chips[k]->engine;
+                            std::memset(&total[k], 0, sizeof(sfe_run_data));
+                        }
+                        for (int64_t done = 0; done < timesteps;)
+                        {
+                            const int64_t chunk = std::min<int64_t>(2048, timesteps - done); // (the device log holds 4096 steps)
+                            const int enq = sfe_engine_batch_enqueue(engines.data(), n, chunk);
+                            if (enq < 0) return -1;
+                            if (enq > 0)
+                            {
+                                if (done == 0) return 1; // not a batch the grid form can run: nothing has been stepped
+                                throw std::runtime_error("sfe_batch_sim: the chips of the batch fell out of lock step");
+                            }
+                            for (uint32_t k = 0; k < n; ++k)
+                            {
+                                sfe_run_data part;
+                                if (sfe_engine_collect(engines[k], &part) != 0) return -1;
+                                if (done == 0) total[k].timestep_start = part.timestep_start;
+                                total[k].timesteps_executed += part.timesteps_executed;
+                                total[k].total_energy += part.total_energy;
+                                total[k].synapse_energy += part.synapse_energy;
+                                total[k].dendrite_energy += part.dendrite_energy;
+                                total[k].soma_energy += part.soma_energy;
+                                total[k].network_energy += part.network_energy;
+                                total[k].sim_time += part.sim_time;
+                                total[k].spikes += part.spikes;
+                                total[k].packets_sent += part.packets_sent;
+                                total[k].neurons_updated += part.neurons_updated;
+                                total[k].neurons_fired += part.neurons_fired;
+                            }
+                            done += chunk;
+                        }
+                        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+                        for (uint32_t k = 0; k < n; ++k)
+                        {
+                            total[k].wall_time = wall;
+                            chips[k]->total_energy += total[k].total_energy; // sim_update_total_energy_and_counts
+                            chips[k]->total_sim_time += total[k].sim_time;   // retire_timestep
+                            if (out != nullptr) out[k] = total[k];
+                        }
+                        return 0;
+                    },
+                    -1);
+            if (rc <= 0) return rc;
+        }
+    }
     return run_batch(n, host_threads, "sfe_batch_sim", [&](uint32_t k) {
         return sfe_chip_sim(chips[k], timesteps, timing_model, reqs != nullptr ? &reqs[k] : nullptr,
                 out != nullptr ? &out[k] : nullptr);

@@ -51,10 +51,14 @@ def test_poisson_engine_refuses_to_step_without_an_overlay():
     assert b"Poisson" in sfe.lib().sfe_last_error()
 
 
-def test_dse_batch_equals_lone_runs_and_the_restatement(tmp_path):
+@pytest.mark.parametrize("mode", ["grid", "streams"])
+def test_dse_batch_equals_lone_runs_and_the_restatement(tmp_path, monkeypatch, mode):
     """BASELINE config 5: chips stepped side by side by sfe_batch_sim give, bit for bit, what each gives when
-    run alone, and what the CPU restatement gives for the same design point."""
+    run alone, and what the CPU restatement gives for the same design point. grid: the batch is an outer grid
+    dimension of the step kernels (one launch per phase and step for all chips, sfe_engine_batch_enqueue);
+    streams: one stream per chip (SFE_BATCH_GRID=0)."""
     from sanafe_b200 import dse
+    monkeypatch.setenv("SFE_BATCH_GRID", "1" if mode == "grid" else "0")
     points = [(64, 1.0), (64, 2.0), (200, 1.0), (200, 0.5), (32, 1.5), (32, 1.0)]
     steps = 40
     batch = dse.Sweep(points, str(tmp_path / "batch"), device=0, host_threads=4)
