@@ -283,7 +283,10 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cores", type=int, default=FULL["cores"], help="scale the workload down (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-dse", action="store_true", help="skip the design-space-sweep side measurement (N=1 only)")
+    ap.add_argument("--no-dse", action="store_true", help="skip the design-space-sweep side measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the record-format variants and the small configurations (N=1 only)")
+    ap.add_argument("--quick", action="store_true",
+                    help="device-resident throughput and roofline only (what the record-format variants run in a child process)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -353,7 +356,7 @@ def main():
     # 4 B per synaptic event + 16 B per message (the layout bytes); `frac` is that over the kernel's CUDA-event time
     # and the measured peak. SURVEY 8(d)'s canonical figure (12 B per event: fp64 weight + post index) is kept as
     # `canonical`; with narrowed records it exceeds the peak and is not a fraction of anything real.
-    record_bytes = 4.0 if os.environ.get("SFE_SYN_Q4", "1") != "0" else 12.0
+    record_bytes = 4.0 if os.environ.get("SFE_SYN_Q4", "1") != "0" and os.environ.get("SFE_FORCE_ORDERED", "0") == "0" else 12.0
     layout_bytes = record_bytes * rd2.spikes + 16.0 * rd2.packets_sent  # over args.steps launches
     fan_bytes = 12.0 * rd2.spikes + 16.0 * rd2.packets_sent
     fan_s = ms_fan.value / 1e3
@@ -375,6 +378,12 @@ def main():
                 "whole_step": {"achieved": step_bytes / (ms_total.value / 1e3) / 1e9,
                                "frac": step_bytes / (ms_total.value / 1e3) / 1e9 / peak,
                                "bytes_per_step": step_bytes / max(args.steps, 1)}}
+
+    if args.quick:
+        print(json.dumps({"ms_per_step": 1e3 * seconds / args.steps, "value": value, "events_per_step": events / args.steps,
+                          "kernel_ms_per_launch": roofline["kernel_ms_per_launch"], "bytes_per_launch": roofline["algorithmic_bytes_per_launch"],
+                          "achieved": roofline["achieved"], "frac": roofline["frac"], "bytes_per_unit": roofline["bytes_per_unit"]}))
+        return 0
 
     # ---- raster checksum (before the end-to-end legs patch the biases) ---------------------------------
     def step_once():
@@ -452,6 +461,15 @@ def main():
     cpu = None if args.no_cpu_baseline else run_reference_sample(100, 1)
     parity = gpu_sample_parity(cpu, local_rank) if cpu else None
     dse = None if args.no_dse else dse_side_measurement()
+    if not args.no_extras and args.cores == FULL["cores"]:
+        # the same workload through the other two message-phase paths (child processes: the record format is chosen at load)
+        roofline["variants"] = {
+            "records_12B_tma": variant_measurement({"SFE_SYN_Q4": "0"}, "12-byte records (fp64 weight + meta word) through cp.async.bulk + mbarrier: "
+                                                                         "the path of cores with delays or without an exactness certificate"),
+            "ordered_fp64": variant_measurement({"SFE_FORCE_ORDERED": "1"}, "every core forced to the ordered mode (what non-dyadic weights select): one warp "
+                                                                             "per core replays the messages in arrival order with fp64 adds", steps=5),
+        }
+    small = None if args.no_extras else small_configs(local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -467,25 +485,141 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         # BASELINE configs[4] (design-space sweep batched on one GPU): a side measurement, not the headline metric
         "dse": dse,
+        # BASELINE configs[0..2] through the drop-in Python module, next to the reference's simulator on the same files
+        "small_configs": small,
     }
     print(json.dumps(line))
     return 0
 
 
+def variant_measurement(env, what, steps=20):
+    """bench.py --quick in a child process with `env` (the synapse record format is chosen when the chip is loaded)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--quick", "--steps", str(steps), "--warmup", "3"]
+    child_env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    child_env.update(env)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=child_env)
+        if res.returncode != 0:
+            return {"error": (res.stderr or res.stdout)[-300:]}
+        out = json.loads(res.stdout.strip().splitlines()[-1])
+        out.update({"what": what, "env": env, "steps": steps})
+        return out
+    except Exception as e:  # noqa: BLE001 - a side measurement must never fail the bench
+        return {"error": repr(e)[:300]}
+
+
+def small_configs(device):
+    """BASELINE configs[0..2] (example chip, DVS gesture with detailed timing, Hodgkin-Huxley plugin) as timesteps/s
+    through SpikingChip.sim() of the drop-in pybind11 module, next to the reference's own simulator (oracle/_ref) on the
+    same description files with all host threads. Descriptions: tests/golden/*.jsonl (made from the reference's files)."""
+    import gzip
+    try:
+        from sanafe_b200 import sanafecpp_b200 as m
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:200]}
+    threads = os.cpu_count() or 1
+    cases = [("config1_example", "example", 100, "simple"), ("config2_dvs", "dvs", 1000, "detailed"), ("config3_hh", "hh", 1000, "simple")]
+    out = {}
+    cwd = os.getcwd()
+    os.chdir(ROOT)  # plugin paths inside the flat files are relative to the repo root
+    try:
+        for key, name, steps, timing in cases:
+            try:
+                flat = os.path.join(ROOT, "tests", "golden", name + ".jsonl")
+                if not os.path.exists(flat):
+                    tmp = tempfile.NamedTemporaryFile(prefix=name + "_", suffix=".jsonl", delete=False)
+                    with gzip.open(flat + ".gz", "rb") as f:
+                        tmp.write(f.read())
+                    tmp.close()
+                    flat = tmp.name
+                arch, net = m.load_flat(flat)
+                chip = m.SpikingChip(arch)
+                chip.load(net)
+                chip.sim(steps, timing_model=timing)  # warm-up call (first launches, pinned buffers, scheduler pool)
+                best, sched = None, 0.0
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    res = chip.sim(steps, timing_model=timing)
+                    wall = time.perf_counter() - t0
+                    if best is None or wall < best:
+                        best = wall
+                entry = {"timesteps": steps, "timing_model": timing, "timesteps_per_s": steps / best, "us_per_timestep": 1e6 * best / steps,
+                         "call": "sanafecpp_b200.SpikingChip.sim(timesteps, timing_model) - best of 3 calls after a warm-up call",
+                         "synaptic_events": int(res["spikes"])}
+                if os.path.exists(REF_BIN):
+                    tmpd = tempfile.mkdtemp(prefix="sfe_small_")
+                    ref = subprocess.run([REF_BIN, flat, "--steps", str(steps), "--timing", timing, "--threads", str(threads),
+                                          "--out", tmpd, "--reps", "4"], capture_output=True, text=True, timeout=300)
+                    if ref.returncode == 0:
+                        with open(os.path.join(tmpd, "summary.json")) as f:
+                            summ = json.load(f)
+                        ref_wall = min(c[1] for c in summ["calls"][1:])
+                        entry["reference"] = {"timesteps_per_s": steps / ref_wall, "us_per_timestep": 1e6 * ref_wall / steps, "threads": threads,
+                                              "synaptic_events": int(summ["calls"][-1][0]),
+                                              "call": "oracle/_ref/sanafe_ref (the reference's SpikingChip.sim), best of 3 calls after a warm-up call"}
+                        entry["speedup_vs_reference"] = ref_wall / best
+                        entry["events_equal"] = int(summ["calls"][-1][0]) == int(res["spikes"])
+                out[key] = entry
+            except Exception as e:  # noqa: BLE001 - a side measurement must never fail the bench
+                out[key] = {"error": repr(e)[:300]}
+    finally:
+        os.chdir(cwd)
+    return out
+
+
 def dse_side_measurement():
-    """A 16-point slice of the config-5 sweep (tools/dse_sweep.py) in a child process, so that nothing it does can
-    cost the headline line; returns its JSON or the reason it is missing."""
+    """128 design points of the config-5 sweep (tools/dse_sweep.py: one after another, batched with one stream per chip,
+    and as one launch per phase for all chips) in a child process, so that nothing it does can cost the headline line; returns its JSON
+    or the reason it is missing."""
     import subprocess
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "dse_sweep.py"), "--mappings", "2", "--multipliers", "8",
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "dse_sweep.py"), "--mappings", "16", "--multipliers", "8",
            "--steps", "200", "--threads", "16"]
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
     try:
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
         if res.returncode != 0:
             return {"error": (res.stderr or res.stdout)[-300:]}
         return json.loads(res.stdout.strip().splitlines()[-1])
     except Exception as e:  # noqa: BLE001 - a side measurement must never fail the bench
         return {"error": repr(e)[:300]}
+
+
+def dse_partitioned(rank, world, local_rank, dist, steps=200):
+    """BASELINE configs[4] at N GPUs: 128 design points of the 32 x 32 sweep per GPU (all 1024 at N = 8), replicas only -
+    independent simulations, no exchange. Every rank times its own batch; rank 0 reports the slowest rank's wall time.
+    No collective inside: a rank that fails reports its error instead of leaving the others at a barrier."""
+    mine_out = None
+    try:
+        from sanafe_b200 import dse
+        every = dse.sweep_points()
+        sel = every[::max(1, 8 // world)][:128 * world]
+        mine = sel[rank::world]
+        t0 = time.time()
+        sweep = dse.Sweep(mine, tempfile.mkdtemp(prefix=f"dse_{rank}_"), device=local_rank, host_threads=16)
+        load_s = time.time() - t0
+        sweep.sim(10)  # warm-up
+        t0 = time.time()
+        rds = sweep.sim(steps)
+        wall = time.time() - t0
+        mine_out = {"points": len(mine), "wall_s": wall, "load_s": load_s, "events": sum(r.spikes for r in rds)}
+    except Exception as e:  # noqa: BLE001
+        mine_out = {"error": repr(e)[:300]}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine_out)
+    if rank != 0:
+        return None
+    bad = [g for g in gathered if g is None or "error" in g]
+    if bad:
+        return {"error": str(bad[0])}
+    points = sum(g["points"] for g in gathered)
+    wall = max(g["wall_s"] for g in gathered)
+    return {"workload": "config 5: design-space sweep of the conv SNN on TrueNorth-shaped chips"
+                        + (" (all 32 x 32 design points)" if points == 1024 else ""),
+            "design_points": points, "points_per_gpu": points // world, "n_gpus": world, "steps": steps,
+            "wall_s": round(wall, 4), "sims_per_s": round(points / wall, 1), "timesteps_per_s": round(points * steps / wall, 1),
+            "synaptic_events_per_s": round(sum(g["events"] for g in gathered) / wall, 1),
+            "load_s_max": round(max(g["load_s"] for g in gathered), 2),
+            "mode": "sfe_batch_sim: one stream per chip, 16 host threads per GPU; replicas only across GPUs"}
 
 
 def nccl_library_path():
@@ -588,6 +722,7 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     xerr = L.sfe_engine_exchange_error(eng)
     xmsg = L.sfe_last_error().decode() if xerr != 0 else ""
     dist.barrier()
+    dse = None if args.no_dse else dse_partitioned(rank, world, local_rank, dist)
     if exchange == "p2p":
         L.sfe_engine_p2p_detach(eng)
     else:
@@ -597,8 +732,9 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
     if rank != 0:
         dist.destroy_process_group()
         return 0
-    step_bytes = 12.0 * events_all + 16.0 * messages_all + 48.0 * n * args.steps
-    fan_bytes = 12.0 * events_all + 16.0 * messages_all
+    record_bytes = 4.0 if os.environ.get("SFE_SYN_Q4", "1") != "0" else 12.0  # lossless 4-byte records, as at N = 1
+    step_bytes = record_bytes * events_all + 16.0 * messages_all + 48.0 * n * args.steps
+    fan_bytes = record_bytes * events_all + 16.0 * messages_all
     line = {
         "metric": METRIC, "value": events_all / seconds, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
@@ -623,6 +759,8 @@ def partitioned_arm(args, sfe, chip, spec, rank, local_rank, world, peak, peak_s
         "e2e": {"value": events_all / seconds, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0, "note": "N>1 reports the device-timed value; the host-buffer e2e leg is the N=1 run"},
         "gpu_launches": launches_all, "clocks": clocks,
+        # BASELINE configs[4]: 128 independent design points per GPU (1024 at 8 GPUs), a side measurement
+        "dse": dse,
     }
     print(json.dumps(line))
     dist.destroy_process_group()

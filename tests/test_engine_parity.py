@@ -23,6 +23,17 @@ def test_engine_matches_reference(name):
     assert abs(chip.get_power() - g["summary"]["power"]) <= 1e-9 * abs(g["summary"]["power"])
 
 
+def test_forced_ordered_mode_matches_reference(monkeypatch):
+    """SFE_FORCE_ORDERED=1 (the measurement knob of bench.py): every core takes the ordered fp64 path of the message
+    phase, whatever its certificate allows; results are those of the reference all the same."""
+    monkeypatch.setenv("SFE_FORCE_ORDERED", "1")
+    for name in ("synth_small", "synth_delay"):
+        chip = load_chip(name, device=0)
+        g = golden(name)
+        rd, out = chip.sim_raw(g["steps"], "simple", steps=True, fired=True, potentials=True)
+        check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
+
+
 def test_sim_calls_continue_state():
     """sim() twice == sim() once (state and the timestep counter persist, src/chip.cpp:481,553)."""
     a = load_chip("synth_delay", device=0)

@@ -6,7 +6,7 @@ for spec in "$@"; do
   label="${spec%%:*}"; envs=""
   if [[ "$spec" == *:* ]]; then envs="${spec#*:}"; fi
   envs="${envs//,/ }"
-  env $envs python bench.py --steps ${AB_STEPS:-200} --warmup 20 --no-cpu-baseline --no-dse ${AB_ARGS} > gpurun_out/ab_${label}.json 2> gpurun_out/ab_${label}.err
+  env $envs python bench.py --steps ${AB_STEPS:-200} --warmup 20 --no-cpu-baseline --no-dse --no-extras ${AB_ARGS} > gpurun_out/ab_${label}.json 2> gpurun_out/ab_${label}.err
   python - "$label" <<'PY'
 import json, sys
 label = sys.argv[1]
