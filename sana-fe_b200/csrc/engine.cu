@@ -4235,6 +4235,7 @@ static void add_record(sfe_run_data &rd, const sfe_step_record &r)
     rd.neurons_fired += r.neurons_fired;
 }
 
+extern "C" int sfe_engine_exchange_error(sfe_engine *e);
 static int collect_records(sfe_engine *e, std::vector<sfe_step_record> &out)
 {
     const int64_t pending = e->total_timesteps - e->log_read;
@@ -4246,6 +4247,7 @@ static int collect_records(sfe_engine *e, std::vector<sfe_step_record> &out)
         sfe::set_last_error("an out-of-tree device model failed to launch its update kernel; results are invalid");
         return -1;
     }
+    if (e->p2p_on && sfe_engine_exchange_error(e) != 0) return -1; // (the message names the word / rank that did not arrive)
     int64_t done = 0;
     while (done < pending)
     {
@@ -4306,7 +4308,9 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
     int64_t done = 0;
     while (done < timesteps)
     {
-        if (e->stop_requested.load(std::memory_order_relaxed))
+        // (a chip with Poisson inputs is only interrupted before its first batch: the random spikes of the whole call
+        // have been drawn already, and stopping in the middle would leave the generators ahead of the timestep counter)
+        if (e->stop_requested.load(std::memory_order_relaxed) && (done == 0 || e->n_poisson_cols == 0))
         {
             // the steps simulated so far stay simulated (state and timestep counter), like an interrupted reference run
             sfe::set_last_error("simulation interrupted after " + std::to_string(done) + " of " + std::to_string(timesteps) + " timesteps");

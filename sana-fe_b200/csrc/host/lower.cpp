@@ -401,7 +401,14 @@ void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, con
         {
             unit.poisson = a.as_double();
         }
-        else if (key == "rate") unit.rate = a.as_double();
+        else if (key == "rate")
+        {
+            unit.rate = a.as_double();
+            // InputModel::update takes timestep % (long)(1 / rate) (src/models.cpp:887-890): a rate above 1 divides by zero
+            // (the reference's host build dies with SIGFPE); refuse it here instead of handing the device a zero divisor
+            if (unit.rate > 1.0)
+                throw std::invalid_argument("input rate " + std::to_string(unit.rate) + " > 1: the period (long)(1 / rate) would be 0");
+        }
     }
     else if (model == UnitModel::neurofem)
     {

@@ -1,3 +1,7 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-bash tools/ab_bench.sh s6def soma4:SFE_LIB_PATH=sana-fe_b200/variants/soma4/libsanafe_b200.so
-bash tools/ncu_capture.sh r2b > gpurun_out/ncu_capture.log 2>&1; tail -3 gpurun_out/ncu_capture.log
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 200 --warmup 20 > gpurun_out/final_n8.json 2> gpurun_out/final_n8.err
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/final_n8.json").read().strip().splitlines()[-1])
+print(d["n_gpus"], d["ms_per_step"], d["value"], d["raster_sha"][:12], d["raster_sha_equal_on_all_ranks"], d["dse"])
+PY
+grep -v "^W1\|OMP_NUM\|^\*\*\*" gpurun_out/final_n8.err | tail -5
