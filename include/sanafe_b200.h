@@ -549,6 +549,9 @@ void sfe_chip_request_stop(sfe_chip *c);
 /* an empty network for the object-by-object builders, and Network.save (src/network.cpp:693-712; YAML) */
 sfe_net *sfe_net_create(const char *name);
 int sfe_net_save_yaml(const sfe_net *net, const char *path);
+/* SpikingNetwork::save(path, use_netlist_format = true): the legacy netlist format, with the reference's losses (groups
+ * become "0", "1", ...; doubles print with 6 digits)  src/network.cpp:606-703, src/netlist.cpp:619-851 */
+int sfe_net_save_netlist(const sfe_net *net, const char *path);
 
 #ifdef __cplusplus
 }

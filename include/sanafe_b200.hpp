@@ -88,9 +88,9 @@ public:
     SpikingNetwork &operator=(const SpikingNetwork &) = delete;
     ~SpikingNetwork() { if (h_ != nullptr) sfe_net_free(h_); }
     sfe_net *handle() const { return h_; }
-    void save(const std::filesystem::path &path) const // src/network.cpp:688-718 (YAML)
+    void save(const std::filesystem::path &path, const bool use_netlist_format = false) const // src/network.cpp:705-718
     {
-        if (sfe_net_save_yaml(h_, path.c_str()) != 0) throw_last_error();
+        if ((use_netlist_format ? sfe_net_save_netlist(h_, path.c_str()) : sfe_net_save_yaml(h_, path.c_str())) != 0) throw_last_error();
     }
 private:
     sfe_net *h_;

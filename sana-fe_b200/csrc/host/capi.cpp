@@ -703,6 +703,18 @@ extern "C" int sfe_net_save_yaml(const sfe_net *net, const char *path)
             -1);
 }
 
+// SpikingNetwork::save(path, use_netlist_format = true)  src/network.cpp:606-703
+extern "C" int sfe_net_save_netlist(const sfe_net *net, const char *path)
+{
+    return guarded(
+            [&]() -> int {
+                if (net == nullptr || !net->net) throw std::invalid_argument("sfe_net_save_netlist: no described network");
+                sfe::save_net_netlist(*net->net, path);
+                return 0;
+            },
+            -1);
+}
+
 extern "C" int sfe_chip_set_neuron_attribute(sfe_chip *c, const char *group, uint64_t offset, const char *name,
         double value)
 {

@@ -24,5 +24,6 @@ namespace sfe
 {
 // Network.save(path)  src/network.cpp:693-712 (YAML format only)
 void save_net_yaml(const SpikingNetwork &net, const std::string &path);
+void save_net_netlist(const SpikingNetwork &net, const std::string &path); // legacy format (lossy, as the reference's)
 } // namespace sfe
 #endif

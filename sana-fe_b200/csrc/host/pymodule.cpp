@@ -857,7 +857,11 @@ PYBIND11_MODULE(sanafecpp_b200, m)
             .def(
                     "save",
                     [](const std::shared_ptr<NetHandle> &n, const std::string &path, bool use_netlist_format) {
-                        if (use_netlist_format) throw std::runtime_error("Network.save: only the YAML format is written by this build");
+                        if (use_netlist_format)
+                        {
+                            if (sfe_net_save_netlist(n->h, path.c_str()) != 0) raise_last();
+                            return;
+                        }
                         if (sfe_net_save_yaml(n->h, path.c_str()) != 0) raise_last();
                     },
                     py::arg("path"), py::arg("use_netlist_format") = false)

@@ -217,4 +217,110 @@ void save_net_yaml(const SpikingNetwork &net, const std::string &path)
     fp << out.str();
 }
 
+// ---------------------------------------------------------------------------
+// Legacy netlist format: SpikingNetwork::save(path, use_netlist_format = true)
+// (src/network.cpp:606-703; line builders src/netlist.cpp:619-851). Same lines as the reference writes, with the
+// reference's losses: groups are written by position (the loader names them "0", "1", ...), a group's log_potential is
+// written under a key the loader does not read (`log_v` is what it reads, src/netlist.cpp:437-441), numbers print
+// through ModelAttribute::print (src/attribute.hpp:129-155: doubles as `std::scientific`, 6 digits).
+// ---------------------------------------------------------------------------
+namespace
+{
+std::string netlist_print(const Attr &a) // ModelAttribute::print
+{
+    if (const bool *b = std::get_if<bool>(&a.value)) return *b ? "true" : "false";
+    if (const int *i = std::get_if<int>(&a.value)) return std::to_string(*i);
+    if (const double *d = std::get_if<double>(&a.value))
+    {
+        std::ostringstream ss;
+        ss << std::scientific << *d;
+        return ss.str();
+    }
+    if (const std::string *str = std::get_if<std::string>(&a.value)) return *str;
+    throw std::runtime_error("Printing vectors not yet supported");
+}
+
+// netlist_attributes_to_netlist  src/netlist.cpp:774-851: ` key=value` per attribute that differs from the group's
+// default; as soon as one attribute is a list, all of them go into one YAML flow mapping instead
+std::string netlist_attributes(const AttrMap &attrs, const AttrMap &defaults)
+{
+    bool nested = false;
+    for (const auto &[key, a] : attrs) nested = nested || a.is_list();
+    if (nested)
+    {
+        const std::vector<std::string> items = flow_items(attrs, &defaults);
+        return " " + flow_map(items);
+    }
+    std::string out;
+    for (const auto &[key, a] : attrs)
+    {
+        const auto d = defaults.find(key);
+        if (d != defaults.end() && same_attr(d->second, a)) continue;
+        out += " " + key + "=" + netlist_print(a);
+    }
+    return out;
+}
+} // namespace
+
+void save_net_netlist(const SpikingNetwork &net, const std::string &path)
+{
+    std::ofstream out(path);
+    if (!out.is_open()) throw std::invalid_argument("Error: Couldn't open net file to save to.");
+    // create_group_name_to_id_mapping: position in the (lexicographic) group map
+    std::map<std::string, size_t> group_id;
+    for (const auto &[name, g] : net.groups) group_id.emplace(name, group_id.size());
+    const AttrMap no_defaults;
+    // save_groups_to_netlist / netlist_group_to_netlist
+    for (const auto &[name, g] : net.groups)
+    {
+        const NeuronConfiguration &c = g->default_neuron_config;
+        std::string line = "g " + std::to_string(g->neurons.size());
+        if (c.default_synapse_hw_name.has_value() && !c.default_synapse_hw_name->empty()) line += " synapse_hw_name=" + *c.default_synapse_hw_name;
+        if (c.dendrite_hw_name.has_value() && !c.dendrite_hw_name->empty()) line += " dendrite_hw_name=" + *c.dendrite_hw_name;
+        if (c.log_potential.value_or(false)) line += " log_potential=1";
+        if (c.log_spikes.value_or(false)) line += " log_spikes=1";
+        if (c.soma_hw_name.has_value() && !c.soma_hw_name->empty()) line += " soma_hw_name=" + *c.soma_hw_name;
+        out << line << netlist_attributes(c.model_attributes, no_defaults) << "\n";
+    }
+    // save_neurons_to_netlist: every neuron followed by its outgoing connections
+    for (const auto &[name, g] : net.groups)
+    {
+        const NeuronConfiguration &c = g->default_neuron_config;
+        for (const Neuron &n : g->neurons)
+        {
+            std::string line = "n " + std::to_string(group_id.at(name)) + "." + std::to_string(n.offset);
+            // (is_unique_attribute: written when the group has no default or a different one)
+            auto unique_name = [&](const char *key, const std::string &value, const std::optional<std::string> &dflt) {
+                if (!value.empty() && (!dflt.has_value() || *dflt != value)) line += std::string(" ") + key + "=" + value;
+            };
+            unique_name("soma_hw_name", n.soma_hw_name, c.soma_hw_name);
+            unique_name("synapse_hw_name", n.default_synapse_hw_name, c.default_synapse_hw_name);
+            unique_name("dendrite_hw_name", n.dendrite_hw_name, c.dendrite_hw_name);
+            if (n.log_spikes && (!c.log_spikes.has_value() || !*c.log_spikes)) line += " log_spikes=1";
+            if (n.log_potential && (!c.log_potential.has_value() || !*c.log_potential)) line += " log_potential=1";
+            out << line << netlist_attributes(n.model_attributes, c.model_attributes) << "\n";
+            for (const Connection &con : n.edges_out)
+            {
+                auto end = [&](const NeuronAddress &a) {
+                    return std::to_string(group_id.at(a.group_name)) + (a.neuron_offset.has_value() ? "." + std::to_string(*a.neuron_offset) : "");
+                };
+                out << "e " << end(con.pre_neuron) << "->" << end(con.post_neuron)
+                    << netlist_attributes(con.synapse_attributes, no_defaults) << "\n";
+            }
+        }
+    }
+    // save_mappings_to_netlist: in mapping order
+    std::vector<const Neuron *> all;
+    for (const auto &[name, g] : net.groups)
+        for (const Neuron &n : g->neurons) all.push_back(&n);
+    std::stable_sort(all.begin(), all.end(), [](const Neuron *a, const Neuron *b) { return a->mapping_order < b->mapping_order; });
+    for (const Neuron *n : all)
+    {
+        if (n->core_address.has_value())
+            out << "& " << group_id.at(n->parent_group_name) << "." << n->offset << "@" << n->core_address->parent_tile_id << "."
+                << n->core_address->offset_within_tile;
+        out << "\n";
+    }
+}
+
 } // namespace sfe

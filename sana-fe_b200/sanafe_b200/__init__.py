@@ -219,7 +219,7 @@ def lib():
         "sfe_chip_set_neuron_log_spikes": (C.c_int, [vp, cstr, u64, C.c_int]),
         "sfe_chip_request_stop": (None, [vp]), "sfe_engine_request_stop": (None, [vp, C.c_int]),
         "sfe_last_error_kind": (C.c_int, []),
-        "sfe_net_create": (vp, [cstr]), "sfe_net_save_yaml": (C.c_int, [vp, cstr]),
+        "sfe_net_create": (vp, [cstr]), "sfe_net_save_yaml": (C.c_int, [vp, cstr]), "sfe_net_save_netlist": (C.c_int, [vp, cstr]),
         "sfe_batch_load": (C.c_int, [vp, vp, u32, u32]),
         "sfe_batch_sim": (C.c_int, [vp, u32, i64, C.c_int, vp, vp, u32]),
         # out-of-tree device models (include/sfe_device_model.h)
@@ -271,6 +271,11 @@ class Architecture:
 class Network:
     def __init__(self, handle):
         self._h = handle
+
+    def save(self, path, use_netlist_format=False):
+        """sanafe.Network.save (src/network.cpp:705-718): YAML, or the legacy netlist format (lossy, as the reference's)."""
+        fn = lib().sfe_net_save_netlist if use_netlist_format else lib().sfe_net_save_yaml
+        _check(fn(self._h, os.fsencode(path)))
 
     def __del__(self):
         if getattr(self, "_h", None):

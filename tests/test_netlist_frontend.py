@@ -76,3 +76,41 @@ def test_sim_command_line_accepts_netlists_flag():
     sim = os.path.join(ROOT, "sana-fe_b200", "sanafe_b200", "sim")
     res = subprocess.run([sim, "-n", ARCH, os.path.join(SRC, "missing.net"), "5"], cwd=ROOT, capture_output=True, text=True, timeout=60)
     assert res.returncode == 1 and "failed to open" in res.stderr
+
+
+def test_netlist_writer_round_trip(tmp_path):
+    """Network.save(path, use_netlist_format=True) (src/network.cpp:606-703, src/netlist.cpp:619-851): the lines the
+    reference writes - groups by position, `n` lines with the attributes that differ from the group's, `e` lines after
+    their neuron, `&` lines in mapping order, doubles through `std::scientific` - and a file that reads back to the same
+    tables (this example's values survive the format's 6 digits)."""
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        arch = sfe.load_arch(ARCH)
+        net = sfe.load_net(os.path.join(SRC, "example_equiv.yaml"), arch)
+        path = tmp_path / "saved.net"
+        net.save(str(path), use_netlist_format=True)
+        text = path.read_text().splitlines()
+        assert text[0].startswith("g 3") and "threshold=1.000000e+00" in text[0] and "log_spikes=1" in text[0]
+        assert text[2].startswith("n 0.0") and "bias=1.000000e+00" in text[2]
+        assert any(line.startswith("e 0.2->1.1") and "weight=5.000000e-01" in line for line in text)
+        assert [line for line in text if line.startswith("&")][:2] == ["& 0.0@0.0", "& 0.1@0.0"]
+        back = sfe.load_net(str(path), arch, use_netlist_format=True)
+        a, b = sfe.SpikingChip(arch, device=-1), sfe.SpikingChip(arch, device=-1)
+        a.load(net)
+        b.load(back)
+    finally:
+        os.chdir(cwd)
+    ta, tb = a.tables, b.tables
+    for field in ("n_neurons", "n_synapses", "n_axons_in", "n_axons_out", "mapped_cores"):
+        assert getattr(ta, field) == getattr(tb, field), field
+    n, m = ta.n_neurons, ta.n_synapses
+    for name, count in (("neuron_bias", n), ("axon_out_begin", n + 1), ("syn_weight", m), ("syn_meta", m)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(ta, name), shape=(count,)),
+                              np.ctypeslib.as_array(getattr(tb, name), shape=(count,))), name
+    rd_a, out_a = Oracle(a).run(50)
+    rd_b, out_b = Oracle(b).run(50)
+    assert rd_a.neurons_fired == rd_b.neurons_fired > 0 and rd_a.spikes == rd_b.spikes > 0
+    assert np.array_equal(out_a["fired_bits"], out_b["fired_bits"])
+    # the format's documented loss: a group's log_potential is written under a key its loader does not read
+    assert a.probe_names() and b.probe_names() == []
