@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 6
+#define SFE_ABI_VERSION 7
 
 /* ---- enums (values follow the reference where it has them) -------------- */
 /* src/arch.hpp:41-49 BufferPosition */
@@ -138,7 +138,10 @@ typedef struct sfe_soma_class
     uint32_t reverse_reset_mode;
     int32_t refractory_delay;
     uint32_t flags;         /* SFE_SOMA_* flags */
-    uint32_t random_mask;   /* truenorth only; must be 0 (std::rand() is not reproducible) */
+    uint32_t random_mask;   /* truenorth only: threshold jitter `rand() & random_mask` (src/models.cpp:749-759). Non-zero: the
+                             * neuron's neuron_aux is its column in the per-step overlay of glibc rand() values
+                             * (sfe_engine_set_rand_overlay; sfe_chip_sim draws them, one per such neuron and timestep in chip
+                             * order - what the reference's process-global std::rand() yields with one processing thread) */
     uint32_t dend_model;    /* SFE_DEND_* of the neuron's dendrite unit */
     uint32_t dend_in_neuron;/* 1: dendrite unit is in the neuron pipeline (buffer_pos <= 1) */
     double threshold, reverse_threshold, reset, reverse_reset;
@@ -292,6 +295,9 @@ typedef struct sfe_tables
     /* out-of-tree soma device models used by this chip */
     const sfe_device_model_block *device_models;
     uint32_t n_device_models, n_device_instances;
+
+    /* TrueNorth neurons with random_mask != 0 (= columns of the rand() overlay) */
+    uint32_t n_rand_cols, pad_rand;
 } sfe_tables;
 
 /* one record per simulated timestep (src/timestep.hpp:21-42) */
@@ -367,6 +373,9 @@ int sfe_engine_set_bias_staged(sfe_engine *e, const double *bias, size_t n);
  * the device as an overlay: bits[step][col] != 0 makes the input neuron with that poisson_col spike in that
  * step. Covers the next `n_steps` steps to be enqueued; sfe_chip_sim does this itself. */
 int sfe_engine_set_input_overlay(sfe_engine *e, const uint8_t *bits, int64_t n_steps, uint32_t n_cols);
+/* rand() values of the TrueNorth neurons with random_mask != 0 for the next n_steps timesteps: values[n_steps][n_cols],
+ * n_cols = sfe_tables.n_rand_cols. An engine with such neurons refuses to step past its overlay. */
+int sfe_engine_set_rand_overlay(sfe_engine *e, const uint32_t *values, int64_t n_steps, uint32_t n_cols);
 /* Cooperative cancellation, callable from another thread: a running sfe_engine_run / sfe_chip_sim returns -1
  * ("simulation interrupted") at its next batch boundary (at most 4096 steps); the steps done so far stay done.
  * The reference polls PyErr_CheckSignals every 100 ms inside its loop (src/pymodule.cpp:629-652). on = 0 re-arms. */
@@ -383,6 +392,9 @@ sfe_poisson *sfe_poisson_create(const sfe_tables *tables);
 void sfe_poisson_destroy(sfe_poisson *p);
 uint32_t sfe_poisson_cols(const sfe_poisson *p);
 int sfe_poisson_fill(sfe_poisson *p, uint8_t *bits, int64_t n_steps);
+/* glibc's rand() (TYPE_3 additive feedback generator) restated: out[k] = the (skip + k)-th value after srand(seed).
+ * The reference's TrueNorth threshold jitter draws from the process-global std::rand() (src/models.cpp:757). */
+void sfe_glibc_rand_draws(uint32_t seed, uint64_t skip, uint32_t *out, size_t n);
 /* cross-check hooks: n draws of U(0,1) from seed through libstdc++'s std::mt19937 + uniform_real_distribution, and
  * through the engine's own host/device MT19937 (csrc/mt19937.cuh, state interleaved with `stride`) */
 void sfe_poisson_reference_draws(uint32_t seed, double *out, size_t n);

@@ -68,10 +68,16 @@ typedef struct sfe_oracle
     double *tap_v, *tap_next;
     uint32_t *tap_off;           /* [n_taps_units] offset of the unit's line in tap_v */
     int64_t *tap_steps;          /* [n_taps_units] timesteps_simulated */
+    /* TrueNorth threshold jitter: the process-global rand() of the reference, restated (below) and drawn as the
+     * neurons are updated - one processing thread, cores and neurons in order */
+    uint32_t rand_state[31];
+    int rand_front, rand_rear;
     const uint8_t *overlay;      /* caller-owned [overlay_steps][overlay_cols], NULL: draw here */
     int64_t overlay_step0, overlay_steps;
     uint32_t overlay_cols;
 } sfe_oracle;
+
+static void oracle_srand(sfe_oracle *o, uint32_t seed);
 
 /* MT19937 (Matsumoto & Nishimura 1998) as std::mt19937 specifies it, and the 53-bit canonical
  * double libstdc++'s std::uniform_real_distribution<double>{0,1} builds from two 32-bit outputs
@@ -183,6 +189,7 @@ sfe_oracle *sfe_oracle_create(const sfe_tables *t)
     for (uint32_t k = 0; k < t->n_inputs; ++k)
         if (t->inputs[k].poisson > 0.0 && t->inputs[k].unit + 1 > o->n_poisson_units) o->n_poisson_units = t->inputs[k].unit + 1;
     o->poisson_gen = (struct mt19937 *) zalloc(o->n_poisson_units, sizeof(struct mt19937));
+    oracle_srand(o, 1u); /* a fresh reference process: srand() is never called */
     for (size_t i = 0; i < t->n_hh; ++i)
     {
         o->hh_m[i] = t->hh[i].m;
@@ -295,7 +302,33 @@ static int lif_update(sfe_oracle *o, const sfe_soma_class *c, size_t i, int has_
     return state;
 }
 
-/* TrueNorthModel::update  src/models.cpp:724-830 (random_mask == 0) */
+/* rand() of glibc (stdlib/random_r.c, TYPE_3): 31 words seeded by a Park-Miller LCG from srand's argument (1 when the
+ * program never calls srand), word[f] += word[r] with f three ahead of r, result = word >> 1, 310 values discarded */
+static uint32_t oracle_rand(sfe_oracle *o)
+{
+    uint32_t *s = o->rand_state;
+    s[o->rand_front] += s[o->rand_rear];
+    const uint32_t result = s[o->rand_front] >> 1;
+    if (++o->rand_front == 31) o->rand_front = 0;
+    if (++o->rand_rear == 31) o->rand_rear = 0;
+    return result;
+}
+static void oracle_srand(sfe_oracle *o, uint32_t seed)
+{
+    int64_t word = seed == 0 ? 1 : (int32_t) seed;
+    o->rand_state[0] = (uint32_t) word;
+    for (int i = 1; i < 31; ++i)
+    {
+        word = (16807 * word) % 2147483647;
+        if (word < 0) word += 2147483647;
+        o->rand_state[i] = (uint32_t) word;
+    }
+    o->rand_front = 3;
+    o->rand_rear = 0;
+    for (int i = 0; i < 310; ++i) (void) oracle_rand(o);
+}
+
+/* TrueNorthModel::update  src/models.cpp:724-830 */
 static int truenorth_update(sfe_oracle *o, const sfe_soma_class *c, size_t i, int has_in, double in)
 {
     double v = o->v[i];
@@ -310,14 +343,17 @@ static int truenorth_update(sfe_oracle *o, const sfe_soma_class *c, size_t i, in
     else v += c->leak;
     v += bias;
     if (has_in) v += in;
-    if (v >= c->threshold)
+    /* truenorth_threshold_and_reset  src/models.cpp:745-759: the jitter shifts the compared value only */
+    double compared = v;
+    if (c->random_mask != 0) compared += (double) (oracle_rand(o) & c->random_mask);
+    if (compared >= c->threshold)
     {
         if (c->reset_mode == SFE_RESET_HARD) v = c->reset;
         else if (c->reset_mode == SFE_RESET_SOFT) v -= c->threshold;
         else if (c->reset_mode == SFE_RESET_SATURATE) v = c->threshold;
         state = SFE_STATUS_FIRED;
     }
-    else if (v <= c->reverse_threshold)
+    else if (compared <= c->reverse_threshold)
     {
         if (c->reverse_reset_mode == SFE_RESET_HARD) v = c->reverse_reset;
         else if (c->reverse_reset_mode == SFE_RESET_SOFT) v += c->reverse_threshold;

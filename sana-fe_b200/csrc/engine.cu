@@ -182,6 +182,10 @@ struct DevTables
     const uint8_t *overlay;
     long long overlay_step0, overlay_steps;
     uint32_t overlay_cols, pad_overlay;
+    // TrueNorth threshold jitter: rand() values [step - rand_step0][jittered neuron] (sfe_engine_set_rand_overlay)
+    const uint32_t *rand_overlay;
+    long long rand_step0, rand_steps;
+    uint32_t rand_cols, pad_rand;
     const sfe_axon_in *axons_in;
     const double *syn_w;
     const uint32_t *syn_meta;
@@ -449,9 +453,10 @@ __device__ __forceinline__ int lif_update(const sfe_soma_class &c, double &v, do
     return state;
 }
 
-// TrueNorthModel::update  src/models.cpp:724-830 (random_mask == 0 enforced at load)
+// TrueNorthModel::update  src/models.cpp:724-830. rnd = this update's `rand() & random_mask` (0 without jitter): it
+// shifts the value the thresholds are compared with, not the potential (truenorth_threshold_and_reset, :745-759)
 __device__ __forceinline__ int truenorth_update(
-        const sfe_soma_class &c, double &v, const double bias, const bool has_in, const double in)
+        const sfe_soma_class &c, double &v, const double bias, const bool has_in, const double in, const uint32_t rnd = 0u)
 {
     int state = SFE_STATUS_IDLE;
     if ((fabs(v) > 0.0) || has_in || (fabs(bias) > 0.0) || (c.flags & SFE_SOMA_FORCE_UPDATE)) state = SFE_STATUS_UPDATED;
@@ -463,14 +468,15 @@ __device__ __forceinline__ int truenorth_update(
     else v = v + c.leak;
     v = v + bias;
     if (has_in) v = v + in;
-    if (v >= c.threshold)
+    const double compared = rnd != 0u ? v + static_cast<double>(rnd) : v;
+    if (compared >= c.threshold)
     {
         if (c.reset_mode == SFE_RESET_HARD) v = c.reset;
         else if (c.reset_mode == SFE_RESET_SOFT) v = v - c.threshold;
         else if (c.reset_mode == SFE_RESET_SATURATE) v = c.threshold;
         state = SFE_STATUS_FIRED;
     }
-    else if (v <= c.reverse_threshold)
+    else if (compared <= c.reverse_threshold)
     {
         if (c.reverse_reset_mode == SFE_RESET_HARD) v = c.reverse_reset;
         else if (c.reverse_reset_mode == SFE_RESET_SOFT) v = v + c.reverse_threshold;
@@ -1016,7 +1022,16 @@ __device__ __forceinline__ void soma_segment(const DevTables &t, const DevState 
             else if (c.model == SFE_SOMA_TRUENORTH)
             {
                 double v = v0;
-                st = truenorth_update(c, v, bias, has_in, in);
+                uint32_t rnd = 0u;
+                if constexpr (kExotic)
+                    if (c.random_mask != 0u)
+                    {
+                        // (check_overlay made sure the overlay covers this step)
+                        const long long row = steps_done - t.rand_step0;
+                        if (row >= 0 && row < t.rand_steps)
+                            rnd = __ldg(t.rand_overlay + static_cast<size_t>(row) * t.rand_cols + t.neuron_aux[i]) & c.random_mask;
+                    }
+                st = truenorth_update(c, v, bias, has_in, in, rnd);
                 s.v[i] = v;
             }
             else if constexpr (kExotic)
@@ -2852,6 +2867,10 @@ struct sfe_engine
     uint32_t n_poisson_cols{0};
     uint8_t *d_overlay{nullptr};
     size_t overlay_cap{0};
+    // TrueNorth threshold jitter overlay
+    uint32_t n_rand_cols{0};
+    uint32_t *d_rand_overlay{nullptr};
+    size_t rand_overlay_cap{0};
 
     template <typename T> int alloc(T **p, size_t count)
     {
@@ -2931,7 +2950,8 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
     e->core_desc.assign(tb->cores, tb->cores + tb->n_cores);
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
         if (tb->soma_classes[k].model == SFE_SOMA_INPUT || tb->soma_classes[k].model == SFE_SOMA_HH ||
-                tb->soma_classes[k].model == SFE_SOMA_NEUROFEM || tb->soma_classes[k].model == SFE_SOMA_DEVICE_MODEL || (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
+                tb->soma_classes[k].model == SFE_SOMA_NEUROFEM || tb->soma_classes[k].model == SFE_SOMA_DEVICE_MODEL ||
+                (tb->soma_classes[k].model == SFE_SOMA_TRUENORTH && tb->soma_classes[k].random_mask != 0u) || (tb->soma_classes[k].flags & SFE_SOMA_NOISE) != 0u)
             e->exotic = true;
     for (uint32_t k = 0; k < tb->n_soma_classes; ++k)
         if (tb->soma_classes[k].model == SFE_SOMA_NEUROFEM) e->neurofem = true;
@@ -3126,6 +3146,7 @@ static int engine_build(sfe_engine *e, const sfe_tables *tb)
         e->exotic = true; // the neuron phase reads the lines' outputs in its `exotic` instantiation
     }
     e->n_poisson_cols = tb->n_poisson_cols;
+    e->n_rand_cols = tb->n_rand_cols;
     for (uint32_t k = 0; k < tb->n_inputs; ++k)
         if (tb->inputs[k].poisson > 0.0 && tb->inputs[k].poisson_col >= tb->n_poisson_cols)
         {
@@ -3746,6 +3767,7 @@ extern "C" void sfe_engine_destroy(sfe_engine *e)
     }
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_overlay != nullptr) cudaFree(e->d_overlay);
+    if (e->d_rand_overlay != nullptr) cudaFree(e->d_rand_overlay);
     if (e->pinned != nullptr) cudaFreeHost(e->pinned);
     if (e->pinned_fired != nullptr) cudaFreeHost(e->pinned_fired);
     if (e->d_fired_ring != nullptr) cudaFree(e->d_fired_ring);
@@ -3974,6 +3996,12 @@ static int apply_pending_bias(sfe_engine *e);
 // would silently drop the random spikes.
 static int check_overlay(const sfe_engine *e)
 {
+    if (e->n_rand_cols != 0 && !(e->total_timesteps >= e->t.rand_step0 && e->total_timesteps < e->t.rand_step0 + e->t.rand_steps))
+    {
+        sfe::set_last_error("this chip has TrueNorth neurons with a random threshold mask: call sfe_engine_set_rand_overlay for the "
+                            "steps to be simulated first; sfe_chip_sim does it itself");
+        return -1;
+    }
     if (e->n_poisson_cols == 0) return 0;
     if (e->total_timesteps >= e->t.overlay_step0 && e->total_timesteps < e->t.overlay_step0 + e->t.overlay_steps) return 0;
     sfe::set_last_error("this chip has Poisson inputs: call sfe_engine_set_input_overlay (see sfe_poisson_fill) for the "
@@ -4068,7 +4096,7 @@ extern "C" int sfe_engine_batch_enqueue(sfe_engine *const *engines, uint32_t n, 
                 e->exotic != lead->exotic || e->fanout_variant != lead->fanout_variant || e->fused_ok || !e->piggyback ||
                 e->total_timesteps != lead->total_timesteps || e->sv.step_seq != lead->sv.step_seq ||
                 e->pending_fold != lead->pending_fold || (e->pending_fold && (e->pending_parity != lead->pending_parity || e->pending_step != lead->pending_step)) ||
-                e->bias_pending >= 0 || e->n_poisson_cols != 0 || e->soma_list.empty() || e->fanout_list.empty() || e->timing ||
+                e->bias_pending >= 0 || e->n_poisson_cols != 0 || e->n_rand_cols != 0 || e->soma_list.empty() || e->fanout_list.empty() || e->timing ||
                 e->total_timesteps - e->log_read + timesteps > e->log_cap)
             return 1;
         for (uint32_t j = 0; j < k; ++j)
@@ -4183,6 +4211,34 @@ extern "C" int sfe_engine_fill_input_overlay(sfe_engine *e, int64_t n_steps)
     e->t.overlay_cols = e->n_poisson_cols;
     e->t.overlay_step0 = e->total_timesteps;
     e->t.overlay_steps = n_steps;
+    return 0;
+}
+
+extern "C" int sfe_engine_set_rand_overlay(sfe_engine *e, const uint32_t *values, int64_t n_steps, uint32_t n_cols)
+{
+    SFE_CUDA(cudaSetDevice(e->device));
+    if (n_cols != e->n_rand_cols || n_steps < 0 || (values == nullptr && n_steps > 0 && n_cols > 0))
+    {
+        sfe::set_last_error("sfe_engine_set_rand_overlay: need values[n_steps][" + std::to_string(e->n_rand_cols) + "]");
+        return -1;
+    }
+    SFE_CUDA(cudaStreamSynchronize(e->stream)); // steps already enqueued may still be reading the previous overlay
+    const size_t count = static_cast<size_t>(n_steps) * n_cols;
+    if (count > e->rand_overlay_cap)
+    {
+        if (e->d_rand_overlay != nullptr) cudaFree(e->d_rand_overlay);
+        e->d_rand_overlay = nullptr;
+        e->rand_overlay_cap = 0;
+        void *q = nullptr;
+        SFE_CUDA(cudaMalloc(&q, count * sizeof(uint32_t)));
+        e->d_rand_overlay = static_cast<uint32_t *>(q);
+        e->rand_overlay_cap = count;
+    }
+    if (count > 0) SFE_CUDA(cudaMemcpy(e->d_rand_overlay, values, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->t.rand_overlay = e->d_rand_overlay;
+    e->t.rand_cols = n_cols;
+    e->t.rand_step0 = e->total_timesteps;
+    e->t.rand_steps = n_steps;
     return 0;
 }
 
@@ -4310,7 +4366,7 @@ extern "C" int sfe_engine_run(sfe_engine *e, int64_t timesteps, const sfe_trace_
     {
         // (a chip with Poisson inputs is only interrupted before its first batch: the random spikes of the whole call
         // have been drawn already, and stopping in the middle would leave the generators ahead of the timestep counter)
-        if (e->stop_requested.load(std::memory_order_relaxed) && (done == 0 || e->n_poisson_cols == 0))
+        if (e->stop_requested.load(std::memory_order_relaxed) && (done == 0 || (e->n_poisson_cols == 0 && e->n_rand_cols == 0)))
         {
             // the steps simulated so far stay simulated (state and timestep counter), like an interrupted reference run
             sfe::set_last_error("simulation interrupted after " + std::to_string(done) + " of " + std::to_string(timesteps) + " timesteps");

@@ -19,6 +19,7 @@
 
 #include "../engine.hpp"
 #include "desc.hpp"
+#include "glibc_rand.hpp"
 #include "handles.hpp"
 #include "lower.hpp"
 #include "schedule.hpp"
@@ -60,6 +61,9 @@ struct sfe_chip
     // process-wide static, src/models.hpp:366) and the host generators of this chip's Poisson units
     uint32_t input_seed_base{0};
     sfe_poisson *poisson{nullptr};
+    // TrueNorth threshold jitter: the chip's stream of rand() values (the reference draws from the process-global
+    // generator, seed 1 unless somebody called srand(): one value per jittered neuron and timestep, in chip order)
+    sfe::GlibcRand jitter{1u};
     // per-neuron bias patches (MappedNeuron.set_attributes in a per-frame loop, scripts/tcad2025/dvs_gesture.py) are
     // collected in the host table and uploaded as ONE vector before the next step instead of one copy per neuron
     bool bias_dirty{false};
@@ -177,6 +181,7 @@ int attach_engine(sfe_chip *c)
     // (a second load() restarts the Poisson streams; the reference's generators would run on)
     sfe_poisson_destroy(c->poisson);
     c->poisson = nullptr;
+    c->jitter = sfe::GlibcRand(1u); // (a second load() restarts the jitter stream, like the Poisson streams)
     c->tables.input_seed_base = c->input_seed_base;
     c->tables.view.input_seed_base = c->input_seed_base;
     if (c->tables.view.n_poisson_cols > 0)
@@ -358,7 +363,8 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                                              "available): out of scope");
                 sfe_run_data rd;
                 const bool detailed = timing_model != SFE_TIMING_SIMPLE;
-                if (!detailed && c->poisson == nullptr)
+                const uint32_t rand_cols = c->tables.view.n_rand_cols;
+                if (!detailed && c->poisson == nullptr && rand_cols == 0)
                 {
                     if (sfe_engine_run(c->engine, timesteps, req, &rd) != 0) return -1;
                 }
@@ -377,8 +383,10 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                     int64_t batch_cap = 4096;
                     if (detailed) batch_cap = std::min<int64_t>(batch_cap, (64ll << 20) / static_cast<int64_t>(std::max<size_t>(n, 1)));
                     if (cols > 0) batch_cap = std::min<int64_t>(batch_cap, (32ll << 20) / static_cast<int64_t>(cols));
+                    if (rand_cols > 0) batch_cap = std::min<int64_t>(batch_cap, (8ll << 20) / static_cast<int64_t>(rand_cols));
                     batch_cap = std::max<int64_t>(1, batch_cap);
                     std::vector<uint8_t> status, overlay;
+                    std::vector<uint32_t> jitter;
                     std::vector<double> sched_time;
                     std::vector<sfe_step_record> recs;
                     std::memset(&rd, 0, sizeof(rd));
@@ -415,6 +423,14 @@ extern "C" int sfe_chip_sim(sfe_chip *c, int64_t timesteps, int timing_model, co
                             overlay.resize(static_cast<size_t>(batch) * cols);
                             if (sfe_poisson_fill(c->poisson, overlay.data(), batch) != 0) return -1;
                             if (sfe_engine_set_input_overlay(c->engine, overlay.data(), batch, cols) != 0) return -1;
+                        }
+                        if (rand_cols > 0)
+                        {
+                            // TrueNorthModel::truenorth_threshold_and_reset  src/models.cpp:749-759: one rand() per
+                            // jittered neuron and timestep, in the order a single processing thread updates them
+                            jitter.resize(static_cast<size_t>(batch) * rand_cols);
+                            for (uint32_t &x : jitter) x = c->jitter.next();
+                            if (sfe_engine_set_rand_overlay(c->engine, jitter.data(), batch, rand_cols) != 0) return -1;
                         }
                         sfe_run_data part;
                         if (sfe_engine_run(c->engine, batch, &sub, &part) != 0) return -1;
@@ -542,7 +558,8 @@ extern "C" int sfe_batch_sim(sfe_chip *const *chips, uint32_t n, int64_t timeste
         for (uint32_t k = 0; k < n && grid; ++k)
         {
             const sfe_chip *c = chips[k];
-            grid = c != nullptr && c->loaded && c->engine != nullptr && c->poisson == nullptr && c->world == 1;
+            grid = c != nullptr && c->loaded && c->engine != nullptr && c->poisson == nullptr && c->world == 1 &&
+                    c->tables.view.n_rand_cols == 0;
             if (grid && reqs != nullptr)
                 grid = reqs[k].steps == nullptr && reqs[k].fired_bits == nullptr && reqs[k].potentials == nullptr &&
                         reqs[k].status == nullptr && reqs[k].neuron_traces == nullptr;

@@ -384,10 +384,9 @@ void set_soma_attribute(LNeuron &ln, UnitState &unit, const UnitModel model, con
         {
             const int mask = a.as_int();
             if (mask < 0) throw std::invalid_argument("random_mask < 0; must be unsigned.");
-            if (mask != 0)
-                throw std::runtime_error("truenorth random_mask != 0 draws from the process-global std::rand() "
-                                         "(src/models.cpp:757), which no parallel engine can reproduce");
-            c.random_mask = 0;
+            // the jitter draws from the process-global std::rand() (src/models.cpp:757): reproduced for the reference's
+            // single-threaded order (one draw per such neuron and timestep, cores and neurons in order; csrc/host/poisson.cpp)
+            c.random_mask = static_cast<uint32_t>(mask);
         }
     }
     else if (model == UnitModel::input)
@@ -690,6 +689,7 @@ void HostTables::finalize_view(const Architecture &arch)
     v.device_models = device_model_view.data();
     v.n_device_models = static_cast<uint32_t>(device_model_view.size());
     v.n_device_instances = first;
+    v.n_rand_cols = n_rand_cols;
 }
 
 uint32_t count_input_units(const Architecture &arch)
@@ -1055,6 +1055,8 @@ void lower_network(const Architecture &arch, const SpikingNetwork &net, HostTabl
                 out.neuron_aux[dev] = static_cast<uint32_t>(out.noise.size());
                 out.noise.push_back(d);
             }
+            else if (soma.model == UnitModel::truenorth && ln.cls.random_mask != 0u)
+                out.neuron_aux[dev] = out.n_rand_cols++; // its column in the rand() overlay: device order = the reference's update order
             else if (soma.model == UnitModel::device_model)
             {
                 // one instance per neuron; neuron_aux is made chip-wide once every block is complete (below)
@@ -1517,8 +1519,9 @@ PatchKind patch_neuron_attribute(HostTables &t, const uint32_t neuron, const std
         else if (name == "random_mask")
         {
             if (value < 0.0) throw std::invalid_argument("random_mask < 0; must be unsigned.");
-            if (value != 0.0) return frozen("random_mask != 0 draws from the process-global std::rand() (src/models.cpp:757)");
-            c.random_mask = 0;
+            if ((value != 0.0) != (c.random_mask != 0u))
+                return frozen("switching the threshold jitter on or off changes the chip's rand() stream (one draw per such neuron and step)");
+            c.random_mask = static_cast<uint32_t>(value);
         }
         else return PatchKind::ignored; // e.g. "leak_decay" (a LIF key)
         break;

@@ -56,6 +56,7 @@ struct HostTables
     std::vector<sfe_device_model_block> device_model_view;
     uint32_t input_seed_base{0}; // "input" units created in this process before this chip (set by the chip)
     uint32_t n_poisson_cols{0};
+    uint32_t n_rand_cols{0};     // TrueNorth neurons with random_mask != 0
     sfe_tables view{};
 
     // host-only naming: device index <-> (group, offset); groups in lexicographic order

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "glibc_rand.hpp"
 #include "mt19937.cuh"
 #include "sanafe_b200.h"
 
@@ -118,4 +119,44 @@ extern "C" void sfe_mt19937_draws(uint32_t seed, double *out, size_t n, size_t s
     uint32_t idx = 0;
     sfe::mt_seed(mt.data(), stride, &idx, seed);
     for (size_t k = 0; k < n; ++k) out[k] = sfe::mt_canonical(mt.data(), stride, &idx);
+}
+
+// glibc's rand() / srand() (stdlib/random_r.c, TYPE_3: x^31 + x^3 + 1 additive feedback over 32-bit words, seeded by the
+// Park-Miller LCG, first 310 outputs discarded, result = word >> 1) restated, so that the TrueNorth threshold jitter
+// (`std::rand() & random_mask`, src/models.cpp:757) does not depend on - or disturb - the host process's own generator.
+namespace sfe
+{
+GlibcRand::GlibcRand(const uint32_t seed)
+{
+    int32_t r[34];
+    r[0] = static_cast<int32_t>(seed == 0u ? 1u : seed);
+    for (int i = 1; i < 31; ++i)
+    {
+        // r[i] = (16807 * r[i-1]) % 2147483647 without overflow (Schrage), negative results wrapped
+        const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        r[i] = static_cast<int32_t>(word);
+    }
+    for (int i = 0; i < 31; ++i) state_[i] = static_cast<uint32_t>(r[i]);
+    front_ = 3;
+    rear_ = 0;
+    for (int i = 0; i < 310; ++i) (void) next();
+}
+
+uint32_t GlibcRand::next()
+{
+    state_[front_] += state_[rear_];
+    const uint32_t result = state_[front_] >> 1;
+    front_ = (front_ + 1) % 31;
+    rear_ = (rear_ + 1) % 31;
+    return result;
+}
+} // namespace sfe
+
+extern "C" void sfe_glibc_rand_draws(uint32_t seed, uint64_t skip, uint32_t *out, size_t n)
+{
+    sfe::GlibcRand gen(seed);
+    for (uint64_t k = 0; k < skip; ++k) (void) gen.next();
+    for (size_t k = 0; k < n; ++k) out[k] = gen.next();
 }

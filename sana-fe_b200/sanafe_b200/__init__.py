@@ -110,7 +110,8 @@ class Tables(C.Structure):
                 ("u_probes", C.POINTER(C.c_uint32)), ("neuron_taps", C.POINTER(C.c_uint32)),
                 ("taps", C.POINTER(TapsDesc)), ("taps_values", C.POINTER(C.c_double)),
                 ("n_taps_units", C.c_uint32), ("n_taps_values", C.c_uint32),
-                ("device_models", C.c_void_p), ("n_device_models", C.c_uint32), ("n_device_instances", C.c_uint32)]
+                ("device_models", C.c_void_p), ("n_device_models", C.c_uint32), ("n_device_instances", C.c_uint32),
+                ("n_rand_cols", C.c_uint32), ("pad_rand", C.c_uint32)]
 
 
 class StepRecord(C.Structure):
@@ -178,6 +179,7 @@ def lib():
         "sfe_poisson_create": (vp, [C.POINTER(Tables)]), "sfe_poisson_destroy": (None, [vp]),
         "sfe_poisson_cols": (u32, [vp]), "sfe_poisson_fill": (C.c_int, [vp, vp, i64]),
         "sfe_poisson_reference_draws": (None, [u32, vp, sz]), "sfe_mt19937_draws": (None, [u32, vp, sz, sz]),
+        "sfe_glibc_rand_draws": (None, [u32, u64, vp, sz]), "sfe_engine_set_rand_overlay": (C.c_int, [vp, vp, i64, u32]),
         "sfe_engine_read_log_tail": (i64, [vp, vp, i64]),
         "sfe_nccl_get_unique_id": (C.c_int, [vp, cstr]),
         "sfe_engine_comm_init": (C.c_int, [vp, vp, cstr]),

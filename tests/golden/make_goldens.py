@@ -60,6 +60,8 @@ CASES = {
                                   dendrite_hw_name="loihi_dendrites", seed=3, w_min=-12, w_max=10), steps=60),
     # BASELINE configs[4] soma model
     "truenorth": dict(arch=f"{REF}/arch/truenorth.yaml", net=f"{SRC}/tn_snn.yaml", max_tiles=8, steps=120),
+    # TrueNorth threshold jitter: std::rand() & random_mask (one processing thread: the draws follow the update order)
+    "truenorth_rand": dict(arch=f"{REF}/arch/truenorth.yaml", net=f"{SRC}/tn_rand_snn.yaml", max_tiles=8, steps=200),
     # ordered fp64 accumulation
     "frac": dict(arch=f"{REF}/arch/example_chip.yaml", net=f"{SRC}/frac_snn.yaml", steps=200),
     # Poisson inputs: libstdc++ mt19937 streams seeded by the InputModel construction order

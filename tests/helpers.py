@@ -166,7 +166,7 @@ GOLDEN_CASES = ["example", "dvs", "hh", "synth_small", "synth_delay", "synth_qui
 # Cases added late in round 1 (Poisson inputs, LIF file noise + model-defined traces): pinned on the CPU against
 # the reference here; their device tests live in tests/test_zz_new_models_gpu.py (collected last; green on a
 # B200, profiles/r1_pytest_new_models_gpu.log).
-NEW_GOLDEN_CASES = ["poisson", "noise", "taps", "neurofem"]
+NEW_GOLDEN_CASES = ["poisson", "noise", "taps", "neurofem", "truenorth_rand"]
 ORACLE_ONLY_CASES = []
 _flat_cache = {}
 

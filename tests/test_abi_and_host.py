@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 40
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert sfe.lib().sfe_abi_version() == 6
+    assert sfe.lib().sfe_abi_version() == 7
 
 
 def test_no_cpu_fallback():

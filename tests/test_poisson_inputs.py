@@ -102,3 +102,20 @@ def test_engine_generator_equals_libstdcxx():
             L.sfe_mt19937_draws(seed, got.ctypes.data, got.size, stride)
             assert np.array_equal(want, got), (seed, stride)
             assert 0.0 <= got.min() and got.max() < 1.0
+
+
+def test_glibc_rand_restatement_equals_libc():
+    """The TrueNorth threshold jitter draws `std::rand() & random_mask` (src/models.cpp:757): the product restates
+    glibc's generator (csrc/host/poisson.cpp) instead of touching the process-global one. Checked against libc itself."""
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.rand.restype = ctypes.c_int
+    for seed in (1, 12345):
+        libc.srand(seed)
+        want = np.array([libc.rand() for _ in range(2000)], dtype=np.uint32)
+        got = np.zeros(2000, dtype=np.uint32)
+        sfe.lib().sfe_glibc_rand_draws(seed, 0, got.ctypes.data, got.size)
+        assert np.array_equal(got, want), seed
+    tail = np.zeros(100, dtype=np.uint32)
+    sfe.lib().sfe_glibc_rand_draws(12345, 1900, tail.ctypes.data, tail.size)
+    assert np.array_equal(tail, want[1900:])
