@@ -106,11 +106,16 @@ def check_truenorth(tmp_path, device, runner):
     # RandomizedThresholdAffectsPotential (:130-137): no mask -> plain hard reset
     st, v = tn(tmp_path, device, runner, dict(threshold=5.0, reset_mode="hard", reset=0.0), [10.0])
     assert st[1] == "fired" and v[1] == 0.0
-    # RandomMaskNegativeThrows (:138-143); a positive mask draws from the process-global std::rand() and is refused
+    # RandomMaskNegativeThrows (:168-173)
     with pytest.raises(sfe.SanafeError, match="random_mask < 0"):
         tn(tmp_path, device, runner, dict(threshold=1.0, random_mask=-1), [])
-    with pytest.raises(sfe.SanafeError, match="std::rand"):
-        tn(tmp_path, device, runner, dict(threshold=1.0, random_mask=255), [])
+    # RandomMaskEnablesRandomizedThreshold (:175-186): srand(1), mask 0xFF, no input -> the first rand() value
+    # (1804289383 & 0xFF = 103) lifts the compared potential over the threshold: fired, hard reset to 0
+    st, v = tn(tmp_path, device, runner, dict(threshold=1.0, reset_mode="hard", reset=0.0, random_mask=255), [], steps=1)
+    assert st[0] == "fired" and v[0] == 0.0
+    # (the jitter shifts what is compared, not the potential: with a threshold out of reach nothing accumulates)
+    st, v = tn(tmp_path, device, runner, dict(threshold=1000.0, random_mask=255), [], steps=3)
+    assert st == ["idle", "idle", "idle"] and v == [0.0, 0.0, 0.0]
 
 
 def check_synapse_and_dendrite(tmp_path, device, runner):
