@@ -2012,7 +2012,12 @@ __device__ __forceinline__ void fanout_body(const DevTables &t, const DevState &
     const uint32_t ring = V == kStreamQ4 ? 1u : core.ring;
     const bool fixed_slots = V != kStreamQ4 && core.fixed_slots != 0u;
 
-    if (acc_mode != SFE_ACC_ORDERED)
+    // Ordered mode, shared-memory accumulators, TMA instantiation: the CTA builds the list of active axons like the exact
+    // modes do (it comes out in arrival order: ascending inbox bit), then ONE warp walks the list in order, its segments
+    // prefetched through the warp's TMA ring, and adds in synapse order - the reference's sequential loop without a
+    // dependent global load on its path (the stand-alone loop further down pays two round trips per message).
+    const bool ordered_stream = V == kStreamTma && acc_mode == SFE_ACC_ORDERED && !in_hbm;
+    if (acc_mode != SFE_ACC_ORDERED || ordered_stream)
     {
         // Exact fixed-point accumulation: any order gives the reference's sums bit for
         // bit (load-time certificate). Per round (normally one per core):
@@ -2105,16 +2110,16 @@ __device__ __forceinline__ void fanout_body(const DevTables &t, const DevState &
             __syncthreads();
             wb += accepted;
             stamp(3u + 4u * tl_item);
-            if (!accumulate || static_cast<uint32_t>(warp) >= n_list) continue;
+            if (!accumulate || static_cast<uint32_t>(warp) >= n_list || (ordered_stream && warp != 0)) continue;
 
             // ---- stream the segments: chunk = 128 consecutive synapses of one axon ------
             // Segments are padded to 4 synapses and 16-byte aligned in HBM (engine-side layout).
             ChunkCursor cur;
-            cur.e = warp;
+            cur.e = ordered_stream ? 0u : warp;
             cur.j0 = 0u;
             cur.count = n_list;
-            cur.stride = kFanoutWarps;
-            cur.ent = list[warp];
+            cur.stride = ordered_stream ? 1u : kFanoutWarps;
+            cur.ent = list[cur.e];
             if constexpr (V == kStreamQ4 && kQ4Bulk)
             {
                 // 4-byte records through the TMA engine: lane 0 issues ONE bulk copy per chunk into the warp's ring
@@ -2286,11 +2291,61 @@ __device__ __forceinline__ void fanout_body(const DevTables &t, const DevState &
                         tma_phase ^= 1u << st;
                         const double *ws = reinterpret_cast<const double *>(stage0 + st * kTmaStageBytes);
                         const uint32_t *ms = reinterpret_cast<const uint32_t *>(stage0 + st * kTmaStageBytes + 1024);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
+                        if (ordered_stream)
                         {
-                            const uint32_t j = lane + 32u * u;
-                            if (j < rem_s[st]) accumulate_one(acc32, cnt32, P, ring, fixed_slots, T, core.scale, packed, ws[j], ms[j]);
+                            // synapse order: 32 at a time, lanes that hit the same cell one after the other, lowest first
+#pragma unroll 1
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const uint32_t j = lane + 32u * u;
+                                const bool valid = j < rem_s[st];
+                                double w = 0.0;
+                                uint32_t cell = 0xffffffffu - lane; // distinct dummies for idle lanes
+                                if (valid)
+                                {
+                                    w = ws[j];
+                                    const uint32_t m = ms[j];
+                                    cell = dendrite_slot(ring, fixed_slots, T, m) * P + SFE_SYN_POST(m);
+                                }
+                                // Do two lanes hit the same cell? Every lane tags its cell (the "has a value" word, set to 1
+                                // below either way) and reads the tag back: all lanes see their own tag <=> no duplicate.
+                                // (match.any resolves one distinct value per pass: ~10x the cost of this test, and the synapses
+                                // of one axon almost never share a post-synaptic neuron.)
+                                if (valid) cnt32[cell] = static_cast<uint32_t>(lane) + 2u;
+                                __syncwarp();
+                                const bool lost = valid && cnt32[cell] != static_cast<uint32_t>(lane) + 2u;
+                                if (__ballot_sync(0xffffffffu, lost) == 0u)
+                                {
+                                    if (valid)
+                                    {
+                                        acc64[cell] = acc64[cell] + w;
+                                        cnt32[cell] = 1u;
+                                    }
+                                    __syncwarp();
+                                    continue;
+                                }
+                                const uint32_t peers = __match_any_sync(0xffffffffu, cell);
+                                const int rank = __popc(peers & ((1u << lane) - 1u));
+                                const int rounds = __reduce_max_sync(0xffffffffu, __popc(peers));
+                                for (int r = 0; r < rounds; ++r)
+                                {
+                                    if (valid && rank == r)
+                                    {
+                                        acc64[cell] = acc64[cell] + w;
+                                        cnt32[cell] = 1u;
+                                    }
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const uint32_t j = lane + 32u * u;
+                                if (j < rem_s[st]) accumulate_one(acc32, cnt32, P, ring, fixed_slots, T, core.scale, packed, ws[j], ms[j]);
+                            }
                         }
                         __syncwarp(); // every lane is done with the stage before it is refilled
                         rem_s[st] = issue(st);
