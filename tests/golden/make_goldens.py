@@ -165,6 +165,20 @@ if __name__ == "__main__":
     if "--traces" in sys.argv[1:]:
         make_traces()
         sys.exit(0)
+    if "--bench-sample" in sys.argv[1:]:
+        # 32 cores x 1024 neurons x fan-out 1000 of the benchmark workload through the reference's
+        # own engine (needs ~22 GB of host memory), 40 timesteps, every raster hashed -> bench_sample32.hash.json
+        sys.path.insert(0, ROOT)
+        import bench
+        ref = bench.run_reference_sample(1, 0, cores=32, hash_steps=40, calls=1)
+        with open(os.path.join(HERE, "bench_sample32.hash.json"), "w") as f:
+            json.dump({"what": "BASELINE.md section 3 sample of the benchmark workload: 32 of the 1024 cores x 1024 LIF neurons, "
+                               "fan-out 8 x 125 (32.8 M synapses), generator include/sfe_synth.h with bench.FULL's parameters; the "
+                               "reference's own engine (oracle/_ref/sanafe_ref) run for 40 timesteps, every raster hashed "
+                               "(bench.raster_hash)",
+                       "made_by": "tests/golden/make_goldens.py --bench-sample", "sample_cores": 32,
+                       "spec": bench.sample_spec(32), "hash": ref["hash"]}, f, indent=1)
+        sys.exit(0)
     only = sys.argv[1:]
     for case_name, case_spec in CASES.items():
         if only and case_name not in only:

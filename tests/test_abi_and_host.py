@@ -118,3 +118,22 @@ def test_generated_loihi_large_equals_reference_yaml(tmp_path):
     assert np.array_equal(out_a["potentials"], out_b["potentials"])
     for key in out_a["steps"].dtype.names:
         assert np.array_equal(out_a["steps"][key], out_b["steps"][key]), key
+
+
+def test_benchmark_sample_golden_matches_bench_py():
+    """tests/golden/bench_sample32.hash.json (made by the reference's engine on BASELINE.md section 3's sample) describes
+    the workload bench.py runs today: same generator parameters, and bench.raster_hash is the hash the harness computes."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    with open(os.path.join(GOLDEN, "bench_sample32.hash.json")) as f:
+        g = json.load(f)
+    assert g["spec"] == bench.sample_spec(g["sample_cores"])
+    assert g["hash"]["hash_steps"] == bench.HASH_STEPS and len(g["hash"]["raster_hash"]) == 16
+    # raster_hash on a tiny raster, by hand: timestep 1, neuron 3 and timestep 2, neuron 0
+    bits = np.zeros((2, 1), dtype=np.uint32)
+    bits[0, 0] = 1 << 3
+    bits[1, 0] = 1
+    want = (int(bench.mix64(np.array([(1 << 32) | 3], dtype=np.uint64))[0]) + int(bench.mix64(np.array([2 << 32], dtype=np.uint64))[0])) % (1 << 64)
+    assert bench.raster_hash(bits) == want

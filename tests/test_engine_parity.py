@@ -34,6 +34,34 @@ def test_forced_ordered_mode_matches_reference(monkeypatch):
         check_against_golden(name, chip, rd, out, potential_rtol=0.0, energy_rtol=1e-9)
 
 
+def test_benchmark_shape_matches_the_reference(tmp_path):
+    """The benchmark's own shape (32 of the 1024 cores x 1024 LIF neurons, fan-out 8 x 125, the
+    generator and parameters of bench.py) against the reference's engine: hash over the rasters of 40 timesteps and the
+    counters bit-exact, energy and simulated time to 1e-9. The golden was made by the reference itself
+    (tests/golden/make_goldens.py --bench-sample); bench.py repeats the comparison live on the GPU box."""
+    import json
+    import os
+    import sys
+    from helpers import GOLDEN, ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    from sanafe_b200 import archgen
+    with open(os.path.join(GOLDEN, "bench_sample32.hash.json")) as f:
+        g = json.load(f)
+    h, cores = g["hash"], g["sample_cores"]
+    assert g["spec"] == bench.sample_spec(cores), "bench.py's workload changed: regenerate the golden"
+    flat = str(tmp_path / "arch.jsonl")
+    archgen.write_flat(archgen.loihi_large(tiles=(cores + 3) // 4), flat)
+    arch, _ = sfe.load_flat(flat)
+    chip = sfe.SpikingChip(arch, device=0)
+    chip.load_synthetic(sfe.SynthSpec(**bench.sample_spec(cores)), generate_on_device=True)
+    rd, out = chip.sim_raw(int(h["hash_steps"]), "simple", steps=True, fired=True)
+    assert f"{bench.raster_hash(out['fired_bits']):016x}" == h["raster_hash"]
+    assert (rd.spikes, rd.packets_sent, rd.neurons_updated, rd.neurons_fired) == (
+        h["hash_spikes"], h["hash_packets"], h["hash_updated"], h["hash_fired"])
+    assert rel_err(rd.total_energy, h["hash_energy"]) <= 1e-9 and rel_err(rd.sim_time, h["hash_sim_time"]) <= 1e-9
+
+
 def test_sim_calls_continue_state():
     """sim() twice == sim() once (state and the timestep counter persist, src/chip.cpp:481,553)."""
     a = load_chip("synth_delay", device=0)
