@@ -584,6 +584,15 @@ def dse_side_measurement():
         return {"error": repr(e)[:300]}
 
 
+def dse_points_of_rank(rank, world):
+    """128 design points of the 32 x 32 sweep for every rank: an evenly strided subset of 128 x world points (all 1024 at
+    world = 8), dealt round-robin, so that every rank holds every mapping (neurons per core) at several cost multipliers."""
+    from sanafe_b200 import dse
+    every = dse.sweep_points()
+    sel = every[::max(1, 8 // world)][:128 * world]
+    return sel[rank::world]
+
+
 def dse_partitioned(rank, world, local_rank, dist, steps=200):
     """BASELINE configs[4] at N GPUs: 128 design points of the 32 x 32 sweep per GPU (all 1024 at N = 8), replicas only -
     independent simulations, no exchange. Every rank times its own batch; rank 0 reports the slowest rank's wall time.
@@ -591,9 +600,7 @@ def dse_partitioned(rank, world, local_rank, dist, steps=200):
     mine_out = None
     try:
         from sanafe_b200 import dse
-        every = dse.sweep_points()
-        sel = every[::max(1, 8 // world)][:128 * world]
-        mine = sel[rank::world]
+        mine = dse_points_of_rank(rank, world)
         t0 = time.time()
         sweep = dse.Sweep(mine, tempfile.mkdtemp(prefix=f"dse_{rank}_"), device=local_rank, host_threads=16)
         load_s = time.time() - t0

@@ -102,3 +102,20 @@ def test_sweep_is_dealt_round_robin_to_ranks():
     pts = dse.sweep_points()
     parts = [dse_sweep.points_of_rank(pts, r, 8) for r in range(8)]
     assert sorted(sum(parts, [])) == sorted(pts) and all(len(p) == 128 for p in parts)
+
+
+def test_bench_deals_128_design_points_to_every_gpu():
+    """bench.py at N GPUs: 128 design points per rank, disjoint, all 1024 at N = 8, every mapping on every rank."""
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    every = set(dse.sweep_points())
+    for world in (1, 2, 4, 8):
+        parts = [bench.dse_points_of_rank(r, world) for r in range(world)]
+        assert all(len(p) == 128 for p in parts)
+        flat = [pt for p in parts for pt in p]
+        assert len(set(flat)) == 128 * world and set(flat) <= every
+        for p in parts:
+            assert {pt[0] for pt in p} == {8 * k for k in range(1, 33)}
+    assert set(pt for r in range(8) for pt in bench.dse_points_of_rank(r, 8)) == every
