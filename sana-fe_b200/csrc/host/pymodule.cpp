@@ -26,6 +26,7 @@
 
 #include "handles.hpp"
 #include "sanafe_b200.h"
+#include "sfe_device_model.h"
 
 namespace py = pybind11;
 
@@ -931,6 +932,23 @@ PYBIND11_MODULE(sanafecpp_b200, m)
                 return py::make_tuple(a, n);
             },
             py::arg("path"));
+    // Out-of-tree hardware-unit models (include/sfe_device_model.h): the programmatic side of the reference's plugin
+    // loader (plugin_get_hw, src/plugins.cpp:85-98). A unit's `plugin:` path is loaded by SpikingChip.load() itself.
+    m.def(
+            "load_device_model",
+            [](const std::string &model, const std::string &library_path) {
+                if (sfe_load_device_model(model.c_str(), library_path.c_str()) != 0) raise_last();
+            },
+            py::arg("model"), py::arg("library_path"));
+    m.def(
+            "unregister_device_model",
+            [](const std::string &model) {
+                if (sfe_unregister_device_model(model.c_str()) != 0) raise_last();
+            },
+            py::arg("model"));
+    m.def(
+            "device_model_registered", [](const std::string &model) { return sfe_device_model_registered(model.c_str()) != 0; },
+            py::arg("model"));
     py::class_<Chip, std::shared_ptr<Chip>>(m, "SpikingChip")
             .def(py::init<const std::shared_ptr<ArchHandle> &, int>(), py::arg("arch"), py::arg("device") = 0)
             .def_property_readonly("mapped_neuron_groups", &Chip::mapped_neuron_groups)

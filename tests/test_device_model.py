@@ -125,3 +125,15 @@ def test_out_of_tree_hodgkin_huxley_matches_reference(route, tmp_path):
         assert np.all(np.isfinite(out2["potentials"]))
     finally:
         L.sfe_unregister_device_model(b"hodgkin_huxley")
+
+
+def test_pybind_module_registers_device_models():
+    """The drop-in Python module exposes the programmatic side of the plugin loader."""
+    from sanafe_b200 import sanafecpp_b200 as m
+    assert not m.device_model_registered("hodgkin_huxley")
+    m.load_device_model("hodgkin_huxley", PLUGIN)
+    assert m.device_model_registered("hodgkin_huxley")
+    m.unregister_device_model("hodgkin_huxley")
+    assert not m.device_model_registered("hodgkin_huxley")
+    with pytest.raises(RuntimeError, match="could not load library"):
+        m.load_device_model("hodgkin_huxley", "/nonexistent/lib.so")
