@@ -792,7 +792,10 @@ __device__ __forceinline__ void finalize_body(const DevTables &t, const DevState
 constexpr bool kTimelineAll = SFE_TIMELINE_ALL != 0;
 constexpr size_t kTimelineWords = 64ull * 1024ull * 16ull; // [64 steps][<= 1024 CTAs][16 stamps]; the neuron-phase kernel uses a second block
 constexpr int kSomaThreads = 256;
-constexpr int kSomaPerThread = 2; // neurons per thread: a segment is kSomaThreads * kSomaPerThread neurons
+#ifndef SFE_SOMA_PER_THREAD
+#define SFE_SOMA_PER_THREAD 2
+#endif
+constexpr int kSomaPerThread = SFE_SOMA_PER_THREAD; // neurons per thread: a segment is kSomaThreads * kSomaPerThread neurons
 
 constexpr int kClassCache = 24; // soma parameter classes cached in shared memory (160 B each)
 
