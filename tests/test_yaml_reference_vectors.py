@@ -94,6 +94,32 @@ def test_rejected_architectures(tmp_path, case, text):
     assert str(e.value).strip(), case
 
 
+def test_architecture_metrics_reach_the_lowered_tables(tmp_path):
+    """ParseAxonInAttributes_Valid / ParseAxonOutAttributes_Valid (:23-40, 58-75), DescriptionParseTileMetricsYaml_Valid
+    (:117-147), ParseProcessingUnitAttributesWithPlugin (:93-115): the parsed figures, read back from the tables a chip
+    lowers them to (the reference tests read them from the parser's structs)."""
+    import sanafe_b200 as sfe
+    tile_attrs = ("{energy_north_hop: 1.0, latency_north_hop: 2.0, energy_east_hop: 3.0, latency_east_hop: 4.0, "
+                  "energy_south_hop: 5.0, latency_south_hop: 6.0, energy_west_hop: 7.0, latency_west_hop: 8.0, log_energy: true}")
+    body = CORE_BODY.replace("{energy_message_in: 0.0, latency_message_in: 0.0}", "{energy_message_in: 7.89, latency_message_in: 0.12}")
+    body = body.replace("{energy_message_out: 1.0, latency_message_out: 1.0}", "{energy_message_out: 7.89, latency_message_out: 0.12}")
+    arch = load_arch(tmp_path, arch_text(body=body).replace(TILE_ATTRS, tile_attrs))
+    net, _ = load_net(tmp_path, "network:\n  name: n\n  groups:\n    - name: g\n      neurons: [0]\n  edges: []\nmappings:\n  - g: {core: 0.0}\n", arch)
+    chip = m().SpikingChip(arch, device=-1)
+    chip.load(net)
+    t = sfe.lib().sfe_chip_tables(chip._handle).contents
+    tile, core = t.tiles[0], t.cores[0]
+    assert (tile.energy_north, tile.latency_north, tile.energy_east, tile.latency_east) == (1.0, 2.0, 3.0, 4.0)
+    assert (tile.energy_south, tile.latency_south, tile.energy_west, tile.latency_west) == (5.0, 6.0, 7.0, 8.0)
+    assert (core.energy_axon_in, core.latency_axon_in, core.energy_axon_out, core.latency_axon_out) == (7.89, 0.12, 7.89, 0.12)
+    # a unit that names a plugin library: the path is kept and asked for a device model when a neuron is mapped to the unit
+    plug = arch_text(body=CORE_BODY.replace("{model: leaky_integrate_fire,", '{model: "testmodel", log_energy: true, log_latency: false, plugin: "plugin.so",'))
+    arch2 = load_arch(tmp_path, plug)
+    net2, _ = load_net(tmp_path, "network:\n  name: n\n  groups:\n    - name: g\n      neurons: [0]\n  edges: []\nmappings:\n  - g: {core: 0.0}\n", arch2)
+    with pytest.raises(Exception, match=r"testmodel.*plugin\.so"):
+        m().SpikingChip(arch2, device=-1).load(net2)
+
+
 def test_arch_file_not_open():
     """LoadArchFromFile_FileNotOpen (:561-566)"""
     with pytest.raises(Exception):
@@ -303,3 +329,42 @@ def test_command_line_required_arguments(case, args, needle):
     assert needle in (res.stdout + res.stderr), (case, res.stdout, res.stderr)
     if "Usage" not in needle:
         assert res.returncode != 0, case
+
+
+# ---- more of test_yaml_snn.cpp (restated in round 2) -------------------------------------------------------------
+MORE_REJECTED_NETS = [
+    ("ParseMultipleNetworks (:258-282)", GROUPS.replace("name: example", "name: example[0..2]") + "  edges: []\n" + MAPPINGS),
+    ("ParseNeuronSection_InvalidNeuronId (:478-496)", "network:\n  name: test\n  groups:\n    - name: Input\n      neurons:\n        - 0..1\n"
+                                                      "        - 5: {weight: 1.0}\n  edges: []\nmappings:\n  - Input: {core: 0.0}\n"),
+    ("ParseSparseHyperedge_InvalidPairTypeThrows (:880-903)", GROUPS + "  edges:\n    - Input -> Output:\n        type: sparse\n"
+                                                              "        source_target_pairs: [0]\n" + MAPPINGS),
+]
+
+
+@pytest.mark.parametrize("case,text", MORE_REJECTED_NETS, ids=[c.split(" ")[0] for c, _ in MORE_REJECTED_NETS])
+def test_more_rejected_networks(tmp_path, case, text):
+    with pytest.raises(Exception) as e:
+        load_net(tmp_path, text)
+    assert str(e.value).strip(), case
+
+
+def test_more_accepted_networks(tmp_path):
+    """ParseNeuronGroup_EmptyName (:1026-1042), ParseHyperedgeType_FromSequence (:757-771: the attributes of a hyper-edge as a
+    sequence of one-key maps), ParseNeuronAttributes_HardwareUnits (:425-441) and ParseMappingInfo_AllHardwareUnits
+    (:1044-1079: unit names given with the mapping)."""
+    net, _ = load_net(tmp_path, 'network:\n  name: test\n  groups:\n    - name: ""\n      neurons:\n        - 0\n  edges: []\nmappings: []\n')
+    assert list(net.groups) == [""] and len(net[""]) == 1
+    net, _ = load_net(tmp_path, GROUPS + "  edges:\n    - Input -> Output:\n        - type: dense\n        - weight: [1.0, 2.0, 3.0, 4.0]\n" + MAPPINGS)
+    assert [c.synapse_attributes["weight"] for n in net["Input"] for c in n.edges_out] == [1.0, 2.0, 3.0, 4.0]
+    text = ("network:\n  name: test\n  groups:\n    - name: Input\n      attributes: {synapse_hw_name: syn, dendrite_hw_name: dend, soma_hw_name: soma}\n"
+            "      neurons:\n        - 0\n    - name: Other\n      neurons:\n        - 0\n  edges: []\n"
+            "mappings:\n  - Input.0: {core: 0.0}\n  - Other.0:\n      core: 0.0\n      synapse: syn\n      dendrite: dend\n      soma: soma\n")
+    net, arch = load_net(tmp_path, text)
+    chip = m().SpikingChip(arch, device=-1)
+    chip.load(net)  # the named units exist on the core: both ways of naming them resolve
+    # ... and the names are really used: a unit the core does not have is refused when the neuron is mapped
+    for bad in (text.replace("soma_hw_name: soma}", "soma_hw_name: nope}"), text.replace("      soma: soma\n", "      soma: nope\n")):
+        assert bad != text
+        net, arch = load_net(tmp_path, bad)
+        with pytest.raises(Exception, match="nope"):
+            m().SpikingChip(arch, device=-1).load(net)
