@@ -18,6 +18,7 @@
 #include <sstream>
 
 #include "handles.hpp"
+#include "yaml.hpp"
 
 namespace sfe
 {
@@ -190,7 +191,10 @@ void save_net_yaml(const SpikingNetwork &net, const std::string &path)
             run_start = i;
         }
     }
-    out << "  edges:\n";
+    size_t n_edges = 0;
+    for (const auto &[gname, gptr] : net.groups)
+        for (const Neuron &n : gptr->neurons) n_edges += n.edges_out.size();
+    out << (n_edges == 0 ? "  edges: []\n" : "  edges:\n"); // (an empty block would read back as null, not as a list)
     for (const auto &[gname, gptr] : net.groups)
         for (const Neuron &n : gptr->neurons)
             for (const Connection &con : n.edges_out)
@@ -212,9 +216,51 @@ void save_net_yaml(const SpikingNetwork &net, const std::string &path)
         if (!n->soma_hw_name.empty()) out << ", soma: " << scalar(n->soma_hw_name);
         out << "}}\n";
     }
+    // An existing file keeps its other top-level sections; `network` and `mappings` are replaced
+    // (yaml_write_network / yaml_write_mappings_file re-open the file as a tree, src/yaml_snn.cpp:1058-1110,1477-1555;
+    // a file that does not parse is an error). The kept sections are copied as text, ahead of the two written here.
+    std::string kept;
+    {
+        std::ifstream old(path);
+        if (old.is_open())
+        {
+            std::ostringstream buf;
+            buf << old.rdbuf();
+            const std::string text = buf.str();
+            bool blank = true;
+            for (const char ch : text) blank = blank && (ch == ' ' || ch == '\n' || ch == '\r' || ch == '\t');
+            if (!blank)
+            {
+                yaml::Node doc;
+                try
+                {
+                    doc = yaml::parse(text);
+                }
+                catch (const std::exception &e)
+                {
+                    throw std::runtime_error("Error: existing file is not valid YAML, cannot save network into it (" + path + "): " + e.what());
+                }
+                if (!doc.is_map()) throw std::runtime_error("Error: existing file is not a YAML mapping, cannot save network into it (" + path + ")");
+                // top-level blocks = runs of lines from one column-0 key to the next
+                std::istringstream lines(text);
+                bool keep = false;
+                for (std::string line; std::getline(lines, line);)
+                {
+                    const bool key_line = !line.empty() && line[0] != ' ' && line[0] != '\t' && line[0] != '#' && line[0] != '-' &&
+                            line.find(':') != std::string::npos;
+                    if (key_line)
+                    {
+                        const std::string key = line.substr(0, line.find(':'));
+                        keep = key != "network" && key != "mappings";
+                    }
+                    if (keep) kept += line + "\n";
+                }
+            }
+        }
+    }
     std::ofstream fp(path);
     if (!fp.is_open()) throw std::runtime_error("Failed to open YAML file for writing: " + path);
-    fp << out.str();
+    fp << kept << out.str();
 }
 
 // ---------------------------------------------------------------------------

@@ -368,3 +368,25 @@ def test_more_accepted_networks(tmp_path):
         net, arch = load_net(tmp_path, bad)
         with pytest.raises(Exception, match="nope"):
             m().SpikingChip(arch, device=-1).load(net)
+
+
+def test_save_into_an_existing_file(tmp_path):
+    """WriteNetwork_PreservesOtherSections (:1291-1332), WriteMappings_PreservesNetworkSection (:1334-1372),
+    WriteNetwork_ExistingFileWithInvalidYAML (:1225-1242): saving into an existing file replaces its `network` and `mappings`
+    sections, keeps the others, and refuses a file that is not YAML."""
+    mod = m()
+    arch = load_arch(tmp_path, arch_text())
+    net = mod.Network()  # (the Python class has no name argument, src/pymodule.cpp:1120-1122: an unnamed network is written as " ")
+    g = net.create_neuron_group("TestGroup", 1)
+    g[0].map_to_core(arch.tiles[0].cores[0])
+    path = tmp_path / "preserve.yaml"
+    path.write_text("\ncustom_section:\n  data: should_be_preserved\nnetwork:\n  name: old\n  groups: []\n  edges: []\n")
+    net.save(str(path))
+    text = path.read_text()
+    assert "custom_section" in text and "should_be_preserved" in text and "TestGroup" in text and "name: old" not in text
+    again = mod.load_net(str(path), arch)
+    assert list(again.groups) == ["TestGroup"]
+    bad = tmp_path / "invalid.yaml"
+    bad.write_text("this is not valid: yaml: content\n[[[")
+    with pytest.raises(RuntimeError):
+        net.save(str(bad))
